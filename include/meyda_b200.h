@@ -1,0 +1,223 @@
+/*
+ * meyda_b200.h -- C ABI of the B200-native Meyda frame-feature path.
+ *
+ * This is the drop-in boundary: a Node.js N-API addon (js/addon.cc), the
+ * Python ctypes binding (meyda_b200/_capi.py) and any other FFI bind exactly
+ * these entry points.  Plain pointers and sizes only; nothing throws across
+ * the boundary; every function returns an mb_status and mb_last_error() holds
+ * the message of the calling thread's last failure.
+ *
+ * What each entry point replaces in the reference (kirbysayshi/meyda v1.1.0;
+ * the reference has no FFI of its own, so these are the seams its JavaScript
+ * would call through):
+ *
+ *   mb_plan_create   <- `new Meyda(audioContext, src, bufSize, callback)`
+ *                       src/meyda.js:17-65: power-of-two check (:20-22), bark
+ *                       scale (:44,170-182), hanning/hamming tables (:47-48,
+ *                       116-138), Loudness bark-band limits
+ *                       (src/extractors/loudness.js:24-45), and the mel/DCT
+ *                       tables mfcc rebuilds on every call
+ *                       (src/extractors/mfcc.js:15-83).
+ *   mb_extract       <- the per-buffer pipeline `onaudioprocess`
+ *                       src/meyda.js:69-91 (window :158-168, FFT
+ *                       lib/jsfft/fft.js:123-208, amplitude :104-114) followed
+ *                       by `get([...features])` src/meyda.js:244-261 over
+ *                       the extractor files under src/extractors/, for every frame of every clip.
+ *   mb_query_output  <- the implicit result shapes of src/feature-info.js:3-64.
+ *   mb_stream_*      <- the stateful buffer-by-buffer use of the same
+ *                       pipeline (src/meyda.js:69-91, start/stop :233-241).
+ *
+ * Framing rule (the reference has none: ScriptProcessor hands over back-to-back
+ * buffers, i.e. hop == bufferSize): frame f of a clip covers samples
+ * [f*hop, f*hop + bufferSize); frames = len < bufferSize ? 0 :
+ * (len - bufferSize) / hop + 1; no padding, trailing partial buffer dropped.
+ *
+ * Output layout: struct-of-arrays per feature, frame-major, clips concatenated
+ * in input order.  "number" features are float32[totalFrames] (zcr is
+ * int32[totalFrames]); array features are float32[totalFrames][len].
+ */
+#ifndef MEYDA_B200_H
+#define MEYDA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MB_VERSION 100 /* 0.1.0 */
+
+typedef int mb_status;
+enum {
+    MB_OK = 0,
+    MB_ERR_INVALID_ARG = 1,      /* NULL pointer, negative size, unknown enum */
+    MB_ERR_NOT_POWER_OF_TWO = 2, /* "Buffer size is not a power of two: Meyda will not run." */
+    MB_ERR_UNSUPPORTED = 3,      /* bufferSize outside [MB_MIN_BUFFER_SIZE, MB_MAX_BUFFER_SIZE] */
+    MB_ERR_CUDA = 4,             /* a CUDA runtime call failed; message has the CUDA error */
+    MB_ERR_NO_DEVICE = 5,        /* no CUDA device / device index out of range */
+    MB_ERR_MISSING_OUTPUT = 6,   /* a requested feature's output pointer is NULL */
+    MB_ERR_OUT_OF_RANGE = 7      /* clip offset/length outside the sample array */
+};
+
+#define MB_MIN_BUFFER_SIZE 16
+#define MB_MAX_BUFFER_SIZE 32768
+
+/* Feature bits, in the key order of src/feature-info.js:3-64. */
+enum {
+    MB_FEAT_BUFFER = 0,
+    MB_FEAT_RMS = 1,
+    MB_FEAT_ENERGY = 2,
+    MB_FEAT_ZCR = 3,
+    MB_FEAT_COMPLEX_SPECTRUM = 4,
+    MB_FEAT_AMPLITUDE_SPECTRUM = 5,
+    MB_FEAT_POWER_SPECTRUM = 6,
+    MB_FEAT_SPECTRAL_CENTROID = 7,
+    MB_FEAT_SPECTRAL_FLATNESS = 8,
+    MB_FEAT_SPECTRAL_SLOPE = 9,
+    MB_FEAT_SPECTRAL_ROLLOFF = 10,
+    MB_FEAT_SPECTRAL_SPREAD = 11,
+    MB_FEAT_SPECTRAL_SKEWNESS = 12,
+    MB_FEAT_SPECTRAL_KURTOSIS = 13,
+    MB_FEAT_LOUDNESS = 14,
+    MB_FEAT_PERCEPTUAL_SPREAD = 15,
+    MB_FEAT_PERCEPTUAL_SHARPNESS = 16,
+    MB_FEAT_MFCC = 17,
+    MB_NUM_FEATURES = 18
+};
+#define MB_FEATURE_BIT(f) (1u << (f))
+#define MB_ALL_FEATURES ((1u << MB_NUM_FEATURES) - 1u)
+
+#define MB_NUM_BARK_BANDS 24 /* src/meyda.js:214 */
+#define MB_NUM_MEL_FILTERS 26 /* src/extractors/mfcc.js:15 */
+#define MB_NUM_MFCC 13        /* src/extractors/mfcc.js:71 */
+
+/* `windowingFunction`, src/meyda.js:41, docs.md:5-11 */
+enum { MB_WINDOW_HANNING = 0, MB_WINDOW_HAMMING = 1 };
+
+/* Where the caller's sample and output pointers live. */
+enum { MB_MEM_HOST = 0, MB_MEM_DEVICE = 1 };
+
+/* Plan flags. */
+enum {
+    MB_FLAG_DEFAULT = 0,
+    /* Force the generic block-per-frame kernel even where a tuned one exists
+     * (testing / A-B comparison). */
+    MB_FLAG_GENERIC_KERNEL = 1u << 0
+};
+
+typedef struct mb_plan mb_plan;     /* opaque: tables, stream, scratch of one (device, bufferSize, hop, ...) */
+typedef struct mb_stream mb_stream; /* opaque: stateful buffer-by-buffer extractor */
+
+/* Caller-allocated outputs.  A pointer may be NULL iff its feature is not in
+ * the plan's mask.  Element counts per frame are given by mb_layout. */
+typedef struct mb_outputs {
+    float *buffer;               /* [frames][N]   raw signal (docs.md:19-21) */
+    float *rms;                  /* [frames]      src/extractors/rms.js */
+    float *energy;               /* [frames]      energy.js */
+    int32_t *zcr;                /* [frames]      zcr.js (integer, bit-exact) */
+    float *complex_real;         /* [frames][N]   complexSpectrum.js -> .real */
+    float *complex_imag;         /* [frames][N]                      -> .imag */
+    float *amplitude_spectrum;   /* [frames][N/2] amplitudeSpectrum.js */
+    float *power_spectrum;       /* [frames][N/2] powerSpectrum.js */
+    float *spectral_centroid;    /* [frames]      spectralCentroid.js (bins) */
+    float *spectral_flatness;    /* [frames]      spectralFlatness.js */
+    float *spectral_slope;       /* [frames]      spectralSlope.js */
+    float *spectral_rolloff;     /* [frames]      spectralRolloff.js (Hz) */
+    float *spectral_spread;      /* [frames]      spectralSpread.js */
+    float *spectral_skewness;    /* [frames]      spectralSkewness.js */
+    float *spectral_kurtosis;    /* [frames]      spectralKurtosis.js */
+    float *loudness_specific;    /* [frames][24]  loudness.js -> .specific */
+    float *loudness_total;       /* [frames]                  -> .total */
+    float *perceptual_spread;    /* [frames]      perceptualSpread.js */
+    float *perceptual_sharpness; /* [frames]      perceptualSharpness.js */
+    float *mfcc;                 /* [frames][13]  mfcc.js */
+} mb_outputs;
+
+/* Result shapes for a given clip list (what `get([...])` would have produced). */
+typedef struct mb_layout {
+    int64_t total_frames;
+    int32_t buffer_size;      /* N */
+    int32_t spectrum_size;    /* N/2 */
+    uint32_t feature_mask;
+    int32_t reserved;
+    int64_t output_bytes;     /* sum over requested outputs, all frames */
+    int64_t bytes_per_frame;  /* requested output bytes per frame */
+} mb_layout;
+
+int mb_version(void);
+const char *mb_last_error(void);
+const char *mb_feature_name(int feature);   /* "rms", "spectralCentroid", ...; NULL if out of range */
+int mb_feature_from_name(const char *name); /* -1 if unknown */
+mb_status mb_device_count(int *count);
+
+/* Frames of one clip under the framing rule above. */
+int64_t mb_num_frames(int64_t clip_len, int buffer_size, int hop);
+
+mb_status mb_plan_create(mb_plan **plan, int device, int buffer_size, int hop, double sample_rate,
+                         int window, uint32_t feature_mask, uint32_t flags);
+void mb_plan_destroy(mb_plan *plan);
+
+/* Launch on this CUDA stream (a cudaStream_t) instead of the plan's own;
+ * NULL restores the plan's stream.  Lets a caller time with its own events. */
+mb_status mb_plan_set_stream(mb_plan *plan, void *cuda_stream);
+
+/* Read back plan tables (host copies) for inspection/tests.  Any pointer may
+ * be NULL.  window: N floats; bb_limits: 25 ints; mel_bins: 28 ints. */
+mb_status mb_plan_tables(const mb_plan *plan, float *window, int32_t *bb_limits, int32_t *mel_bins);
+
+mb_status mb_query_output(const mb_plan *plan, int64_t n_clips, const int64_t *clip_len,
+                          int64_t *frames_per_clip /* [n_clips] or NULL */, mb_layout *layout);
+
+/*
+ * Extract every frame of every clip.  clip c is samples[clip_offset[c] ..
+ * clip_offset[c] + clip_len[c]).  clip_offset/clip_len are HOST arrays in
+ * both memory kinds.  Blocking: returns after the results are in `out`.
+ *   MB_MEM_HOST:   samples/out are host pointers (pinned memory from
+ *                  mb_host_alloc makes the copies asynchronous and overlapped).
+ *   MB_MEM_DEVICE: samples/out are device pointers on the plan's device.
+ * n_samples is the length of `samples` in floats (bounds check).
+ */
+mb_status mb_extract(mb_plan *plan, const float *samples, int64_t n_samples, const int64_t *clip_offset,
+                     const int64_t *clip_len, int64_t n_clips, const mb_outputs *out, int mem_kind);
+
+/* Same, MB_MEM_DEVICE only, without the final stream synchronize (the caller
+ * synchronizes or records events on the stream it set). */
+mb_status mb_extract_async(mb_plan *plan, const float *samples, int64_t n_samples, const int64_t *clip_offset,
+                           const int64_t *clip_len, int64_t n_clips, const mb_outputs *out);
+mb_status mb_plan_synchronize(mb_plan *plan);
+
+/* Clip-sharded extraction over several devices from HOST memory: contiguous
+ * clip ranges balanced on frame count, one plan per device (all created with
+ * the same parameters), no inter-GPU traffic.  Results land in `out` exactly
+ * as a single-device call would put them. */
+mb_status mb_extract_multi(mb_plan *const *plans, int n_plans, const float *samples, int64_t n_samples,
+                           const int64_t *clip_offset, const int64_t *clip_len, int64_t n_clips,
+                           const mb_outputs *out);
+
+/* Number of kernel launches issued by this plan so far (bench evidence). */
+int64_t mb_plan_launch_count(const mb_plan *plan);
+/* Name of the kernel variant the plan dispatches to ("generic", "warp2048", ...). */
+const char *mb_plan_kernel_name(const mb_plan *plan);
+
+/* Pinned host memory for samples/outputs of MB_MEM_HOST calls. */
+mb_status mb_host_alloc(void **ptr, size_t bytes);
+void mb_host_free(void *ptr);
+
+/*
+ * Buffer-by-buffer (streaming) use, mirroring onaudioprocess: push any number
+ * of new samples, get back the features of every frame completed by them
+ * (0 or more).  The hop-overlap tail stays on the device between calls.
+ * `out` arrays must have room for mb_stream_frames_after(n_new) frames.
+ */
+mb_status mb_stream_create(mb_stream **stream, mb_plan *plan);
+void mb_stream_destroy(mb_stream *stream);
+int64_t mb_stream_frames_after(const mb_stream *stream, int64_t n_new_samples);
+mb_status mb_stream_push(mb_stream *stream, const float *new_samples, int64_t n_new_samples,
+                         const mb_outputs *out, int mem_kind, int64_t *frames_done);
+mb_status mb_stream_reset(mb_stream *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MEYDA_B200_H */

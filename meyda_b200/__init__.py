@@ -1,0 +1,14 @@
+"""meyda_b200 -- B200-native (sm_100a) implementation of Meyda's per-frame
+feature-extraction hot path behind the reference's extractor API.
+
+  csrc/      CUDA kernels + the C ABI of include/meyda_b200.h
+  _capi.py   ctypes binding of that ABI
+  meyda.py   host-side mirror of the reference interface (Meyda, get, featureInfo, extract)
+  build.py   nvcc build of _lib/libmeyda_b200.so
+"""
+from .meyda import (AudioContext, ExtractResult, FEATURES, Meyda, MeydaError, MeydaNativeError, Plan, Stream,
+                    extract, extract_multi, feature_mask, featureInfo, isPowerOfTwo)
+
+__all__ = ["AudioContext", "ExtractResult", "FEATURES", "Meyda", "MeydaError", "MeydaNativeError", "Plan", "Stream",
+           "extract", "extract_multi", "feature_mask", "featureInfo", "isPowerOfTwo"]
+__version__ = "0.1.0"

@@ -1,0 +1,791 @@
+// capi.cu -- the C ABI of include/meyda_b200.h: plan construction (the tables
+// `new Meyda(...)` precomputes), clip/frame bookkeeping, host<->device staging
+// and kernel dispatch.  No CPU compute fallback exists: every feature value
+// comes out of a CUDA kernel or the call fails.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "mb_kernels.h"
+
+namespace {
+
+thread_local std::string g_last_error;
+
+mb_status fail(mb_status code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+
+#define MB_CUDA(expr)                                                                              \
+    do {                                                                                           \
+        cudaError_t _e = (expr);                                                                   \
+        if (_e != cudaSuccess) return fail(MB_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(_e)); \
+    } while (0)
+
+const char *const kFeatureNames[MB_NUM_FEATURES] = {
+    "buffer", "rms", "energy", "zcr", "complexSpectrum", "amplitudeSpectrum", "powerSpectrum",
+    "spectralCentroid", "spectralFlatness", "spectralSlope", "spectralRolloff", "spectralSpread",
+    "spectralSkewness", "spectralKurtosis", "loudness", "perceptualSpread", "perceptualSharpness", "mfcc"};
+
+// One output array of mb_outputs: which feature owns it and its floats per frame.
+struct OutField {
+    size_t offset;  // byte offset of the pointer inside mb_outputs
+    int feature;
+    int kind;  // 0: 1, 1: N, 2: N/2, 3: 24, 4: 13
+};
+#define MB_FIELD(name, feat, kind) {offsetof(mb_outputs, name), feat, kind}
+const OutField kFields[] = {
+    MB_FIELD(buffer, MB_FEAT_BUFFER, 1),
+    MB_FIELD(rms, MB_FEAT_RMS, 0),
+    MB_FIELD(energy, MB_FEAT_ENERGY, 0),
+    MB_FIELD(zcr, MB_FEAT_ZCR, 0),
+    MB_FIELD(complex_real, MB_FEAT_COMPLEX_SPECTRUM, 1),
+    MB_FIELD(complex_imag, MB_FEAT_COMPLEX_SPECTRUM, 1),
+    MB_FIELD(amplitude_spectrum, MB_FEAT_AMPLITUDE_SPECTRUM, 2),
+    MB_FIELD(power_spectrum, MB_FEAT_POWER_SPECTRUM, 2),
+    MB_FIELD(spectral_centroid, MB_FEAT_SPECTRAL_CENTROID, 0),
+    MB_FIELD(spectral_flatness, MB_FEAT_SPECTRAL_FLATNESS, 0),
+    MB_FIELD(spectral_slope, MB_FEAT_SPECTRAL_SLOPE, 0),
+    MB_FIELD(spectral_rolloff, MB_FEAT_SPECTRAL_ROLLOFF, 0),
+    MB_FIELD(spectral_spread, MB_FEAT_SPECTRAL_SPREAD, 0),
+    MB_FIELD(spectral_skewness, MB_FEAT_SPECTRAL_SKEWNESS, 0),
+    MB_FIELD(spectral_kurtosis, MB_FEAT_SPECTRAL_KURTOSIS, 0),
+    MB_FIELD(loudness_specific, MB_FEAT_LOUDNESS, 3),
+    MB_FIELD(loudness_total, MB_FEAT_LOUDNESS, 0),
+    MB_FIELD(perceptual_spread, MB_FEAT_PERCEPTUAL_SPREAD, 0),
+    MB_FIELD(perceptual_sharpness, MB_FEAT_PERCEPTUAL_SHARPNESS, 0),
+    MB_FIELD(mfcc, MB_FEAT_MFCC, 4),
+};
+constexpr int kNumFields = sizeof(kFields) / sizeof(kFields[0]);
+
+int field_elems(const OutField &f, int N) {
+    switch (f.kind) {
+        case 0: return 1;
+        case 1: return N;
+        case 2: return N / 2;
+        case 3: return MB_NUM_BARK_BANDS;
+        default: return MB_NUM_MFCC;
+    }
+}
+void *&field_ptr(mb_outputs &o, const OutField &f) { return *reinterpret_cast<void **>(reinterpret_cast<char *>(&o) + f.offset); }
+void *field_ptr(const mb_outputs &o, const OutField &f) {
+    return *reinterpret_cast<void *const *>(reinterpret_cast<const char *>(&o) + f.offset);
+}
+
+bool is_power_of_two(int n) { return n > 0 && (n & (n - 1)) == 0; }
+
+struct Slot {  // one pipeline stage of a host-memory extract
+    cudaStream_t stream = nullptr;
+    float *d_samples = nullptr;
+    size_t samples_cap = 0;  // floats
+    char *d_out = nullptr;
+    size_t out_cap = 0;  // bytes
+    int64_t *d_tab = nullptr;
+    int64_t *h_tab = nullptr;  // pinned
+    size_t tab_cap = 0;        // int64 entries
+};
+
+}  // namespace
+
+struct mb_plan {
+    int device = 0, N = 0, hop = 0, window = 0;
+    double sr = 0;
+    uint32_t mask = 0, flags = 0;
+    int num_sms = 0;
+    MbDevPlan dev{};
+    std::vector<float> h_window;
+    float *d_window = nullptr, *d_dct = nullptr, *d_mel_inv = nullptr;
+    float2 *d_twM = nullptr, *d_twN = nullptr;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    // device-memory calls: clip tables staged through pinned memory
+    int64_t *d_tab = nullptr, *h_tab = nullptr;
+    size_t tab_cap = 0;
+    cudaEvent_t tab_event = nullptr;
+    bool tab_event_pending = false;
+    Slot slots[2];
+    int64_t launches = 0;
+    int64_t bytes_per_frame = 0;
+    const char *kernel_name = "generic";
+};
+
+struct mb_stream {
+    mb_plan *plan = nullptr;
+    float *d_buf[2] = {nullptr, nullptr};
+    size_t cap = 0;  // floats per buffer
+    int cur = 0;
+    int64_t filled = 0;
+    int64_t skip = 0;  // samples still to drop before the next frame starts (hop > bufferSize)
+};
+
+namespace {
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        ok = cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+// ---- plan tables (host, double precision, same formulas and evaluation
+// order as the reference so that every discrete table is identical).
+
+void build_window(std::vector<float> &w, int N, int which) {
+    w.resize(N);
+    for (int i = 0; i < N; i++) {
+        if (which == MB_WINDOW_HAMMING)  // src/meyda.js:116-126
+            w[i] = (float)(0.54 - 0.46 * cos(2 * M_PI * ((double)i / N - 1)));
+        else  // src/meyda.js:128-138
+            w[i] = (float)(0.5 - 0.5 * cos(2 * M_PI * i / (N - 1)));
+    }
+}
+
+void build_bark_limits(int *bb, int N, double sr) {
+    // src/meyda.js:170-182 then src/extractors/loudness.js:24-45
+    const int n = N / 2;
+    std::vector<float> bark(N);
+    for (int i = 0; i < N; i++) {
+        const float hz = (float)(i * sr / N);
+        bark[i] = (float)(13 * atan((double)hz / 1315.8) + 3.5 * atan(pow((double)hz / 7518, 2)));
+    }
+    const double last = bark[n - 1];
+    double band_end = last / MB_NUM_BARK_BANDS;
+    int band = 1;
+    for (int i = 0; i <= MB_NUM_BARK_BANDS; i++) bb[i] = 0;
+    for (int i = 0; i < n; i++) {
+        while ((double)bark[i] > band_end) {
+            if (band <= MB_NUM_BARK_BANDS) bb[band] = i;
+            band++;
+            band_end = band * last / MB_NUM_BARK_BANDS;
+        }
+    }
+    bb[MB_NUM_BARK_BANDS] = n - 1;
+}
+
+void build_mel_bins(int *mel, int N, double sr) {
+    // src/extractors/mfcc.js:7-38
+    const double lower = 1125 * log(1 + 0.0 / 700), upper = 1125 * log(1 + (sr / 2) / 700);
+    const double step = (upper - lower) / (MB_NUM_MEL_FILTERS + 1);
+    for (int i = 0; i < MB_NUM_MEL_FILTERS + 2; i++) {
+        const float m = (float)(i * step);
+        const float hz = (float)(700 * (exp((double)m / 1125) - 1));
+        int b = (int)floor((N + 1) * (double)hz / sr);
+        mel[i] = std::min(std::max(b, 0), N / 2);  // sums only run over j < N/2 (mfcc.js:56)
+    }
+}
+
+void build_dct(float *dct) {
+    // src/extractors/mfcc.js:67-83
+    const double k = M_PI / MB_NUM_MEL_FILTERS;
+    const double w1 = 1.0 / sqrt((double)MB_NUM_MEL_FILTERS), w2 = sqrt(2.0 / MB_NUM_MEL_FILTERS);
+    for (int i = 0; i < MB_NUM_MFCC; i++)
+        for (int j = 0; j < MB_NUM_MEL_FILTERS; j++)
+            dct[i + j * MB_NUM_MFCC] = (float)((i == 0 ? w1 : w2) * cos(k * (i + 1) * (j + 0.5)));
+}
+
+template <typename T>
+cudaError_t upload(T **dst, const std::vector<T> &src) {
+    cudaError_t e = cudaMalloc((void **)dst, std::max<size_t>(1, src.size()) * sizeof(T));
+    if (e != cudaSuccess) return e;
+    return cudaMemcpy(*dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice);
+}
+
+void free_slot(Slot &s) {
+    if (s.stream) cudaStreamDestroy(s.stream);
+    cudaFree(s.d_samples);
+    cudaFree(s.d_out);
+    cudaFree(s.d_tab);
+    if (s.h_tab) cudaFreeHost(s.h_tab);
+    s = Slot();
+}
+
+mb_status ensure_table(int64_t **d_tab, int64_t **h_tab, size_t *cap, size_t entries) {
+    if (*cap >= entries) return MB_OK;
+    size_t want = std::max<size_t>(entries, 1024);
+    want += want / 2;
+    cudaFree(*d_tab);
+    if (*h_tab) cudaFreeHost(*h_tab);
+    *d_tab = nullptr;
+    *h_tab = nullptr;
+    *cap = 0;
+    MB_CUDA(cudaMalloc((void **)d_tab, want * sizeof(int64_t)));
+    MB_CUDA(cudaMallocHost((void **)h_tab, want * sizeof(int64_t)));
+    *cap = want;
+    return MB_OK;
+}
+
+mb_status check_outputs(const mb_plan *p, const mb_outputs *out) {
+    if (!out) return fail(MB_ERR_INVALID_ARG, "outputs struct is NULL");
+    for (int i = 0; i < kNumFields; i++)
+        if (mb_has(p->mask, kFields[i].feature) && !field_ptr(*out, kFields[i]))
+            return fail(MB_ERR_MISSING_OUTPUT, "output pointer for requested feature '%s' is NULL",
+                        kFeatureNames[kFields[i].feature]);
+    return MB_OK;
+}
+
+mb_status check_clips(const mb_plan *p, int64_t n_samples, const int64_t *off, const int64_t *len, int64_t n_clips) {
+    if (n_clips < 0 || n_samples < 0) return fail(MB_ERR_INVALID_ARG, "negative clip or sample count");
+    if (n_clips > 0 && (!off || !len)) return fail(MB_ERR_INVALID_ARG, "clip_offset/clip_len is NULL");
+    for (int64_t c = 0; c < n_clips; c++)
+        if (off[c] < 0 || len[c] < 0 || off[c] > n_samples || len[c] > n_samples - off[c])
+            return fail(MB_ERR_OUT_OF_RANGE, "clip %lld [%lld, +%lld) lies outside the %lld samples given",
+                        (long long)c, (long long)off[c], (long long)len[c], (long long)n_samples);
+    (void)p;
+    return MB_OK;
+}
+
+// Launch the plan's kernel over `n` (virtual) clips whose offsets/prefix are
+// already in device memory.
+mb_status launch(mb_plan *p, const int64_t *d_off, const int64_t *d_frame_start, int64_t n, int64_t total_frames,
+                 const float *d_samples, const mb_outputs &d_out, cudaStream_t stream) {
+    if (total_frames == 0) return MB_OK;
+    MbClipTable T{d_off, d_frame_start, n, total_frames};
+    MB_CUDA(mb_launch_generic(p->dev, T, d_samples, d_out, p->num_sms, stream));
+    p->launches++;
+    return MB_OK;
+}
+
+void offset_outputs(mb_outputs &o, const mb_outputs &base, int64_t frame0, int N) {
+    o = base;
+    for (int i = 0; i < kNumFields; i++) {
+        void *b = field_ptr(base, kFields[i]);
+        if (b) field_ptr(o, kFields[i]) = (char *)b + (size_t)frame0 * field_elems(kFields[i], N) * 4;
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int mb_version(void) { return MB_VERSION; }
+const char *mb_last_error(void) { return g_last_error.c_str(); }
+
+const char *mb_feature_name(int feature) {
+    return (feature >= 0 && feature < MB_NUM_FEATURES) ? kFeatureNames[feature] : nullptr;
+}
+
+int mb_feature_from_name(const char *name) {
+    if (!name) return -1;
+    for (int i = 0; i < MB_NUM_FEATURES; i++)
+        if (strcmp(name, kFeatureNames[i]) == 0) return i;
+    return -1;
+}
+
+mb_status mb_device_count(int *count) {
+    if (!count) return fail(MB_ERR_INVALID_ARG, "count is NULL");
+    *count = 0;
+    cudaError_t e = cudaGetDeviceCount(count);
+    if (e != cudaSuccess) {
+        *count = 0;
+        return fail(MB_ERR_NO_DEVICE, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+    }
+    return MB_OK;
+}
+
+int64_t mb_num_frames(int64_t clip_len, int buffer_size, int hop) {
+    if (buffer_size <= 0 || hop <= 0 || clip_len < buffer_size) return 0;
+    return (clip_len - buffer_size) / hop + 1;
+}
+
+mb_status mb_plan_create(mb_plan **plan, int device, int buffer_size, int hop, double sample_rate, int window,
+                         uint32_t feature_mask, uint32_t flags) {
+    if (!plan) return fail(MB_ERR_INVALID_ARG, "plan is NULL");
+    *plan = nullptr;
+    if (!is_power_of_two(buffer_size))  // src/meyda.js:20-22
+        return fail(MB_ERR_NOT_POWER_OF_TWO, "Buffer size is not a power of two: Meyda will not run.");
+    if (buffer_size < MB_MIN_BUFFER_SIZE || buffer_size > MB_MAX_BUFFER_SIZE)
+        return fail(MB_ERR_UNSUPPORTED, "bufferSize %d outside [%d, %d]", buffer_size, MB_MIN_BUFFER_SIZE,
+                    MB_MAX_BUFFER_SIZE);
+    if (hop <= 0) return fail(MB_ERR_INVALID_ARG, "hop must be positive (got %d)", hop);
+    if (!(sample_rate > 0)) return fail(MB_ERR_INVALID_ARG, "sampleRate must be positive");
+    if (window != MB_WINDOW_HANNING && window != MB_WINDOW_HAMMING)
+        return fail(MB_ERR_INVALID_ARG, "unknown windowingFunction %d", window);
+    if (feature_mask == 0 || (feature_mask & ~MB_ALL_FEATURES))
+        return fail(MB_ERR_INVALID_ARG, "feature mask 0x%x is empty or has unknown bits", feature_mask);
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(MB_ERR_NO_DEVICE, "no CUDA device available: the Meyda B200 path has no CPU fallback");
+    }
+    if (device < 0 || device >= ndev) return fail(MB_ERR_NO_DEVICE, "device %d out of range (have %d)", device, ndev);
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(MB_ERR_CUDA, "cudaSetDevice(%d) failed", device);
+
+    mb_plan *p = new mb_plan();
+    p->device = device;
+    p->N = buffer_size;
+    p->hop = hop;
+    p->sr = sample_rate;
+    p->window = window;
+    p->mask = feature_mask;
+    p->flags = flags;
+    const int N = buffer_size, M = N / 2;
+    cudaDeviceProp prop;
+    cudaError_t e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) {
+        delete p;
+        return fail(MB_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+    }
+    p->num_sms = prop.multiProcessorCount;
+
+    MbDevPlan &D = p->dev;
+    D.N = N;
+    D.M = M;
+    D.log2M = 0;
+    while ((1 << D.log2M) < M) D.log2M++;
+    D.hop = hop;
+    D.mask = feature_mask;
+    D.inv_sqrt_N = (float)(1.0 / sqrt((double)N));
+    D.sr = sample_rate;
+    {  // spectralSlope.js:9-16 and spectralRolloff.js:4 constants, accumulated in the reference's order
+        double fs = 0, pfs = 0;
+        for (int i = 0; i < M; i++) {
+            const double f = i * sample_rate / N;
+            pfs += f * f;
+            fs += f;
+        }
+        D.slope_freq_sum = fs;
+        D.slope_pow_freq_sum = pfs;
+        D.rolloff_bin_hz = sample_rate / (2 * (M - 1));
+        double sc = 0;
+        for (int i = 15; i < MB_NUM_BARK_BANDS; i++) sc += 0.066 * exp(0.171 * (i + 1));
+        D.sharp_const = sc;
+    }
+    build_window(p->h_window, N, window);
+    build_bark_limits(D.bb, N, sample_rate);
+    build_mel_bins(D.mel, N, sample_rate);
+    std::vector<float> dct(MB_NUM_MFCC * MB_NUM_MEL_FILTERS), mel_inv(MB_NUM_MEL_FILTERS + 1);
+    build_dct(dct.data());
+    for (int s = 0; s <= MB_NUM_MEL_FILTERS; s++) {
+        const int w = D.mel[s + 1] - D.mel[s];
+        mel_inv[s] = w > 0 ? (float)(1.0 / w) : 0.f;
+    }
+    std::vector<float2> twM(std::max(1, M / 2)), twN(M);
+    for (int j = 0; j < M / 2; j++) twM[j] = make_float2((float)cos(2 * M_PI * j / M), (float)sin(2 * M_PI * j / M));
+    for (int k = 0; k < M; k++) twN[k] = make_float2((float)cos(2 * M_PI * k / N), (float)sin(2 * M_PI * k / N));
+
+    bool ok = upload(&p->d_window, p->h_window) == cudaSuccess && upload(&p->d_dct, dct) == cudaSuccess &&
+              upload(&p->d_mel_inv, mel_inv) == cudaSuccess && upload(&p->d_twM, twM) == cudaSuccess &&
+              upload(&p->d_twN, twN) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&p->own_stream, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaEventCreateWithFlags(&p->tab_event, cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) {
+        mb_status st = fail(MB_ERR_CUDA, "plan table upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+        mb_plan_destroy(p);
+        return st;
+    }
+    p->stream = p->own_stream;
+    D.window = p->d_window;
+    D.dct = p->d_dct;
+    D.mel_inv_width = p->d_mel_inv;
+    D.twM = p->d_twM;
+    D.twN = p->d_twN;
+    p->bytes_per_frame = 0;
+    for (int i = 0; i < kNumFields; i++)
+        if (mb_has(feature_mask, kFields[i].feature)) p->bytes_per_frame += 4 * (int64_t)field_elems(kFields[i], N);
+    *plan = p;
+    return MB_OK;
+}
+
+void mb_plan_destroy(mb_plan *p) {
+    if (!p) return;
+    DeviceGuard guard(p->device);
+    if (p->own_stream) cudaStreamSynchronize(p->own_stream);
+    for (auto &s : p->slots) free_slot(s);
+    cudaFree(p->d_window);
+    cudaFree(p->d_dct);
+    cudaFree(p->d_mel_inv);
+    cudaFree(p->d_twM);
+    cudaFree(p->d_twN);
+    cudaFree(p->d_tab);
+    if (p->h_tab) cudaFreeHost(p->h_tab);
+    if (p->tab_event) cudaEventDestroy(p->tab_event);
+    if (p->own_stream) cudaStreamDestroy(p->own_stream);
+    delete p;
+}
+
+mb_status mb_plan_set_stream(mb_plan *p, void *cuda_stream) {
+    if (!p) return fail(MB_ERR_INVALID_ARG, "plan is NULL");
+    p->stream = cuda_stream ? (cudaStream_t)cuda_stream : p->own_stream;
+    return MB_OK;
+}
+
+mb_status mb_plan_tables(const mb_plan *p, float *window, int32_t *bb_limits, int32_t *mel_bins) {
+    if (!p) return fail(MB_ERR_INVALID_ARG, "plan is NULL");
+    if (window) memcpy(window, p->h_window.data(), sizeof(float) * p->N);
+    if (bb_limits) memcpy(bb_limits, p->dev.bb, sizeof(p->dev.bb));
+    if (mel_bins) memcpy(mel_bins, p->dev.mel, sizeof(p->dev.mel));
+    return MB_OK;
+}
+
+mb_status mb_query_output(const mb_plan *p, int64_t n_clips, const int64_t *clip_len, int64_t *frames_per_clip,
+                          mb_layout *layout) {
+    if (!p) return fail(MB_ERR_INVALID_ARG, "plan is NULL");
+    if (n_clips < 0 || (n_clips > 0 && !clip_len)) return fail(MB_ERR_INVALID_ARG, "bad clip list");
+    int64_t total = 0;
+    for (int64_t c = 0; c < n_clips; c++) {
+        if (clip_len[c] < 0) return fail(MB_ERR_INVALID_ARG, "clip %lld has negative length", (long long)c);
+        const int64_t f = mb_num_frames(clip_len[c], p->N, p->hop);
+        if (frames_per_clip) frames_per_clip[c] = f;
+        total += f;
+    }
+    if (layout) {
+        layout->total_frames = total;
+        layout->buffer_size = p->N;
+        layout->spectrum_size = p->N / 2;
+        layout->feature_mask = p->mask;
+        layout->reserved = 0;
+        layout->bytes_per_frame = p->bytes_per_frame;
+        layout->output_bytes = p->bytes_per_frame * total;
+    }
+    return MB_OK;
+}
+
+mb_status mb_extract_async(mb_plan *p, const float *samples, int64_t n_samples, const int64_t *clip_offset,
+                           const int64_t *clip_len, int64_t n_clips, const mb_outputs *out) {
+    if (!p) return fail(MB_ERR_INVALID_ARG, "plan is NULL");
+    mb_status st = check_outputs(p, out);
+    if (st != MB_OK) return st;
+    st = check_clips(p, n_samples, clip_offset, clip_len, n_clips);
+    if (st != MB_OK) return st;
+    if (n_clips == 0) return MB_OK;
+    if (!samples) return fail(MB_ERR_INVALID_ARG, "samples is NULL");
+    DeviceGuard guard(p->device);
+    const size_t entries = 2 * (size_t)n_clips + 1;
+    if (p->tab_event_pending) {  // the staging buffer may still be in flight from the previous call
+        MB_CUDA(cudaEventSynchronize(p->tab_event));
+        p->tab_event_pending = false;
+    }
+    st = ensure_table(&p->d_tab, &p->h_tab, &p->tab_cap, entries);
+    if (st != MB_OK) return st;
+    int64_t *h_off = p->h_tab, *h_fs = p->h_tab + n_clips;
+    int64_t total = 0;
+    for (int64_t c = 0; c < n_clips; c++) {
+        h_off[c] = clip_offset[c];
+        h_fs[c] = total;
+        total += mb_num_frames(clip_len[c], p->N, p->hop);
+    }
+    h_fs[n_clips] = total;
+    MB_CUDA(cudaMemcpyAsync(p->d_tab, p->h_tab, entries * sizeof(int64_t), cudaMemcpyHostToDevice, p->stream));
+    MB_CUDA(cudaEventRecord(p->tab_event, p->stream));
+    p->tab_event_pending = true;
+    return launch(p, p->d_tab, p->d_tab + n_clips, n_clips, total, samples, *out, p->stream);
+}
+
+mb_status mb_plan_synchronize(mb_plan *p) {
+    if (!p) return fail(MB_ERR_INVALID_ARG, "plan is NULL");
+    DeviceGuard guard(p->device);
+    MB_CUDA(cudaStreamSynchronize(p->stream));
+    return MB_OK;
+}
+
+// Host-memory extract: frames are cut into chunks (possibly inside a clip);
+// each chunk is copied in, processed and copied out on one of two streams so
+// that PCIe traffic in both directions overlaps the kernels.
+static mb_status extract_host(mb_plan *p, const float *samples, const int64_t *clip_offset, const int64_t *clip_len,
+                              int64_t n_clips, const mb_outputs *out) {
+    DeviceGuard guard(p->device);
+    const int N = p->N, hop = p->hop;
+    const int64_t bpf = std::max<int64_t>(p->bytes_per_frame, 4);
+    // chunk budget: ~192 MiB of output or ~64 MiB of fresh input, whichever is hit first
+    const int64_t max_frames_out = std::max<int64_t>(1, (192ll << 20) / bpf);
+    const int64_t max_frames_in = std::max<int64_t>(1, (64ll << 20) / (4ll * hop));
+    const int64_t chunk_frames = std::min(max_frames_out, max_frames_in);
+
+    struct VClip { int64_t off, frames; };
+    std::vector<VClip> v;
+    int64_t c = 0, f_in_clip = 0, g_done = 0;
+    int chunk_idx = 0;
+    mb_status st = MB_OK;
+    while (c < n_clips) {
+        // gather virtual clips for this chunk
+        v.clear();
+        int64_t frames = 0, lo = INT64_MAX, hi = 0;
+        while (c < n_clips && frames < chunk_frames) {
+            const int64_t nf = mb_num_frames(clip_len[c], N, hop);
+            if (f_in_clip >= nf) { c++; f_in_clip = 0; continue; }
+            const int64_t take = std::min(nf - f_in_clip, chunk_frames - frames);
+            const int64_t off = clip_offset[c] + f_in_clip * hop;
+            v.push_back({off, take});
+            lo = std::min(lo, off);
+            hi = std::max(hi, off + (take - 1) * hop + N);
+            frames += take;
+            f_in_clip += take;
+        }
+        if (frames == 0) break;
+        Slot &s = p->slots[chunk_idx & 1];
+        if (!s.stream) MB_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+        // the slot's previous chunk (two chunks ago) must have drained before its buffers are reused
+        MB_CUDA(cudaStreamSynchronize(s.stream));
+        const size_t span = (size_t)(hi - lo);
+        if (s.samples_cap < span) {
+            cudaFree(s.d_samples);
+            s.d_samples = nullptr;
+            s.samples_cap = 0;
+            MB_CUDA(cudaMalloc((void **)&s.d_samples, span * sizeof(float)));
+            s.samples_cap = span;
+        }
+        const size_t out_bytes = (size_t)frames * (size_t)p->bytes_per_frame;
+        if (s.out_cap < out_bytes) {
+            cudaFree(s.d_out);
+            s.d_out = nullptr;
+            s.out_cap = 0;
+            MB_CUDA(cudaMalloc((void **)&s.d_out, out_bytes));
+            s.out_cap = out_bytes;
+        }
+        const size_t entries = 2 * v.size() + 1;
+        st = ensure_table(&s.d_tab, &s.h_tab, &s.tab_cap, entries);
+        if (st != MB_OK) return st;
+        int64_t acc = 0;
+        for (size_t i = 0; i < v.size(); i++) {
+            s.h_tab[i] = v[i].off - lo;
+            s.h_tab[v.size() + i] = acc;
+            acc += v[i].frames;
+        }
+        s.h_tab[2 * v.size()] = acc;
+        MB_CUDA(cudaMemcpyAsync(s.d_tab, s.h_tab, entries * sizeof(int64_t), cudaMemcpyHostToDevice, s.stream));
+        MB_CUDA(cudaMemcpyAsync(s.d_samples, samples + lo, span * sizeof(float), cudaMemcpyHostToDevice, s.stream));
+        // carve the slot's output arena
+        mb_outputs d_out;
+        memset(&d_out, 0, sizeof(d_out));
+        size_t cursor = 0;
+        for (int i = 0; i < kNumFields; i++) {
+            if (!mb_has(p->mask, kFields[i].feature)) continue;
+            field_ptr(d_out, kFields[i]) = s.d_out + cursor;
+            cursor += (size_t)frames * field_elems(kFields[i], N) * 4;
+        }
+        st = launch(p, s.d_tab, s.d_tab + v.size(), (int64_t)v.size(), frames, s.d_samples, d_out, s.stream);
+        if (st != MB_OK) return st;
+        for (int i = 0; i < kNumFields; i++) {
+            if (!mb_has(p->mask, kFields[i].feature)) continue;
+            const size_t per = (size_t)field_elems(kFields[i], N) * 4;
+            MB_CUDA(cudaMemcpyAsync((char *)field_ptr(*out, kFields[i]) + (size_t)g_done * per,
+                                    field_ptr(d_out, kFields[i]), (size_t)frames * per, cudaMemcpyDeviceToHost,
+                                    s.stream));
+        }
+        g_done += frames;
+        chunk_idx++;
+    }
+    for (auto &s : p->slots)
+        if (s.stream) MB_CUDA(cudaStreamSynchronize(s.stream));
+    return MB_OK;
+}
+
+mb_status mb_extract(mb_plan *p, const float *samples, int64_t n_samples, const int64_t *clip_offset,
+                     const int64_t *clip_len, int64_t n_clips, const mb_outputs *out, int mem_kind) {
+    if (!p) return fail(MB_ERR_INVALID_ARG, "plan is NULL");
+    if (mem_kind == MB_MEM_DEVICE) {
+        mb_status st = mb_extract_async(p, samples, n_samples, clip_offset, clip_len, n_clips, out);
+        if (st != MB_OK) return st;
+        return mb_plan_synchronize(p);
+    }
+    if (mem_kind != MB_MEM_HOST) return fail(MB_ERR_INVALID_ARG, "unknown memory kind %d", mem_kind);
+    mb_status st = check_outputs(p, out);
+    if (st != MB_OK) return st;
+    st = check_clips(p, n_samples, clip_offset, clip_len, n_clips);
+    if (st != MB_OK) return st;
+    if (n_clips == 0) return MB_OK;
+    if (!samples) return fail(MB_ERR_INVALID_ARG, "samples is NULL");
+    return extract_host(p, samples, clip_offset, clip_len, n_clips, out);
+}
+
+mb_status mb_extract_multi(mb_plan *const *plans, int n_plans, const float *samples, int64_t n_samples,
+                           const int64_t *clip_offset, const int64_t *clip_len, int64_t n_clips,
+                           const mb_outputs *out) {
+    if (!plans || n_plans <= 0) return fail(MB_ERR_INVALID_ARG, "no plans given");
+    for (int i = 0; i < n_plans; i++) {
+        if (!plans[i]) return fail(MB_ERR_INVALID_ARG, "plan %d is NULL", i);
+        if (plans[i]->N != plans[0]->N || plans[i]->hop != plans[0]->hop || plans[i]->mask != plans[0]->mask ||
+            plans[i]->sr != plans[0]->sr || plans[i]->window != plans[0]->window)
+            return fail(MB_ERR_INVALID_ARG, "plan %d was created with different parameters than plan 0", i);
+    }
+    mb_plan *p0 = plans[0];
+    mb_status st = check_outputs(p0, out);
+    if (st != MB_OK) return st;
+    st = check_clips(p0, n_samples, clip_offset, clip_len, n_clips);
+    if (st != MB_OK) return st;
+    if (n_clips == 0) return MB_OK;
+    // contiguous clip ranges balanced on cumulative frame count
+    std::vector<int64_t> prefix(n_clips + 1, 0);
+    for (int64_t c = 0; c < n_clips; c++) prefix[c + 1] = prefix[c] + mb_num_frames(clip_len[c], p0->N, p0->hop);
+    const int64_t total = prefix[n_clips];
+    std::vector<int64_t> cut(n_plans + 1, n_clips);
+    cut[0] = 0;
+    for (int d = 1; d < n_plans; d++) {
+        const int64_t target = total * d / n_plans;
+        cut[d] = std::lower_bound(prefix.begin(), prefix.end(), target) - prefix.begin();
+        cut[d] = std::min<int64_t>(std::max(cut[d], cut[d - 1]), n_clips);
+    }
+    std::vector<mb_status> status(n_plans, MB_OK);
+    std::vector<std::string> msgs(n_plans);
+    std::vector<std::thread> th;
+    for (int d = 0; d < n_plans; d++) {
+        th.emplace_back([&, d]() {
+            const int64_t c0 = cut[d], c1 = cut[d + 1];
+            if (c1 <= c0) return;
+            mb_outputs o;
+            offset_outputs(o, *out, prefix[c0], p0->N);
+            status[d] = mb_extract(plans[d], samples, n_samples, clip_offset + c0, clip_len + c0, c1 - c0, &o,
+                                   MB_MEM_HOST);
+            if (status[d] != MB_OK) msgs[d] = mb_last_error();
+        });
+    }
+    for (auto &t : th) t.join();
+    for (int d = 0; d < n_plans; d++)
+        if (status[d] != MB_OK) return fail(status[d], "device shard %d: %s", d, msgs[d].c_str());
+    return MB_OK;
+}
+
+int64_t mb_plan_launch_count(const mb_plan *p) { return p ? p->launches : 0; }
+const char *mb_plan_kernel_name(const mb_plan *p) { return p ? p->kernel_name : ""; }
+
+mb_status mb_host_alloc(void **ptr, size_t bytes) {
+    if (!ptr) return fail(MB_ERR_INVALID_ARG, "ptr is NULL");
+    *ptr = nullptr;
+    MB_CUDA(cudaMallocHost(ptr, std::max<size_t>(bytes, 1)));
+    return MB_OK;
+}
+void mb_host_free(void *ptr) {
+    if (ptr) cudaFreeHost(ptr);
+}
+
+// ---- streaming (buffer-by-buffer) use, src/meyda.js:69-91
+
+mb_status mb_stream_create(mb_stream **stream, mb_plan *plan) {
+    if (!stream || !plan) return fail(MB_ERR_INVALID_ARG, "stream/plan is NULL");
+    *stream = new mb_stream();
+    (*stream)->plan = plan;
+    return MB_OK;
+}
+
+void mb_stream_destroy(mb_stream *s) {
+    if (!s) return;
+    DeviceGuard guard(s->plan->device);
+    cudaStreamSynchronize(s->plan->stream);
+    cudaFree(s->d_buf[0]);
+    cudaFree(s->d_buf[1]);
+    delete s;
+}
+
+int64_t mb_stream_frames_after(const mb_stream *s, int64_t n_new) {
+    if (!s || n_new < 0) return 0;
+    const int64_t usable = n_new > s->skip ? n_new - s->skip : 0;
+    return mb_num_frames(s->filled + usable, s->plan->N, s->plan->hop);
+}
+
+mb_status mb_stream_reset(mb_stream *s) {
+    if (!s) return fail(MB_ERR_INVALID_ARG, "stream is NULL");
+    s->filled = 0;
+    s->skip = 0;
+    return MB_OK;
+}
+
+mb_status mb_stream_push(mb_stream *s, const float *new_samples, int64_t n_new, const mb_outputs *out, int mem_kind,
+                         int64_t *frames_done) {
+    if (!s) return fail(MB_ERR_INVALID_ARG, "stream is NULL");
+    if (n_new < 0 || (n_new > 0 && !new_samples)) return fail(MB_ERR_INVALID_ARG, "bad sample block");
+    if (mem_kind != MB_MEM_HOST && mem_kind != MB_MEM_DEVICE) return fail(MB_ERR_INVALID_ARG, "unknown memory kind");
+    mb_plan *p = s->plan;
+    DeviceGuard guard(p->device);
+    if (frames_done) *frames_done = 0;
+    {
+        const int64_t drop = std::min(s->skip, n_new);
+        new_samples += drop;
+        n_new -= drop;
+        s->skip -= drop;
+    }
+    const int64_t need = s->filled + n_new;
+    if ((int64_t)s->cap < need) {
+        size_t cap = (size_t)need + (size_t)need / 2 + p->N;
+        float *nb[2] = {nullptr, nullptr};
+        MB_CUDA(cudaMalloc((void **)&nb[0], cap * sizeof(float)));
+        MB_CUDA(cudaMalloc((void **)&nb[1], cap * sizeof(float)));
+        if (s->filled)
+            MB_CUDA(cudaMemcpyAsync(nb[0], s->d_buf[s->cur], s->filled * sizeof(float), cudaMemcpyDeviceToDevice,
+                                    p->stream));
+        MB_CUDA(cudaStreamSynchronize(p->stream));
+        cudaFree(s->d_buf[0]);
+        cudaFree(s->d_buf[1]);
+        s->d_buf[0] = nb[0];
+        s->d_buf[1] = nb[1];
+        s->cur = 0;
+        s->cap = cap;
+    }
+    float *buf = s->d_buf[s->cur];
+    if (n_new)
+        MB_CUDA(cudaMemcpyAsync(buf + s->filled, new_samples, n_new * sizeof(float),
+                                mem_kind == MB_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice,
+                                p->stream));
+    s->filled = need;
+    const int64_t nf = mb_num_frames(s->filled, p->N, p->hop);
+    if (nf == 0) {
+        MB_CUDA(cudaStreamSynchronize(p->stream));
+        return MB_OK;
+    }
+    mb_status st = check_outputs(p, out);
+    if (st != MB_OK) return st;
+    const int64_t off = 0, len = s->filled;
+    if (mem_kind == MB_MEM_DEVICE) {
+        st = mb_extract_async(p, buf, s->filled, &off, &len, 1, out);
+        if (st != MB_OK) return st;
+    } else {
+        // device-side result arena from slot 0, then one D2H per requested array
+        Slot &sl = p->slots[0];
+        const size_t out_bytes = (size_t)nf * (size_t)p->bytes_per_frame;
+        if (sl.out_cap < out_bytes) {
+            MB_CUDA(cudaStreamSynchronize(p->stream));
+            cudaFree(sl.d_out);
+            sl.d_out = nullptr;
+            sl.out_cap = 0;
+            MB_CUDA(cudaMalloc((void **)&sl.d_out, out_bytes + out_bytes / 2));
+            sl.out_cap = out_bytes + out_bytes / 2;
+        }
+        mb_outputs d_out;
+        memset(&d_out, 0, sizeof(d_out));
+        size_t cursor = 0;
+        for (int i = 0; i < kNumFields; i++) {
+            if (!mb_has(p->mask, kFields[i].feature)) continue;
+            field_ptr(d_out, kFields[i]) = sl.d_out + cursor;
+            cursor += (size_t)nf * field_elems(kFields[i], p->N) * 4;
+        }
+        st = mb_extract_async(p, buf, s->filled, &off, &len, 1, &d_out);
+        if (st != MB_OK) return st;
+        for (int i = 0; i < kNumFields; i++) {
+            if (!mb_has(p->mask, kFields[i].feature)) continue;
+            const size_t bytes = (size_t)nf * field_elems(kFields[i], p->N) * 4;
+            MB_CUDA(cudaMemcpyAsync(field_ptr(*out, kFields[i]), field_ptr(d_out, kFields[i]), bytes,
+                                    cudaMemcpyDeviceToHost, p->stream));
+        }
+    }
+    // keep the hop-overlap tail for the next push
+    const int64_t consumed = nf * p->hop;
+    const int64_t rest = std::max<int64_t>(0, s->filled - consumed);
+    s->skip = std::max<int64_t>(0, consumed - s->filled);
+    if (rest)
+        MB_CUDA(cudaMemcpyAsync(s->d_buf[s->cur ^ 1], buf + consumed, rest * sizeof(float), cudaMemcpyDeviceToDevice,
+                                p->stream));
+    s->cur ^= 1;
+    s->filled = rest;
+    MB_CUDA(cudaStreamSynchronize(p->stream));
+    if (frames_done) *frames_done = nf;
+    return MB_OK;
+}
+
+}  // extern "C"

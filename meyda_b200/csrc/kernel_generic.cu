@@ -1,0 +1,341 @@
+// kernel_generic.cu -- block-per-frame kernel for any power-of-two bufferSize
+// in [16, 32768].  One CTA walks frames (grid-stride); the frame lives in
+// shared memory as N/2 packed complex values, is transformed in place by a
+// decimation-in-frequency FFT with radix-8 fused passes, split into the real
+// spectrum, and every requested Meyda feature is produced in the same pass.
+// Nothing but the requested features is written to HBM.
+//
+// Reference path being replaced: src/meyda.js:69-91,104-114,158-168,
+// lib/jsfft/fft.js:123-208, src/extractors/*.js (see mb_device.cuh for the
+// per-formula citations).
+#include "mb_device.cuh"
+#include "mb_kernels.h"
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+
+// One padding element every 32 and every 1024 entries keeps both the unit-stride
+// butterfly accesses and the bit-reversed gather of the split pass off a
+// single shared-memory bank.
+__device__ __forceinline__ int pidx(int i) { return i + (i >> 5) + (i >> 10); }
+
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+    return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+
+// Q fused radix-2 DIF stages starting at span s: 2^Q points per work item.
+template <int Q>
+__device__ __forceinline__ void fft_pass(float2 *work, const float2 *__restrict__ twM, int M, int log2M, int s,
+                                         int log2s) {
+    constexpr int R = 1 << Q;
+    const int items = M >> Q;
+    const int log2sub = log2s - Q;
+    const int sub = 1 << log2sub;
+    for (int idx = threadIdx.x; idx < items; idx += kThreads) {
+        const int j = idx & (sub - 1);
+        const int b = (idx >> log2sub) << log2s;
+        float2 v[R];
+#pragma unroll
+        for (int t = 0; t < R; t++) v[t] = work[pidx(b + j + t * sub)];
+#pragma unroll
+        for (int q = 0; q < Q; q++) {
+            const int h = R >> (q + 1);
+            const int tw_shift = log2M - (log2s - q);  // M / (s >> q)
+#pragma unroll
+            for (int t = 0; t < R; t++) {
+                if (t & h) continue;
+                const int e = (j + (t & (h - 1)) * sub) << tw_shift;
+                const float2 u = v[t], w = v[t + h];
+                v[t] = make_float2(u.x + w.x, u.y + w.y);
+                v[t + h] = cmul(make_float2(u.x - w.x, u.y - w.y), __ldg(&twM[e]));
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < R; t++) work[pidx(b + j + t * sub)] = v[t];
+    }
+    (void)s;
+}
+
+__device__ __forceinline__ double block_sum(double v, double *scratch /*[kWarps]*/) {
+    v = mb_warp_sum(v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double r = 0;
+#pragma unroll
+    for (int w = 0; w < kWarps; w++) r += scratch[w];
+    return r;
+}
+
+__device__ __forceinline__ int block_sum_int(int v, int *scratch /*[kWarps]*/) {
+    v = mb_warp_sum(v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
+    __syncthreads();
+    int r = 0;
+#pragma unroll
+    for (int w = 0; w < kWarps; w++) r += scratch[w];
+    return r;
+}
+
+__global__ void __launch_bounds__(kThreads)
+mb_generic_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ MbClipTable T,
+                  const float *__restrict__ samples, const __grid_constant__ mb_outputs O) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int N = P.N, M = P.M, log2M = P.log2M;
+    float2 *work = reinterpret_cast<float2 *>(smem_raw);
+    float *amp = reinterpret_cast<float *>(work + pidx(M) + 1);
+
+    __shared__ double red_d[kWarps];
+    __shared__ int red_i[kWarps];
+    __shared__ double scan_d[kWarps];
+    __shared__ double band_sum[MB_NUM_BARK_BANDS];
+    __shared__ float specific[MB_NUM_BARK_BANDS];
+    __shared__ float mel_log[MB_NUM_MEL_FILTERS];
+
+    const uint32_t mask = P.mask;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool want_moments =
+        mask & (MB_FEATURE_BIT(MB_FEAT_SPECTRAL_CENTROID) | MB_FEATURE_BIT(MB_FEAT_SPECTRAL_SPREAD) |
+                MB_FEATURE_BIT(MB_FEAT_SPECTRAL_SKEWNESS) | MB_FEATURE_BIT(MB_FEAT_SPECTRAL_KURTOSIS) |
+                MB_FEATURE_BIT(MB_FEAT_SPECTRAL_FLATNESS) | MB_FEATURE_BIT(MB_FEAT_SPECTRAL_SLOPE));
+    const bool want_time = mask & (MB_FEATURE_BIT(MB_FEAT_RMS) | MB_FEATURE_BIT(MB_FEAT_ENERGY) |
+                                   MB_FEATURE_BIT(MB_FEAT_ZCR) | MB_FEATURE_BIT(MB_FEAT_BUFFER));
+    const bool want_bark = mask & (MB_FEATURE_BIT(MB_FEAT_LOUDNESS) | MB_FEATURE_BIT(MB_FEAT_PERCEPTUAL_SPREAD) |
+                                   MB_FEATURE_BIT(MB_FEAT_PERCEPTUAL_SHARPNESS));
+    const uint32_t time_only = MB_FEATURE_BIT(MB_FEAT_RMS) | MB_FEATURE_BIT(MB_FEAT_ENERGY) |
+                               MB_FEATURE_BIT(MB_FEAT_ZCR) | MB_FEATURE_BIT(MB_FEAT_BUFFER);
+    const bool want_spectrum = (mask & ~time_only) != 0;
+
+    for (int64_t g = blockIdx.x; g < T.total_frames; g += gridDim.x) {
+        const int64_t clip = mb_find_clip(T, g);
+        const float *__restrict__ src = samples + T.clip_off[clip] + (g - T.frame_start[clip]) * (int64_t)P.hop;
+
+        MbFrameSums S;
+        S.s0 = S.s1 = S.s2 = S.s3 = S.s4 = S.log2sum = S.energy = 0;
+        S.zcr = 0;
+        S.rolloff_bin = M;
+
+        // ---- time domain: buffer, energy, zcr; windowed frame into smem as N/2 complex
+        {
+            double e = 0;
+            int z = 0;
+            for (int i = tid; i < M; i += kThreads) {
+                const float x0 = __ldg(src + 2 * i), x1 = __ldg(src + 2 * i + 1);
+                if (want_time) {
+                    e += (double)x0 * (double)x0 + (double)x1 * (double)x1;
+                    z += ((x0 >= 0.f) != (x1 >= 0.f)) && (x0 == x0) && (x1 == x1);
+                    if (2 * i + 2 < N) {
+                        const float x2 = __ldg(src + 2 * i + 2);
+                        z += ((x1 >= 0.f) != (x2 >= 0.f)) && (x1 == x1) && (x2 == x2);
+                    }
+                    if (mb_has(mask, MB_FEAT_BUFFER)) {
+                        O.buffer[g * N + 2 * i] = x0;
+                        O.buffer[g * N + 2 * i + 1] = x1;
+                    }
+                }
+                work[pidx(i)] = make_float2(x0 * __ldg(P.window + 2 * i), x1 * __ldg(P.window + 2 * i + 1));
+            }
+            if (want_time) {
+                S.energy = block_sum(e, red_d);
+                S.zcr = block_sum_int(z, red_i);
+            }
+        }
+        __syncthreads();
+
+        if (want_spectrum) {
+            // ---- in-place DIF FFT, output in bit-reversed positions
+            {
+                int log2s = log2M;
+                while (log2s > 0) {
+                    const int q = log2s >= 3 ? 3 : log2s;
+                    if (q == 3) fft_pass<3>(work, P.twM, M, log2M, 1 << log2s, log2s);
+                    else if (q == 2) fft_pass<2>(work, P.twM, M, log2M, 1 << log2s, log2s);
+                    else fft_pass<1>(work, P.twM, M, log2M, 1 << log2s, log2s);
+                    log2s -= q;
+                    __syncthreads();
+                }
+            }
+
+            // ---- real-FFT split, spectra out, amplitude into smem, moment partials
+            {
+                double s0 = 0, s1 = 0, s2 = 0, s3 = 0, s4 = 0, lg = 0;
+                const float sc = P.inv_sqrt_N;
+                const int rshift = 32 - log2M;
+                for (int k = tid; k < M; k += kThreads) {
+                    const int kk = (M - k) & (M - 1);
+                    const float2 a = work[pidx((int)(__brev((unsigned)k) >> rshift))];
+                    const float2 b = work[pidx((int)(__brev((unsigned)kk) >> rshift))];
+                    const float er = 0.5f * (a.x + b.x), ei = 0.5f * (a.y - b.y);
+                    const float orr = 0.5f * (a.y + b.y), oi = -0.5f * (a.x - b.x);
+                    const float2 w = __ldg(&P.twN[k]);
+                    float zr = (er + (w.x * orr - w.y * oi)) * sc;
+                    float zi = (ei + (w.x * oi + w.y * orr)) * sc;
+                    if (k == 0) zi = 0.f;
+                    if (mb_has(mask, MB_FEAT_COMPLEX_SPECTRUM)) {
+                        float *re = O.complex_real + g * N, *im = O.complex_imag + g * N;
+                        re[k] = zr;
+                        im[k] = zi;
+                        if (k > 0) {
+                            re[N - k] = zr;
+                            im[N - k] = -zi;
+                        } else {
+                            re[M] = (a.x - a.y) * sc;  // Nyquist bin: (E[0] - O[0]) / sqrt(N)
+                            im[M] = 0.f;
+                        }
+                    }
+                    const float av = sqrtf(zr * zr + zi * zi);
+                    amp[k] = av;
+                    if (mb_has(mask, MB_FEAT_AMPLITUDE_SPECTRUM)) O.amplitude_spectrum[g * M + k] = av;
+                    if (mb_has(mask, MB_FEAT_POWER_SPECTRUM)) O.power_spectrum[g * M + k] = av * av;
+                    if (want_moments) {
+                        const double ad = (double)av, kd = (double)k;
+                        double t = ad * kd;
+                        s0 += ad;
+                        s1 += t;
+                        t *= kd; s2 += t;
+                        t *= kd; s3 += t;
+                        t *= kd; s4 += t;
+                        if (mb_has(mask, MB_FEAT_SPECTRAL_FLATNESS)) lg += (double)log2f(av);
+                    }
+                }
+                if (want_moments) {
+                    S.s0 = block_sum(s0, red_d);
+                    S.s1 = block_sum(s1, red_d);
+                    S.s2 = block_sum(s2, red_d);
+                    S.s3 = block_sum(s3, red_d);
+                    S.s4 = block_sum(s4, red_d);
+                    if (mb_has(mask, MB_FEAT_SPECTRAL_FLATNESS)) S.log2sum = block_sum(lg, red_d);
+                }
+            }
+            __syncthreads();
+
+            // ---- rolloff: prefix sums of the amplitude spectrum in double
+            if (mb_has(mask, MB_FEAT_SPECTRAL_ROLLOFF)) {
+                const int chunk = (M + kThreads - 1) / kThreads;
+                const int k0 = min(M, tid * chunk), k1 = min(M, k0 + chunk);
+                double csum = 0;
+                for (int k = k0; k < k1; k++) csum += (double)amp[k];
+                // block exclusive scan of csum
+                double incl = csum;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const double y = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += y;
+                }
+                if (lane == 31) scan_d[warp] = incl;
+                __syncthreads();
+                double base = 0, total = 0;
+#pragma unroll
+                for (int w = 0; w < kWarps; w++) {
+                    if (w < warp) base += scan_d[w];
+                    total += scan_d[w];
+                }
+                const double thr = 0.99 * total;
+                double pre = base + incl - csum;  // sum of amp[0..k0)
+                int cnt = 0;
+                for (int k = k0; k < k1; k++) {
+                    cnt += (pre <= thr);
+                    pre += (double)amp[k];
+                }
+                cnt = block_sum_int(cnt, red_i);
+                // spectralRolloff.js:11-15: the loop only runs while ec > threshold
+                S.rolloff_bin = (total > thr) ? cnt - 1 : M;
+            }
+
+            // ---- bark band sums (loudness.js:55-63), one warp per band
+            if (want_bark) {
+                for (int b = warp; b < MB_NUM_BARK_BANDS; b += kWarps) {
+                    double s = 0;
+                    for (int k = P.bb[b] + lane; k < P.bb[b + 1]; k += 32) s += (double)amp[k];
+                    s = mb_warp_sum(s);
+                    if (lane == 0) band_sum[b] = s;
+                }
+            }
+            // ---- mel filterbank energies (mfcc.js:40-65), one warp per filter
+            if (mb_has(mask, MB_FEAT_MFCC)) {
+                for (int f = warp; f < MB_NUM_MEL_FILTERS; f += kWarps) {
+                    const int e0 = P.mel[f], e1 = P.mel[f + 1], e2 = P.mel[f + 2];
+                    const float up = __ldg(P.mel_inv_width + f), dn = __ldg(P.mel_inv_width + f + 1);
+                    float s = 0.f;
+                    for (int k = e0 + lane; k < e1; k += 32) {
+                        const float a = amp[k];
+                        s += (float)(k - e0) * up * (a * a);
+                    }
+                    for (int k = e1 + lane; k < e2; k += 32) {
+                        const float a = amp[k];
+                        s += (float)(e2 - k) * dn * (a * a);
+                    }
+                    s = mb_warp_sum(s);
+                    if (lane == 0) mel_log[f] = (float)log((double)s);
+                }
+            }
+            __syncthreads();
+
+            if (want_bark) {
+                if (tid < MB_NUM_BARK_BANDS) {
+                    const float sp = (float)pow(band_sum[tid], 0.23);
+                    specific[tid] = sp;
+                    if (mb_has(mask, MB_FEAT_LOUDNESS)) O.loudness_specific[g * MB_NUM_BARK_BANDS + tid] = sp;
+                }
+                __syncthreads();
+                if (tid == 0) {
+                    double total = 0, mx = 0, sharp = 0;
+                    for (int i = 0; i < MB_NUM_BARK_BANDS; i++) {
+                        const double sp = (double)specific[i];
+                        total += sp;
+                        if (sp > mx) mx = sp;
+                        if (i >= 1 && i <= 15) sharp += (double)i * sp;  // (i+1) * spec[i+1], i < 15
+                    }
+                    sharp += P.sharp_const;
+                    if (mb_has(mask, MB_FEAT_LOUDNESS)) O.loudness_total[g] = (float)total;
+                    if (mb_has(mask, MB_FEAT_PERCEPTUAL_SPREAD)) {
+                        const double r = (total - mx) / total;
+                        O.perceptual_spread[g] = (float)(r * r);
+                    }
+                    if (mb_has(mask, MB_FEAT_PERCEPTUAL_SHARPNESS))
+                        O.perceptual_sharpness[g] = (float)(sharp * (0.11 / total));
+                }
+            }
+            if (mb_has(mask, MB_FEAT_MFCC) && tid >= 32 && tid < 32 + MB_NUM_MFCC) {
+                const int c = tid - 32;
+                double v = 0;
+                for (int f = 0; f < MB_NUM_MEL_FILTERS; f++)
+                    v += (double)__ldg(P.dct + c + f * MB_NUM_MFCC) * (double)mel_log[f];
+                O.mfcc[g * MB_NUM_MFCC + c] = (float)(v / (double)MB_NUM_MFCC);
+            }
+        }
+        if (tid == 64) mb_store_scalars(P, O, g, S);
+        __syncthreads();  // smem reused by the next frame
+    }
+}
+
+}  // namespace
+
+size_t mb_generic_smem_bytes(int M) {
+    const int padded = M + (M >> 5) + (M >> 10) + 1;
+    return (size_t)padded * sizeof(float2) + (size_t)M * sizeof(float);
+}
+
+cudaError_t mb_launch_generic(const MbDevPlan &P, const MbClipTable &T, const float *samples, const mb_outputs &O,
+                              int num_sms, cudaStream_t stream) {
+    const size_t smem = mb_generic_smem_bytes(P.M);
+    static thread_local size_t configured[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 64 && configured[dev] < smem) {
+        cudaError_t e = cudaFuncSetAttribute(mb_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured[dev] = smem;
+    }
+    int per_sm = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mb_generic_kernel, kThreads, smem);
+    if (per_sm < 1) per_sm = 1;
+    int64_t grid = (int64_t)num_sms * per_sm;
+    if (grid > T.total_frames) grid = T.total_frames;
+    if (grid < 1) return cudaSuccess;
+    mb_generic_kernel<<<(unsigned)grid, kThreads, smem, stream>>>(P, T, samples, O);
+    return cudaGetLastError();
+}

@@ -1,0 +1,104 @@
+// mb_device.cuh -- device-side plan/clip structures and helpers shared by the
+// kernels of the Meyda frame path (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/meyda_b200.h"
+
+// Per-plan constants handed to kernels by value (__grid_constant__).  Tables
+// are what `new Meyda(...)` precomputes (src/meyda.js:44-48) plus the ones
+// mfcc.js rebuilds per call (src/extractors/mfcc.js:15-83).
+struct MbDevPlan {
+    int N;              // bufferSize
+    int M;              // N/2: complex FFT length == ampSpectrum.length
+    int log2M;
+    int hop;
+    uint32_t mask;      // MB_FEATURE_BIT(...) set
+    float inv_sqrt_N;   // unitary scaling: jsfft multiplies by SQRT1_2 per stage (lib/jsfft/fft.js:158-161)
+    double sr;
+    double slope_freq_sum;      // sum_k f_k         (spectralSlope.js:14)
+    double slope_pow_freq_sum;  // sum_k f_k^2       (spectralSlope.js:13)
+    double rolloff_bin_hz;      // sr / (2 (n-1))    (spectralRolloff.js:4)
+    double sharp_const;         // sum_{i=15..23} 0.066 exp(0.171 (i+1))  (perceptualSharpness.js:10)
+    const float *window;        // [N] hanning or hamming (src/meyda.js:116-138)
+    const float2 *twM;          // [M/2] exp(+2 pi i j / M)
+    const float2 *twN;          // [M]   exp(+2 pi i k / N)
+    const float *dct;           // [13*26] idx = i + j*13 (mfcc.js:72-83)
+    const float *mel_inv_width; // [27] 1 / (mel[s+1] - mel[s]) (0 if empty)
+    int bb[MB_NUM_BARK_BANDS + 1];     // loudness.js:24-45
+    int mel[MB_NUM_MEL_FILTERS + 2];   // mfcc.js:31-38
+};
+
+// Clip list of one extract call (device arrays).
+struct MbClipTable {
+    const int64_t *clip_off;     // [n_clips] first sample of each clip
+    const int64_t *frame_start;  // [n_clips + 1] exclusive prefix of frames per clip
+    int64_t n_clips;
+    int64_t total_frames;
+};
+
+__host__ __device__ __forceinline__ bool mb_has(uint32_t mask, int f) { return (mask >> f) & 1u; }
+
+// Largest c with frame_start[c] <= g (g < total_frames).
+__device__ __forceinline__ int64_t mb_find_clip(const MbClipTable &T, int64_t g) {
+    int64_t lo = 0, hi = T.n_clips;  // invariant: frame_start[lo] <= g < frame_start[hi]
+    while (hi - lo > 1) {
+        int64_t mid = (lo + hi) >> 1;
+        if (T.frame_start[mid] <= g) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+__device__ __forceinline__ double mb_warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float mb_warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ int mb_warp_sum(int v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Scalar features from the per-frame sums; shared by every kernel variant so
+// that the formulas (and their quirks) live in one place.
+struct MbFrameSums {
+    double s0, s1, s2, s3, s4;  // sum_k k^p a[k]            (src/utils.js:1-11)
+    double log2sum;             // sum_k log2 a[k]           (spectralFlatness.js:6)
+    double energy;              // sum x^2 over the raw frame (energy.js, rms.js)
+    int zcr;                    // zcr.js
+    int rolloff_bin;            // (n + 1) of spectralRolloff.js:15
+};
+
+__device__ __forceinline__ void mb_store_scalars(const MbDevPlan &P, const mb_outputs &O, int64_t g,
+                                                 const MbFrameSums &S) {
+    const uint32_t mask = P.mask;
+    const double n = (double)P.M;
+    if (mb_has(mask, MB_FEAT_RMS)) O.rms[g] = (float)sqrt(S.energy / (double)P.N);
+    if (mb_has(mask, MB_FEAT_ENERGY)) O.energy[g] = (float)S.energy;
+    if (mb_has(mask, MB_FEAT_ZCR)) O.zcr[g] = S.zcr;
+    const double m1 = S.s1 / S.s0, m2 = S.s2 / S.s0, m3 = S.s3 / S.s0, m4 = S.s4 / S.s0;
+    if (mb_has(mask, MB_FEAT_SPECTRAL_CENTROID)) O.spectral_centroid[g] = (float)m1;
+    const double var = m2 - m1 * m1;
+    const double sd = sqrt(var);
+    if (mb_has(mask, MB_FEAT_SPECTRAL_SPREAD)) O.spectral_spread[g] = (float)sd;
+    if (mb_has(mask, MB_FEAT_SPECTRAL_SKEWNESS))  // spectralSkewness.js:6-8
+        O.spectral_skewness[g] = (float)((2 * m1 * m1 * m1 - 3 * m1 * m2 + m3) / (sd * sd * sd));
+    if (mb_has(mask, MB_FEAT_SPECTRAL_KURTOSIS))  // spectralKurtosis.js:7-9: 6*m1*m2, not 6*m1^2*m2
+        O.spectral_kurtosis[g] =
+            (float)((-3 * m1 * m1 * m1 * m1 + 6 * m1 * m2 - 4 * m1 * m3 + m4) / (sd * sd * sd * sd));
+    if (mb_has(mask, MB_FEAT_SPECTRAL_FLATNESS))  // (exp(mean ln a) * n) / sum a
+        O.spectral_flatness[g] = (float)(exp(S.log2sum * 0.6931471805599453 / n) * n / S.s0);
+    if (mb_has(mask, MB_FEAT_SPECTRAL_SLOPE)) {   // spectralSlope.js:17; sum f a = (sr/N) s1
+        const double amp_freq_sum = S.s1 * (P.sr / (double)P.N);
+        O.spectral_slope[g] = (float)((n * amp_freq_sum - P.slope_freq_sum * S.s0) /
+                                      (S.s0 * (P.slope_pow_freq_sum - P.slope_freq_sum * P.slope_freq_sum)));
+    }
+    if (mb_has(mask, MB_FEAT_SPECTRAL_ROLLOFF)) O.spectral_rolloff[g] = (float)((double)S.rolloff_bin * P.rolloff_bin_hz);
+}

@@ -1,0 +1,457 @@
+"""Host-side mirror of the reference's extractor API over the CUDA C ABI.
+
+The reference (kirbysayshi/meyda v1.1.0) is JavaScript and no JS toolchain
+exists in this image, so the host layer that would be `js/meyda_b200.js` over
+an N-API addon is mirrored here in Python over ctypes, keeping the reference's
+names, argument meaning and error behaviour:
+
+  Meyda(audioContext, src, bufSize, callback)   src/meyda.js:17
+  meyda.get(feature | [features])               src/meyda.js:244-261
+  meyda.start(features) / stop()                src/meyda.js:233-241
+  meyda.setSource(src)                          src/meyda.js:229-231
+  meyda.windowingFunction = "hanning"|"hamming" src/meyda.js:41, docs.md:5-11
+  meyda.featureInfo                             src/feature-info.js:3-64
+
+plus the batched call the north star adds: extract(clips, bufferSize, hop, ...).
+Every feature value comes from the CUDA kernels; nothing here computes audio
+features on the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import sys
+from typing import Callable, Iterable, Sequence
+
+import numpy as np
+
+from . import _capi
+from ._capi import MeydaNativeError, Outputs, OUTPUT_FIELDS
+
+# src/feature-info.js:3-64 -- lower-case types as in the code (README spells
+# them 'Number'/'Array'; readme.md:84-85).
+featureInfo = {
+    "buffer": {"type": "array"},
+    "rms": {"type": "number"},
+    "energy": {"type": "number"},
+    "zcr": {"type": "number"},
+    "complexSpectrum": {"type": "multipleArrays", "arrayNames": {"1": "real", "2": "imag"}},
+    "amplitudeSpectrum": {"type": "array"},
+    "powerSpectrum": {"type": "array"},
+    "spectralCentroid": {"type": "number"},
+    "spectralFlatness": {"type": "number"},
+    "spectralSlope": {"type": "number"},
+    "spectralRolloff": {"type": "number"},
+    "spectralSpread": {"type": "number"},
+    "spectralSkewness": {"type": "number"},
+    "spectralKurtosis": {"type": "number"},
+    "loudness": {"type": "multipleArrays", "arrayNames": {"1": "total", "2": "specific"}},
+    "perceptualSpread": {"type": "number"},
+    "perceptualSharpness": {"type": "number"},
+    "mfcc": {"type": "array"},
+}
+FEATURES = list(featureInfo)
+_FEATURE_BIT = {name: i for i, name in enumerate(FEATURES)}
+
+
+class MeydaError(Exception):
+    """JS `Error` thrown by the reference (src/meyda.js:20-26,259)."""
+
+
+def isPowerOfTwo(num) -> bool:
+    """src/utils.js:13-19."""
+    try:
+        num = float(num)
+    except (TypeError, ValueError):
+        return False
+    if num != num:
+        return False
+    while num % 2 == 0 and num > 1:
+        num /= 2
+    return num == 1
+
+
+def feature_mask(features: Iterable[str]) -> int:
+    m = 0
+    for f in features:
+        m |= 1 << _FEATURE_BIT[f]
+    return m
+
+
+def _normalize_clips(clips):
+    """-> (flat float32 samples, int64 offsets, int64 lengths)."""
+    if isinstance(clips, dict):
+        data = np.ascontiguousarray(clips["data"], dtype=np.float32)
+        return data, np.ascontiguousarray(clips["offsets"], dtype=np.int64), np.ascontiguousarray(
+            clips["lengths"], dtype=np.int64)
+    if isinstance(clips, np.ndarray) and clips.ndim == 1:
+        clips = [clips]
+    if isinstance(clips, np.ndarray) and clips.ndim == 2:
+        data = np.ascontiguousarray(clips, dtype=np.float32)
+        n, L = data.shape
+        return data.reshape(-1), np.arange(n, dtype=np.int64) * L, np.full(n, L, dtype=np.int64)
+    arrs = [np.ascontiguousarray(c, dtype=np.float32).reshape(-1) for c in clips]
+    lengths = np.array([len(a) for a in arrs], dtype=np.int64)
+    offsets = np.concatenate([[0], np.cumsum(lengths)[:-1]]).astype(np.int64) if len(arrs) else np.zeros(0, np.int64)
+    data = np.concatenate(arrs) if arrs else np.zeros(0, np.float32)
+    return data, offsets, lengths
+
+
+class Plan:
+    """One (device, bufferSize, hop, sampleRate, window, feature set): the
+    tables `new Meyda(...)` precomputes, resident on the GPU."""
+
+    def __init__(self, bufferSize: int, hop: int | None = None, sampleRate: float = 44100.0,
+                 windowingFunction: str = "hanning", features: Sequence[str] = tuple(FEATURES),
+                 device: int = 0, flags: int = 0):
+        if not isPowerOfTwo(bufferSize):
+            raise MeydaError("Buffer size is not a power of two: Meyda will not run.")
+        if windowingFunction not in _capi.MB_WINDOW:
+            raise MeydaError("unknown windowingFunction %r" % (windowingFunction,))
+        self.bufferSize = int(bufferSize)
+        self.hop = int(bufferSize if hop is None else hop)
+        self.sampleRate = float(sampleRate)
+        self.windowingFunction = windowingFunction
+        self.features = list(features)
+        self.device = device
+        self.mask = feature_mask(self.features)
+        self._L = _capi.lib()
+        self._h = C.c_void_p()
+        _capi.check(self._L.mb_plan_create(C.byref(self._h), device, self.bufferSize, self.hop, self.sampleRate,
+                                           _capi.MB_WINDOW[windowingFunction], self.mask, flags))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.mb_plan_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    @property
+    def handle(self):
+        return self._h
+
+    @property
+    def kernel_name(self) -> str:
+        return self._L.mb_plan_kernel_name(self._h).decode()
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._L.mb_plan_launch_count(self._h))
+
+    def set_stream(self, cuda_stream: int | None):
+        _capi.check(self._L.mb_plan_set_stream(self._h, C.c_void_p(cuda_stream or 0)))
+
+    def synchronize(self):
+        _capi.check(self._L.mb_plan_synchronize(self._h))
+
+    def tables(self) -> dict:
+        win = np.zeros(self.bufferSize, np.float32)
+        bb = np.zeros(25, np.int32)
+        mel = np.zeros(28, np.int32)
+        _capi.check(self._L.mb_plan_tables(self._h, win.ctypes.data, bb.ctypes.data, mel.ctypes.data))
+        return {"window": win, "bbLimits": bb, "melBins": mel}
+
+    def query(self, lengths: np.ndarray):
+        lengths = np.ascontiguousarray(lengths, dtype=np.int64)
+        per = np.zeros(len(lengths), np.int64)
+        lay = _capi.Layout()
+        _capi.check(self._L.mb_query_output(self._h, len(lengths), lengths.ctypes.data_as(C.POINTER(C.c_int64)),
+                                            per.ctypes.data_as(C.POINTER(C.c_int64)), C.byref(lay)))
+        return per, lay
+
+    def output_shapes(self, total_frames: int) -> dict:
+        """field name -> (shape, dtype) for the requested features."""
+        shapes = {}
+        for field, feat, per in OUTPUT_FIELDS:
+            if feat in self.features:
+                n = per(self.bufferSize)
+                shapes[field] = ((total_frames,) if n == 1 else (total_frames, n),
+                                 np.int32 if field == "zcr" else np.float32)
+        return shapes
+
+    def alloc_host_outputs(self, total_frames: int) -> dict:
+        return {k: np.zeros(s, dtype=d) for k, (s, d) in self.output_shapes(total_frames).items()}
+
+    @staticmethod
+    def pack_outputs(ptrs: dict) -> Outputs:
+        o = Outputs()
+        for k, v in ptrs.items():
+            setattr(o, k, v)
+        return o
+
+    def extract_host(self, data: np.ndarray, offsets: np.ndarray, lengths: np.ndarray, out: dict | None = None):
+        """MB_MEM_HOST call: numpy in, numpy out (dict field -> array)."""
+        per, lay = self.query(lengths)
+        if out is None:
+            out = self.alloc_host_outputs(int(lay.total_frames))
+        o = self.pack_outputs({k: v.ctypes.data for k, v in out.items()})
+        i64p = C.POINTER(C.c_int64)
+        _capi.check(self._L.mb_extract(self._h, data.ctypes.data, data.size, offsets.ctypes.data_as(i64p),
+                                       lengths.ctypes.data_as(i64p), len(lengths), C.byref(o), _capi.MB_MEM_HOST))
+        return out, per
+
+    def extract_device(self, samples_ptr: int, n_samples: int, offsets: np.ndarray, lengths: np.ndarray,
+                       out_ptrs: dict, sync: bool = True):
+        """MB_MEM_DEVICE call on raw device pointers (e.g. torch tensors' data_ptr())."""
+        o = self.pack_outputs(out_ptrs)
+        i64p = C.POINTER(C.c_int64)
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        lengths = np.ascontiguousarray(lengths, dtype=np.int64)
+        fn = self._L.mb_extract if sync else self._L.mb_extract_async
+        args = [self._h, C.c_void_p(samples_ptr), n_samples, offsets.ctypes.data_as(i64p),
+                lengths.ctypes.data_as(i64p), len(lengths), C.byref(o)]
+        if sync:
+            args.append(_capi.MB_MEM_DEVICE)
+        _capi.check(fn(*args))
+
+
+def extract_multi(plans: Sequence[Plan], data: np.ndarray, offsets: np.ndarray, lengths: np.ndarray,
+                  out: dict | None = None):
+    """Clip-sharded MB_MEM_HOST extraction over several devices (no collectives)."""
+    p0 = plans[0]
+    per, lay = p0.query(lengths)
+    if out is None:
+        out = p0.alloc_host_outputs(int(lay.total_frames))
+    o = Plan.pack_outputs({k: v.ctypes.data for k, v in out.items()})
+    handles = (C.c_void_p * len(plans))(*[p.handle for p in plans])
+    i64p = C.POINTER(C.c_int64)
+    _capi.check(p0._L.mb_extract_multi(handles, len(plans), data.ctypes.data, data.size,
+                                       offsets.ctypes.data_as(i64p), lengths.ctypes.data_as(i64p), len(lengths),
+                                       C.byref(o)))
+    return out, per
+
+
+class ExtractResult:
+    """Per-feature typed arrays for every frame, plus `get`-shaped frame views."""
+
+    def __init__(self, features, arrays: dict, frames_per_clip: np.ndarray, bufferSize: int):
+        self.features = list(features)
+        self.arrays = arrays
+        self.frames_per_clip = frames_per_clip
+        self.clip_frame_start = np.concatenate([[0], np.cumsum(frames_per_clip)]).astype(np.int64)
+        self.total_frames = int(self.clip_frame_start[-1])
+        self.bufferSize = bufferSize
+
+    def __len__(self):
+        return self.total_frames
+
+    def __getitem__(self, feature: str):
+        """Whole-batch arrays of one feature, in the reference's value shape."""
+        a = self.arrays
+        if feature == "complexSpectrum":
+            return {"real": a["complex_real"], "imag": a["complex_imag"]}
+        if feature == "loudness":
+            return {"specific": a["loudness_specific"], "total": a["loudness_total"]}
+        for field, feat, _ in OUTPUT_FIELDS:
+            if feat == feature:
+                return a[field]
+        raise KeyError(feature)
+
+    def value(self, i: int, feature: str):
+        """What `get(feature)` returned for frame i (number | array | object)."""
+        a = self.arrays
+        if feature == "complexSpectrum":
+            return {"real": a["complex_real"][i], "imag": a["complex_imag"][i]}
+        if feature == "loudness":
+            return {"specific": a["loudness_specific"][i], "total": float(a["loudness_total"][i])}
+        v = self[feature][i]
+        if featureInfo[feature]["type"] == "number":
+            return int(v) if feature == "zcr" else float(v)
+        return v
+
+    def frame(self, i: int, features=None) -> dict:
+        """What `get([...features])` returned for frame i."""
+        return {f: self.value(i, f) for f in (self.features if features is None else features)}
+
+    def clip(self, c: int) -> range:
+        return range(int(self.clip_frame_start[c]), int(self.clip_frame_start[c + 1]))
+
+
+def _split_features(features):
+    """List form: unknown names are reported and dropped (src/meyda.js:248-254).
+    String form: unknown name is a TypeError, as calling undefined is in JS."""
+    if isinstance(features, str):
+        if features not in featureInfo:
+            raise TypeError("Cannot read property 'process' of undefined (feature %r)" % (features,))
+        return [features], True
+    if isinstance(features, (list, tuple)):
+        known = []
+        for f in features:
+            if isinstance(f, str) and f in featureInfo:
+                if f not in known:
+                    known.append(f)
+            else:
+                print("TypeError: unknown feature %r" % (f,), file=sys.stderr)  # console.error(e)
+        return known, False
+    raise MeydaError("Invalid Feature Format")
+
+
+def extract(clips, bufferSize: int, hop: int | None = None, sampleRate: float = 44100.0,
+            windowingFunction: str = "hanning", features=tuple(FEATURES),
+            callback: Callable[[dict], None] | None = None, devices: Sequence[int] | None = None,
+            flags: int = 0) -> ExtractResult:
+    """Batched drop-in for "construct Meyda, feed every buffer, get(features)".
+
+    clips: 1-D array, list of 1-D arrays, 2-D [clips, samples] array, or
+    {"data", "offsets", "lengths"}.  If `callback` is given it is invoked once
+    per frame, in order, with the `get([...])`-shaped object (the
+    buffer-by-buffer contract, src/meyda.js:87-89)."""
+    feats, _single = _split_features(features)
+    if not feats:
+        raise MeydaError("Invalid Feature Format")
+    data, offsets, lengths = _normalize_clips(clips)
+    devices = [0] if devices is None else list(devices)
+    plans = [Plan(bufferSize, hop, sampleRate, windowingFunction, feats, device=d, flags=flags) for d in devices]
+    try:
+        if len(plans) == 1:
+            arrays, per = plans[0].extract_host(data, offsets, lengths)
+        else:
+            arrays, per = extract_multi(plans, data, offsets, lengths)
+    finally:
+        for p in plans:
+            p.close()
+    res = ExtractResult(feats, arrays, per, int(bufferSize))
+    if callback is not None:
+        for i in range(res.total_frames):
+            callback(res.frame(i))
+    return res
+
+
+class AudioContext:
+    """Stand-in for the Web Audio context the reference constructor needs:
+    only `.sampleRate` is read (src/meyda.js:29)."""
+
+    def __init__(self, sampleRate: float = 44100.0):
+        self.sampleRate = float(sampleRate)
+
+
+class Meyda:
+    """The reference's class (src/meyda.js:15-263) over the CUDA path.
+
+    `src` is the source signal (1-D float array) instead of a Web Audio node.
+    `process()` plays it through: every complete buffer is framed on the GPU in
+    one batch, then delivered buffer by buffer -- `get()` sees the current
+    buffer, and `callback(get(features))` fires per buffer while started.
+    """
+
+    def __init__(self, audioContext, src, bufSize, callback=None, hop=None, device: int = 0):
+        if not isPowerOfTwo(bufSize):  # src/meyda.js:20-22
+            raise MeydaError("Buffer size is not a power of two: Meyda will not run.")
+        if not audioContext:  # src/meyda.js:24-26
+            raise MeydaError("AudioContext wasn't specified: Meyda will not run.")
+        self.audioContext = audioContext
+        self.bufferSize = int(bufSize)
+        self.hop = int(bufSize if hop is None else hop)
+        self.sampleRate = float(audioContext.sampleRate)
+        self.windowingFunction = "hanning"  # src/meyda.js:41
+        self.featureInfo = featureInfo
+        self.featureExtractors = {name: (lambda n=name: self.get(n)) for name in FEATURES}
+        self.EXTRACTION_STARTED = False
+        self._featuresToExtract = None
+        self._callback = callback
+        self._device = device
+        self._source = None
+        self._result = None
+        self._result_window = None
+        self._cursor = -1
+        self.signal = None
+        self.setSource(src)
+
+    def setSource(self, _src):
+        self._source = None if _src is None else np.ascontiguousarray(_src, dtype=np.float32).reshape(-1)
+        self._result = None
+        self._cursor = -1
+
+    def start(self, features):
+        self._featuresToExtract = features
+        self.EXTRACTION_STARTED = True
+
+    def stop(self):
+        self._featuresToExtract = None
+        self.EXTRACTION_STARTED = False
+
+    def _ensure_result(self):
+        if self._result is None or self._result_window != self.windowingFunction:
+            if self._source is None:
+                raise MeydaError("no source set")
+            self._result = extract(self._source, self.bufferSize, self.hop, self.sampleRate, self.windowingFunction,
+                                   FEATURES, devices=[self._device])
+            self._result_window = self.windowingFunction
+
+    def process(self, max_buffers: int | None = None) -> int:
+        """Deliver the source buffer by buffer (the onaudioprocess loop,
+        src/meyda.js:69-91).  Returns the number of buffers delivered."""
+        self._ensure_result()
+        n = self._result.total_frames
+        done = 0
+        while self._cursor + 1 < n and (max_buffers is None or done < max_buffers):
+            self._cursor += 1
+            self.signal = self._result.arrays["buffer"][self._cursor]
+            if callable(self._callback) and self.EXTRACTION_STARTED:
+                self._callback(self.get(self._featuresToExtract))
+            done += 1
+        return done
+
+    def get(self, feature):
+        """src/meyda.js:244-261."""
+        if isinstance(feature, (list, tuple)):
+            self._require_buffer()
+            results = {}
+            for name in feature:
+                try:
+                    if not isinstance(name, str) or name not in featureInfo:
+                        raise TypeError("Cannot read property 'process' of undefined (feature %r)" % (name,))
+                    results[name] = self._result.value(self._cursor, name)
+                except TypeError as e:
+                    print("%s: %s" % (type(e).__name__, e), file=sys.stderr)  # console.error(e)
+            return results
+        if isinstance(feature, str):
+            if feature not in featureInfo:
+                raise TypeError("Cannot read property 'process' of undefined (feature %r)" % (feature,))
+            self._require_buffer()
+            return self._result.value(self._cursor, feature)
+        raise MeydaError("Invalid Feature Format")
+
+    def _require_buffer(self):
+        self._ensure_result()
+        if self._cursor < 0:
+            if self._result.total_frames == 0:
+                raise MeydaError("source is shorter than one buffer")
+            self._cursor = 0
+            self.signal = self._result.arrays["buffer"][0]
+
+
+class Stream:
+    """Stateful buffer-by-buffer extractor (mb_stream_*): push samples, get the
+    features of every frame they complete."""
+
+    def __init__(self, plan: Plan):
+        self.plan = plan
+        self._L = plan._L
+        self._h = C.c_void_p()
+        _capi.check(self._L.mb_stream_create(C.byref(self._h), plan.handle))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.mb_stream_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def reset(self):
+        _capi.check(self._L.mb_stream_reset(self._h))
+
+    def push(self, samples) -> ExtractResult:
+        x = np.ascontiguousarray(samples, dtype=np.float32).reshape(-1)
+        nf = int(self._L.mb_stream_frames_after(self._h, x.size))
+        out = self.plan.alloc_host_outputs(nf)
+        o = Plan.pack_outputs({k: v.ctypes.data for k, v in out.items()})
+        done = C.c_int64(0)
+        _capi.check(self._L.mb_stream_push(self._h, x.ctypes.data, x.size, C.byref(o), _capi.MB_MEM_HOST,
+                                           C.byref(done)))
+        assert done.value == nf
+        return ExtractResult(self.plan.features, out, np.array([nf], np.int64), self.plan.bufferSize)
+
+
+__all__ = ["Meyda", "AudioContext", "MeydaError", "MeydaNativeError", "featureInfo", "FEATURES", "extract",
+           "extract_multi", "Plan", "Stream", "ExtractResult", "isPowerOfTwo", "feature_mask"]

@@ -1,0 +1,86 @@
+"""No-GPU checks of the C-ABI library: it loads, exports every symbol the
+header declares, and its device-independent entry points behave."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from meyda_b200 import _capi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from meyda_b200.build import build
+    build()
+    return _capi.lib()
+
+
+def _header_functions():
+    src = open(os.path.join(ROOT, "include", "meyda_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(mb_[a-z_0-9]+)\s*\(", src)))
+
+
+def test_exports_every_header_symbol(lib):
+    names = _header_functions()
+    assert len(names) >= 20
+    assert sorted(names) == sorted(_capi.EXPORTS)
+    for n in names:
+        assert hasattr(lib, n), n
+
+
+def test_version_and_feature_names(lib):
+    assert lib.mb_version() == 100
+    from meyda_b200 import FEATURES
+    assert _capi.feature_names() == FEATURES  # key order of src/feature-info.js
+    for i, n in enumerate(FEATURES):
+        assert lib.mb_feature_from_name(n.encode()) == i
+    assert lib.mb_feature_from_name(b"nope") == -1
+    assert lib.mb_feature_name(99) is None
+
+
+def test_num_frames_rule(lib):
+    assert lib.mb_num_frames(166400, 512, 512) == 325
+    assert lib.mb_num_frames(441001, 2048, 2048) == 215
+    assert lib.mb_num_frames(441000, 2048, 512) == 858
+    assert lib.mb_num_frames(1323000, 2048, 512) == 2580
+    assert lib.mb_num_frames(2646000, 32768, 8192) == 319
+    assert lib.mb_num_frames(2047, 2048, 512) == 0
+    assert lib.mb_num_frames(2048, 2048, 512) == 1
+
+
+def test_plan_create_errors_without_device(lib):
+    h = C.c_void_p()
+    st = lib.mb_plan_create(C.byref(h), 0, 600, 600, 44100.0, 0, 1, 0)
+    assert st == _capi.MB_ERR_NOT_POWER_OF_TWO
+    assert lib.mb_last_error().decode() == "Buffer size is not a power of two: Meyda will not run."
+    assert lib.mb_plan_create(C.byref(h), 0, 8, 8, 44100.0, 0, 1, 0) == _capi.MB_ERR_UNSUPPORTED
+    assert lib.mb_plan_create(C.byref(h), 0, 512, 0, 44100.0, 0, 1, 0) == _capi.MB_ERR_INVALID_ARG
+    assert lib.mb_plan_create(C.byref(h), 0, 512, 512, 44100.0, 7, 1, 0) == _capi.MB_ERR_INVALID_ARG
+    assert lib.mb_plan_create(C.byref(h), 0, 512, 512, 44100.0, 0, 0, 0) == _capi.MB_ERR_INVALID_ARG
+    n = C.c_int(-1)
+    lib.mb_device_count(C.byref(n))
+    if n.value == 0:  # no GPU here: the product path must fail loudly, not fall back
+        st = lib.mb_plan_create(C.byref(h), 0, 512, 512, 44100.0, 0, 1, 0)
+        assert st == _capi.MB_ERR_NO_DEVICE and b"no CPU fallback" in lib.mb_last_error()
+        assert not h.value
+
+
+def test_struct_layouts_match_header():
+    assert C.sizeof(_capi.Outputs) == 20 * C.sizeof(C.c_void_p)
+    assert C.sizeof(_capi.Layout) == 8 + 4 + 4 + 4 + 4 + 8 + 8
+    assert [f for f, _, _ in _capi.OUTPUT_FIELDS][:4] == ["buffer", "rms", "energy", "zcr"]
+
+
+def test_product_package_never_imports_oracle():
+    """The product path must not route through oracle/ (or any CPU fallback)."""
+    pkg = os.path.join(ROOT, "meyda_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in txt.replace("oracle/ (or", ""), os.path.join(dirpath, f)
