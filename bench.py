@@ -137,9 +137,9 @@ def run_cpu_oracle(sample_clips: np.ndarray, threads: int):
     n_clips = sample_clips.shape[0]
     t0 = time.perf_counter()
     r = c_oracle.extract(sample_clips.reshape(-1), N, HOP, SR, "hanning", arrays=True, threads=threads,
-                         n_clips=n_clips)
+                         n_clips=n_clips, ring_per_thread=256)
     dt = time.perf_counter() - t0
-    return len(r["rms"]), dt
+    return r["frames_processed"], dt
 
 
 def host_sample_clips(n_clips: int, length: int = CLIP_LEN) -> np.ndarray:
@@ -153,9 +153,12 @@ def cpu_calibrated_sample(threads: int, target_s: float):
     f, dt = run_cpu_oracle(probe, threads)
     rate = f / max(dt, 1e-6)
     want_frames = max(64 * threads, int(rate * target_s))
-    fpc = min(frames_per_clip(), max(64, want_frames // threads))
+    per_thread = max(64, want_frames // threads)
+    clips_per_thread = max(1, -(-per_thread // frames_per_clip()))
+    fpc = min(frames_per_clip(), -(-per_thread // clips_per_thread))
     length = N + HOP * (fpc - 1)
-    return host_sample_clips(threads, length), fpc
+    base = host_sample_clips(threads, length)
+    return np.concatenate([base] * clips_per_thread, axis=0), fpc
 
 
 def reference_arm(args):

@@ -103,8 +103,15 @@ enum {
     MB_FLAG_DEFAULT = 0,
     /* Force the generic block-per-frame kernel even where a tuned one exists
      * (testing / A-B comparison). */
-    MB_FLAG_GENERIC_KERNEL = 1u << 0
+    MB_FLAG_GENERIC_KERNEL = 1u << 0,
+    /* Reproduce the reference FFT's arithmetic exactly (lib/jsfft/fft.js:123-171:
+     * radix-2, float64 butterflies with the recurrence twiddles, float32 store
+     * per stage): complexSpectrum / amplitudeSpectrum / powerSpectrum come out
+     * bit for bit and every derived feature follows.  Slower than the default
+     * float32 FFT; bufferSize <= MB_MAX_EXACT_BUFFER_SIZE. */
+    MB_FLAG_EXACT_FFT = 1u << 1
 };
+#define MB_MAX_EXACT_BUFFER_SIZE 16384
 
 typedef struct mb_plan mb_plan;     /* opaque: tables, stream, scratch of one (device, bufferSize, hop, ...) */
 typedef struct mb_stream mb_stream; /* opaque: stateful buffer-by-buffer extractor */

@@ -15,6 +15,7 @@ MB_ERR_NO_DEVICE, MB_ERR_MISSING_OUTPUT, MB_ERR_OUT_OF_RANGE = 5, 6, 7
 MB_MEM_HOST, MB_MEM_DEVICE = 0, 1
 MB_WINDOW = {"hanning": 0, "hamming": 1}
 MB_FLAG_GENERIC_KERNEL = 1
+MB_FLAG_EXACT_FFT = 2
 MB_NUM_FEATURES = 18
 
 # every symbol include/meyda_b200.h declares

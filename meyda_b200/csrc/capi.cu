@@ -109,6 +109,10 @@ struct mb_plan {
     std::vector<float> h_window;
     float *d_window = nullptr, *d_dct = nullptr, *d_mel_inv = nullptr;
     float2 *d_twM = nullptr, *d_twN = nullptr;
+    double2 *d_tw_exact = nullptr;
+    MbWarpTables *d_warp_tables = nullptr;
+    bool has_warp_kernel = false;
+    int64_t launches_warp = 0, launches_generic = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr;
     // device-memory calls: clip tables staged through pinned memory
     int64_t *d_tab = nullptr, *h_tab = nullptr;
@@ -253,13 +257,61 @@ mb_status check_clips(const mb_plan *p, int64_t n_samples, const int64_t *off, c
 
 // Launch the plan's kernel over `n` (virtual) clips whose offsets/prefix are
 // already in device memory.
+// `aligned`: every frame of this call starts on a 16-byte boundary (TMA bulk copies).
 mb_status launch(mb_plan *p, const int64_t *d_off, const int64_t *d_frame_start, int64_t n, int64_t total_frames,
-                 const float *d_samples, const mb_outputs &d_out, cudaStream_t stream) {
+                 const float *d_samples, const mb_outputs &d_out, cudaStream_t stream, bool aligned) {
     if (total_frames == 0) return MB_OK;
     MbClipTable T{d_off, d_frame_start, n, total_frames};
-    MB_CUDA(mb_launch_generic(p->dev, T, d_samples, d_out, p->num_sms, stream));
+    const bool tma_ok = aligned && ((uintptr_t)d_samples % 16 == 0) && ((uintptr_t)d_out.buffer % 16 == 0) &&
+                        (p->hop % 4 == 0);
+    if (p->has_warp_kernel && tma_ok) {
+        MB_CUDA(mb_launch_warp2048(p->dev, T, d_samples, d_out, p->num_sms, stream));
+        p->launches_warp++;
+    } else {
+        MB_CUDA(mb_launch_generic(p->dev, T, d_samples, d_out, p->num_sms, stream));
+        p->launches_generic++;
+    }
     p->launches++;
     return MB_OK;
+}
+
+bool offsets_aligned(const int64_t *off, int64_t n) {
+    for (int64_t c = 0; c < n; c++)
+        if (off[c] & 3) return false;
+    return true;
+}
+
+// Boundary bookkeeping of the warp kernel: the union of Bark limits and mel edges below M, in order.
+void build_warp_tables(MbWarpTables &W, const MbDevPlan &D) {
+    const int M = D.M;
+    memset(&W, 0, sizeof(W));
+    for (int c = 0; c < 32; c++)
+        for (int b = 0; b < 32; b++) {
+            const double ang = 2 * M_PI * (double)(b * c) / (double)M;
+            W.tw32[c * 32 + b] = make_float2((float)cos(ang), (float)sin(ang));
+        }
+    std::vector<int> edges;
+    for (int i = 0; i <= MB_NUM_BARK_BANDS; i++) edges.push_back(D.bb[i]);
+    for (int i = 0; i < MB_NUM_MEL_FILTERS + 2; i++) edges.push_back(D.mel[i]);
+    std::sort(edges.begin(), edges.end());
+    edges.erase(std::unique(edges.begin(), edges.end()), edges.end());
+    std::vector<int> below;  // boundaries < M
+    for (int e : edges)
+        if (e < M) below.push_back(e);
+    W.n_slots = (int)below.size() + 1;
+    auto slot_of = [&](int e) {
+        if (e >= M) return (int)below.size();
+        return (int)(std::lower_bound(below.begin(), below.end(), e) - below.begin());
+    };
+    for (int i = 0; i <= MB_NUM_BARK_BANDS; i++) W.bark_slot[i] = slot_of(D.bb[i]);
+    for (int i = 0; i < MB_NUM_MEL_FILTERS + 2; i++) W.mel_slot[i] = slot_of(D.mel[i]);
+    for (int lane = 0; lane < 32; lane++) {
+        W.lane_slot_base[lane] = (int)(std::lower_bound(below.begin(), below.end(), 32 * lane) - below.begin());
+        uint32_t m = 0;
+        for (int i = 0; i < 32; i++)
+            if (std::binary_search(below.begin(), below.end(), 32 * lane + i)) m |= 1u << i;
+        W.lane_bmask[lane] = m;
+    }
 }
 
 void offset_outputs(mb_outputs &o, const mb_outputs &base, int64_t frame0, int N) {
@@ -313,6 +365,11 @@ mb_status mb_plan_create(mb_plan **plan, int device, int buffer_size, int hop, d
     if (buffer_size < MB_MIN_BUFFER_SIZE || buffer_size > MB_MAX_BUFFER_SIZE)
         return fail(MB_ERR_UNSUPPORTED, "bufferSize %d outside [%d, %d]", buffer_size, MB_MIN_BUFFER_SIZE,
                     MB_MAX_BUFFER_SIZE);
+    if ((flags & MB_FLAG_EXACT_FFT) && buffer_size > MB_MAX_EXACT_BUFFER_SIZE)
+        return fail(MB_ERR_UNSUPPORTED, "exact-FFT mode supports bufferSize <= %d (got %d)", MB_MAX_EXACT_BUFFER_SIZE,
+                    buffer_size);
+    if (flags & ~(uint32_t)(MB_FLAG_GENERIC_KERNEL | MB_FLAG_EXACT_FFT))
+        return fail(MB_ERR_INVALID_ARG, "unknown plan flags 0x%x", flags);
     if (hop <= 0) return fail(MB_ERR_INVALID_ARG, "hop must be positive (got %d)", hop);
     if (!(sample_rate > 0)) return fail(MB_ERR_INVALID_ARG, "sampleRate must be positive");
     if (window != MB_WINDOW_HANNING && window != MB_WINDOW_HAMMING)
@@ -381,7 +438,22 @@ mb_status mb_plan_create(mb_plan **plan, int device, int buffer_size, int hop, d
     for (int j = 0; j < M / 2; j++) twM[j] = make_float2((float)cos(2 * M_PI * j / M), (float)sin(2 * M_PI * j / M));
     for (int k = 0; k < M; k++) twN[k] = make_float2((float)cos(2 * M_PI * k / N), (float)sin(2 * M_PI * k / N));
 
-    bool ok = upload(&p->d_window, p->h_window) == cudaSuccess && upload(&p->d_dct, dct) == cudaSuccess &&
+    std::vector<double2> tw_exact;
+    if (flags & MB_FLAG_EXACT_FFT) {
+        // lib/jsfft/fft.js:143-164: per stage del = (cos, sin)(PI / width); f <- f * del, in doubles
+        tw_exact.resize(N - 1);
+        for (int width = 1; width < N; width <<= 1) {
+            const double del_r = cos(M_PI / width), del_i = sin(M_PI / width);
+            double f_r = 1, f_i = 0;
+            for (int j = 0; j < width; j++) {
+                tw_exact[width - 1 + j] = make_double2(f_r, f_i);
+                const double temp = f_r * del_r - f_i * del_i;
+                f_i = f_r * del_i + f_i * del_r;
+                f_r = temp;
+            }
+        }
+    }
+    bool ok = upload(&p->d_tw_exact, tw_exact) == cudaSuccess && upload(&p->d_window, p->h_window) == cudaSuccess && upload(&p->d_dct, dct) == cudaSuccess &&
               upload(&p->d_mel_inv, mel_inv) == cudaSuccess && upload(&p->d_twM, twM) == cudaSuccess &&
               upload(&p->d_twN, twN) == cudaSuccess &&
               cudaStreamCreateWithFlags(&p->own_stream, cudaStreamNonBlocking) == cudaSuccess &&
@@ -397,6 +469,31 @@ mb_status mb_plan_create(mb_plan **plan, int device, int buffer_size, int hop, d
     D.mel_inv_width = p->d_mel_inv;
     D.twM = p->d_twM;
     D.twN = p->d_twN;
+    D.tw_exact = p->d_tw_exact;
+    D.exact = (flags & MB_FLAG_EXACT_FFT) ? 1 : 0;
+    if (D.exact) p->kernel_name = "generic-exact";
+    D.warp_tables = nullptr;
+    if (N == 2048 && !D.exact && !(flags & MB_FLAG_GENERIC_KERNEL)) {
+        MbWarpTables *W = new MbWarpTables();
+        build_warp_tables(*W, D);
+        const bool fits = W->n_slots <= MB_WARP_MAX_SLOTS && (size_t)prop.sharedMemPerBlockOptin >= mb_warp2048_smem_bytes();
+        cudaError_t we = cudaSuccess;
+        if (fits) {
+            we = cudaMalloc((void **)&p->d_warp_tables, sizeof(MbWarpTables));
+            if (we == cudaSuccess) we = cudaMemcpy(p->d_warp_tables, W, sizeof(MbWarpTables), cudaMemcpyHostToDevice);
+        }
+        delete W;
+        if (we != cudaSuccess) {
+            mb_status st = fail(MB_ERR_CUDA, "warp-kernel table upload failed: %s", cudaGetErrorString(we));
+            mb_plan_destroy(p);
+            return st;
+        }
+        if (fits) {
+            D.warp_tables = p->d_warp_tables;
+            p->has_warp_kernel = true;
+            p->kernel_name = "warp2048";
+        }
+    }
     p->bytes_per_frame = 0;
     for (int i = 0; i < kNumFields; i++)
         if (mb_has(feature_mask, kFields[i].feature)) p->bytes_per_frame += 4 * (int64_t)field_elems(kFields[i], N);
@@ -414,6 +511,8 @@ void mb_plan_destroy(mb_plan *p) {
     cudaFree(p->d_mel_inv);
     cudaFree(p->d_twM);
     cudaFree(p->d_twN);
+    cudaFree(p->d_tw_exact);
+    cudaFree(p->d_warp_tables);
     cudaFree(p->d_tab);
     if (p->h_tab) cudaFreeHost(p->h_tab);
     if (p->tab_event) cudaEventDestroy(p->tab_event);
@@ -486,7 +585,8 @@ mb_status mb_extract_async(mb_plan *p, const float *samples, int64_t n_samples, 
     MB_CUDA(cudaMemcpyAsync(p->d_tab, p->h_tab, entries * sizeof(int64_t), cudaMemcpyHostToDevice, p->stream));
     MB_CUDA(cudaEventRecord(p->tab_event, p->stream));
     p->tab_event_pending = true;
-    return launch(p, p->d_tab, p->d_tab + n_clips, n_clips, total, samples, *out, p->stream);
+    return launch(p, p->d_tab, p->d_tab + n_clips, n_clips, total, samples, *out, p->stream,
+                  offsets_aligned(clip_offset, n_clips));
 }
 
 mb_status mb_plan_synchronize(mb_plan *p) {
@@ -530,6 +630,7 @@ static mb_status extract_host(mb_plan *p, const float *samples, const int64_t *c
             f_in_clip += take;
         }
         if (frames == 0) break;
+        lo &= ~(int64_t)3;  // keep the device copy's 16-byte phase equal to the host array's
         Slot &s = p->slots[chunk_idx & 1];
         if (!s.stream) MB_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
         // the slot's previous chunk (two chunks ago) must have drained before its buffers are reused
@@ -571,7 +672,8 @@ static mb_status extract_host(mb_plan *p, const float *samples, const int64_t *c
             field_ptr(d_out, kFields[i]) = s.d_out + cursor;
             cursor += (size_t)frames * field_elems(kFields[i], N) * 4;
         }
-        st = launch(p, s.d_tab, s.d_tab + v.size(), (int64_t)v.size(), frames, s.d_samples, d_out, s.stream);
+        st = launch(p, s.d_tab, s.d_tab + v.size(), (int64_t)v.size(), frames, s.d_samples, d_out, s.stream,
+                    offsets_aligned(s.h_tab, (int64_t)v.size()));
         if (st != MB_OK) return st;
         for (int i = 0; i < kNumFields; i++) {
             if (!mb_has(p->mask, kFields[i].feature)) continue;

@@ -1,13 +1,22 @@
 // kernel_generic.cu -- block-per-frame kernel for any power-of-two bufferSize
 // in [16, 32768].  One CTA walks frames (grid-stride); the frame lives in
-// shared memory as N/2 packed complex values, is transformed in place by a
-// decimation-in-frequency FFT with radix-8 fused passes, split into the real
-// spectrum, and every requested Meyda feature is produced in the same pass.
-// Nothing but the requested features is written to HBM.
+// shared memory, is transformed in place, and every requested Meyda feature is
+// produced in the same pass.  Nothing but the requested features is written
+// to HBM.  Two FFT modes:
+//
+//   fast (default)  the frame is packed as N/2 complex values, transformed by a
+//                   float32 decimation-in-frequency FFT with radix-8 fused
+//                   passes and split into the real spectrum.
+//   exact           (MB_FLAG_EXACT_FFT) the reference's own arithmetic: N-point
+//                   radix-2 decimation-in-time on a zero-imaginary array,
+//                   float64 butterflies with the recurrence twiddles and a
+//                   float32 rounding at every stage store
+//                   (lib/jsfft/fft.js:123-171), so complexSpectrum /
+//                   amplitudeSpectrum / powerSpectrum come out bit for bit.
 //
 // Reference path being replaced: src/meyda.js:69-91,104-114,158-168,
-// lib/jsfft/fft.js:123-208, src/extractors/*.js (see mb_device.cuh for the
-// per-formula citations).
+// lib/jsfft/fft.js:123-208, the extractor files under src/extractors/ (see
+// mb_device.cuh for the per-formula citations).
 #include "mb_device.cuh"
 #include "mb_kernels.h"
 
@@ -25,10 +34,9 @@ __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
     return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
 }
 
-// Q fused radix-2 DIF stages starting at span s: 2^Q points per work item.
+// Q fused radix-2 DIF stages starting at span 2^log2s: 2^Q points per work item.
 template <int Q>
-__device__ __forceinline__ void fft_pass(float2 *work, const float2 *__restrict__ twM, int M, int log2M, int s,
-                                         int log2s) {
+__device__ __forceinline__ void fft_pass(float2 *work, const float2 *__restrict__ twM, int M, int log2M, int log2s) {
     constexpr int R = 1 << Q;
     const int items = M >> Q;
     const int log2sub = log2s - Q;
@@ -55,7 +63,6 @@ __device__ __forceinline__ void fft_pass(float2 *work, const float2 *__restrict_
 #pragma unroll
         for (int t = 0; t < R; t++) work[pidx(b + j + t * sub)] = v[t];
     }
-    (void)s;
 }
 
 __device__ __forceinline__ double block_sum(double v, double *scratch /*[kWarps]*/) {
@@ -80,13 +87,31 @@ __device__ __forceinline__ int block_sum_int(int v, int *scratch /*[kWarps]*/) {
     return r;
 }
 
+struct MomentAcc {
+    double s0 = 0, s1 = 0, s2 = 0, s3 = 0, s4 = 0, lg = 0;
+    __device__ __forceinline__ void add(float av, int k, bool want_log) {
+        const double ad = (double)av, kd = (double)k;
+        double t = ad * kd;
+        s0 += ad;
+        s1 += t;
+        t *= kd; s2 += t;
+        t *= kd; s3 += t;
+        t *= kd; s4 += t;
+        if (want_log) lg += (double)log2f(av);
+    }
+};
+
+template <bool EXACT>
 __global__ void __launch_bounds__(kThreads)
 mb_generic_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ MbClipTable T,
                   const float *__restrict__ samples, const __grid_constant__ mb_outputs O) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int N = P.N, M = P.M, log2M = P.log2M;
+    // fast: work = padded M complex, then amp[M].  exact: re[N], im[N], then amp[M].
     float2 *work = reinterpret_cast<float2 *>(smem_raw);
-    float *amp = reinterpret_cast<float *>(work + pidx(M) + 1);
+    float *xre = reinterpret_cast<float *>(smem_raw);
+    float *xim = xre + N;
+    float *amp = EXACT ? (xim + N) : reinterpret_cast<float *>(work + pidx(M) + 1);
 
     __shared__ double red_d[kWarps];
     __shared__ int red_i[kWarps];
@@ -101,6 +126,7 @@ mb_generic_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ M
         mask & (MB_FEATURE_BIT(MB_FEAT_SPECTRAL_CENTROID) | MB_FEATURE_BIT(MB_FEAT_SPECTRAL_SPREAD) |
                 MB_FEATURE_BIT(MB_FEAT_SPECTRAL_SKEWNESS) | MB_FEATURE_BIT(MB_FEAT_SPECTRAL_KURTOSIS) |
                 MB_FEATURE_BIT(MB_FEAT_SPECTRAL_FLATNESS) | MB_FEATURE_BIT(MB_FEAT_SPECTRAL_SLOPE));
+    const bool want_log = mb_has(mask, MB_FEAT_SPECTRAL_FLATNESS);
     const bool want_time = mask & (MB_FEATURE_BIT(MB_FEAT_RMS) | MB_FEATURE_BIT(MB_FEAT_ENERGY) |
                                    MB_FEATURE_BIT(MB_FEAT_ZCR) | MB_FEATURE_BIT(MB_FEAT_BUFFER));
     const bool want_bark = mask & (MB_FEATURE_BIT(MB_FEAT_LOUDNESS) | MB_FEATURE_BIT(MB_FEAT_PERCEPTUAL_SPREAD) |
@@ -118,7 +144,7 @@ mb_generic_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ M
         S.zcr = 0;
         S.rolloff_bin = M;
 
-        // ---- time domain: buffer, energy, zcr; windowed frame into smem as N/2 complex
+        // ---- time domain: buffer, energy, zcr; windowed frame into smem
         {
             double e = 0;
             int z = 0;
@@ -136,7 +162,18 @@ mb_generic_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ M
                         O.buffer[g * N + 2 * i + 1] = x1;
                     }
                 }
-                work[pidx(i)] = make_float2(x0 * __ldg(P.window + 2 * i), x1 * __ldg(P.window + 2 * i + 1));
+                // computeWindow src/meyda.js:158-168: float32 store of the product
+                const float w0 = __fmul_rn(x0, __ldg(P.window + 2 * i));
+                const float w1 = __fmul_rn(x1, __ldg(P.window + 2 * i + 1));
+                if (EXACT) {  // BitReverseComplexArray lib/jsfft/fft.js:185-208, imag zero
+                    const int rshift = 32 - (log2M + 1);
+                    const int r0 = (int)(__brev((unsigned)(2 * i)) >> rshift);
+                    const int r1 = (int)(__brev((unsigned)(2 * i + 1)) >> rshift);
+                    xre[r0] = w0; xim[r0] = 0.f;
+                    xre[r1] = w1; xim[r1] = 0.f;
+                } else {
+                    work[pidx(i)] = make_float2(w0, w1);
+                }
             }
             if (want_time) {
                 S.energy = block_sum(e, red_d);
@@ -146,22 +183,55 @@ mb_generic_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ M
         __syncthreads();
 
         if (want_spectrum) {
-            // ---- in-place DIF FFT, output in bit-reversed positions
-            {
+            MomentAcc acc;
+            if (EXACT) {
+                // ---- FFT_2_Iterative lib/jsfft/fft.js:139-168: doubles, no FMA, f32 stage stores
+                const double SQRT1_2 = 0.70710678118654752440;
+                for (int log2w = 0; log2w <= log2M; log2w++) {
+                    const int w = 1 << log2w;
+                    const double2 *__restrict__ tw = P.tw_exact + (w - 1);
+                    for (int idx = tid; idx < M; idx += kThreads) {
+                        const int j = idx & (w - 1);
+                        const int l = ((idx >> log2w) << (log2w + 1)) + j;
+                        const int r = l + w;
+                        const double2 f = __ldg(&tw[j]);
+                        const double lr = (double)xre[l], li = (double)xim[l];
+                        const double xr = (double)xre[r], xi = (double)xim[r];
+                        const double rr = __dsub_rn(__dmul_rn(f.x, xr), __dmul_rn(f.y, xi));
+                        const double ri = __dadd_rn(__dmul_rn(f.y, xr), __dmul_rn(f.x, xi));
+                        xre[l] = (float)__dmul_rn(SQRT1_2, __dadd_rn(lr, rr));
+                        xim[l] = (float)__dmul_rn(SQRT1_2, __dadd_rn(li, ri));
+                        xre[r] = (float)__dmul_rn(SQRT1_2, __dsub_rn(lr, rr));
+                        xim[r] = (float)__dmul_rn(SQRT1_2, __dsub_rn(li, ri));
+                    }
+                    __syncthreads();
+                }
+                if (mb_has(mask, MB_FEAT_COMPLEX_SPECTRUM)) {
+                    for (int k = tid; k < N; k += kThreads) {
+                        O.complex_real[g * N + k] = xre[k];
+                        O.complex_imag[g * N + k] = xim[k];
+                    }
+                }
+                for (int k = tid; k < M; k += kThreads) {  // computeAmplitude src/meyda.js:104-114
+                    const double r = (double)xre[k], i = (double)xim[k];
+                    const float av = (float)sqrt(__dadd_rn(__dmul_rn(r, r), __dmul_rn(i, i)));
+                    amp[k] = av;
+                    if (mb_has(mask, MB_FEAT_AMPLITUDE_SPECTRUM)) O.amplitude_spectrum[g * M + k] = av;
+                    if (mb_has(mask, MB_FEAT_POWER_SPECTRUM)) O.power_spectrum[g * M + k] = __fmul_rn(av, av);
+                    if (want_moments) acc.add(av, k, want_log);
+                }
+            } else {
+                // ---- in-place DIF FFT, output in bit-reversed positions
                 int log2s = log2M;
                 while (log2s > 0) {
                     const int q = log2s >= 3 ? 3 : log2s;
-                    if (q == 3) fft_pass<3>(work, P.twM, M, log2M, 1 << log2s, log2s);
-                    else if (q == 2) fft_pass<2>(work, P.twM, M, log2M, 1 << log2s, log2s);
-                    else fft_pass<1>(work, P.twM, M, log2M, 1 << log2s, log2s);
+                    if (q == 3) fft_pass<3>(work, P.twM, M, log2M, log2s);
+                    else if (q == 2) fft_pass<2>(work, P.twM, M, log2M, log2s);
+                    else fft_pass<1>(work, P.twM, M, log2M, log2s);
                     log2s -= q;
                     __syncthreads();
                 }
-            }
-
-            // ---- real-FFT split, spectra out, amplitude into smem, moment partials
-            {
-                double s0 = 0, s1 = 0, s2 = 0, s3 = 0, s4 = 0, lg = 0;
+                // ---- real-FFT split, spectra out, amplitude into smem, moment partials
                 const float sc = P.inv_sqrt_N;
                 const int rshift = 32 - log2M;
                 for (int k = tid; k < M; k += kThreads) {
@@ -189,26 +259,17 @@ mb_generic_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ M
                     const float av = sqrtf(zr * zr + zi * zi);
                     amp[k] = av;
                     if (mb_has(mask, MB_FEAT_AMPLITUDE_SPECTRUM)) O.amplitude_spectrum[g * M + k] = av;
-                    if (mb_has(mask, MB_FEAT_POWER_SPECTRUM)) O.power_spectrum[g * M + k] = av * av;
-                    if (want_moments) {
-                        const double ad = (double)av, kd = (double)k;
-                        double t = ad * kd;
-                        s0 += ad;
-                        s1 += t;
-                        t *= kd; s2 += t;
-                        t *= kd; s3 += t;
-                        t *= kd; s4 += t;
-                        if (mb_has(mask, MB_FEAT_SPECTRAL_FLATNESS)) lg += (double)log2f(av);
-                    }
+                    if (mb_has(mask, MB_FEAT_POWER_SPECTRUM)) O.power_spectrum[g * M + k] = __fmul_rn(av, av);
+                    if (want_moments) acc.add(av, k, want_log);
                 }
-                if (want_moments) {
-                    S.s0 = block_sum(s0, red_d);
-                    S.s1 = block_sum(s1, red_d);
-                    S.s2 = block_sum(s2, red_d);
-                    S.s3 = block_sum(s3, red_d);
-                    S.s4 = block_sum(s4, red_d);
-                    if (mb_has(mask, MB_FEAT_SPECTRAL_FLATNESS)) S.log2sum = block_sum(lg, red_d);
-                }
+            }
+            if (want_moments) {
+                S.s0 = block_sum(acc.s0, red_d);
+                S.s1 = block_sum(acc.s1, red_d);
+                S.s2 = block_sum(acc.s2, red_d);
+                S.s3 = block_sum(acc.s3, red_d);
+                S.s4 = block_sum(acc.s4, red_d);
+                if (want_log) S.log2sum = block_sum(acc.lg, red_d);
             }
             __syncthreads();
 
@@ -218,7 +279,6 @@ mb_generic_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ M
                 const int k0 = min(M, tid * chunk), k1 = min(M, k0 + chunk);
                 double csum = 0;
                 for (int k = k0; k < k1; k++) csum += (double)amp[k];
-                // block exclusive scan of csum
                 double incl = csum;
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) {
@@ -254,22 +314,40 @@ mb_generic_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ M
                     if (lane == 0) band_sum[b] = s;
                 }
             }
-            // ---- mel filterbank energies (mfcc.js:40-65), one warp per filter
+            // ---- mel filterbank energies (mfcc.js:40-65)
             if (mb_has(mask, MB_FEAT_MFCC)) {
-                for (int f = warp; f < MB_NUM_MEL_FILTERS; f += kWarps) {
-                    const int e0 = P.mel[f], e1 = P.mel[f + 1], e2 = P.mel[f + 2];
-                    const float up = __ldg(P.mel_inv_width + f), dn = __ldg(P.mel_inv_width + f + 1);
-                    float s = 0.f;
-                    for (int k = e0 + lane; k < e1; k += 32) {
-                        const float a = amp[k];
-                        s += (float)(k - e0) * up * (a * a);
+                if (EXACT) {  // the reference's order: one float32 running sum per filter
+                    if (tid < MB_NUM_MEL_FILTERS) {
+                        const int e0 = P.mel[tid], e1 = P.mel[tid + 1], e2 = P.mel[tid + 2];
+                        float s = 0.f;
+                        for (int k = e0; k < e1 && k < M; k++) {
+                            const double wgt = (double)(k - e0) / (double)(e1 - e0);
+                            const float a = amp[k];
+                            s = (float)__dadd_rn((double)s, __dmul_rn(wgt, (double)__fmul_rn(a, a)));
+                        }
+                        for (int k = e1; k < e2 && k < M; k++) {
+                            const double wgt = (double)(e2 - k) / (double)(e2 - e1);
+                            const float a = amp[k];
+                            s = (float)__dadd_rn((double)s, __dmul_rn(wgt, (double)__fmul_rn(a, a)));
+                        }
+                        mel_log[tid] = (float)log((double)s);
                     }
-                    for (int k = e1 + lane; k < e2; k += 32) {
-                        const float a = amp[k];
-                        s += (float)(e2 - k) * dn * (a * a);
+                } else {  // one warp per filter
+                    for (int f = warp; f < MB_NUM_MEL_FILTERS; f += kWarps) {
+                        const int e0 = P.mel[f], e1 = P.mel[f + 1], e2 = P.mel[f + 2];
+                        const float up = __ldg(P.mel_inv_width + f), dn = __ldg(P.mel_inv_width + f + 1);
+                        float s = 0.f;
+                        for (int k = e0 + lane; k < e1; k += 32) {
+                            const float a = amp[k];
+                            s += (float)(k - e0) * up * (a * a);
+                        }
+                        for (int k = e1 + lane; k < e2; k += 32) {
+                            const float a = amp[k];
+                            s += (float)(e2 - k) * dn * (a * a);
+                        }
+                        s = mb_warp_sum(s);
+                        if (lane == 0) mel_log[f] = (float)log((double)s);
                     }
-                    s = mb_warp_sum(s);
-                    if (lane == 0) mel_log[f] = (float)log((double)s);
                 }
             }
             __syncthreads();
@@ -314,28 +392,32 @@ mb_generic_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ M
 
 }  // namespace
 
-size_t mb_generic_smem_bytes(int M) {
+size_t mb_generic_smem_bytes(int M, bool exact) {
+    if (exact) return (size_t)(2 * M) * 2 * sizeof(float) + (size_t)M * sizeof(float);
     const int padded = M + (M >> 5) + (M >> 10) + 1;
     return (size_t)padded * sizeof(float2) + (size_t)M * sizeof(float);
 }
 
-cudaError_t mb_launch_generic(const MbDevPlan &P, const MbClipTable &T, const float *samples, const mb_outputs &O,
-                              int num_sms, cudaStream_t stream) {
-    const size_t smem = mb_generic_smem_bytes(P.M);
-    static thread_local size_t configured[64] = {0};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev < 64 && configured[dev] < smem) {
-        cudaError_t e = cudaFuncSetAttribute(mb_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        configured[dev] = smem;
-    }
+template <bool EXACT>
+static cudaError_t launch_generic(const MbDevPlan &P, const MbClipTable &T, const float *samples,
+                                  const mb_outputs &O, int num_sms, cudaStream_t stream) {
+    const size_t smem = mb_generic_smem_bytes(P.M, EXACT);
+    cudaError_t e = cudaFuncSetAttribute(mb_generic_kernel<EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)smem);
+    if (e != cudaSuccess) return e;
     int per_sm = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mb_generic_kernel, kThreads, smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mb_generic_kernel<EXACT>, kThreads, smem);
     if (per_sm < 1) per_sm = 1;
     int64_t grid = (int64_t)num_sms * per_sm;
     if (grid > T.total_frames) grid = T.total_frames;
     if (grid < 1) return cudaSuccess;
-    mb_generic_kernel<<<(unsigned)grid, kThreads, smem, stream>>>(P, T, samples, O);
+    (void)cudaGetLastError();  // drop any stale non-sticky error left by other users of the context
+    mb_generic_kernel<EXACT><<<(unsigned)grid, kThreads, smem, stream>>>(P, T, samples, O);
     return cudaGetLastError();
+}
+
+cudaError_t mb_launch_generic(const MbDevPlan &P, const MbClipTable &T, const float *samples, const mb_outputs &O,
+                              int num_sms, cudaStream_t stream) {
+    return P.exact ? launch_generic<true>(P, T, samples, O, num_sms, stream)
+                   : launch_generic<false>(P, T, samples, O, num_sms, stream);
 }

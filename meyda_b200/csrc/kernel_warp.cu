@@ -1,0 +1,526 @@
+// kernel_warp.cu -- warp-per-frame kernel for bufferSize 2048 (the headline
+// configuration), float32 FFT.
+//
+// One warp owns one frame at a time and never synchronises with another warp:
+//   1. lane 0 pulls the frame's 2048 raw samples into the warp's shared-memory
+//      slot with one TMA bulk copy (cp.async.bulk + mbarrier); `buffer` leaves
+//      the same slot with a TMA bulk store, untouched by registers;
+//   2. the windowed frame is read as 1024 packed complex values, 32 per lane,
+//      and transformed as 32 x 32: a register radix-2^5 FFT per lane, a
+//      twiddle, a transpose through the warp's slot, a second register FFT;
+//   3. the real-FFT split produces Z[k] for k = lane + 32 d; complex /
+//      amplitude / power spectra go straight from registers to HBM in 128-byte
+//      rows, and the spectral moments, log sum, and time-domain sums are
+//      accumulated on the way;
+//   4. the amplitudes take one more trip through the slot into a blocked
+//      layout (32 consecutive bins per lane) for the prefix sums that give
+//      rolloff, the 24 Bark bands and the 26 mel filters, which the lanes then
+//      finish (one band / filter / cepstral coefficient per lane);
+//   5. per-frame scalars are parked in a 32-frame stash and turned into the
+//      twelve "number" features once per 32 frames with one frame per lane,
+//      so the float64 divisions/sqrt/exp and the scalar stores run at full
+//      lane efficiency and leave as coalesced 128-byte rows.
+// A warp's work unit is a chunk of 32 consecutive output frames.
+//
+// Reference path being replaced: src/meyda.js:69-91,104-114,158-168,
+// lib/jsfft/fft.js:123-208 and the extractor files under src/extractors/.
+#include <utility>
+
+#include "mb_device.cuh"
+#include "mb_kernels.h"
+
+namespace {
+
+constexpr int kP = 32;             // points per lane per pass
+constexpr int kM = kP * kP;        // 1024 complex points
+constexpr int kN = 2 * kM;         // bufferSize 2048
+constexpr int kWarps = 16;
+constexpr int kThreads = kWarps * 32;
+constexpr int kRow = kP + 1;                  // float2 stride of a transpose row
+constexpr int kSlotFloats = 2 * kP * kRow;    // 2112 floats = 8448 B per warp
+constexpr int kAmpStride = 36;                // floats per lane in the blocked amplitude layout
+constexpr int kBoundaryOff = 1152;            // float offset of the boundary-sample area (after 32*36 amps)
+constexpr int kMaxSlots = MB_WARP_MAX_SLOTS;  // 56
+constexpr int kStashRows = 18;                // floats per frame in the scalar stash
+constexpr int kChunk = 32;                    // frames per work unit
+
+static_assert(kBoundaryOff * 4 + 3 * kMaxSlots * 8 <= kSlotFloats * 4, "boundary samples must fit the warp slot");
+
+// ---- shared memory carve-up (dynamic)
+struct Smem {
+    float2 tw32[kP * kP];        // exp(+2 pi i b c / 1024) at [c*32 + b]
+    float2 twN[kM];              // exp(+2 pi i k / 2048)
+    float window[kN];
+    float dct[MB_NUM_MFCC * MB_NUM_MEL_FILTERS];
+    float mel_inv[MB_NUM_MEL_FILTERS + 2];
+    int mel_edge[MB_NUM_MEL_FILTERS + 2];
+    int mel_slot[MB_NUM_MEL_FILTERS + 2];
+    int bark_slot[MB_NUM_BARK_BANDS + 2];
+    unsigned long long bar[kWarps];
+    float stash[kWarps][kStashRows][kChunk];
+    float slot[kWarps][kSlotFloats];  // 16-byte aligned by construction
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "MB_WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra MB_DONE_%=;\n\t"
+        "bra MB_WAIT_%=;\n\t"
+        "MB_DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+}
+// TMA bulk copies (1-D): global -> shared with mbarrier completion, shared -> global as a bulk group.
+__device__ __forceinline__ void bulk_load(void *dst_smem, const void *src_gmem, uint32_t bytes, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_store(void *dst_gmem, const void *src_smem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)),
+                 "r"(bytes)
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// ---- 32-point FFT in registers: radix-2 decimation in frequency, forward
+// sign +i (lib/jsfft/fft.js:145), natural order in, X[k] left in v[brev5(k)].
+__device__ constexpr float kCos32[16] = {1.000000000e+00f, 9.807852804e-01f, 9.238795325e-01f, 8.314696123e-01f,
+                                         7.071067812e-01f, 5.555702330e-01f, 3.826834324e-01f, 1.950903220e-01f,
+                                         0.0f, -1.950903220e-01f, -3.826834324e-01f, -5.555702330e-01f,
+                                         -7.071067812e-01f, -8.314696123e-01f, -9.238795325e-01f, -9.807852804e-01f};
+__device__ constexpr float kSin32[16] = {0.000000000e+00f, 1.950903220e-01f, 3.826834324e-01f, 5.555702330e-01f,
+                                         7.071067812e-01f, 8.314696123e-01f, 9.238795325e-01f, 9.807852804e-01f,
+                                         1.000000000e+00f, 9.807852804e-01f, 9.238795325e-01f, 8.314696123e-01f,
+                                         7.071067812e-01f, 5.555702330e-01f, 3.826834324e-01f, 1.950903220e-01f};
+
+template <int E>  // d * exp(+2 pi i E / 32), 0 <= E < 16
+__device__ __forceinline__ float2 mul_w32(float2 d) {
+    constexpr float R = 7.071067812e-01f;
+    if constexpr (E == 0) return d;
+    else if constexpr (E == 8) return make_float2(-d.y, d.x);
+    else if constexpr (E == 4) return make_float2((d.x - d.y) * R, (d.x + d.y) * R);
+    else if constexpr (E == 12) return make_float2((-d.x - d.y) * R, (d.x - d.y) * R);
+    else {
+        constexpr float c = kCos32[E], s = kSin32[E];
+        return make_float2(d.x * c - d.y * s, d.x * s + d.y * c);
+    }
+}
+template <int H, int I>
+__device__ __forceinline__ void bfly32(float2 (&v)[32]) {
+    constexpr int B = (I / H) * 2 * H, J = I % H;
+    const float2 u = v[B + J], w = v[B + J + H];
+    v[B + J] = make_float2(u.x + w.x, u.y + w.y);
+    v[B + J + H] = mul_w32<J * (16 / H)>(make_float2(u.x - w.x, u.y - w.y));
+}
+template <int H, int... I>
+__device__ __forceinline__ void stage32(float2 (&v)[32], std::integer_sequence<int, I...>) {
+    (bfly32<H, I>(v), ...);
+}
+__device__ __forceinline__ void fft32(float2 (&v)[32]) {
+    using S = std::make_integer_sequence<int, 16>;
+    stage32<16>(v, S{});
+    stage32<8>(v, S{});
+    stage32<4>(v, S{});
+    stage32<2>(v, S{});
+    stage32<1>(v, S{});
+}
+__host__ __device__ constexpr int brev5(int k) {
+    return ((k & 1) << 4) | ((k & 2) << 2) | (k & 4) | ((k & 8) >> 2) | ((k & 16) >> 4);
+}
+
+__device__ __forceinline__ double warp_sum_d(double v) { return mb_warp_sum(v); }
+
+__device__ __forceinline__ void stash_put_d(float (*st)[kChunk], int row, int col, double v) {
+    st[row][col] = __int_as_float(__double2hiint(v));
+    st[row + 1][col] = __int_as_float(__double2loint(v));
+}
+__device__ __forceinline__ double stash_get_d(float (*st)[kChunk], int row, int col) {
+    return __hiloint2double(__float_as_int(st[row][col]), __float_as_int(st[row + 1][col]));
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+mb_warp2048_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ MbClipTable T,
+                   const float *__restrict__ samples, const __grid_constant__ mb_outputs O, const int64_t total_chunks) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    Smem &S = *reinterpret_cast<Smem *>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t mask = P.mask;
+    const MbWarpTables *__restrict__ WT = P.warp_tables;
+
+    // ---- CTA-wide tables into shared memory (once per persistent CTA)
+    for (int i = tid; i < kP * kP; i += kThreads) S.tw32[i] = WT->tw32[i];
+    for (int i = tid; i < kM; i += kThreads) S.twN[i] = P.twN[i];
+    for (int i = tid; i < kN; i += kThreads) S.window[i] = P.window[i];
+    for (int i = tid; i < MB_NUM_MFCC * MB_NUM_MEL_FILTERS; i += kThreads) S.dct[i] = P.dct[i];
+    if (tid < MB_NUM_MEL_FILTERS + 2) {
+        S.mel_edge[tid] = P.mel[tid];
+        S.mel_slot[tid] = WT->mel_slot[tid];
+        S.mel_inv[tid] = tid < MB_NUM_MEL_FILTERS + 1 ? P.mel_inv_width[tid] : 0.f;
+    }
+    if (tid < MB_NUM_BARK_BANDS + 1) S.bark_slot[tid] = WT->bark_slot[tid];
+    if (lane == 0) mbar_init(&S.bar[warp], 1);
+    __syncthreads();
+
+    const uint32_t bmask = WT->lane_bmask[lane];     // boundaries inside this lane's 32 blocked bins
+    const int slot_base = WT->lane_slot_base[lane];  // index of the first of them
+    const int n_slots = WT->n_slots;                 // slot n_slots-1 is the edge k == M (totals)
+
+    const bool want_buffer = mb_has(mask, MB_FEAT_BUFFER);
+    const bool want_time = mask & (MB_FEATURE_BIT(MB_FEAT_RMS) | MB_FEATURE_BIT(MB_FEAT_ENERGY) | MB_FEATURE_BIT(MB_FEAT_ZCR));
+    const bool want_cs = mb_has(mask, MB_FEAT_COMPLEX_SPECTRUM);
+    const bool want_amp_out = mb_has(mask, MB_FEAT_AMPLITUDE_SPECTRUM);
+    const bool want_pow_out = mb_has(mask, MB_FEAT_POWER_SPECTRUM);
+    const bool want_moments =
+        mask & (MB_FEATURE_BIT(MB_FEAT_SPECTRAL_CENTROID) | MB_FEATURE_BIT(MB_FEAT_SPECTRAL_SPREAD) |
+                MB_FEATURE_BIT(MB_FEAT_SPECTRAL_SKEWNESS) | MB_FEATURE_BIT(MB_FEAT_SPECTRAL_KURTOSIS) |
+                MB_FEATURE_BIT(MB_FEAT_SPECTRAL_FLATNESS) | MB_FEATURE_BIT(MB_FEAT_SPECTRAL_SLOPE));
+    const bool want_log = mb_has(mask, MB_FEAT_SPECTRAL_FLATNESS);
+    const bool want_rolloff = mb_has(mask, MB_FEAT_SPECTRAL_ROLLOFF);
+    const bool want_bark = mask & (MB_FEATURE_BIT(MB_FEAT_LOUDNESS) | MB_FEATURE_BIT(MB_FEAT_PERCEPTUAL_SPREAD) |
+                                   MB_FEATURE_BIT(MB_FEAT_PERCEPTUAL_SHARPNESS));
+    const bool want_mfcc = mb_has(mask, MB_FEAT_MFCC);
+    const bool want_blocked = want_rolloff || want_bark || want_mfcc;
+    const uint32_t time_only = MB_FEATURE_BIT(MB_FEAT_RMS) | MB_FEATURE_BIT(MB_FEAT_ENERGY) |
+                               MB_FEATURE_BIT(MB_FEAT_ZCR) | MB_FEATURE_BIT(MB_FEAT_BUFFER);
+    const bool want_spectrum = (mask & ~time_only) != 0;
+
+    float *slot = S.slot[warp];
+    float2 *slot2 = reinterpret_cast<float2 *>(slot);
+    float(*stash)[kChunk] = S.stash[warp];
+    unsigned long long *bar = &S.bar[warp];
+    uint32_t parity = 0;
+
+    int64_t clip = 0, clip_f0 = 0, clip_f1 = 0;  // cached clip of the previous frame: frames [clip_f0, clip_f1)
+    if (T.n_clips > 0) clip_f1 = T.frame_start[1];
+
+    const int64_t warp_global = (int64_t)blockIdx.x * kWarps + warp;
+    const int64_t warp_stride = (int64_t)gridDim.x * kWarps;
+
+    for (int64_t ch = warp_global; ch < total_chunks; ch += warp_stride) {
+        const int64_t g0 = ch * kChunk;
+        const int nfc = (int)min((int64_t)kChunk, T.total_frames - g0);
+
+        for (int j = 0; j < nfc; j++) {
+            const int64_t g = g0 + j;
+            // ---- which clip (frames ascend, so mostly the cached one or its successor)
+            if (g >= clip_f1 || g < clip_f0) {
+                if (g >= clip_f1 && clip + 2 <= T.n_clips && g < T.frame_start[clip + 2]) clip += 1;
+                else clip = mb_find_clip(T, g);
+                clip_f0 = T.frame_start[clip];
+                clip_f1 = T.frame_start[clip + 1];
+            }
+            const float *src = samples + T.clip_off[clip] + (g - clip_f0) * (int64_t)P.hop;
+
+            // ---- 1. frame into the warp's slot (TMA), buffer out of it (TMA)
+            __syncwarp();  // every lane is done with the slot's previous contents
+            if (lane == 0) {
+                bulk_store_wait_read();  // an earlier frame's `buffer` store has finished reading the slot
+                // generic-proxy accesses to the slot are ordered before the async-proxy write that follows
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_expect_tx(bar, kN * 4);
+                bulk_load(slot, src, kN * 4, bar);
+            }
+            __syncwarp();
+            mbar_wait(bar, parity);
+            parity ^= 1;
+            if (want_buffer && lane == 0) bulk_store(O.buffer + g * kN, slot, kN * 4);
+
+            // ---- 2. pass 1: window, time-domain sums, FFT32 over a for b = lane
+            float2 v[32];
+            float esum = 0.f;
+            uint32_t sgn_e = 0, sgn_o = 0;  // bit a: sample 2(32a+lane) (+1) is >= 0
+#pragma unroll
+            for (int a = 0; a < 32; a++) {
+                const float2 x = slot2[32 * a + lane];
+                const float2 w = reinterpret_cast<const float2 *>(S.window)[32 * a + lane];
+                if (want_time) {
+                    esum = fmaf(x.x, x.x, esum);
+                    esum = fmaf(x.y, x.y, esum);
+                    sgn_e |= (x.x >= 0.f) ? (1u << a) : 0u;
+                    sgn_o |= (x.y >= 0.f) ? (1u << a) : 0u;
+                }
+                v[a] = make_float2(__fmul_rn(x.x, w.x), __fmul_rn(x.y, w.y));
+            }
+            float energy = 0.f;
+            int zcr = 0;
+            if (want_time) {
+                energy = mb_warp_sum(esum);
+                // crossings inside a pair (2m, 2m+1), and between 2m+1 and 2m+2 (= lane+1, or lane 0 of the next row)
+                int z = __popc(sgn_e ^ sgn_o);
+                uint32_t nxt = __shfl_down_sync(0xffffffffu, sgn_e, 1);
+                const uint32_t e0 = __shfl_sync(0xffffffffu, sgn_e, 0);
+                uint32_t valid = 0xffffffffu;
+                if (lane == 31) {
+                    nxt = e0 >> 1;
+                    valid = 0x7fffffffu;  // sample 2047 has no successor in the frame (zcr.js: signal[N] undefined)
+                }
+                z += __popc((sgn_o ^ nxt) & valid);
+                zcr = mb_warp_sum(z);
+                if (!(energy == energy)) {
+                    // a NaN sample: zcr.js compares are all false around it; recount exactly
+                    z = 0;
+                    for (int i = lane; i < kN - 1; i += 32) {
+                        const float p = slot[i], q = slot[i + 1];
+                        z += ((p >= 0.f && q < 0.f) || (p < 0.f && q >= 0.f)) ? 1 : 0;
+                    }
+                    zcr = mb_warp_sum(z);
+                }
+            }
+            if (lane == j) {
+                stash[0][j] = energy;
+                stash[1][j] = __int_as_float(zcr);
+            }
+
+            if (want_spectrum) {
+                fft32(v);
+                __syncwarp();  // all lanes have read their raw samples: the slot becomes the transpose buffer
+                if (want_buffer && lane == 0) bulk_store_wait_read();
+                __syncwarp();
+#pragma unroll
+                for (int c = 0; c < 32; c++) {
+                    float2 y = v[brev5(c)];
+                    if (c > 0) {
+                        const float2 t = S.tw32[c * 32 + lane];
+                        y = make_float2(y.x * t.x - y.y * t.y, y.x * t.y + y.y * t.x);
+                    }
+                    slot2[c * kRow + lane] = y;
+                }
+                __syncwarp();
+                // ---- pass 2: FFT32 over b for c = lane -> X[lane + 32 d] in v[brev5(d)]
+#pragma unroll
+                for (int b = 0; b < 32; b++) v[b] = slot2[lane * kRow + b];
+                fft32(v);
+                __syncwarp();
+                // ---- 3. real-FFT split.  X in natural order through the slot so that lane can fetch X[M-k].
+#pragma unroll
+                for (int d = 0; d < 32; d++) slot2[lane + 32 * d] = v[brev5(d)];
+                __syncwarp();
+
+                float av[32];
+                double s0 = 0, s1 = 0, s2 = 0, s3 = 0, s4 = 0;
+                float lg = 0.f;
+                const float sc = P.inv_sqrt_N;
+                float *out_re = O.complex_real + g * kN, *out_im = O.complex_imag + g * kN;
+                float *out_amp = O.amplitude_spectrum + g * kM, *out_pow = O.power_spectrum + g * kM;
+#pragma unroll
+                for (int d = 0; d < 32; d++) {
+                    const int k = lane + 32 * d;
+                    const float2 a = v[brev5(d)];
+                    const float2 b = slot2[(kM - k) & (kM - 1)];
+                    const float2 w = S.twN[k];
+                    const float er = 0.5f * (a.x + b.x), ei = 0.5f * (a.y - b.y);
+                    const float orr = 0.5f * (a.y + b.y), oi = -0.5f * (a.x - b.x);
+                    float zr = (er + (w.x * orr - w.y * oi)) * sc;
+                    float zi = (ei + (w.x * oi + w.y * orr)) * sc;
+                    if (d == 0 && lane == 0) zi = 0.f;
+                    if (want_cs) {
+                        out_re[k] = zr;
+                        out_im[k] = zi;
+                        if (d == 0 && lane == 0) {
+                            out_re[kM] = (a.x - a.y) * sc;  // Nyquist bin (E[0] - O[0]) / sqrt(N)
+                            out_im[kM] = 0.f;
+                        } else {
+                            out_re[kN - k] = zr;
+                            out_im[kN - k] = -zi;
+                        }
+                    }
+                    const float amp = sqrtf(fmaf(zr, zr, zi * zi));
+                    av[d] = amp;
+                    if (want_amp_out) out_amp[k] = amp;
+                    if (want_pow_out) out_pow[k] = __fmul_rn(amp, amp);
+                    if (want_moments) {
+                        const double ad = (double)amp, kd = (double)k;
+                        double t = ad * kd;
+                        s0 += ad;
+                        s1 += t;
+                        t *= kd; s2 += t;
+                        t *= kd; s3 += t;
+                        t *= kd; s4 += t;
+                        if (want_log) lg += __log2f(amp);
+                    }
+                }
+                if (want_moments) {
+                    s0 = warp_sum_d(s0);
+                    s1 = warp_sum_d(s1);
+                    s2 = warp_sum_d(s2);
+                    s3 = warp_sum_d(s3);
+                    s4 = warp_sum_d(s4);
+                    lg = mb_warp_sum(lg);
+                    if (lane == j) {
+                        stash_put_d(stash, 2, j, s0);
+                        stash_put_d(stash, 4, j, s1);
+                        stash_put_d(stash, 6, j, s2);
+                        stash_put_d(stash, 8, j, s3);
+                        stash_put_d(stash, 10, j, s4);
+                        stash[12][j] = lg;
+                    }
+                }
+
+                if (want_blocked) {
+                    // ---- 4. amplitudes into the blocked layout: lane L gets bins [32 L, 32 L + 32)
+                    __syncwarp();  // every lane has fetched its X[M-k]
+#pragma unroll
+                    for (int d = 0; d < 32; d++) slot[lane + kAmpStride * d] = av[d];
+                    __syncwarp();
+                    float ab[32];
+#pragma unroll
+                    for (int q = 0; q < 8; q++) {
+                        const float4 t = *reinterpret_cast<const float4 *>(slot + kAmpStride * lane + 4 * q);
+                        ab[4 * q] = t.x; ab[4 * q + 1] = t.y; ab[4 * q + 2] = t.z; ab[4 * q + 3] = t.w;
+                    }
+                    // lane totals of a, p = a^2, k*p, then exclusive scans across lanes
+                    double ta = 0, tp = 0, tq = 0;
+#pragma unroll
+                    for (int i = 0; i < 32; i++) {
+                        const double a = (double)ab[i];
+                        const double p = (double)__fmul_rn(ab[i], ab[i]);
+                        ta += a;
+                        tp += p;
+                        tq = fma((double)(32 * lane + i), p, tq);
+                    }
+                    double ia = ta, ip = tp, iq = tq;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const double ya = __shfl_up_sync(0xffffffffu, ia, o);
+                        const double yp = __shfl_up_sync(0xffffffffu, ip, o);
+                        const double yq = __shfl_up_sync(0xffffffffu, iq, o);
+                        if (lane >= o) { ia += ya; ip += yp; iq += yq; }
+                    }
+                    const double total_a = __shfl_sync(0xffffffffu, ia, 31);
+                    const double thr = 0.99 * total_a;
+                    double ra = ia - ta, rp = ip - tp, rq = iq - tq;  // prefix before this lane's first bin
+                    double *bnd = reinterpret_cast<double *>(slot + kBoundaryOff);  // [3][kMaxSlots]
+                    __syncwarp();  // blocked reads done before boundary samples overwrite nothing they need (disjoint), keep order simple
+                    int sidx = slot_base, cnt = 0;
+#pragma unroll
+                    for (int i = 0; i < 32; i++) {
+                        if ((bmask >> i) & 1u) {
+                            bnd[sidx] = ra;
+                            bnd[kMaxSlots + sidx] = rp;
+                            bnd[2 * kMaxSlots + sidx] = rq;
+                            sidx++;
+                        }
+                        cnt += (ra <= thr) ? 1 : 0;
+                        const double p = (double)__fmul_rn(ab[i], ab[i]);
+                        ra += (double)ab[i];
+                        rp += p;
+                        rq = fma((double)(32 * lane + i), p, rq);
+                    }
+                    if (lane == 31) {  // the edge k == M: everything
+                        bnd[n_slots - 1] = ra;
+                        bnd[kMaxSlots + n_slots - 1] = rp;
+                        bnd[2 * kMaxSlots + n_slots - 1] = rq;
+                    }
+                    if (want_rolloff) {
+                        cnt = mb_warp_sum(cnt);
+                        // spectralRolloff.js:11-15: the loop only runs while ec > threshold
+                        const int rbin = (total_a > thr) ? cnt - 1 : kM;
+                        if (lane == j) stash[13][j] = __int_as_float(rbin);
+                    }
+                    __syncwarp();
+                    // ---- lanes finish the bands: loudness.js:55-63, perceptual*.js
+                    if (want_bark) {
+                        float sp = 0.f;
+                        if (lane < MB_NUM_BARK_BANDS) {
+                            const double bsum = bnd[S.bark_slot[lane + 1]] - bnd[S.bark_slot[lane]];
+                            sp = powf((float)bsum, 0.23f);
+                            if (mb_has(mask, MB_FEAT_LOUDNESS)) O.loudness_specific[g * MB_NUM_BARK_BANDS + lane] = sp;
+                        }
+                        const float total = mb_warp_sum(sp);
+                        float mx = (sp > 0.f) ? sp : 0.f;  // NaN never compares greater (perceptualSpread.js:6)
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+                        const float wsh = (lane >= 1 && lane <= 15) ? (float)lane : 0.f;  // (i+1) * spec[i+1], i < 15
+                        const float sharp = mb_warp_sum(wsh * sp);
+                        if (lane == j) {
+                            stash[14][j] = total;
+                            stash[15][j] = mx;
+                            stash[16][j] = sharp;
+                        }
+                    }
+                    // ---- mel energies from the prefix samples, log, DCT (mfcc.js:40-93)
+                    if (want_mfcc) {
+                        float lgE = 0.f;
+                        if (lane < MB_NUM_MEL_FILTERS) {
+                            const double *bp = bnd + kMaxSlots, *bq = bnd + 2 * kMaxSlots;
+                            const int k0 = S.mel_slot[lane], k1 = S.mel_slot[lane + 1], k2 = S.mel_slot[lane + 2];
+                            const double p_up = bp[k1] - bp[k0], q_up = bq[k1] - bq[k0];
+                            const double p_dn = bp[k2] - bp[k1], q_dn = bq[k2] - bq[k1];
+                            const double rise = (q_up - (double)S.mel_edge[lane] * p_up) * (double)S.mel_inv[lane];
+                            const double rise2 = (q_dn - (double)S.mel_edge[lane + 1] * p_dn) * (double)S.mel_inv[lane + 1];
+                            const double e = rise + (p_dn - rise2);
+                            lgE = logf((float)e);
+                        }
+                        float acc = 0.f;
+#pragma unroll
+                        for (int f = 0; f < MB_NUM_MEL_FILTERS; f++) {
+                            const float lf = __shfl_sync(0xffffffffu, lgE, f);
+                            if (lane < MB_NUM_MFCC) acc = fmaf(S.dct[lane + f * MB_NUM_MFCC], lf, acc);
+                        }
+                        if (lane < MB_NUM_MFCC) O.mfcc[g * MB_NUM_MFCC + lane] = acc * (1.0f / (float)MB_NUM_MFCC);
+                    }
+                }
+            }
+        }  // frames of the chunk
+
+        // ---- 5. one frame per lane: the "number" features of the chunk, coalesced
+        __syncwarp();
+        if (lane < nfc) {
+            MbFrameSums F;
+            F.energy = (double)stash[0][lane];
+            F.zcr = __float_as_int(stash[1][lane]);
+            F.s0 = stash_get_d(stash, 2, lane);
+            F.s1 = stash_get_d(stash, 4, lane);
+            F.s2 = stash_get_d(stash, 6, lane);
+            F.s3 = stash_get_d(stash, 8, lane);
+            F.s4 = stash_get_d(stash, 10, lane);
+            F.log2sum = (double)stash[12][lane];
+            F.rolloff_bin = __float_as_int(stash[13][lane]);
+            const int64_t g = g0 + lane;
+            mb_store_scalars(P, O, g, F);
+            if (want_bark) {
+                const double total = (double)stash[14][lane], mx = (double)stash[15][lane];
+                const double sharp = (double)stash[16][lane] + P.sharp_const;
+                if (mb_has(mask, MB_FEAT_LOUDNESS)) O.loudness_total[g] = (float)total;
+                if (mb_has(mask, MB_FEAT_PERCEPTUAL_SPREAD)) {
+                    const double r = (total - mx) / total;
+                    O.perceptual_spread[g] = (float)(r * r);
+                }
+                if (mb_has(mask, MB_FEAT_PERCEPTUAL_SHARPNESS)) O.perceptual_sharpness[g] = (float)(sharp * (0.11 / total));
+            }
+        }
+    }
+    if (lane == 0) bulk_store_wait_all();  // outstanding `buffer` stores complete before the CTA retires
+}
+
+}  // namespace
+
+size_t mb_warp2048_smem_bytes() { return sizeof(Smem) + 128; }
+
+cudaError_t mb_launch_warp2048(const MbDevPlan &P, const MbClipTable &T, const float *samples, const mb_outputs &O,
+                               int num_sms, cudaStream_t stream) {
+    const size_t smem = mb_warp2048_smem_bytes();
+    cudaError_t e = cudaFuncSetAttribute(mb_warp2048_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const int64_t chunks = (T.total_frames + kChunk - 1) / kChunk;
+    int64_t grid = (chunks + kWarps - 1) / kWarps;
+    if (grid > num_sms) grid = num_sms;
+    if (grid < 1) return cudaSuccess;
+    (void)cudaGetLastError();
+    mb_warp2048_kernel<<<(unsigned)grid, kThreads, smem, stream>>>(P, T, samples, O, chunks);
+    return cudaGetLastError();
+}

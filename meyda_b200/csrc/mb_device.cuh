@@ -6,6 +6,17 @@
 
 #include "../../include/meyda_b200.h"
 
+// Tables of the warp-per-frame kernel (bufferSize 2048), one device copy per plan.
+#define MB_WARP_MAX_SLOTS 56
+struct MbWarpTables {
+    float2 tw32[32 * 32];          // exp(+2 pi i b c / 1024) at [c*32 + b]
+    uint32_t lane_bmask[32];       // bit i: bin 32*lane + i is a Bark limit or a mel edge
+    int lane_slot_base[32];        // number of such boundaries below bin 32*lane
+    int bark_slot[MB_NUM_BARK_BANDS + 1];   // boundary index of bbLimits[b]
+    int mel_slot[MB_NUM_MEL_FILTERS + 2];   // boundary index of each mel edge
+    int n_slots;                   // boundaries below M, plus one for the edge k == M
+};
+
 // Per-plan constants handed to kernels by value (__grid_constant__).  Tables
 // are what `new Meyda(...)` precomputes (src/meyda.js:44-48) plus the ones
 // mfcc.js rebuilds per call (src/extractors/mfcc.js:15-83).
@@ -26,6 +37,9 @@ struct MbDevPlan {
     const float2 *twN;          // [M]   exp(+2 pi i k / N)
     const float *dct;           // [13*26] idx = i + j*13 (mfcc.js:72-83)
     const float *mel_inv_width; // [27] 1 / (mel[s+1] - mel[s]) (0 if empty)
+    const double2 *tw_exact;    // [N-1] jsfft recurrence twiddles, stage of width w at [w-1, 2w-1) (exact mode)
+    int exact;                  // MB_FLAG_EXACT_FFT
+    const MbWarpTables *warp_tables;  // bufferSize 2048 only, else NULL
     int bb[MB_NUM_BARK_BANDS + 1];     // loudness.js:24-45
     int mel[MB_NUM_MEL_FILTERS + 2];   // mfcc.js:31-38
 };

@@ -5,6 +5,12 @@
 #include "mb_device.cuh"
 
 // Block-per-frame kernel, any power-of-two bufferSize in [16, 32768].
-size_t mb_generic_smem_bytes(int M);
+size_t mb_generic_smem_bytes(int M, bool exact);
+// Warp-per-frame kernel, bufferSize 2048, float32 FFT.  Needs 16-byte aligned frames:
+// samples pointer and `buffer` output 16-byte aligned, hop and every clip offset multiples of 4.
+size_t mb_warp2048_smem_bytes();
+cudaError_t mb_launch_warp2048(const MbDevPlan &P, const MbClipTable &T, const float *samples, const mb_outputs &O,
+                               int num_sms, cudaStream_t stream);
+
 cudaError_t mb_launch_generic(const MbDevPlan &P, const MbClipTable &T, const float *samples, const mb_outputs &O,
                               int num_sms, cudaStream_t stream);

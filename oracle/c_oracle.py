@@ -51,7 +51,7 @@ def lib():
         _lib.mo_num_frames.argtypes = [C.c_int64, C.c_int, C.c_int]
         _lib.mo_extract_threads.restype = C.c_int64
         _lib.mo_extract_threads.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int,
-                                            C.POINTER(_BatchOut), C.c_int]
+                                            C.POINTER(_BatchOut), C.c_int, C.c_int64]
     return _lib
 
 
@@ -63,7 +63,7 @@ def fft(real: np.ndarray, imag: np.ndarray):
 
 
 def extract(signal, bufferSize: int, hop=None, sr: float = 44100.0, window: str = "hanning",
-            arrays: bool = True, threads: int = 1, n_clips: int = 1) -> dict:
+            arrays: bool = True, threads: int = 1, n_clips: int = 1, ring_per_thread: int = 0) -> dict:
     """Every feature of every frame of `n_clips` equal-length clips laid back to
     back in `signal`.  Same result shapes as meyda_oracle.extract."""
     L = lib()
@@ -75,6 +75,9 @@ def extract(signal, bufferSize: int, hop=None, sr: float = 44100.0, window: str 
         raise ValueError("Buffer size is not a power of two: Meyda will not run.")
     try:
         nf = L.mo_num_frames(clip_len, bufferSize, hop) * n_clips
+        total = nf
+        if ring_per_thread:  # timing runs: bounded output arena, results are overwritten
+            nf = ring_per_thread * threads
         N, n = bufferSize, bufferSize // 2
         bufs = {"scalars": np.zeros((nf, 13), np.float64), "specific": np.zeros((nf, 24), np.float32),
                 "mfcc": np.zeros((nf, 13), np.float32)}
@@ -83,11 +86,12 @@ def extract(signal, bufferSize: int, hop=None, sr: float = 44100.0, window: str 
                         cs_imag=np.zeros((nf, N), np.float32), amp=np.zeros((nf, n), np.float32),
                         power=np.zeros((nf, n), np.float32))
         bo = _BatchOut(**{k: v.ctypes.data for k, v in bufs.items()})
-        got = L.mo_extract_threads(plan, sig.ctypes.data, n_clips, clip_len, hop, C.byref(bo), threads)
-        assert got == nf
+        got = L.mo_extract_threads(plan, sig.ctypes.data, n_clips, clip_len, hop, C.byref(bo), threads,
+                                   ring_per_thread)
+        assert got == total
     finally:
         L.mo_plan_destroy(plan)
-    out = {}
+    out = {"frames_processed": total} if ring_per_thread else {}
     for i, name in enumerate(SCALAR_NAMES):
         if name != "loudness.total":
             out[name] = bufs["scalars"][:, i].copy()

@@ -372,14 +372,16 @@ int64_t mo_num_frames(int64_t len, int N, int hop) {
     return len < N ? 0 : (len - N) / hop + 1;
 }
 
+/* ring > 0: results go to slot ring_base + (frame index % ring) instead of the
+ * frame's own row, so a long timing run needs only a bounded output arena. */
 static void batch_range(const mo_plan *p, const float *samples, int hop, int64_t f0, int64_t f1,
-                        const mo_batch_out *out, int64_t out_base) {
+                        const mo_batch_out *out, int64_t out_base, int64_t ring, int64_t ring_base) {
     void *work = malloc(mo_work_bytes(p));
     const int N = p->N, n = p->n;
     for (int64_t f = f0; f < f1; f++) {
         mo_frame_out o;
         memset(&o, 0, sizeof(o));
-        int64_t g = out_base + f;
+        int64_t g = ring > 0 ? ring_base + ((out_base + f) % ring) : out_base + f;
         o.buffer = out->buffer ? out->buffer + g * N : NULL;
         o.cs_real = out->cs_real ? out->cs_real + g * N : NULL;
         o.cs_imag = out->cs_imag ? out->cs_imag + g * N : NULL;
@@ -402,7 +404,7 @@ static void batch_range(const mo_plan *p, const float *samples, int hop, int64_t
 int64_t mo_extract_clip(const mo_plan *p, const float *samples, int64_t len, int hop,
                         const mo_batch_out *out, int64_t out_base) {
     int64_t nf = mo_num_frames(len, p->N, hop);
-    batch_range(p, samples, hop, 0, nf, out, out_base);
+    batch_range(p, samples, hop, 0, nf, out, out_base, 0, 0);
     return nf;
 }
 
@@ -410,7 +412,7 @@ int64_t mo_extract_clip(const mo_plan *p, const float *samples, int64_t len, int
  * back to back; frames are split evenly over `threads` pthreads. */
 typedef struct {
     const mo_plan *p; const float *samples; int64_t clip_len; int hop; int64_t fpc;
-    int64_t g0, g1; const mo_batch_out *out;
+    int64_t g0, g1; const mo_batch_out *out; int64_t ring, ring_base;
 } mo_job;
 
 static void *job_main(void *arg) {
@@ -420,14 +422,16 @@ static void *job_main(void *arg) {
         int64_t clip = g / j->fpc, f0 = g % j->fpc;
         int64_t f1 = f0 + (j->g1 - g);
         if (f1 > j->fpc) f1 = j->fpc;
-        batch_range(j->p, j->samples + clip * j->clip_len, j->hop, f0, f1, j->out, clip * j->fpc);
+        batch_range(j->p, j->samples + clip * j->clip_len, j->hop, f0, f1, j->out, clip * j->fpc, j->ring,
+                    j->ring_base);
         g += f1 - f0;
     }
     return NULL;
 }
 
+/* ring_per_thread > 0: the output arrays hold threads * ring_per_thread frames. */
 int64_t mo_extract_threads(const mo_plan *p, const float *samples, int64_t n_clips, int64_t clip_len,
-                           int hop, const mo_batch_out *out, int threads) {
+                           int hop, const mo_batch_out *out, int threads, int64_t ring_per_thread) {
     int64_t fpc = mo_num_frames(clip_len, p->N, hop);
     int64_t total = fpc * n_clips;
     if (total == 0) return 0;
@@ -439,6 +443,7 @@ int64_t mo_extract_threads(const mo_plan *p, const float *samples, int64_t n_cli
         jobs[t].p = p; jobs[t].samples = samples; jobs[t].clip_len = clip_len; jobs[t].hop = hop;
         jobs[t].fpc = fpc; jobs[t].out = out;
         jobs[t].g0 = total * t / threads; jobs[t].g1 = total * (t + 1) / threads;
+        jobs[t].ring = ring_per_thread; jobs[t].ring_base = ring_per_thread * t;
         pthread_create(&tid[t], NULL, job_main, &jobs[t]);
     }
     for (int t = 0; t < threads; t++) pthread_join(tid[t], NULL);

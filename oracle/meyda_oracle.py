@@ -227,11 +227,16 @@ def _mu(i: int, amp64: np.ndarray) -> np.ndarray:
 
 
 def extract_frames(frames: np.ndarray, sr: float = 44100.0, window: str = "hanning",
-                   features=None) -> dict:
+                   features=None, fft: str = "jsfft") -> dict:
     """All requested features for a [F, N] float32 batch of raw frames.
 
     Number features -> float64[F]; arrays -> float32[F, len];
     complexSpectrum -> {'real','imag'}; loudness -> {'specific','total'}.
+
+    fft="jsfft" is the reference's arithmetic.  fft="float64" swaps in a
+    mathematically exact transform (numpy.fft in float64, same sign and 1/sqrt(N)
+    scaling, rounded to float32 once): NOT the reference -- it measures how far the
+    reference's own per-stage float32 rounding moves each feature (tests/parity.py).
     """
     feats = ALL_FEATURES if features is None else ([features] if isinstance(features, str) else list(features))
     frames = np.atleast_2d(np.asarray(frames, dtype=f32))
@@ -244,7 +249,13 @@ def extract_frames(frames: np.ndarray, sr: float = 44100.0, window: str = "hanni
     with np.errstate(all="ignore"):
         win = window_table(N, window)
         windowed = (sig64 * win.astype(f64)).astype(f32)  # src/meyda.js:158-168
-        re, im = fft_jsfft(windowed)
+        if fft == "jsfft":
+            re, im = fft_jsfft(windowed)
+        elif fft == "float64":
+            z = np.conj(np.fft.fft(windowed.astype(f64), axis=1)) / np.sqrt(f64(N))
+            re, im = z.real.astype(f32), z.imag.astype(f32)
+        else:
+            raise ValueError(fft)
         amp = np.sqrt(re[:, :n].astype(f64) ** 2 + im[:, :n].astype(f64) ** 2).astype(f32)  # src/meyda.js:104-114
         amp64 = amp.astype(f64)
         power = (amp64 * amp64).astype(f32)  # powerSpectrum.js:1-7
@@ -349,13 +360,13 @@ def _mfcc(power: np.ndarray, N: int, sr: float) -> np.ndarray:
 
 
 def extract(signal: np.ndarray, bufferSize: int, hop: int | None = None, sr: float = 44100.0,
-            window: str = "hanning", features=None, chunk: int = 4096) -> dict:
+            window: str = "hanning", features=None, chunk: int = 4096, fft: str = "jsfft") -> dict:
     """Frame a clip ([f*hop, f*hop+N), no padding) and extract, in chunks."""
     hop = bufferSize if hop is None else hop
     frames = frame_signal(signal, bufferSize, hop)
-    parts = [extract_frames(frames[i:i + chunk], sr, window, features) for i in range(0, len(frames), chunk)]
+    parts = [extract_frames(frames[i:i + chunk], sr, window, features, fft) for i in range(0, len(frames), chunk)]
     if not parts:
-        parts = [extract_frames(np.zeros((0, bufferSize), dtype=f32), sr, window, features)]
+        parts = [extract_frames(np.zeros((0, bufferSize), dtype=f32), sr, window, features, fft)]
     return _concat(parts)
 
 

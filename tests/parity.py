@@ -5,11 +5,22 @@ oracle.meyda_oracle.extract returns).  Tolerances are BASELINE.json's:
   zcr, buffer            bit-exact
   spectralRolloff        exact bin (discrete output)
   spectra                |gpu-ref| <= 1e-4 * max_k|ref_frame|  and per-bin relative
-                         <= 1e-4 on bins >= 1e-3 * peak (float32 FFT error is absolute,
-                         SURVEY.md section 7)
+                         <= 1e-4 on bins >= 1e-2 * peak (float32 FFT error is absolute,
+                         ~1e-7 * peak per bin: SURVEY.md section 7)
   numbers, loudness, mfcc   1e-3 relative OR absolute (slope: relative only -- its
                          magnitude is ~1e-7, an absolute 1e-3 would be vacuous)
   NaN / +-Inf            same positions and signs
+
+Noise band (float32-FFT mode only).  Some features amplify the spectrum's
+rounding-noise floor without bound: x^0.23 and ln(x) of a band that holds
+nothing but FFT rounding noise, or k^3/k^4-weighted sums over ~n empty bins of
+a pure tone.  On such frames the REFERENCE's own value is set by its float32
+per-stage rounding (lib/jsfft/fft.js:158-161), and no FFT that is not bit
+identical can land within 1e-3 of it.  `noise_ref` is the same oracle pipeline
+fed an exact (float64) FFT; a value may miss the tolerance only if it is
+within NOISE_BAND_FACTOR x |ref - noise_ref|, i.e. as close to the reference as
+the reference is to the mathematically exact answer.  Such values are counted
+and returned, never hidden; the exact-FFT mode (MB_FLAG_EXACT_FFT) must need none.
 """
 from __future__ import annotations
 
@@ -17,6 +28,7 @@ import numpy as np
 
 SPECTRA_TOL = 1e-4
 NUMBER_TOL = 1e-3
+NOISE_BAND_FACTOR = 4.0
 
 NUMBER_FIELDS = {
     "rms": "rms", "energy": "energy", "spectral_centroid": "spectralCentroid",
@@ -27,38 +39,40 @@ NUMBER_FIELDS = {
 }
 
 
-def _special_match(g, r):
+def _special_match(g, r, name=""):
     """NaN/Inf positions and signs identical; returns the finite mask."""
     g = np.asarray(g, dtype=np.float64)
     r = np.asarray(r, dtype=np.float64)
-    assert g.shape == r.shape, (g.shape, r.shape)
+    assert g.shape == r.shape, (name, g.shape, r.shape)
     fin_g, fin_r = np.isfinite(g), np.isfinite(r)
     bad = fin_g != fin_r
-    assert not bad.any(), "finite/non-finite mismatch at %s: gpu=%s ref=%s" % (
-        np.argwhere(bad)[:5].tolist(), g[bad][:5], r[bad][:5])
+    assert not bad.any(), "%s: finite/non-finite mismatch at %s: gpu=%s ref=%s" % (
+        name, np.argwhere(bad)[:5].tolist(), g[bad][:5], r[bad][:5])
     nf = ~fin_r
     same = (np.isnan(g[nf]) & np.isnan(r[nf])) | (g[nf] == r[nf])
-    assert same.all(), "NaN/Inf kind mismatch: gpu=%s ref=%s" % (g[nf][~same][:5], r[nf][~same][:5])
+    assert same.all(), "%s: NaN/Inf kind mismatch: gpu=%s ref=%s" % (name, g[nf][~same][:5], r[nf][~same][:5])
     return fin_r
 
 
-def number_violations(g, r, tol=NUMBER_TOL, relative_only=False):
-    """Indices whose error exceeds `tol` both relatively and absolutely."""
+def assert_numbers(name, g, r, tol=NUMBER_TOL, relative_only=False, noise_ref=None):
+    """Returns the number of values that needed the noise band."""
     g = np.asarray(g, dtype=np.float64)
     r = np.asarray(r, dtype=np.float64)
-    fin = _special_match(g, r)
+    fin = _special_match(g, r, name)
     err = np.abs(np.where(fin, g - r, 0.0))
     rel_ok = err <= tol * np.abs(np.where(fin, r, 1.0))
     ok = rel_ok if relative_only else (rel_ok | (err <= tol))
-    return np.argwhere(~ok), err
-
-
-def assert_numbers(name, g, r, tol=NUMBER_TOL, relative_only=False, allow=0):
-    bad, err = number_violations(g, r, tol, relative_only)
-    assert len(bad) <= allow, "%s: %d values outside %g (allowed %d); worst err %g at %s (gpu=%s ref=%s)" % (
-        name, len(bad), tol, allow, err.max(), bad[:3].tolist(),
-        np.asarray(g)[tuple(bad[0])] if len(bad) else None, np.asarray(r)[tuple(bad[0])] if len(bad) else None)
-    return len(bad)
+    banded = 0
+    if noise_ref is not None and not ok.all():
+        nr = np.asarray(noise_ref, dtype=np.float64)
+        band = NOISE_BAND_FACTOR * np.abs(np.where(fin & np.isfinite(nr), r - nr, 0.0))
+        in_band = ~ok & (err <= band)
+        banded = int(in_band.sum())
+        ok = ok | in_band
+    bad = np.argwhere(~ok)
+    assert len(bad) == 0, "%s: %d values outside %g; worst err %g at %s (gpu=%s ref=%s)" % (
+        name, len(bad), tol, err[~ok].max(), bad[:3].tolist(), g[tuple(bad[0])], r[tuple(bad[0])])
+    return banded
 
 
 def assert_spectrum(name, g, r, tol=SPECTRA_TOL, peak=None):
@@ -66,38 +80,59 @@ def assert_spectrum(name, g, r, tol=SPECTRA_TOL, peak=None):
     (complexSpectrum real/imag share the frame's complex peak)."""
     g = np.atleast_2d(np.asarray(g, dtype=np.float64))
     r = np.atleast_2d(np.asarray(r, dtype=np.float64))
-    fin = _special_match(g, r)
+    fin = _special_match(g, r, name)
     if g.size == 0:
         return
     rr = np.where(fin, r, 0.0)
     pk = np.abs(rr).max(axis=1, keepdims=True) if peak is None else np.asarray(peak, dtype=np.float64).reshape(-1, 1)
     err = np.abs(np.where(fin, g - r, 0.0))
-    lim = tol * pk
-    bad = err > lim
+    bad = err > tol * pk
     assert not bad.any(), "%s: peak-relative error %g > %g at %s" % (
         name, (err / np.maximum(pk, 1e-300)).max(), tol, np.argwhere(bad)[:3].tolist())
-    big = np.abs(rr) >= 1e-3 * pk
+    big = (np.abs(rr) >= 1e-2 * pk) & (np.abs(rr) > 0)
     rel = err[big] / np.abs(rr[big])
     assert rel.size == 0 or rel.max() <= tol, "%s: per-bin relative error %g > %g" % (name, rel.max(), tol)
 
 
-def compare_all(gpu: dict, ref: dict, N: int, sr: float = 44100.0, allow_moment_outliers: int = 0) -> dict:
-    """Compare whatever features `gpu` holds.  Returns {feature: outlier count}."""
+def assert_bits(name, g, r):
+    g, r = np.asarray(g), np.asarray(r, dtype=g.dtype)
+    same = (g.view(np.uint32) == r.view(np.uint32)) | (np.isnan(g) & np.isnan(r))
+    assert same.all(), "%s: %d of %d values not bit-identical, first at %s (gpu=%r ref=%r)" % (
+        name, int((~same).sum()), same.size, np.argwhere(~same)[:3].tolist(), g[~same][:3], r[~same][:3])
+
+
+def compare_all(gpu: dict, ref: dict, N: int, sr: float = 44100.0, noise_ref: dict | None = None,
+                exact: bool = False) -> dict:
+    """Compare whatever features `gpu` holds.  Returns {feature: values that
+    needed the noise band}.  exact=True: spectra must be bit-identical and
+    every number within 5e-6 (float32 output rounding + libm)."""
     out = {}
     n = N // 2
+    tol = 5e-6 if exact else NUMBER_TOL
+    nz = (lambda k: None) if (noise_ref is None or exact) else (lambda k: noise_ref[k])
     if "buffer" in gpu:
-        assert np.array_equal(gpu["buffer"].view(np.uint32), ref["buffer"].view(np.uint32)), "buffer not bit-exact"
+        assert_bits("buffer", gpu["buffer"], ref["buffer"])
     if "zcr" in gpu:
         assert np.array_equal(gpu["zcr"].astype(np.int64), ref["zcr"].astype(np.int64)), "zcr not bit-exact"
     if "complex_real" in gpu:
         rr, ri = ref["complexSpectrum"]["real"], ref["complexSpectrum"]["imag"]
-        pk = np.sqrt(rr.astype(np.float64) ** 2 + ri.astype(np.float64) ** 2).max(axis=1) if len(rr) else None
-        assert_spectrum("complexSpectrum.real", gpu["complex_real"], rr, peak=pk)
-        assert_spectrum("complexSpectrum.imag", gpu["complex_imag"], ri, peak=pk)
+        if exact:
+            assert_bits("complexSpectrum.real", gpu["complex_real"], rr)
+            assert_bits("complexSpectrum.imag", gpu["complex_imag"], ri)
+        else:
+            pk = np.sqrt(rr.astype(np.float64) ** 2 + ri.astype(np.float64) ** 2).max(axis=1) if len(rr) else None
+            assert_spectrum("complexSpectrum.real", gpu["complex_real"], rr, peak=pk)
+            assert_spectrum("complexSpectrum.imag", gpu["complex_imag"], ri, peak=pk)
     if "amplitude_spectrum" in gpu:
-        assert_spectrum("amplitudeSpectrum", gpu["amplitude_spectrum"], ref["amplitudeSpectrum"])
+        if exact:
+            assert_bits("amplitudeSpectrum", gpu["amplitude_spectrum"], ref["amplitudeSpectrum"])
+        else:
+            assert_spectrum("amplitudeSpectrum", gpu["amplitude_spectrum"], ref["amplitudeSpectrum"])
     if "power_spectrum" in gpu:
-        assert_spectrum("powerSpectrum", gpu["power_spectrum"], ref["powerSpectrum"], tol=2.5 * SPECTRA_TOL)
+        if exact:
+            assert_bits("powerSpectrum", gpu["power_spectrum"], ref["powerSpectrum"])
+        else:
+            assert_spectrum("powerSpectrum", gpu["power_spectrum"], ref["powerSpectrum"], tol=2.5 * SPECTRA_TOL)
     if "spectral_rolloff" in gpu:
         bin_hz = sr / (2 * (n - 1))
         gb = np.rint(gpu["spectral_rolloff"].astype(np.float64) / bin_hz)
@@ -106,11 +141,15 @@ def compare_all(gpu: dict, ref: dict, N: int, sr: float = 44100.0, allow_moment_
         assert_numbers("spectralRolloff", gpu["spectral_rolloff"], ref["spectralRolloff"], tol=1e-6, relative_only=True)
     for field, feat in NUMBER_FIELDS.items():
         if field in gpu:
-            allow = allow_moment_outliers if feat in ("spectralSkewness", "spectralKurtosis", "spectralSpread") else 0
-            out[feat] = assert_numbers(feat, gpu[field], ref[feat], relative_only=(feat == "spectralSlope"), allow=allow)
+            out[feat] = assert_numbers(feat, gpu[field], ref[feat], tol=tol, relative_only=(feat == "spectralSlope"),
+                                       noise_ref=nz(feat))
     if "loudness_specific" in gpu:
-        assert_numbers("loudness.specific", gpu["loudness_specific"], ref["loudness"]["specific"])
-        assert_numbers("loudness.total", gpu["loudness_total"], ref["loudness"]["total"])
+        nl = None if nz("loudness") is None else nz("loudness")
+        out["loudness.specific"] = assert_numbers("loudness.specific", gpu["loudness_specific"],
+                                                  ref["loudness"]["specific"], tol=tol,
+                                                  noise_ref=None if nl is None else nl["specific"])
+        out["loudness.total"] = assert_numbers("loudness.total", gpu["loudness_total"], ref["loudness"]["total"],
+                                               tol=tol, noise_ref=None if nl is None else nl["total"])
     if "mfcc" in gpu:
-        assert_numbers("mfcc", gpu["mfcc"], ref["mfcc"])
-    return out
+        out["mfcc"] = assert_numbers("mfcc", gpu["mfcc"], ref["mfcc"], tol=tol, noise_ref=nz("mfcc"))
+    return {k: v for k, v in out.items() if v}
