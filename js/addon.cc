@@ -1,0 +1,147 @@
+// addon.cc -- Node.js N-API veneer over the C ABI of include/meyda_b200.h.
+//
+// NOT BUILT OR RUN IN THIS REPO'S IMAGE: there is no `node` and no node_api.h
+// here.  It is the reference-side binding a maintainer
+// adds on a machine with Node >= 18 + CUDA; everything below the C ABI is
+// exercised from Python (meyda_b200/_capi.py binds the same entry points).
+//
+//   const native = require('./build/Release/meyda_b200.node')
+//   const plan = native.createPlan({bufferSize, hop, sampleRate, window, featureMask, device, flags})
+//   const out  = native.extract(plan, samples /*Float32Array*/, offsets /*BigInt64Array*/, lengths /*BigInt64Array*/)
+//   native.destroyPlan(plan)
+//
+// `out` maps mb_outputs field names to typed arrays laid out exactly as the C
+// ABI documents (frame-major SoA); js/meyda_b200.js turns them into the
+// reference's per-frame `get([...])` objects.
+#include <node_api.h>
+#include <stdint.h>
+#include <string.h>
+
+#include "../include/meyda_b200.h"
+
+#define NAPI_OK_OR_THROW(env, call)                                   \
+    do {                                                              \
+        if ((call) != napi_ok) {                                      \
+            napi_throw_error((env), NULL, "N-API call failed: " #call); \
+            return NULL;                                              \
+        }                                                             \
+    } while (0)
+
+static napi_value throw_mb(napi_env env, mb_status st) {
+    // src/meyda.js:20-22 throws `new Error(...)` with this exact text for MB_ERR_NOT_POWER_OF_TWO
+    napi_throw_error(env, st == MB_ERR_NOT_POWER_OF_TWO ? "ERR_MEYDA_BUFFER_SIZE" : "ERR_MEYDA_NATIVE", mb_last_error());
+    return NULL;
+}
+
+static int32_t get_i32(napi_env env, napi_value obj, const char *key, int32_t dflt) {
+    napi_value v;
+    bool has = false;
+    if (napi_has_named_property(env, obj, key, &has) != napi_ok || !has) return dflt;
+    int32_t out = dflt;
+    if (napi_get_named_property(env, obj, key, &v) == napi_ok) napi_get_value_int32(env, v, &out);
+    return out;
+}
+static double get_f64(napi_env env, napi_value obj, const char *key, double dflt) {
+    napi_value v;
+    bool has = false;
+    if (napi_has_named_property(env, obj, key, &has) != napi_ok || !has) return dflt;
+    double out = dflt;
+    if (napi_get_named_property(env, obj, key, &v) == napi_ok) napi_get_value_double(env, v, &out);
+    return out;
+}
+
+static void plan_finalize(napi_env, void *data, void *) { mb_plan_destroy((mb_plan *)data); }
+
+static napi_value CreatePlan(napi_env env, napi_callback_info info) {
+    size_t argc = 1;
+    napi_value argv[1];
+    NAPI_OK_OR_THROW(env, napi_get_cb_info(env, info, &argc, argv, NULL, NULL));
+    const int32_t n = get_i32(env, argv[0], "bufferSize", 0);
+    mb_plan *plan = NULL;
+    mb_status st = mb_plan_create(&plan, get_i32(env, argv[0], "device", 0), n, get_i32(env, argv[0], "hop", n),
+                                  get_f64(env, argv[0], "sampleRate", 44100.0), get_i32(env, argv[0], "window", 0),
+                                  (uint32_t)get_i32(env, argv[0], "featureMask", (int32_t)MB_ALL_FEATURES),
+                                  (uint32_t)get_i32(env, argv[0], "flags", 0));
+    if (st != MB_OK) return throw_mb(env, st);
+    napi_value ext;
+    NAPI_OK_OR_THROW(env, napi_create_external(env, plan, plan_finalize, NULL, &ext));
+    return ext;
+}
+
+struct FieldDesc { const char *name; int feature; int kind; size_t offset; };  // kind 0:1 1:N 2:N/2 3:24 4:13
+#define F(name, feat, kind) {#name, feat, kind, offsetof(mb_outputs, name)}
+static const FieldDesc kFields[] = {
+    F(buffer, MB_FEAT_BUFFER, 1), F(rms, MB_FEAT_RMS, 0), F(energy, MB_FEAT_ENERGY, 0), F(zcr, MB_FEAT_ZCR, 0),
+    F(complex_real, MB_FEAT_COMPLEX_SPECTRUM, 1), F(complex_imag, MB_FEAT_COMPLEX_SPECTRUM, 1),
+    F(amplitude_spectrum, MB_FEAT_AMPLITUDE_SPECTRUM, 2), F(power_spectrum, MB_FEAT_POWER_SPECTRUM, 2),
+    F(spectral_centroid, MB_FEAT_SPECTRAL_CENTROID, 0), F(spectral_flatness, MB_FEAT_SPECTRAL_FLATNESS, 0),
+    F(spectral_slope, MB_FEAT_SPECTRAL_SLOPE, 0), F(spectral_rolloff, MB_FEAT_SPECTRAL_ROLLOFF, 0),
+    F(spectral_spread, MB_FEAT_SPECTRAL_SPREAD, 0), F(spectral_skewness, MB_FEAT_SPECTRAL_SKEWNESS, 0),
+    F(spectral_kurtosis, MB_FEAT_SPECTRAL_KURTOSIS, 0), F(loudness_specific, MB_FEAT_LOUDNESS, 3),
+    F(loudness_total, MB_FEAT_LOUDNESS, 0), F(perceptual_spread, MB_FEAT_PERCEPTUAL_SPREAD, 0),
+    F(perceptual_sharpness, MB_FEAT_PERCEPTUAL_SHARPNESS, 0), F(mfcc, MB_FEAT_MFCC, 4)};
+
+static napi_value Extract(napi_env env, napi_callback_info info) {
+    size_t argc = 4;
+    napi_value argv[4];
+    NAPI_OK_OR_THROW(env, napi_get_cb_info(env, info, &argc, argv, NULL, NULL));
+    mb_plan *plan = NULL;
+    NAPI_OK_OR_THROW(env, napi_get_value_external(env, argv[0], (void **)&plan));
+    napi_typedarray_type tt;
+    size_t n_samples = 0, n_clips = 0, n_len = 0;
+    void *samples = NULL, *offs = NULL, *lens = NULL;
+    NAPI_OK_OR_THROW(env, napi_get_typedarray_info(env, argv[1], &tt, &n_samples, &samples, NULL, NULL));
+    if (tt != napi_float32_array) { napi_throw_type_error(env, NULL, "samples must be a Float32Array"); return NULL; }
+    NAPI_OK_OR_THROW(env, napi_get_typedarray_info(env, argv[2], &tt, &n_clips, &offs, NULL, NULL));
+    if (tt != napi_bigint64_array) { napi_throw_type_error(env, NULL, "offsets must be a BigInt64Array"); return NULL; }
+    NAPI_OK_OR_THROW(env, napi_get_typedarray_info(env, argv[3], &tt, &n_len, &lens, NULL, NULL));
+    if (tt != napi_bigint64_array || n_len != n_clips) { napi_throw_type_error(env, NULL, "lengths must match offsets"); return NULL; }
+
+    mb_layout lay;
+    mb_status st = mb_query_output(plan, (int64_t)n_clips, (const int64_t *)lens, NULL, &lay);
+    if (st != MB_OK) return throw_mb(env, st);
+    napi_value result;
+    NAPI_OK_OR_THROW(env, napi_create_object(env, &result));
+    mb_outputs out;
+    memset(&out, 0, sizeof(out));
+    for (const FieldDesc &f : kFields) {
+        if (!((lay.feature_mask >> f.feature) & 1u)) continue;
+        const size_t per = f.kind == 0 ? 1 : f.kind == 1 ? (size_t)lay.buffer_size : f.kind == 2 ? (size_t)lay.spectrum_size
+                                         : f.kind == 3 ? MB_NUM_BARK_BANDS : MB_NUM_MFCC;
+        const size_t elems = per * (size_t)lay.total_frames;
+        napi_value ab, ta;
+        void *data = NULL;
+        NAPI_OK_OR_THROW(env, napi_create_arraybuffer(env, elems * 4, &data, &ab));
+        NAPI_OK_OR_THROW(env, napi_create_typedarray(env, strcmp(f.name, "zcr") == 0 ? napi_int32_array : napi_float32_array,
+                                                     elems, ab, 0, &ta));
+        *(void **)((char *)&out + f.offset) = data;
+        NAPI_OK_OR_THROW(env, napi_set_named_property(env, result, f.name, ta));
+    }
+    st = mb_extract(plan, (const float *)samples, (int64_t)n_samples, (const int64_t *)offs, (const int64_t *)lens,
+                    (int64_t)n_clips, &out, MB_MEM_HOST);
+    if (st != MB_OK) return throw_mb(env, st);
+    napi_value frames;
+    NAPI_OK_OR_THROW(env, napi_create_int64(env, lay.total_frames, &frames));
+    NAPI_OK_OR_THROW(env, napi_set_named_property(env, result, "totalFrames", frames));
+    return result;
+}
+
+static napi_value DestroyPlan(napi_env env, napi_callback_info info) {
+    size_t argc = 1;
+    napi_value argv[1];
+    NAPI_OK_OR_THROW(env, napi_get_cb_info(env, info, &argc, argv, NULL, NULL));
+    void *plan = NULL;
+    if (napi_remove_wrap(env, argv[0], &plan) != napi_ok) { /* externals are released by the finalizer */ }
+    return NULL;
+}
+
+static napi_value Init(napi_env env, napi_value exports) {
+    napi_property_descriptor props[] = {
+        {"createPlan", NULL, CreatePlan, NULL, NULL, NULL, napi_default, NULL},
+        {"extract", NULL, Extract, NULL, NULL, NULL, napi_default, NULL},
+        {"destroyPlan", NULL, DestroyPlan, NULL, NULL, NULL, napi_default, NULL},
+    };
+    napi_define_properties(env, exports, sizeof(props) / sizeof(props[0]), props);
+    return exports;
+}
+NAPI_MODULE(NODE_GYP_MODULE_NAME, Init)

@@ -1,0 +1,92 @@
+// meyda_b200.js -- JavaScript facade over the N-API addon: the reference's
+// extractor API (feature names, featureInfo, get([...]) shapes, per-buffer
+// callback) served from one batched GPU call.
+//
+// NOT RUN IN THIS REPO'S IMAGE (no Node).  meyda_b200/meyda.py is the tested
+// mirror of this file; keep the two in step.
+'use strict'
+const native = require('./build/Release/meyda_b200.node')
+
+// src/feature-info.js:3-64
+const featureInfo = {
+  buffer: {type: 'array'}, rms: {type: 'number'}, energy: {type: 'number'}, zcr: {type: 'number'},
+  complexSpectrum: {type: 'multipleArrays', arrayNames: {1: 'real', 2: 'imag'}},
+  amplitudeSpectrum: {type: 'array'}, powerSpectrum: {type: 'array'},
+  spectralCentroid: {type: 'number'}, spectralFlatness: {type: 'number'}, spectralSlope: {type: 'number'},
+  spectralRolloff: {type: 'number'}, spectralSpread: {type: 'number'}, spectralSkewness: {type: 'number'},
+  spectralKurtosis: {type: 'number'},
+  loudness: {type: 'multipleArrays', arrayNames: {1: 'total', 2: 'specific'}},
+  perceptualSpread: {type: 'number'}, perceptualSharpness: {type: 'number'}, mfcc: {type: 'array'}
+}
+const FEATURES = Object.keys(featureInfo)
+const FIELD = {  // feature -> [mb_outputs field, per-frame length(N)]
+  buffer: ['buffer', N => N], rms: ['rms'], energy: ['energy'], zcr: ['zcr'],
+  amplitudeSpectrum: ['amplitude_spectrum', N => N / 2], powerSpectrum: ['power_spectrum', N => N / 2],
+  spectralCentroid: ['spectral_centroid'], spectralFlatness: ['spectral_flatness'], spectralSlope: ['spectral_slope'],
+  spectralRolloff: ['spectral_rolloff'], spectralSpread: ['spectral_spread'], spectralSkewness: ['spectral_skewness'],
+  spectralKurtosis: ['spectral_kurtosis'], perceptualSpread: ['perceptual_spread'],
+  perceptualSharpness: ['perceptual_sharpness'], mfcc: ['mfcc', () => 13]
+}
+
+// src/utils.js:13-19
+function isPowerOfTwo (num) {
+  while (((num % 2) === 0) && num > 1) num /= 2
+  return num === 1
+}
+
+function splitFeatures (features) {
+  if (typeof features === 'string') return [features]
+  if (typeof features === 'object' && features !== null) {
+    return features.filter(f => {  // src/meyda.js:248-254: unknown names are reported and skipped
+      if (featureInfo[f]) return true
+      console.error(new TypeError('unknown feature ' + f))
+      return false
+    })
+  }
+  throw new Error('Invalid Feature Format')  // src/meyda.js:259
+}
+
+function frameValue (out, N, i, feature) {
+  if (feature === 'complexSpectrum') {
+    return {real: out.complex_real.subarray(i * N, (i + 1) * N), imag: out.complex_imag.subarray(i * N, (i + 1) * N)}
+  }
+  if (feature === 'loudness') {
+    return {specific: out.loudness_specific.subarray(i * 24, (i + 1) * 24), total: out.loudness_total[i]}
+  }
+  const [field, len] = FIELD[feature]
+  if (!len) return out[field][i]
+  const n = len(N)
+  return out[field].subarray(i * n, (i + 1) * n)
+}
+
+// extract(clips, {bufferSize, hop, sampleRate, windowingFunction, features, device}, callback?)
+function extract (clips, opts, callback) {
+  const N = opts.bufferSize
+  if (!isPowerOfTwo(N)) throw new Error('Buffer size is not a power of two: Meyda will not run.')  // src/meyda.js:20-22
+  const features = splitFeatures(opts.features || FEATURES)
+  const list = Array.isArray(clips) ? clips : [clips]
+  const lengths = BigInt64Array.from(list.map(c => BigInt(c.length)))
+  const offsets = new BigInt64Array(list.length)
+  let total = 0
+  list.forEach((c, i) => { offsets[i] = BigInt(total); total += c.length })
+  const samples = new Float32Array(total)
+  list.forEach((c, i) => samples.set(c, Number(offsets[i])))
+  const featureMask = features.reduce((m, f) => m | (1 << FEATURES.indexOf(f)), 0)
+  const plan = native.createPlan({
+    bufferSize: N, hop: opts.hop || N, sampleRate: opts.sampleRate || 44100, featureMask,
+    window: (opts.windowingFunction || 'hanning') === 'hamming' ? 1 : 0, device: opts.device || 0
+  })
+  const out = native.extract(plan, samples, offsets, lengths)
+  native.destroyPlan(plan)
+  const result = {
+    features, arrays: out, totalFrames: Number(out.totalFrames),
+    value: (i, f) => frameValue(out, N, i, f),
+    frame: i => Object.fromEntries(features.map(f => [f, frameValue(out, N, i, f)]))
+  }
+  if (typeof callback === 'function') {  // the buffer-by-buffer contract, src/meyda.js:87-89
+    for (let i = 0; i < result.totalFrames; i++) callback(result.frame(i))
+  }
+  return result
+}
+
+module.exports = {extract, featureInfo, isPowerOfTwo, FEATURES}

@@ -298,20 +298,38 @@ void build_warp_tables(MbWarpTables &W, const MbDevPlan &D) {
     std::vector<int> below;  // boundaries < M
     for (int e : edges)
         if (e < M) below.push_back(e);
-    W.n_slots = (int)below.size() + 1;
-    auto slot_of = [&](int e) {
-        if (e >= M) return (int)below.size();
-        return (int)(std::lower_bound(below.begin(), below.end(), e) - below.begin());
-    };
-    for (int i = 0; i <= MB_NUM_BARK_BANDS; i++) W.bark_slot[i] = slot_of(D.bb[i]);
-    for (int i = 0; i < MB_NUM_MEL_FILTERS + 2; i++) W.mel_slot[i] = slot_of(D.mel[i]);
+    W.n_slots = (int)below.size();
+    if (W.n_slots > MB_WARP_MAX_SLOTS || below.empty() || below[0] != 0) {
+        W.n_slots = MB_WARP_MAX_SLOTS + 1;  // signals "does not fit" to the caller
+        return;
+    }
+    std::vector<int> head_end(32);  // lane L's head piece covers [32 L, head_end[L])
     for (int lane = 0; lane < 32; lane++) {
-        W.lane_slot_base[lane] = (int)(std::lower_bound(below.begin(), below.end(), 32 * lane) - below.begin());
+        const auto first = std::lower_bound(below.begin(), below.end(), 32 * lane);
+        W.lane_slot_base[lane] = (int)(first - below.begin());
+        W.lane_seg_start[lane] = *(std::upper_bound(below.begin(), below.end(), 32 * lane) - 1);
         uint32_t m = 0;
         for (int i = 0; i < 32; i++)
             if (std::binary_search(below.begin(), below.end(), 32 * lane + i)) m |= 1u << i;
         W.lane_bmask[lane] = m;
+        head_end[lane] = (first != below.end() && *first < 32 * lane + 32) ? *first : 32 * lane + 32;
+        W.piece_edge[MB_WARP_HEAD + lane] = W.lane_seg_start[lane];
     }
+    for (int s = 0; s < W.n_slots; s++) W.piece_edge[s] = below[s];
+    // pieces of every Bark band [bb[b], bb[b+1]) and mel segment [mel[s], mel[s+1])
+    int n_items = 0;
+    auto add_segment = [&](int seg, int e0, int e1) {
+        W.seg_ptr[seg] = n_items;
+        for (int s = 0; s < W.n_slots; s++)
+            if (below[s] >= e0 && below[s] < e1 && n_items < MB_WARP_MAX_ITEMS) W.seg_items[n_items++] = (unsigned char)s;
+        for (int lane = 0; lane < 32; lane++)
+            if (head_end[lane] > 32 * lane && 32 * lane > e0 && 32 * lane < e1 && n_items < MB_WARP_MAX_ITEMS)
+                W.seg_items[n_items++] = (unsigned char)(MB_WARP_HEAD + lane);
+    };
+    for (int b = 0; b < MB_NUM_BARK_BANDS; b++) add_segment(b, D.bb[b], D.bb[b + 1]);
+    for (int s = 0; s <= MB_NUM_MEL_FILTERS; s++) add_segment(MB_NUM_BARK_BANDS + s, D.mel[s], D.mel[s + 1]);
+    W.seg_ptr[MB_WARP_SEGMENTS] = n_items;
+    if (n_items >= MB_WARP_MAX_ITEMS) W.n_slots = MB_WARP_MAX_SLOTS + 1;
 }
 
 void offset_outputs(mb_outputs &o, const mb_outputs &base, int64_t frame0, int N) {

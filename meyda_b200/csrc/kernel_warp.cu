@@ -39,12 +39,12 @@ constexpr int kThreads = kWarps * 32;
 constexpr int kRow = kP + 1;                  // float2 stride of a transpose row
 constexpr int kSlotFloats = 2 * kP * kRow;    // 2112 floats = 8448 B per warp
 constexpr int kAmpStride = 36;                // floats per lane in the blocked amplitude layout
-constexpr int kBoundaryOff = 1152;            // float offset of the boundary-sample area (after 32*36 amps)
-constexpr int kMaxSlots = MB_WARP_MAX_SLOTS;  // 56
+constexpr int kPieceOff = 1152;               // float offset of the piece area (after 32*36 amps)
+constexpr int kPieces = MB_WARP_PIECES;       // 96: 64 boundary pieces + 32 lane heads
 constexpr int kStashRows = 18;                // floats per frame in the scalar stash
 constexpr int kChunk = 32;                    // frames per work unit
 
-static_assert(kBoundaryOff * 4 + 3 * kMaxSlots * 8 <= kSlotFloats * 4, "boundary samples must fit the warp slot");
+static_assert(kPieceOff * 4 + 3 * kPieces * 8 <= kSlotFloats * 4, "band pieces must fit the warp slot");
 
 // ---- shared memory carve-up (dynamic)
 struct Smem {
@@ -54,8 +54,9 @@ struct Smem {
     float dct[MB_NUM_MFCC * MB_NUM_MEL_FILTERS];
     float mel_inv[MB_NUM_MEL_FILTERS + 2];
     int mel_edge[MB_NUM_MEL_FILTERS + 2];
-    int mel_slot[MB_NUM_MEL_FILTERS + 2];
-    int bark_slot[MB_NUM_BARK_BANDS + 2];
+    int piece_edge[kPieces];
+    int seg_ptr[MB_WARP_SEGMENTS + 1];
+    unsigned char seg_items[MB_WARP_MAX_ITEMS];
     unsigned long long bar[kWarps];
     float stash[kWarps][kStashRows][kChunk];
     float slot[kWarps][kSlotFloats];  // 16-byte aligned by construction
@@ -168,16 +169,17 @@ mb_warp2048_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
     for (int i = tid; i < MB_NUM_MFCC * MB_NUM_MEL_FILTERS; i += kThreads) S.dct[i] = P.dct[i];
     if (tid < MB_NUM_MEL_FILTERS + 2) {
         S.mel_edge[tid] = P.mel[tid];
-        S.mel_slot[tid] = WT->mel_slot[tid];
         S.mel_inv[tid] = tid < MB_NUM_MEL_FILTERS + 1 ? P.mel_inv_width[tid] : 0.f;
     }
-    if (tid < MB_NUM_BARK_BANDS + 1) S.bark_slot[tid] = WT->bark_slot[tid];
+    if (tid < kPieces) S.piece_edge[tid] = WT->piece_edge[tid];
+    if (tid <= MB_WARP_SEGMENTS) S.seg_ptr[tid] = WT->seg_ptr[tid];
+    if (tid < MB_WARP_MAX_ITEMS) S.seg_items[tid] = WT->seg_items[tid];
     if (lane == 0) mbar_init(&S.bar[warp], 1);
     __syncthreads();
 
     const uint32_t bmask = WT->lane_bmask[lane];     // boundaries inside this lane's 32 blocked bins
     const int slot_base = WT->lane_slot_base[lane];  // index of the first of them
-    const int n_slots = WT->n_slots;                 // slot n_slots-1 is the edge k == M (totals)
+    const int seg_start = WT->lane_seg_start[lane];  // the boundary that opened the run this lane's first bin is in
 
     const bool want_buffer = mb_has(mask, MB_FEAT_BUFFER);
     const bool want_time = mask & (MB_FEATURE_BIT(MB_FEAT_RMS) | MB_FEATURE_BIT(MB_FEAT_ENERGY) | MB_FEATURE_BIT(MB_FEAT_ZCR));
@@ -382,50 +384,50 @@ mb_warp2048_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
                         const float4 t = *reinterpret_cast<const float4 *>(slot + kAmpStride * lane + 4 * q);
                         ab[4 * q] = t.x; ab[4 * q + 1] = t.y; ab[4 * q + 2] = t.z; ab[4 * q + 3] = t.w;
                     }
-                    // lane totals of a, p = a^2, k*p, then exclusive scans across lanes
-                    double ta = 0, tp = 0, tq = 0;
-#pragma unroll
-                    for (int i = 0; i < 32; i++) {
-                        const double a = (double)ab[i];
-                        const double p = (double)__fmul_rn(ab[i], ab[i]);
-                        ta += a;
-                        tp += p;
-                        tq = fma((double)(32 * lane + i), p, tq);
-                    }
-                    double ia = ta, ip = tp, iq = tq;
-#pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) {
-                        const double ya = __shfl_up_sync(0xffffffffu, ia, o);
-                        const double yp = __shfl_up_sync(0xffffffffu, ip, o);
-                        const double yq = __shfl_up_sync(0xffffffffu, iq, o);
-                        if (lane >= o) { ia += ya; ip += yp; iq += yq; }
-                    }
-                    const double total_a = __shfl_sync(0xffffffffu, ia, 31);
-                    const double thr = 0.99 * total_a;
-                    double ra = ia - ta, rp = ip - tp, rq = iq - tq;  // prefix before this lane's first bin
-                    double *bnd = reinterpret_cast<double *>(slot + kBoundaryOff);  // [3][kMaxSlots]
-                    __syncwarp();  // blocked reads done before boundary samples overwrite nothing they need (disjoint), keep order simple
-                    int sidx = slot_base, cnt = 0;
+                    // One sequential pass per lane over its 32 bins: running sums of a, p = a^2 and
+                    // (k - e) p since the last boundary e, flushed into a piece at every boundary.
+                    // Only additions of non-negative terms: a silent band next to a loud bin keeps its value.
+                    double *piece = reinterpret_cast<double *>(slot + kPieceOff);  // [3][kPieces]: a, p, (k-e)p
+                    double ra = 0, rp = 0, rr = 0, ta = 0;
+                    double wd = (double)(32 * lane - seg_start);
+                    int cur = MB_WARP_HEAD + lane, sidx = slot_base;
 #pragma unroll
                     for (int i = 0; i < 32; i++) {
                         if ((bmask >> i) & 1u) {
-                            bnd[sidx] = ra;
-                            bnd[kMaxSlots + sidx] = rp;
-                            bnd[2 * kMaxSlots + sidx] = rq;
-                            sidx++;
+                            piece[cur] = ra;
+                            piece[kPieces + cur] = rp;
+                            piece[2 * kPieces + cur] = rr;
+                            ta += ra;
+                            cur = sidx++;
+                            ra = rp = rr = wd = 0;
                         }
-                        cnt += (ra <= thr) ? 1 : 0;
-                        const double p = (double)__fmul_rn(ab[i], ab[i]);
+                        const double pd = (double)__fmul_rn(ab[i], ab[i]);
                         ra += (double)ab[i];
-                        rp += p;
-                        rq = fma((double)(32 * lane + i), p, rq);
+                        rp += pd;
+                        rr = fma(wd, pd, rr);
+                        wd += 1.0;
                     }
-                    if (lane == 31) {  // the edge k == M: everything
-                        bnd[n_slots - 1] = ra;
-                        bnd[kMaxSlots + n_slots - 1] = rp;
-                        bnd[2 * kMaxSlots + n_slots - 1] = rq;
-                    }
+                    piece[cur] = ra;
+                    piece[kPieces + cur] = rp;
+                    piece[2 * kPieces + cur] = rr;
+                    ta += ra;
                     if (want_rolloff) {
+                        // spectralRolloff.js: largest m with sum_{k<m} a[k] <= 0.99 sum a
+                        double ia = ta;
+#pragma unroll
+                        for (int o = 1; o < 32; o <<= 1) {
+                            const double ya = __shfl_up_sync(0xffffffffu, ia, o);
+                            if (lane >= o) ia += ya;
+                        }
+                        const double total_a = __shfl_sync(0xffffffffu, ia, 31);
+                        const double thr = 0.99 * total_a;
+                        double pre = ia - ta;
+                        int cnt = 0;
+#pragma unroll
+                        for (int i = 0; i < 32; i++) {
+                            cnt += (pre <= thr) ? 1 : 0;
+                            pre += (double)ab[i];
+                        }
                         cnt = mb_warp_sum(cnt);
                         // spectralRolloff.js:11-15: the loop only runs while ec > threshold
                         const int rbin = (total_a > thr) ? cnt - 1 : kM;
@@ -436,7 +438,8 @@ mb_warp2048_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
                     if (want_bark) {
                         float sp = 0.f;
                         if (lane < MB_NUM_BARK_BANDS) {
-                            const double bsum = bnd[S.bark_slot[lane + 1]] - bnd[S.bark_slot[lane]];
+                            double bsum = 0;
+                            for (int it = S.seg_ptr[lane]; it < S.seg_ptr[lane + 1]; it++) bsum += piece[S.seg_items[it]];
                             sp = powf((float)bsum, 0.23f);
                             if (mb_has(mask, MB_FEAT_LOUDNESS)) O.loudness_specific[g * MB_NUM_BARK_BANDS + lane] = sp;
                         }
@@ -452,19 +455,25 @@ mb_warp2048_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
                             stash[16][j] = sharp;
                         }
                     }
-                    // ---- mel energies from the prefix samples, log, DCT (mfcc.js:40-93)
+                    // ---- mel energies from the pieces, log, DCT (mfcc.js:40-93).  Lane s owns mel segment
+                    // [mel[s], mel[s+1]): rising weights (k - mel[s]) / width feed filter s, the
+                    // complement feeds filter s - 1.
                     if (want_mfcc) {
-                        float lgE = 0.f;
-                        if (lane < MB_NUM_MEL_FILTERS) {
-                            const double *bp = bnd + kMaxSlots, *bq = bnd + 2 * kMaxSlots;
-                            const int k0 = S.mel_slot[lane], k1 = S.mel_slot[lane + 1], k2 = S.mel_slot[lane + 2];
-                            const double p_up = bp[k1] - bp[k0], q_up = bq[k1] - bq[k0];
-                            const double p_dn = bp[k2] - bp[k1], q_dn = bq[k2] - bq[k1];
-                            const double rise = (q_up - (double)S.mel_edge[lane] * p_up) * (double)S.mel_inv[lane];
-                            const double rise2 = (q_dn - (double)S.mel_edge[lane + 1] * p_dn) * (double)S.mel_inv[lane + 1];
-                            const double e = rise + (p_dn - rise2);
-                            lgE = logf((float)e);
+                        double rise = 0, fall = 0;
+                        if (lane <= MB_NUM_MEL_FILTERS) {
+                            const int seg = MB_NUM_BARK_BANDS + lane, e0 = S.mel_edge[lane];
+                            double ps = 0, rs = 0;
+                            for (int it = S.seg_ptr[seg]; it < S.seg_ptr[seg + 1]; it++) {
+                                const int pc = S.seg_items[it];
+                                const double pp = piece[kPieces + pc];
+                                ps += pp;
+                                rs += piece[2 * kPieces + pc] + (double)(S.piece_edge[pc] - e0) * pp;
+                            }
+                            rise = rs * (double)S.mel_inv[lane];
+                            fall = ps - rise;
                         }
+                        const double fall_next = __shfl_down_sync(0xffffffffu, fall, 1);
+                        const float lgE = logf((float)(rise + fall_next));  // lanes >= 26 are not used below
                         float acc = 0.f;
 #pragma unroll
                         for (int f = 0; f < MB_NUM_MEL_FILTERS; f++) {

@@ -7,14 +7,27 @@
 #include "../../include/meyda_b200.h"
 
 // Tables of the warp-per-frame kernel (bufferSize 2048), one device copy per plan.
-#define MB_WARP_MAX_SLOTS 56
+//
+// Band sums are pure additions of "pieces".  The union of Bark limits and mel
+// edges cuts the N/2 bins into runs; in the blocked layout (lane L owns bins
+// [32 L, 32 L + 32)) a lane produces one piece per boundary inside it (bins
+// from that boundary to the next one or the lane's end) plus a head piece (its
+// bins before its first boundary).  Piece ids: boundary s -> s, head of lane L
+// -> MB_WARP_HEAD + L.  A Bark band or a mel segment is a short list of pieces.
+#define MB_WARP_MAX_SLOTS 64
+#define MB_WARP_HEAD 64
+#define MB_WARP_PIECES (MB_WARP_HEAD + 32)
+#define MB_WARP_SEGMENTS (MB_NUM_BARK_BANDS + MB_NUM_MEL_FILTERS + 1)  // 24 bands + 27 mel segments
+#define MB_WARP_MAX_ITEMS 256
 struct MbWarpTables {
     float2 tw32[32 * 32];          // exp(+2 pi i b c / 1024) at [c*32 + b]
     uint32_t lane_bmask[32];       // bit i: bin 32*lane + i is a Bark limit or a mel edge
     int lane_slot_base[32];        // number of such boundaries below bin 32*lane
-    int bark_slot[MB_NUM_BARK_BANDS + 1];   // boundary index of bbLimits[b]
-    int mel_slot[MB_NUM_MEL_FILTERS + 2];   // boundary index of each mel edge
-    int n_slots;                   // boundaries below M, plus one for the edge k == M
+    int lane_seg_start[32];        // largest boundary <= 32*lane
+    int piece_edge[MB_WARP_PIECES];            // the boundary a piece's k-weights are measured from
+    int seg_ptr[MB_WARP_SEGMENTS + 1];         // CSR: pieces of band b (0..23) / mel segment s (24 + s)
+    unsigned char seg_items[MB_WARP_MAX_ITEMS];
+    int n_slots;                   // boundaries below M
 };
 
 // Per-plan constants handed to kernels by value (__grid_constant__).  Tables

@@ -226,8 +226,66 @@ def _mu(i: int, amp64: np.ndarray) -> np.ndarray:
         return _seqsum(k * np.abs(amp64)) / _seqsum(amp64)
 
 
+def exact_spectrum(windowed: np.ndarray) -> np.ndarray:
+    """The transform jsfft approximates, in float64: conj(DFT)/sqrt(N)."""
+    w = np.atleast_2d(np.asarray(windowed)).astype(f64)
+    return np.conj(np.fft.fft(w, axis=1)) / np.sqrt(f64(w.shape[1]))
+
+
+NOISE_FEATURES = ["spectralCentroid", "spectralFlatness", "spectralSlope", "spectralSpread", "spectralSkewness",
+                  "spectralKurtosis", "loudness", "perceptualSpread", "perceptualSharpness", "mfcc"]
+
+
+def noise_band(signal: np.ndarray, bufferSize: int, hop: int | None = None, sr: float = 44100.0,
+               window: str = "hanning", draws: int = 8, seed: int = 20261018, chunk: int = 2048) -> dict:
+    """How far each spectral feature moves under spectral noise of the size of
+    the REFERENCE's own FFT rounding noise (test infrastructure for the
+    float32-FFT kernels, see tests/parity.py).
+
+    Per frame: sigma = rms_k |Z_jsfft[k] - Z_exact[k]| (the reference's actual
+    noise level on that frame).  The band of a feature is the largest of
+    |feat(jsfft) - feat(exact)| and |feat(exact + white noise of that sigma) -
+    feat(exact)| over `draws` draws.  Returns {feature: band array}; loudness ->
+    {'specific','total'}.
+    """
+    hop = bufferSize if hop is None else hop
+    frames_all = frame_signal(signal, bufferSize, hop)
+    rng = np.random.default_rng(seed)
+    parts = []
+    for c0 in range(0, max(len(frames_all), 1), chunk):
+        frames = frames_all[c0:c0 + chunk]
+        N = bufferSize
+        win = window_table(N, window)
+        windowed = (frames.astype(f64) * win.astype(f64)).astype(f32)
+        zx = exact_spectrum(windowed) if len(frames) else np.zeros((0, N), np.complex128)
+        rr, ri = fft_jsfft(windowed) if len(frames) else (np.zeros((0, N), f32),) * 2
+        with np.errstate(all="ignore"):
+            sigma = np.sqrt(np.mean(np.abs((rr.astype(f64) + 1j * ri.astype(f64)) - zx) ** 2, axis=1, keepdims=True))
+            base = extract_frames(frames, sr, window, NOISE_FEATURES, (zx.real, zx.imag))
+            ref = extract_frames(frames, sr, window, NOISE_FEATURES, (rr, ri))
+            band = _absdiff(ref, base)
+            for _ in range(draws):
+                nz = (rng.standard_normal(zx.shape) + 1j * rng.standard_normal(zx.shape)) * (sigma / np.sqrt(2.0))
+                zi = zx + nz
+                band = _maxdict(band, _absdiff(extract_frames(frames, sr, window, NOISE_FEATURES, (zi.real, zi.imag)), base))
+        parts.append(band)
+    return _concat(parts)
+
+
+def _absdiff(a: dict, b: dict) -> dict:
+    with np.errstate(all="ignore"):
+        return {k: ({s: np.nan_to_num(np.abs(a[k][s].astype(f64) - b[k][s].astype(f64)), nan=0.0, posinf=0.0)
+                     for s in a[k]} if isinstance(a[k], dict)
+                    else np.nan_to_num(np.abs(a[k].astype(f64) - b[k].astype(f64)), nan=0.0, posinf=0.0)) for k in a}
+
+
+def _maxdict(a: dict, b: dict) -> dict:
+    return {k: ({s: np.maximum(a[k][s], b[k][s]) for s in a[k]} if isinstance(a[k], dict) else np.maximum(a[k], b[k]))
+            for k in a}
+
+
 def extract_frames(frames: np.ndarray, sr: float = 44100.0, window: str = "hanning",
-                   features=None, fft: str = "jsfft") -> dict:
+                   features=None, fft="jsfft") -> dict:
     """All requested features for a [F, N] float32 batch of raw frames.
 
     Number features -> float64[F]; arrays -> float32[F, len];
@@ -249,10 +307,12 @@ def extract_frames(frames: np.ndarray, sr: float = 44100.0, window: str = "hanni
     with np.errstate(all="ignore"):
         win = window_table(N, window)
         windowed = (sig64 * win.astype(f64)).astype(f32)  # src/meyda.js:158-168
-        if fft == "jsfft":
+        if isinstance(fft, tuple):  # an explicit (real, imag) spectrum, see noise_band()
+            re, im = (np.asarray(a, dtype=f32) for a in fft)
+        elif fft == "jsfft":
             re, im = fft_jsfft(windowed)
         elif fft == "float64":
-            z = np.conj(np.fft.fft(windowed.astype(f64), axis=1)) / np.sqrt(f64(N))
+            z = exact_spectrum(windowed)
             re, im = z.real.astype(f32), z.imag.astype(f32)
         else:
             raise ValueError(fft)

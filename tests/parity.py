@@ -6,21 +6,23 @@ oracle.meyda_oracle.extract returns).  Tolerances are BASELINE.json's:
   spectralRolloff        exact bin (discrete output)
   spectra                |gpu-ref| <= 1e-4 * max_k|ref_frame|  and per-bin relative
                          <= 1e-4 on bins >= 1e-2 * peak (float32 FFT error is absolute,
-                         ~1e-7 * peak per bin: SURVEY.md section 7)
-  numbers, loudness, mfcc   1e-3 relative OR absolute (slope: relative only -- its
-                         magnitude is ~1e-7, an absolute 1e-3 would be vacuous)
+                         ~1e-8 * peak per bin: SURVEY.md section 7)
+  numbers, loudness, mfcc   1e-3 relative OR absolute (slope: relative, or 1e-13
+                         absolute -- its magnitude is ~1e-7, an absolute 1e-3 would
+                         be vacuous, and on a flat spectrum it is pure cancellation)
   NaN / +-Inf            same positions and signs
 
-Noise band (float32-FFT mode only).  Some features amplify the spectrum's
+Noise band (float32-FFT kernels only).  Some features amplify the spectrum's
 rounding-noise floor without bound: x^0.23 and ln(x) of a band that holds
 nothing but FFT rounding noise, or k^3/k^4-weighted sums over ~n empty bins of
 a pure tone.  On such frames the REFERENCE's own value is set by its float32
 per-stage rounding (lib/jsfft/fft.js:158-161), and no FFT that is not bit
-identical can land within 1e-3 of it.  `noise_ref` is the same oracle pipeline
-fed an exact (float64) FFT; a value may miss the tolerance only if it is
-within NOISE_BAND_FACTOR x |ref - noise_ref|, i.e. as close to the reference as
-the reference is to the mathematically exact answer.  Such values are counted
-and returned, never hidden; the exact-FFT mode (MB_FLAG_EXACT_FFT) must need none.
+identical can land within 1e-3 of it.  `noise_band` (oracle.noise_band) is, per
+value, how far the feature moves when the exact spectrum is perturbed by noise
+of the reference's own measured level; a value may miss the tolerance only if
+it is within NOISE_BAND_FACTOR x that band.  Such values are counted and
+returned, never hidden; the exact-FFT mode (MB_FLAG_EXACT_FFT) must need none
+and gets bit-identical spectra.
 """
 from __future__ import annotations
 
@@ -28,6 +30,7 @@ import numpy as np
 
 SPECTRA_TOL = 1e-4
 NUMBER_TOL = 1e-3
+SLOPE_ABS_TOL = 1e-13
 NOISE_BAND_FACTOR = 4.0
 
 NUMBER_FIELDS = {
@@ -54,24 +57,23 @@ def _special_match(g, r, name=""):
     return fin_r
 
 
-def assert_numbers(name, g, r, tol=NUMBER_TOL, relative_only=False, noise_ref=None):
-    """Returns the number of values that needed the noise band."""
+def assert_numbers(name, g, r, tol=NUMBER_TOL, abs_tol=None, band=None):
+    """Pass: relative error <= tol, or absolute error <= abs_tol (default tol),
+    or inside NOISE_BAND_FACTOR x band.  Returns how many values needed the band."""
     g = np.asarray(g, dtype=np.float64)
     r = np.asarray(r, dtype=np.float64)
     fin = _special_match(g, r, name)
     err = np.abs(np.where(fin, g - r, 0.0))
-    rel_ok = err <= tol * np.abs(np.where(fin, r, 1.0))
-    ok = rel_ok if relative_only else (rel_ok | (err <= tol))
+    ok = (err <= tol * np.abs(np.where(fin, r, 1.0))) | (err <= (tol if abs_tol is None else abs_tol))
     banded = 0
-    if noise_ref is not None and not ok.all():
-        nr = np.asarray(noise_ref, dtype=np.float64)
-        band = NOISE_BAND_FACTOR * np.abs(np.where(fin & np.isfinite(nr), r - nr, 0.0))
-        in_band = ~ok & (err <= band)
+    if band is not None and not ok.all():
+        in_band = ~ok & (err <= NOISE_BAND_FACTOR * np.asarray(band, dtype=np.float64))
         banded = int(in_band.sum())
         ok = ok | in_band
     bad = np.argwhere(~ok)
-    assert len(bad) == 0, "%s: %d values outside %g; worst err %g at %s (gpu=%s ref=%s)" % (
-        name, len(bad), tol, err[~ok].max(), bad[:3].tolist(), g[tuple(bad[0])], r[tuple(bad[0])])
+    assert len(bad) == 0, "%s: %d values outside %g; worst err %g at %s (gpu=%s ref=%s band=%s)" % (
+        name, len(bad), tol, err[~ok].max(), bad[:3].tolist(), g[tuple(bad[0])], r[tuple(bad[0])],
+        None if band is None else np.asarray(band)[tuple(bad[0])])
     return banded
 
 
@@ -101,7 +103,7 @@ def assert_bits(name, g, r):
         name, int((~same).sum()), same.size, np.argwhere(~same)[:3].tolist(), g[~same][:3], r[~same][:3])
 
 
-def compare_all(gpu: dict, ref: dict, N: int, sr: float = 44100.0, noise_ref: dict | None = None,
+def compare_all(gpu: dict, ref: dict, N: int, sr: float = 44100.0, noise_band: dict | None = None,
                 exact: bool = False) -> dict:
     """Compare whatever features `gpu` holds.  Returns {feature: values that
     needed the noise band}.  exact=True: spectra must be bit-identical and
@@ -109,7 +111,7 @@ def compare_all(gpu: dict, ref: dict, N: int, sr: float = 44100.0, noise_ref: di
     out = {}
     n = N // 2
     tol = 5e-6 if exact else NUMBER_TOL
-    nz = (lambda k: None) if (noise_ref is None or exact) else (lambda k: noise_ref[k])
+    nb = (lambda k: None) if (noise_band is None or exact) else (lambda k: noise_band.get(k))
     if "buffer" in gpu:
         assert_bits("buffer", gpu["buffer"], ref["buffer"])
     if "zcr" in gpu:
@@ -138,18 +140,18 @@ def compare_all(gpu: dict, ref: dict, N: int, sr: float = 44100.0, noise_ref: di
         gb = np.rint(gpu["spectral_rolloff"].astype(np.float64) / bin_hz)
         rb = np.rint(ref["spectralRolloff"] / bin_hz)
         assert np.array_equal(gb, rb), "rolloff bin mismatch at %s" % np.argwhere(gb != rb)[:5].tolist()
-        assert_numbers("spectralRolloff", gpu["spectral_rolloff"], ref["spectralRolloff"], tol=1e-6, relative_only=True)
+        assert_numbers("spectralRolloff", gpu["spectral_rolloff"], ref["spectralRolloff"], tol=1e-6, abs_tol=0.0)
     for field, feat in NUMBER_FIELDS.items():
         if field in gpu:
-            out[feat] = assert_numbers(feat, gpu[field], ref[feat], tol=tol, relative_only=(feat == "spectralSlope"),
-                                       noise_ref=nz(feat))
+            out[feat] = assert_numbers(feat, gpu[field], ref[feat], tol=tol,
+                                       abs_tol=SLOPE_ABS_TOL if feat == "spectralSlope" else None, band=nb(feat))
     if "loudness_specific" in gpu:
-        nl = None if nz("loudness") is None else nz("loudness")
+        nl = nb("loudness")
         out["loudness.specific"] = assert_numbers("loudness.specific", gpu["loudness_specific"],
                                                   ref["loudness"]["specific"], tol=tol,
-                                                  noise_ref=None if nl is None else nl["specific"])
+                                                  band=None if nl is None else nl["specific"])
         out["loudness.total"] = assert_numbers("loudness.total", gpu["loudness_total"], ref["loudness"]["total"],
-                                               tol=tol, noise_ref=None if nl is None else nl["total"])
+                                               tol=tol, band=None if nl is None else nl["total"])
     if "mfcc" in gpu:
-        out["mfcc"] = assert_numbers("mfcc", gpu["mfcc"], ref["mfcc"], tol=tol, noise_ref=nz("mfcc"))
+        out["mfcc"] = assert_numbers("mfcc", gpu["mfcc"], ref["mfcc"], tol=tol, band=nb("mfcc"))
     return {k: v for k, v in out.items() if v}
