@@ -24,6 +24,7 @@
 //
 // Reference path being replaced: src/meyda.js:69-91,104-114,158-168,
 // lib/jsfft/fft.js:123-208 and the extractor files under src/extractors/.
+#include <cstddef>
 #include <utility>
 
 #include "mb_device.cuh"
@@ -59,8 +60,10 @@ struct Smem {
     unsigned char seg_items[MB_WARP_MAX_ITEMS];
     unsigned long long bar[kWarps];
     float stash[kWarps][kStashRows][kChunk];
-    float slot[kWarps][kSlotFloats];  // 16-byte aligned by construction
+    alignas(128) float slot[kWarps][kSlotFloats];  // TMA destination / float4 reads: 16-byte alignment required
 };
+static_assert(offsetof(Smem, slot) % 128 == 0 && (kSlotFloats * 4) % 16 == 0, "warp slots must stay 16-byte aligned");
+static_assert(offsetof(Smem, twN) % 8 == 0 && offsetof(Smem, window) % 8 == 0, "float2 tables");
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -157,7 +160,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 mb_warp2048_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ MbClipTable T,
                    const float *__restrict__ samples, const __grid_constant__ mb_outputs O, const int64_t total_chunks) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    Smem &S = *reinterpret_cast<Smem *>(smem_raw);
+    Smem &S = *reinterpret_cast<Smem *>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t mask = P.mask;
     const MbWarpTables *__restrict__ WT = P.warp_tables;
