@@ -114,6 +114,7 @@ mb_generic_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ M
     float *amp = EXACT ? (xim + N) : reinterpret_cast<float *>(work + pidx(M) + 1);
 
     __shared__ double red_d[kWarps];
+    __shared__ float red_f[kWarps];
     __shared__ int red_i[kWarps];
     __shared__ double scan_d[kWarps];
     __shared__ double band_sum[MB_NUM_BARK_BANDS];
@@ -145,11 +146,14 @@ mb_generic_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ M
         S.rolloff_bin = M;
 
         // ---- time domain: buffer, energy, zcr; windowed frame into smem
+        int kscale = 0;  // fast mode: power-of-two rescale of frames that would under/overflow float32 squares
         {
             double e = 0;
             int z = 0;
+            float mxabs = 0.f;
             for (int i = tid; i < M; i += kThreads) {
                 const float x0 = __ldg(src + 2 * i), x1 = __ldg(src + 2 * i + 1);
+                mxabs = fmaxf(mxabs, fmaxf(fabsf(x0), fabsf(x1)));
                 if (want_time) {
                     e += (double)x0 * (double)x0 + (double)x1 * (double)x1;
                     z += ((x0 >= 0.f) != (x1 >= 0.f)) && (x0 == x0) && (x1 == x1);
@@ -179,7 +183,30 @@ mb_generic_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ M
                 S.energy = block_sum(e, red_d);
                 S.zcr = block_sum_int(z, red_i);
             }
+            if (!EXACT && want_spectrum) {
+                // the reference squares |Z| in float64; a frame far outside the float32 comfort zone is
+                // rescaled by an exact power of two and scaled back on the way out
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) mxabs = fmaxf(mxabs, __shfl_xor_sync(0xffffffffu, mxabs, o));
+                __syncthreads();
+                if (lane == 0) red_f[warp] = mxabs;
+                __syncthreads();
+                float mx = 0.f;
+#pragma unroll
+                for (int w = 0; w < kWarps; w++) mx = fmaxf(mx, red_f[w]);
+                if (mx > 0.f && mx < 3.0e38f && (mx < 0x1p-40f || mx > 0x1p40f)) {
+                    int ex;
+                    (void)frexpf(mx, &ex);
+                    kscale = max(-100, min(100, -ex));
+                    const float up = ldexpf(1.f, kscale);
+                    for (int i = tid; i < M; i += kThreads) {
+                        float2 t = work[pidx(i)];
+                        work[pidx(i)] = make_float2(t.x * up, t.y * up);
+                    }
+                }
+            }
         }
+        const float unscale = ldexpf(1.f, -kscale);
         __syncthreads();
 
         if (want_spectrum) {
@@ -246,17 +273,18 @@ mb_generic_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ M
                     if (k == 0) zi = 0.f;
                     if (mb_has(mask, MB_FEAT_COMPLEX_SPECTRUM)) {
                         float *re = O.complex_real + g * N, *im = O.complex_imag + g * N;
-                        re[k] = zr;
-                        im[k] = zi;
+                        const float zro = zr * unscale, zio = zi * unscale;
+                        re[k] = zro;
+                        im[k] = zio;
                         if (k > 0) {
-                            re[N - k] = zr;
-                            im[N - k] = -zi;
+                            re[N - k] = zro;
+                            im[N - k] = -zio;
                         } else {
-                            re[M] = (a.x - a.y) * sc;  // Nyquist bin: (E[0] - O[0]) / sqrt(N)
+                            re[M] = (a.x - a.y) * sc * unscale;  // Nyquist bin: (E[0] - O[0]) / sqrt(N)
                             im[M] = 0.f;
                         }
                     }
-                    const float av = sqrtf(zr * zr + zi * zi);
+                    const float av = sqrtf(zr * zr + zi * zi) * unscale;
                     amp[k] = av;
                     if (mb_has(mask, MB_FEAT_AMPLITUDE_SPECTRUM)) O.amplitude_spectrum[g * M + k] = av;
                     if (mb_has(mask, MB_FEAT_POWER_SPECTRUM)) O.power_spectrum[g * M + k] = __fmul_rn(av, av);

@@ -246,20 +246,53 @@ mb_warp2048_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
 
             // ---- 2. pass 1: window, time-domain sums, FFT32 over a for b = lane
             float2 v[32];
-            float esum = 0.f;
-            uint32_t sgn_e = 0, sgn_o = 0;  // bit a: sample 2(32a+lane) (+1) is >= 0
+            float esum;
+            uint32_t sgn_e, sgn_o;  // bit a: sample 2(32a+lane) (+1) is >= 0
+            uint32_t orbits;        // OR of every sample's bit pattern: bounds the largest exponent
+            auto pass1 = [&]() {
+                esum = 0.f;
+                sgn_e = sgn_o = orbits = 0;
 #pragma unroll
-            for (int a = 0; a < 32; a++) {
-                const float2 x = slot2[32 * a + lane];
-                const float2 w = reinterpret_cast<const float2 *>(S.window)[32 * a + lane];
-                if (want_time) {
-                    esum = fmaf(x.x, x.x, esum);
-                    esum = fmaf(x.y, x.y, esum);
-                    sgn_e |= (x.x >= 0.f) ? (1u << a) : 0u;
-                    sgn_o |= (x.y >= 0.f) ? (1u << a) : 0u;
+                for (int a = 0; a < 32; a++) {
+                    const float2 x = slot2[32 * a + lane];
+                    const float2 w = reinterpret_cast<const float2 *>(S.window)[32 * a + lane];
+                    orbits |= __float_as_uint(x.x) | __float_as_uint(x.y);
+                    if (want_time) {
+                        esum = fmaf(x.x, x.x, esum);
+                        esum = fmaf(x.y, x.y, esum);
+                        sgn_e |= (x.x >= 0.f) ? (1u << a) : 0u;
+                        sgn_o |= (x.y >= 0.f) ? (1u << a) : 0u;
+                    }
+                    v[a] = make_float2(__fmul_rn(x.x, w.x), __fmul_rn(x.y, w.y));
                 }
-                v[a] = make_float2(__fmul_rn(x.x, w.x), __fmul_rn(x.y, w.y));
+            };
+            pass1();
+            // Frames whose samples all sit below 2^-40 (or reach above 2^40) would under/overflow the
+            // float32 squares in |Z|; the reference squares in float64.  Such a frame (rare: decayed
+            // tails, digital silence) is rescaled by an exact power of two in place and redone; Z and
+            // |Z| are scaled back on the way out.
+            int kscale = 0;
+            {
+                const int e_or = (int)((__reduce_or_sync(0xffffffffu, orbits) >> 23) & 0xffu);
+                if (want_spectrum && (e_or < 127 - 40 || (e_or > 127 + 40 && e_or != 255))) {
+                    float mx = 0.f;
+                    for (int i = lane; i < kN; i += 32) mx = fmaxf(mx, fabsf(slot[i]));
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+                    if (mx > 0.f && mx < 3.0e38f && (mx < 0x1p-40f || mx > 0x1p40f)) {
+                        int e;
+                        (void)frexpf(mx, &e);
+                        kscale = max(-100, min(100, -e));
+                        if (want_buffer && lane == 0) bulk_store_wait_read();  // the slot is about to change
+                        __syncwarp();
+                        const float up = ldexpf(1.f, kscale);
+                        for (int i = lane; i < kN; i += 32) slot[i] *= up;
+                        __syncwarp();
+                        pass1();
+                    }
+                }
             }
+            const float unscale = ldexpf(1.f, -kscale);
             float energy = 0.f;
             int zcr = 0;
             if (want_time) {
@@ -286,8 +319,9 @@ mb_warp2048_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
                 }
             }
             if (lane == j) {
-                stash[0][j] = energy;
+                stash[0][j] = energy;  // of the rescaled samples when kscale != 0
                 stash[1][j] = __int_as_float(zcr);
+                stash[17][j] = __int_as_float(kscale);
             }
 
             if (want_spectrum) {
@@ -333,17 +367,18 @@ mb_warp2048_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
                     float zi = (ei + (w.x * oi + w.y * orr)) * sc;
                     if (d == 0 && lane == 0) zi = 0.f;
                     if (want_cs) {
-                        out_re[k] = zr;
-                        out_im[k] = zi;
+                        const float zro = zr * unscale, zio = zi * unscale;
+                        out_re[k] = zro;
+                        out_im[k] = zio;
                         if (d == 0 && lane == 0) {
-                            out_re[kM] = (a.x - a.y) * sc;  // Nyquist bin (E[0] - O[0]) / sqrt(N)
+                            out_re[kM] = (a.x - a.y) * sc * unscale;  // Nyquist bin (E[0] - O[0]) / sqrt(N)
                             out_im[kM] = 0.f;
                         } else {
-                            out_re[kN - k] = zr;
-                            out_im[kN - k] = -zi;
+                            out_re[kN - k] = zro;
+                            out_im[kN - k] = -zio;
                         }
                     }
-                    const float amp = sqrtf(fmaf(zr, zr, zi * zi));
+                    const float amp = sqrtf(fmaf(zr, zr, zi * zi)) * unscale;
                     av[d] = amp;
                     if (want_amp_out) out_amp[k] = amp;
                     if (want_pow_out) out_pow[k] = __fmul_rn(amp, amp);
@@ -493,7 +528,7 @@ mb_warp2048_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
         __syncwarp();
         if (lane < nfc) {
             MbFrameSums F;
-            F.energy = (double)stash[0][lane];
+            F.energy = ldexp((double)stash[0][lane], -2 * __float_as_int(stash[17][lane]));
             F.zcr = __float_as_int(stash[1][lane]);
             F.s0 = stash_get_d(stash, 2, lane);
             F.s1 = stash_get_d(stash, 4, lane);

@@ -237,13 +237,15 @@ NOISE_FEATURES = ["spectralCentroid", "spectralFlatness", "spectralSlope", "spec
 
 
 def noise_band(signal: np.ndarray, bufferSize: int, hop: int | None = None, sr: float = 44100.0,
-               window: str = "hanning", draws: int = 8, seed: int = 20261018, chunk: int = 2048) -> dict:
+               window: str = "hanning", draws: int = 8, seed: int = 20261018, chunk: int = 2048,
+               level: float = 2.0) -> dict:
     """How far each spectral feature moves under spectral noise of the size of
     the REFERENCE's own FFT rounding noise (test infrastructure for the
     float32-FFT kernels, see tests/parity.py).
 
-    Per frame: sigma = rms_k |Z_jsfft[k] - Z_exact[k]| (the reference's actual
-    noise level on that frame).  The band of a feature is the largest of
+    Per frame: sigma = level * rms_k |Z_jsfft[k] - Z_exact[k]| (the reference's
+    actual noise level on that frame; level 2 because the float32 kernels measure
+    1.6x the reference's noise (tools/fft_noise.py) and gpu - ref carries both).  The band of a feature is the largest of
     |feat(jsfft) - feat(exact)| and |feat(exact + white noise of that sigma) -
     feat(exact)| over `draws` draws.  Returns {feature: band array}; loudness ->
     {'specific','total'}.
@@ -260,7 +262,8 @@ def noise_band(signal: np.ndarray, bufferSize: int, hop: int | None = None, sr: 
         zx = exact_spectrum(windowed) if len(frames) else np.zeros((0, N), np.complex128)
         rr, ri = fft_jsfft(windowed) if len(frames) else (np.zeros((0, N), f32),) * 2
         with np.errstate(all="ignore"):
-            sigma = np.sqrt(np.mean(np.abs((rr.astype(f64) + 1j * ri.astype(f64)) - zx) ** 2, axis=1, keepdims=True))
+            sigma = level * np.sqrt(np.mean(np.abs((rr.astype(f64) + 1j * ri.astype(f64)) - zx) ** 2, axis=1,
+                                            keepdims=True))
             base = extract_frames(frames, sr, window, NOISE_FEATURES, (zx.real, zx.imag))
             ref = extract_frames(frames, sr, window, NOISE_FEATURES, (rr, ri))
             band = _absdiff(ref, base)
