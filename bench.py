@@ -267,7 +267,11 @@ def main():
     outs = {k: torch.empty(s, dtype=torch.int32 if d == np.int32 else torch.float32, device=dev)
             for k, (s, d) in shapes.items()}
     out_ptrs = {k: v.data_ptr() for k, v in outs.items()}
-    stream = torch.cuda.current_stream()
+    # A real (non-default) stream: the legacy default stream's handle is 0, which mb_plan_set_stream
+    # reads as "use the plan's own stream" -- the events below must sit on the launching stream.
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     plan.set_stream(stream.cuda_stream)
     waves = [(w0, min(my_clips, w0 + wave_clips)) for w0 in range(0, my_clips, wave_clips)]
     wave_tabs = [(np.arange(w0, w1, dtype=np.int64) * CLIP_LEN, np.full(w1 - w0, CLIP_LEN, np.int64))

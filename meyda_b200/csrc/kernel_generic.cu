@@ -270,7 +270,6 @@ mb_generic_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ M
                     const float2 w = __ldg(&P.twN[k]);
                     float zr = (er + (w.x * orr - w.y * oi)) * sc;
                     float zi = (ei + (w.x * oi + w.y * orr)) * sc;
-                    if (k == 0) zi = 0.f;
                     if (mb_has(mask, MB_FEAT_COMPLEX_SPECTRUM)) {
                         float *re = O.complex_real + g * N, *im = O.complex_imag + g * N;
                         const float zro = zr * unscale, zio = zi * unscale;
@@ -281,7 +280,7 @@ mb_generic_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ M
                             im[N - k] = -zio;
                         } else {
                             re[M] = (a.x - a.y) * sc * unscale;  // Nyquist bin: (E[0] - O[0]) / sqrt(N)
-                            im[M] = 0.f;
+                            im[M] = (a.x - a.y) * 0.f + 0.f;  // +0, or NaN when the frame holds a NaN
                         }
                     }
                     const float av = sqrtf(zr * zr + zi * zi) * unscale;

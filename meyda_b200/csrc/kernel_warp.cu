@@ -148,6 +148,13 @@ __host__ __device__ constexpr int brev5(int k) {
 
 __device__ __forceinline__ double warp_sum_d(double v) { return mb_warp_sum(v); }
 
+// sqrt.approx.f32: one MUFU, <= 1 ulp, subnormals handled (no .ftz); 0 -> 0, NaN -> NaN, inf -> inf.
+__device__ __forceinline__ float sqrt_approx(float x) {
+    float r;
+    asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
 __device__ __forceinline__ void stash_put_d(float (*st)[kChunk], int row, int col, double v) {
     st[row][col] = __int_as_float(__double2hiint(v));
     st[row + 1][col] = __int_as_float(__double2loint(v));
@@ -160,7 +167,10 @@ __global__ void __launch_bounds__(kThreads, 1)
 mb_warp2048_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ MbClipTable T,
                    const float *__restrict__ samples, const __grid_constant__ mb_outputs O, const int64_t total_chunks) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    Smem &S = *reinterpret_cast<Smem *>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+    // Keep the shared address space visible to the compiler (LDS/STS, not generic LD/ST): no integer round trip.
+    // The kernel has no static shared memory, so the dynamic window starts at the (1 KB aligned) window base.
+    Smem &S = *reinterpret_cast<Smem *>(smem_raw);
+    if (smem_u32(smem_raw) & 127u) __trap();
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t mask = P.mask;
     const MbWarpTables *__restrict__ WT = P.warp_tables;
@@ -365,20 +375,19 @@ mb_warp2048_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
                     const float orr = 0.5f * (a.y + b.y), oi = -0.5f * (a.x - b.x);
                     float zr = (er + (w.x * orr - w.y * oi)) * sc;
                     float zi = (ei + (w.x * oi + w.y * orr)) * sc;
-                    if (d == 0 && lane == 0) zi = 0.f;
                     if (want_cs) {
                         const float zro = zr * unscale, zio = zi * unscale;
                         out_re[k] = zro;
                         out_im[k] = zio;
                         if (d == 0 && lane == 0) {
                             out_re[kM] = (a.x - a.y) * sc * unscale;  // Nyquist bin (E[0] - O[0]) / sqrt(N)
-                            out_im[kM] = 0.f;
+                            out_im[kM] = (a.x - a.y) * 0.f + 0.f;  // +0, or NaN when the frame holds a NaN
                         } else {
                             out_re[kN - k] = zro;
                             out_im[kN - k] = -zio;
                         }
                     }
-                    const float amp = sqrtf(fmaf(zr, zr, zi * zi)) * unscale;
+                    const float amp = sqrt_approx(fmaf(zr, zr, zi * zi)) * unscale;
                     av[d] = amp;
                     if (want_amp_out) out_amp[k] = amp;
                     if (want_pow_out) out_pow[k] = __fmul_rn(amp, amp);

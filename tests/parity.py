@@ -31,7 +31,7 @@ import numpy as np
 SPECTRA_TOL = 1e-4
 NUMBER_TOL = 1e-3
 SLOPE_ABS_TOL = 1e-13
-NOISE_BAND_FACTOR = 4.0
+NOISE_BAND_FACTOR = 8.0
 
 NUMBER_FIELDS = {
     "rms": "rms", "energy": "energy", "spectral_centroid": "spectralCentroid",
