@@ -163,6 +163,8 @@ __device__ __forceinline__ double stash_get_d(float (*st)[kChunk], int row, int 
     return __hiloint2double(__float_as_int(st[row][col]), __float_as_int(st[row + 1][col]));
 }
 
+// kFull: every feature is requested (the headline configuration) -- the per-bin feature tests fold away.
+template <bool kFull>
 __global__ void __launch_bounds__(kThreads, 1)
 mb_warp2048_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ MbClipTable T,
                    const float *__restrict__ samples, const __grid_constant__ mb_outputs O, const int64_t total_chunks) {
@@ -177,7 +179,10 @@ mb_warp2048_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
 
     // ---- CTA-wide tables into shared memory (once per persistent CTA)
     for (int i = tid; i < kP * kP; i += kThreads) S.tw32[i] = WT->tw32[i];
-    for (int i = tid; i < kM; i += kThreads) S.twN[i] = P.twN[i];
+    {  // split twiddles pre-multiplied by 0.5 / sqrt(N): Z = h (E-part) + (h w) (O-part)
+        const float h = 0.5f * P.inv_sqrt_N;
+        for (int i = tid; i < kM; i += kThreads) S.twN[i] = make_float2(P.twN[i].x * h, P.twN[i].y * h);
+    }
     for (int i = tid; i < kN; i += kThreads) S.window[i] = P.window[i];
     for (int i = tid; i < MB_NUM_MFCC * MB_NUM_MEL_FILTERS; i += kThreads) S.dct[i] = P.dct[i];
     if (tid < MB_NUM_MEL_FILTERS + 2) {
@@ -194,24 +199,24 @@ mb_warp2048_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
     const int slot_base = WT->lane_slot_base[lane];  // index of the first of them
     const int seg_start = WT->lane_seg_start[lane];  // the boundary that opened the run this lane's first bin is in
 
-    const bool want_buffer = mb_has(mask, MB_FEAT_BUFFER);
-    const bool want_time = mask & (MB_FEATURE_BIT(MB_FEAT_RMS) | MB_FEATURE_BIT(MB_FEAT_ENERGY) | MB_FEATURE_BIT(MB_FEAT_ZCR));
-    const bool want_cs = mb_has(mask, MB_FEAT_COMPLEX_SPECTRUM);
-    const bool want_amp_out = mb_has(mask, MB_FEAT_AMPLITUDE_SPECTRUM);
-    const bool want_pow_out = mb_has(mask, MB_FEAT_POWER_SPECTRUM);
-    const bool want_moments =
-        mask & (MB_FEATURE_BIT(MB_FEAT_SPECTRAL_CENTROID) | MB_FEATURE_BIT(MB_FEAT_SPECTRAL_SPREAD) |
+    const bool want_buffer = kFull || mb_has(mask, MB_FEAT_BUFFER);
+    const bool want_time = kFull || (mask & (MB_FEATURE_BIT(MB_FEAT_RMS) | MB_FEATURE_BIT(MB_FEAT_ENERGY) | MB_FEATURE_BIT(MB_FEAT_ZCR)));
+    const bool want_cs = kFull || mb_has(mask, MB_FEAT_COMPLEX_SPECTRUM);
+    const bool want_amp_out = kFull || mb_has(mask, MB_FEAT_AMPLITUDE_SPECTRUM);
+    const bool want_pow_out = kFull || mb_has(mask, MB_FEAT_POWER_SPECTRUM);
+    const bool want_moments = kFull ||
+        (mask & (MB_FEATURE_BIT(MB_FEAT_SPECTRAL_CENTROID) | MB_FEATURE_BIT(MB_FEAT_SPECTRAL_SPREAD) |
                 MB_FEATURE_BIT(MB_FEAT_SPECTRAL_SKEWNESS) | MB_FEATURE_BIT(MB_FEAT_SPECTRAL_KURTOSIS) |
-                MB_FEATURE_BIT(MB_FEAT_SPECTRAL_FLATNESS) | MB_FEATURE_BIT(MB_FEAT_SPECTRAL_SLOPE));
-    const bool want_log = mb_has(mask, MB_FEAT_SPECTRAL_FLATNESS);
-    const bool want_rolloff = mb_has(mask, MB_FEAT_SPECTRAL_ROLLOFF);
-    const bool want_bark = mask & (MB_FEATURE_BIT(MB_FEAT_LOUDNESS) | MB_FEATURE_BIT(MB_FEAT_PERCEPTUAL_SPREAD) |
-                                   MB_FEATURE_BIT(MB_FEAT_PERCEPTUAL_SHARPNESS));
-    const bool want_mfcc = mb_has(mask, MB_FEAT_MFCC);
+                MB_FEATURE_BIT(MB_FEAT_SPECTRAL_FLATNESS) | MB_FEATURE_BIT(MB_FEAT_SPECTRAL_SLOPE)));
+    const bool want_log = kFull || mb_has(mask, MB_FEAT_SPECTRAL_FLATNESS);
+    const bool want_rolloff = kFull || mb_has(mask, MB_FEAT_SPECTRAL_ROLLOFF);
+    const bool want_bark = kFull || (mask & (MB_FEATURE_BIT(MB_FEAT_LOUDNESS) | MB_FEATURE_BIT(MB_FEAT_PERCEPTUAL_SPREAD) |
+                                             MB_FEATURE_BIT(MB_FEAT_PERCEPTUAL_SHARPNESS)));
+    const bool want_mfcc = kFull || mb_has(mask, MB_FEAT_MFCC);
     const bool want_blocked = want_rolloff || want_bark || want_mfcc;
     const uint32_t time_only = MB_FEATURE_BIT(MB_FEAT_RMS) | MB_FEATURE_BIT(MB_FEAT_ENERGY) |
                                MB_FEATURE_BIT(MB_FEAT_ZCR) | MB_FEATURE_BIT(MB_FEAT_BUFFER);
-    const bool want_spectrum = (mask & ~time_only) != 0;
+    const bool want_spectrum = kFull || (mask & ~time_only) != 0;
 
     float *slot = S.slot[warp];
     float2 *slot2 = reinterpret_cast<float2 *>(slot);
@@ -248,6 +253,9 @@ mb_warp2048_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 mbar_expect_tx(bar, kN * 4);
                 bulk_load(slot, src, kN * 4, bar);
+                // the samples the next frame adds, towards L2 while this frame is being worked on
+                if (j + 1 < nfc && g + 1 < clip_f1)
+                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src + kN), "r"((uint32_t)(P.hop * 4)) : "memory");
             }
             __syncwarp();
             mbar_wait(bar, parity);
@@ -362,7 +370,7 @@ mb_warp2048_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
                 float av[32];
                 double s0 = 0, s1 = 0, s2 = 0, s3 = 0, s4 = 0;
                 float lg = 0.f;
-                const float sc = P.inv_sqrt_N;
+                const float sc = P.inv_sqrt_N, hsc = 0.5f * sc;
                 float *out_re = O.complex_real + g * kN, *out_im = O.complex_imag + g * kN;
                 float *out_amp = O.amplitude_spectrum + g * kM, *out_pow = O.power_spectrum + g * kM;
 #pragma unroll
@@ -370,11 +378,10 @@ mb_warp2048_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
                     const int k = lane + 32 * d;
                     const float2 a = v[brev5(d)];
                     const float2 b = slot2[(kM - k) & (kM - 1)];
-                    const float2 w = S.twN[k];
-                    const float er = 0.5f * (a.x + b.x), ei = 0.5f * (a.y - b.y);
-                    const float orr = 0.5f * (a.y + b.y), oi = -0.5f * (a.x - b.x);
-                    float zr = (er + (w.x * orr - w.y * oi)) * sc;
-                    float zi = (ei + (w.x * oi + w.y * orr)) * sc;
+                    const float2 w = S.twN[k];  // h * exp(+2 pi i k / N), h = 0.5 / sqrt(N)
+                    const float sx = a.x + b.x, dx = a.x - b.x, sy = a.y + b.y, dy = a.y - b.y;
+                    const float zr = fmaf(hsc, sx, fmaf(w.x, sy, w.y * dx));
+                    const float zi = fmaf(hsc, dy, fmaf(w.y, sy, -(w.x * dx)));
                     if (want_cs) {
                         const float zro = zr * unscale, zio = zi * unscale;
                         out_re[k] = zro;
@@ -434,9 +441,11 @@ mb_warp2048_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
                     // One sequential pass per lane over its 32 bins: running sums of a, p = a^2 and
                     // (k - e) p since the last boundary e, flushed into a piece at every boundary.
                     // Only additions of non-negative terms: a silent band next to a loud bin keeps its value.
-                    double *piece = reinterpret_cast<double *>(slot + kPieceOff);  // [3][kPieces]: a, p, (k-e)p
-                    double ra = 0, rp = 0, rr = 0, ta = 0;
-                    double wd = (double)(32 * lane - seg_start);
+                    // (float32 is enough: at most 32 non-negative terms per piece, no subtraction anywhere.)
+                    float *piece = slot + kPieceOff;  // [3][kPieces]: a, p, (k-e)p
+                    float ra = 0.f, rp = 0.f, rr = 0.f;
+                    float wf = (float)(32 * lane - seg_start);
+                    double ta = 0;  // lane total of a in double: rolloff is a discrete output
                     int cur = MB_WARP_HEAD + lane, sidx = slot_base;
 #pragma unroll
                     for (int i = 0; i < 32; i++) {
@@ -444,22 +453,23 @@ mb_warp2048_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
                             piece[cur] = ra;
                             piece[kPieces + cur] = rp;
                             piece[2 * kPieces + cur] = rr;
-                            ta += ra;
                             cur = sidx++;
-                            ra = rp = rr = wd = 0;
+                            ra = rp = rr = wf = 0.f;
                         }
-                        const double pd = (double)__fmul_rn(ab[i], ab[i]);
-                        ra += (double)ab[i];
-                        rp += pd;
-                        rr = fma(wd, pd, rr);
-                        wd += 1.0;
+                        const float pf = __fmul_rn(ab[i], ab[i]);
+                        ra += ab[i];
+                        rp += pf;
+                        rr = fmaf(wf, pf, rr);
+                        wf += 1.0f;
+                        if (want_rolloff) ta += (double)ab[i];
                     }
                     piece[cur] = ra;
                     piece[kPieces + cur] = rp;
                     piece[2 * kPieces + cur] = rr;
-                    ta += ra;
                     if (want_rolloff) {
-                        // spectralRolloff.js: largest m with sum_{k<m} a[k] <= 0.99 sum a
+                        // spectralRolloff.js: the largest m with sum_{k<m} a[k] <= 0.99 sum a.  Lane totals are
+                        // scanned in double; the one lane the threshold falls into is then scanned bin by
+                        // bin by the whole warp (its 32 amplitudes, one per lane).
                         double ia = ta;
 #pragma unroll
                         for (int o = 1; o < 32; o <<= 1) {
@@ -468,16 +478,22 @@ mb_warp2048_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
                         }
                         const double total_a = __shfl_sync(0xffffffffu, ia, 31);
                         const double thr = 0.99 * total_a;
-                        double pre = ia - ta;
-                        int cnt = 0;
+                        // lanes whose first bin is still at or under the threshold form a prefix of the warp
+                        const uint32_t under = __ballot_sync(0xffffffffu, (ia - ta) <= thr);
+                        int rbin = kM;
+                        if (total_a > thr && under != 0u) {  // spectralRolloff.js:11-15: the loop runs only while ec > threshold
+                            const int lc = 31 - __clz(under);  // last lane starting at or under the threshold
+                            const double base = __shfl_sync(0xffffffffu, ia - ta, lc);
+                            double x = (double)slot[kAmpStride * lc + lane];  // bin 32 lc + lane
+                            double incl = x;
 #pragma unroll
-                        for (int i = 0; i < 32; i++) {
-                            cnt += (pre <= thr) ? 1 : 0;
-                            pre += (double)ab[i];
+                            for (int o = 1; o < 32; o <<= 1) {
+                                const double y = __shfl_up_sync(0xffffffffu, incl, o);
+                                if (lane >= o) incl += y;
+                            }
+                            const uint32_t ok = __ballot_sync(0xffffffffu, base + (incl - x) <= thr);  // P[32 lc + lane] <= thr
+                            rbin = 32 * lc + (31 - __clz(ok));
                         }
-                        cnt = mb_warp_sum(cnt);
-                        // spectralRolloff.js:11-15: the loop only runs while ec > threshold
-                        const int rbin = (total_a > thr) ? cnt - 1 : kM;
                         if (lane == j) stash[13][j] = __int_as_float(rbin);
                     }
                     __syncwarp();
@@ -485,9 +501,9 @@ mb_warp2048_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
                     if (want_bark) {
                         float sp = 0.f;
                         if (lane < MB_NUM_BARK_BANDS) {
-                            double bsum = 0;
+                            float bsum = 0.f;
                             for (int it = S.seg_ptr[lane]; it < S.seg_ptr[lane + 1]; it++) bsum += piece[S.seg_items[it]];
-                            sp = powf((float)bsum, 0.23f);
+                            sp = powf(bsum, 0.23f);
                             if (mb_has(mask, MB_FEAT_LOUDNESS)) O.loudness_specific[g * MB_NUM_BARK_BANDS + lane] = sp;
                         }
                         const float total = mb_warp_sum(sp);
@@ -506,21 +522,21 @@ mb_warp2048_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
                     // [mel[s], mel[s+1]): rising weights (k - mel[s]) / width feed filter s, the
                     // complement feeds filter s - 1.
                     if (want_mfcc) {
-                        double rise = 0, fall = 0;
+                        float rise = 0.f, fall = 0.f;
                         if (lane <= MB_NUM_MEL_FILTERS) {
                             const int seg = MB_NUM_BARK_BANDS + lane, e0 = S.mel_edge[lane];
-                            double ps = 0, rs = 0;
+                            const float inv = S.mel_inv[lane];
                             for (int it = S.seg_ptr[seg]; it < S.seg_ptr[seg + 1]; it++) {
                                 const int pc = S.seg_items[it];
-                                const double pp = piece[kPieces + pc];
-                                ps += pp;
-                                rs += piece[2 * kPieces + pc] + (double)(S.piece_edge[pc] - e0) * pp;
+                                const float pp = piece[kPieces + pc];
+                                // sum (k - e0) p over the piece, then its complement (e1 - k) p: both non-negative
+                                const float up = fmaf((float)(S.piece_edge[pc] - e0), pp, piece[2 * kPieces + pc]) * inv;
+                                rise += up;
+                                fall += fmaxf(pp - up, 0.f);
                             }
-                            rise = rs * (double)S.mel_inv[lane];
-                            fall = ps - rise;
                         }
-                        const double fall_next = __shfl_down_sync(0xffffffffu, fall, 1);
-                        const float lgE = logf((float)(rise + fall_next));  // lanes >= 26 are not used below
+                        const float fall_next = __shfl_down_sync(0xffffffffu, fall, 1);
+                        const float lgE = logf(rise + fall_next);  // lanes >= 26 are not used below
                         float acc = 0.f;
 #pragma unroll
                         for (int f = 0; f < MB_NUM_MEL_FILTERS; f++) {
@@ -570,13 +586,16 @@ size_t mb_warp2048_smem_bytes() { return sizeof(Smem) + 128; }
 cudaError_t mb_launch_warp2048(const MbDevPlan &P, const MbClipTable &T, const float *samples, const mb_outputs &O,
                                int num_sms, cudaStream_t stream) {
     const size_t smem = mb_warp2048_smem_bytes();
-    cudaError_t e = cudaFuncSetAttribute(mb_warp2048_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const bool full = (P.mask & MB_ALL_FEATURES) == MB_ALL_FEATURES;
+    cudaError_t e = cudaFuncSetAttribute(full ? mb_warp2048_kernel<true> : mb_warp2048_kernel<false>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const int64_t chunks = (T.total_frames + kChunk - 1) / kChunk;
     int64_t grid = (chunks + kWarps - 1) / kWarps;
     if (grid > num_sms) grid = num_sms;
     if (grid < 1) return cudaSuccess;
     (void)cudaGetLastError();
-    mb_warp2048_kernel<<<(unsigned)grid, kThreads, smem, stream>>>(P, T, samples, O, chunks);
+    if (full) mb_warp2048_kernel<true><<<(unsigned)grid, kThreads, smem, stream>>>(P, T, samples, O, chunks);
+    else mb_warp2048_kernel<false><<<(unsigned)grid, kThreads, smem, stream>>>(P, T, samples, O, chunks);
     return cudaGetLastError();
 }
