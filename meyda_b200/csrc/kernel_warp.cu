@@ -148,10 +148,17 @@ __host__ __device__ constexpr int brev5(int k) {
 
 __device__ __forceinline__ double warp_sum_d(double v) { return mb_warp_sum(v); }
 
-// sqrt.approx.f32: one MUFU, <= 1 ulp, subnormals handled (no .ftz); 0 -> 0, NaN -> NaN, inf -> inf.
+// One MUFU each, <= 1 ulp.  .ftz: the arguments are |Z|^2 and |Z| of a frame whose samples were brought
+// into [2^-40, 2^40] (see kscale), so a subnormal argument is 2^-86 below the frame's scale: flushing it
+// to zero changes nothing that float32 could have resolved.  0 -> 0 / -inf, NaN -> NaN.
 __device__ __forceinline__ float sqrt_approx(float x) {
     float r;
-    asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float log2_approx(float x) {
+    float r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 }
 
@@ -343,29 +350,36 @@ mb_warp2048_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
             }
 
             if (want_spectrum) {
-                fft32(v);
-                __syncwarp();  // all lanes have read their raw samples: the slot becomes the transpose buffer
-                if (want_buffer && lane == 0) bulk_store_wait_read();
-                __syncwarp();
+                // Both FFT passes run through ONE copy of the 32-point register FFT (a two-trip loop, not
+                // unrolled): the straight-line code of a frame is ~70 KB and instruction fetch matters.
+#pragma unroll 1
+                for (int pass = 0; pass < 2; pass++) {
+                    if (pass == 1) {
+                        // ---- pass 2: FFT32 over b for c = lane -> X[lane + 32 d] in v[brev5(d)]
 #pragma unroll
-                for (int c = 0; c < 32; c++) {
-                    float2 y = v[brev5(c)];
-                    if (c > 0) {
-                        const float2 t = S.tw32[c * 32 + lane];
-                        y = make_float2(y.x * t.x - y.y * t.y, y.x * t.y + y.y * t.x);
+                        for (int b = 0; b < 32; b++) v[b] = slot2[lane * kRow + b];
                     }
-                    slot2[c * kRow + lane] = y;
+                    fft32(v);
+                    __syncwarp();  // pass 0: all lanes have read their raw samples, the slot becomes the transpose buffer
+                    if (pass == 0) {
+                        if (want_buffer && lane == 0) bulk_store_wait_read();
+                        __syncwarp();
+#pragma unroll
+                        for (int c = 0; c < 32; c++) {
+                            float2 y = v[brev5(c)];
+                            if (c > 0) {
+                                const float2 t = S.tw32[c * 32 + lane];
+                                y = make_float2(y.x * t.x - y.y * t.y, y.x * t.y + y.y * t.x);
+                            }
+                            slot2[c * kRow + lane] = y;
+                        }
+                    } else {
+                        // ---- 3. real-FFT split.  X in natural order through the slot so that lane can fetch X[M-k].
+#pragma unroll
+                        for (int d = 0; d < 32; d++) slot2[lane + 32 * d] = v[brev5(d)];
+                    }
+                    __syncwarp();
                 }
-                __syncwarp();
-                // ---- pass 2: FFT32 over b for c = lane -> X[lane + 32 d] in v[brev5(d)]
-#pragma unroll
-                for (int b = 0; b < 32; b++) v[b] = slot2[lane * kRow + b];
-                fft32(v);
-                __syncwarp();
-                // ---- 3. real-FFT split.  X in natural order through the slot so that lane can fetch X[M-k].
-#pragma unroll
-                for (int d = 0; d < 32; d++) slot2[lane + 32 * d] = v[brev5(d)];
-                __syncwarp();
 
                 float av[32];
                 double s0 = 0, s1 = 0, s2 = 0, s3 = 0, s4 = 0;
@@ -394,7 +408,8 @@ mb_warp2048_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
                             out_im[kN - k] = -zio;
                         }
                     }
-                    const float amp = sqrt_approx(fmaf(zr, zr, zi * zi)) * unscale;
+                    const float amp_s = sqrt_approx(fmaf(zr, zr, zi * zi));  // in the frame's rescaled units
+                    const float amp = amp_s * unscale;
                     av[d] = amp;
                     if (want_amp_out) out_amp[k] = amp;
                     if (want_pow_out) out_pow[k] = __fmul_rn(amp, amp);
@@ -406,7 +421,7 @@ mb_warp2048_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
                         t *= kd; s2 += t;
                         t *= kd; s3 += t;
                         t *= kd; s4 += t;
-                        if (want_log) lg += __log2f(amp);
+                        if (want_log) lg += log2_approx(amp_s);
                     }
                 }
                 if (want_moments) {
@@ -422,7 +437,7 @@ mb_warp2048_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
                         stash_put_d(stash, 6, j, s2);
                         stash_put_d(stash, 8, j, s3);
                         stash_put_d(stash, 10, j, s4);
-                        stash[12][j] = lg;
+                        stash[12][j] = lg - (float)(kM * kscale);  // sum log2 |Z| = sum log2 (2^k |Z|) - n k
                     }
                 }
 
