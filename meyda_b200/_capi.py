@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_lib", "libmeyda_b200.so")
+# MEYDA_B200_LIB points at an alternative build of the same library (kernel tuning experiments).
+LIB_PATH = os.environ.get("MEYDA_B200_LIB") or os.path.join(_HERE, "_lib", "libmeyda_b200.so")
 
 MB_OK = 0
 MB_ERR_INVALID_ARG, MB_ERR_NOT_POWER_OF_TWO, MB_ERR_UNSUPPORTED, MB_ERR_CUDA = 1, 2, 3, 4

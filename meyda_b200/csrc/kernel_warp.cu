@@ -35,7 +35,10 @@ namespace {
 constexpr int kP = 32;             // points per lane per pass
 constexpr int kM = kP * kP;        // 1024 complex points
 constexpr int kN = 2 * kM;         // bufferSize 2048
-constexpr int kWarps = 16;
+#ifndef MB_WARPS
+#define MB_WARPS 16
+#endif
+constexpr int kWarps = MB_WARPS;  // warps per persistent CTA: 128 registers each at 16
 constexpr int kThreads = kWarps * 32;
 constexpr int kRow = kP + 1;                  // float2 stride of a transpose row
 constexpr int kSlotFloats = 2 * kP * kRow;    // 2112 floats = 8448 B per warp
@@ -85,18 +88,34 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t pari
         : "memory");
 }
 // TMA bulk copies (1-D): global -> shared with mbarrier completion, shared -> global as a bulk group.
-__device__ __forceinline__ void bulk_load(void *dst_smem, const void *src_gmem, uint32_t bytes, unsigned long long *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_u32(dst_smem)),
-                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
+// L2 policies: a frame's samples are read again by the next three frames (hop 512 of 2048), while the
+// output stream is written once and is 16x larger -- keep the former, let the latter go first.
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
 }
-__device__ __forceinline__ void bulk_store(void *dst_gmem, const void *src_smem, uint32_t bytes) {
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)),
-                 "r"(bytes)
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void bulk_load(void *dst_smem, const void *src_gmem, uint32_t bytes, unsigned long long *bar,
+                                          uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+            smem_u32(dst_smem)),
+        "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_store(void *dst_gmem, const void *src_smem, uint32_t bytes, uint64_t policy) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(dst_gmem),
+                 "r"(smem_u32(src_smem)), "r"(bytes), "l"(policy)
                  : "memory");
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
+// streaming store: written once, never read back by this kernel
+__device__ __forceinline__ void st_stream(float *p, float v) { __stcs(p, v); }
 __device__ __forceinline__ void bulk_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
@@ -230,6 +249,7 @@ mb_warp2048_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
     float(*stash)[kChunk] = S.stash[warp];
     unsigned long long *bar = &S.bar[warp];
     uint32_t parity = 0;
+    const uint64_t pol_keep = l2_policy_evict_last(), pol_stream = l2_policy_evict_first();
 
     int64_t clip = 0, clip_f0 = 0, clip_f1 = 0;  // cached clip of the previous frame: frames [clip_f0, clip_f1)
     if (T.n_clips > 0) clip_f1 = T.frame_start[1];
@@ -254,12 +274,15 @@ mb_warp2048_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
 
             // ---- 1. frame into the warp's slot (TMA), buffer out of it (TMA)
             __syncwarp();  // every lane is done with the slot's previous contents
+#ifdef MB_EXP_NOWAIT  // timing experiment only (results are garbage): how much does the frame load + wait cost?
+            if (j == 0) {
+#endif
             if (lane == 0) {
                 bulk_store_wait_read();  // an earlier frame's `buffer` store has finished reading the slot
                 // generic-proxy accesses to the slot are ordered before the async-proxy write that follows
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 mbar_expect_tx(bar, kN * 4);
-                bulk_load(slot, src, kN * 4, bar);
+                bulk_load(slot, src, kN * 4, bar, pol_keep);
                 // the samples the next frame adds, towards L2 while this frame is being worked on
                 if (j + 1 < nfc && g + 1 < clip_f1)
                     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src + kN), "r"((uint32_t)(P.hop * 4)) : "memory");
@@ -267,7 +290,15 @@ mb_warp2048_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
             __syncwarp();
             mbar_wait(bar, parity);
             parity ^= 1;
-            if (want_buffer && lane == 0) bulk_store(O.buffer + g * kN, slot, kN * 4);
+#ifdef MB_EXP_NOWAIT
+            }
+#endif
+#ifdef MB_EXP_NOSTORE  // timing experiment only: all the arithmetic, none of the spectra/buffer traffic
+            const bool exp_store = (total_chunks < 0);
+#else
+            const bool exp_store = true;
+#endif
+            if (want_buffer && exp_store && lane == 0) bulk_store(O.buffer + g * kN, slot, kN * 4, pol_stream);
 
             // ---- 2. pass 1: window, time-domain sums, FFT32 over a for b = lane
             float2 v[32];
@@ -396,23 +427,23 @@ mb_warp2048_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
                     const float sx = a.x + b.x, dx = a.x - b.x, sy = a.y + b.y, dy = a.y - b.y;
                     const float zr = fmaf(hsc, sx, fmaf(w.x, sy, w.y * dx));
                     const float zi = fmaf(hsc, dy, fmaf(w.y, sy, -(w.x * dx)));
-                    if (want_cs) {
+                    if (want_cs && exp_store) {
                         const float zro = zr * unscale, zio = zi * unscale;
-                        out_re[k] = zro;
-                        out_im[k] = zio;
+                        st_stream(out_re + k, zro);
+                        st_stream(out_im + k, zio);
                         if (d == 0 && lane == 0) {
-                            out_re[kM] = (a.x - a.y) * sc * unscale;  // Nyquist bin (E[0] - O[0]) / sqrt(N)
-                            out_im[kM] = (a.x - a.y) * 0.f + 0.f;  // +0, or NaN when the frame holds a NaN
+                            st_stream(out_re + kM, (a.x - a.y) * sc * unscale);  // Nyquist bin (E[0] - O[0]) / sqrt(N)
+                            st_stream(out_im + kM, (a.x - a.y) * 0.f + 0.f);     // +0, or NaN when the frame holds a NaN
                         } else {
-                            out_re[kN - k] = zro;
-                            out_im[kN - k] = -zio;
+                            st_stream(out_re + (kN - k), zro);
+                            st_stream(out_im + (kN - k), -zio);
                         }
                     }
                     const float amp_s = sqrt_approx(fmaf(zr, zr, zi * zi));  // in the frame's rescaled units
                     const float amp = amp_s * unscale;
                     av[d] = amp;
-                    if (want_amp_out) out_amp[k] = amp;
-                    if (want_pow_out) out_pow[k] = __fmul_rn(amp, amp);
+                    if (want_amp_out && exp_store) st_stream(out_amp + k, amp);
+                    if (want_pow_out && exp_store) st_stream(out_pow + k, __fmul_rn(amp, amp));
                     if (want_moments) {
                         const double ad = (double)amp, kd = (double)k;
                         double t = ad * kd;
