@@ -416,8 +416,10 @@ mb_warp2048_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
                 double s0 = 0, s1 = 0, s2 = 0, s3 = 0, s4 = 0;
                 float lg = 0.f;
                 const float sc = P.inv_sqrt_N, hsc = 0.5f * sc;
-                float *out_re = O.complex_real + g * kN, *out_im = O.complex_imag + g * kN;
-                float *out_amp = O.amplitude_spectrum + g * kM, *out_pow = O.power_spectrum + g * kM;
+                // per-lane row pointers: every store below is base + a compile-time offset (32 d floats)
+                float *out_re = O.complex_real + g * kN + lane, *out_im = O.complex_imag + g * kN + lane;
+                float *mir_re = O.complex_real + g * kN + (kN - lane), *mir_im = O.complex_imag + g * kN + (kN - lane);
+                float *out_amp = O.amplitude_spectrum + g * kM + lane, *out_pow = O.power_spectrum + g * kM + lane;
 #pragma unroll
                 for (int d = 0; d < 32; d++) {
                     const int k = lane + 32 * d;
@@ -429,21 +431,21 @@ mb_warp2048_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
                     const float zi = fmaf(hsc, dy, fmaf(w.y, sy, -(w.x * dx)));
                     if (want_cs && exp_store) {
                         const float zro = zr * unscale, zio = zi * unscale;
-                        st_stream(out_re + k, zro);
-                        st_stream(out_im + k, zio);
+                        st_stream(out_re + 32 * d, zro);
+                        st_stream(out_im + 32 * d, zio);
                         if (d == 0 && lane == 0) {
                             st_stream(out_re + kM, (a.x - a.y) * sc * unscale);  // Nyquist bin (E[0] - O[0]) / sqrt(N)
                             st_stream(out_im + kM, (a.x - a.y) * 0.f + 0.f);     // +0, or NaN when the frame holds a NaN
                         } else {
-                            st_stream(out_re + (kN - k), zro);
-                            st_stream(out_im + (kN - k), -zio);
+                            st_stream(mir_re - 32 * d, zro);
+                            st_stream(mir_im - 32 * d, -zio);
                         }
                     }
                     const float amp_s = sqrt_approx(fmaf(zr, zr, zi * zi));  // in the frame's rescaled units
                     const float amp = amp_s * unscale;
                     av[d] = amp;
-                    if (want_amp_out && exp_store) st_stream(out_amp + k, amp);
-                    if (want_pow_out && exp_store) st_stream(out_pow + k, __fmul_rn(amp, amp));
+                    if (want_amp_out && exp_store) st_stream(out_amp + 32 * d, amp);
+                    if (want_pow_out && exp_store) st_stream(out_pow + 32 * d, __fmul_rn(amp, amp));
                     if (want_moments) {
                         const double ad = (double)amp, kd = (double)k;
                         double t = ad * kd;
