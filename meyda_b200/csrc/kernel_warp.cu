@@ -48,7 +48,7 @@ constexpr int kPieces = MB_WARP_PIECES;       // 96: 64 boundary pieces + 32 lan
 constexpr int kStashRows = 18;                // floats per frame in the scalar stash
 constexpr int kChunk = 32;                    // frames per work unit
 
-static_assert(kPieceOff * 4 + 3 * kPieces * 8 <= kSlotFloats * 4, "band pieces must fit the warp slot");
+static_assert(kPieceOff * 4 + kPieces * 16 <= kSlotFloats * 4, "band pieces must fit the warp slot");
 
 // ---- shared memory carve-up (dynamic)
 struct Smem {
@@ -395,11 +395,13 @@ mb_warp2048_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
                     if (pass == 0) {
                         if (want_buffer && lane == 0) bulk_store_wait_read();
                         __syncwarp();
+                        float2 t_nx = S.tw32[32 + lane];
 #pragma unroll
                         for (int c = 0; c < 32; c++) {
                             float2 y = v[brev5(c)];
                             if (c > 0) {
-                                const float2 t = S.tw32[c * 32 + lane];
+                                const float2 t = t_nx;
+                                if (c + 1 < 32) t_nx = S.tw32[(c + 1) * 32 + lane];
                                 y = make_float2(y.x * t.x - y.y * t.y, y.x * t.y + y.y * t.x);
                             }
                             slot2[c * kRow + lane] = y;
@@ -408,11 +410,15 @@ mb_warp2048_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
                         // ---- 3. real-FFT split.  X in natural order through the slot so that lane can fetch X[M-k].
 #pragma unroll
                         for (int d = 0; d < 32; d++) slot2[lane + 32 * d] = v[brev5(d)];
+                        if (lane == 0) slot2[kM] = v[0];  // X[M] := X[0], so that X[M-k] is slot2[kM - k] for every k
                     }
                     __syncwarp();
                 }
 
                 float av[32];
+                const float2 *xm = slot2 + (kM - lane);
+                const float2 *twp = S.twN + lane;
+                float2 b_nx = xm[0], w_nx = twp[0];  // operands of bin d are fetched during bin d-1
                 double s0 = 0, s1 = 0, s2 = 0, s3 = 0, s4 = 0;
                 float lg = 0.f;
                 const float sc = P.inv_sqrt_N, hsc = 0.5f * sc;
@@ -424,8 +430,12 @@ mb_warp2048_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
                 for (int d = 0; d < 32; d++) {
                     const int k = lane + 32 * d;
                     const float2 a = v[brev5(d)];
-                    const float2 b = slot2[(kM - k) & (kM - 1)];
-                    const float2 w = S.twN[k];  // h * exp(+2 pi i k / N), h = 0.5 / sqrt(N)
+                    const float2 b = b_nx;  // X[M-k]
+                    const float2 w = w_nx;  // h * exp(+2 pi i k / N), h = 0.5 / sqrt(N)
+                    if (d + 1 < 32) {
+                        b_nx = xm[-32 * (d + 1)];
+                        w_nx = twp[32 * (d + 1)];
+                    }
                     const float sx = a.x + b.x, dx = a.x - b.x, sy = a.y + b.y, dy = a.y - b.y;
                     const float zr = fmaf(hsc, sx, fmaf(w.x, sy, w.y * dx));
                     const float zi = fmaf(hsc, dy, fmaf(w.y, sy, -(w.x * dx)));
@@ -490,7 +500,7 @@ mb_warp2048_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
                     // (k - e) p since the last boundary e, flushed into a piece at every boundary.
                     // Only additions of non-negative terms: a silent band next to a loud bin keeps its value.
                     // (float32 is enough: at most 32 non-negative terms per piece, no subtraction anywhere.)
-                    float *piece = slot + kPieceOff;  // [3][kPieces]: a, p, (k-e)p
+                    float4 *piece = reinterpret_cast<float4 *>(slot + kPieceOff);  // [kPieces]: {sum a, sum p, sum (k-e) p, -}
                     float ra = 0.f, rp = 0.f, rr = 0.f;
                     float wf = (float)(32 * lane - seg_start);
                     double ta = 0;  // lane total of a in double: rolloff is a discrete output
@@ -498,9 +508,7 @@ mb_warp2048_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
 #pragma unroll
                     for (int i = 0; i < 32; i++) {
                         if ((bmask >> i) & 1u) {
-                            piece[cur] = ra;
-                            piece[kPieces + cur] = rp;
-                            piece[2 * kPieces + cur] = rr;
+                            piece[cur] = make_float4(ra, rp, rr, 0.f);
                             cur = sidx++;
                             ra = rp = rr = wf = 0.f;
                         }
@@ -511,9 +519,7 @@ mb_warp2048_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
                         wf += 1.0f;
                         if (want_rolloff) ta += (double)ab[i];
                     }
-                    piece[cur] = ra;
-                    piece[kPieces + cur] = rp;
-                    piece[2 * kPieces + cur] = rr;
+                    piece[cur] = make_float4(ra, rp, rr, 0.f);
                     if (want_rolloff) {
                         // spectralRolloff.js: the largest m with sum_{k<m} a[k] <= 0.99 sum a.  Lane totals are
                         // scanned in double; the one lane the threshold falls into is then scanned bin by
@@ -550,7 +556,7 @@ mb_warp2048_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
                         float sp = 0.f;
                         if (lane < MB_NUM_BARK_BANDS) {
                             float bsum = 0.f;
-                            for (int it = S.seg_ptr[lane]; it < S.seg_ptr[lane + 1]; it++) bsum += piece[S.seg_items[it]];
+                            for (int it = S.seg_ptr[lane]; it < S.seg_ptr[lane + 1]; it++) bsum += piece[S.seg_items[it]].x;
                             sp = powf(bsum, 0.23f);
                             if (mb_has(mask, MB_FEAT_LOUDNESS)) O.loudness_specific[g * MB_NUM_BARK_BANDS + lane] = sp;
                         }
@@ -576,9 +582,10 @@ mb_warp2048_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
                             const float inv = S.mel_inv[lane];
                             for (int it = S.seg_ptr[seg]; it < S.seg_ptr[seg + 1]; it++) {
                                 const int pc = S.seg_items[it];
-                                const float pp = piece[kPieces + pc];
+                                const float4 pv = piece[pc];
+                                const float pp = pv.y;
                                 // sum (k - e0) p over the piece, then its complement (e1 - k) p: both non-negative
-                                const float up = fmaf((float)(S.piece_edge[pc] - e0), pp, piece[2 * kPieces + pc]) * inv;
+                                const float up = fmaf((float)(S.piece_edge[pc] - e0), pp, pv.z) * inv;
                                 rise += up;
                                 fall += fmaxf(pp - up, 0.f);
                             }
