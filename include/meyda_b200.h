@@ -108,10 +108,14 @@ enum {
      * radix-2, float64 butterflies with the recurrence twiddles, float32 store
      * per stage): complexSpectrum / amplitudeSpectrum / powerSpectrum come out
      * bit for bit and every derived feature follows.  Slower than the default
-     * float32 FFT; bufferSize <= MB_MAX_EXACT_BUFFER_SIZE. */
-    MB_FLAG_EXACT_FFT = 1u << 1
+     * float32 FFT.  Above 16384 samples the N-point complex frame no longer fits
+     * one CTA and a 2-CTA thread-block cluster holds it (DSMEM exchange). */
+    MB_FLAG_EXACT_FFT = 1u << 1,
+    /* With MB_FLAG_EXACT_FFT: use the 2-CTA cluster kernel at every bufferSize >= 64
+     * (it is automatic above 16384). */
+    MB_FLAG_CLUSTER_FFT = 1u << 2
 };
-#define MB_MAX_EXACT_BUFFER_SIZE 16384
+#define MB_MAX_EXACT_BUFFER_SIZE 32768
 
 typedef struct mb_plan mb_plan;     /* opaque: tables, stream, scratch of one (device, bufferSize, hop, ...) */
 typedef struct mb_stream mb_stream; /* opaque: stateful buffer-by-buffer extractor */

@@ -17,6 +17,7 @@ MB_MEM_HOST, MB_MEM_DEVICE = 0, 1
 MB_WINDOW = {"hanning": 0, "hamming": 1}
 MB_FLAG_GENERIC_KERNEL = 1
 MB_FLAG_EXACT_FFT = 2
+MB_FLAG_CLUSTER_FFT = 4
 MB_NUM_FEATURES = 18
 
 # every symbol include/meyda_b200.h declares

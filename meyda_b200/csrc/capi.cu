@@ -112,6 +112,7 @@ struct mb_plan {
     double2 *d_tw_exact = nullptr;
     MbWarpTables *d_warp_tables = nullptr;
     bool has_warp_kernel = false;
+    bool use_cluster = false;
     int64_t launches_warp = 0, launches_generic = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr;
     // device-memory calls: clip tables staged through pinned memory
@@ -264,7 +265,10 @@ mb_status launch(mb_plan *p, const int64_t *d_off, const int64_t *d_frame_start,
     MbClipTable T{d_off, d_frame_start, n, total_frames};
     const bool tma_ok = aligned && ((uintptr_t)d_samples % 16 == 0) && ((uintptr_t)d_out.buffer % 16 == 0) &&
                         (p->hop % 4 == 0);
-    if (p->has_warp_kernel && tma_ok) {
+    if (p->use_cluster) {
+        MB_CUDA(mb_launch_exact_cluster(p->dev, T, d_samples, d_out, p->num_sms, stream));
+        p->launches_generic++;
+    } else if (p->has_warp_kernel && tma_ok) {
         MB_CUDA(mb_launch_warp2048(p->dev, T, d_samples, d_out, p->num_sms, stream));
         p->launches_warp++;
     } else {
@@ -386,7 +390,7 @@ mb_status mb_plan_create(mb_plan **plan, int device, int buffer_size, int hop, d
     if ((flags & MB_FLAG_EXACT_FFT) && buffer_size > MB_MAX_EXACT_BUFFER_SIZE)
         return fail(MB_ERR_UNSUPPORTED, "exact-FFT mode supports bufferSize <= %d (got %d)", MB_MAX_EXACT_BUFFER_SIZE,
                     buffer_size);
-    if (flags & ~(uint32_t)(MB_FLAG_GENERIC_KERNEL | MB_FLAG_EXACT_FFT))
+    if (flags & ~(uint32_t)(MB_FLAG_GENERIC_KERNEL | MB_FLAG_EXACT_FFT | MB_FLAG_CLUSTER_FFT))
         return fail(MB_ERR_INVALID_ARG, "unknown plan flags 0x%x", flags);
     if (hop <= 0) return fail(MB_ERR_INVALID_ARG, "hop must be positive (got %d)", hop);
     if (!(sample_rate > 0)) return fail(MB_ERR_INVALID_ARG, "sampleRate must be positive");
@@ -490,6 +494,10 @@ mb_status mb_plan_create(mb_plan **plan, int device, int buffer_size, int hop, d
     D.tw_exact = p->d_tw_exact;
     D.exact = (flags & MB_FLAG_EXACT_FFT) ? 1 : 0;
     if (D.exact) p->kernel_name = "generic-exact";
+    if (D.exact && (N > 16384 || ((flags & MB_FLAG_CLUSTER_FFT) && N >= 64))) {
+        p->use_cluster = true;
+        p->kernel_name = "exact-cluster2";
+    }
     D.warp_tables = nullptr;
     if (N == 2048 && !D.exact && !(flags & MB_FLAG_GENERIC_KERNEL)) {
         MbWarpTables *W = new MbWarpTables();

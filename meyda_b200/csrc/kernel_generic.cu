@@ -17,8 +17,12 @@
 // Reference path being replaced: src/meyda.js:69-91,104-114,158-168,
 // lib/jsfft/fft.js:123-208, the extractor files under src/extractors/ (see
 // mb_device.cuh for the per-formula citations).
+#include <cooperative_groups.h>
+
 #include "mb_device.cuh"
 #include "mb_kernels.h"
+
+namespace cg = cooperative_groups;
 
 namespace {
 
@@ -101,6 +105,157 @@ struct MomentAcc {
     }
 };
 
+// Everything after the amplitude spectrum: block reductions of the moment partials, rolloff, Bark bands,
+// mel/log/DCT and the per-band outputs.  `amp` holds the N/2 amplitudes of the frame in shared memory.
+struct Scratch {
+    double red_d[kWarps];
+    float red_f[kWarps];
+    int red_i[kWarps];
+    double scan_d[kWarps];
+    double band_sum[MB_NUM_BARK_BANDS];
+    float specific[MB_NUM_BARK_BANDS];
+    float mel_log[MB_NUM_MEL_FILTERS];
+};
+
+template <bool EXACT>
+__device__ __forceinline__ void frame_epilogue(const MbDevPlan &P, const mb_outputs &O, int64_t g, MbFrameSums &S,
+                                               const MomentAcc &acc, const float *amp, Scratch &sc) {
+    const int M = P.M;
+    const uint32_t mask = P.mask;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double *red_d = sc.red_d, *scan_d = sc.scan_d, *band_sum = sc.band_sum;
+    int *red_i = sc.red_i;
+    float *specific = sc.specific, *mel_log = sc.mel_log;
+    const bool want_moments =
+        mask & (MB_FEATURE_BIT(MB_FEAT_SPECTRAL_CENTROID) | MB_FEATURE_BIT(MB_FEAT_SPECTRAL_SPREAD) |
+                MB_FEATURE_BIT(MB_FEAT_SPECTRAL_SKEWNESS) | MB_FEATURE_BIT(MB_FEAT_SPECTRAL_KURTOSIS) |
+                MB_FEATURE_BIT(MB_FEAT_SPECTRAL_FLATNESS) | MB_FEATURE_BIT(MB_FEAT_SPECTRAL_SLOPE));
+    const bool want_log = mb_has(mask, MB_FEAT_SPECTRAL_FLATNESS);
+    const bool want_bark = mask & (MB_FEATURE_BIT(MB_FEAT_LOUDNESS) | MB_FEATURE_BIT(MB_FEAT_PERCEPTUAL_SPREAD) |
+                                   MB_FEATURE_BIT(MB_FEAT_PERCEPTUAL_SHARPNESS));
+    if (want_moments) {
+        S.s0 = block_sum(acc.s0, red_d);
+        S.s1 = block_sum(acc.s1, red_d);
+        S.s2 = block_sum(acc.s2, red_d);
+        S.s3 = block_sum(acc.s3, red_d);
+        S.s4 = block_sum(acc.s4, red_d);
+        if (want_log) S.log2sum = block_sum(acc.lg, red_d);
+    }
+    __syncthreads();
+
+    // ---- rolloff: prefix sums of the amplitude spectrum in double
+    if (mb_has(mask, MB_FEAT_SPECTRAL_ROLLOFF)) {
+        const int chunk = (M + kThreads - 1) / kThreads;
+        const int k0 = min(M, tid * chunk), k1 = min(M, k0 + chunk);
+        double csum = 0;
+        for (int k = k0; k < k1; k++) csum += (double)amp[k];
+        double incl = csum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const double y = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += y;
+        }
+        if (lane == 31) scan_d[warp] = incl;
+        __syncthreads();
+        double base = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < kWarps; w++) {
+            if (w < warp) base += scan_d[w];
+            total += scan_d[w];
+        }
+        const double thr = 0.99 * total;
+        double pre = base + incl - csum;  // sum of amp[0..k0)
+        int cnt = 0;
+        for (int k = k0; k < k1; k++) {
+            cnt += (pre <= thr);
+            pre += (double)amp[k];
+        }
+        cnt = block_sum_int(cnt, red_i);
+        // spectralRolloff.js:11-15: the loop only runs while ec > threshold
+        S.rolloff_bin = (total > thr) ? cnt - 1 : M;
+    }
+
+    // ---- bark band sums (loudness.js:55-63), one warp per band
+    if (want_bark) {
+        for (int b = warp; b < MB_NUM_BARK_BANDS; b += kWarps) {
+            double s = 0;
+            for (int k = P.bb[b] + lane; k < P.bb[b + 1]; k += 32) s += (double)amp[k];
+            s = mb_warp_sum(s);
+            if (lane == 0) band_sum[b] = s;
+        }
+    }
+    // ---- mel filterbank energies (mfcc.js:40-65)
+    if (mb_has(mask, MB_FEAT_MFCC)) {
+        if (EXACT) {  // the reference's order: one float32 running sum per filter
+            if (tid < MB_NUM_MEL_FILTERS) {
+                const int e0 = P.mel[tid], e1 = P.mel[tid + 1], e2 = P.mel[tid + 2];
+                float s = 0.f;
+                for (int k = e0; k < e1 && k < M; k++) {
+                    const double wgt = (double)(k - e0) / (double)(e1 - e0);
+                    const float a = amp[k];
+                    s = (float)__dadd_rn((double)s, __dmul_rn(wgt, (double)__fmul_rn(a, a)));
+                }
+                for (int k = e1; k < e2 && k < M; k++) {
+                    const double wgt = (double)(e2 - k) / (double)(e2 - e1);
+                    const float a = amp[k];
+                    s = (float)__dadd_rn((double)s, __dmul_rn(wgt, (double)__fmul_rn(a, a)));
+                }
+                mel_log[tid] = (float)log((double)s);
+            }
+        } else {  // one warp per filter
+            for (int f = warp; f < MB_NUM_MEL_FILTERS; f += kWarps) {
+                const int e0 = P.mel[f], e1 = P.mel[f + 1], e2 = P.mel[f + 2];
+                const float up = __ldg(P.mel_inv_width + f), dn = __ldg(P.mel_inv_width + f + 1);
+                float s = 0.f;
+                for (int k = e0 + lane; k < e1; k += 32) {
+                    const float a = amp[k];
+                    s += (float)(k - e0) * up * (a * a);
+                }
+                for (int k = e1 + lane; k < e2; k += 32) {
+                    const float a = amp[k];
+                    s += (float)(e2 - k) * dn * (a * a);
+                }
+                s = mb_warp_sum(s);
+                if (lane == 0) mel_log[f] = (float)log((double)s);
+            }
+        }
+    }
+    __syncthreads();
+
+    if (want_bark) {
+        if (tid < MB_NUM_BARK_BANDS) {
+            const float sp = (float)pow(band_sum[tid], 0.23);
+            specific[tid] = sp;
+            if (mb_has(mask, MB_FEAT_LOUDNESS)) O.loudness_specific[g * MB_NUM_BARK_BANDS + tid] = sp;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            double total = 0, mx = 0, sharp = 0;
+            for (int i = 0; i < MB_NUM_BARK_BANDS; i++) {
+                const double sp = (double)specific[i];
+                total += sp;
+                if (sp > mx) mx = sp;
+                if (i >= 1 && i <= 15) sharp += (double)i * sp;  // (i+1) * spec[i+1], i < 15
+            }
+            sharp += P.sharp_const;
+            if (mb_has(mask, MB_FEAT_LOUDNESS)) O.loudness_total[g] = (float)total;
+            if (mb_has(mask, MB_FEAT_PERCEPTUAL_SPREAD)) {
+                const double r = (total - mx) / total;
+                O.perceptual_spread[g] = (float)(r * r);
+            }
+            if (mb_has(mask, MB_FEAT_PERCEPTUAL_SHARPNESS))
+                O.perceptual_sharpness[g] = (float)(sharp * (0.11 / total));
+        }
+    }
+    if (mb_has(mask, MB_FEAT_MFCC) && tid >= 32 && tid < 32 + MB_NUM_MFCC) {
+        const int c = tid - 32;
+        double v = 0;
+        for (int f = 0; f < MB_NUM_MEL_FILTERS; f++)
+            v += (double)__ldg(P.dct + c + f * MB_NUM_MFCC) * (double)mel_log[f];
+        O.mfcc[g * MB_NUM_MFCC + c] = (float)(v / (double)MB_NUM_MFCC);
+    }
+}
+
 template <bool EXACT>
 __global__ void __launch_bounds__(kThreads)
 mb_generic_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ MbClipTable T,
@@ -113,13 +268,10 @@ mb_generic_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ M
     float *xim = xre + N;
     float *amp = EXACT ? (xim + N) : reinterpret_cast<float *>(work + pidx(M) + 1);
 
-    __shared__ double red_d[kWarps];
-    __shared__ float red_f[kWarps];
-    __shared__ int red_i[kWarps];
-    __shared__ double scan_d[kWarps];
-    __shared__ double band_sum[MB_NUM_BARK_BANDS];
-    __shared__ float specific[MB_NUM_BARK_BANDS];
-    __shared__ float mel_log[MB_NUM_MEL_FILTERS];
+    __shared__ Scratch sc;
+    double *red_d = sc.red_d;
+    float *red_f = sc.red_f;
+    int *red_i = sc.red_i;
 
     const uint32_t mask = P.mask;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -290,130 +442,134 @@ mb_generic_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ M
                     if (want_moments) acc.add(av, k, want_log);
                 }
             }
-            if (want_moments) {
-                S.s0 = block_sum(acc.s0, red_d);
-                S.s1 = block_sum(acc.s1, red_d);
-                S.s2 = block_sum(acc.s2, red_d);
-                S.s3 = block_sum(acc.s3, red_d);
-                S.s4 = block_sum(acc.s4, red_d);
-                if (want_log) S.log2sum = block_sum(acc.lg, red_d);
-            }
-            __syncthreads();
-
-            // ---- rolloff: prefix sums of the amplitude spectrum in double
-            if (mb_has(mask, MB_FEAT_SPECTRAL_ROLLOFF)) {
-                const int chunk = (M + kThreads - 1) / kThreads;
-                const int k0 = min(M, tid * chunk), k1 = min(M, k0 + chunk);
-                double csum = 0;
-                for (int k = k0; k < k1; k++) csum += (double)amp[k];
-                double incl = csum;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const double y = __shfl_up_sync(0xffffffffu, incl, o);
-                    if (lane >= o) incl += y;
-                }
-                if (lane == 31) scan_d[warp] = incl;
-                __syncthreads();
-                double base = 0, total = 0;
-#pragma unroll
-                for (int w = 0; w < kWarps; w++) {
-                    if (w < warp) base += scan_d[w];
-                    total += scan_d[w];
-                }
-                const double thr = 0.99 * total;
-                double pre = base + incl - csum;  // sum of amp[0..k0)
-                int cnt = 0;
-                for (int k = k0; k < k1; k++) {
-                    cnt += (pre <= thr);
-                    pre += (double)amp[k];
-                }
-                cnt = block_sum_int(cnt, red_i);
-                // spectralRolloff.js:11-15: the loop only runs while ec > threshold
-                S.rolloff_bin = (total > thr) ? cnt - 1 : M;
-            }
-
-            // ---- bark band sums (loudness.js:55-63), one warp per band
-            if (want_bark) {
-                for (int b = warp; b < MB_NUM_BARK_BANDS; b += kWarps) {
-                    double s = 0;
-                    for (int k = P.bb[b] + lane; k < P.bb[b + 1]; k += 32) s += (double)amp[k];
-                    s = mb_warp_sum(s);
-                    if (lane == 0) band_sum[b] = s;
-                }
-            }
-            // ---- mel filterbank energies (mfcc.js:40-65)
-            if (mb_has(mask, MB_FEAT_MFCC)) {
-                if (EXACT) {  // the reference's order: one float32 running sum per filter
-                    if (tid < MB_NUM_MEL_FILTERS) {
-                        const int e0 = P.mel[tid], e1 = P.mel[tid + 1], e2 = P.mel[tid + 2];
-                        float s = 0.f;
-                        for (int k = e0; k < e1 && k < M; k++) {
-                            const double wgt = (double)(k - e0) / (double)(e1 - e0);
-                            const float a = amp[k];
-                            s = (float)__dadd_rn((double)s, __dmul_rn(wgt, (double)__fmul_rn(a, a)));
-                        }
-                        for (int k = e1; k < e2 && k < M; k++) {
-                            const double wgt = (double)(e2 - k) / (double)(e2 - e1);
-                            const float a = amp[k];
-                            s = (float)__dadd_rn((double)s, __dmul_rn(wgt, (double)__fmul_rn(a, a)));
-                        }
-                        mel_log[tid] = (float)log((double)s);
-                    }
-                } else {  // one warp per filter
-                    for (int f = warp; f < MB_NUM_MEL_FILTERS; f += kWarps) {
-                        const int e0 = P.mel[f], e1 = P.mel[f + 1], e2 = P.mel[f + 2];
-                        const float up = __ldg(P.mel_inv_width + f), dn = __ldg(P.mel_inv_width + f + 1);
-                        float s = 0.f;
-                        for (int k = e0 + lane; k < e1; k += 32) {
-                            const float a = amp[k];
-                            s += (float)(k - e0) * up * (a * a);
-                        }
-                        for (int k = e1 + lane; k < e2; k += 32) {
-                            const float a = amp[k];
-                            s += (float)(e2 - k) * dn * (a * a);
-                        }
-                        s = mb_warp_sum(s);
-                        if (lane == 0) mel_log[f] = (float)log((double)s);
-                    }
-                }
-            }
-            __syncthreads();
-
-            if (want_bark) {
-                if (tid < MB_NUM_BARK_BANDS) {
-                    const float sp = (float)pow(band_sum[tid], 0.23);
-                    specific[tid] = sp;
-                    if (mb_has(mask, MB_FEAT_LOUDNESS)) O.loudness_specific[g * MB_NUM_BARK_BANDS + tid] = sp;
-                }
-                __syncthreads();
-                if (tid == 0) {
-                    double total = 0, mx = 0, sharp = 0;
-                    for (int i = 0; i < MB_NUM_BARK_BANDS; i++) {
-                        const double sp = (double)specific[i];
-                        total += sp;
-                        if (sp > mx) mx = sp;
-                        if (i >= 1 && i <= 15) sharp += (double)i * sp;  // (i+1) * spec[i+1], i < 15
-                    }
-                    sharp += P.sharp_const;
-                    if (mb_has(mask, MB_FEAT_LOUDNESS)) O.loudness_total[g] = (float)total;
-                    if (mb_has(mask, MB_FEAT_PERCEPTUAL_SPREAD)) {
-                        const double r = (total - mx) / total;
-                        O.perceptual_spread[g] = (float)(r * r);
-                    }
-                    if (mb_has(mask, MB_FEAT_PERCEPTUAL_SHARPNESS))
-                        O.perceptual_sharpness[g] = (float)(sharp * (0.11 / total));
-                }
-            }
-            if (mb_has(mask, MB_FEAT_MFCC) && tid >= 32 && tid < 32 + MB_NUM_MFCC) {
-                const int c = tid - 32;
-                double v = 0;
-                for (int f = 0; f < MB_NUM_MEL_FILTERS; f++)
-                    v += (double)__ldg(P.dct + c + f * MB_NUM_MFCC) * (double)mel_log[f];
-                O.mfcc[g * MB_NUM_MFCC + c] = (float)(v / (double)MB_NUM_MFCC);
-            }
+            frame_epilogue<EXACT>(P, O, g, S, acc, amp, sc);
         }
         if (tid == 64) mb_store_scalars(P, O, g, S);
         __syncthreads();  // smem reused by the next frame
+    }
+}
+
+
+// ---- exact-FFT mode for a frame that does not fit one CTA ---------------------------------------
+// At bufferSize 32768 the reference's N-point complex transform needs 256 KB as float32 re/im -- more
+// than one CTA's shared memory.  A 2-CTA thread-block cluster holds it: CTA r keeps positions
+// [r N/2, (r+1) N/2) of the bit-reversed array.  Every radix-2 stage but the last pairs elements inside
+// one half; the last stage (width N/2) pairs element j of CTA 0 with element j of CTA 1, which each CTA
+// reads from its peer through distributed shared memory (cluster.map_shared_rank), after a
+// cluster-wide barrier.  Amplitudes are gathered into CTA 0, which runs the feature epilogue.
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads)
+mb_exact_cluster_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ MbClipTable T,
+                        const float *__restrict__ samples, const __grid_constant__ mb_outputs O) {
+    cg::cluster_group cluster = cg::this_cluster();
+    const unsigned rank = cluster.block_rank();
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int N = P.N, M = P.M, H = N / 2, log2N = P.log2M + 1;
+    float *xre = reinterpret_cast<float *>(smem_raw), *xim = xre + H, *amp = xim + H;  // amp[M] is used on CTA 0
+    __shared__ Scratch sc;
+    const float *re0 = cluster.map_shared_rank(xre, 0), *im0 = cluster.map_shared_rank(xim, 0);
+    const float *re1 = cluster.map_shared_rank(xre, 1), *im1 = cluster.map_shared_rank(xim, 1);
+    float *amp0 = cluster.map_shared_rank(amp, 0);
+
+    const uint32_t mask = P.mask;
+    const int tid = threadIdx.x;
+    const bool want_moments =
+        mask & (MB_FEATURE_BIT(MB_FEAT_SPECTRAL_CENTROID) | MB_FEATURE_BIT(MB_FEAT_SPECTRAL_SPREAD) |
+                MB_FEATURE_BIT(MB_FEAT_SPECTRAL_SKEWNESS) | MB_FEATURE_BIT(MB_FEAT_SPECTRAL_KURTOSIS) |
+                MB_FEATURE_BIT(MB_FEAT_SPECTRAL_FLATNESS) | MB_FEATURE_BIT(MB_FEAT_SPECTRAL_SLOPE));
+    const bool want_log = mb_has(mask, MB_FEAT_SPECTRAL_FLATNESS);
+    const bool want_time = mask & (MB_FEATURE_BIT(MB_FEAT_RMS) | MB_FEATURE_BIT(MB_FEAT_ENERGY) |
+                                   MB_FEATURE_BIT(MB_FEAT_ZCR) | MB_FEATURE_BIT(MB_FEAT_BUFFER));
+    const uint32_t time_only = MB_FEATURE_BIT(MB_FEAT_RMS) | MB_FEATURE_BIT(MB_FEAT_ENERGY) |
+                               MB_FEATURE_BIT(MB_FEAT_ZCR) | MB_FEATURE_BIT(MB_FEAT_BUFFER);
+    const bool want_spectrum = (mask & ~time_only) != 0;
+    const double SQRT1_2 = 0.70710678118654752440;
+    const int64_t n_clusters = gridDim.x / 2, cid = blockIdx.x / 2;
+
+    for (int64_t g = cid; g < T.total_frames; g += n_clusters) {
+        const int64_t clip = mb_find_clip(T, g);
+        const float *__restrict__ src = samples + T.clip_off[clip] + (g - T.frame_start[clip]) * (int64_t)P.hop;
+        MbFrameSums S;
+        S.s0 = S.s1 = S.s2 = S.s3 = S.s4 = S.log2sum = S.energy = 0;
+        S.zcr = 0;
+        S.rolloff_bin = M;
+
+        if (rank == 0 && want_time) {  // time-domain features over the whole raw frame
+            double e = 0;
+            int z = 0;
+            for (int i = tid; i < N; i += kThreads) {
+                const float x0 = __ldg(src + i);
+                e += (double)x0 * (double)x0;
+                if (i + 1 < N) {
+                    const float x1 = __ldg(src + i + 1);
+                    z += ((x0 >= 0.f) != (x1 >= 0.f)) && (x0 == x0) && (x1 == x1);
+                }
+                if (mb_has(mask, MB_FEAT_BUFFER)) O.buffer[g * N + i] = x0;
+            }
+            S.energy = block_sum(e, sc.red_d);
+            S.zcr = block_sum_int(z, sc.red_i);
+        }
+        if (want_spectrum) {
+            // this CTA's half of BitReverseComplexArray(windowed frame), imag zero
+            const int rshift = 32 - log2N;
+            for (int pl = tid; pl < H; pl += kThreads) {
+                const int i = (int)(__brev((unsigned)(rank * H + pl)) >> rshift);
+                xre[pl] = __fmul_rn(__ldg(src + i), __ldg(P.window + i));
+                xim[pl] = 0.f;
+            }
+            __syncthreads();
+            for (int log2w = 0; log2w < log2N - 1; log2w++) {  // widths 1 .. N/4: inside the half
+                const int w = 1 << log2w;
+                const double2 *__restrict__ tw = P.tw_exact + (w - 1);
+                for (int idx = tid; idx < H / 2; idx += kThreads) {
+                    const int j = idx & (w - 1);
+                    const int l = ((idx >> log2w) << (log2w + 1)) + j;
+                    const int r = l + w;
+                    const double2 f = __ldg(&tw[j]);
+                    const double lr = (double)xre[l], li = (double)xim[l];
+                    const double xr = (double)xre[r], xi = (double)xim[r];
+                    const double rr = __dsub_rn(__dmul_rn(f.x, xr), __dmul_rn(f.y, xi));
+                    const double ri = __dadd_rn(__dmul_rn(f.y, xr), __dmul_rn(f.x, xi));
+                    xre[l] = (float)__dmul_rn(SQRT1_2, __dadd_rn(lr, rr));
+                    xim[l] = (float)__dmul_rn(SQRT1_2, __dadd_rn(li, ri));
+                    xre[r] = (float)__dmul_rn(SQRT1_2, __dsub_rn(lr, rr));
+                    xim[r] = (float)__dmul_rn(SQRT1_2, __dsub_rn(li, ri));
+                }
+                __syncthreads();
+            }
+            cluster.sync();  // both halves are complete and visible cluster-wide
+            {                // width N/2: element j of CTA 0 with element j of CTA 1, through DSMEM
+                const double2 *__restrict__ tw = P.tw_exact + (H - 1);
+                for (int jj = tid; jj < H / 2; jj += kThreads) {
+                    const int j = (int)rank * (H / 2) + jj;
+                    const double2 f = __ldg(&tw[j]);
+                    const double lr = (double)re0[j], li = (double)im0[j];
+                    const double xr = (double)re1[j], xi = (double)im1[j];
+                    const double rr = __dsub_rn(__dmul_rn(f.x, xr), __dmul_rn(f.y, xi));
+                    const double ri = __dadd_rn(__dmul_rn(f.y, xr), __dmul_rn(f.x, xi));
+                    const float zr = (float)__dmul_rn(SQRT1_2, __dadd_rn(lr, rr));
+                    const float zi = (float)__dmul_rn(SQRT1_2, __dadd_rn(li, ri));
+                    if (mb_has(mask, MB_FEAT_COMPLEX_SPECTRUM)) {
+                        O.complex_real[g * N + j] = zr;
+                        O.complex_imag[g * N + j] = zi;
+                        O.complex_real[g * N + j + H] = (float)__dmul_rn(SQRT1_2, __dsub_rn(lr, rr));
+                        O.complex_imag[g * N + j + H] = (float)__dmul_rn(SQRT1_2, __dsub_rn(li, ri));
+                    }
+                    const float av = (float)sqrt(__dadd_rn(__dmul_rn((double)zr, (double)zr), __dmul_rn((double)zi, (double)zi)));
+                    amp0[j] = av;  // gathered on CTA 0
+                    if (mb_has(mask, MB_FEAT_AMPLITUDE_SPECTRUM)) O.amplitude_spectrum[g * M + j] = av;
+                    if (mb_has(mask, MB_FEAT_POWER_SPECTRUM)) O.power_spectrum[g * M + j] = __fmul_rn(av, av);
+                }
+            }
+            cluster.sync();  // CTA 0 holds all N/2 amplitudes
+            if (rank == 0) {
+                MomentAcc acc;
+                if (want_moments)
+                    for (int k = tid; k < M; k += kThreads) acc.add(amp[k], k, want_log);
+                frame_epilogue<true>(P, O, g, S, acc, amp, sc);
+            }
+        }
+        if (rank == 0 && tid == 64) mb_store_scalars(P, O, g, S);
+        cluster.sync();  // CTA 0 is done with the gathered amplitudes before the next frame overwrites them
     }
 }
 
@@ -440,6 +596,21 @@ static cudaError_t launch_generic(const MbDevPlan &P, const MbClipTable &T, cons
     if (grid < 1) return cudaSuccess;
     (void)cudaGetLastError();  // drop any stale non-sticky error left by other users of the context
     mb_generic_kernel<EXACT><<<(unsigned)grid, kThreads, smem, stream>>>(P, T, samples, O);
+    return cudaGetLastError();
+}
+
+size_t mb_exact_cluster_smem_bytes(int N) { return (size_t)3 * (N / 2) * sizeof(float); }
+
+cudaError_t mb_launch_exact_cluster(const MbDevPlan &P, const MbClipTable &T, const float *samples, const mb_outputs &O,
+                                    int num_sms, cudaStream_t stream) {
+    const size_t smem = mb_exact_cluster_smem_bytes(P.N);
+    cudaError_t e = cudaFuncSetAttribute(mb_exact_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int64_t clusters = num_sms / 2;
+    if (clusters > T.total_frames) clusters = T.total_frames;
+    if (clusters < 1) return cudaSuccess;
+    (void)cudaGetLastError();
+    mb_exact_cluster_kernel<<<(unsigned)(2 * clusters), kThreads, smem, stream>>>(P, T, samples, O);
     return cudaGetLastError();
 }
 

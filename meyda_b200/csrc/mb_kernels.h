@@ -12,5 +12,10 @@ size_t mb_warp2048_smem_bytes();
 cudaError_t mb_launch_warp2048(const MbDevPlan &P, const MbClipTable &T, const float *samples, const mb_outputs &O,
                                int num_sms, cudaStream_t stream);
 
+// Exact-FFT mode on a 2-CTA cluster (DSMEM exchange in the last radix-2 stage): bufferSize up to 32768.
+size_t mb_exact_cluster_smem_bytes(int N);
+cudaError_t mb_launch_exact_cluster(const MbDevPlan &P, const MbClipTable &T, const float *samples, const mb_outputs &O,
+                                    int num_sms, cudaStream_t stream);
+
 cudaError_t mb_launch_generic(const MbDevPlan &P, const MbClipTable &T, const float *samples, const mb_outputs &O,
                               int num_sms, cudaStream_t stream);

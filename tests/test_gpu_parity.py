@@ -14,7 +14,8 @@ pytestmark = pytest.mark.gpu
 SR = 44100.0
 EXACT = _capi.MB_FLAG_EXACT_FFT
 FLAG_VARIANTS = [pytest.param(0, id="fast"), pytest.param(_capi.MB_FLAG_GENERIC_KERNEL, id="generic"),
-                 pytest.param(EXACT, id="exact")]
+                 pytest.param(EXACT, id="exact"),
+                 pytest.param(EXACT | _capi.MB_FLAG_CLUSTER_FFT, id="exact-cluster")]
 
 
 def run_gpu(clips, N, hop=None, window="hanning", features=mb.FEATURES, flags=0):
@@ -125,11 +126,10 @@ def test_ragged_and_empty_clips(flags):
 @pytest.mark.parametrize("flags", FLAG_VARIANTS)
 @pytest.mark.parametrize("N", [16, 64, 128, 4096, 8192, 32768])
 def test_other_buffer_sizes(N, flags):
-    if (flags & EXACT) and N > 16384:
-        with pytest.raises(mb.MeydaNativeError) as ei:
-            mb.Plan(N, N, SR, flags=flags)
-        assert ei.value.status == _capi.MB_ERR_UNSUPPORTED
-        return
+    if (flags & EXACT) and N > 16384:  # does not fit one CTA: the 2-CTA cluster kernel takes over
+        plan = mb.Plan(N, N, SR, flags=flags)
+        assert plan.kernel_name == "exact-cluster2"
+        plan.close()
     x = mo.synth_clip(N, N * 3 + 5)
     hop = N // 4
     out, per = run_gpu(x, N, hop, flags=flags)
