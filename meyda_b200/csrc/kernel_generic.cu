@@ -24,556 +24,19 @@
 
 namespace cg = cooperative_groups;
 
-namespace {
+// The kernels are compiled for two CTA sizes: 256 threads (several CTAs per SM at small bufferSize) and
+// 1024 threads (one CTA per SM once a frame needs most of the shared memory, bufferSize >= 8192).
+namespace g256 {
+#define MB_GENERIC_THREADS 256
+#include "kernel_generic_impl.cuh"
+#undef MB_GENERIC_THREADS
+}  // namespace g256
+namespace g1024 {
+#define MB_GENERIC_THREADS 1024
+#include "kernel_generic_impl.cuh"
+#undef MB_GENERIC_THREADS
+}  // namespace g1024
 
-constexpr int kThreads = 256;
-constexpr int kWarps = kThreads / 32;
-
-// One padding element every 32 and every 1024 entries keeps both the unit-stride
-// butterfly accesses and the bit-reversed gather of the split pass off a
-// single shared-memory bank.
-__device__ __forceinline__ int pidx(int i) { return i + (i >> 5) + (i >> 10); }
-
-__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
-    return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
-}
-
-// Q fused radix-2 DIF stages starting at span 2^log2s: 2^Q points per work item.
-template <int Q>
-__device__ __forceinline__ void fft_pass(float2 *work, const float2 *__restrict__ twM, int M, int log2M, int log2s) {
-    constexpr int R = 1 << Q;
-    const int items = M >> Q;
-    const int log2sub = log2s - Q;
-    const int sub = 1 << log2sub;
-    for (int idx = threadIdx.x; idx < items; idx += kThreads) {
-        const int j = idx & (sub - 1);
-        const int b = (idx >> log2sub) << log2s;
-        float2 v[R];
-#pragma unroll
-        for (int t = 0; t < R; t++) v[t] = work[pidx(b + j + t * sub)];
-#pragma unroll
-        for (int q = 0; q < Q; q++) {
-            const int h = R >> (q + 1);
-            const int tw_shift = log2M - (log2s - q);  // M / (s >> q)
-#pragma unroll
-            for (int t = 0; t < R; t++) {
-                if (t & h) continue;
-                const int e = (j + (t & (h - 1)) * sub) << tw_shift;
-                const float2 u = v[t], w = v[t + h];
-                v[t] = make_float2(u.x + w.x, u.y + w.y);
-                v[t + h] = cmul(make_float2(u.x - w.x, u.y - w.y), __ldg(&twM[e]));
-            }
-        }
-#pragma unroll
-        for (int t = 0; t < R; t++) work[pidx(b + j + t * sub)] = v[t];
-    }
-}
-
-__device__ __forceinline__ double block_sum(double v, double *scratch /*[kWarps]*/) {
-    v = mb_warp_sum(v);
-    __syncthreads();
-    if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
-    __syncthreads();
-    double r = 0;
-#pragma unroll
-    for (int w = 0; w < kWarps; w++) r += scratch[w];
-    return r;
-}
-
-__device__ __forceinline__ int block_sum_int(int v, int *scratch /*[kWarps]*/) {
-    v = mb_warp_sum(v);
-    __syncthreads();
-    if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
-    __syncthreads();
-    int r = 0;
-#pragma unroll
-    for (int w = 0; w < kWarps; w++) r += scratch[w];
-    return r;
-}
-
-struct MomentAcc {
-    double s0 = 0, s1 = 0, s2 = 0, s3 = 0, s4 = 0, lg = 0;
-    __device__ __forceinline__ void add(float av, int k, bool want_log) {
-        const double ad = (double)av, kd = (double)k;
-        double t = ad * kd;
-        s0 += ad;
-        s1 += t;
-        t *= kd; s2 += t;
-        t *= kd; s3 += t;
-        t *= kd; s4 += t;
-        if (want_log) lg += (double)log2f(av);
-    }
-};
-
-// Everything after the amplitude spectrum: block reductions of the moment partials, rolloff, Bark bands,
-// mel/log/DCT and the per-band outputs.  `amp` holds the N/2 amplitudes of the frame in shared memory.
-struct Scratch {
-    double red_d[kWarps];
-    float red_f[kWarps];
-    int red_i[kWarps];
-    double scan_d[kWarps];
-    double band_sum[MB_NUM_BARK_BANDS];
-    float specific[MB_NUM_BARK_BANDS];
-    float mel_log[MB_NUM_MEL_FILTERS];
-};
-
-template <bool EXACT>
-__device__ __forceinline__ void frame_epilogue(const MbDevPlan &P, const mb_outputs &O, int64_t g, MbFrameSums &S,
-                                               const MomentAcc &acc, const float *amp, Scratch &sc) {
-    const int M = P.M;
-    const uint32_t mask = P.mask;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    double *red_d = sc.red_d, *scan_d = sc.scan_d, *band_sum = sc.band_sum;
-    int *red_i = sc.red_i;
-    float *specific = sc.specific, *mel_log = sc.mel_log;
-    const bool want_moments =
-        mask & (MB_FEATURE_BIT(MB_FEAT_SPECTRAL_CENTROID) | MB_FEATURE_BIT(MB_FEAT_SPECTRAL_SPREAD) |
-                MB_FEATURE_BIT(MB_FEAT_SPECTRAL_SKEWNESS) | MB_FEATURE_BIT(MB_FEAT_SPECTRAL_KURTOSIS) |
-                MB_FEATURE_BIT(MB_FEAT_SPECTRAL_FLATNESS) | MB_FEATURE_BIT(MB_FEAT_SPECTRAL_SLOPE));
-    const bool want_log = mb_has(mask, MB_FEAT_SPECTRAL_FLATNESS);
-    const bool want_bark = mask & (MB_FEATURE_BIT(MB_FEAT_LOUDNESS) | MB_FEATURE_BIT(MB_FEAT_PERCEPTUAL_SPREAD) |
-                                   MB_FEATURE_BIT(MB_FEAT_PERCEPTUAL_SHARPNESS));
-    if (want_moments) {
-        S.s0 = block_sum(acc.s0, red_d);
-        S.s1 = block_sum(acc.s1, red_d);
-        S.s2 = block_sum(acc.s2, red_d);
-        S.s3 = block_sum(acc.s3, red_d);
-        S.s4 = block_sum(acc.s4, red_d);
-        if (want_log) S.log2sum = block_sum(acc.lg, red_d);
-    }
-    __syncthreads();
-
-    // ---- rolloff: prefix sums of the amplitude spectrum in double
-    if (mb_has(mask, MB_FEAT_SPECTRAL_ROLLOFF)) {
-        const int chunk = (M + kThreads - 1) / kThreads;
-        const int k0 = min(M, tid * chunk), k1 = min(M, k0 + chunk);
-        double csum = 0;
-        for (int k = k0; k < k1; k++) csum += (double)amp[k];
-        double incl = csum;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const double y = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += y;
-        }
-        if (lane == 31) scan_d[warp] = incl;
-        __syncthreads();
-        double base = 0, total = 0;
-#pragma unroll
-        for (int w = 0; w < kWarps; w++) {
-            if (w < warp) base += scan_d[w];
-            total += scan_d[w];
-        }
-        const double thr = 0.99 * total;
-        double pre = base + incl - csum;  // sum of amp[0..k0)
-        int cnt = 0;
-        for (int k = k0; k < k1; k++) {
-            cnt += (pre <= thr);
-            pre += (double)amp[k];
-        }
-        cnt = block_sum_int(cnt, red_i);
-        // spectralRolloff.js:11-15: the loop only runs while ec > threshold
-        S.rolloff_bin = (total > thr) ? cnt - 1 : M;
-    }
-
-    // ---- bark band sums (loudness.js:55-63), one warp per band
-    if (want_bark) {
-        for (int b = warp; b < MB_NUM_BARK_BANDS; b += kWarps) {
-            double s = 0;
-            for (int k = P.bb[b] + lane; k < P.bb[b + 1]; k += 32) s += (double)amp[k];
-            s = mb_warp_sum(s);
-            if (lane == 0) band_sum[b] = s;
-        }
-    }
-    // ---- mel filterbank energies (mfcc.js:40-65)
-    if (mb_has(mask, MB_FEAT_MFCC)) {
-        if (EXACT) {  // the reference's order: one float32 running sum per filter
-            if (tid < MB_NUM_MEL_FILTERS) {
-                const int e0 = P.mel[tid], e1 = P.mel[tid + 1], e2 = P.mel[tid + 2];
-                float s = 0.f;
-                for (int k = e0; k < e1 && k < M; k++) {
-                    const double wgt = (double)(k - e0) / (double)(e1 - e0);
-                    const float a = amp[k];
-                    s = (float)__dadd_rn((double)s, __dmul_rn(wgt, (double)__fmul_rn(a, a)));
-                }
-                for (int k = e1; k < e2 && k < M; k++) {
-                    const double wgt = (double)(e2 - k) / (double)(e2 - e1);
-                    const float a = amp[k];
-                    s = (float)__dadd_rn((double)s, __dmul_rn(wgt, (double)__fmul_rn(a, a)));
-                }
-                mel_log[tid] = (float)log((double)s);
-            }
-        } else {  // one warp per filter
-            for (int f = warp; f < MB_NUM_MEL_FILTERS; f += kWarps) {
-                const int e0 = P.mel[f], e1 = P.mel[f + 1], e2 = P.mel[f + 2];
-                const float up = __ldg(P.mel_inv_width + f), dn = __ldg(P.mel_inv_width + f + 1);
-                float s = 0.f;
-                for (int k = e0 + lane; k < e1; k += 32) {
-                    const float a = amp[k];
-                    s += (float)(k - e0) * up * (a * a);
-                }
-                for (int k = e1 + lane; k < e2; k += 32) {
-                    const float a = amp[k];
-                    s += (float)(e2 - k) * dn * (a * a);
-                }
-                s = mb_warp_sum(s);
-                if (lane == 0) mel_log[f] = (float)log((double)s);
-            }
-        }
-    }
-    __syncthreads();
-
-    if (want_bark) {
-        if (tid < MB_NUM_BARK_BANDS) {
-            const float sp = (float)pow(band_sum[tid], 0.23);
-            specific[tid] = sp;
-            if (mb_has(mask, MB_FEAT_LOUDNESS)) O.loudness_specific[g * MB_NUM_BARK_BANDS + tid] = sp;
-        }
-        __syncthreads();
-        if (tid == 0) {
-            double total = 0, mx = 0, sharp = 0;
-            for (int i = 0; i < MB_NUM_BARK_BANDS; i++) {
-                const double sp = (double)specific[i];
-                total += sp;
-                if (sp > mx) mx = sp;
-                if (i >= 1 && i <= 15) sharp += (double)i * sp;  // (i+1) * spec[i+1], i < 15
-            }
-            sharp += P.sharp_const;
-            if (mb_has(mask, MB_FEAT_LOUDNESS)) O.loudness_total[g] = (float)total;
-            if (mb_has(mask, MB_FEAT_PERCEPTUAL_SPREAD)) {
-                const double r = (total - mx) / total;
-                O.perceptual_spread[g] = (float)(r * r);
-            }
-            if (mb_has(mask, MB_FEAT_PERCEPTUAL_SHARPNESS))
-                O.perceptual_sharpness[g] = (float)(sharp * (0.11 / total));
-        }
-    }
-    if (mb_has(mask, MB_FEAT_MFCC) && tid >= 32 && tid < 32 + MB_NUM_MFCC) {
-        const int c = tid - 32;
-        double v = 0;
-        for (int f = 0; f < MB_NUM_MEL_FILTERS; f++)
-            v += (double)__ldg(P.dct + c + f * MB_NUM_MFCC) * (double)mel_log[f];
-        O.mfcc[g * MB_NUM_MFCC + c] = (float)(v / (double)MB_NUM_MFCC);
-    }
-}
-
-template <bool EXACT>
-__global__ void __launch_bounds__(kThreads)
-mb_generic_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ MbClipTable T,
-                  const float *__restrict__ samples, const __grid_constant__ mb_outputs O) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int N = P.N, M = P.M, log2M = P.log2M;
-    // fast: work = padded M complex, then amp[M].  exact: re[N], im[N], then amp[M].
-    float2 *work = reinterpret_cast<float2 *>(smem_raw);
-    float *xre = reinterpret_cast<float *>(smem_raw);
-    float *xim = xre + N;
-    float *amp = EXACT ? (xim + N) : reinterpret_cast<float *>(work + pidx(M) + 1);
-
-    __shared__ Scratch sc;
-    double *red_d = sc.red_d;
-    float *red_f = sc.red_f;
-    int *red_i = sc.red_i;
-
-    const uint32_t mask = P.mask;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const bool want_moments =
-        mask & (MB_FEATURE_BIT(MB_FEAT_SPECTRAL_CENTROID) | MB_FEATURE_BIT(MB_FEAT_SPECTRAL_SPREAD) |
-                MB_FEATURE_BIT(MB_FEAT_SPECTRAL_SKEWNESS) | MB_FEATURE_BIT(MB_FEAT_SPECTRAL_KURTOSIS) |
-                MB_FEATURE_BIT(MB_FEAT_SPECTRAL_FLATNESS) | MB_FEATURE_BIT(MB_FEAT_SPECTRAL_SLOPE));
-    const bool want_log = mb_has(mask, MB_FEAT_SPECTRAL_FLATNESS);
-    const bool want_time = mask & (MB_FEATURE_BIT(MB_FEAT_RMS) | MB_FEATURE_BIT(MB_FEAT_ENERGY) |
-                                   MB_FEATURE_BIT(MB_FEAT_ZCR) | MB_FEATURE_BIT(MB_FEAT_BUFFER));
-    const bool want_bark = mask & (MB_FEATURE_BIT(MB_FEAT_LOUDNESS) | MB_FEATURE_BIT(MB_FEAT_PERCEPTUAL_SPREAD) |
-                                   MB_FEATURE_BIT(MB_FEAT_PERCEPTUAL_SHARPNESS));
-    const uint32_t time_only = MB_FEATURE_BIT(MB_FEAT_RMS) | MB_FEATURE_BIT(MB_FEAT_ENERGY) |
-                               MB_FEATURE_BIT(MB_FEAT_ZCR) | MB_FEATURE_BIT(MB_FEAT_BUFFER);
-    const bool want_spectrum = (mask & ~time_only) != 0;
-
-    for (int64_t g = blockIdx.x; g < T.total_frames; g += gridDim.x) {
-        const int64_t clip = mb_find_clip(T, g);
-        const float *__restrict__ src = samples + T.clip_off[clip] + (g - T.frame_start[clip]) * (int64_t)P.hop;
-
-        MbFrameSums S;
-        S.s0 = S.s1 = S.s2 = S.s3 = S.s4 = S.log2sum = S.energy = 0;
-        S.zcr = 0;
-        S.rolloff_bin = M;
-
-        // ---- time domain: buffer, energy, zcr; windowed frame into smem
-        int kscale = 0;  // fast mode: power-of-two rescale of frames that would under/overflow float32 squares
-        {
-            double e = 0;
-            int z = 0;
-            float mxabs = 0.f;
-            for (int i = tid; i < M; i += kThreads) {
-                const float x0 = __ldg(src + 2 * i), x1 = __ldg(src + 2 * i + 1);
-                mxabs = fmaxf(mxabs, fmaxf(fabsf(x0), fabsf(x1)));
-                if (want_time) {
-                    e += (double)x0 * (double)x0 + (double)x1 * (double)x1;
-                    z += ((x0 >= 0.f) != (x1 >= 0.f)) && (x0 == x0) && (x1 == x1);
-                    if (2 * i + 2 < N) {
-                        const float x2 = __ldg(src + 2 * i + 2);
-                        z += ((x1 >= 0.f) != (x2 >= 0.f)) && (x1 == x1) && (x2 == x2);
-                    }
-                    if (mb_has(mask, MB_FEAT_BUFFER)) {
-                        O.buffer[g * N + 2 * i] = x0;
-                        O.buffer[g * N + 2 * i + 1] = x1;
-                    }
-                }
-                // computeWindow src/meyda.js:158-168: float32 store of the product
-                const float w0 = __fmul_rn(x0, __ldg(P.window + 2 * i));
-                const float w1 = __fmul_rn(x1, __ldg(P.window + 2 * i + 1));
-                if (EXACT) {  // BitReverseComplexArray lib/jsfft/fft.js:185-208, imag zero
-                    const int rshift = 32 - (log2M + 1);
-                    const int r0 = (int)(__brev((unsigned)(2 * i)) >> rshift);
-                    const int r1 = (int)(__brev((unsigned)(2 * i + 1)) >> rshift);
-                    xre[r0] = w0; xim[r0] = 0.f;
-                    xre[r1] = w1; xim[r1] = 0.f;
-                } else {
-                    work[pidx(i)] = make_float2(w0, w1);
-                }
-            }
-            if (want_time) {
-                S.energy = block_sum(e, red_d);
-                S.zcr = block_sum_int(z, red_i);
-            }
-            if (!EXACT && want_spectrum) {
-                // the reference squares |Z| in float64; a frame far outside the float32 comfort zone is
-                // rescaled by an exact power of two and scaled back on the way out
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) mxabs = fmaxf(mxabs, __shfl_xor_sync(0xffffffffu, mxabs, o));
-                __syncthreads();
-                if (lane == 0) red_f[warp] = mxabs;
-                __syncthreads();
-                float mx = 0.f;
-#pragma unroll
-                for (int w = 0; w < kWarps; w++) mx = fmaxf(mx, red_f[w]);
-                if (mx > 0.f && mx < 3.0e38f && (mx < 0x1p-40f || mx > 0x1p40f)) {
-                    int ex;
-                    (void)frexpf(mx, &ex);
-                    kscale = max(-100, min(100, -ex));
-                    const float up = ldexpf(1.f, kscale);
-                    for (int i = tid; i < M; i += kThreads) {
-                        float2 t = work[pidx(i)];
-                        work[pidx(i)] = make_float2(t.x * up, t.y * up);
-                    }
-                }
-            }
-        }
-        const float unscale = ldexpf(1.f, -kscale);
-        __syncthreads();
-
-        if (want_spectrum) {
-            MomentAcc acc;
-            if (EXACT) {
-                // ---- FFT_2_Iterative lib/jsfft/fft.js:139-168: doubles, no FMA, f32 stage stores
-                const double SQRT1_2 = 0.70710678118654752440;
-                for (int log2w = 0; log2w <= log2M; log2w++) {
-                    const int w = 1 << log2w;
-                    const double2 *__restrict__ tw = P.tw_exact + (w - 1);
-                    for (int idx = tid; idx < M; idx += kThreads) {
-                        const int j = idx & (w - 1);
-                        const int l = ((idx >> log2w) << (log2w + 1)) + j;
-                        const int r = l + w;
-                        const double2 f = __ldg(&tw[j]);
-                        const double lr = (double)xre[l], li = (double)xim[l];
-                        const double xr = (double)xre[r], xi = (double)xim[r];
-                        const double rr = __dsub_rn(__dmul_rn(f.x, xr), __dmul_rn(f.y, xi));
-                        const double ri = __dadd_rn(__dmul_rn(f.y, xr), __dmul_rn(f.x, xi));
-                        xre[l] = (float)__dmul_rn(SQRT1_2, __dadd_rn(lr, rr));
-                        xim[l] = (float)__dmul_rn(SQRT1_2, __dadd_rn(li, ri));
-                        xre[r] = (float)__dmul_rn(SQRT1_2, __dsub_rn(lr, rr));
-                        xim[r] = (float)__dmul_rn(SQRT1_2, __dsub_rn(li, ri));
-                    }
-                    __syncthreads();
-                }
-                if (mb_has(mask, MB_FEAT_COMPLEX_SPECTRUM)) {
-                    for (int k = tid; k < N; k += kThreads) {
-                        O.complex_real[g * N + k] = xre[k];
-                        O.complex_imag[g * N + k] = xim[k];
-                    }
-                }
-                for (int k = tid; k < M; k += kThreads) {  // computeAmplitude src/meyda.js:104-114
-                    const double r = (double)xre[k], i = (double)xim[k];
-                    const float av = (float)sqrt(__dadd_rn(__dmul_rn(r, r), __dmul_rn(i, i)));
-                    amp[k] = av;
-                    if (mb_has(mask, MB_FEAT_AMPLITUDE_SPECTRUM)) O.amplitude_spectrum[g * M + k] = av;
-                    if (mb_has(mask, MB_FEAT_POWER_SPECTRUM)) O.power_spectrum[g * M + k] = __fmul_rn(av, av);
-                    if (want_moments) acc.add(av, k, want_log);
-                }
-            } else {
-                // ---- in-place DIF FFT, output in bit-reversed positions
-                int log2s = log2M;
-                while (log2s > 0) {
-                    const int q = log2s >= 3 ? 3 : log2s;
-                    if (q == 3) fft_pass<3>(work, P.twM, M, log2M, log2s);
-                    else if (q == 2) fft_pass<2>(work, P.twM, M, log2M, log2s);
-                    else fft_pass<1>(work, P.twM, M, log2M, log2s);
-                    log2s -= q;
-                    __syncthreads();
-                }
-                // ---- real-FFT split, spectra out, amplitude into smem, moment partials
-                const float sc = P.inv_sqrt_N;
-                const int rshift = 32 - log2M;
-                for (int k = tid; k < M; k += kThreads) {
-                    const int kk = (M - k) & (M - 1);
-                    const float2 a = work[pidx((int)(__brev((unsigned)k) >> rshift))];
-                    const float2 b = work[pidx((int)(__brev((unsigned)kk) >> rshift))];
-                    const float er = 0.5f * (a.x + b.x), ei = 0.5f * (a.y - b.y);
-                    const float orr = 0.5f * (a.y + b.y), oi = -0.5f * (a.x - b.x);
-                    const float2 w = __ldg(&P.twN[k]);
-                    float zr = (er + (w.x * orr - w.y * oi)) * sc;
-                    float zi = (ei + (w.x * oi + w.y * orr)) * sc;
-                    if (mb_has(mask, MB_FEAT_COMPLEX_SPECTRUM)) {
-                        float *re = O.complex_real + g * N, *im = O.complex_imag + g * N;
-                        const float zro = zr * unscale, zio = zi * unscale;
-                        re[k] = zro;
-                        im[k] = zio;
-                        if (k > 0) {
-                            re[N - k] = zro;
-                            im[N - k] = -zio;
-                        } else {
-                            re[M] = (a.x - a.y) * sc * unscale;  // Nyquist bin: (E[0] - O[0]) / sqrt(N)
-                            im[M] = (a.x - a.y) * 0.f + 0.f;  // +0, or NaN when the frame holds a NaN
-                        }
-                    }
-                    const float av = sqrtf(zr * zr + zi * zi) * unscale;
-                    amp[k] = av;
-                    if (mb_has(mask, MB_FEAT_AMPLITUDE_SPECTRUM)) O.amplitude_spectrum[g * M + k] = av;
-                    if (mb_has(mask, MB_FEAT_POWER_SPECTRUM)) O.power_spectrum[g * M + k] = __fmul_rn(av, av);
-                    if (want_moments) acc.add(av, k, want_log);
-                }
-            }
-            frame_epilogue<EXACT>(P, O, g, S, acc, amp, sc);
-        }
-        if (tid == 64) mb_store_scalars(P, O, g, S);
-        __syncthreads();  // smem reused by the next frame
-    }
-}
-
-
-// ---- exact-FFT mode for a frame that does not fit one CTA ---------------------------------------
-// At bufferSize 32768 the reference's N-point complex transform needs 256 KB as float32 re/im -- more
-// than one CTA's shared memory.  A 2-CTA thread-block cluster holds it: CTA r keeps positions
-// [r N/2, (r+1) N/2) of the bit-reversed array.  Every radix-2 stage but the last pairs elements inside
-// one half; the last stage (width N/2) pairs element j of CTA 0 with element j of CTA 1, which each CTA
-// reads from its peer through distributed shared memory (cluster.map_shared_rank), after a
-// cluster-wide barrier.  Amplitudes are gathered into CTA 0, which runs the feature epilogue.
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads)
-mb_exact_cluster_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ MbClipTable T,
-                        const float *__restrict__ samples, const __grid_constant__ mb_outputs O) {
-    cg::cluster_group cluster = cg::this_cluster();
-    const unsigned rank = cluster.block_rank();
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int N = P.N, M = P.M, H = N / 2, log2N = P.log2M + 1;
-    float *xre = reinterpret_cast<float *>(smem_raw), *xim = xre + H, *amp = xim + H;  // amp[M] is used on CTA 0
-    __shared__ Scratch sc;
-    const float *re0 = cluster.map_shared_rank(xre, 0), *im0 = cluster.map_shared_rank(xim, 0);
-    const float *re1 = cluster.map_shared_rank(xre, 1), *im1 = cluster.map_shared_rank(xim, 1);
-    float *amp0 = cluster.map_shared_rank(amp, 0);
-
-    const uint32_t mask = P.mask;
-    const int tid = threadIdx.x;
-    const bool want_moments =
-        mask & (MB_FEATURE_BIT(MB_FEAT_SPECTRAL_CENTROID) | MB_FEATURE_BIT(MB_FEAT_SPECTRAL_SPREAD) |
-                MB_FEATURE_BIT(MB_FEAT_SPECTRAL_SKEWNESS) | MB_FEATURE_BIT(MB_FEAT_SPECTRAL_KURTOSIS) |
-                MB_FEATURE_BIT(MB_FEAT_SPECTRAL_FLATNESS) | MB_FEATURE_BIT(MB_FEAT_SPECTRAL_SLOPE));
-    const bool want_log = mb_has(mask, MB_FEAT_SPECTRAL_FLATNESS);
-    const bool want_time = mask & (MB_FEATURE_BIT(MB_FEAT_RMS) | MB_FEATURE_BIT(MB_FEAT_ENERGY) |
-                                   MB_FEATURE_BIT(MB_FEAT_ZCR) | MB_FEATURE_BIT(MB_FEAT_BUFFER));
-    const uint32_t time_only = MB_FEATURE_BIT(MB_FEAT_RMS) | MB_FEATURE_BIT(MB_FEAT_ENERGY) |
-                               MB_FEATURE_BIT(MB_FEAT_ZCR) | MB_FEATURE_BIT(MB_FEAT_BUFFER);
-    const bool want_spectrum = (mask & ~time_only) != 0;
-    const double SQRT1_2 = 0.70710678118654752440;
-    const int64_t n_clusters = gridDim.x / 2, cid = blockIdx.x / 2;
-
-    for (int64_t g = cid; g < T.total_frames; g += n_clusters) {
-        const int64_t clip = mb_find_clip(T, g);
-        const float *__restrict__ src = samples + T.clip_off[clip] + (g - T.frame_start[clip]) * (int64_t)P.hop;
-        MbFrameSums S;
-        S.s0 = S.s1 = S.s2 = S.s3 = S.s4 = S.log2sum = S.energy = 0;
-        S.zcr = 0;
-        S.rolloff_bin = M;
-
-        if (rank == 0 && want_time) {  // time-domain features over the whole raw frame
-            double e = 0;
-            int z = 0;
-            for (int i = tid; i < N; i += kThreads) {
-                const float x0 = __ldg(src + i);
-                e += (double)x0 * (double)x0;
-                if (i + 1 < N) {
-                    const float x1 = __ldg(src + i + 1);
-                    z += ((x0 >= 0.f) != (x1 >= 0.f)) && (x0 == x0) && (x1 == x1);
-                }
-                if (mb_has(mask, MB_FEAT_BUFFER)) O.buffer[g * N + i] = x0;
-            }
-            S.energy = block_sum(e, sc.red_d);
-            S.zcr = block_sum_int(z, sc.red_i);
-        }
-        if (want_spectrum) {
-            // this CTA's half of BitReverseComplexArray(windowed frame), imag zero
-            const int rshift = 32 - log2N;
-            for (int pl = tid; pl < H; pl += kThreads) {
-                const int i = (int)(__brev((unsigned)(rank * H + pl)) >> rshift);
-                xre[pl] = __fmul_rn(__ldg(src + i), __ldg(P.window + i));
-                xim[pl] = 0.f;
-            }
-            __syncthreads();
-            for (int log2w = 0; log2w < log2N - 1; log2w++) {  // widths 1 .. N/4: inside the half
-                const int w = 1 << log2w;
-                const double2 *__restrict__ tw = P.tw_exact + (w - 1);
-                for (int idx = tid; idx < H / 2; idx += kThreads) {
-                    const int j = idx & (w - 1);
-                    const int l = ((idx >> log2w) << (log2w + 1)) + j;
-                    const int r = l + w;
-                    const double2 f = __ldg(&tw[j]);
-                    const double lr = (double)xre[l], li = (double)xim[l];
-                    const double xr = (double)xre[r], xi = (double)xim[r];
-                    const double rr = __dsub_rn(__dmul_rn(f.x, xr), __dmul_rn(f.y, xi));
-                    const double ri = __dadd_rn(__dmul_rn(f.y, xr), __dmul_rn(f.x, xi));
-                    xre[l] = (float)__dmul_rn(SQRT1_2, __dadd_rn(lr, rr));
-                    xim[l] = (float)__dmul_rn(SQRT1_2, __dadd_rn(li, ri));
-                    xre[r] = (float)__dmul_rn(SQRT1_2, __dsub_rn(lr, rr));
-                    xim[r] = (float)__dmul_rn(SQRT1_2, __dsub_rn(li, ri));
-                }
-                __syncthreads();
-            }
-            cluster.sync();  // both halves are complete and visible cluster-wide
-            {                // width N/2: element j of CTA 0 with element j of CTA 1, through DSMEM
-                const double2 *__restrict__ tw = P.tw_exact + (H - 1);
-                for (int jj = tid; jj < H / 2; jj += kThreads) {
-                    const int j = (int)rank * (H / 2) + jj;
-                    const double2 f = __ldg(&tw[j]);
-                    const double lr = (double)re0[j], li = (double)im0[j];
-                    const double xr = (double)re1[j], xi = (double)im1[j];
-                    const double rr = __dsub_rn(__dmul_rn(f.x, xr), __dmul_rn(f.y, xi));
-                    const double ri = __dadd_rn(__dmul_rn(f.y, xr), __dmul_rn(f.x, xi));
-                    const float zr = (float)__dmul_rn(SQRT1_2, __dadd_rn(lr, rr));
-                    const float zi = (float)__dmul_rn(SQRT1_2, __dadd_rn(li, ri));
-                    if (mb_has(mask, MB_FEAT_COMPLEX_SPECTRUM)) {
-                        O.complex_real[g * N + j] = zr;
-                        O.complex_imag[g * N + j] = zi;
-                        O.complex_real[g * N + j + H] = (float)__dmul_rn(SQRT1_2, __dsub_rn(lr, rr));
-                        O.complex_imag[g * N + j + H] = (float)__dmul_rn(SQRT1_2, __dsub_rn(li, ri));
-                    }
-                    const float av = (float)sqrt(__dadd_rn(__dmul_rn((double)zr, (double)zr), __dmul_rn((double)zi, (double)zi)));
-                    amp0[j] = av;  // gathered on CTA 0
-                    if (mb_has(mask, MB_FEAT_AMPLITUDE_SPECTRUM)) O.amplitude_spectrum[g * M + j] = av;
-                    if (mb_has(mask, MB_FEAT_POWER_SPECTRUM)) O.power_spectrum[g * M + j] = __fmul_rn(av, av);
-                }
-            }
-            cluster.sync();  // CTA 0 holds all N/2 amplitudes
-            if (rank == 0) {
-                MomentAcc acc;
-                if (want_moments)
-                    for (int k = tid; k < M; k += kThreads) acc.add(amp[k], k, want_log);
-                frame_epilogue<true>(P, O, g, S, acc, amp, sc);
-            }
-        }
-        if (rank == 0 && tid == 64) mb_store_scalars(P, O, g, S);
-        cluster.sync();  // CTA 0 is done with the gathered amplitudes before the next frame overwrites them
-    }
-}
-
-}  // namespace
 
 size_t mb_generic_smem_bytes(int M, bool exact) {
     if (exact) return (size_t)(2 * M) * 2 * sizeof(float) + (size_t)M * sizeof(float);
@@ -581,41 +44,50 @@ size_t mb_generic_smem_bytes(int M, bool exact) {
     return (size_t)padded * sizeof(float2) + (size_t)M * sizeof(float);
 }
 
-template <bool EXACT>
-static cudaError_t launch_generic(const MbDevPlan &P, const MbClipTable &T, const float *samples,
-                                  const mb_outputs &O, int num_sms, cudaStream_t stream) {
-    const size_t smem = mb_generic_smem_bytes(P.M, EXACT);
-    cudaError_t e = cudaFuncSetAttribute(mb_generic_kernel<EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)smem);
-    if (e != cudaSuccess) return e;
-    int per_sm = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mb_generic_kernel<EXACT>, kThreads, smem);
-    if (per_sm < 1) per_sm = 1;
-    int64_t grid = (int64_t)num_sms * per_sm;
-    if (grid > T.total_frames) grid = T.total_frames;
-    if (grid < 1) return cudaSuccess;
-    (void)cudaGetLastError();  // drop any stale non-sticky error left by other users of the context
-    mb_generic_kernel<EXACT><<<(unsigned)grid, kThreads, smem, stream>>>(P, T, samples, O);
-    return cudaGetLastError();
-}
+#define MB_DEFINE_LAUNCH_GENERIC(NS, THREADS)                                                                        \
+    template <bool EXACT>                                                                                            \
+    static cudaError_t launch_generic_##NS(const MbDevPlan &P, const MbClipTable &T, const float *samples,          \
+                                           const mb_outputs &O, int num_sms, cudaStream_t stream) {                  \
+        const size_t smem = mb_generic_smem_bytes(P.M, EXACT);                                                       \
+        cudaError_t e = cudaFuncSetAttribute(NS::mb_generic_kernel<EXACT>,                                           \
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                \
+        if (e != cudaSuccess) return e;                                                                              \
+        int per_sm = 1;                                                                                              \
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, NS::mb_generic_kernel<EXACT>, THREADS, smem);         \
+        if (per_sm < 1) per_sm = 1;                                                                                  \
+        int64_t grid = (int64_t)num_sms * per_sm;                                                                    \
+        if (grid > T.total_frames) grid = T.total_frames;                                                            \
+        if (grid < 1) return cudaSuccess;                                                                            \
+        (void)cudaGetLastError(); /* drop any stale non-sticky error left by other users of the context */          \
+        NS::mb_generic_kernel<EXACT><<<(unsigned)grid, THREADS, smem, stream>>>(P, T, samples, O);                   \
+        return cudaGetLastError();                                                                                   \
+    }
+MB_DEFINE_LAUNCH_GENERIC(g256, 256)
+MB_DEFINE_LAUNCH_GENERIC(g1024, 1024)
 
 size_t mb_exact_cluster_smem_bytes(int N) { return (size_t)3 * (N / 2) * sizeof(float); }
 
 cudaError_t mb_launch_exact_cluster(const MbDevPlan &P, const MbClipTable &T, const float *samples, const mb_outputs &O,
                                     int num_sms, cudaStream_t stream) {
     const size_t smem = mb_exact_cluster_smem_bytes(P.N);
-    cudaError_t e = cudaFuncSetAttribute(mb_exact_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const bool big = P.N >= 8192;
+    cudaError_t e = cudaFuncSetAttribute(big ? g1024::mb_exact_cluster_kernel : g256::mb_exact_cluster_kernel,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int64_t clusters = num_sms / 2;
     if (clusters > T.total_frames) clusters = T.total_frames;
     if (clusters < 1) return cudaSuccess;
     (void)cudaGetLastError();
-    mb_exact_cluster_kernel<<<(unsigned)(2 * clusters), kThreads, smem, stream>>>(P, T, samples, O);
+    if (big) g1024::mb_exact_cluster_kernel<<<(unsigned)(2 * clusters), 1024, smem, stream>>>(P, T, samples, O);
+    else g256::mb_exact_cluster_kernel<<<(unsigned)(2 * clusters), 256, smem, stream>>>(P, T, samples, O);
     return cudaGetLastError();
 }
 
 cudaError_t mb_launch_generic(const MbDevPlan &P, const MbClipTable &T, const float *samples, const mb_outputs &O,
                               int num_sms, cudaStream_t stream) {
-    return P.exact ? launch_generic<true>(P, T, samples, O, num_sms, stream)
-                   : launch_generic<false>(P, T, samples, O, num_sms, stream);
+    if (P.N >= 8192)
+        return P.exact ? launch_generic_g1024<true>(P, T, samples, O, num_sms, stream)
+                       : launch_generic_g1024<false>(P, T, samples, O, num_sms, stream);
+    return P.exact ? launch_generic_g256<true>(P, T, samples, O, num_sms, stream)
+                   : launch_generic_g256<false>(P, T, samples, O, num_sms, stream);
 }

@@ -139,6 +139,13 @@ class Plan:
         return int(self._L.mb_plan_launch_count(self._h))
 
     def set_stream(self, cuda_stream: int | None):
+        """Launch on this cudaStream_t handle; None restores the plan's own stream.  Handle 0 (the legacy
+        default stream, e.g. torch's default `current_stream().cuda_stream`) is passed as cudaStreamLegacy,
+        because a NULL handle means "the plan's own stream" at the C ABI.  Device-memory calls are ordered
+        only against work on the stream they run on: buffers produced on another stream (a `torch.zeros`
+        on torch's stream, say) must be synchronised by the caller or share the stream."""
+        if cuda_stream == 0:
+            cuda_stream = 1  # cudaStreamLegacy
         _capi.check(self._L.mb_plan_set_stream(self._h, C.c_void_p(cuda_stream or 0)))
 
     def synchronize(self):

@@ -305,6 +305,7 @@ def test_full_size_properties(flags):
     x += 0.3 * torch.sin(2 * np.pi * (110.0 * (1 + torch.arange(n_clips, device="cuda"))[:, None]) * t[None, :])
     feats = ["rms", "energy", "zcr", "amplitudeSpectrum", "powerSpectrum", "loudness", "spectralCentroid", "mfcc"]
     plan = mb.Plan(N, hop, SR, features=feats, flags=flags)
+    plan.set_stream(torch.cuda.current_stream().cuda_stream)  # same stream as the torch.zeros fills below
     nf_clip = mo.num_frames(L, N, hop)
     nf = nf_clip * n_clips
     outs = {k: torch.zeros(s, dtype=torch.int32 if d == np.int32 else torch.float32, device="cuda")
