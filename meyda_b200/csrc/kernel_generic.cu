@@ -39,7 +39,7 @@ namespace g1024 {
 
 
 size_t mb_generic_smem_bytes(int M, bool exact) {
-    if (exact) return (size_t)(2 * M) * 2 * sizeof(float) + (size_t)M * sizeof(float);
+    if (exact) return (size_t)2 * (2 * M + (2 * M >> 5) + 1) * sizeof(float) + (size_t)M * sizeof(float);  // padded re, im; amp
     const int padded = M + (M >> 5) + (M >> 10) + 1;
     return (size_t)padded * sizeof(float2) + (size_t)M * sizeof(float);
 }
@@ -65,7 +65,10 @@ size_t mb_generic_smem_bytes(int M, bool exact) {
 MB_DEFINE_LAUNCH_GENERIC(g256, 256)
 MB_DEFINE_LAUNCH_GENERIC(g1024, 1024)
 
-size_t mb_exact_cluster_smem_bytes(int N) { return (size_t)3 * (N / 2) * sizeof(float); }
+size_t mb_exact_cluster_smem_bytes(int N) {
+    const size_t H = (size_t)N / 2;
+    return (2 * (H + (H >> 5) + 1) + H) * sizeof(float);  // padded re, im halves; gathered amplitudes
+}
 
 cudaError_t mb_launch_exact_cluster(const MbDevPlan &P, const MbClipTable &T, const float *samples, const mb_outputs &O,
                                     int num_sms, cudaStream_t stream) {

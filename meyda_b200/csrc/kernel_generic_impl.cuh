@@ -13,6 +13,70 @@ __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
     return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
 }
 
+// ---- exact mode: the reference's butterfly (lib/jsfft/fft.js:151-161) on float32-stored values, in
+// float64 without FMA contraction, rounded to float32 where the reference stores into its Float32Array.
+__device__ __forceinline__ int xidx(int i) { return i + (i >> 5); }  // one pad word per 32: conflict-free strides
+
+__device__ __forceinline__ void exact_bfly(float &l_r, float &l_i, float &r_r, float &r_i, const double2 f) {
+    const double SQRT1_2 = 0.70710678118654752440;
+    const double lr = (double)l_r, li = (double)l_i, xr = (double)r_r, xi = (double)r_i;
+    const double rr = __dsub_rn(__dmul_rn(f.x, xr), __dmul_rn(f.y, xi));
+    const double ri = __dadd_rn(__dmul_rn(f.y, xr), __dmul_rn(f.x, xi));
+    l_r = (float)__dmul_rn(SQRT1_2, __dadd_rn(lr, rr));
+    l_i = (float)__dmul_rn(SQRT1_2, __dadd_rn(li, ri));
+    r_r = (float)__dmul_rn(SQRT1_2, __dsub_rn(lr, rr));
+    r_i = (float)__dmul_rn(SQRT1_2, __dsub_rn(li, ri));
+}
+
+// Q consecutive radix-2 DIT stages (widths w, 2w, .. 2^(Q-1) w) of an n-point array fused in registers:
+// the same butterflies in the same order of stages as FFT_2_Iterative, each result rounded to float32
+// exactly where the stage-by-stage loop would have stored it, so the outcome is bit-identical.
+template <int Q>
+__device__ __forceinline__ void exact_pass(float *xre, float *xim, const double2 *__restrict__ tw_exact, int n,
+                                           int log2w) {
+    constexpr int R = 1 << Q;
+    const int w = 1 << log2w;
+    for (int idx = threadIdx.x; idx < (n >> Q); idx += kThreads) {
+        const int j = idx & (w - 1);
+        const int base = ((idx >> log2w) << (log2w + Q)) + j;
+        float re[R], im[R];
+#pragma unroll
+        for (int t = 0; t < R; t++) {
+            re[t] = xre[xidx(base + t * w)];
+            im[t] = xim[xidx(base + t * w)];
+        }
+#pragma unroll
+        for (int q = 0; q < Q; q++) {
+            const int h = 1 << q;  // partner distance in units of w; this stage has width h * w
+            const double2 *__restrict__ tw = tw_exact + ((w << q) - 1);
+#pragma unroll
+            for (int t = 0; t < R; t++) {
+                if (t & h) continue;
+                exact_bfly(re[t], im[t], re[t + h], im[t + h], __ldg(&tw[j + (t & (h - 1)) * w]));
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < R; t++) {
+            xre[xidx(base + t * w)] = re[t];
+            xim[xidx(base + t * w)] = im[t];
+        }
+    }
+}
+
+// stages of widths 2^first .. 2^(last-1) of an n-point array, three at a time
+__device__ __forceinline__ void exact_stages(float *xre, float *xim, const double2 *__restrict__ tw_exact, int n,
+                                             int first, int last) {
+    int log2w = first;
+    while (log2w < last) {
+        const int q = last - log2w >= 3 ? 3 : last - log2w;
+        if (q == 3) exact_pass<3>(xre, xim, tw_exact, n, log2w);
+        else if (q == 2) exact_pass<2>(xre, xim, tw_exact, n, log2w);
+        else exact_pass<1>(xre, xim, tw_exact, n, log2w);
+        log2w += q;
+        __syncthreads();
+    }
+}
+
 // Q fused radix-2 DIF stages starting at span 2^log2s: 2^Q points per work item.
 template <int Q>
 __device__ __forceinline__ void fft_pass(float2 *work, const float2 *__restrict__ twM, int M, int log2M, int log2s) {
@@ -240,8 +304,8 @@ mb_generic_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ M
     // fast: work = padded M complex, then amp[M].  exact: re[N], im[N], then amp[M].
     float2 *work = reinterpret_cast<float2 *>(smem_raw);
     float *xre = reinterpret_cast<float *>(smem_raw);
-    float *xim = xre + N;
-    float *amp = EXACT ? (xim + N) : reinterpret_cast<float *>(work + pidx(M) + 1);
+    float *xim = xre + xidx(N) + 1;
+    float *amp = EXACT ? (xim + xidx(N) + 1) : reinterpret_cast<float *>(work + pidx(M) + 1);
 
     __shared__ Scratch sc;
     double *red_d = sc.red_d;
@@ -300,8 +364,8 @@ mb_generic_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ M
                     const int rshift = 32 - (log2M + 1);
                     const int r0 = (int)(__brev((unsigned)(2 * i)) >> rshift);
                     const int r1 = (int)(__brev((unsigned)(2 * i + 1)) >> rshift);
-                    xre[r0] = w0; xim[r0] = 0.f;
-                    xre[r1] = w1; xim[r1] = 0.f;
+                    xre[xidx(r0)] = w0; xim[xidx(r0)] = 0.f;
+                    xre[xidx(r1)] = w1; xim[xidx(r1)] = 0.f;
                 } else {
                     work[pidx(i)] = make_float2(w0, w1);
                 }
@@ -340,34 +404,15 @@ mb_generic_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ M
             MomentAcc acc;
             if (EXACT) {
                 // ---- FFT_2_Iterative lib/jsfft/fft.js:139-168: doubles, no FMA, f32 stage stores
-                const double SQRT1_2 = 0.70710678118654752440;
-                for (int log2w = 0; log2w <= log2M; log2w++) {
-                    const int w = 1 << log2w;
-                    const double2 *__restrict__ tw = P.tw_exact + (w - 1);
-                    for (int idx = tid; idx < M; idx += kThreads) {
-                        const int j = idx & (w - 1);
-                        const int l = ((idx >> log2w) << (log2w + 1)) + j;
-                        const int r = l + w;
-                        const double2 f = __ldg(&tw[j]);
-                        const double lr = (double)xre[l], li = (double)xim[l];
-                        const double xr = (double)xre[r], xi = (double)xim[r];
-                        const double rr = __dsub_rn(__dmul_rn(f.x, xr), __dmul_rn(f.y, xi));
-                        const double ri = __dadd_rn(__dmul_rn(f.y, xr), __dmul_rn(f.x, xi));
-                        xre[l] = (float)__dmul_rn(SQRT1_2, __dadd_rn(lr, rr));
-                        xim[l] = (float)__dmul_rn(SQRT1_2, __dadd_rn(li, ri));
-                        xre[r] = (float)__dmul_rn(SQRT1_2, __dsub_rn(lr, rr));
-                        xim[r] = (float)__dmul_rn(SQRT1_2, __dsub_rn(li, ri));
-                    }
-                    __syncthreads();
-                }
+                exact_stages(xre, xim, P.tw_exact, N, 0, log2M + 1);
                 if (mb_has(mask, MB_FEAT_COMPLEX_SPECTRUM)) {
                     for (int k = tid; k < N; k += kThreads) {
-                        O.complex_real[g * N + k] = xre[k];
-                        O.complex_imag[g * N + k] = xim[k];
+                        O.complex_real[g * N + k] = xre[xidx(k)];
+                        O.complex_imag[g * N + k] = xim[xidx(k)];
                     }
                 }
                 for (int k = tid; k < M; k += kThreads) {  // computeAmplitude src/meyda.js:104-114
-                    const double r = (double)xre[k], i = (double)xim[k];
+                    const double r = (double)xre[xidx(k)], i = (double)xim[xidx(k)];
                     const float av = (float)sqrt(__dadd_rn(__dmul_rn(r, r), __dmul_rn(i, i)));
                     amp[k] = av;
                     if (mb_has(mask, MB_FEAT_AMPLITUDE_SPECTRUM)) O.amplitude_spectrum[g * M + k] = av;
@@ -439,7 +484,7 @@ mb_exact_cluster_kernel(const __grid_constant__ MbDevPlan P, const __grid_consta
     const unsigned rank = cluster.block_rank();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int N = P.N, M = P.M, H = N / 2, log2N = P.log2M + 1;
-    float *xre = reinterpret_cast<float *>(smem_raw), *xim = xre + H, *amp = xim + H;  // amp[M] is used on CTA 0
+    float *xre = reinterpret_cast<float *>(smem_raw), *xim = xre + xidx(H) + 1, *amp = xim + xidx(H) + 1;  // amp[M]: CTA 0
     __shared__ Scratch sc;
     const float *re0 = cluster.map_shared_rank(xre, 0), *im0 = cluster.map_shared_rank(xim, 0);
     const float *re1 = cluster.map_shared_rank(xre, 1), *im1 = cluster.map_shared_rank(xim, 1);
@@ -488,37 +533,19 @@ mb_exact_cluster_kernel(const __grid_constant__ MbDevPlan P, const __grid_consta
             const int rshift = 32 - log2N;
             for (int pl = tid; pl < H; pl += kThreads) {
                 const int i = (int)(__brev((unsigned)(rank * H + pl)) >> rshift);
-                xre[pl] = __fmul_rn(__ldg(src + i), __ldg(P.window + i));
-                xim[pl] = 0.f;
+                xre[xidx(pl)] = __fmul_rn(__ldg(src + i), __ldg(P.window + i));
+                xim[xidx(pl)] = 0.f;
             }
             __syncthreads();
-            for (int log2w = 0; log2w < log2N - 1; log2w++) {  // widths 1 .. N/4: inside the half
-                const int w = 1 << log2w;
-                const double2 *__restrict__ tw = P.tw_exact + (w - 1);
-                for (int idx = tid; idx < H / 2; idx += kThreads) {
-                    const int j = idx & (w - 1);
-                    const int l = ((idx >> log2w) << (log2w + 1)) + j;
-                    const int r = l + w;
-                    const double2 f = __ldg(&tw[j]);
-                    const double lr = (double)xre[l], li = (double)xim[l];
-                    const double xr = (double)xre[r], xi = (double)xim[r];
-                    const double rr = __dsub_rn(__dmul_rn(f.x, xr), __dmul_rn(f.y, xi));
-                    const double ri = __dadd_rn(__dmul_rn(f.y, xr), __dmul_rn(f.x, xi));
-                    xre[l] = (float)__dmul_rn(SQRT1_2, __dadd_rn(lr, rr));
-                    xim[l] = (float)__dmul_rn(SQRT1_2, __dadd_rn(li, ri));
-                    xre[r] = (float)__dmul_rn(SQRT1_2, __dsub_rn(lr, rr));
-                    xim[r] = (float)__dmul_rn(SQRT1_2, __dsub_rn(li, ri));
-                }
-                __syncthreads();
-            }
+            exact_stages(xre, xim, P.tw_exact, H, 0, log2N - 1);  // widths 1 .. N/4: inside the half
             cluster.sync();  // both halves are complete and visible cluster-wide
             {                // width N/2: element j of CTA 0 with element j of CTA 1, through DSMEM
                 const double2 *__restrict__ tw = P.tw_exact + (H - 1);
                 for (int jj = tid; jj < H / 2; jj += kThreads) {
                     const int j = (int)rank * (H / 2) + jj;
                     const double2 f = __ldg(&tw[j]);
-                    const double lr = (double)re0[j], li = (double)im0[j];
-                    const double xr = (double)re1[j], xi = (double)im1[j];
+                    const double lr = (double)re0[xidx(j)], li = (double)im0[xidx(j)];
+                    const double xr = (double)re1[xidx(j)], xi = (double)im1[xidx(j)];
                     const double rr = __dsub_rn(__dmul_rn(f.x, xr), __dmul_rn(f.y, xi));
                     const double ri = __dadd_rn(__dmul_rn(f.y, xr), __dmul_rn(f.x, xi));
                     const float zr = (float)__dmul_rn(SQRT1_2, __dadd_rn(lr, rr));
