@@ -110,6 +110,7 @@ struct mb_plan {
     float *d_window = nullptr, *d_dct = nullptr, *d_mel_inv = nullptr;
     float2 *d_twM = nullptr, *d_twN = nullptr;
     double2 *d_tw_exact = nullptr;
+    double *d_mel_w_exact = nullptr;
     MbWarpTables *d_warp_tables = nullptr;
     bool has_warp_kernel = false;
     bool use_cluster = false;
@@ -475,7 +476,17 @@ mb_status mb_plan_create(mb_plan **plan, int device, int buffer_size, int hop, d
             }
         }
     }
-    bool ok = upload(&p->d_tw_exact, tw_exact) == cudaSuccess && upload(&p->d_window, p->h_window) == cudaSuccess && upload(&p->d_dct, dct) == cudaSuccess &&
+    std::vector<double> mel_w;
+    if (flags & MB_FLAG_EXACT_FFT) {  // src/extractors/mfcc.js:45-50, evaluated in doubles as the reference does
+        for (int f = 0; f < MB_NUM_MEL_FILTERS; f++) {
+            D.mel_w_off[f] = (int)mel_w.size();
+            const int e0 = D.mel[f], e1 = D.mel[f + 1], e2 = D.mel[f + 2];
+            for (int k = e0; k < e1; k++) mel_w.push_back((double)(k - e0) / (double)(e1 - e0));
+            for (int k = e1; k < e2; k++) mel_w.push_back((double)(e2 - k) / (double)(e2 - e1));
+        }
+        D.mel_w_off[MB_NUM_MEL_FILTERS] = (int)mel_w.size();
+    }
+    bool ok = upload(&p->d_mel_w_exact, mel_w) == cudaSuccess && upload(&p->d_tw_exact, tw_exact) == cudaSuccess && upload(&p->d_window, p->h_window) == cudaSuccess && upload(&p->d_dct, dct) == cudaSuccess &&
               upload(&p->d_mel_inv, mel_inv) == cudaSuccess && upload(&p->d_twM, twM) == cudaSuccess &&
               upload(&p->d_twN, twN) == cudaSuccess &&
               cudaStreamCreateWithFlags(&p->own_stream, cudaStreamNonBlocking) == cudaSuccess &&
@@ -492,6 +503,7 @@ mb_status mb_plan_create(mb_plan **plan, int device, int buffer_size, int hop, d
     D.twM = p->d_twM;
     D.twN = p->d_twN;
     D.tw_exact = p->d_tw_exact;
+    D.mel_w_exact = p->d_mel_w_exact;
     D.exact = (flags & MB_FLAG_EXACT_FFT) ? 1 : 0;
     if (D.exact) p->kernel_name = "generic-exact";
     if (D.exact && (N > 16384 || ((flags & MB_FLAG_CLUSTER_FFT) && N >= 64))) {
@@ -538,6 +550,7 @@ void mb_plan_destroy(mb_plan *p) {
     cudaFree(p->d_twM);
     cudaFree(p->d_twN);
     cudaFree(p->d_tw_exact);
+    cudaFree(p->d_mel_w_exact);
     cudaFree(p->d_warp_tables);
     cudaFree(p->d_tab);
     if (p->h_tab) cudaFreeHost(p->h_tab);

@@ -228,16 +228,14 @@ __device__ __forceinline__ void frame_epilogue(const MbDevPlan &P, const mb_outp
         if (EXACT) {  // the reference's order: one float32 running sum per filter
             if (tid < MB_NUM_MEL_FILTERS) {
                 const int e0 = P.mel[tid], e1 = P.mel[tid + 1], e2 = P.mel[tid + 2];
+                // weights (i - lo) / (hi - lo) and (hi - i) / (hi - lo) come from the plan (float64 divisions
+                // done once, mfcc.js:45-50); the float32 running sum keeps the reference's order (mfcc.js:56-62)
+                const double *__restrict__ wgt = P.mel_w_exact + P.mel_w_off[tid] - e0;
+                (void)e1;
                 float s = 0.f;
-                for (int k = e0; k < e1 && k < M; k++) {
-                    const double wgt = (double)(k - e0) / (double)(e1 - e0);
+                for (int k = e0; k < e2 && k < M; k++) {
                     const float a = amp[k];
-                    s = (float)__dadd_rn((double)s, __dmul_rn(wgt, (double)__fmul_rn(a, a)));
-                }
-                for (int k = e1; k < e2 && k < M; k++) {
-                    const double wgt = (double)(e2 - k) / (double)(e2 - e1);
-                    const float a = amp[k];
-                    s = (float)__dadd_rn((double)s, __dmul_rn(wgt, (double)__fmul_rn(a, a)));
+                    s = (float)__dadd_rn((double)s, __dmul_rn(__ldg(wgt + k), (double)__fmul_rn(a, a)));
                 }
                 mel_log[tid] = (float)log((double)s);
             }

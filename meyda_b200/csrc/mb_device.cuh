@@ -52,6 +52,8 @@ struct MbDevPlan {
     const float *mel_inv_width; // [27] 1 / (mel[s+1] - mel[s]) (0 if empty)
     const double2 *tw_exact;    // [N-1] jsfft recurrence twiddles, stage of width w at [w-1, 2w-1) (exact mode)
     int exact;                  // MB_FLAG_EXACT_FFT
+    const double *mel_w_exact;  // exact mode: filter f's weights for bins mel[f] .. mel[f+2]-1, (i-lo)/(hi-lo) as doubles
+    int mel_w_off[MB_NUM_MEL_FILTERS + 1];  // offsets of each filter's run in mel_w_exact
     const MbWarpTables *warp_tables;  // bufferSize 2048 only, else NULL
     int bb[MB_NUM_BARK_BANDS + 1];     // loudness.js:24-45
     int mel[MB_NUM_MEL_FILTERS + 2];   // mfcc.js:31-38
