@@ -440,23 +440,23 @@ mb_warp2048_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
                     const float zr = fmaf(hsc, sx, fmaf(w.x, sy, w.y * dx));
                     const float zi = fmaf(hsc, dy, fmaf(w.y, sy, -(w.x * dx)));
                     if (want_cs && exp_store) {
-                        const float zro = zr * unscale, zio = zi * unscale;
-                        st_stream(out_re + 32 * d, zro);
-                        st_stream(out_im + 32 * d, zio);
+                        // (a rescaled frame, kscale != 0, is brought back to its own units by the fix-up below)
+                        st_stream(out_re + 32 * d, zr);
+                        st_stream(out_im + 32 * d, zi);
                         if (d == 0 && lane == 0) {
-                            st_stream(out_re + kM, (a.x - a.y) * sc * unscale);  // Nyquist bin (E[0] - O[0]) / sqrt(N)
-                            st_stream(out_im + kM, (a.x - a.y) * 0.f + 0.f);     // +0, or NaN when the frame holds a NaN
+                            st_stream(out_re + kM, (a.x - a.y) * sc);         // Nyquist bin (E[0] - O[0]) / sqrt(N)
+                            st_stream(out_im + kM, (a.x - a.y) * 0.f + 0.f);  // +0, or NaN when the frame holds a NaN
                         } else {
-                            st_stream(mir_re - 32 * d, zro);
-                            st_stream(mir_im - 32 * d, -zio);
+                            st_stream(mir_re - 32 * d, zr);
+                            st_stream(mir_im - 32 * d, -zi);
                         }
                     }
-                    const float amp_s = sqrt_approx(fmaf(zr, zr, zi * zi));  // in the frame's rescaled units
-                    const float amp = amp_s * unscale;
+                    const float amp = sqrt_approx(fmaf(zr, zr, zi * zi));
                     av[d] = amp;
                     if (want_amp_out && exp_store) st_stream(out_amp + 32 * d, amp);
                     if (want_pow_out && exp_store) st_stream(out_pow + 32 * d, __fmul_rn(amp, amp));
                     if (want_moments) {
+                        // centroid .. kurtosis, flatness and slope are ratios: the frame's rescaling cancels
                         const double ad = (double)amp, kd = (double)k;
                         double t = ad * kd;
                         s0 += ad;
@@ -464,7 +464,7 @@ mb_warp2048_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
                         t *= kd; s2 += t;
                         t *= kd; s3 += t;
                         t *= kd; s4 += t;
-                        if (want_log) lg += log2_approx(amp_s);
+                        if (want_log) lg += log2_approx(amp);
                     }
                 }
                 if (want_moments) {
@@ -480,7 +480,24 @@ mb_warp2048_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
                         stash_put_d(stash, 6, j, s2);
                         stash_put_d(stash, 8, j, s3);
                         stash_put_d(stash, 10, j, s4);
-                        stash[12][j] = lg - (float)(kM * kscale);  // sum log2 |Z| = sum log2 (2^k |Z|) - n k
+                        stash[12][j] = lg;
+                    }
+                }
+
+                if (kscale != 0) {
+                    // Rare: the frame was rescaled by 2^kscale.  Bring the stored spectra (each lane re-reads what
+                    // it wrote) and the amplitudes used by the band features back to the frame's own units.
+#pragma unroll
+                    for (int d = 0; d < 32; d++) {
+                        av[d] *= unscale;
+                        if (want_cs && exp_store) {
+                            out_re[32 * d] *= unscale;
+                            out_im[32 * d] *= unscale;
+                            if (d == 0 && lane == 0) out_re[kM] *= unscale;
+                            else { mir_re[-32 * d] *= unscale; mir_im[-32 * d] *= unscale; }
+                        }
+                        if (want_amp_out && exp_store) out_amp[32 * d] = av[d];
+                        if (want_pow_out && exp_store) out_pow[32 * d] = __fmul_rn(av[d], av[d]);
                     }
                 }
 
