@@ -114,6 +114,7 @@ struct mb_plan {
     MbWarpTables *d_warp_tables = nullptr;
     bool has_warp_kernel = false;
     bool use_cluster = false;
+    bool has_big_kernel = false;
     int64_t launches_warp = 0, launches_generic = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr;
     // device-memory calls: clip tables staged through pinned memory
@@ -269,6 +270,9 @@ mb_status launch(mb_plan *p, const int64_t *d_off, const int64_t *d_frame_start,
     if (p->use_cluster) {
         MB_CUDA(mb_launch_exact_cluster(p->dev, T, d_samples, d_out, p->num_sms, stream));
         p->launches_generic++;
+    } else if (p->has_big_kernel && tma_ok) {
+        MB_CUDA(mb_launch_big32768(p->dev, T, d_samples, d_out, p->num_sms, stream));
+        p->launches_warp++;
     } else if (p->has_warp_kernel && tma_ok) {
         MB_CUDA(mb_launch_warp2048(p->dev, T, d_samples, d_out, p->num_sms, stream));
         p->launches_warp++;
@@ -511,6 +515,11 @@ mb_status mb_plan_create(mb_plan **plan, int device, int buffer_size, int hop, d
         p->kernel_name = "exact-cluster2";
     }
     D.warp_tables = nullptr;
+    if (N == 32768 && !D.exact && !(flags & MB_FLAG_GENERIC_KERNEL) &&
+        (size_t)prop.sharedMemPerBlockOptin >= mb_big32768_smem_bytes() + 2048) {
+        p->has_big_kernel = true;
+        p->kernel_name = "big32768";
+    }
     if (N == 2048 && !D.exact && !(flags & MB_FLAG_GENERIC_KERNEL)) {
         MbWarpTables *W = new MbWarpTables();
         build_warp_tables(*W, D);

@@ -20,6 +20,7 @@
 #include <cooperative_groups.h>
 
 #include "mb_device.cuh"
+#include "mb_fft.cuh"
 #include "mb_kernels.h"
 
 namespace cg = cooperative_groups;
@@ -31,6 +32,11 @@ namespace g256 {
 #include "kernel_generic_impl.cuh"
 #undef MB_GENERIC_THREADS
 }  // namespace g256
+namespace g512 {  // hosts the bufferSize-32768 kernel (16 warps per frame)
+#define MB_GENERIC_THREADS 512
+#include "kernel_generic_impl.cuh"
+#undef MB_GENERIC_THREADS
+}  // namespace g512
 namespace g1024 {
 #define MB_GENERIC_THREADS 1024
 #include "kernel_generic_impl.cuh"
@@ -64,6 +70,21 @@ size_t mb_generic_smem_bytes(int M, bool exact) {
     }
 MB_DEFINE_LAUNCH_GENERIC(g256, 256)
 MB_DEFINE_LAUNCH_GENERIC(g1024, 1024)
+
+size_t mb_big32768_smem_bytes() { return sizeof(g512::BigSmem); }
+
+cudaError_t mb_launch_big32768(const MbDevPlan &P, const MbClipTable &T, const float *samples, const mb_outputs &O,
+                               int num_sms, cudaStream_t stream) {
+    const size_t smem = mb_big32768_smem_bytes();
+    cudaError_t e = cudaFuncSetAttribute(g512::mb_big32768_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int64_t grid = num_sms;
+    if (grid > T.total_frames) grid = T.total_frames;
+    if (grid < 1) return cudaSuccess;
+    (void)cudaGetLastError();
+    g512::mb_big32768_kernel<<<(unsigned)grid, 512, smem, stream>>>(P, T, samples, O);
+    return cudaGetLastError();
+}
 
 size_t mb_exact_cluster_smem_bytes(int N) {
     const size_t H = (size_t)N / 2;

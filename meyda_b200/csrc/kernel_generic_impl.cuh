@@ -108,15 +108,15 @@ __device__ __forceinline__ void fft_pass(float2 *work, const float2 *__restrict_
     }
 }
 
+// Block-wide sums: per-warp partials through shared memory, then every warp folds them with shuffles
+// (kWarps <= 32), so all threads get the total.
 __device__ __forceinline__ double block_sum(double v, double *scratch /*[kWarps]*/) {
     v = mb_warp_sum(v);
     __syncthreads();
     if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
     __syncthreads();
-    double r = 0;
-#pragma unroll
-    for (int w = 0; w < kWarps; w++) r += scratch[w];
-    return r;
+    const int lane = threadIdx.x & 31;
+    return mb_warp_sum(lane < kWarps ? scratch[lane] : 0.0);
 }
 
 __device__ __forceinline__ int block_sum_int(int v, int *scratch /*[kWarps]*/) {
@@ -124,10 +124,8 @@ __device__ __forceinline__ int block_sum_int(int v, int *scratch /*[kWarps]*/) {
     __syncthreads();
     if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
     __syncthreads();
-    int r = 0;
-#pragma unroll
-    for (int w = 0; w < kWarps; w++) r += scratch[w];
-    return r;
+    const int lane = threadIdx.x & 31;
+    return mb_warp_sum(lane < kWarps ? scratch[lane] : 0);
 }
 
 struct MomentAcc {
@@ -184,32 +182,33 @@ __device__ __forceinline__ void frame_epilogue(const MbDevPlan &P, const mb_outp
 
     // ---- rolloff: prefix sums of the amplitude spectrum in double
     if (mb_has(mask, MB_FEAT_SPECTRAL_ROLLOFF)) {
-        const int chunk = (M + kThreads - 1) / kThreads;
-        const int k0 = min(M, tid * chunk), k1 = min(M, k0 + chunk);
-        double csum = 0;
-        for (int k = k0; k < k1; k++) csum += (double)amp[k];
-        double incl = csum;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const double y = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += y;
-        }
-        if (lane == 31) scan_d[warp] = incl;
+        // warp w owns the contiguous bins [w L, (w+1) L); lanes read them 32 at a time (coalesced, no bank
+        // conflicts): first the warp totals, then a running scan that counts the bins m with P[m] <= thr
+        const int L = max(32, (M + kWarps - 1) / kWarps);
+        const int k_lo = min(M, warp * L), k_hi = min(M, k_lo + L);
+        double part = 0;
+        for (int k = k_lo + lane; k < k_hi; k += 32) part += (double)amp[k];
+        part = mb_warp_sum(part);
+        if (lane == 0) scan_d[warp] = part;
         __syncthreads();
-        double base = 0, total = 0;
-#pragma unroll
-        for (int w = 0; w < kWarps; w++) {
-            if (w < warp) base += scan_d[w];
-            total += scan_d[w];
-        }
+        const double mine = lane < kWarps ? scan_d[lane] : 0.0;
+        const double total = mb_warp_sum(mine);
+        double run = mb_warp_sum(lane < warp ? mine : 0.0);  // sum of amp[0 .. k_lo)
         const double thr = 0.99 * total;
-        double pre = base + incl - csum;  // sum of amp[0..k0)
         int cnt = 0;
-        for (int k = k0; k < k1; k++) {
-            cnt += (pre <= thr);
-            pre += (double)amp[k];
+        for (int k0 = k_lo; k0 < k_hi; k0 += 32) {
+            const int k = k0 + lane;
+            const double x = k < k_hi ? (double)amp[k] : 0.0;
+            double incl = x;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const double y = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += y;
+            }
+            cnt += __popc(__ballot_sync(0xffffffffu, k < k_hi && run + (incl - x) <= thr));
+            run += __shfl_sync(0xffffffffu, incl, 31);
         }
-        cnt = block_sum_int(cnt, red_i);
+        cnt = block_sum_int(lane == 0 ? cnt : 0, red_i);
         // spectralRolloff.js:11-15: the loop only runs while ec > threshold
         S.rolloff_bin = (total > thr) ? cnt - 1 : M;
     }
@@ -573,3 +572,203 @@ mb_exact_cluster_kernel(const __grid_constant__ MbDevPlan P, const __grid_consta
     }
 }
 
+#if MB_GENERIC_THREADS == 512
+// ---- bufferSize 32768, float32 FFT: one CTA (16 warps) per frame ---------------------------------
+// The packed frame is M = 16384 complex points = 16 x 1024.  Decimation in time by 16: warp r
+// transforms z_r[m] = z[16 m + r] with the same 32 x 32 register FFT as the bufferSize-2048 kernel
+// (two register FFTs and one transpose through the warp's slot), multiplies X_r[k] by
+// exp(+2 pi i r k / M), and a radix-16 register FFT across the sixteen warps' results gives
+// C[k + 1024 q].  Shared memory (213 KB): one 136 KB area that is in turn the padded windowed frame,
+// the sixteen transpose slots, the twiddled sub-spectra and the natural-order spectrum; 64 KB of
+// amplitudes for the band features; 12 KB of twiddle tables.
+constexpr int kBigN = 32768, kBigM = 16384, kBigRow = 33, kBigSlot = 32 * kBigRow;  // slot: 1056 float2
+struct BigSmem {
+    float2 area[kBigM + kBigM / 16];  // 17408 float2: z padded one per 16; >= 16 slots of 1056; >= C[16384]
+    float amp[kBigM];
+    float2 tw32[32 * 32];             // exp(+2 pi i b c / 1024) at [c*32 + b]
+    float2 tw16[16 * 32];             // exp(+2 pi i r d / 512) at [r*32 + d]
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+mb_big32768_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ MbClipTable T,
+                   const float *__restrict__ samples, const __grid_constant__ mb_outputs O) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    BigSmem &B = *reinterpret_cast<BigSmem *>(smem_raw);
+    __shared__ Scratch sc;
+    const int N = kBigN, M = kBigM;
+    const uint32_t mask = P.mask;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool want_moments =
+        mask & (MB_FEATURE_BIT(MB_FEAT_SPECTRAL_CENTROID) | MB_FEATURE_BIT(MB_FEAT_SPECTRAL_SPREAD) |
+                MB_FEATURE_BIT(MB_FEAT_SPECTRAL_SKEWNESS) | MB_FEATURE_BIT(MB_FEAT_SPECTRAL_KURTOSIS) |
+                MB_FEATURE_BIT(MB_FEAT_SPECTRAL_FLATNESS) | MB_FEATURE_BIT(MB_FEAT_SPECTRAL_SLOPE));
+    const bool want_log = mb_has(mask, MB_FEAT_SPECTRAL_FLATNESS);
+    const bool want_time = mask & (MB_FEATURE_BIT(MB_FEAT_RMS) | MB_FEATURE_BIT(MB_FEAT_ENERGY) |
+                                   MB_FEATURE_BIT(MB_FEAT_ZCR) | MB_FEATURE_BIT(MB_FEAT_BUFFER));
+    const uint32_t time_only = MB_FEATURE_BIT(MB_FEAT_RMS) | MB_FEATURE_BIT(MB_FEAT_ENERGY) |
+                               MB_FEATURE_BIT(MB_FEAT_ZCR) | MB_FEATURE_BIT(MB_FEAT_BUFFER);
+    const bool want_spectrum = (mask & ~time_only) != 0;
+    const bool want_cs = mb_has(mask, MB_FEAT_COMPLEX_SPECTRUM);
+
+    // tables (once per persistent CTA) and this thread's own twiddle exp(+2 pi i warp lane / M)
+    for (int i = tid; i < 32 * 32; i += kThreads) {
+        const double ang = 2.0 * 3.14159265358979323846 * (double)((i >> 5) * (i & 31)) / 1024.0;
+        B.tw32[i] = make_float2((float)cos(ang), (float)sin(ang));
+    }
+    for (int i = tid; i < 16 * 32; i += kThreads) {
+        const double ang = 2.0 * 3.14159265358979323846 * (double)((i >> 5) * (i & 31)) / 512.0;
+        B.tw16[i] = make_float2((float)cos(ang), (float)sin(ang));
+    }
+    float2 tw_own;
+    {
+        const double ang = 2.0 * 3.14159265358979323846 * (double)(warp * lane) / (double)M;
+        tw_own = make_float2((float)cos(ang), (float)sin(ang));
+    }
+    __syncthreads();
+    float2 *slot = B.area + warp * kBigSlot;  // this warp's transpose slot / sub-spectrum row
+
+    for (int64_t g = blockIdx.x; g < T.total_frames; g += gridDim.x) {
+        const int64_t clip = mb_find_clip(T, g);
+        const float *__restrict__ src = samples + T.clip_off[clip] + (g - T.frame_start[clip]) * (int64_t)P.hop;
+        MbFrameSums S;
+        S.s0 = S.s1 = S.s2 = S.s3 = S.s4 = S.log2sum = S.energy = 0;
+        S.zcr = 0;
+        S.rolloff_bin = M;
+
+        // ---- 1. the frame, windowed, into the padded area (coalesced 16-byte loads); time-domain sums
+        int kscale = 0;
+        {
+            double e = 0;
+            int z = 0;
+            float mxabs = 0.f;
+            const float4 *__restrict__ src4 = reinterpret_cast<const float4 *>(src);
+            const float4 *__restrict__ win4 = reinterpret_cast<const float4 *>(P.window);
+            for (int i = tid; i < N / 4; i += kThreads) {
+                const float4 x = __ldg(src4 + i), w = __ldg(win4 + i);
+                mxabs = fmaxf(mxabs, fmaxf(fmaxf(fabsf(x.x), fabsf(x.y)), fmaxf(fabsf(x.z), fabsf(x.w))));
+                if (want_time) {
+                    e += (double)(x.x * x.x + x.y * x.y) + (double)(x.z * x.z + x.w * x.w);
+                    const float nx = (4 * i + 4 < N) ? __ldg(src + 4 * i + 4) : x.w;  // last sample has no successor
+                    const bool p0 = x.x >= 0.f, p1 = x.y >= 0.f, p2 = x.z >= 0.f, p3 = x.w >= 0.f, p4 = nx >= 0.f;
+                    const bool n0 = x.x == x.x, n1 = x.y == x.y, n2 = x.z == x.z, n3 = x.w == x.w, n4 = nx == nx;
+                    z += ((p0 != p1) && n0 && n1) + ((p1 != p2) && n1 && n2) + ((p2 != p3) && n2 && n3) +
+                         ((p3 != p4) && n3 && n4);
+                    if (mb_has(mask, MB_FEAT_BUFFER)) __stcs(reinterpret_cast<float4 *>(O.buffer + g * N) + i, x);
+                }
+                const int m0 = 2 * i, m1 = 2 * i + 1;
+                B.area[m0 + (m0 >> 4)] = make_float2(__fmul_rn(x.x, w.x), __fmul_rn(x.y, w.y));
+                B.area[m1 + (m1 >> 4)] = make_float2(__fmul_rn(x.z, w.z), __fmul_rn(x.w, w.w));
+            }
+            if (want_time) {
+                S.energy = block_sum(e, sc.red_d);
+                S.zcr = block_sum_int(z, sc.red_i);
+            }
+            if (want_spectrum) {  // frames outside the float32 comfort zone: exact power-of-two rescale (see generic kernel)
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) mxabs = fmaxf(mxabs, __shfl_xor_sync(0xffffffffu, mxabs, o));
+                __syncthreads();
+                if (lane == 0) sc.red_f[warp] = mxabs;
+                __syncthreads();
+                float mx = lane < kWarps ? sc.red_f[lane] : 0.f;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+                if (mx > 0.f && mx < 3.0e38f && (mx < 0x1p-40f || mx > 0x1p40f)) {
+                    int ex;
+                    (void)frexpf(mx, &ex);
+                    kscale = max(-100, min(100, -ex));
+                    const float up = ldexpf(1.f, kscale);
+                    for (int m = tid; m < M; m += kThreads) {
+                        float2 t = B.area[m + (m >> 4)];
+                        B.area[m + (m >> 4)] = make_float2(t.x * up, t.y * up);
+                    }
+                }
+            }
+        }
+        const float unscale = ldexpf(1.f, -kscale);
+        __syncthreads();
+
+        if (want_spectrum) {
+            // ---- 2. warp r takes z[16 m + r], m = 32 a + lane
+            float2 v[32];
+#pragma unroll
+            for (int a = 0; a < 32; a++) v[a] = B.area[544 * a + 17 * lane + warp];  // (512a+16b+r) + its padding (32a+b)
+            __syncthreads();  // everybody has its samples: the area becomes the sixteen warp slots
+            // ---- 3. the 1024-point sub-FFT of this warp: 32 x 32 in registers, one transpose through the slot
+#pragma unroll 1
+            for (int pass = 0; pass < 2; pass++) {
+                if (pass == 1) {
+#pragma unroll
+                    for (int b = 0; b < 32; b++) v[b] = slot[lane * kBigRow + b];
+                }
+                mbfft::fft_reg<32>(v);
+                if (pass == 0) {
+#pragma unroll
+                    for (int c = 0; c < 32; c++) {
+                        float2 y = v[mbfft::brev<5>(c)];
+                        if (c > 0) y = cmul(y, B.tw32[c * 32 + lane]);
+                        slot[c * kBigRow + lane] = y;
+                    }
+                }
+                __syncwarp();
+            }
+            // ---- 4. X_r[k] * exp(+2 pi i r k / M), k = lane + 32 d, into the warp's row in natural order
+#pragma unroll
+            for (int d = 0; d < 32; d++) {
+                float2 y = v[mbfft::brev<5>(d)];
+                if (warp > 0) y = cmul(y, cmul(tw_own, B.tw16[warp * 32 + d]));
+                slot[lane + 32 * d] = y;
+            }
+            __syncthreads();
+            // ---- 5. radix-16 across the warps' rows: C[k + 1024 q] for k = tid, tid + 512
+            float2 u0[16], u1[16];
+#pragma unroll
+            for (int r = 0; r < 16; r++) {
+                u0[r] = B.area[r * kBigSlot + tid];
+                u1[r] = B.area[r * kBigSlot + tid + 512];
+            }
+            mbfft::fft_reg<16>(u0);
+            mbfft::fft_reg<16>(u1);
+            __syncthreads();  // all rows consumed: the area becomes the natural-order spectrum C[0 .. M)
+#pragma unroll
+            for (int q = 0; q < 16; q++) {
+                B.area[tid + 1024 * q] = u0[mbfft::brev<4>(q)];
+                B.area[tid + 512 + 1024 * q] = u1[mbfft::brev<4>(q)];
+            }
+            __syncthreads();
+            // ---- 6. real-FFT split, spectra out, amplitude into smem, moment partials
+            MomentAcc acc;
+            const float sc_n = P.inv_sqrt_N;
+            for (int k = tid; k < M; k += kThreads) {
+                const float2 a = B.area[k];
+                const float2 b = B.area[(M - k) & (M - 1)];
+                const float2 w = __ldg(&P.twN[k]);
+                const float er = 0.5f * (a.x + b.x), ei = 0.5f * (a.y - b.y);
+                const float orr = 0.5f * (a.y + b.y), oi = -0.5f * (a.x - b.x);
+                const float zr = (er + (w.x * orr - w.y * oi)) * sc_n;
+                const float zi = (ei + (w.x * oi + w.y * orr)) * sc_n;
+                if (want_cs) {
+                    float *re = O.complex_real + g * N, *im = O.complex_imag + g * N;
+                    const float zro = zr * unscale, zio = zi * unscale;
+                    __stcs(re + k, zro);
+                    __stcs(im + k, zio);
+                    if (k > 0) {
+                        __stcs(re + (N - k), zro);
+                        __stcs(im + (N - k), -zio);
+                    } else {
+                        __stcs(re + M, (a.x - a.y) * sc_n * unscale);  // Nyquist bin
+                        __stcs(im + M, (a.x - a.y) * 0.f + 0.f);
+                    }
+                }
+                const float av = sqrtf(zr * zr + zi * zi) * unscale;
+                B.amp[k] = av;
+                if (mb_has(mask, MB_FEAT_AMPLITUDE_SPECTRUM)) __stcs(O.amplitude_spectrum + g * M + k, av);
+                if (mb_has(mask, MB_FEAT_POWER_SPECTRUM)) __stcs(O.power_spectrum + g * M + k, __fmul_rn(av, av));
+                if (want_moments) acc.add(av, k, want_log);
+            }
+            frame_epilogue<false>(P, O, g, S, acc, B.amp, sc);
+        }
+        if (tid == 64) mb_store_scalars(P, O, g, S);
+        __syncthreads();  // smem reused by the next frame
+    }
+}
+#endif  // MB_GENERIC_THREADS == 512

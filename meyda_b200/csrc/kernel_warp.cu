@@ -28,6 +28,7 @@
 #include <utility>
 
 #include "mb_device.cuh"
+#include "mb_fft.cuh"
 #include "mb_kernels.h"
 
 namespace {
@@ -119,51 +120,9 @@ __device__ __forceinline__ void st_stream(float *p, float v) { __stcs(p, v); }
 __device__ __forceinline__ void bulk_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
-// ---- 32-point FFT in registers: radix-2 decimation in frequency, forward
-// sign +i (lib/jsfft/fft.js:145), natural order in, X[k] left in v[brev5(k)].
-__device__ constexpr float kCos32[16] = {1.000000000e+00f, 9.807852804e-01f, 9.238795325e-01f, 8.314696123e-01f,
-                                         7.071067812e-01f, 5.555702330e-01f, 3.826834324e-01f, 1.950903220e-01f,
-                                         0.0f, -1.950903220e-01f, -3.826834324e-01f, -5.555702330e-01f,
-                                         -7.071067812e-01f, -8.314696123e-01f, -9.238795325e-01f, -9.807852804e-01f};
-__device__ constexpr float kSin32[16] = {0.000000000e+00f, 1.950903220e-01f, 3.826834324e-01f, 5.555702330e-01f,
-                                         7.071067812e-01f, 8.314696123e-01f, 9.238795325e-01f, 9.807852804e-01f,
-                                         1.000000000e+00f, 9.807852804e-01f, 9.238795325e-01f, 8.314696123e-01f,
-                                         7.071067812e-01f, 5.555702330e-01f, 3.826834324e-01f, 1.950903220e-01f};
-
-template <int E>  // d * exp(+2 pi i E / 32), 0 <= E < 16
-__device__ __forceinline__ float2 mul_w32(float2 d) {
-    constexpr float R = 7.071067812e-01f;
-    if constexpr (E == 0) return d;
-    else if constexpr (E == 8) return make_float2(-d.y, d.x);
-    else if constexpr (E == 4) return make_float2((d.x - d.y) * R, (d.x + d.y) * R);
-    else if constexpr (E == 12) return make_float2((-d.x - d.y) * R, (d.x - d.y) * R);
-    else {
-        constexpr float c = kCos32[E], s = kSin32[E];
-        return make_float2(d.x * c - d.y * s, d.x * s + d.y * c);
-    }
-}
-template <int H, int I>
-__device__ __forceinline__ void bfly32(float2 (&v)[32]) {
-    constexpr int B = (I / H) * 2 * H, J = I % H;
-    const float2 u = v[B + J], w = v[B + J + H];
-    v[B + J] = make_float2(u.x + w.x, u.y + w.y);
-    v[B + J + H] = mul_w32<J * (16 / H)>(make_float2(u.x - w.x, u.y - w.y));
-}
-template <int H, int... I>
-__device__ __forceinline__ void stage32(float2 (&v)[32], std::integer_sequence<int, I...>) {
-    (bfly32<H, I>(v), ...);
-}
-__device__ __forceinline__ void fft32(float2 (&v)[32]) {
-    using S = std::make_integer_sequence<int, 16>;
-    stage32<16>(v, S{});
-    stage32<8>(v, S{});
-    stage32<4>(v, S{});
-    stage32<2>(v, S{});
-    stage32<1>(v, S{});
-}
-__host__ __device__ constexpr int brev5(int k) {
-    return ((k & 1) << 4) | ((k & 2) << 2) | (k & 4) | ((k & 8) >> 2) | ((k & 16) >> 4);
-}
+// ---- 32-point FFT in registers (mb_fft.cuh): natural order in, X[k] left in v[brev5(k)].
+__device__ __forceinline__ void fft32(float2 (&v)[32]) { mbfft::fft_reg<32>(v); }
+__host__ __device__ constexpr int brev5(int k) { return mbfft::brev<5>(k); }
 
 __device__ __forceinline__ double warp_sum_d(double v) { return mb_warp_sum(v); }
 

@@ -12,6 +12,12 @@ size_t mb_warp2048_smem_bytes();
 cudaError_t mb_launch_warp2048(const MbDevPlan &P, const MbClipTable &T, const float *samples, const mb_outputs &O,
                                int num_sms, cudaStream_t stream);
 
+// bufferSize 32768, float32 FFT: 16 warps per frame (16 x 1024-point register sub-FFTs + radix-16 combine).
+// Needs 16-byte aligned frames like the warp kernel.
+size_t mb_big32768_smem_bytes();
+cudaError_t mb_launch_big32768(const MbDevPlan &P, const MbClipTable &T, const float *samples, const mb_outputs &O,
+                               int num_sms, cudaStream_t stream);
+
 // Exact-FFT mode on a 2-CTA cluster (DSMEM exchange in the last radix-2 stage): bufferSize up to 32768.
 size_t mb_exact_cluster_smem_bytes(int N);
 cudaError_t mb_launch_exact_cluster(const MbDevPlan &P, const MbClipTable &T, const float *samples, const mb_outputs &O,
