@@ -128,8 +128,21 @@ __device__ __forceinline__ int block_sum_int(int v, int *scratch /*[kWarps]*/) {
     return mb_warp_sum(lane < kWarps ? scratch[lane] : 0);
 }
 
+// float32-mode helpers: one MUFU each (<= 1 ulp / 2^-22 abs), subnormals handled (no .ftz)
+__device__ __forceinline__ float sqrt_fast(float x) {
+    float r;
+    asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float log2_fast(float x) {
+    float r;
+    asm("lg2.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
 struct MomentAcc {
     double s0 = 0, s1 = 0, s2 = 0, s3 = 0, s4 = 0, lg = 0;
+    template <bool FAST = false>
     __device__ __forceinline__ void add(float av, int k, bool want_log) {
         const double ad = (double)av, kd = (double)k;
         double t = ad * kd;
@@ -138,7 +151,7 @@ struct MomentAcc {
         t *= kd; s2 += t;
         t *= kd; s3 += t;
         t *= kd; s4 += t;
-        if (want_log) lg += (double)log2f(av);
+        if (want_log) lg += (double)(FAST ? log2_fast(av) : log2f(av));
     }
 };
 
@@ -195,7 +208,12 @@ __device__ __forceinline__ void frame_epilogue(const MbDevPlan &P, const mb_outp
         const double total = mb_warp_sum(mine);
         double run = mb_warp_sum(lane < warp ? mine : 0.0);  // sum of amp[0 .. k_lo)
         const double thr = 0.99 * total;
+        // bins below this warp's range all count when its first prefix is under the threshold, none of its
+        // own count when it is over; only the warp the threshold falls into scans bin by bin
         int cnt = 0;
+        const bool starts_under = run <= thr, ends_under = run + part <= thr;
+        if (starts_under && ends_under) cnt = k_hi - k_lo;
+        else if (starts_under)
         for (int k0 = k_lo; k0 < k_hi; k0 += 32) {
             const int k = k0 + lane;
             const double x = k < k_hi ? (double)amp[k] : 0.0;
@@ -452,11 +470,11 @@ mb_generic_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ M
                             im[M] = (a.x - a.y) * 0.f + 0.f;  // +0, or NaN when the frame holds a NaN
                         }
                     }
-                    const float av = sqrtf(zr * zr + zi * zi) * unscale;
+                    const float av = sqrt_fast(zr * zr + zi * zi) * unscale;
                     amp[k] = av;
                     if (mb_has(mask, MB_FEAT_AMPLITUDE_SPECTRUM)) O.amplitude_spectrum[g * M + k] = av;
                     if (mb_has(mask, MB_FEAT_POWER_SPECTRUM)) O.power_spectrum[g * M + k] = __fmul_rn(av, av);
-                    if (want_moments) acc.add(av, k, want_log);
+                    if (want_moments) acc.add<true>(av, k, want_log);
                 }
             }
             frame_epilogue<EXACT>(P, O, g, S, acc, amp, sc);
@@ -643,6 +661,7 @@ mb_big32768_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
             float mxabs = 0.f;
             const float4 *__restrict__ src4 = reinterpret_cast<const float4 *>(src);
             const float4 *__restrict__ win4 = reinterpret_cast<const float4 *>(P.window);
+#pragma unroll 4
             for (int i = tid; i < N / 4; i += kThreads) {
                 const float4 x = __ldg(src4 + i), w = __ldg(win4 + i);
                 mxabs = fmaxf(mxabs, fmaxf(fmaxf(fabsf(x.x), fabsf(x.y)), fmaxf(fabsf(x.z), fabsf(x.w))));
@@ -738,10 +757,11 @@ mb_big32768_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
             // ---- 6. real-FFT split, spectra out, amplitude into smem, moment partials
             MomentAcc acc;
             const float sc_n = P.inv_sqrt_N;
+#pragma unroll 4
             for (int k = tid; k < M; k += kThreads) {
+                const float2 w = __ldg(&P.twN[k]);  // 128 KB table, L2-resident: issued first, four in flight
                 const float2 a = B.area[k];
                 const float2 b = B.area[(M - k) & (M - 1)];
-                const float2 w = __ldg(&P.twN[k]);
                 const float er = 0.5f * (a.x + b.x), ei = 0.5f * (a.y - b.y);
                 const float orr = 0.5f * (a.y + b.y), oi = -0.5f * (a.x - b.x);
                 const float zr = (er + (w.x * orr - w.y * oi)) * sc_n;
@@ -759,11 +779,11 @@ mb_big32768_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
                         __stcs(im + M, (a.x - a.y) * 0.f + 0.f);
                     }
                 }
-                const float av = sqrtf(zr * zr + zi * zi) * unscale;
+                const float av = sqrt_fast(zr * zr + zi * zi) * unscale;
                 B.amp[k] = av;
                 if (mb_has(mask, MB_FEAT_AMPLITUDE_SPECTRUM)) __stcs(O.amplitude_spectrum + g * M + k, av);
                 if (mb_has(mask, MB_FEAT_POWER_SPECTRUM)) __stcs(O.power_spectrum + g * M + k, __fmul_rn(av, av));
-                if (want_moments) acc.add(av, k, want_log);
+                if (want_moments) acc.add<true>(av, k, want_log);
             }
             frame_epilogue<false>(P, O, g, S, acc, B.amp, sc);
         }
