@@ -265,15 +265,17 @@ mb_status launch(mb_plan *p, const int64_t *d_off, const int64_t *d_frame_start,
                  const float *d_samples, const mb_outputs &d_out, cudaStream_t stream, bool aligned) {
     if (total_frames == 0) return MB_OK;
     MbClipTable T{d_off, d_frame_start, n, total_frames};
-    const bool tma_ok = aligned && ((uintptr_t)d_samples % 16 == 0) && ((uintptr_t)d_out.buffer % 16 == 0) &&
-                        (p->hop % 4 == 0);
+    // 16-byte aligned frames: required by the bufferSize-32768 kernel's float4 loads; the warp kernel takes
+    // any float-aligned frame (misaligned ones bypass TMA inside the kernel) but bulk-stores `buffer` rows
+    const bool out_ok = (uintptr_t)d_out.buffer % 16 == 0;
+    const bool tma_ok = aligned && ((uintptr_t)d_samples % 16 == 0) && out_ok && (p->hop % 4 == 0);
     if (p->use_cluster) {
         MB_CUDA(mb_launch_exact_cluster(p->dev, T, d_samples, d_out, p->num_sms, stream));
         p->launches_generic++;
     } else if (p->has_big_kernel && tma_ok) {
         MB_CUDA(mb_launch_big32768(p->dev, T, d_samples, d_out, p->num_sms, stream));
         p->launches_warp++;
-    } else if (p->has_warp_kernel && tma_ok) {
+    } else if (p->has_warp_kernel && out_ok && ((uintptr_t)d_samples % 4 == 0)) {
         MB_CUDA(mb_launch_warp2048(p->dev, T, d_samples, d_out, p->num_sms, stream));
         p->launches_warp++;
     } else {

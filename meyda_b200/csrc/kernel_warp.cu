@@ -233,6 +233,17 @@ mb_warp2048_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
 
             // ---- 1. frame into the warp's slot (TMA), buffer out of it (TMA)
             __syncwarp();  // every lane is done with the slot's previous contents
+            // TMA needs a 16-byte aligned source: a frame that starts elsewhere (odd clip offsets, hop not a
+            // multiple of 4) is copied in by the lanes instead; everything after that is the same.
+            const bool src_aligned = (reinterpret_cast<uintptr_t>(src) & 15) == 0;
+            if (!src_aligned) {
+                if (lane == 0) bulk_store_wait_read();
+                __syncwarp();
+                for (int i = lane; i < kN; i += 32) slot[i] = __ldg(src + i);
+                // the `buffer` bulk store below reads the slot through the async proxy
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+            } else {
 #ifdef MB_EXP_NOWAIT  // timing experiment only (results are garbage): how much does the frame load + wait cost?
             if (j == 0) {
 #endif
@@ -252,6 +263,7 @@ mb_warp2048_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
 #ifdef MB_EXP_NOWAIT
             }
 #endif
+            }
 #ifdef MB_EXP_NOSTORE  // timing experiment only: all the arithmetic, none of the spectra/buffer traffic
             const bool exp_store = (total_chunks < 0);
 #else

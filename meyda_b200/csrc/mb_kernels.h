@@ -6,8 +6,8 @@
 
 // Block-per-frame kernel, any power-of-two bufferSize in [16, 32768].
 size_t mb_generic_smem_bytes(int M, bool exact);
-// Warp-per-frame kernel, bufferSize 2048, float32 FFT.  Needs 16-byte aligned frames:
-// samples pointer and `buffer` output 16-byte aligned, hop and every clip offset multiples of 4.
+// Warp-per-frame kernel, bufferSize 2048, float32 FFT.  `buffer` output rows must be 16-byte aligned; frames
+// that are not 16-byte aligned (odd clip offsets / hops) are loaded by the lanes instead of TMA.
 size_t mb_warp2048_smem_bytes();
 cudaError_t mb_launch_warp2048(const MbDevPlan &P, const MbClipTable &T, const float *samples, const mb_outputs &O,
                                int num_sms, cudaStream_t stream);

@@ -327,3 +327,22 @@ def test_full_size_properties(flags):
     for c in (0, n_clips - 1):
         sl = slice(c * nf_clip, (c + 1) * nf_clip)
         verify({k: v[sl].cpu().numpy() for k, v in outs.items()}, x[c].cpu().numpy(), N, hop, flags=flags)
+
+
+def test_ragged_clips_stay_on_the_warp_kernel():
+    """Odd clip lengths put most frames off 16-byte alignment: the bufferSize-2048 kernel loads
+    those by lanes instead of TMA rather than falling back to the generic kernel."""
+    N, hop = 2048, 512
+    lens = [2048 + 512 * 3 + 1, 5000, 2047, 2048, 7777, 4099]
+    clips = [mo.synth_clip(60 + i, L) for i, L in enumerate(lens)]
+    data, off, ln = mb.meyda._normalize_clips(clips)
+    assert any(int(o) % 4 for o in off)
+    plan = mb.Plan(N, hop, SR)
+    out, per = plan.extract_host(data, off, ln)
+    assert plan.kernel_name == "warp2048"
+    plan.close()
+    assert per.tolist() == [mo.num_frames(L, N, hop) for L in lens]
+    verify(out, clips, N, hop)
+    # and an odd hop
+    out, per = run_gpu(clips[1], N, 333)
+    verify(out, clips[1], N, 333)
