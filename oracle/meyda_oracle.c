@@ -8,12 +8,17 @@
  * reference stores into a Float32Array, there is no fused multiply-add
  * (compile with -ffp-contract=off), and loops run in the reference's order.
  *
- * PARITY UNPINNED: the reference ships no tests / golden vectors and no JS
- * engine exists in this image, so this restatement cannot be checked against
- * the reference executing.  It is guarded instead by (i) an independently
- * written numpy restatement (oracle/meyda_oracle.py) that must agree with it
- * bit for bit, (ii) numpy.fft / closed-form identities, (iii) the survey's
- * spot values.  See DESIGN.md "Oracle".
+ * PINNING: the reference ships no tests / golden vectors and no JavaScript
+ * engine exists in this image.  The restatement is pinned against the
+ * reference's OWN source files executed by oracle/minijs.py, an ES5-subset
+ * interpreter written for that purpose: tests/golden/js_reference_vectors.npz
+ * (tools/make_js_golden.py) holds what lib/jsfft/*.js, src/utils.js, every
+ * src/extractors/*.js and the compute* methods of src/meyda.js return on nine
+ * frames, and tests/test_js_pin.py requires this file to reproduce them bit
+ * for bit (Float32Array results) / to 1e-12 (Numbers).  Further guards: (i) an
+ * independently written numpy restatement (oracle/meyda_oracle.py) that must
+ * agree bit for bit, (ii) numpy.fft / closed-form identities, (iii) the
+ * survey's spot values.  See DESIGN.md "Oracle".
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
  * --impl reference leg may load this library.  The product path

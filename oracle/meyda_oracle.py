@@ -7,8 +7,9 @@ bit.  JS semantics: float64 arithmetic, float32 rounding exactly where the
 reference stores into a Float32Array, no FMA, sequential accumulation order
 (np.cumsum is a running sum, not pairwise).
 
-PARITY UNPINNED: the reference has no tests/golden vectors and no JS engine is
-available in this image (see DESIGN.md "Oracle").
+PINNING: the reference has no tests/golden vectors and no JS engine is available
+in this image; both restatements are pinned against the reference's own .js
+files executed by oracle/minijs.py (tests/test_js_pin.py, DESIGN.md "Oracle").
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may import
 this module; meyda_b200/ never does.

@@ -1,0 +1,113 @@
+"""Pins the oracle against the reference's OWN JavaScript.
+
+tests/golden/js_reference_vectors.npz holds what the unmodified files
+lib/jsfft/{complex_array,fft}.js, src/utils.js, src/extractors/*.js and the
+compute* method bodies of src/meyda.js return on nine frames when executed by
+oracle/minijs.py (an ES5-subset interpreter written for this purpose, since no
+JavaScript engine exists in the image; tools/make_js_golden.py is the generator).
+Both oracle restatements must reproduce them: Float32Array results bit for bit,
+Numbers to 1e-12 (relative; 1e-13 absolute where a value is pure cancellation noise).  Where /root/reference is mounted, two cases are re-executed
+live to show the vectors are reproducible from the reference sources."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import c_oracle, meyda_oracle as mo
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SR = 44100.0
+NUMBERS = ["rms", "energy", "zcr", "spectralCentroid", "spectralFlatness", "spectralSlope", "spectralRolloff",
+           "spectralSpread", "spectralSkewness", "spectralKurtosis", "perceptualSpread", "perceptualSharpness"]
+
+
+@pytest.fixture(scope="module")
+def js():
+    return np.load(os.path.join(ROOT, "tests", "golden", "js_reference_vectors.npz"))
+
+
+def _signal(golden_audio, clip, N, f):
+    if clip == "silence":
+        return np.zeros(N, np.float32)
+    if clip == "impulse":
+        return np.eye(1, N, 7, dtype=np.float32)[0]
+    if clip == "square":
+        return np.where((np.arange(N) // 16) % 2 == 0, 1.0, -1.0).astype(np.float32)
+    return golden_audio[clip][f * N:(f + 1) * N]
+
+
+def _bits(a, b):
+    a, b = np.asarray(a, np.float32), np.asarray(b, np.float32)
+    return a.shape == b.shape and bool(((a.view(np.uint32) == b.view(np.uint32)) | (np.isnan(a) & np.isnan(b))).all())
+
+
+def _num(a, b):
+    a, b = float(a), float(b)
+    if np.isnan(a) or np.isnan(b):
+        return np.isnan(a) and np.isnan(b)
+    if np.isinf(a) or np.isinf(b):
+        return a == b
+    return abs(a - b) <= 1e-12 * max(abs(a), abs(b)) + 1e-13  # 1e-13 absolute: values that are pure cancellation noise
+
+
+def _check(js, ci, r, who):
+    for k in NUMBERS:
+        assert _num(r[k][0], js["%d/%s" % (ci, k)]), (who, ci, k, r[k][0], float(js["%d/%s" % (ci, k)]))
+    assert _num(r["loudness"]["total"][0], js["%d/loudness.total" % ci]), (who, ci, "loudness.total")
+    assert _bits(r["loudness"]["specific"][0], js["%d/loudness.specific" % ci]), (who, ci, "loudness.specific")
+    assert _bits(r["mfcc"][0], js["%d/mfcc" % ci]), (who, ci, "mfcc", r["mfcc"][0], js["%d/mfcc" % ci])
+    assert _bits(r["amplitudeSpectrum"][0], js["%d/amplitudeSpectrum" % ci]), (who, ci, "amplitudeSpectrum")
+    assert _bits(r["powerSpectrum"][0], js["%d/powerSpectrum" % ci]), (who, ci, "powerSpectrum")
+    assert _bits(r["complexSpectrum"]["real"][0], js["%d/complexSpectrum.real" % ci]), (who, ci, "real")
+    assert _bits(r["complexSpectrum"]["imag"][0], js["%d/complexSpectrum.imag" % ci]), (who, ci, "imag")
+    assert _bits(r["buffer"][0], js["%d/buffer" % ci]), (who, ci, "buffer")
+
+
+def test_oracles_reproduce_the_reference_javascript(js, golden_audio):
+    cases = [str(c).split("/") for c in js["cases"]]
+    assert len(cases) == 9
+    for ci, (clip, N, f, window) in enumerate(cases):
+        N, f = int(N), int(f)
+        sig = _signal(golden_audio, clip, N, f)
+        _check(js, ci, c_oracle.extract(sig, N, N, SR, window), "C oracle")
+        _check(js, ci, mo.extract(sig, N, N, SR, window), "numpy oracle")
+        # plan-time tables computed by the reference's own constructor code
+        t = c_oracle.plan_tables(N, SR)
+        assert _bits(t["hanning"], js["%d/hanning" % ci]) and _bits(t["hamming"], js["%d/hamming" % ci])
+        assert _bits(t["bark"], js["%d/barkScale" % ci])
+        assert np.array_equal(t["bbLimits"], js["%d/bbLimits" % ci].astype(np.int32))
+    got = [mo.is_power_of_two(v) for v in js["isPowerOfTwo/in"]]
+    assert got == [bool(v) for v in js["isPowerOfTwo/out"]]
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/src/extractors"), reason="reference checkout not mounted")
+def test_vectors_are_reproducible_from_the_reference_sources(js, golden_audio):
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import make_js_golden as gen
+    it = gen.build()
+    cases = [str(c).split("/") for c in js["cases"]]
+    for ci in (2, 7):  # sound2 N=256 (the +-Infinity mfcc case) and the impulse
+        clip, N, f, window = cases[ci]
+        r = gen.run_frame(it, _signal(golden_audio, clip, int(N), int(f)), SR, window)
+        assert _bits(r["mfcc"], js["%d/mfcc" % ci]) and _bits(r["amplitudeSpectrum"], js["%d/amplitudeSpectrum" % ci])
+        assert _num(r["spectralKurtosis"], js["%d/spectralKurtosis" % ci])
+        assert _bits(r["complexSpectrum"]["imag"], js["%d/complexSpectrum.imag" % ci])
+
+
+def test_minijs_semantics():
+    """The interpreter itself on the constructs the reference relies on."""
+    from oracle.minijs import Interpreter
+    it = Interpreter(ROOT)
+    run = lambda src: it.run_source("return (function(){" + src + "})()")  # noqa: E731
+    assert run("var a = 1\nvar b = 2\nreturn a + b") == 3.0  # ASI
+    assert run("var x = 5; x >>= 1; x <<= 3; return (x & 24) + (x | 1)") == 33.0
+    assert run("var f = {}; f[3] = f[1.5] = true; return f.hasOwnProperty(3) && f.hasOwnProperty('1.5') && !f.hasOwnProperty(2)")
+    assert run("var a = new Float32Array(2); a[0] = 0.1; a[5] = 7; return a[0]") == float(np.float32(0.1))
+    assert run("var z = Array.apply(null, new Array(4)).map(Number.prototype.valueOf, 0); return z.length + z[3]") == 4.0
+    assert run("function P(){ if (!(this instanceof P)) return new P(); this.v = 4 } P.prototype.g = function(){ return this.v }; return P().g()") == 4.0
+    assert run("var o = {v: 2, f: function(){ return this.v }}; var g = o.f.bind({v: 9}); return g() + o.f()") == 11.0
+    assert run("return typeof nope === 'undefined' && typeof Math.pow === 'function'")
+    assert np.isnan(run("return 0/0")) and run("return 1/0") == float("inf") and run("return Math.pow(0, 0.23)") == 0.0
+    assert run("var i = 0, s = 0; while (i < 5) { i++; if (i == 2) continue; s += i } return s") == 13.0
+    assert run("return (7 % 2 === 1) && (-7 % 2 === -1) && ('a' + 1 === 'a1')")

@@ -9,9 +9,10 @@
                     hanning: every scalar feature + loudness.specific + mfcc for
                     every frame, and the array features for three frames each.
 
-The reference has no golden vectors of its own (package.json:25) and cannot be
-executed here (no JS engine), so these pin the ORACLE against drift; they are
-not outputs of the reference itself.  PARITY UNPINNED -- see DESIGN.md.
+The reference has no golden vectors of its own (package.json:25).  These pin the
+ORACLE against drift on the full demo clips; they are not outputs of the
+reference itself.  The vectors that ARE the reference's own outputs (its .js
+files executed by oracle/minijs.py) are made by tools/make_js_golden.py.
 """
 import os
 import sys
