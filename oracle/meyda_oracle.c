@@ -12,8 +12,8 @@
  * engine exists in this image.  The restatement is pinned against the
  * reference's OWN source files executed by oracle/minijs.py, an ES5-subset
  * interpreter written for that purpose: tests/golden/js_reference_vectors.npz
- * (tools/make_js_golden.py) holds what lib/jsfft/*.js, src/utils.js, every
- * src/extractors/*.js and the compute* methods of src/meyda.js return on nine
+ * (tools/make_js_golden.py) holds what the lib/jsfft sources, src/utils.js, every
+ * file under src/extractors and the compute* methods of src/meyda.js return on nine
  * frames, and tests/test_js_pin.py requires this file to reproduce them bit
  * for bit (Float32Array results) / to 1e-12 (Numbers).  Further guards: (i) an
  * independently written numpy restatement (oracle/meyda_oracle.py) that must
