@@ -324,18 +324,22 @@ void build_warp_tables(MbWarpTables &W, const MbDevPlan &D) {
             if (std::binary_search(below.begin(), below.end(), 32 * lane + i)) m |= 1u << i;
         W.lane_bmask[lane] = m;
         head_end[lane] = (first != below.end() && *first < 32 * lane + 32) ? *first : 32 * lane + 32;
-        W.piece_edge[MB_WARP_HEAD + lane] = W.lane_seg_start[lane];
     }
-    for (int s = 0; s < W.n_slots; s++) W.piece_edge[s] = below[s];
+    // piece ids: a lane's pieces are consecutive, head first (the kernel walks them with one pointer)
+    auto head_id = [&](int lane) { return W.lane_slot_base[lane] + lane; };
+    auto boundary_id = [&](int s) { return s + below[s] / 32 + 1; };
+    for (int lane = 0; lane < 32; lane++) W.piece_edge[head_id(lane)] = 32 * lane;
+    for (int s = 0; s < W.n_slots; s++) W.piece_edge[boundary_id(s)] = 32 * (below[s] / 32);
     // pieces of every Bark band [bb[b], bb[b+1]) and mel segment [mel[s], mel[s+1])
     int n_items = 0;
     auto add_segment = [&](int seg, int e0, int e1) {
         W.seg_ptr[seg] = n_items;
         for (int s = 0; s < W.n_slots; s++)
-            if (below[s] >= e0 && below[s] < e1 && n_items < MB_WARP_MAX_ITEMS) W.seg_items[n_items++] = (unsigned char)s;
+            if (below[s] >= e0 && below[s] < e1 && n_items < MB_WARP_MAX_ITEMS)
+                W.seg_items[n_items++] = (unsigned char)boundary_id(s);
         for (int lane = 0; lane < 32; lane++)
             if (head_end[lane] > 32 * lane && 32 * lane > e0 && 32 * lane < e1 && n_items < MB_WARP_MAX_ITEMS)
-                W.seg_items[n_items++] = (unsigned char)(MB_WARP_HEAD + lane);
+                W.seg_items[n_items++] = (unsigned char)head_id(lane);
     };
     for (int b = 0; b < MB_NUM_BARK_BANDS; b++) add_segment(b, D.bb[b], D.bb[b + 1]);
     for (int s = 0; s <= MB_NUM_MEL_FILTERS; s++) add_segment(MB_NUM_BARK_BANDS + s, D.mel[s], D.mel[s + 1]);

@@ -181,8 +181,7 @@ mb_warp2048_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
     __syncthreads();
 
     const uint32_t bmask = WT->lane_bmask[lane];     // boundaries inside this lane's 32 blocked bins
-    const int slot_base = WT->lane_slot_base[lane];  // index of the first of them
-    const int seg_start = WT->lane_seg_start[lane];  // the boundary that opened the run this lane's first bin is in
+    const int slot_base = WT->lane_slot_base[lane];  // how many boundaries lie below this lane's first bin
 
     const bool want_buffer = kFull || mb_has(mask, MB_FEAT_BUFFER);
     const bool want_time = kFull || (mask & (MB_FEATURE_BIT(MB_FEAT_RMS) | MB_FEATURE_BIT(MB_FEAT_ENERGY) | MB_FEATURE_BIT(MB_FEAT_ZCR)));
@@ -198,7 +197,8 @@ mb_warp2048_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
     const bool want_bark = kFull || (mask & (MB_FEATURE_BIT(MB_FEAT_LOUDNESS) | MB_FEATURE_BIT(MB_FEAT_PERCEPTUAL_SPREAD) |
                                              MB_FEATURE_BIT(MB_FEAT_PERCEPTUAL_SHARPNESS)));
     const bool want_mfcc = kFull || mb_has(mask, MB_FEAT_MFCC);
-    const bool want_blocked = want_rolloff || want_bark || want_mfcc;
+    const bool want_pieces = want_bark || want_mfcc;
+    const bool want_blocked = want_rolloff || want_pieces || want_moments;
     const uint32_t time_only = MB_FEATURE_BIT(MB_FEAT_RMS) | MB_FEATURE_BIT(MB_FEAT_ENERGY) |
                                MB_FEATURE_BIT(MB_FEAT_ZCR) | MB_FEATURE_BIT(MB_FEAT_BUFFER);
     const bool want_spectrum = kFull || (mask & ~time_only) != 0;
@@ -390,16 +390,19 @@ mb_warp2048_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
                 const float2 *xm = slot2 + (kM - lane);
                 const float2 *twp = S.twN + lane;
                 float2 b_nx = xm[0], w_nx = twp[0];  // operands of bin d are fetched during bin d-1
-                double s0 = 0, s1 = 0, s2 = 0, s3 = 0, s4 = 0;
                 float lg = 0.f;
                 const float sc = P.inv_sqrt_N, hsc = 0.5f * sc;
                 // per-lane row pointers: every store below is base + a compile-time offset (32 d floats)
                 float *out_re = O.complex_real + g * kN + lane, *out_im = O.complex_imag + g * kN + lane;
                 float *mir_re = O.complex_real + g * kN + (kN - lane), *mir_im = O.complex_imag + g * kN + (kN - lane);
                 float *out_amp = O.amplitude_spectrum + g * kM + lane, *out_pow = O.power_spectrum + g * kM + lane;
+                // The mirrored half Z[N-k] = conj(Z[k]): row d of k = lane + 32 d lands on [N-32d-31, N-32d], which
+                // straddles two 128-byte lines.  Lanes >= 1 therefore hold their value back by one row, and
+                // store it next to lane 0's current one: [N-32d, N-32d+31] is one aligned line.
+                float *mirq_re = mir_re + (lane == 0 ? 0 : 32), *mirq_im = mir_im + (lane == 0 ? 0 : 32);
+                float pzr = 0.f, pzi = 0.f;
 #pragma unroll
                 for (int d = 0; d < 32; d++) {
-                    const int k = lane + 32 * d;
                     const float2 a = v[brev5(d)];
                     const float2 b = b_nx;  // X[M-k]
                     const float2 w = w_nx;  // h * exp(+2 pi i k / N), h = 0.5 / sqrt(N)
@@ -414,45 +417,31 @@ mb_warp2048_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
                         // (a rescaled frame, kscale != 0, is brought back to its own units by the fix-up below)
                         st_stream(out_re + 32 * d, zr);
                         st_stream(out_im + 32 * d, zi);
-                        if (d == 0 && lane == 0) {
-                            st_stream(out_re + kM, (a.x - a.y) * sc);         // Nyquist bin (E[0] - O[0]) / sqrt(N)
-                            st_stream(out_im + kM, (a.x - a.y) * 0.f + 0.f);  // +0, or NaN when the frame holds a NaN
+                        if (d == 0) {
+                            if (lane == 0) {
+                                st_stream(out_re + kM, (a.x - a.y) * sc);         // Nyquist bin (E[0] - O[0]) / sqrt(N)
+                                st_stream(out_im + kM, (a.x - a.y) * 0.f + 0.f);  // +0, or NaN when the frame holds a NaN
+                            }
                         } else {
-                            st_stream(mir_re - 32 * d, zr);
-                            st_stream(mir_im - 32 * d, -zi);
+                            st_stream(mirq_re - 32 * d, lane == 0 ? zr : pzr);
+                            st_stream(mirq_im - 32 * d, -(lane == 0 ? zi : pzi));
+                        }
+                        pzr = zr;
+                        pzi = zi;
+                        if (d == 31 && lane != 0) {  // row 31 of lanes >= 1 completes the line the Nyquist bin opened
+                            st_stream(mirq_re - 32 * 32, zr);
+                            st_stream(mirq_im - 32 * 32, -zi);
                         }
                     }
                     const float amp = sqrt_approx(fmaf(zr, zr, zi * zi));
                     av[d] = amp;
                     if (want_amp_out && exp_store) st_stream(out_amp + 32 * d, amp);
                     if (want_pow_out && exp_store) st_stream(out_pow + 32 * d, __fmul_rn(amp, amp));
-                    if (want_moments) {
-                        // centroid .. kurtosis, flatness and slope are ratios: the frame's rescaling cancels
-                        const double ad = (double)amp, kd = (double)k;
-                        double t = ad * kd;
-                        s0 += ad;
-                        s1 += t;
-                        t *= kd; s2 += t;
-                        t *= kd; s3 += t;
-                        t *= kd; s4 += t;
-                        if (want_log) lg += log2_approx(amp);
-                    }
+                    if (want_log) lg += log2_approx(amp);  // (of the rescaled amplitude: see the chunk finalize)
                 }
-                if (want_moments) {
-                    s0 = warp_sum_d(s0);
-                    s1 = warp_sum_d(s1);
-                    s2 = warp_sum_d(s2);
-                    s3 = warp_sum_d(s3);
-                    s4 = warp_sum_d(s4);
+                if (want_log) {
                     lg = mb_warp_sum(lg);
-                    if (lane == j) {
-                        stash_put_d(stash, 2, j, s0);
-                        stash_put_d(stash, 4, j, s1);
-                        stash_put_d(stash, 6, j, s2);
-                        stash_put_d(stash, 8, j, s3);
-                        stash_put_d(stash, 10, j, s4);
-                        stash[12][j] = lg;
-                    }
+                    if (lane == j) stash[12][j] = lg;
                 }
 
                 if (kscale != 0) {
@@ -484,30 +473,73 @@ mb_warp2048_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
                         const float4 t = *reinterpret_cast<const float4 *>(slot + kAmpStride * lane + 4 * q);
                         ab[4 * q] = t.x; ab[4 * q + 1] = t.y; ab[4 * q + 2] = t.z; ab[4 * q + 3] = t.w;
                     }
-                    // One sequential pass per lane over its 32 bins: running sums of a, p = a^2 and
-                    // (k - e) p since the last boundary e, flushed into a piece at every boundary.
+                    // One sequential pass per lane over its 32 bins: running sums of a, p = a^2 and i p (i = the
+                    // bin's position in the lane) since the last boundary, flushed into a piece at every boundary.
                     // Only additions of non-negative terms: a silent band next to a loud bin keeps its value.
-                    // (float32 is enough: at most 32 non-negative terms per piece, no subtraction anywhere.)
-                    float4 *piece = reinterpret_cast<float4 *>(slot + kPieceOff);  // [kPieces]: {sum a, sum p, sum (k-e) p, -}
+                    // (float32 is enough: at most 32 non-negative terms per piece.)  The lane's pieces have
+                    // consecutive ids (head first), and the pass is branch-free: boundaries sit at different
+                    // positions in every lane, so a branch per boundary would run the flush ~30 times per warp.
+                    // A flush is a predicated store, and the restart is folded into the next accumulation
+                    // (r * keep + x with keep 0 or 1; r is finite unless the whole frame is NaN anyway).
+                    float4 *piece = reinterpret_cast<float4 *>(slot + kPieceOff);  // [kPieces]: {sum a, sum p, sum i p, -}
                     float ra = 0.f, rp = 0.f, rr = 0.f;
-                    float wf = (float)(32 * lane - seg_start);
-                    double ta = 0;  // lane total of a in double: rolloff is a discrete output
-                    int cur = MB_WARP_HEAD + lane, sidx = slot_base;
+                    // Float64 on the otherwise idle DP pipe: sum i^q a over the lane's bins, i = 0..31 (exact
+                    // products, compile-time weights).  q = 0 is the lane total the rolloff scan needs (a
+                    // discrete output); q = 1..4 become the spectral moments (src/utils.js:1-11) after the
+                    // shift to k = 32 lane + i below.
+                    double ta = 0, t1 = 0, t2 = 0, t3 = 0, t4 = 0;
+                    uint32_t paddr = smem_u32(piece + (slot_base + lane));
 #pragma unroll
                     for (int i = 0; i < 32; i++) {
-                        if ((bmask >> i) & 1u) {
-                            piece[cur] = make_float4(ra, rp, rr, 0.f);
-                            cur = sidx++;
-                            ra = rp = rr = wf = 0.f;
+                        if (want_moments || want_rolloff) {
+                            const double ad = (double)ab[i];
+                            ta += ad;
+                            if (want_moments) {
+                                t1 = fma(ad, (double)i, t1);
+                                t2 = fma(ad, (double)(i * i), t2);
+                                t3 = fma(ad, (double)(i * i * i), t3);
+                                t4 = fma(ad, (double)(i * i * i * i), t4);
+                            }
                         }
+                        if (!want_pieces) continue;
+                        float keep;  // 0 at a boundary (flush, step to the next piece, restart), else 1
+                        asm volatile(
+                            "{\n\t.reg .pred p;\n\t.reg .b32 t;\n\t"
+                            "and.b32 t, %6, %7;\n\t"
+                            "setp.ne.u32 p, t, 0;\n\t"
+                            "@p st.shared.v4.f32 [%1], {%2, %3, %4, %5};\n\t"
+                            "@p add.u32 %1, %1, 16;\n\t"
+                            "selp.f32 %0, 0f00000000, 0f3F800000, p;\n\t}"
+                            : "=f"(keep), "+r"(paddr)
+                            : "f"(ra), "f"(rp), "f"(rr), "f"(0.f), "r"(bmask), "r"(1u << i)
+                            : "memory");
                         const float pf = __fmul_rn(ab[i], ab[i]);
-                        ra += ab[i];
-                        rp += pf;
-                        rr = fmaf(wf, pf, rr);
-                        wf += 1.0f;
-                        if (want_rolloff) ta += (double)ab[i];
+                        ra = fmaf(ra, keep, ab[i]);
+                        rp = fmaf(rp, keep, pf);
+                        rr = fmaf((float)i, pf, rr * keep);
                     }
-                    piece[cur] = make_float4(ra, rp, rr, 0.f);
+                    if (want_pieces)
+                        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(paddr), "f"(ra), "f"(rp), "f"(rr), "f"(0.f)
+                                     : "memory");
+                    if (want_moments) {
+                        // sum (c + i)^p a with c = 32 lane: binomial shift, every term non-negative
+                        const double c = (double)(32 * lane), c2 = c * c;
+                        const double s1 = fma(c, ta, t1);
+                        const double s2 = fma(c2, ta, fma(2.0 * c, t1, t2));
+                        const double s3 = fma(c2 * c, ta, fma(3.0 * c2, t1, fma(3.0 * c, t2, t3)));
+                        const double s4 = fma(c2 * c2, ta, fma(4.0 * c2 * c, t1, fma(6.0 * c2, t2, fma(4.0 * c, t3, t4))));
+                        const double r1 = warp_sum_d(s1), r2 = warp_sum_d(s2), r3 = warp_sum_d(s3), r4 = warp_sum_d(s4);
+                        if (!want_rolloff) {  // (the rolloff scan below yields the same total)
+                            const double r0 = warp_sum_d(ta);
+                            if (lane == j) stash_put_d(stash, 2, j, r0);
+                        }
+                        if (lane == j) {
+                            stash_put_d(stash, 4, j, r1);
+                            stash_put_d(stash, 6, j, r2);
+                            stash_put_d(stash, 8, j, r3);
+                            stash_put_d(stash, 10, j, r4);
+                        }
+                    }
                     if (want_rolloff) {
                         // spectralRolloff.js: the largest m with sum_{k<m} a[k] <= 0.99 sum a.  Lane totals are
                         // scanned in double; the one lane the threshold falls into is then scanned bin by
@@ -536,7 +568,10 @@ mb_warp2048_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
                             const uint32_t ok = __ballot_sync(0xffffffffu, base + (incl - x) <= thr);  // P[32 lc + lane] <= thr
                             rbin = 32 * lc + (31 - __clz(ok));
                         }
-                        if (lane == j) stash[13][j] = __int_as_float(rbin);
+                        if (lane == j) {
+                            stash[13][j] = __int_as_float(rbin);
+                            if (want_moments) stash_put_d(stash, 2, j, total_a);
+                        }
                     }
                     __syncwarp();
                     // ---- lanes finish the bands: loudness.js:55-63, perceptual*.js
@@ -572,8 +607,10 @@ mb_warp2048_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
                                 const int pc = S.seg_items[it];
                                 const float4 pv = piece[pc];
                                 const float pp = pv.y;
-                                // sum (k - e0) p over the piece, then its complement (e1 - k) p: both non-negative
-                                const float up = fmaf((float)(S.piece_edge[pc] - e0), pp, pv.z) * inv;
+                                // sum (k - e0) p over the piece (pv.z counts k from the piece's lane start), then its
+                                // complement (e1 - k) p: both non-negative up to rounding (NaN stays NaN)
+                                float up = fmaf((float)(S.piece_edge[pc] - e0), pp, pv.z) * inv;
+                                up = (up < 0.f) ? 0.f : up;
                                 rise += up;
                                 fall += fmaxf(pp - up, 0.f);
                             }
@@ -603,7 +640,8 @@ mb_warp2048_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
             F.s2 = stash_get_d(stash, 6, lane);
             F.s3 = stash_get_d(stash, 8, lane);
             F.s4 = stash_get_d(stash, 10, lane);
-            F.log2sum = (double)stash[12][lane];
+            // the log sum was taken on the rescaled amplitudes (a 2^kscale), the moment sums on the frame's own
+            F.log2sum = (double)stash[12][lane] - (double)(kM * __float_as_int(stash[17][lane]));
             F.rolloff_bin = __float_as_int(stash[13][lane]);
             const int64_t g = g0 + lane;
             mb_store_scalars(P, O, g, F);

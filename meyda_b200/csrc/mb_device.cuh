@@ -12,8 +12,9 @@
 // edges cuts the N/2 bins into runs; in the blocked layout (lane L owns bins
 // [32 L, 32 L + 32)) a lane produces one piece per boundary inside it (bins
 // from that boundary to the next one or the lane's end) plus a head piece (its
-// bins before its first boundary).  Piece ids: boundary s -> s, head of lane L
-// -> MB_WARP_HEAD + L.  A Bark band or a mel segment is a short list of pieces.
+// bins before its first boundary).  A lane's pieces have consecutive ids, head
+// first: head of lane L -> lane_slot_base[L] + L, boundary s (in lane L) ->
+// s + L + 1.  A Bark band or a mel segment is a short list of pieces.
 #define MB_WARP_MAX_SLOTS 64
 #define MB_WARP_HEAD 64
 #define MB_WARP_PIECES (MB_WARP_HEAD + 32)
@@ -24,7 +25,7 @@ struct MbWarpTables {
     uint32_t lane_bmask[32];       // bit i: bin 32*lane + i is a Bark limit or a mel edge
     int lane_slot_base[32];        // number of such boundaries below bin 32*lane
     int lane_seg_start[32];        // largest boundary <= 32*lane
-    int piece_edge[MB_WARP_PIECES];            // the boundary a piece's k-weights are measured from
+    int piece_edge[MB_WARP_PIECES];            // the bin a piece's k-weights are measured from (its lane's first bin)
     int seg_ptr[MB_WARP_SEGMENTS + 1];         // CSR: pieces of band b (0..23) / mel segment s (24 + s)
     unsigned char seg_items[MB_WARP_MAX_ITEMS];
     int n_slots;                   // boundaries below M
