@@ -56,7 +56,7 @@ struct Smem {
     float2 tw32[kP * kP];        // exp(+2 pi i b c / 1024) at [c*32 + b]
     float2 twN[kM];              // exp(+2 pi i k / 2048)
     float window[kN];
-    float dct[MB_NUM_MFCC * MB_NUM_MEL_FILTERS];
+    float dct2[MB_NUM_MFCC * 32];  // [n][lane]: lane = k + 13 h holds dct[k + 13 (n + 13 h)] (mfcc.js:72-83), 0 for lanes >= 26
     float mel_inv[MB_NUM_MEL_FILTERS + 2];
     int mel_edge[MB_NUM_MEL_FILTERS + 2];
     int piece_edge[kPieces];
@@ -140,6 +140,20 @@ __device__ __forceinline__ float log2_approx(float x) {
     return r;
 }
 
+// Sums four doubles across the warp with 6 shuffle steps instead of 20: the first two steps fold the four
+// values onto lane bits 4 and 3 (a lane keeps one value of a pair and hands over the other), the last three
+// are plain.  Lane l returns the total of value (l >> 3) & 3.
+__device__ __forceinline__ double warp_sum4_d(double a0, double a1, double a2, double a3, int lane) {
+    const bool h16 = lane & 16, h8 = lane & 8;
+    const double b0 = (h16 ? a2 : a0) + __shfl_xor_sync(0xffffffffu, h16 ? a0 : a2, 16);  // a0 | a2
+    const double b1 = (h16 ? a3 : a1) + __shfl_xor_sync(0xffffffffu, h16 ? a1 : a3, 16);  // a1 | a3
+    double c = (h8 ? b1 : b0) + __shfl_xor_sync(0xffffffffu, h8 ? b0 : b1, 8);            // a0, a1 | a2, a3
+    c += __shfl_xor_sync(0xffffffffu, c, 4);
+    c += __shfl_xor_sync(0xffffffffu, c, 2);
+    c += __shfl_xor_sync(0xffffffffu, c, 1);
+    return c;
+}
+
 __device__ __forceinline__ void stash_put_d(float (*st)[kChunk], int row, int col, double v) {
     st[row][col] = __int_as_float(__double2hiint(v));
     st[row + 1][col] = __int_as_float(__double2loint(v));
@@ -169,7 +183,10 @@ mb_warp2048_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
         for (int i = tid; i < kM; i += kThreads) S.twN[i] = make_float2(P.twN[i].x * h, P.twN[i].y * h);
     }
     for (int i = tid; i < kN; i += kThreads) S.window[i] = P.window[i];
-    for (int i = tid; i < MB_NUM_MFCC * MB_NUM_MEL_FILTERS; i += kThreads) S.dct[i] = P.dct[i];
+    for (int i = tid; i < MB_NUM_MFCC * 32; i += kThreads) {
+        const int n = i >> 5, l = i & 31, k = l % MB_NUM_MFCC, h = l / MB_NUM_MFCC;
+        S.dct2[i] = l < 2 * MB_NUM_MFCC ? P.dct[k + MB_NUM_MFCC * (n + MB_NUM_MFCC * h)] : 0.f;
+    }
     if (tid < MB_NUM_MEL_FILTERS + 2) {
         S.mel_edge[tid] = P.mel[tid];
         S.mel_inv[tid] = tid < MB_NUM_MEL_FILTERS + 1 ? P.mel_inv_width[tid] : 0.f;
@@ -216,12 +233,30 @@ mb_warp2048_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
     const int64_t warp_global = (int64_t)blockIdx.x * kWarps + warp;
     const int64_t warp_stride = (int64_t)gridDim.x * kWarps;
 
+#ifdef MB_EXP_SYNC  // experiment: keep the CTA's warps in step (same code window -> instruction-cache reuse)
+    const int64_t cta_first = (int64_t)blockIdx.x * kWarps;
+    for (int64_t chb = cta_first; chb < total_chunks; chb += warp_stride) {
+        const int64_t ch = chb + warp;
+        const int64_t g0 = ch * kChunk;
+        const int nfc = ch < total_chunks ? (int)min((int64_t)kChunk, T.total_frames - g0) : 0;
+        for (int j = 0; j < kChunk; j++) {
+#if MB_EXP_SYNC == 1
+            __syncthreads();
+#elif MB_EXP_SYNC == 2
+            asm volatile("bar.sync %0, %1;" ::"r"(1 + (warp >> 3)), "r"(kThreads / 2) : "memory");
+#elif MB_EXP_SYNC == 4
+            if ((j & 3) == 0) __syncthreads();
+#endif
+            if (j >= nfc) continue;
+            const int64_t g = g0 + j;
+#else
     for (int64_t ch = warp_global; ch < total_chunks; ch += warp_stride) {
         const int64_t g0 = ch * kChunk;
         const int nfc = (int)min((int64_t)kChunk, T.total_frames - g0);
 
         for (int j = 0; j < nfc; j++) {
             const int64_t g = g0 + j;
+#endif
             // ---- which clip (frames ascend, so mostly the cached one or its successor)
             if (g >= clip_f1 || g < clip_f0) {
                 if (g >= clip_f1 && clip + 2 <= T.n_clips && g < T.frame_start[clip + 2]) clip += 1;
@@ -275,33 +310,34 @@ mb_warp2048_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
             float2 v[32];
             float esum;
             uint32_t sgn_e, sgn_o;  // bit a: sample 2(32a+lane) (+1) is >= 0
-            uint32_t orbits;        // OR of every sample's bit pattern: bounds the largest exponent
             auto pass1 = [&]() {
                 esum = 0.f;
-                sgn_e = sgn_o = orbits = 0;
+                sgn_e = sgn_o = 0;
 #pragma unroll
                 for (int a = 0; a < 32; a++) {
                     const float2 x = slot2[32 * a + lane];
                     const float2 w = reinterpret_cast<const float2 *>(S.window)[32 * a + lane];
-                    orbits |= __float_as_uint(x.x) | __float_as_uint(x.y);
-                    if (want_time) {
-                        esum = fmaf(x.x, x.x, esum);
-                        esum = fmaf(x.y, x.y, esum);
-                        sgn_e |= (x.x >= 0.f) ? (1u << a) : 0u;
-                        sgn_o |= (x.y >= 0.f) ? (1u << a) : 0u;
+                    esum = fmaf(x.x, x.x, esum);
+                    esum = fmaf(x.y, x.y, esum);
+                    if (want_time) {  // (compare + predicated OR: two instructions per sample)
+                        asm("{\n\t.reg .pred p;\n\tsetp.ge.f32 p, %1, 0f00000000;\n\t@p or.b32 %0, %0, %2;\n\t}"
+                            : "+r"(sgn_e) : "f"(x.x), "r"(1u << a));
+                        asm("{\n\t.reg .pred p;\n\tsetp.ge.f32 p, %1, 0f00000000;\n\t@p or.b32 %0, %0, %2;\n\t}"
+                            : "+r"(sgn_o) : "f"(x.y), "r"(1u << a));
                     }
                     v[a] = make_float2(__fmul_rn(x.x, w.x), __fmul_rn(x.y, w.y));
                 }
             };
             pass1();
+            float energy = mb_warp_sum(esum);
             // Frames whose samples all sit below 2^-40 (or reach above 2^40) would under/overflow the
             // float32 squares in |Z|; the reference squares in float64.  Such a frame (rare: decayed
-            // tails, digital silence) is rescaled by an exact power of two in place and redone; Z and
-            // |Z| are scaled back on the way out.
+            // tails) is rescaled by an exact power of two in place and redone; Z and |Z| are scaled back
+            // on the way out.  The frame's energy is the cheap trigger (all |x| < 2^-40 puts it under 2^-69,
+            // one |x| > 2^40 above 2^80; zero and NaN take the look too), the largest sample decides.
             int kscale = 0;
             {
-                const int e_or = (int)((__reduce_or_sync(0xffffffffu, orbits) >> 23) & 0xffu);
-                if (want_spectrum && (e_or < 127 - 40 || (e_or > 127 + 40 && e_or != 255))) {
+                if (want_spectrum && !(energy >= 0x1p-60f && energy <= 0x1p70f)) {
                     float mx = 0.f;
                     for (int i = lane; i < kN; i += 32) mx = fmaxf(mx, fabsf(slot[i]));
 #pragma unroll
@@ -316,14 +352,13 @@ mb_warp2048_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
                         for (int i = lane; i < kN; i += 32) slot[i] *= up;
                         __syncwarp();
                         pass1();
+                        energy = mb_warp_sum(esum);
                     }
                 }
             }
             const float unscale = ldexpf(1.f, -kscale);
-            float energy = 0.f;
             int zcr = 0;
             if (want_time) {
-                energy = mb_warp_sum(esum);
                 // crossings inside a pair (2m, 2m+1), and between 2m+1 and 2m+2 (= lane+1, or lane 0 of the next row)
                 int z = __popc(sgn_e ^ sgn_o);
                 uint32_t nxt = __shfl_down_sync(0xffffffffu, sgn_e, 1);
@@ -528,16 +563,12 @@ mb_warp2048_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
                         const double s2 = fma(c2, ta, fma(2.0 * c, t1, t2));
                         const double s3 = fma(c2 * c, ta, fma(3.0 * c2, t1, fma(3.0 * c, t2, t3)));
                         const double s4 = fma(c2 * c2, ta, fma(4.0 * c2 * c, t1, fma(6.0 * c2, t2, fma(4.0 * c, t3, t4))));
-                        const double r1 = warp_sum_d(s1), r2 = warp_sum_d(s2), r3 = warp_sum_d(s3), r4 = warp_sum_d(s4);
+                        // four sums reduced together: after the two folding steps every lane carries one of them
+                        const double rq = warp_sum4_d(s1, s2, s3, s4, lane);
+                        if ((lane & 7) == 0) stash_put_d(stash, 4 + 2 * (lane >> 3), j, rq);  // lanes 0, 8, 16, 24: s1 .. s4
                         if (!want_rolloff) {  // (the rolloff scan below yields the same total)
                             const double r0 = warp_sum_d(ta);
                             if (lane == j) stash_put_d(stash, 2, j, r0);
-                        }
-                        if (lane == j) {
-                            stash_put_d(stash, 4, j, r1);
-                            stash_put_d(stash, 6, j, r2);
-                            stash_put_d(stash, 8, j, r3);
-                            stash_put_d(stash, 10, j, r4);
                         }
                     }
                     if (want_rolloff) {
@@ -617,12 +648,15 @@ mb_warp2048_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
                         }
                         const float fall_next = __shfl_down_sync(0xffffffffu, fall, 1);
                         const float lgE = logf(rise + fall_next);  // lanes >= 26 are not used below
+                        // 13 x 26 DCT on 26 lanes: lane k + 13 h sums filters 13 h .. 13 h + 12 of coefficient k
                         float acc = 0.f;
+                        const int half = lane >= MB_NUM_MFCC ? MB_NUM_MFCC : 0;
 #pragma unroll
-                        for (int f = 0; f < MB_NUM_MEL_FILTERS; f++) {
-                            const float lf = __shfl_sync(0xffffffffu, lgE, f);
-                            if (lane < MB_NUM_MFCC) acc = fmaf(S.dct[lane + f * MB_NUM_MFCC], lf, acc);
+                        for (int n = 0; n < MB_NUM_MFCC; n++) {
+                            const float lf = __shfl_sync(0xffffffffu, lgE, n + half);
+                            acc = fmaf(S.dct2[n * 32 + lane], lf, acc);
                         }
+                        acc += __shfl_down_sync(0xffffffffu, acc, MB_NUM_MFCC);
                         if (lane < MB_NUM_MFCC) O.mfcc[g * MB_NUM_MFCC + lane] = acc * (1.0f / (float)MB_NUM_MFCC);
                     }
                 }
