@@ -26,6 +26,12 @@
  *   mb_query_output  <- the implicit result shapes of src/feature-info.js:3-64.
  *   mb_stream_*      <- the stateful buffer-by-buffer use of the same
  *                       pipeline (src/meyda.js:69-91, start/stop :233-241).
+ *   mb_extract_pcm16 <- the same pipeline fed with the 16-bit PCM a WAV file
+ *   mb_wav_parse        holds instead of decoded float32: replaces
+ *                       lib/bufferLoader.js:13-44 (XHR + decodeAudioData, which
+ *                       turns int16 s into s / 32768) and the channel pick
+ *                       `getChannelData(0)` of src/meyda.js:72; the conversion
+ *                       happens inside the framing load of the kernels.
  *
  * Framing rule (the reference has none: ScriptProcessor hands over back-to-back
  * buffers, i.e. hop == bufferSize): frame f of a clip covers samples
@@ -205,6 +211,32 @@ mb_status mb_plan_synchronize(mb_plan *plan);
 mb_status mb_extract_multi(mb_plan *const *plans, int n_plans, const float *samples, int64_t n_samples,
                            const int64_t *clip_offset, const int64_t *clip_len, int64_t n_clips,
                            const mb_outputs *out);
+
+/*
+ * 16-bit PCM input (what the reference's fixtures audio/*.wav hold).  `pcm` is
+ * n_sample_frames x channels interleaved int16; channel `channel` is used and
+ * every sample becomes (float)s / 32768 on load (Web Audio decodeAudioData),
+ * so the results equal mb_extract on the converted samples bit for bit while
+ * the device reads half the bytes.  clip_offset / clip_len count sample frames.
+ * mem_kind as in mb_extract.  The _async form is MB_MEM_DEVICE only.
+ */
+mb_status mb_extract_pcm16(mb_plan *plan, const int16_t *pcm, int64_t n_sample_frames, int channels, int channel,
+                           const int64_t *clip_offset, const int64_t *clip_len, int64_t n_clips,
+                           const mb_outputs *out, int mem_kind);
+mb_status mb_extract_pcm16_async(mb_plan *plan, const int16_t *pcm, int64_t n_sample_frames, int channels,
+                                 int channel, const int64_t *clip_offset, const int64_t *clip_len, int64_t n_clips,
+                                 const mb_outputs *out);
+
+/* RIFF/WAVE header of an in-memory file: where the sample data lies and how to read it. */
+typedef struct mb_wav_info {
+    int32_t format;          /* 1 = integer PCM, 3 = IEEE float */
+    int32_t channels;
+    int32_t sample_rate;
+    int32_t bits_per_sample;
+    int64_t data_offset;     /* byte offset of the first sample frame */
+    int64_t n_sample_frames; /* per channel */
+} mb_wav_info;
+mb_status mb_wav_parse(const void *file_bytes, int64_t n_bytes, mb_wav_info *info);
 
 /* Number of kernel launches issued by this plan so far (bench evidence). */
 int64_t mb_plan_launch_count(const mb_plan *plan);

@@ -27,6 +27,7 @@ EXPORTS = [
     "mb_query_output", "mb_extract", "mb_extract_async", "mb_plan_synchronize", "mb_extract_multi",
     "mb_plan_launch_count", "mb_plan_kernel_name", "mb_host_alloc", "mb_host_free",
     "mb_stream_create", "mb_stream_destroy", "mb_stream_frames_after", "mb_stream_push", "mb_stream_reset",
+    "mb_extract_pcm16", "mb_extract_pcm16_async", "mb_wav_parse",
 ]
 
 # (field name in mb_outputs, feature name, per-frame length as a function of N)
@@ -62,6 +63,11 @@ class Layout(C.Structure):
     _fields_ = [("total_frames", C.c_int64), ("buffer_size", C.c_int32), ("spectrum_size", C.c_int32),
                 ("feature_mask", C.c_uint32), ("reserved", C.c_int32), ("output_bytes", C.c_int64),
                 ("bytes_per_frame", C.c_int64)]
+
+
+class WavInfo(C.Structure):
+    _fields_ = [("format", C.c_int32), ("channels", C.c_int32), ("sample_rate", C.c_int32),
+                ("bits_per_sample", C.c_int32), ("data_offset", C.c_int64), ("n_sample_frames", C.c_int64)]
 
 
 class MeydaNativeError(RuntimeError):
@@ -117,6 +123,11 @@ def lib():
     L.mb_stream_frames_after.argtypes = [vp, C.c_int64]
     L.mb_stream_push.argtypes = [vp, vp, C.c_int64, C.POINTER(Outputs), C.c_int, i64p]
     L.mb_stream_reset.argtypes = [vp]
+    L.mb_extract_pcm16.argtypes = [vp, vp, C.c_int64, C.c_int, C.c_int, i64p, i64p, C.c_int64, C.POINTER(Outputs),
+                                   C.c_int]
+    L.mb_extract_pcm16_async.argtypes = [vp, vp, C.c_int64, C.c_int, C.c_int, i64p, i64p, C.c_int64,
+                                         C.POINTER(Outputs)]
+    L.mb_wav_parse.argtypes = [vp, C.c_int64, C.POINTER(WavInfo)]
     _lib = L
     return L
 

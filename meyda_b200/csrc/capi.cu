@@ -90,7 +90,7 @@ bool is_power_of_two(int n) { return n > 0 && (n & (n - 1)) == 0; }
 struct Slot {  // one pipeline stage of a host-memory extract
     cudaStream_t stream = nullptr;
     float *d_samples = nullptr;
-    size_t samples_cap = 0;  // floats
+    size_t samples_cap = 0;  // bytes
     char *d_out = nullptr;
     size_t out_cap = 0;  // bytes
     int64_t *d_tab = nullptr;
@@ -261,10 +261,13 @@ mb_status check_clips(const mb_plan *p, int64_t n_samples, const int64_t *off, c
 // Launch the plan's kernel over `n` (virtual) clips whose offsets/prefix are
 // already in device memory.
 // `aligned`: every frame of this call starts on a 16-byte boundary (TMA bulk copies).
+// `pcm_channels` > 0: d_samples is interleaved int16 PCM (see MbClipTable).
 mb_status launch(mb_plan *p, const int64_t *d_off, const int64_t *d_frame_start, int64_t n, int64_t total_frames,
-                 const float *d_samples, const mb_outputs &d_out, cudaStream_t stream, bool aligned) {
+                 const float *d_samples, const mb_outputs &d_out, cudaStream_t stream, bool aligned,
+                 int pcm_channels = 0, int pcm_channel = 0) {
     if (total_frames == 0) return MB_OK;
-    MbClipTable T{d_off, d_frame_start, n, total_frames};
+    MbClipTable T{d_off, d_frame_start, n, total_frames, pcm_channels, pcm_channel};
+    const bool pcm = pcm_channels > 0;
     // 16-byte aligned frames: required by the bufferSize-32768 kernel's float4 loads; the warp kernel takes
     // any float-aligned frame (misaligned ones bypass TMA inside the kernel) but bulk-stores `buffer` rows
     const bool out_ok = (uintptr_t)d_out.buffer % 16 == 0;
@@ -272,10 +275,10 @@ mb_status launch(mb_plan *p, const int64_t *d_off, const int64_t *d_frame_start,
     if (p->use_cluster) {
         MB_CUDA(mb_launch_exact_cluster(p->dev, T, d_samples, d_out, p->num_sms, stream));
         p->launches_generic++;
-    } else if (p->has_big_kernel && tma_ok) {
+    } else if (p->has_big_kernel && tma_ok && !pcm) {
         MB_CUDA(mb_launch_big32768(p->dev, T, d_samples, d_out, p->num_sms, stream));
         p->launches_warp++;
-    } else if (p->has_warp_kernel && out_ok && ((uintptr_t)d_samples % 4 == 0)) {
+    } else if (p->has_warp_kernel && out_ok && ((uintptr_t)d_samples % (pcm ? 2 : 4) == 0)) {
         MB_CUDA(mb_launch_warp2048(p->dev, T, d_samples, d_out, p->num_sms, stream));
         p->launches_warp++;
     } else {
@@ -611,8 +614,9 @@ mb_status mb_query_output(const mb_plan *p, int64_t n_clips, const int64_t *clip
     return MB_OK;
 }
 
-mb_status mb_extract_async(mb_plan *p, const float *samples, int64_t n_samples, const int64_t *clip_offset,
-                           const int64_t *clip_len, int64_t n_clips, const mb_outputs *out) {
+static mb_status extract_device(mb_plan *p, const float *samples, int64_t n_samples, const int64_t *clip_offset,
+                                const int64_t *clip_len, int64_t n_clips, const mb_outputs *out, int pcm_channels,
+                                int pcm_channel) {
     if (!p) return fail(MB_ERR_INVALID_ARG, "plan is NULL");
     mb_status st = check_outputs(p, out);
     if (st != MB_OK) return st;
@@ -640,7 +644,27 @@ mb_status mb_extract_async(mb_plan *p, const float *samples, int64_t n_samples, 
     MB_CUDA(cudaEventRecord(p->tab_event, p->stream));
     p->tab_event_pending = true;
     return launch(p, p->d_tab, p->d_tab + n_clips, n_clips, total, samples, *out, p->stream,
-                  offsets_aligned(clip_offset, n_clips));
+                  offsets_aligned(clip_offset, n_clips), pcm_channels, pcm_channel);
+}
+
+mb_status mb_extract_async(mb_plan *p, const float *samples, int64_t n_samples, const int64_t *clip_offset,
+                           const int64_t *clip_len, int64_t n_clips, const mb_outputs *out) {
+    return extract_device(p, samples, n_samples, clip_offset, clip_len, n_clips, out, 0, 0);
+}
+
+static mb_status check_pcm(int channels, int channel) {
+    if (channels < 1 || channels > 64) return fail(MB_ERR_INVALID_ARG, "channel count %d outside [1, 64]", channels);
+    if (channel < 0 || channel >= channels) return fail(MB_ERR_INVALID_ARG, "channel %d of %d", channel, channels);
+    return MB_OK;
+}
+
+mb_status mb_extract_pcm16_async(mb_plan *p, const int16_t *pcm, int64_t n_sample_frames, int channels, int channel,
+                                 const int64_t *clip_offset, const int64_t *clip_len, int64_t n_clips,
+                                 const mb_outputs *out) {
+    mb_status st = check_pcm(channels, channel);
+    if (st != MB_OK) return st;
+    return extract_device(p, reinterpret_cast<const float *>(pcm), n_sample_frames, clip_offset, clip_len, n_clips, out,
+                          channels, channel);
 }
 
 mb_status mb_plan_synchronize(mb_plan *p) {
@@ -653,10 +677,12 @@ mb_status mb_plan_synchronize(mb_plan *p) {
 // Host-memory extract: frames are cut into chunks (possibly inside a clip);
 // each chunk is copied in, processed and copied out on one of two streams so
 // that PCIe traffic in both directions overlaps the kernels.
-static mb_status extract_host(mb_plan *p, const float *samples, const int64_t *clip_offset, const int64_t *clip_len,
-                              int64_t n_clips, const mb_outputs *out) {
+// `samples` is float32 (pcm_channels == 0) or interleaved int16 PCM; offsets count sample frames either way.
+static mb_status extract_host(mb_plan *p, const void *samples, const int64_t *clip_offset, const int64_t *clip_len,
+                              int64_t n_clips, const mb_outputs *out, int pcm_channels = 0, int pcm_channel = 0) {
     DeviceGuard guard(p->device);
     const int N = p->N, hop = p->hop;
+    const size_t frame_bytes = pcm_channels > 0 ? 2u * (size_t)pcm_channels : 4u;  // bytes per sample frame
     const int64_t bpf = std::max<int64_t>(p->bytes_per_frame, 4);
     // chunk budget: ~192 MiB of output or ~64 MiB of fresh input, whichever is hit first
     const int64_t max_frames_out = std::max<int64_t>(1, (192ll << 20) / bpf);
@@ -684,18 +710,18 @@ static mb_status extract_host(mb_plan *p, const float *samples, const int64_t *c
             f_in_clip += take;
         }
         if (frames == 0) break;
-        lo &= ~(int64_t)3;  // keep the device copy's 16-byte phase equal to the host array's
+        lo &= ~(int64_t)7;  // keep the device copy's 16-byte phase equal to the host array's (float32 and mono int16)
         Slot &s = p->slots[chunk_idx & 1];
         if (!s.stream) MB_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
         // the slot's previous chunk (two chunks ago) must have drained before its buffers are reused
         MB_CUDA(cudaStreamSynchronize(s.stream));
         const size_t span = (size_t)(hi - lo);
-        if (s.samples_cap < span) {
+        if (s.samples_cap < span * frame_bytes) {
             cudaFree(s.d_samples);
             s.d_samples = nullptr;
             s.samples_cap = 0;
-            MB_CUDA(cudaMalloc((void **)&s.d_samples, span * sizeof(float)));
-            s.samples_cap = span;
+            MB_CUDA(cudaMalloc((void **)&s.d_samples, span * frame_bytes));
+            s.samples_cap = span * frame_bytes;
         }
         const size_t out_bytes = (size_t)frames * (size_t)p->bytes_per_frame;
         if (s.out_cap < out_bytes) {
@@ -716,7 +742,8 @@ static mb_status extract_host(mb_plan *p, const float *samples, const int64_t *c
         }
         s.h_tab[2 * v.size()] = acc;
         MB_CUDA(cudaMemcpyAsync(s.d_tab, s.h_tab, entries * sizeof(int64_t), cudaMemcpyHostToDevice, s.stream));
-        MB_CUDA(cudaMemcpyAsync(s.d_samples, samples + lo, span * sizeof(float), cudaMemcpyHostToDevice, s.stream));
+        MB_CUDA(cudaMemcpyAsync(s.d_samples, (const char *)samples + (size_t)lo * frame_bytes, span * frame_bytes,
+                                cudaMemcpyHostToDevice, s.stream));
         // carve the slot's output arena
         mb_outputs d_out;
         memset(&d_out, 0, sizeof(d_out));
@@ -727,7 +754,7 @@ static mb_status extract_host(mb_plan *p, const float *samples, const int64_t *c
             cursor += (size_t)frames * field_elems(kFields[i], N) * 4;
         }
         st = launch(p, s.d_tab, s.d_tab + v.size(), (int64_t)v.size(), frames, s.d_samples, d_out, s.stream,
-                    offsets_aligned(s.h_tab, (int64_t)v.size()));
+                    offsets_aligned(s.h_tab, (int64_t)v.size()), pcm_channels, pcm_channel);
         if (st != MB_OK) return st;
         for (int i = 0; i < kNumFields; i++) {
             if (!mb_has(p->mask, kFields[i].feature)) continue;
@@ -760,6 +787,66 @@ mb_status mb_extract(mb_plan *p, const float *samples, int64_t n_samples, const 
     if (n_clips == 0) return MB_OK;
     if (!samples) return fail(MB_ERR_INVALID_ARG, "samples is NULL");
     return extract_host(p, samples, clip_offset, clip_len, n_clips, out);
+}
+
+
+mb_status mb_extract_pcm16(mb_plan *p, const int16_t *pcm, int64_t n_sample_frames, int channels, int channel,
+                           const int64_t *clip_offset, const int64_t *clip_len, int64_t n_clips, const mb_outputs *out,
+                           int mem_kind) {
+    if (!p) return fail(MB_ERR_INVALID_ARG, "plan is NULL");
+    mb_status st = check_pcm(channels, channel);
+    if (st != MB_OK) return st;
+    if (mem_kind == MB_MEM_DEVICE) {
+        st = mb_extract_pcm16_async(p, pcm, n_sample_frames, channels, channel, clip_offset, clip_len, n_clips, out);
+        if (st != MB_OK) return st;
+        return mb_plan_synchronize(p);
+    }
+    if (mem_kind != MB_MEM_HOST) return fail(MB_ERR_INVALID_ARG, "unknown memory kind %d", mem_kind);
+    st = check_outputs(p, out);
+    if (st != MB_OK) return st;
+    st = check_clips(p, n_sample_frames, clip_offset, clip_len, n_clips);
+    if (st != MB_OK) return st;
+    if (n_clips == 0) return MB_OK;
+    if (!pcm) return fail(MB_ERR_INVALID_ARG, "pcm is NULL");
+    return extract_host(p, pcm, clip_offset, clip_len, n_clips, out, channels, channel);
+}
+
+// RIFF/WAVE: "RIFF" <size> "WAVE" then chunks <id> <size> <payload, padded to even>; needs "fmt " and "data".
+mb_status mb_wav_parse(const void *file_bytes, int64_t n_bytes, mb_wav_info *info) {
+    if (!file_bytes || !info || n_bytes < 12) return fail(MB_ERR_INVALID_ARG, "not a RIFF/WAVE file (too short)");
+    const unsigned char *b = (const unsigned char *)file_bytes;
+    auto u16 = [&](int64_t o) { return (uint32_t)b[o] | ((uint32_t)b[o + 1] << 8); };
+    auto u32 = [&](int64_t o) { return u16(o) | (u16(o + 2) << 16); };
+    if (memcmp(b, "RIFF", 4) != 0 || memcmp(b + 8, "WAVE", 4) != 0)
+        return fail(MB_ERR_INVALID_ARG, "not a RIFF/WAVE file (bad magic)");
+    memset(info, 0, sizeof(*info));
+    bool have_fmt = false, have_data = false;
+    int block_align = 0;
+    int64_t data_bytes = 0;
+    for (int64_t o = 12; o + 8 <= n_bytes;) {
+        const int64_t size = u32(o + 4), body = o + 8;
+        if (memcmp(b + o, "fmt ", 4) == 0) {
+            if (size < 16 || body + 16 > n_bytes) return fail(MB_ERR_INVALID_ARG, "truncated fmt chunk");
+            info->format = (int32_t)u16(body);
+            info->channels = (int32_t)u16(body + 2);
+            info->sample_rate = (int32_t)u32(body + 4);
+            block_align = (int)u16(body + 12);
+            info->bits_per_sample = (int32_t)u16(body + 14);
+            if (info->format == 0xFFFE && size >= 26 && body + 26 <= n_bytes) info->format = (int32_t)u16(body + 24);  // WAVE_FORMAT_EXTENSIBLE: sub-format
+            have_fmt = true;
+        } else if (memcmp(b + o, "data", 4) == 0) {
+            info->data_offset = body;
+            data_bytes = std::min<int64_t>(size, n_bytes - body);
+            have_data = true;
+            break;
+        }
+        o = body + size + (size & 1);
+    }
+    if (!have_fmt || !have_data) return fail(MB_ERR_INVALID_ARG, "WAVE file without a fmt or data chunk");
+    if (info->channels < 1 || info->bits_per_sample < 8) return fail(MB_ERR_INVALID_ARG, "bad fmt chunk");
+    if (block_align <= 0) block_align = info->channels * (info->bits_per_sample / 8);
+    info->n_sample_frames = data_bytes / block_align;
+    return MB_OK;
 }
 
 mb_status mb_extract_multi(mb_plan *const *plans, int n_plans, const float *samples, int64_t n_samples,

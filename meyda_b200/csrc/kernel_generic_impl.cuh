@@ -344,7 +344,7 @@ mb_generic_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ M
 
     for (int64_t g = blockIdx.x; g < T.total_frames; g += gridDim.x) {
         const int64_t clip = mb_find_clip(T, g);
-        const float *__restrict__ src = samples + T.clip_off[clip] + (g - T.frame_start[clip]) * (int64_t)P.hop;
+        const MbFrameSrc src = mb_frame_src(T, samples, T.clip_off[clip] + (g - T.frame_start[clip]) * (int64_t)P.hop);
 
         MbFrameSums S;
         S.s0 = S.s1 = S.s2 = S.s3 = S.s4 = S.log2sum = S.energy = 0;
@@ -358,13 +358,13 @@ mb_generic_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ M
             int z = 0;
             float mxabs = 0.f;
             for (int i = tid; i < M; i += kThreads) {
-                const float x0 = __ldg(src + 2 * i), x1 = __ldg(src + 2 * i + 1);
+                const float x0 = src[2 * i], x1 = src[2 * i + 1];
                 mxabs = fmaxf(mxabs, fmaxf(fabsf(x0), fabsf(x1)));
                 if (want_time) {
                     e += (double)x0 * (double)x0 + (double)x1 * (double)x1;
                     z += ((x0 >= 0.f) != (x1 >= 0.f)) && (x0 == x0) && (x1 == x1);
                     if (2 * i + 2 < N) {
-                        const float x2 = __ldg(src + 2 * i + 2);
+                        const float x2 = src[2 * i + 2];
                         z += ((x1 >= 0.f) != (x2 >= 0.f)) && (x1 == x1) && (x2 == x2);
                     }
                     if (mb_has(mask, MB_FEAT_BUFFER)) {
@@ -522,7 +522,7 @@ mb_exact_cluster_kernel(const __grid_constant__ MbDevPlan P, const __grid_consta
 
     for (int64_t g = cid; g < T.total_frames; g += n_clusters) {
         const int64_t clip = mb_find_clip(T, g);
-        const float *__restrict__ src = samples + T.clip_off[clip] + (g - T.frame_start[clip]) * (int64_t)P.hop;
+        const MbFrameSrc src = mb_frame_src(T, samples, T.clip_off[clip] + (g - T.frame_start[clip]) * (int64_t)P.hop);
         MbFrameSums S;
         S.s0 = S.s1 = S.s2 = S.s3 = S.s4 = S.log2sum = S.energy = 0;
         S.zcr = 0;
@@ -532,10 +532,10 @@ mb_exact_cluster_kernel(const __grid_constant__ MbDevPlan P, const __grid_consta
             double e = 0;
             int z = 0;
             for (int i = tid; i < N; i += kThreads) {
-                const float x0 = __ldg(src + i);
+                const float x0 = src[i];
                 e += (double)x0 * (double)x0;
                 if (i + 1 < N) {
-                    const float x1 = __ldg(src + i + 1);
+                    const float x1 = src[i + 1];
                     z += ((x0 >= 0.f) != (x1 >= 0.f)) && (x0 == x0) && (x1 == x1);
                 }
                 if (mb_has(mask, MB_FEAT_BUFFER)) O.buffer[g * N + i] = x0;
@@ -548,7 +548,7 @@ mb_exact_cluster_kernel(const __grid_constant__ MbDevPlan P, const __grid_consta
             const int rshift = 32 - log2N;
             for (int pl = tid; pl < H; pl += kThreads) {
                 const int i = (int)(__brev((unsigned)(rank * H + pl)) >> rshift);
-                xre[xidx(pl)] = __fmul_rn(__ldg(src + i), __ldg(P.window + i));
+                xre[xidx(pl)] = __fmul_rn(src[i], __ldg(P.window + i));
                 xim[xidx(pl)] = 0.f;
             }
             __syncthreads();

@@ -163,7 +163,10 @@ __device__ __forceinline__ double stash_get_d(float (*st)[kChunk], int row, int 
 }
 
 // kFull: every feature is requested (the headline configuration) -- the per-bin feature tests fold away.
-template <bool kFull>
+// kPcm: `samples` holds 16-bit PCM (MbClipTable::pcm_channels interleaved channels); a frame arrives as 4 KB
+// instead of 8 KB and is converted in pass 1 (x = s / 32768, exact), after which nothing differs -- the results
+// are bit-identical to the float32 path on the converted samples.  `buffer` then leaves from registers.
+template <bool kFull, bool kPcm>
 __global__ void __launch_bounds__(kThreads, 1)
 mb_warp2048_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ MbClipTable T,
                    const float *__restrict__ samples, const __grid_constant__ mb_outputs O, const int64_t total_chunks) {
@@ -233,30 +236,12 @@ mb_warp2048_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
     const int64_t warp_global = (int64_t)blockIdx.x * kWarps + warp;
     const int64_t warp_stride = (int64_t)gridDim.x * kWarps;
 
-#ifdef MB_EXP_SYNC  // experiment: keep the CTA's warps in step (same code window -> instruction-cache reuse)
-    const int64_t cta_first = (int64_t)blockIdx.x * kWarps;
-    for (int64_t chb = cta_first; chb < total_chunks; chb += warp_stride) {
-        const int64_t ch = chb + warp;
-        const int64_t g0 = ch * kChunk;
-        const int nfc = ch < total_chunks ? (int)min((int64_t)kChunk, T.total_frames - g0) : 0;
-        for (int j = 0; j < kChunk; j++) {
-#if MB_EXP_SYNC == 1
-            __syncthreads();
-#elif MB_EXP_SYNC == 2
-            asm volatile("bar.sync %0, %1;" ::"r"(1 + (warp >> 3)), "r"(kThreads / 2) : "memory");
-#elif MB_EXP_SYNC == 4
-            if ((j & 3) == 0) __syncthreads();
-#endif
-            if (j >= nfc) continue;
-            const int64_t g = g0 + j;
-#else
     for (int64_t ch = warp_global; ch < total_chunks; ch += warp_stride) {
         const int64_t g0 = ch * kChunk;
         const int nfc = (int)min((int64_t)kChunk, T.total_frames - g0);
 
         for (int j = 0; j < nfc; j++) {
             const int64_t g = g0 + j;
-#endif
             // ---- which clip (frames ascend, so mostly the cached one or its successor)
             if (g >= clip_f1 || g < clip_f0) {
                 if (g >= clip_f1 && clip + 2 <= T.n_clips && g < T.frame_start[clip + 2]) clip += 1;
@@ -264,17 +249,26 @@ mb_warp2048_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
                 clip_f0 = T.frame_start[clip];
                 clip_f1 = T.frame_start[clip + 1];
             }
-            const float *src = samples + T.clip_off[clip] + (g - clip_f0) * (int64_t)P.hop;
+            const int64_t first = T.clip_off[clip] + (g - clip_f0) * (int64_t)P.hop;
+            const float *src = samples + first;  // (float32 input)
+            const int16_t *src16 = reinterpret_cast<const int16_t *>(samples) + first * T.pcm_channels + T.pcm_channel;
+            constexpr uint32_t kFrameBytes = kPcm ? kN * 2 : kN * 4;
 
             // ---- 1. frame into the warp's slot (TMA), buffer out of it (TMA)
             __syncwarp();  // every lane is done with the slot's previous contents
             // TMA needs a 16-byte aligned source: a frame that starts elsewhere (odd clip offsets, hop not a
             // multiple of 4) is copied in by the lanes instead; everything after that is the same.
-            const bool src_aligned = (reinterpret_cast<uintptr_t>(src) & 15) == 0;
+            const bool src_aligned = kPcm ? (T.pcm_channels == 1 && (reinterpret_cast<uintptr_t>(src16) & 15) == 0)
+                                          : (reinterpret_cast<uintptr_t>(src) & 15) == 0;
             if (!src_aligned) {
                 if (lane == 0) bulk_store_wait_read();
                 __syncwarp();
-                for (int i = lane; i < kN; i += 32) slot[i] = __ldg(src + i);
+                if (kPcm) {  // also the channel pick of interleaved PCM
+                    const int st = T.pcm_channels;
+                    for (int i = lane; i < kN; i += 32) reinterpret_cast<int16_t *>(slot)[i] = __ldg(src16 + (int64_t)i * st);
+                } else {
+                    for (int i = lane; i < kN; i += 32) slot[i] = __ldg(src + i);
+                }
                 // the `buffer` bulk store below reads the slot through the async proxy
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
@@ -286,11 +280,14 @@ mb_warp2048_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
                 bulk_store_wait_read();  // an earlier frame's `buffer` store has finished reading the slot
                 // generic-proxy accesses to the slot are ordered before the async-proxy write that follows
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                mbar_expect_tx(bar, kN * 4);
-                bulk_load(slot, src, kN * 4, bar, pol_keep);
+                mbar_expect_tx(bar, kFrameBytes);
+                bulk_load(slot, kPcm ? (const void *)src16 : (const void *)src, kFrameBytes, bar, pol_keep);
                 // the samples the next frame adds, towards L2 while this frame is being worked on
                 if (j + 1 < nfc && g + 1 < clip_f1)
-                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src + kN), "r"((uint32_t)(P.hop * 4)) : "memory");
+                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(kPcm ? (const void *)(src16 + kN)
+                                                                                           : (const void *)(src + kN)),
+                                 "r"((uint32_t)(P.hop * (kPcm ? 2 : 4)))
+                                 : "memory");
             }
             __syncwarp();
             mbar_wait(bar, parity);
@@ -304,7 +301,7 @@ mb_warp2048_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
 #else
             const bool exp_store = true;
 #endif
-            if (want_buffer && exp_store && lane == 0) bulk_store(O.buffer + g * kN, slot, kN * 4, pol_stream);
+            if (!kPcm && want_buffer && exp_store && lane == 0) bulk_store(O.buffer + g * kN, slot, kN * 4, pol_stream);
 
             // ---- 2. pass 1: window, time-domain sums, FFT32 over a for b = lane
             float2 v[32];
@@ -315,7 +312,16 @@ mb_warp2048_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
                 sgn_e = sgn_o = 0;
 #pragma unroll
                 for (int a = 0; a < 32; a++) {
-                    const float2 x = slot2[32 * a + lane];
+                    float2 x;
+                    if (kPcm) {
+                        const uint32_t raw = reinterpret_cast<const uint32_t *>(slot)[32 * a + lane];  // two samples
+                        x = make_float2((float)(int16_t)(raw & 0xffffu) * (1.0f / 32768.0f),
+                                        (float)(int16_t)(raw >> 16) * (1.0f / 32768.0f));
+                        if (want_buffer && exp_store)
+                            __stcs(reinterpret_cast<float2 *>(O.buffer + g * kN) + 32 * a + lane, x);
+                    } else {
+                        x = slot2[32 * a + lane];
+                    }
                     const float2 w = reinterpret_cast<const float2 *>(S.window)[32 * a + lane];
                     esum = fmaf(x.x, x.x, esum);
                     esum = fmaf(x.y, x.y, esum);
@@ -337,7 +343,7 @@ mb_warp2048_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
             // one |x| > 2^40 above 2^80; zero and NaN take the look too), the largest sample decides.
             int kscale = 0;
             {
-                if (want_spectrum && !(energy >= 0x1p-60f && energy <= 0x1p70f)) {
+                if (!kPcm && want_spectrum && !(energy >= 0x1p-60f && energy <= 0x1p70f)) {  // (PCM: |x| is 0 or >= 2^-15)
                     float mx = 0.f;
                     for (int i = lane; i < kN; i += 32) mx = fmaxf(mx, fabsf(slot[i]));
 #pragma unroll
@@ -370,7 +376,7 @@ mb_warp2048_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
                 }
                 z += __popc((sgn_o ^ nxt) & valid);
                 zcr = mb_warp_sum(z);
-                if (!(energy == energy)) {
+                if (!kPcm && !(energy == energy)) {
                     // a NaN sample: zcr.js compares are all false around it; recount exactly
                     z = 0;
                     for (int i = lane; i < kN - 1; i += 32) {
@@ -399,7 +405,7 @@ mb_warp2048_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
                     fft32(v);
                     __syncwarp();  // pass 0: all lanes have read their raw samples, the slot becomes the transpose buffer
                     if (pass == 0) {
-                        if (want_buffer && lane == 0) bulk_store_wait_read();
+                        if (!kPcm && want_buffer && lane == 0) bulk_store_wait_read();
                         __syncwarp();
                         float2 t_nx = S.tw32[32 + lane];
 #pragma unroll
@@ -701,16 +707,16 @@ size_t mb_warp2048_smem_bytes() { return sizeof(Smem) + 128; }
 cudaError_t mb_launch_warp2048(const MbDevPlan &P, const MbClipTable &T, const float *samples, const mb_outputs &O,
                                int num_sms, cudaStream_t stream) {
     const size_t smem = mb_warp2048_smem_bytes();
-    const bool full = (P.mask & MB_ALL_FEATURES) == MB_ALL_FEATURES;
-    cudaError_t e = cudaFuncSetAttribute(full ? mb_warp2048_kernel<true> : mb_warp2048_kernel<false>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const bool full = (P.mask & MB_ALL_FEATURES) == MB_ALL_FEATURES, pcm = T.pcm_channels > 0;
+    auto kernel = full ? (pcm ? mb_warp2048_kernel<true, true> : mb_warp2048_kernel<true, false>)
+                       : (pcm ? mb_warp2048_kernel<false, true> : mb_warp2048_kernel<false, false>);
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const int64_t chunks = (T.total_frames + kChunk - 1) / kChunk;
     int64_t grid = (chunks + kWarps - 1) / kWarps;
     if (grid > num_sms) grid = num_sms;
     if (grid < 1) return cudaSuccess;
     (void)cudaGetLastError();
-    if (full) mb_warp2048_kernel<true><<<(unsigned)grid, kThreads, smem, stream>>>(P, T, samples, O, chunks);
-    else mb_warp2048_kernel<false><<<(unsigned)grid, kThreads, smem, stream>>>(P, T, samples, O, chunks);
+    kernel<<<(unsigned)grid, kThreads, smem, stream>>>(P, T, samples, O, chunks);
     return cudaGetLastError();
 }

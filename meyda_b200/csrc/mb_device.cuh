@@ -62,11 +62,39 @@ struct MbDevPlan {
 
 // Clip list of one extract call (device arrays).
 struct MbClipTable {
-    const int64_t *clip_off;     // [n_clips] first sample of each clip
+    const int64_t *clip_off;     // [n_clips] first sample (per channel) of each clip
     const int64_t *frame_start;  // [n_clips + 1] exclusive prefix of frames per clip
     int64_t n_clips;
     int64_t total_frames;
+    // 0: `samples` is float32 mono.  > 0: `samples` is 16-bit PCM with this many interleaved channels, of which
+    // `pcm_channel` is taken and converted on load as decodeAudioData does (int16 / 32768; the step
+    // lib/bufferLoader.js:13-44 + getChannelData(0), src/meyda.js:72, perform in the reference).
+    int pcm_channels;
+    int pcm_channel;
 };
+
+// One frame's samples, whatever the storage.
+struct MbFrameSrc {
+    const float *f;
+    const int16_t *s;
+    int stride;
+    __device__ __forceinline__ float operator[](int i) const {
+        return s ? (float)__ldg(s + (int64_t)i * stride) * (1.0f / 32768.0f) : __ldg(f + i);
+    }
+};
+__device__ __forceinline__ MbFrameSrc mb_frame_src(const MbClipTable &T, const float *samples, int64_t first) {
+    MbFrameSrc r;
+    if (T.pcm_channels > 0) {
+        r.f = nullptr;
+        r.s = reinterpret_cast<const int16_t *>(samples) + first * T.pcm_channels + T.pcm_channel;
+        r.stride = T.pcm_channels;
+    } else {
+        r.f = samples + first;
+        r.s = nullptr;
+        r.stride = 1;
+    }
+    return r;
+}
 
 __host__ __device__ __forceinline__ bool mb_has(uint32_t mask, int f) { return (mask >> f) & 1u; }
 

@@ -197,6 +197,39 @@ class Plan:
                                        lengths.ctypes.data_as(i64p), len(lengths), C.byref(o), _capi.MB_MEM_HOST))
         return out, per
 
+    def extract_pcm16_host(self, pcm: np.ndarray, offsets: np.ndarray, lengths: np.ndarray, channel: int = 0,
+                           out: dict | None = None):
+        """MB_MEM_HOST call on 16-bit PCM: `pcm` is int16 [sample_frames] (mono) or [sample_frames, channels]
+        (interleaved, as a WAV data chunk holds it); offsets/lengths count sample frames.  The int16 -> float32
+        conversion of decodeAudioData (s / 32768) and the channel pick happen inside the kernels' frame load."""
+        pcm = np.ascontiguousarray(pcm, dtype=np.int16)
+        channels = 1 if pcm.ndim == 1 else pcm.shape[1]
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        lengths = np.ascontiguousarray(lengths, dtype=np.int64)
+        per, lay = self.query(lengths)
+        if out is None:
+            out = self.alloc_host_outputs(int(lay.total_frames))
+        o = self.pack_outputs({k: v.ctypes.data for k, v in out.items()})
+        i64p = C.POINTER(C.c_int64)
+        _capi.check(self._L.mb_extract_pcm16(self._h, pcm.ctypes.data, pcm.shape[0], channels, channel,
+                                             offsets.ctypes.data_as(i64p), lengths.ctypes.data_as(i64p), len(lengths),
+                                             C.byref(o), _capi.MB_MEM_HOST))
+        return out, per
+
+    def extract_pcm16_device(self, pcm_ptr: int, n_sample_frames: int, channels: int, channel: int,
+                             offsets: np.ndarray, lengths: np.ndarray, out_ptrs: dict, sync: bool = True):
+        """MB_MEM_DEVICE call on 16-bit PCM already resident on the plan's device."""
+        o = self.pack_outputs(out_ptrs)
+        i64p = C.POINTER(C.c_int64)
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        lengths = np.ascontiguousarray(lengths, dtype=np.int64)
+        args = [self._h, C.c_void_p(pcm_ptr), n_sample_frames, channels, channel, offsets.ctypes.data_as(i64p),
+                lengths.ctypes.data_as(i64p), len(lengths), C.byref(o)]
+        if sync:
+            _capi.check(self._L.mb_extract_pcm16(*args, _capi.MB_MEM_DEVICE))
+        else:
+            _capi.check(self._L.mb_extract_pcm16_async(*args))
+
     def extract_device(self, samples_ptr: int, n_samples: int, offsets: np.ndarray, lengths: np.ndarray,
                        out_ptrs: dict, sync: bool = True):
         """MB_MEM_DEVICE call on raw device pointers (e.g. torch tensors' data_ptr())."""
@@ -317,6 +350,63 @@ def extract(clips, bufferSize: int, hop: int | None = None, sampleRate: float = 
     finally:
         for p in plans:
             p.close()
+    res = ExtractResult(feats, arrays, per, int(bufferSize))
+    if callback is not None:
+        for i in range(res.total_frames):
+            callback(res.frame(i))
+    return res
+
+
+def wav_info(file_bytes) -> dict:
+    """RIFF/WAVE header of an in-memory file (mb_wav_parse): format, channels, sampleRate, bitsPerSample,
+    dataOffset, sampleFrames."""
+    buf = np.frombuffer(bytes(file_bytes), dtype=np.uint8)
+    info = _capi.WavInfo()
+    _capi.check(_capi.lib().mb_wav_parse(buf.ctypes.data, buf.size, C.byref(info)))
+    return {"format": info.format, "channels": info.channels, "sampleRate": info.sample_rate,
+            "bitsPerSample": info.bits_per_sample, "dataOffset": info.data_offset,
+            "sampleFrames": info.n_sample_frames}
+
+
+def extract_wav(files, bufferSize: int, hop: int | None = None, windowingFunction: str = "hanning",
+                features=tuple(FEATURES), channel: int = 0, callback: Callable[[dict], None] | None = None,
+                device: int = 0, flags: int = 0) -> ExtractResult:
+    """Replaces BufferLoader + decodeAudioData + getChannelData(channel) (lib/bufferLoader.js:13-44,
+    src/meyda.js:72) in front of `extract`: `files` is one path / bytes object or a list of them, each a
+    16-bit PCM WAV; the int16 samples go to the GPU as they are and become s / 32768 inside the frame load.
+    All files must share the channel count and sample rate (which becomes the plan's sampleRate)."""
+    feats, _single = _split_features(features)
+    if not feats:
+        raise MeydaError("Invalid Feature Format")
+    if isinstance(files, (str, bytes, bytearray, memoryview)):
+        files = [files]
+    blobs = []
+    for f in files:
+        if isinstance(f, str):
+            with open(f, "rb") as fh:
+                f = fh.read()
+        blobs.append(bytes(f))
+    infos = [wav_info(b) for b in blobs]
+    for i in infos:
+        if i["format"] != 1 or i["bitsPerSample"] != 16:
+            raise MeydaError("extract_wav takes 16-bit integer PCM (got format %d, %d bits)" % (i["format"], i["bitsPerSample"]))
+        if (i["channels"], i["sampleRate"]) != (infos[0]["channels"], infos[0]["sampleRate"]):
+            raise MeydaError("all WAV files of one call must share channel count and sample rate")
+    ch = infos[0]["channels"]
+    parts = [np.frombuffer(b, dtype="<i2", count=i["sampleFrames"] * ch, offset=i["dataOffset"]).reshape(-1, ch)
+             for b, i in zip(blobs, infos)]
+    # clips start on multiples of 8 sample frames so that mono frames stay 16-byte aligned (TMA bulk loads)
+    lengths = np.array([p.shape[0] for p in parts], dtype=np.int64)
+    padded = (lengths + 7) // 8 * 8
+    offsets = np.concatenate([[0], np.cumsum(padded)[:-1]]).astype(np.int64)
+    pcm = np.zeros((int(padded.sum()), ch), dtype=np.int16)
+    for o, p in zip(offsets, parts):
+        pcm[o:o + p.shape[0]] = p
+    plan = Plan(bufferSize, hop, float(infos[0]["sampleRate"]), windowingFunction, feats, device=device, flags=flags)
+    try:
+        arrays, per = plan.extract_pcm16_host(pcm if ch > 1 else pcm[:, 0], offsets, lengths, channel=channel)
+    finally:
+        plan.close()
     res = ExtractResult(feats, arrays, per, int(bufferSize))
     if callback is not None:
         for i in range(res.total_frames):
