@@ -259,6 +259,8 @@ int64_t mb_stream_frames_after(const mb_stream *stream, int64_t n_new_samples);
 mb_status mb_stream_push(mb_stream *stream, const float *new_samples, int64_t n_new_samples,
                          const mb_outputs *out, int mem_kind, int64_t *frames_done);
 mb_status mb_stream_reset(mb_stream *stream);
+/* How many pushes were replayed as a CUDA graph so far (MB_MEM_HOST pushes of a repeating shape). */
+int64_t mb_stream_graph_launches(const mb_stream *stream);
 
 #ifdef __cplusplus
 }

@@ -27,7 +27,7 @@ EXPORTS = [
     "mb_query_output", "mb_extract", "mb_extract_async", "mb_plan_synchronize", "mb_extract_multi",
     "mb_plan_launch_count", "mb_plan_kernel_name", "mb_host_alloc", "mb_host_free",
     "mb_stream_create", "mb_stream_destroy", "mb_stream_frames_after", "mb_stream_push", "mb_stream_reset",
-    "mb_extract_pcm16", "mb_extract_pcm16_async", "mb_wav_parse",
+    "mb_extract_pcm16", "mb_extract_pcm16_async", "mb_wav_parse", "mb_stream_graph_launches",
 ]
 
 # (field name in mb_outputs, feature name, per-frame length as a function of N)
@@ -123,6 +123,8 @@ def lib():
     L.mb_stream_frames_after.argtypes = [vp, C.c_int64]
     L.mb_stream_push.argtypes = [vp, vp, C.c_int64, C.POINTER(Outputs), C.c_int, i64p]
     L.mb_stream_reset.argtypes = [vp]
+    L.mb_stream_graph_launches.restype = C.c_int64
+    L.mb_stream_graph_launches.argtypes = [vp]
     L.mb_extract_pcm16.argtypes = [vp, vp, C.c_int64, C.c_int, C.c_int, i64p, i64p, C.c_int64, C.POINTER(Outputs),
                                    C.c_int]
     L.mb_extract_pcm16_async.argtypes = [vp, vp, C.c_int64, C.c_int, C.c_int, i64p, i64p, C.c_int64,

@@ -128,6 +128,13 @@ struct mb_plan {
     const char *kernel_name = "generic";
 };
 
+struct StreamGraph {  // one captured push: same buffer parity, same fill level, same block size
+    int cur = -1;
+    int64_t filled = -1, n_new = -1;
+    int seen = 0;
+    cudaGraphExec_t exec = nullptr;
+};
+
 struct mb_stream {
     mb_plan *plan = nullptr;
     float *d_buf[2] = {nullptr, nullptr};
@@ -135,6 +142,15 @@ struct mb_stream {
     int cur = 0;
     int64_t filled = 0;
     int64_t skip = 0;  // samples still to drop before the next frame starts (hop > bufferSize)
+    // host-memory pushes: pinned staging both ways, one device arena for all outputs, a private clip table
+    float *h_in = nullptr;
+    size_t h_in_cap = 0;  // floats
+    char *d_out = nullptr, *h_out = nullptr;
+    size_t out_cap = 0;  // bytes
+    int64_t *d_tab = nullptr, *h_tab = nullptr;  // {clip_off = 0, frame_start = 0, nf}
+    int64_t tab_nf = -1;
+    StreamGraph graphs[4];
+    int64_t graph_launches = 0;
 };
 
 namespace {
@@ -922,10 +938,19 @@ void mb_stream_destroy(mb_stream *s) {
     if (!s) return;
     DeviceGuard guard(s->plan->device);
     cudaStreamSynchronize(s->plan->stream);
+    for (auto &g : s->graphs)
+        if (g.exec) cudaGraphExecDestroy(g.exec);
     cudaFree(s->d_buf[0]);
     cudaFree(s->d_buf[1]);
+    cudaFree(s->d_out);
+    cudaFree(s->d_tab);
+    if (s->h_in) cudaFreeHost(s->h_in);
+    if (s->h_out) cudaFreeHost(s->h_out);
+    if (s->h_tab) cudaFreeHost(s->h_tab);
     delete s;
 }
+
+int64_t mb_stream_graph_launches(const mb_stream *s) { return s ? s->graph_launches : 0; }
 
 int64_t mb_stream_frames_after(const mb_stream *s, int64_t n_new) {
     if (!s || n_new < 0) return 0;
@@ -970,63 +995,150 @@ mb_status mb_stream_push(mb_stream *s, const float *new_samples, int64_t n_new, 
         s->d_buf[1] = nb[1];
         s->cur = 0;
         s->cap = cap;
+        for (auto &g : s->graphs) g.cur = -1;  // captured pushes point into the old buffers
     }
     float *buf = s->d_buf[s->cur];
-    if (n_new)
-        MB_CUDA(cudaMemcpyAsync(buf + s->filled, new_samples, n_new * sizeof(float),
-                                mem_kind == MB_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice,
-                                p->stream));
-    s->filled = need;
-    const int64_t nf = mb_num_frames(s->filled, p->N, p->hop);
-    if (nf == 0) {
-        MB_CUDA(cudaStreamSynchronize(p->stream));
-        return MB_OK;
-    }
-    mb_status st = check_outputs(p, out);
-    if (st != MB_OK) return st;
-    const int64_t off = 0, len = s->filled;
-    if (mem_kind == MB_MEM_DEVICE) {
-        st = mb_extract_async(p, buf, s->filled, &off, &len, 1, out);
+    const int64_t filled_before = s->filled;
+    const int64_t nf = mb_num_frames(need, p->N, p->hop);
+    if (nf > 0) {
+        mb_status st = check_outputs(p, out);
         if (st != MB_OK) return st;
-    } else {
-        // device-side result arena from slot 0, then one D2H per requested array
-        Slot &sl = p->slots[0];
-        const size_t out_bytes = (size_t)nf * (size_t)p->bytes_per_frame;
-        if (sl.out_cap < out_bytes) {
-            MB_CUDA(cudaStreamSynchronize(p->stream));
-            cudaFree(sl.d_out);
-            sl.d_out = nullptr;
-            sl.out_cap = 0;
-            MB_CUDA(cudaMalloc((void **)&sl.d_out, out_bytes + out_bytes / 2));
-            sl.out_cap = out_bytes + out_bytes / 2;
+    }
+    const int64_t consumed = nf * p->hop;  // the hop-overlap tail [consumed, need) stays for the next push
+    const int64_t rest = std::max<int64_t>(0, need - consumed);
+
+    if (mem_kind == MB_MEM_DEVICE) {
+        if (n_new)
+            MB_CUDA(cudaMemcpyAsync(buf + filled_before, new_samples, n_new * sizeof(float), cudaMemcpyDeviceToDevice,
+                                    p->stream));
+        if (nf > 0) {
+            const int64_t off = 0, len = need;
+            mb_status st = mb_extract_async(p, buf, need, &off, &len, 1, out);
+            if (st != MB_OK) return st;
+            if (rest)
+                MB_CUDA(cudaMemcpyAsync(s->d_buf[s->cur ^ 1], buf + consumed, rest * sizeof(float),
+                                        cudaMemcpyDeviceToDevice, p->stream));
         }
+        MB_CUDA(cudaStreamSynchronize(p->stream));
+    } else {
+        // Host memory, the latency path (one buffer per call, as onaudioprocess delivers them): the block goes
+        // through pinned staging, every output leaves in ONE device-to-host copy of a packed arena, and the
+        // whole push (copy in, kernel, copy out, tail move) is replayed as a CUDA graph once its shape
+        // (buffer parity, fill level, block size) has been seen before.
+        const size_t out_bytes = (size_t)nf * (size_t)p->bytes_per_frame;
+        if (s->h_in_cap < (size_t)n_new) {
+            if (s->h_in) cudaFreeHost(s->h_in);
+            s->h_in = nullptr;
+            s->h_in_cap = 0;
+            MB_CUDA(cudaMallocHost((void **)&s->h_in, ((size_t)n_new + (size_t)n_new / 2 + 64) * sizeof(float)));
+            s->h_in_cap = (size_t)n_new + (size_t)n_new / 2 + 64;
+            for (auto &g : s->graphs) g.cur = -1;  // captured pointers are stale
+        }
+        if (s->out_cap < out_bytes) {
+            MB_CUDA(cudaStreamSynchronize(p->stream));
+            cudaFree(s->d_out);
+            if (s->h_out) cudaFreeHost(s->h_out);
+            s->d_out = s->h_out = nullptr;
+            s->out_cap = 0;
+            MB_CUDA(cudaMalloc((void **)&s->d_out, out_bytes + out_bytes / 2));
+            MB_CUDA(cudaMallocHost((void **)&s->h_out, out_bytes + out_bytes / 2));
+            s->out_cap = out_bytes + out_bytes / 2;
+            for (auto &g : s->graphs) g.cur = -1;
+        }
+        if (!s->d_tab) {
+            MB_CUDA(cudaMalloc((void **)&s->d_tab, 3 * sizeof(int64_t)));
+            MB_CUDA(cudaMallocHost((void **)&s->h_tab, 3 * sizeof(int64_t)));
+        }
+        if (nf > 0 && s->tab_nf != nf) {  // clip table of the single clip [0, need): only its frame count varies
+            MB_CUDA(cudaStreamSynchronize(p->stream));
+            s->h_tab[0] = 0;
+            s->h_tab[1] = 0;
+            s->h_tab[2] = nf;
+            MB_CUDA(cudaMemcpyAsync(s->d_tab, s->h_tab, 3 * sizeof(int64_t), cudaMemcpyHostToDevice, p->stream));
+            s->tab_nf = nf;
+        }
+        if (n_new) memcpy(s->h_in, new_samples, (size_t)n_new * sizeof(float));
         mb_outputs d_out;
         memset(&d_out, 0, sizeof(d_out));
         size_t cursor = 0;
         for (int i = 0; i < kNumFields; i++) {
             if (!mb_has(p->mask, kFields[i].feature)) continue;
-            field_ptr(d_out, kFields[i]) = sl.d_out + cursor;
+            field_ptr(d_out, kFields[i]) = s->d_out + cursor;
             cursor += (size_t)nf * field_elems(kFields[i], p->N) * 4;
         }
-        st = mb_extract_async(p, buf, s->filled, &off, &len, 1, &d_out);
-        if (st != MB_OK) return st;
-        for (int i = 0; i < kNumFields; i++) {
+        auto enqueue = [&]() -> mb_status {
+            if (n_new)
+                MB_CUDA(cudaMemcpyAsync(buf + filled_before, s->h_in, n_new * sizeof(float), cudaMemcpyHostToDevice,
+                                        p->stream));
+            if (nf > 0) {
+                mb_status st = launch(p, s->d_tab, s->d_tab + 1, 1, nf, buf, d_out, p->stream, true);
+                if (st != MB_OK) return st;
+                MB_CUDA(cudaMemcpyAsync(s->h_out, s->d_out, out_bytes, cudaMemcpyDeviceToHost, p->stream));
+                if (rest)
+                    MB_CUDA(cudaMemcpyAsync(s->d_buf[s->cur ^ 1], buf + consumed, rest * sizeof(float),
+                                            cudaMemcpyDeviceToDevice, p->stream));
+            }
+            return MB_OK;
+        };
+        StreamGraph *slot_g = nullptr;
+        if (nf > 0 && p->stream == p->own_stream) {
+            for (auto &g : s->graphs)
+                if (g.cur == s->cur && g.filled == filled_before && g.n_new == n_new) slot_g = &g;
+            if (!slot_g) {  // take the least used entry for this new shape
+                slot_g = &s->graphs[0];
+                for (auto &g : s->graphs)
+                    if (g.cur < 0 || g.seen < slot_g->seen) { slot_g = &g; if (g.cur < 0) break; }
+                if (slot_g->exec) cudaGraphExecDestroy(slot_g->exec);
+                *slot_g = StreamGraph();
+                slot_g->cur = s->cur;
+                slot_g->filled = filled_before;
+                slot_g->n_new = n_new;
+            }
+            slot_g->seen++;
+        }
+        if (slot_g && slot_g->exec) {
+            MB_CUDA(cudaGraphLaunch(slot_g->exec, p->stream));
+            p->launches++;
+            p->launches_warp += p->has_warp_kernel ? 1 : 0;
+            s->graph_launches++;
+        } else if (slot_g && slot_g->seen >= 2) {
+            cudaGraph_t graph = nullptr;
+            MB_CUDA(cudaStreamBeginCapture(p->stream, cudaStreamCaptureModeThreadLocal));
+            mb_status st = enqueue();
+            cudaError_t ce = cudaStreamEndCapture(p->stream, &graph);
+            if (st != MB_OK) {
+                if (graph) cudaGraphDestroy(graph);
+                return st;
+            }
+            if (ce != cudaSuccess) return fail(MB_ERR_CUDA, "stream capture: %s", cudaGetErrorString(ce));
+            ce = cudaGraphInstantiate(&slot_g->exec, graph, 0);
+            cudaGraphDestroy(graph);
+            if (ce != cudaSuccess) {
+                slot_g->exec = nullptr;
+                return fail(MB_ERR_CUDA, "graph instantiate: %s", cudaGetErrorString(ce));
+            }
+            MB_CUDA(cudaGraphLaunch(slot_g->exec, p->stream));
+            s->graph_launches++;
+        } else {
+            mb_status st = enqueue();
+            if (st != MB_OK) return st;
+        }
+        MB_CUDA(cudaStreamSynchronize(p->stream));
+        cursor = 0;
+        for (int i = 0; i < kNumFields && nf > 0; i++) {
             if (!mb_has(p->mask, kFields[i].feature)) continue;
             const size_t bytes = (size_t)nf * field_elems(kFields[i], p->N) * 4;
-            MB_CUDA(cudaMemcpyAsync(field_ptr(*out, kFields[i]), field_ptr(d_out, kFields[i]), bytes,
-                                    cudaMemcpyDeviceToHost, p->stream));
+            memcpy(field_ptr(*out, kFields[i]), s->h_out + cursor, bytes);
+            cursor += bytes;
         }
     }
-    // keep the hop-overlap tail for the next push
-    const int64_t consumed = nf * p->hop;
-    const int64_t rest = std::max<int64_t>(0, s->filled - consumed);
-    s->skip = std::max<int64_t>(0, consumed - s->filled);
-    if (rest)
-        MB_CUDA(cudaMemcpyAsync(s->d_buf[s->cur ^ 1], buf + consumed, rest * sizeof(float), cudaMemcpyDeviceToDevice,
-                                p->stream));
-    s->cur ^= 1;
-    s->filled = rest;
-    MB_CUDA(cudaStreamSynchronize(p->stream));
+    if (nf > 0) {
+        s->skip = std::max<int64_t>(0, consumed - need);
+        s->cur ^= 1;
+        s->filled = rest;
+    } else {
+        s->filled = need;
+    }
     if (frames_done) *frames_done = nf;
     return MB_OK;
 }

@@ -538,6 +538,19 @@ class Stream:
     def reset(self):
         _capi.check(self._L.mb_stream_reset(self._h))
 
+    @property
+    def graph_launches(self) -> int:
+        """Pushes replayed as a CUDA graph so far (a repeating push shape is captured on its second occurrence)."""
+        return int(self._L.mb_stream_graph_launches(self._h))
+
+    def push_into(self, samples: np.ndarray, out: dict) -> int:
+        """push() into caller-owned arrays (from Plan.alloc_host_outputs); returns the frames completed."""
+        o = Plan.pack_outputs({k: v.ctypes.data for k, v in out.items()})
+        done = C.c_int64(0)
+        _capi.check(self._L.mb_stream_push(self._h, samples.ctypes.data, samples.size, C.byref(o), _capi.MB_MEM_HOST,
+                                           C.byref(done)))
+        return int(done.value)
+
     def push(self, samples) -> ExtractResult:
         x = np.ascontiguousarray(samples, dtype=np.float32).reshape(-1)
         nf = int(self._L.mb_stream_frames_after(self._h, x.size))

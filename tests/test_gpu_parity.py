@@ -233,6 +233,27 @@ def test_streaming_matches_batch():
             assert np.array_equal(cat[k], batch[k], equal_nan=True), (N, hop, k)
 
 
+def test_streaming_fixed_buffers_replay_a_cuda_graph():
+    """One buffer per push (the onaudioprocess cadence): the push shape repeats, so it is captured once and
+    replayed as a CUDA graph; results stay bit-identical to the batch call, also across a reset."""
+    x = mo.synth_clip(78, 40000)
+    for N, hop, block in ((2048, 512, 512), (512, 512, 512), (1024, 256, 768)):
+        batch, per = run_gpu(x, N, hop)
+        plan = mb.Plan(N, hop, SR)
+        st = mb.Stream(plan)
+        for _round in range(2):
+            got = [st.push(x[pos:pos + block]).arrays for pos in range(0, len(x), block)]
+            cat = {k: np.concatenate([g[k] for g in got]) for k in batch}
+            assert len(cat["rms"]) == per[0]
+            for k in batch:
+                assert np.array_equal(cat[k], batch[k], equal_nan=True), (N, hop, k, _round)
+            st.reset()
+            st.push(x[:0])
+        assert st.graph_launches > 0.8 * 2 * (len(x) // block - N // block - 4), st.graph_launches
+        st.close()
+        plan.close()
+
+
 def test_meyda_class_get_and_callback(golden_audio):
     """The reference's usage: construct, start(features), per-buffer callback
     with the get([...]) object; get('name') returns the bare value."""

@@ -1,6 +1,6 @@
 """Device-resident throughput of the other BASELINE configs and modes (not the
 driver's bench): config 3 (mfcc + moments, N=2048), config 5 (N=32768 spectrum +
-rolloff/flatness/slope), exact-FFT mode, other buffer sizes."""
+rolloff/flatness/slope), exact-FFT mode, other buffer sizes, 16-bit PCM input."""
 import json, os, sys, time
 import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -13,11 +13,13 @@ dev = torch.device("cuda", 0)
 PER = {"buffer": lambda N: N, "complexSpectrum": lambda N: 2 * N, "amplitudeSpectrum": lambda N: N // 2,
        "powerSpectrum": lambda N: N // 2, "loudness": lambda N: 25, "mfcc": lambda N: 13}
 
-def run(name, N, hop, n_clips, clip_len, feats, flags=0, steps=3):
+def run(name, N, hop, n_clips, clip_len, feats, flags=0, steps=3, pcm16=False):
     g = torch.Generator(device=dev).manual_seed(7)
     x = (torch.rand(n_clips, clip_len, device=dev, generator=g) - 0.5) * 0.5
     t = torch.arange(clip_len, device=dev, dtype=torch.float32) / SR
     x += 0.3 * torch.sin(2 * np.pi * 440.0 * t)[None, :]
+    if pcm16:  # the same clips as 16-bit PCM (what a WAV file holds): half the input bytes
+        x = (x * 32767.0).round().to(torch.int16)
     plan = mb.Plan(N, hop, SR, "hanning", feats, flags=flags)
     fpc = (clip_len - N) // hop + 1
     nf = fpc * n_clips
@@ -26,14 +28,17 @@ def run(name, N, hop, n_clips, clip_len, feats, flags=0, steps=3):
     st = torch.cuda.Stream(device=dev); torch.cuda.set_stream(st); plan.set_stream(st.cuda_stream)
     off = np.arange(n_clips, dtype=np.int64) * clip_len; ln = np.full(n_clips, clip_len, np.int64)
     ptrs = {k: v.data_ptr() for k, v in outs.items()}
-    for _ in range(3): plan.extract_device(x.data_ptr(), x.numel(), off, ln, ptrs, sync=False)
+    def call():
+        if pcm16: plan.extract_pcm16_device(x.data_ptr(), x.numel(), 1, 0, off, ln, ptrs, sync=False)
+        else: plan.extract_device(x.data_ptr(), x.numel(), off, ln, ptrs, sync=False)
+    for _ in range(3): call()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(st)
-    for _ in range(steps): plan.extract_device(x.data_ptr(), x.numel(), off, ln, ptrs, sync=False)
+    for _ in range(steps): call()
     e1.record(st); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps
-    bpf = 4 * hop + 4 * sum(PER.get(f, lambda N: 1)(N) for f in feats)
+    bpf = (2 if pcm16 else 4) * hop + 4 * sum(PER.get(f, lambda N: 1)(N) for f in feats)
     fps = nf / (ms * 1e-3)
     print(json.dumps({"config": name, "kernel": plan.kernel_name, "N": N, "hop": hop, "frames": nf, "ms": round(ms, 3),
                       "frames_per_s": round(fps), "alg_bytes_per_frame": bpf, "alg_GBps": round(fps * bpf / 1e9, 1),
@@ -42,7 +47,11 @@ def run(name, N, hop, n_clips, clip_len, feats, flags=0, steps=3):
 
 C3 = ["mfcc", "spectralCentroid", "spectralSpread", "spectralSkewness", "spectralKurtosis"]
 C5 = ["amplitudeSpectrum", "spectralRolloff", "spectralFlatness", "spectralSlope"]
-which = sys.argv[1:] or ["c3", "c5", "exact", "sizes"]
+which = sys.argv[1:] or ["c3", "c5", "exact", "sizes", "pcm"]
+if "pcm" in which:
+    run("full set, float32 input", 2048, 512, 1500, 441000, mb.FEATURES)
+    run("full set, 16-bit PCM input", 2048, 512, 1500, 441000, mb.FEATURES, pcm16=True)
+    run("config3, 16-bit PCM input", 2048, 512, 4000, 441000, C3, pcm16=True)
 if "c3" in which:
     run("config3 mfcc+moments", 2048, 512, 4000, 441000, C3)
     run("config3 generic", 2048, 512, 1000, 441000, C3, flags=_capi.MB_FLAG_GENERIC_KERNEL)
