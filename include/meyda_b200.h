@@ -98,8 +98,9 @@ enum {
 #define MB_NUM_MEL_FILTERS 26 /* src/extractors/mfcc.js:15 */
 #define MB_NUM_MFCC 13        /* src/extractors/mfcc.js:71 */
 
-/* `windowingFunction`, src/meyda.js:41, docs.md:5-11 */
-enum { MB_WINDOW_HANNING = 0, MB_WINDOW_HAMMING = 1 };
+/* `windowingFunction`, src/meyda.js:41, docs.md:5-11.  Blackman is the window the reference leaves commented
+ * out as unfinished (src/meyda.js:140-156); its stated formula, 0.42 - 0.5 cos(2 pi i/(N-1)) + 0.08 cos(4 pi i/(N-1)). */
+enum { MB_WINDOW_HANNING = 0, MB_WINDOW_HAMMING = 1, MB_WINDOW_BLACKMAN = 2 };
 
 /* Where the caller's sample and output pointers live. */
 enum { MB_MEM_HOST = 0, MB_MEM_DEVICE = 1 };

@@ -74,7 +74,7 @@ function extract (clips, opts, callback) {
   const featureMask = features.reduce((m, f) => m | (1 << FEATURES.indexOf(f)), 0)
   const plan = native.createPlan({
     bufferSize: N, hop: opts.hop || N, sampleRate: opts.sampleRate || 44100, featureMask,
-    window: (opts.windowingFunction || 'hanning') === 'hamming' ? 1 : 0, device: opts.device || 0
+    window: {hanning: 0, hamming: 1, blackman: 2}[opts.windowingFunction || 'hanning'] || 0, device: opts.device || 0
   })
   const out = native.extract(plan, samples, offsets, lengths)
   native.destroyPlan(plan)

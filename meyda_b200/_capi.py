@@ -14,7 +14,7 @@ MB_OK = 0
 MB_ERR_INVALID_ARG, MB_ERR_NOT_POWER_OF_TWO, MB_ERR_UNSUPPORTED, MB_ERR_CUDA = 1, 2, 3, 4
 MB_ERR_NO_DEVICE, MB_ERR_MISSING_OUTPUT, MB_ERR_OUT_OF_RANGE = 5, 6, 7
 MB_MEM_HOST, MB_MEM_DEVICE = 0, 1
-MB_WINDOW = {"hanning": 0, "hamming": 1}
+MB_WINDOW = {"hanning": 0, "hamming": 1, "blackman": 2}
 MB_FLAG_GENERIC_KERNEL = 1
 MB_FLAG_EXACT_FFT = 2
 MB_FLAG_CLUSTER_FFT = 4

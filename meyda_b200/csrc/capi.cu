@@ -173,7 +173,9 @@ struct DeviceGuard {
 void build_window(std::vector<float> &w, int N, int which) {
     w.resize(N);
     for (int i = 0; i < N; i++) {
-        if (which == MB_WINDOW_HAMMING)  // src/meyda.js:116-126
+        if (which == MB_WINDOW_BLACKMAN)  // src/meyda.js:140-156 (commented out there: the formula it states)
+            w[i] = (float)(0.42 - 0.5 * cos(2 * M_PI * i / (N - 1)) + 0.08 * cos(4 * M_PI * i / (N - 1)));
+        else if (which == MB_WINDOW_HAMMING)  // src/meyda.js:116-126
             w[i] = (float)(0.54 - 0.46 * cos(2 * M_PI * ((double)i / N - 1)));
         else  // src/meyda.js:128-138
             w[i] = (float)(0.5 - 0.5 * cos(2 * M_PI * i / (N - 1)));
@@ -424,7 +426,7 @@ mb_status mb_plan_create(mb_plan **plan, int device, int buffer_size, int hop, d
         return fail(MB_ERR_INVALID_ARG, "unknown plan flags 0x%x", flags);
     if (hop <= 0) return fail(MB_ERR_INVALID_ARG, "hop must be positive (got %d)", hop);
     if (!(sample_rate > 0)) return fail(MB_ERR_INVALID_ARG, "sampleRate must be positive");
-    if (window != MB_WINDOW_HANNING && window != MB_WINDOW_HAMMING)
+    if (window != MB_WINDOW_HANNING && window != MB_WINDOW_HAMMING && window != MB_WINDOW_BLACKMAN)
         return fail(MB_ERR_INVALID_ARG, "unknown windowingFunction %d", window);
     if (feature_mask == 0 || (feature_mask & ~MB_ALL_FEATURES))
         return fail(MB_ERR_INVALID_ARG, "feature mask 0x%x is empty or has unknown bits", feature_mask);

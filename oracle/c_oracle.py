@@ -70,7 +70,7 @@ def extract(signal, bufferSize: int, hop=None, sr: float = 44100.0, window: str 
     hop = bufferSize if hop is None else hop
     sig = np.ascontiguousarray(signal, dtype=np.float32)
     clip_len = len(sig) // n_clips
-    plan = L.mo_plan_create(bufferSize, float(sr), {"hanning": 0, "hamming": 1}[window])
+    plan = L.mo_plan_create(bufferSize, float(sr), {"hanning": 0, "hamming": 1, "blackman": 2}[window])
     if not plan:
         raise ValueError("Buffer size is not a power of two: Meyda will not run.")
     try:

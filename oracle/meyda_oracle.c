@@ -39,7 +39,7 @@
 #define MO_NUM_MEL 26
 #define MO_NUM_MFCC 13
 
-enum { MO_WIN_HANNING = 0, MO_WIN_HAMMING = 1 };
+enum { MO_WIN_HANNING = 0, MO_WIN_HAMMING = 1, MO_WIN_BLACKMAN = 2 };
 
 typedef struct mo_plan {
     int N;            /* bufferSize */
@@ -48,6 +48,7 @@ typedef struct mo_plan {
     int window;
     float *hanning;   /* Float32Array(N) */
     float *hamming;   /* Float32Array(N) */
+    float *blackman;  /* Float32Array(N) */
     float *bark;      /* Float32Array(N) */
     int32_t bbLimits[MO_NUM_BARK + 1];
 } mo_plan;
@@ -85,6 +86,14 @@ static void compute_hamming(float *w, int N) {
         w[i] = (float)(0.54 - 0.46 * cos(2 * M_PI * ((double)i / N - 1)));
 }
 
+/* src/meyda.js:140-156: the reference leaves this window commented out ("UNFINISHED"); what it states is the
+ * formula (the symmetric window of the MathWorks page it cites), evaluated here for every i.  No reference
+ * output exists for it -- this table is pinned by its closed form only. */
+static void compute_blackman(float *w, int N) {
+    for (int i = 0; i < N; i++)
+        w[i] = (float)(0.42 - 0.5 * cos(2 * M_PI * i / (N - 1)) + 0.08 * cos(4 * M_PI * i / (N - 1)));
+}
+
 /* src/meyda.js:170-182 -- the Hz value is stored to the Float32Array first,
  * then read back for the bark formula. */
 static void compute_bark_scale(float *b, int N, double sr) {
@@ -117,9 +126,11 @@ mo_plan *mo_plan_create(int N, double sr, int window) {
     p->N = N; p->n = N / 2; p->sr = sr; p->window = window;
     p->hanning = (float *)malloc(sizeof(float) * N);
     p->hamming = (float *)malloc(sizeof(float) * N);
+    p->blackman = (float *)malloc(sizeof(float) * N);
     p->bark = (float *)malloc(sizeof(float) * N);
     compute_hanning(p->hanning, N);
     compute_hamming(p->hamming, N);
+    compute_blackman(p->blackman, N);
     compute_bark_scale(p->bark, N, sr);
     compute_bark_band_limits(p->bbLimits, p->bark, p->n, MO_NUM_BARK);
     return p;
@@ -127,10 +138,12 @@ mo_plan *mo_plan_create(int N, double sr, int window) {
 
 void mo_plan_destroy(mo_plan *p) {
     if (!p) return;
-    free(p->hanning); free(p->hamming); free(p->bark); free(p);
+    free(p->hanning); free(p->hamming); free(p->blackman); free(p->bark); free(p);
 }
 
-const float *mo_plan_window(const mo_plan *p, int which) { return which ? p->hamming : p->hanning; }
+const float *mo_plan_window(const mo_plan *p, int which) {
+    return which == MO_WIN_BLACKMAN ? p->blackman : which == MO_WIN_HAMMING ? p->hamming : p->hanning;
+}
 const float *mo_plan_bark(const mo_plan *p) { return p->bark; }
 const int32_t *mo_plan_bb_limits(const mo_plan *p) { return p->bbLimits; }
 
@@ -265,7 +278,7 @@ void mo_frame(const mo_plan *p, const float *signal, mo_frame_out *o, void *work
     const double sr = p->sr;
     float *re = (float *)work, *im = re + N;
     double *fb_scratch = (double *)(im + N);
-    const float *win = p->window == MO_WIN_HAMMING ? p->hamming : p->hanning;
+    const float *win = mo_plan_window(p, p->window);
 
     /* computeWindow src/meyda.js:158-168; ComplexArray.map lib/jsfft/complex_array.js:54-70 */
     for (int i = 0; i < N; i++) { re[i] = (float)((double)signal[i] * (double)win[i]); im[i] = 0.0f; }

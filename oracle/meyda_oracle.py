@@ -93,11 +93,19 @@ def hamming(N: int) -> np.ndarray:
     return (0.54 - 0.46 * np.cos(2 * np.pi * (i / N - 1))).astype(f32)
 
 
+def blackman(N: int) -> np.ndarray:
+    """src/meyda.js:140-156: commented out in the reference ("UNFINISHED"); the formula it states, for every i."""
+    i = np.arange(N, dtype=f64)
+    return (0.42 - 0.5 * np.cos(2 * np.pi * i / (N - 1)) + 0.08 * np.cos(4 * np.pi * i / (N - 1))).astype(f32)
+
+
 def window_table(N: int, name: str) -> np.ndarray:
     if name == "hanning":
         return hanning(N)
     if name == "hamming":
         return hamming(N)
+    if name == "blackman":
+        return blackman(N)
     raise ValueError("unknown windowingFunction %r" % (name,))
 
 

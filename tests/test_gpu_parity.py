@@ -108,6 +108,17 @@ def test_hamming_window(golden_audio, flags):
     verify(out, x, 1024, 512, window="hamming", flags=flags)
 
 
+@pytest.mark.parametrize("N,hop,flags", [(2048, 512, 0), (512, 512, 0), (1024, 256, EXACT)])
+def test_blackman_window(golden_audio, N, hop, flags):
+    """src/meyda.js:140-156 (commented out in the reference)."""
+    x = golden_audio["sound1"][:50000]
+    out, _ = run_gpu(x, N, hop, window="blackman", flags=flags)
+    verify(out, x, N, hop, window="blackman", flags=flags)
+    plan = mb.Plan(N, hop, SR, "blackman")
+    assert np.array_equal(plan.tables()["window"], mo.blackman(N))
+    plan.close()
+
+
 @pytest.mark.parametrize("flags", FLAG_VARIANTS)
 def test_ragged_and_empty_clips(flags):
     N, hop = 512, 128

@@ -110,6 +110,20 @@ def test_hamming_path_agrees(golden_audio):
         assert _same(a[k], b[k], rtol=1e-7), k
 
 
+def test_blackman_window_closed_form_and_path(golden_audio):
+    """The window the reference leaves commented out (src/meyda.js:140-156): its stated formula.  Symmetric,
+    zero-ish at the ends, 1 in the middle of an odd length; both oracles agree on the whole path."""
+    for N in (16, 512, 2048):
+        w = mo.blackman(N).astype(np.float64)
+        assert np.allclose(w, w[::-1], atol=1e-7) and abs(w[0]) < 1e-7 and w.max() <= 1.0
+        assert np.allclose(w, np.blackman(N), atol=2e-7)  # numpy's is the same symmetric window
+    x = golden_audio["sound1"][:8192]
+    a = mo.extract(x, 512, 256, SR, window="blackman")
+    b = c_oracle.extract(x, 512, 256, SR, window="blackman")
+    for k in a:
+        assert _same(a[k], b[k], rtol=1e-7), k
+
+
 def test_golden_fixture_matches_oracle(golden_audio, golden_features):
     """Guards the oracle against drift; also exercises the numpy path on full clips."""
     names = [str(s) for s in golden_features["scalar_names"]]
