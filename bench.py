@@ -326,11 +326,16 @@ def main():
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
         try:
-            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            tj = json.load(open(tp))
+            # measured by ncu on a full 302-clip launch of this kernel with the full feature set; DRAM traffic is
+            # proportional to the frames of a launch, so it is restated for this run's (average) launch size
+            if tj.get("kernel") == plan.kernel_name and feats == mb.FEATURES:
+                traffic = tj["dram_bytes_per_launch"] * frames_per_launch / tj["frames_per_launch"]
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "peak_source": peak_src, "kernel": plan.kernel_name,
+                "traffic": traffic, "traffic_source": "ncu --set full capture (profiles/traffic.json), scaled to this run's frames per launch",
+                "peak_source": peak_src, "kernel": plan.kernel_name,
                 "algorithmic_bytes_per_frame": alg_bpf, "frames_per_launch": frames_per_launch,
                 "avg_launch_ms": avg_launch_s * 1e3}
 
