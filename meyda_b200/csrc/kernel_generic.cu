@@ -18,6 +18,7 @@
 // lib/jsfft/fft.js:123-208, the extractor files under src/extractors/ (see
 // mb_device.cuh for the per-formula citations).
 #include <cooperative_groups.h>
+#include <stdlib.h>
 
 #include "mb_device.cuh"
 #include "mb_fft.cuh"
@@ -25,8 +26,23 @@
 
 namespace cg = cooperative_groups;
 
-// The kernels are compiled for two CTA sizes: 256 threads (several CTAs per SM at small bufferSize) and
-// 1024 threads (one CTA per SM once a frame needs most of the shared memory, bufferSize >= 8192).
+// The kernels are compiled for every CTA size from one warp to 1024 threads; mb_launch_generic picks by
+// bufferSize (32 threads up to 512 ... 1024 threads at 32768, where a frame needs most of an SM's shared memory).
+namespace g32 {
+#define MB_GENERIC_THREADS 32
+#include "kernel_generic_impl.cuh"
+#undef MB_GENERIC_THREADS
+}  // namespace g32
+namespace g64 {
+#define MB_GENERIC_THREADS 64
+#include "kernel_generic_impl.cuh"
+#undef MB_GENERIC_THREADS
+}  // namespace g64
+namespace g128 {
+#define MB_GENERIC_THREADS 128
+#include "kernel_generic_impl.cuh"
+#undef MB_GENERIC_THREADS
+}  // namespace g128
 namespace g256 {
 #define MB_GENERIC_THREADS 256
 #include "kernel_generic_impl.cuh"
@@ -68,6 +84,10 @@ size_t mb_generic_smem_bytes(int M, bool exact) {
         NS::mb_generic_kernel<EXACT><<<(unsigned)grid, THREADS, smem, stream>>>(P, T, samples, O);                   \
         return cudaGetLastError();                                                                                   \
     }
+MB_DEFINE_LAUNCH_GENERIC(g32, 32)
+MB_DEFINE_LAUNCH_GENERIC(g64, 64)
+MB_DEFINE_LAUNCH_GENERIC(g512, 512)
+MB_DEFINE_LAUNCH_GENERIC(g128, 128)
 MB_DEFINE_LAUNCH_GENERIC(g256, 256)
 MB_DEFINE_LAUNCH_GENERIC(g1024, 1024)
 
@@ -109,9 +129,29 @@ cudaError_t mb_launch_exact_cluster(const MbDevPlan &P, const MbClipTable &T, co
 
 cudaError_t mb_launch_generic(const MbDevPlan &P, const MbClipTable &T, const float *samples, const mb_outputs &O,
                               int num_sms, cudaStream_t stream) {
-    if (P.N >= 8192)
-        return P.exact ? launch_generic_g1024<true>(P, T, samples, O, num_sms, stream)
-                       : launch_generic_g1024<false>(P, T, samples, O, num_sms, stream);
-    return P.exact ? launch_generic_g256<true>(P, T, samples, O, num_sms, stream)
-                   : launch_generic_g256<false>(P, T, samples, O, num_sms, stream);
+    if (const char *env = getenv("MB_GENERIC_CTA")) {  // tuning experiments only: force a CTA size
+        const int t = atoi(env);
+#define MB_FORCE(NS, T_)                                                                        \
+    if (t == T_)                                                                                \
+        return P.exact ? launch_generic_##NS<true>(P, T, samples, O, num_sms, stream)           \
+                       : launch_generic_##NS<false>(P, T, samples, O, num_sms, stream);
+        MB_FORCE(g32, 32) MB_FORCE(g64, 64) MB_FORCE(g128, 128) MB_FORCE(g256, 256) MB_FORCE(g512, 512) MB_FORCE(g1024, 1024)
+#undef MB_FORCE
+    }
+    // CTA size by bufferSize, from a sweep on the B200 (tools/sweep_generic_cta.py): one warp per frame up to 512
+    // (no block-wide barriers left, every reduction is a shuffle), then just enough threads to keep the N/2
+    // complex points busy; large frames are shared-memory bound and want few, big CTAs.
+#define MB_GO(NS)                                                                           \
+    return P.exact ? launch_generic_##NS<true>(P, T, samples, O, num_sms, stream)           \
+                   : launch_generic_##NS<false>(P, T, samples, O, num_sms, stream)
+    // (a launch with fewer frames than SMs is a latency case -- the streaming path, one buffer per push --
+    // and is better served by many threads on the one frame than by many frames in flight)
+    if (T.total_frames <= num_sms && P.N >= 128 && P.N < 8192) MB_GO(g256);
+    if (P.N <= 512) MB_GO(g32);
+    if (P.N == 1024) MB_GO(g64);
+    if (P.N <= 4096) MB_GO(g128);
+    if (P.N == 8192) MB_GO(g256);
+    if (P.N == 16384) MB_GO(g512);
+    MB_GO(g1024);
+#undef MB_GO
 }

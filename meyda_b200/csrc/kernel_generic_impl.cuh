@@ -3,6 +3,7 @@
 
 constexpr int kThreads = MB_GENERIC_THREADS;
 constexpr int kWarps = kThreads / 32;
+constexpr int kScalarThread = kThreads > 64 ? 64 : 0;  // the lane that turns the frame's sums into the number features
 
 // One padding element every 32 and every 1024 entries keeps both the unit-stride
 // butterfly accesses and the bit-reversed gather of the split pass off a
@@ -301,8 +302,9 @@ __device__ __forceinline__ void frame_epilogue(const MbDevPlan &P, const mb_outp
                 O.perceptual_sharpness[g] = (float)(sharp * (0.11 / total));
         }
     }
-    if (mb_has(mask, MB_FEAT_MFCC) && tid >= 32 && tid < 32 + MB_NUM_MFCC) {
-        const int c = tid - 32;
+    constexpr int kDctThread0 = kThreads > 32 ? 32 : 0;  // (a second warp where there is one)
+    if (mb_has(mask, MB_FEAT_MFCC) && tid >= kDctThread0 && tid < kDctThread0 + MB_NUM_MFCC) {
+        const int c = tid - kDctThread0;
         double v = 0;
         for (int f = 0; f < MB_NUM_MEL_FILTERS; f++)
             v += (double)__ldg(P.dct + c + f * MB_NUM_MFCC) * (double)mel_log[f];
@@ -479,12 +481,13 @@ mb_generic_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ M
             }
             frame_epilogue<EXACT>(P, O, g, S, acc, amp, sc);
         }
-        if (tid == 64) mb_store_scalars(P, O, g, S);
+        if (tid == kScalarThread) mb_store_scalars(P, O, g, S);
         __syncthreads();  // smem reused by the next frame
     }
 }
 
 
+#if MB_GENERIC_THREADS == 256 || MB_GENERIC_THREADS == 1024  // the two CTA sizes the cluster kernel is launched with
 // ---- exact-FFT mode for a frame that does not fit one CTA ---------------------------------------
 // At bufferSize 32768 the reference's N-point complex transform needs 256 KB as float32 re/im -- more
 // than one CTA's shared memory.  A 2-CTA thread-block cluster holds it: CTA r keeps positions
@@ -585,10 +588,12 @@ mb_exact_cluster_kernel(const __grid_constant__ MbDevPlan P, const __grid_consta
                 frame_epilogue<true>(P, O, g, S, acc, amp, sc);
             }
         }
-        if (rank == 0 && tid == 64) mb_store_scalars(P, O, g, S);
+        if (rank == 0 && tid == kScalarThread) mb_store_scalars(P, O, g, S);
         cluster.sync();  // CTA 0 is done with the gathered amplitudes before the next frame overwrites them
     }
 }
+
+#endif
 
 #if MB_GENERIC_THREADS == 512
 // ---- bufferSize 32768, float32 FFT: one CTA (16 warps) per frame ---------------------------------
@@ -787,7 +792,7 @@ mb_big32768_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
             }
             frame_epilogue<false>(P, O, g, S, acc, B.amp, sc);
         }
-        if (tid == 64) mb_store_scalars(P, O, g, S);
+        if (tid == kScalarThread) mb_store_scalars(P, O, g, S);
         __syncthreads();  // smem reused by the next frame
     }
 }

@@ -60,6 +60,11 @@ if "c5" in which:
 if "exact" in which:
     run("full set exact-FFT", 2048, 512, 200, 441000, mb.FEATURES, flags=_capi.MB_FLAG_EXACT_FFT)
     run("config3 exact-FFT", 2048, 512, 200, 441000, C3, flags=_capi.MB_FLAG_EXACT_FFT)
+if "small" in which:  # the reference's own cadence: back-to-back buffers (hop = bufferSize)
+    for N in (256, 512, 1024):
+        run("full set N=%d hop=N" % N, N, N, 800, 441000, mb.FEATURES)
+    run("config-1 features N=512 hop=N", 512, 512, 2000, 441000, ["rms", "energy", "zcr", "amplitudeSpectrum", "spectralCentroid"])
+    run("full set exact-FFT N=512 hop=N", 512, 512, 200, 441000, mb.FEATURES, flags=_capi.MB_FLAG_EXACT_FFT)
 if "sizes" in which:
     for N in (256, 512, 1024, 4096):
         run("full set N=%d hop=N/4" % N, N, N // 4, 400, 441000, mb.FEATURES)
