@@ -3,6 +3,11 @@
 
 constexpr int kThreads = MB_GENERIC_THREADS;
 constexpr int kWarps = kThreads / 32;
+// One-warp CTAs (bufferSize <= 512) need no block barrier: warp-level ordering is enough.
+__device__ __forceinline__ void block_sync() {
+    if constexpr (kWarps == 1) __syncwarp();
+    else __syncthreads();
+}
 constexpr int kScalarThread = kThreads > 64 ? 64 : 0;  // the lane that turns the frame's sums into the number features
 
 // One padding element every 32 and every 1024 entries keeps both the unit-stride
@@ -74,7 +79,7 @@ __device__ __forceinline__ void exact_stages(float *xre, float *xim, const doubl
         else if (q == 2) exact_pass<2>(xre, xim, tw_exact, n, log2w);
         else exact_pass<1>(xre, xim, tw_exact, n, log2w);
         log2w += q;
-        __syncthreads();
+        block_sync();
     }
 }
 
@@ -113,18 +118,20 @@ __device__ __forceinline__ void fft_pass(float2 *work, const float2 *__restrict_
 // (kWarps <= 32), so all threads get the total.
 __device__ __forceinline__ double block_sum(double v, double *scratch /*[kWarps]*/) {
     v = mb_warp_sum(v);
-    __syncthreads();
+    if constexpr (kWarps == 1) return v;
+    block_sync();
     if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
-    __syncthreads();
+    block_sync();
     const int lane = threadIdx.x & 31;
     return mb_warp_sum(lane < kWarps ? scratch[lane] : 0.0);
 }
 
 __device__ __forceinline__ int block_sum_int(int v, int *scratch /*[kWarps]*/) {
     v = mb_warp_sum(v);
-    __syncthreads();
+    if constexpr (kWarps == 1) return v;
+    block_sync();
     if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
-    __syncthreads();
+    block_sync();
     const int lane = threadIdx.x & 31;
     return mb_warp_sum(lane < kWarps ? scratch[lane] : 0);
 }
@@ -192,7 +199,7 @@ __device__ __forceinline__ void frame_epilogue(const MbDevPlan &P, const mb_outp
         S.s4 = block_sum(acc.s4, red_d);
         if (want_log) S.log2sum = block_sum(acc.lg, red_d);
     }
-    __syncthreads();
+    block_sync();
 
     // ---- rolloff: prefix sums of the amplitude spectrum in double
     if (mb_has(mask, MB_FEAT_SPECTRAL_ROLLOFF)) {
@@ -204,7 +211,7 @@ __device__ __forceinline__ void frame_epilogue(const MbDevPlan &P, const mb_outp
         for (int k = k_lo + lane; k < k_hi; k += 32) part += (double)amp[k];
         part = mb_warp_sum(part);
         if (lane == 0) scan_d[warp] = part;
-        __syncthreads();
+        block_sync();
         const double mine = lane < kWarps ? scan_d[lane] : 0.0;
         const double total = mb_warp_sum(mine);
         double run = mb_warp_sum(lane < warp ? mine : 0.0);  // sum of amp[0 .. k_lo)
@@ -275,7 +282,7 @@ __device__ __forceinline__ void frame_epilogue(const MbDevPlan &P, const mb_outp
             }
         }
     }
-    __syncthreads();
+    block_sync();
 
     if (want_bark) {
         if (tid < MB_NUM_BARK_BANDS) {
@@ -283,7 +290,7 @@ __device__ __forceinline__ void frame_epilogue(const MbDevPlan &P, const mb_outp
             specific[tid] = sp;
             if (mb_has(mask, MB_FEAT_LOUDNESS)) O.loudness_specific[g * MB_NUM_BARK_BANDS + tid] = sp;
         }
-        __syncthreads();
+        block_sync();
         if (tid == 0) {
             double total = 0, mx = 0, sharp = 0;
             for (int i = 0; i < MB_NUM_BARK_BANDS; i++) {
@@ -396,9 +403,9 @@ mb_generic_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ M
                 // rescaled by an exact power of two and scaled back on the way out
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) mxabs = fmaxf(mxabs, __shfl_xor_sync(0xffffffffu, mxabs, o));
-                __syncthreads();
+                block_sync();
                 if (lane == 0) red_f[warp] = mxabs;
-                __syncthreads();
+                block_sync();
                 float mx = 0.f;
 #pragma unroll
                 for (int w = 0; w < kWarps; w++) mx = fmaxf(mx, red_f[w]);
@@ -415,7 +422,7 @@ mb_generic_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ M
             }
         }
         const float unscale = ldexpf(1.f, -kscale);
-        __syncthreads();
+        block_sync();
 
         if (want_spectrum) {
             MomentAcc acc;
@@ -445,7 +452,7 @@ mb_generic_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ M
                     else if (q == 2) fft_pass<2>(work, P.twM, M, log2M, log2s);
                     else fft_pass<1>(work, P.twM, M, log2M, log2s);
                     log2s -= q;
-                    __syncthreads();
+                    block_sync();
                 }
                 // ---- real-FFT split, spectra out, amplitude into smem, moment partials
                 const float sc = P.inv_sqrt_N;
@@ -482,7 +489,7 @@ mb_generic_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ M
             frame_epilogue<EXACT>(P, O, g, S, acc, amp, sc);
         }
         if (tid == kScalarThread) mb_store_scalars(P, O, g, S);
-        __syncthreads();  // smem reused by the next frame
+        block_sync();  // smem reused by the next frame
     }
 }
 
@@ -554,7 +561,7 @@ mb_exact_cluster_kernel(const __grid_constant__ MbDevPlan P, const __grid_consta
                 xre[xidx(pl)] = __fmul_rn(src[i], __ldg(P.window + i));
                 xim[xidx(pl)] = 0.f;
             }
-            __syncthreads();
+            block_sync();
             exact_stages(xre, xim, P.tw_exact, H, 0, log2N - 1);  // widths 1 .. N/4: inside the half
             cluster.sync();  // both halves are complete and visible cluster-wide
             {                // width N/2: element j of CTA 0 with element j of CTA 1, through DSMEM
@@ -647,7 +654,7 @@ mb_big32768_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
         const double ang = 2.0 * 3.14159265358979323846 * (double)(warp * lane) / (double)M;
         tw_own = make_float2((float)cos(ang), (float)sin(ang));
     }
-    __syncthreads();
+    block_sync();
     float2 *slot = B.area + warp * kBigSlot;  // this warp's transpose slot / sub-spectrum row
 
     for (int64_t g = blockIdx.x; g < T.total_frames; g += gridDim.x) {
@@ -690,9 +697,9 @@ mb_big32768_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
             if (want_spectrum) {  // frames outside the float32 comfort zone: exact power-of-two rescale (see generic kernel)
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) mxabs = fmaxf(mxabs, __shfl_xor_sync(0xffffffffu, mxabs, o));
-                __syncthreads();
+                block_sync();
                 if (lane == 0) sc.red_f[warp] = mxabs;
-                __syncthreads();
+                block_sync();
                 float mx = lane < kWarps ? sc.red_f[lane] : 0.f;
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
@@ -709,14 +716,14 @@ mb_big32768_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
             }
         }
         const float unscale = ldexpf(1.f, -kscale);
-        __syncthreads();
+        block_sync();
 
         if (want_spectrum) {
             // ---- 2. warp r takes z[16 m + r], m = 32 a + lane
             float2 v[32];
 #pragma unroll
             for (int a = 0; a < 32; a++) v[a] = B.area[544 * a + 17 * lane + warp];  // (512a+16b+r) + its padding (32a+b)
-            __syncthreads();  // everybody has its samples: the area becomes the sixteen warp slots
+            block_sync();  // everybody has its samples: the area becomes the sixteen warp slots
             // ---- 3. the 1024-point sub-FFT of this warp: 32 x 32 in registers, one transpose through the slot
 #pragma unroll 1
             for (int pass = 0; pass < 2; pass++) {
@@ -742,7 +749,7 @@ mb_big32768_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
                 if (warp > 0) y = cmul(y, cmul(tw_own, B.tw16[warp * 32 + d]));
                 slot[lane + 32 * d] = y;
             }
-            __syncthreads();
+            block_sync();
             // ---- 5. radix-16 across the warps' rows: C[k + 1024 q] for k = tid, tid + 512
             float2 u0[16], u1[16];
 #pragma unroll
@@ -752,13 +759,13 @@ mb_big32768_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
             }
             mbfft::fft_reg<16>(u0);
             mbfft::fft_reg<16>(u1);
-            __syncthreads();  // all rows consumed: the area becomes the natural-order spectrum C[0 .. M)
+            block_sync();  // all rows consumed: the area becomes the natural-order spectrum C[0 .. M)
 #pragma unroll
             for (int q = 0; q < 16; q++) {
                 B.area[tid + 1024 * q] = u0[mbfft::brev<4>(q)];
                 B.area[tid + 512 + 1024 * q] = u1[mbfft::brev<4>(q)];
             }
-            __syncthreads();
+            block_sync();
             // ---- 6. real-FFT split, spectra out, amplitude into smem, moment partials
             MomentAcc acc;
             const float sc_n = P.inv_sqrt_N;
@@ -793,7 +800,7 @@ mb_big32768_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
             frame_epilogue<false>(P, O, g, S, acc, B.amp, sc);
         }
         if (tid == kScalarThread) mb_store_scalars(P, O, g, S);
-        __syncthreads();  // smem reused by the next frame
+        block_sync();  // smem reused by the next frame
     }
 }
 #endif  // MB_GENERIC_THREADS == 512
