@@ -144,12 +144,11 @@ cudaError_t mb_launch_generic(const MbDevPlan &P, const MbClipTable &T, const fl
 #define MB_GO(NS)                                                                           \
     return P.exact ? launch_generic_##NS<true>(P, T, samples, O, num_sms, stream)           \
                    : launch_generic_##NS<false>(P, T, samples, O, num_sms, stream)
-    // (a launch with fewer frames than SMs is a latency case -- the streaming path, one buffer per push --
-    // and is better served by many threads on the one frame than by many frames in flight)
-    if (T.total_frames <= num_sms && P.N >= 128 && P.N < 8192) MB_GO(g256);
+    // (the choice depends on bufferSize alone: a frame's result must not depend on how many frames share its
+    // launch, so that the streaming path -- one buffer per push -- stays bit-identical to the batch call)
     if (P.N <= 512) MB_GO(g32);
-    if (P.N == 1024) MB_GO(g64);
-    if (P.N <= 4096) MB_GO(g128);
+    if (P.N <= 2048) MB_GO(g64);
+    if (P.N == 4096) MB_GO(g128);
     if (P.N == 8192) MB_GO(g256);
     if (P.N == 16384) MB_GO(g512);
     MB_GO(g1024);

@@ -8,6 +8,7 @@ __device__ __forceinline__ void block_sync() {
     if constexpr (kWarps == 1) __syncwarp();
     else __syncthreads();
 }
+constexpr int kLaneBandWarps = 2;  // CTAs of up to this many warps (bufferSize <= 2048) sum bands / filters one per lane
 constexpr int kScalarThread = kThreads > 64 ? 64 : 0;  // the lane that turns the frame's sums into the number features
 
 // One padding element every 32 and every 1024 entries keeps both the unit-stride
@@ -241,11 +242,19 @@ __device__ __forceinline__ void frame_epilogue(const MbDevPlan &P, const mb_outp
 
     // ---- bark band sums (loudness.js:55-63), one warp per band
     if (want_bark) {
-        for (int b = warp; b < MB_NUM_BARK_BANDS; b += kWarps) {
-            double s = 0;
-            for (int k = P.bb[b] + lane; k < P.bb[b + 1]; k += 32) s += (double)amp[k];
-            s = mb_warp_sum(s);
-            if (lane == 0) band_sum[b] = s;
+        if constexpr (kWarps <= kLaneBandWarps) {  // small CTAs: one lane per band, ascending like sumArray (loudness.js:69-77)
+            if (warp == 0 && lane < MB_NUM_BARK_BANDS) {
+                double s = 0;
+                for (int k = P.bb[lane]; k < P.bb[lane + 1]; k++) s += (double)amp[k];
+                band_sum[lane] = s;
+            }
+        } else {
+            for (int b = warp; b < MB_NUM_BARK_BANDS; b += kWarps) {
+                double s = 0;
+                for (int k = P.bb[b] + lane; k < P.bb[b + 1]; k += 32) s += (double)amp[k];
+                s = mb_warp_sum(s);
+                if (lane == 0) band_sum[b] = s;
+            }
         }
     }
     // ---- mel filterbank energies (mfcc.js:40-65)
@@ -264,6 +273,21 @@ __device__ __forceinline__ void frame_epilogue(const MbDevPlan &P, const mb_outp
                 }
                 mel_log[tid] = (float)log((double)s);
             }
+        } else if constexpr (kWarps <= kLaneBandWarps) {  // small CTAs: one lane per filter (on the second warp where there is one)
+            if (warp == (kWarps > 1 ? 1 : 0) && lane < MB_NUM_MEL_FILTERS) {
+                const int e0 = P.mel[lane], e1 = P.mel[lane + 1], e2 = min(P.mel[lane + 2], M);
+                const float up = __ldg(P.mel_inv_width + lane), dn = __ldg(P.mel_inv_width + lane + 1);
+                float s = 0.f;
+                for (int k = e0; k < e1; k++) {
+                    const float a = amp[k];
+                    s += (float)(k - e0) * up * (a * a);
+                }
+                for (int k = e1; k < e2; k++) {
+                    const float a = amp[k];
+                    s += (float)(e2 - k) * dn * (a * a);
+                }
+                mel_log[lane] = s;  // (the logarithm is taken below, all filters at once)
+            }
         } else {  // one warp per filter
             for (int f = warp; f < MB_NUM_MEL_FILTERS; f += kWarps) {
                 const int e0 = P.mel[f], e1 = P.mel[f + 1], e2 = P.mel[f + 2];
@@ -278,11 +302,16 @@ __device__ __forceinline__ void frame_epilogue(const MbDevPlan &P, const mb_outp
                     s += (float)(e2 - k) * dn * (a * a);
                 }
                 s = mb_warp_sum(s);
-                if (lane == 0) mel_log[f] = (float)log((double)s);
+                if (lane == 0) mel_log[f] = s;
             }
         }
     }
     block_sync();
+    // ln of the 26 filter energies by 26 threads at once (mfcc.js:63), not one filter at a time
+    if (!EXACT && mb_has(mask, MB_FEAT_MFCC)) {
+        if (tid < MB_NUM_MEL_FILTERS) mel_log[tid] = (float)log((double)mel_log[tid]);
+        block_sync();
+    }
 
     if (want_bark) {
         if (tid < MB_NUM_BARK_BANDS) {
