@@ -8,6 +8,8 @@
 //   const native = require('./build/Release/meyda_b200.node')
 //   const plan = native.createPlan({bufferSize, hop, sampleRate, window, featureMask, device, flags})
 //   const out  = native.extract(plan, samples /*Float32Array*/, offsets /*BigInt64Array*/, lengths /*BigInt64Array*/)
+//   const out  = native.extractPcm16(plan, pcm /*Int16Array, interleaved*/, channels, channel, offsets, lengths)
+//   const info = native.wavInfo(fileBytes /*Uint8Array*/)   // {format, channels, sampleRate, bitsPerSample, dataOffset, sampleFrames}
 //   native.destroyPlan(plan)
 //
 // `out` maps mb_outputs field names to typed arrays laid out exactly as the C
@@ -81,20 +83,30 @@ static const FieldDesc kFields[] = {
     F(loudness_total, MB_FEAT_LOUDNESS, 0), F(perceptual_spread, MB_FEAT_PERCEPTUAL_SPREAD, 0),
     F(perceptual_sharpness, MB_FEAT_PERCEPTUAL_SHARPNESS, 0), F(mfcc, MB_FEAT_MFCC, 4)};
 
-static napi_value Extract(napi_env env, napi_callback_info info) {
-    size_t argc = 4;
-    napi_value argv[4];
+// extract(plan, Float32Array, offsets, lengths)  /  extractPcm16(plan, Int16Array, channels, channel, offsets, lengths)
+static napi_value ExtractImpl(napi_env env, napi_callback_info info, bool pcm16) {
+    size_t argc = 6;
+    napi_value argv[6];
     NAPI_OK_OR_THROW(env, napi_get_cb_info(env, info, &argc, argv, NULL, NULL));
     mb_plan *plan = NULL;
     NAPI_OK_OR_THROW(env, napi_get_value_external(env, argv[0], (void **)&plan));
     napi_typedarray_type tt;
     size_t n_samples = 0, n_clips = 0, n_len = 0;
     void *samples = NULL, *offs = NULL, *lens = NULL;
+    int32_t channels = 1, channel = 0;
     NAPI_OK_OR_THROW(env, napi_get_typedarray_info(env, argv[1], &tt, &n_samples, &samples, NULL, NULL));
-    if (tt != napi_float32_array) { napi_throw_type_error(env, NULL, "samples must be a Float32Array"); return NULL; }
-    NAPI_OK_OR_THROW(env, napi_get_typedarray_info(env, argv[2], &tt, &n_clips, &offs, NULL, NULL));
+    if (tt != (pcm16 ? napi_int16_array : napi_float32_array)) {
+        napi_throw_type_error(env, NULL, pcm16 ? "pcm must be an Int16Array" : "samples must be a Float32Array");
+        return NULL;
+    }
+    if (pcm16) {
+        NAPI_OK_OR_THROW(env, napi_get_value_int32(env, argv[2], &channels));
+        NAPI_OK_OR_THROW(env, napi_get_value_int32(env, argv[3], &channel));
+    }
+    const int a0 = pcm16 ? 4 : 2;
+    NAPI_OK_OR_THROW(env, napi_get_typedarray_info(env, argv[a0], &tt, &n_clips, &offs, NULL, NULL));
     if (tt != napi_bigint64_array) { napi_throw_type_error(env, NULL, "offsets must be a BigInt64Array"); return NULL; }
-    NAPI_OK_OR_THROW(env, napi_get_typedarray_info(env, argv[3], &tt, &n_len, &lens, NULL, NULL));
+    NAPI_OK_OR_THROW(env, napi_get_typedarray_info(env, argv[a0 + 1], &tt, &n_len, &lens, NULL, NULL));
     if (tt != napi_bigint64_array || n_len != n_clips) { napi_throw_type_error(env, NULL, "lengths must match offsets"); return NULL; }
 
     mb_layout lay;
@@ -117,12 +129,44 @@ static napi_value Extract(napi_env env, napi_callback_info info) {
         *(void **)((char *)&out + f.offset) = data;
         NAPI_OK_OR_THROW(env, napi_set_named_property(env, result, f.name, ta));
     }
-    st = mb_extract(plan, (const float *)samples, (int64_t)n_samples, (const int64_t *)offs, (const int64_t *)lens,
-                    (int64_t)n_clips, &out, MB_MEM_HOST);
+    if (pcm16)  // the WAV data chunk as it is: conversion and channel pick happen on the device
+        st = mb_extract_pcm16(plan, (const int16_t *)samples, (int64_t)(n_samples / (channels > 0 ? channels : 1)), channels,
+                              channel, (const int64_t *)offs, (const int64_t *)lens, (int64_t)n_clips, &out, MB_MEM_HOST);
+    else
+        st = mb_extract(plan, (const float *)samples, (int64_t)n_samples, (const int64_t *)offs, (const int64_t *)lens,
+                        (int64_t)n_clips, &out, MB_MEM_HOST);
     if (st != MB_OK) return throw_mb(env, st);
     napi_value frames;
     NAPI_OK_OR_THROW(env, napi_create_int64(env, lay.total_frames, &frames));
     NAPI_OK_OR_THROW(env, napi_set_named_property(env, result, "totalFrames", frames));
+    return result;
+}
+
+static napi_value Extract(napi_env env, napi_callback_info info) { return ExtractImpl(env, info, false); }
+static napi_value ExtractPcm16(napi_env env, napi_callback_info info) { return ExtractImpl(env, info, true); }
+
+// wavInfo(Uint8Array) -> the fields of mb_wav_info (replaces the header half of decodeAudioData, lib/bufferLoader.js:28-38)
+static napi_value WavInfo(napi_env env, napi_callback_info info) {
+    size_t argc = 1;
+    napi_value argv[1];
+    NAPI_OK_OR_THROW(env, napi_get_cb_info(env, info, &argc, argv, NULL, NULL));
+    napi_typedarray_type tt;
+    size_t n = 0;
+    void *bytes = NULL;
+    NAPI_OK_OR_THROW(env, napi_get_typedarray_info(env, argv[0], &tt, &n, &bytes, NULL, NULL));
+    if (tt != napi_uint8_array) { napi_throw_type_error(env, NULL, "file bytes must be a Uint8Array"); return NULL; }
+    mb_wav_info wi;
+    const mb_status st = mb_wav_parse(bytes, (int64_t)n, &wi);
+    if (st != MB_OK) return throw_mb(env, st);
+    napi_value result, v;
+    NAPI_OK_OR_THROW(env, napi_create_object(env, &result));
+    const struct { const char *name; int64_t value; } fields[] = {
+        {"format", wi.format}, {"channels", wi.channels}, {"sampleRate", wi.sample_rate},
+        {"bitsPerSample", wi.bits_per_sample}, {"dataOffset", wi.data_offset}, {"sampleFrames", wi.n_sample_frames}};
+    for (const auto &f : fields) {
+        NAPI_OK_OR_THROW(env, napi_create_int64(env, f.value, &v));
+        NAPI_OK_OR_THROW(env, napi_set_named_property(env, result, f.name, v));
+    }
     return result;
 }
 
@@ -139,6 +183,8 @@ static napi_value Init(napi_env env, napi_value exports) {
     napi_property_descriptor props[] = {
         {"createPlan", NULL, CreatePlan, NULL, NULL, NULL, napi_default, NULL},
         {"extract", NULL, Extract, NULL, NULL, NULL, napi_default, NULL},
+        {"extractPcm16", NULL, ExtractPcm16, NULL, NULL, NULL, napi_default, NULL},
+        {"wavInfo", NULL, WavInfo, NULL, NULL, NULL, napi_default, NULL},
         {"destroyPlan", NULL, DestroyPlan, NULL, NULL, NULL, napi_default, NULL},
     };
     napi_define_properties(env, exports, sizeof(props) / sizeof(props[0]), props);

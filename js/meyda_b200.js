@@ -89,4 +89,41 @@ function extract (clips, opts, callback) {
   return result
 }
 
-module.exports = {extract, featureInfo, isPowerOfTwo, FEATURES}
+// extractWav(files /* Uint8Array | Uint8Array[] of 16-bit PCM WAV files */, {bufferSize, hop, windowingFunction,
+// features, channel, device}, callback?): BufferLoader + decodeAudioData + getChannelData(channel)
+// (lib/bufferLoader.js:13-44, src/meyda.js:72) in front of the same pipeline; the int16 samples go to the GPU as
+// they are and become s / 32768 inside the kernels' frame load.
+function extractWav (files, opts, callback) {
+  const N = opts.bufferSize
+  if (!isPowerOfTwo(N)) throw new Error('Buffer size is not a power of two: Meyda will not run.')
+  const features = splitFeatures(opts.features || FEATURES)
+  const list = Array.isArray(files) ? files : [files]
+  const infos = list.map(b => native.wavInfo(b))
+  infos.forEach(i => {
+    if (i.format !== 1 || i.bitsPerSample !== 16) throw new Error('extractWav takes 16-bit integer PCM')
+    if (i.channels !== infos[0].channels || i.sampleRate !== infos[0].sampleRate) throw new Error('all WAV files of one call must share channel count and sample rate')
+  })
+  const ch = infos[0].channels
+  const lengths = BigInt64Array.from(infos.map(i => BigInt(i.sampleFrames)))
+  const offsets = new BigInt64Array(list.length)
+  let total = 0  // clips start on multiples of 8 sample frames: mono frames stay 16-byte aligned for the TMA loads
+  infos.forEach((i, c) => { offsets[c] = BigInt(total); total += Math.ceil(i.sampleFrames / 8) * 8 })
+  const pcm = new Int16Array(total * ch)
+  list.forEach((b, c) => pcm.set(new Int16Array(b.buffer, b.byteOffset + infos[c].dataOffset, infos[c].sampleFrames * ch), Number(offsets[c]) * ch))
+  const featureMask = features.reduce((m, f) => m | (1 << FEATURES.indexOf(f)), 0)
+  const plan = native.createPlan({
+    bufferSize: N, hop: opts.hop || N, sampleRate: infos[0].sampleRate, featureMask,
+    window: {hanning: 0, hamming: 1, blackman: 2}[opts.windowingFunction || 'hanning'] || 0, device: opts.device || 0
+  })
+  const out = native.extractPcm16(plan, pcm, ch, opts.channel || 0, offsets, lengths)
+  native.destroyPlan(plan)
+  const result = {
+    features, arrays: out, totalFrames: Number(out.totalFrames),
+    value: (i, f) => frameValue(out, N, i, f),
+    frame: i => Object.fromEntries(features.map(f => [f, frameValue(out, N, i, f)]))
+  }
+  if (typeof callback === 'function') for (let i = 0; i < result.totalFrames; i++) callback(result.frame(i))
+  return result
+}
+
+module.exports = {extract, extractWav, featureInfo, isPowerOfTwo, FEATURES}
