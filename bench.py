@@ -203,6 +203,24 @@ def workload_config(clips_total, n_gpus, wave_clips):
             "l2_policy": "inputs (>=13 GB per rank) and outputs far larger than the 126 MB L2; no flush needed"}
 
 
+def bind_near_gpu(index: int):
+    """Multi-GPU runs: keep this rank's host threads (and therefore its pinned staging buffers, first-touch) on the
+    CPUs NVML reports as local to its GPU, so that the end-to-end leg's PCIe copies do not cross sockets."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return "%d cpus local to gpu %d" % (len(cpus), index)
+    except Exception as e:  # best effort: the measurement does not depend on it
+        return "unbound (%s)" % (str(e)[:60],)
+    return "unbound"
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -231,6 +249,7 @@ def main():
         raise SystemExit("bench.py: no CUDA device; the Meyda B200 path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa_note = bind_near_gpu(local_rank) if world > 1 else None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -386,6 +405,8 @@ def main():
         e2e = {"value": nf * world * args.steps / dt, "unit": UNIT, "h2d_bytes_per_step": int(hx.nbytes),
                "d2h_bytes_per_step": int(sum(v.nbytes for v in ho.values())),
                "batch": "%d clips x 30 s per rank per step, pinned host memory, mb_extract(MB_MEM_HOST)" % e2e_clips}
+        if numa_note:
+            e2e["host_binding"] = numa_note
         del host_x, host_out
 
     cpu_baseline = None

@@ -221,6 +221,13 @@ mb_status mb_extract_multi(mb_plan *const *plans, int n_plans, const float *samp
  * the device reads half the bytes.  clip_offset / clip_len count sample frames.
  * mem_kind as in mb_extract.  The _async form is MB_MEM_DEVICE only.
  */
+enum { MB_SAMPLE_S16 = 1, MB_SAMPLE_S24 = 2, MB_SAMPLE_F32 = 3 };
+/* The general form: `data` holds n_sample_frames x channels interleaved samples of `sample_format` (16-bit,
+ * packed little-endian 24-bit, or 32-bit float -- the payloads of WAV formats 1 and 3); int24 becomes s / 8388608.
+ * mb_extract_pcm16 is this call with MB_SAMPLE_S16 (the only format with a tuned bufferSize-2048 path). */
+mb_status mb_extract_pcm(mb_plan *plan, const void *data, int sample_format, int64_t n_sample_frames, int channels,
+                         int channel, const int64_t *clip_offset, const int64_t *clip_len, int64_t n_clips,
+                         const mb_outputs *out, int mem_kind);
 mb_status mb_extract_pcm16(mb_plan *plan, const int16_t *pcm, int64_t n_sample_frames, int channels, int channel,
                            const int64_t *clip_offset, const int64_t *clip_len, int64_t n_clips,
                            const mb_outputs *out, int mem_kind);

@@ -19,6 +19,7 @@ MB_FLAG_GENERIC_KERNEL = 1
 MB_FLAG_EXACT_FFT = 2
 MB_FLAG_CLUSTER_FFT = 4
 MB_NUM_FEATURES = 18
+MB_SAMPLE_S16, MB_SAMPLE_S24, MB_SAMPLE_F32 = 1, 2, 3
 
 # every symbol include/meyda_b200.h declares
 EXPORTS = [
@@ -27,7 +28,7 @@ EXPORTS = [
     "mb_query_output", "mb_extract", "mb_extract_async", "mb_plan_synchronize", "mb_extract_multi",
     "mb_plan_launch_count", "mb_plan_kernel_name", "mb_host_alloc", "mb_host_free",
     "mb_stream_create", "mb_stream_destroy", "mb_stream_frames_after", "mb_stream_push", "mb_stream_reset",
-    "mb_extract_pcm16", "mb_extract_pcm16_async", "mb_wav_parse", "mb_stream_graph_launches",
+    "mb_extract_pcm16", "mb_extract_pcm16_async", "mb_wav_parse", "mb_stream_graph_launches", "mb_extract_pcm",
 ]
 
 # (field name in mb_outputs, feature name, per-frame length as a function of N)
@@ -130,6 +131,8 @@ def lib():
     L.mb_extract_pcm16_async.argtypes = [vp, vp, C.c_int64, C.c_int, C.c_int, i64p, i64p, C.c_int64,
                                          C.POINTER(Outputs)]
     L.mb_wav_parse.argtypes = [vp, C.c_int64, C.POINTER(WavInfo)]
+    L.mb_extract_pcm.argtypes = [vp, vp, C.c_int, C.c_int64, C.c_int, C.c_int, i64p, i64p, C.c_int64, C.POINTER(Outputs),
+                                 C.c_int]
     _lib = L
     return L
 

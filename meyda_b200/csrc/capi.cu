@@ -279,13 +279,15 @@ mb_status check_clips(const mb_plan *p, int64_t n_samples, const int64_t *off, c
 // Launch the plan's kernel over `n` (virtual) clips whose offsets/prefix are
 // already in device memory.
 // `aligned`: every frame of this call starts on a 16-byte boundary (TMA bulk copies).
-// `pcm_channels` > 0: d_samples is interleaved int16 PCM (see MbClipTable).
+// `pcm_channels` > 0: d_samples is interleaved PCM of `pcm_format` (see MbClipTable).
 mb_status launch(mb_plan *p, const int64_t *d_off, const int64_t *d_frame_start, int64_t n, int64_t total_frames,
                  const float *d_samples, const mb_outputs &d_out, cudaStream_t stream, bool aligned,
-                 int pcm_channels = 0, int pcm_channel = 0) {
+                 int pcm_channels = 0, int pcm_channel = 0, int pcm_format = MB_SAMPLE_S16) {
     if (total_frames == 0) return MB_OK;
-    MbClipTable T{d_off, d_frame_start, n, total_frames, pcm_channels, pcm_channel};
+    MbClipTable T{d_off, d_frame_start, n, total_frames, pcm_channels, pcm_channel, pcm_format};
     const bool pcm = pcm_channels > 0;
+    // the tuned kernels take float32 mono or 16-bit PCM; other payloads go through the generic kernel's loader
+    const bool tuned_ok = !pcm || pcm_format == MB_SAMPLE_S16;
     // 16-byte aligned frames: required by the bufferSize-32768 kernel's float4 loads; the warp kernel takes
     // any float-aligned frame (misaligned ones bypass TMA inside the kernel) but bulk-stores `buffer` rows
     const bool out_ok = (uintptr_t)d_out.buffer % 16 == 0;
@@ -296,7 +298,7 @@ mb_status launch(mb_plan *p, const int64_t *d_off, const int64_t *d_frame_start,
     } else if (p->has_big_kernel && tma_ok && !pcm) {
         MB_CUDA(mb_launch_big32768(p->dev, T, d_samples, d_out, p->num_sms, stream));
         p->launches_warp++;
-    } else if (p->has_warp_kernel && out_ok && ((uintptr_t)d_samples % (pcm ? 2 : 4) == 0)) {
+    } else if (p->has_warp_kernel && tuned_ok && out_ok && ((uintptr_t)d_samples % (pcm ? 2 : 4) == 0)) {
         MB_CUDA(mb_launch_warp2048(p->dev, T, d_samples, d_out, p->num_sms, stream));
         p->launches_warp++;
     } else {
@@ -634,7 +636,7 @@ mb_status mb_query_output(const mb_plan *p, int64_t n_clips, const int64_t *clip
 
 static mb_status extract_device(mb_plan *p, const float *samples, int64_t n_samples, const int64_t *clip_offset,
                                 const int64_t *clip_len, int64_t n_clips, const mb_outputs *out, int pcm_channels,
-                                int pcm_channel) {
+                                int pcm_channel, int pcm_format = MB_SAMPLE_S16) {
     if (!p) return fail(MB_ERR_INVALID_ARG, "plan is NULL");
     mb_status st = check_outputs(p, out);
     if (st != MB_OK) return st;
@@ -662,7 +664,7 @@ static mb_status extract_device(mb_plan *p, const float *samples, int64_t n_samp
     MB_CUDA(cudaEventRecord(p->tab_event, p->stream));
     p->tab_event_pending = true;
     return launch(p, p->d_tab, p->d_tab + n_clips, n_clips, total, samples, *out, p->stream,
-                  offsets_aligned(clip_offset, n_clips), pcm_channels, pcm_channel);
+                  offsets_aligned(clip_offset, n_clips), pcm_channels, pcm_channel, pcm_format);
 }
 
 mb_status mb_extract_async(mb_plan *p, const float *samples, int64_t n_samples, const int64_t *clip_offset,
@@ -697,10 +699,12 @@ mb_status mb_plan_synchronize(mb_plan *p) {
 // that PCIe traffic in both directions overlaps the kernels.
 // `samples` is float32 (pcm_channels == 0) or interleaved int16 PCM; offsets count sample frames either way.
 static mb_status extract_host(mb_plan *p, const void *samples, const int64_t *clip_offset, const int64_t *clip_len,
-                              int64_t n_clips, const mb_outputs *out, int pcm_channels = 0, int pcm_channel = 0) {
+                              int64_t n_clips, const mb_outputs *out, int pcm_channels = 0, int pcm_channel = 0,
+                              int pcm_format = MB_SAMPLE_S16) {
     DeviceGuard guard(p->device);
     const int N = p->N, hop = p->hop;
-    const size_t frame_bytes = pcm_channels > 0 ? 2u * (size_t)pcm_channels : 4u;  // bytes per sample frame
+    const size_t frame_bytes =
+        pcm_channels > 0 ? (size_t)mb_sample_bytes(pcm_format) * (size_t)pcm_channels : 4u;  // bytes per sample frame
     const int64_t bpf = std::max<int64_t>(p->bytes_per_frame, 4);
     // chunk budget: ~192 MiB of output or ~64 MiB of fresh input, whichever is hit first
     const int64_t max_frames_out = std::max<int64_t>(1, (192ll << 20) / bpf);
@@ -772,7 +776,7 @@ static mb_status extract_host(mb_plan *p, const void *samples, const int64_t *cl
             cursor += (size_t)frames * field_elems(kFields[i], N) * 4;
         }
         st = launch(p, s.d_tab, s.d_tab + v.size(), (int64_t)v.size(), frames, s.d_samples, d_out, s.stream,
-                    offsets_aligned(s.h_tab, (int64_t)v.size()), pcm_channels, pcm_channel);
+                    offsets_aligned(s.h_tab, (int64_t)v.size()), pcm_channels, pcm_channel, pcm_format);
         if (st != MB_OK) return st;
         for (int i = 0; i < kNumFields; i++) {
             if (!mb_has(p->mask, kFields[i].feature)) continue;
@@ -811,11 +815,21 @@ mb_status mb_extract(mb_plan *p, const float *samples, int64_t n_samples, const 
 mb_status mb_extract_pcm16(mb_plan *p, const int16_t *pcm, int64_t n_sample_frames, int channels, int channel,
                            const int64_t *clip_offset, const int64_t *clip_len, int64_t n_clips, const mb_outputs *out,
                            int mem_kind) {
+    return mb_extract_pcm(p, pcm, MB_SAMPLE_S16, n_sample_frames, channels, channel, clip_offset, clip_len, n_clips, out,
+                          mem_kind);
+}
+
+mb_status mb_extract_pcm(mb_plan *p, const void *pcm, int format, int64_t n_sample_frames, int channels, int channel,
+                         const int64_t *clip_offset, const int64_t *clip_len, int64_t n_clips, const mb_outputs *out,
+                         int mem_kind) {
     if (!p) return fail(MB_ERR_INVALID_ARG, "plan is NULL");
+    if (format != MB_SAMPLE_S16 && format != MB_SAMPLE_S24 && format != MB_SAMPLE_F32)
+        return fail(MB_ERR_INVALID_ARG, "unknown sample format %d", format);
     mb_status st = check_pcm(channels, channel);
     if (st != MB_OK) return st;
     if (mem_kind == MB_MEM_DEVICE) {
-        st = mb_extract_pcm16_async(p, pcm, n_sample_frames, channels, channel, clip_offset, clip_len, n_clips, out);
+        st = extract_device(p, reinterpret_cast<const float *>(pcm), n_sample_frames, clip_offset, clip_len, n_clips, out,
+                            channels, channel, format);
         if (st != MB_OK) return st;
         return mb_plan_synchronize(p);
     }
@@ -826,7 +840,7 @@ mb_status mb_extract_pcm16(mb_plan *p, const int16_t *pcm, int64_t n_sample_fram
     if (st != MB_OK) return st;
     if (n_clips == 0) return MB_OK;
     if (!pcm) return fail(MB_ERR_INVALID_ARG, "pcm is NULL");
-    return extract_host(p, pcm, clip_offset, clip_len, n_clips, out, channels, channel);
+    return extract_host(p, pcm, clip_offset, clip_len, n_clips, out, channels, channel, format);
 }
 
 // RIFF/WAVE: "RIFF" <size> "WAVE" then chunks <id> <size> <payload, padded to even>; needs "fmt " and "data".

@@ -66,32 +66,45 @@ struct MbClipTable {
     const int64_t *frame_start;  // [n_clips + 1] exclusive prefix of frames per clip
     int64_t n_clips;
     int64_t total_frames;
-    // 0: `samples` is float32 mono.  > 0: `samples` is 16-bit PCM with this many interleaved channels, of which
-    // `pcm_channel` is taken and converted on load as decodeAudioData does (int16 / 32768; the step
-    // lib/bufferLoader.js:13-44 + getChannelData(0), src/meyda.js:72, perform in the reference).
+    // 0: `samples` is float32 mono.  > 0: `samples` is what a WAV data chunk holds, this many interleaved
+    // channels of `pcm_format` samples, of which channel `pcm_channel` is taken and converted on load as
+    // decodeAudioData does (int16 / 32768, int24 / 8388608, float32 as is): the step lib/bufferLoader.js:13-44 +
+    // getChannelData(0), src/meyda.js:72, perform in the reference.
     int pcm_channels;
     int pcm_channel;
+    int pcm_format;  // MB_SAMPLE_S16 / MB_SAMPLE_S24 / MB_SAMPLE_F32 (meaningful when pcm_channels > 0)
 };
 
 // One frame's samples, whatever the storage.
 struct MbFrameSrc {
-    const float *f;
-    const int16_t *s;
-    int stride;
+    const unsigned char *base;  // first sample of the frame (of the chosen channel)
+    int format;                 // -1: float32 mono
+    int stride;                 // bytes between consecutive samples of the channel
     __device__ __forceinline__ float operator[](int i) const {
-        return s ? (float)__ldg(s + (int64_t)i * stride) * (1.0f / 32768.0f) : __ldg(f + i);
+        const unsigned char *p = base + (int64_t)i * stride;
+        if (format < 0) return __ldg(reinterpret_cast<const float *>(base) + i);
+        if (format == MB_SAMPLE_S16) return (float)__ldg(reinterpret_cast<const int16_t *>(p)) * (1.0f / 32768.0f);
+        if (format == MB_SAMPLE_S24) {  // little-endian packed 3 bytes, sign in the last one
+            const int v = (int)__ldg(p) | ((int)__ldg(p + 1) << 8) | ((int)(signed char)__ldg(p + 2) << 16);
+            return (float)v * (1.0f / 8388608.0f);
+        }
+        return __ldg(reinterpret_cast<const float *>(p));
     }
 };
+__host__ __device__ __forceinline__ int mb_sample_bytes(int format) {
+    return format == MB_SAMPLE_S16 ? 2 : format == MB_SAMPLE_S24 ? 3 : 4;
+}
 __device__ __forceinline__ MbFrameSrc mb_frame_src(const MbClipTable &T, const float *samples, int64_t first) {
     MbFrameSrc r;
     if (T.pcm_channels > 0) {
-        r.f = nullptr;
-        r.s = reinterpret_cast<const int16_t *>(samples) + first * T.pcm_channels + T.pcm_channel;
-        r.stride = T.pcm_channels;
+        const int sb = mb_sample_bytes(T.pcm_format);
+        r.base = reinterpret_cast<const unsigned char *>(samples) + (first * T.pcm_channels + T.pcm_channel) * sb;
+        r.format = T.pcm_format;
+        r.stride = T.pcm_channels * sb;
     } else {
-        r.f = samples + first;
-        r.s = nullptr;
-        r.stride = 1;
+        r.base = reinterpret_cast<const unsigned char *>(samples + first);
+        r.format = -1;
+        r.stride = 4;
     }
     return r;
 }

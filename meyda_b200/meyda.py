@@ -216,6 +216,26 @@ class Plan:
                                              C.byref(o), _capi.MB_MEM_HOST))
         return out, per
 
+    def extract_pcm_host(self, data: np.ndarray, sample_format: int, channels: int, offsets: np.ndarray,
+                         lengths: np.ndarray, channel: int = 0, out: dict | None = None):
+        """MB_MEM_HOST call on a WAV payload of any supported sample format (mb_extract_pcm): `data` is the
+        interleaved sample block as int16 / float32 values or, for packed 24-bit, as bytes (uint8);
+        sample_format is _capi.MB_SAMPLE_S16 / _S24 / _F32.  offsets/lengths count sample frames."""
+        data = np.ascontiguousarray(data)
+        bytes_per = {_capi.MB_SAMPLE_S16: 2, _capi.MB_SAMPLE_S24: 3}.get(sample_format, 4)  # (the ABI rejects unknown formats)
+        n_sample_frames = data.nbytes // (bytes_per * channels)
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        lengths = np.ascontiguousarray(lengths, dtype=np.int64)
+        per, lay = self.query(lengths)
+        if out is None:
+            out = self.alloc_host_outputs(int(lay.total_frames))
+        o = self.pack_outputs({k: v.ctypes.data for k, v in out.items()})
+        i64p = C.POINTER(C.c_int64)
+        _capi.check(self._L.mb_extract_pcm(self._h, data.ctypes.data, sample_format, n_sample_frames, channels, channel,
+                                           offsets.ctypes.data_as(i64p), lengths.ctypes.data_as(i64p), len(lengths),
+                                           C.byref(o), _capi.MB_MEM_HOST))
+        return out, per
+
     def extract_pcm16_device(self, pcm_ptr: int, n_sample_frames: int, channels: int, channel: int,
                              offsets: np.ndarray, lengths: np.ndarray, out_ptrs: dict, sync: bool = True):
         """MB_MEM_DEVICE call on 16-bit PCM already resident on the plan's device."""
@@ -373,8 +393,9 @@ def extract_wav(files, bufferSize: int, hop: int | None = None, windowingFunctio
                 device: int = 0, flags: int = 0) -> ExtractResult:
     """Replaces BufferLoader + decodeAudioData + getChannelData(channel) (lib/bufferLoader.js:13-44,
     src/meyda.js:72) in front of `extract`: `files` is one path / bytes object or a list of them, each a
-    16-bit PCM WAV; the int16 samples go to the GPU as they are and become s / 32768 inside the frame load.
-    All files must share the channel count and sample rate (which becomes the plan's sampleRate)."""
+    16-bit PCM WAV (or 24-bit PCM / 32-bit float, which take the generic kernels); the samples go to the GPU as the
+    file holds them and are converted (s / 32768, s / 8388608) inside the frame load.  All files must share the
+    channel count, sample format and sample rate (which becomes the plan's sampleRate)."""
     feats, _single = _split_features(features)
     if not feats:
         raise MeydaError("Invalid Feature Format")
@@ -387,24 +408,28 @@ def extract_wav(files, bufferSize: int, hop: int | None = None, windowingFunctio
                 f = fh.read()
         blobs.append(bytes(f))
     infos = [wav_info(b) for b in blobs]
+    kinds = {(1, 16): (_capi.MB_SAMPLE_S16, 2), (1, 24): (_capi.MB_SAMPLE_S24, 3), (3, 32): (_capi.MB_SAMPLE_F32, 4)}
     for i in infos:
-        if i["format"] != 1 or i["bitsPerSample"] != 16:
-            raise MeydaError("extract_wav takes 16-bit integer PCM (got format %d, %d bits)" % (i["format"], i["bitsPerSample"]))
-        if (i["channels"], i["sampleRate"]) != (infos[0]["channels"], infos[0]["sampleRate"]):
-            raise MeydaError("all WAV files of one call must share channel count and sample rate")
+        if (i["format"], i["bitsPerSample"]) not in kinds:
+            raise MeydaError("extract_wav takes 16- or 24-bit integer PCM or 32-bit float (got format %d, %d bits)"
+                             % (i["format"], i["bitsPerSample"]))
+        if (i["channels"], i["sampleRate"], i["format"], i["bitsPerSample"]) != \
+                (infos[0]["channels"], infos[0]["sampleRate"], infos[0]["format"], infos[0]["bitsPerSample"]):
+            raise MeydaError("all WAV files of one call must share channel count, sample rate and sample format")
     ch = infos[0]["channels"]
-    parts = [np.frombuffer(b, dtype="<i2", count=i["sampleFrames"] * ch, offset=i["dataOffset"]).reshape(-1, ch)
-             for b, i in zip(blobs, infos)]
-    # clips start on multiples of 8 sample frames so that mono frames stay 16-byte aligned (TMA bulk loads)
-    lengths = np.array([p.shape[0] for p in parts], dtype=np.int64)
+    fmt, sbytes = kinds[(infos[0]["format"], infos[0]["bitsPerSample"])]
+    fb = sbytes * ch  # bytes per sample frame
+    # clips start on multiples of 8 sample frames so that mono 16-bit frames stay 16-byte aligned (TMA bulk loads)
+    lengths = np.array([i["sampleFrames"] for i in infos], dtype=np.int64)
     padded = (lengths + 7) // 8 * 8
     offsets = np.concatenate([[0], np.cumsum(padded)[:-1]]).astype(np.int64)
-    pcm = np.zeros((int(padded.sum()), ch), dtype=np.int16)
-    for o, p in zip(offsets, parts):
-        pcm[o:o + p.shape[0]] = p
+    payload = np.zeros(int(padded.sum()) * fb, dtype=np.uint8)  # the data chunks, back to back, untouched
+    for o, b, i in zip(offsets, blobs, infos):
+        n = int(i["sampleFrames"]) * fb
+        payload[int(o) * fb:int(o) * fb + n] = np.frombuffer(b, dtype=np.uint8, count=n, offset=i["dataOffset"])
     plan = Plan(bufferSize, hop, float(infos[0]["sampleRate"]), windowingFunction, feats, device=device, flags=flags)
     try:
-        arrays, per = plan.extract_pcm16_host(pcm if ch > 1 else pcm[:, 0], offsets, lengths, channel=channel)
+        arrays, per = plan.extract_pcm_host(payload, fmt, ch, offsets, lengths, channel=channel)
     finally:
         plan.close()
     res = ExtractResult(feats, arrays, per, int(bufferSize))

@@ -124,6 +124,45 @@ def test_extract_wav_against_the_oracle():
         parity.assert_bits(k, r2.arrays[k], res.arrays[k][:325])
 
 
+def _wav_bytes(fmt_tag, channels, rate, bits, payload: bytes) -> bytes:
+    import struct
+    block = channels * bits // 8
+    fmt = struct.pack("<HHIIHH", fmt_tag, channels, rate, rate * block, block, bits)
+    body = b"WAVE" + b"fmt " + struct.pack("<I", len(fmt)) + fmt + b"data" + struct.pack("<I", len(payload)) + payload
+    return b"RIFF" + struct.pack("<I", len(body)) + body
+
+
+@pytest.mark.parametrize("N,hop", [(2048, 512), (512, 512), (1024, 300)])
+def test_24bit_and_float_wav_payloads(N, hop):
+    """WAV format 1 / 24 bits (s / 8388608, exact in float32) and format 3 / 32-bit float, mono and interleaved stereo:
+    converted inside the generic kernels' frame load, bit-identical to the float path on the decoded samples."""
+    rng = np.random.default_rng(24)
+    n = 30000
+    v24 = rng.integers(-(1 << 23), 1 << 23, size=(n, 2), dtype=np.int64)
+    v24[100:100 + N, 0] = -(1 << 23)
+    v24[5000:5000 + N:3, 1] = (1 << 23) - 1
+    f32 = (rng.standard_normal((n, 2)) * 0.3).astype(np.float32)
+    packed = (v24.astype("<i4").view(np.uint8).reshape(n, 2, 4)[:, :, :3]).copy()  # little-endian, low 3 bytes
+    feats = mb.FEATURES
+    for ch in (1, 2):
+        for c in range(ch):
+            # 24-bit
+            payload = packed[:, :ch].tobytes() if ch == 2 else packed[:, 0].tobytes()
+            res = mb.extract_wav(_wav_bytes(1, ch, 44100, 24, payload), N, hop=hop, features=feats, channel=c)
+            x = (v24[:, c].astype(np.float32) / np.float32(8388608.0)).astype(np.float32)
+            ref, per = run_gpu(x, N, hop, flags=_capi.MB_FLAG_GENERIC_KERNEL)
+            assert res.frames_per_clip.tolist() == per.tolist()
+            assert_same_bits(res.arrays, ref)
+            # 32-bit float
+            payload = f32[:, :ch].tobytes() if ch == 2 else f32[:, 0].tobytes()
+            res = mb.extract_wav(_wav_bytes(3, ch, 44100, 32, payload), N, hop=hop, features=feats, channel=c)
+            ref, _ = run_gpu(f32[:, c].copy(), N, hop, flags=_capi.MB_FLAG_GENERIC_KERNEL)
+            assert_same_bits(res.arrays, ref)
+    # and against the oracle itself on one of them
+    res = mb.extract_wav(_wav_bytes(1, 1, 44100, 24, packed[:, 0].tobytes()), N, hop=hop, features=feats)
+    verify(res.arrays, (v24[:, 0].astype(np.float32) / np.float32(8388608.0)).astype(np.float32), N, hop)
+
+
 def test_pcm_errors():
     plan = mb.Plan(512, 512, SR, "hanning", ["rms"])
     try:
@@ -138,6 +177,13 @@ def test_pcm_errors():
         plan.close()
     with pytest.raises(mb.MeydaError):
         mb.extract_wav(make_wav(np.zeros(100, np.int16)), 16, features=["nope"])
+    with pytest.raises(mb.MeydaNativeError) as e:
+        plan2 = mb.Plan(512, 512, SR, "hanning", ["rms"])
+        try:
+            plan2.extract_pcm_host(np.zeros(2048, np.int16), 7, 1, np.zeros(1, np.int64), np.array([1024], np.int64))
+        finally:
+            plan2.close()
+    assert e.value.status == _capi.MB_ERR_INVALID_ARG
     with pytest.raises(mb.MeydaError):  # 8-bit file
         import io, wave
         b = io.BytesIO(); w = wave.open(b, "wb"); w.setnchannels(1); w.setsampwidth(1); w.setframerate(8000)
