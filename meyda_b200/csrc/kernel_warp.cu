@@ -162,11 +162,13 @@ __device__ __forceinline__ double stash_get_d(float (*st)[kChunk], int row, int 
     return __hiloint2double(__float_as_int(st[row][col]), __float_as_int(st[row + 1][col]));
 }
 
-// kFull: every feature is requested (the headline configuration) -- the per-bin feature tests fold away.
+// kMask: a compile-time feature set (0 = take the plan's at run time).  With the set known the per-bin feature
+// tests fold away; instantiated for every feature (the headline configuration), for BASELINE config 3 (mfcc +
+// the four spectral moments) and for "everything but the four big arrays".
 // kPcm: `samples` holds 16-bit PCM (MbClipTable::pcm_channels interleaved channels); a frame arrives as 4 KB
 // instead of 8 KB and is converted in pass 1 (x = s / 32768, exact), after which nothing differs -- the results
 // are bit-identical to the float32 path on the converted samples.  `buffer` then leaves from registers.
-template <bool kFull, bool kPcm>
+template <uint32_t kMask, bool kPcm>
 __global__ void __launch_bounds__(kThreads, 1)
 mb_warp2048_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ MbClipTable T,
                    const float *__restrict__ samples, const __grid_constant__ mb_outputs O, const int64_t total_chunks) {
@@ -176,7 +178,7 @@ mb_warp2048_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
     Smem &S = *reinterpret_cast<Smem *>(smem_raw);
     if (smem_u32(smem_raw) & 127u) __trap();
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t mask = P.mask;
+    const uint32_t mask = kMask ? kMask : P.mask;
     const MbWarpTables *__restrict__ WT = P.warp_tables;
 
     // ---- CTA-wide tables into shared memory (once per persistent CTA)
@@ -203,25 +205,24 @@ mb_warp2048_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
     const uint32_t bmask = WT->lane_bmask[lane];     // boundaries inside this lane's 32 blocked bins
     const int slot_base = WT->lane_slot_base[lane];  // how many boundaries lie below this lane's first bin
 
-    const bool want_buffer = kFull || mb_has(mask, MB_FEAT_BUFFER);
-    const bool want_time = kFull || (mask & (MB_FEATURE_BIT(MB_FEAT_RMS) | MB_FEATURE_BIT(MB_FEAT_ENERGY) | MB_FEATURE_BIT(MB_FEAT_ZCR)));
-    const bool want_cs = kFull || mb_has(mask, MB_FEAT_COMPLEX_SPECTRUM);
-    const bool want_amp_out = kFull || mb_has(mask, MB_FEAT_AMPLITUDE_SPECTRUM);
-    const bool want_pow_out = kFull || mb_has(mask, MB_FEAT_POWER_SPECTRUM);
-    const bool want_moments = kFull ||
-        (mask & (MB_FEATURE_BIT(MB_FEAT_SPECTRAL_CENTROID) | MB_FEATURE_BIT(MB_FEAT_SPECTRAL_SPREAD) |
+    const bool want_buffer = mb_has(mask, MB_FEAT_BUFFER);
+    const bool want_time = (mask & (MB_FEATURE_BIT(MB_FEAT_RMS) | MB_FEATURE_BIT(MB_FEAT_ENERGY) | MB_FEATURE_BIT(MB_FEAT_ZCR)));
+    const bool want_cs = mb_has(mask, MB_FEAT_COMPLEX_SPECTRUM);
+    const bool want_amp_out = mb_has(mask, MB_FEAT_AMPLITUDE_SPECTRUM);
+    const bool want_pow_out = mb_has(mask, MB_FEAT_POWER_SPECTRUM);
+    const bool want_moments = (mask & (MB_FEATURE_BIT(MB_FEAT_SPECTRAL_CENTROID) | MB_FEATURE_BIT(MB_FEAT_SPECTRAL_SPREAD) |
                 MB_FEATURE_BIT(MB_FEAT_SPECTRAL_SKEWNESS) | MB_FEATURE_BIT(MB_FEAT_SPECTRAL_KURTOSIS) |
                 MB_FEATURE_BIT(MB_FEAT_SPECTRAL_FLATNESS) | MB_FEATURE_BIT(MB_FEAT_SPECTRAL_SLOPE)));
-    const bool want_log = kFull || mb_has(mask, MB_FEAT_SPECTRAL_FLATNESS);
-    const bool want_rolloff = kFull || mb_has(mask, MB_FEAT_SPECTRAL_ROLLOFF);
-    const bool want_bark = kFull || (mask & (MB_FEATURE_BIT(MB_FEAT_LOUDNESS) | MB_FEATURE_BIT(MB_FEAT_PERCEPTUAL_SPREAD) |
+    const bool want_log = mb_has(mask, MB_FEAT_SPECTRAL_FLATNESS);
+    const bool want_rolloff = mb_has(mask, MB_FEAT_SPECTRAL_ROLLOFF);
+    const bool want_bark = (mask & (MB_FEATURE_BIT(MB_FEAT_LOUDNESS) | MB_FEATURE_BIT(MB_FEAT_PERCEPTUAL_SPREAD) |
                                              MB_FEATURE_BIT(MB_FEAT_PERCEPTUAL_SHARPNESS)));
-    const bool want_mfcc = kFull || mb_has(mask, MB_FEAT_MFCC);
+    const bool want_mfcc = mb_has(mask, MB_FEAT_MFCC);
     const bool want_pieces = want_bark || want_mfcc;
     const bool want_blocked = want_rolloff || want_pieces || want_moments;
     const uint32_t time_only = MB_FEATURE_BIT(MB_FEAT_RMS) | MB_FEATURE_BIT(MB_FEAT_ENERGY) |
                                MB_FEATURE_BIT(MB_FEAT_ZCR) | MB_FEATURE_BIT(MB_FEAT_BUFFER);
-    const bool want_spectrum = kFull || (mask & ~time_only) != 0;
+    const bool want_spectrum = (mask & ~time_only) != 0;
 
     float *slot = S.slot[warp];
     float2 *slot2 = reinterpret_cast<float2 *>(slot);
@@ -707,9 +708,17 @@ size_t mb_warp2048_smem_bytes() { return sizeof(Smem) + 128; }
 cudaError_t mb_launch_warp2048(const MbDevPlan &P, const MbClipTable &T, const float *samples, const mb_outputs &O,
                                int num_sms, cudaStream_t stream) {
     const size_t smem = mb_warp2048_smem_bytes();
-    const bool full = (P.mask & MB_ALL_FEATURES) == MB_ALL_FEATURES, pcm = T.pcm_channels > 0;
-    auto kernel = full ? (pcm ? mb_warp2048_kernel<true, true> : mb_warp2048_kernel<true, false>)
-                       : (pcm ? mb_warp2048_kernel<false, true> : mb_warp2048_kernel<false, false>);
+    const bool pcm = T.pcm_channels > 0;
+    const uint32_t m = P.mask & MB_ALL_FEATURES;
+    constexpr uint32_t kC3 = MB_FEATURE_BIT(MB_FEAT_MFCC) | MB_FEATURE_BIT(MB_FEAT_SPECTRAL_CENTROID) |
+                             MB_FEATURE_BIT(MB_FEAT_SPECTRAL_SPREAD) | MB_FEATURE_BIT(MB_FEAT_SPECTRAL_SKEWNESS) |
+                             MB_FEATURE_BIT(MB_FEAT_SPECTRAL_KURTOSIS);
+    constexpr uint32_t kNoArrays = MB_ALL_FEATURES & ~(MB_FEATURE_BIT(MB_FEAT_BUFFER) | MB_FEATURE_BIT(MB_FEAT_COMPLEX_SPECTRUM) |
+                                                       MB_FEATURE_BIT(MB_FEAT_AMPLITUDE_SPECTRUM) | MB_FEATURE_BIT(MB_FEAT_POWER_SPECTRUM));
+#define MB_PICK(MASK) (pcm ? mb_warp2048_kernel<MASK, true> : mb_warp2048_kernel<MASK, false>)
+    auto kernel = m == MB_ALL_FEATURES ? MB_PICK(MB_ALL_FEATURES) : m == kC3 ? MB_PICK(kC3) : m == kNoArrays ? MB_PICK(kNoArrays)
+                                                                                                             : MB_PICK(0u);
+#undef MB_PICK
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const int64_t chunks = (T.total_frames + kChunk - 1) / kChunk;
