@@ -13,7 +13,7 @@
  * reference's OWN source files executed by oracle/minijs.py, an ES5-subset
  * interpreter written for that purpose: tests/golden/js_reference_vectors.npz
  * (tools/make_js_golden.py) holds what the lib/jsfft sources, src/utils.js, every
- * file under src/extractors and the compute* methods of src/meyda.js return on nine
+ * file under src/extractors and the compute* methods of src/meyda.js return on seventeen
  * frames, and tests/test_js_pin.py requires this file to reproduce them bit
  * for bit (Float32Array results) / to 1e-12 (Numbers).  Further guards: (i) an
  * independently written numpy restatement (oracle/meyda_oracle.py) that must

@@ -77,6 +77,31 @@ def read_wav_pcm16(path: str):
     return pcm16_to_float(pcm), float(fmt[2])
 
 
+def degenerate_frame(name: str, N: int) -> np.ndarray:
+    """Named synthetic frames shared by the JS-vector generator and the tests."""
+    t = np.arange(N)
+    if name == "silence":
+        x = np.zeros(N)
+    elif name == "impulse":
+        x = np.eye(1, N, 7)[0]
+    elif name == "square":
+        x = np.where((t // 16) % 2 == 0, 1.0, -1.0)
+    elif name == "dc":
+        x = np.full(N, 0.5)
+    elif name == "tone":
+        x = 0.8 * np.sin(2 * np.pi * 32 * t / N)
+    elif name == "tiny":
+        x = np.random.default_rng(5).standard_normal(N) * 1e-30
+    elif name == "negzero":
+        x = np.where(t % 2 == 0, -0.0, 0.0)
+    elif name == "nan":
+        x = synth_clip(2, N).astype(np.float64)
+        x[N // 3] = np.nan
+    else:
+        raise KeyError(name)
+    return x.astype(f32)
+
+
 def pcm16_to_float(pcm: np.ndarray) -> np.ndarray:
     return (pcm.astype(f32) / f32(32768.0)).astype(f32)
 

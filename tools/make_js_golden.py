@@ -116,13 +116,17 @@ def run_frame(it, signal, sr, window):
 def main():
     z = np.load(os.path.join(ROOT, "tests", "golden", "audio_pcm16.npz"))
     clips = {k: mo.pcm16_to_float(z[k]) for k in z.files}
-    t = np.arange(256)
     cases = [("sound1", 512, 0, "hanning"), ("sound1", 512, 100, "hanning"), ("sound2", 256, 5, "hanning"),
              ("sound3", 1024, 200, "hanning"), ("sound2", 512, 40, "hamming"), ("sound1", 2048, 10, "hanning"),
-             ("silence", 256, 0, "hanning"), ("impulse", 256, 0, "hanning"), ("square", 256, 0, "hamming")]
-    clips["silence"] = np.zeros(256, np.float32)
-    clips["impulse"] = np.eye(1, 256, 7, dtype=np.float32)[0]
-    clips["square"] = np.where((t // 16) % 2 == 0, 1.0, -1.0).astype(np.float32)
+             ("silence", 256, 0, "hanning"), ("impulse", 256, 0, "hanning"), ("square", 256, 0, "hamming"),
+             # second batch: the special-value frames (NaN compares, -0, float32 underflow), a bin-centred tone, DC,
+             # and more of the demo clips at other sizes / windows
+             ("nan", 256, 0, "hanning"), ("negzero", 256, 0, "hanning"), ("tiny", 256, 0, "hanning"),
+             ("tone", 512, 0, "hanning"), ("dc", 256, 0, "hamming"), ("sound2", 1024, 100, "hanning"),
+             ("sound3", 2048, 50, "hamming"), ("sound1", 256, 300, "hamming")]
+    for name, N, _f, _w in cases:
+        if name not in clips:
+            clips[name] = mo.degenerate_frame(name, N)
     it = build()
     out = {"cases": np.array(["%s/%d/%d/%s" % c for c in cases])}
     for ci, (clip, N, f, window) in enumerate(cases):
