@@ -875,8 +875,13 @@ mb_status mb_wav_parse(const void *file_bytes, int64_t n_bytes, mb_wav_info *inf
         o = body + size + (size & 1);
     }
     if (!have_fmt || !have_data) return fail(MB_ERR_INVALID_ARG, "WAVE file without a fmt or data chunk");
-    if (info->channels < 1 || info->bits_per_sample < 8) return fail(MB_ERR_INVALID_ARG, "bad fmt chunk");
-    if (block_align <= 0) block_align = info->channels * (info->bits_per_sample / 8);
+    if (info->channels < 1 || info->bits_per_sample < 8 || info->bits_per_sample % 8 != 0)
+        return fail(MB_ERR_INVALID_ARG, "bad fmt chunk");
+    const int expect_align = info->channels * (info->bits_per_sample / 8);
+    if (block_align <= 0) block_align = expect_align;
+    if (block_align != expect_align)  // a frame count derived from a lying block size would point past the data
+        return fail(MB_ERR_INVALID_ARG, "fmt chunk: block align %d is not channels x bytes per sample (%d)", block_align,
+                    expect_align);
     info->n_sample_frames = data_bytes / block_align;
     return MB_OK;
 }

@@ -85,3 +85,29 @@ def test_reference_fixtures_parse_like_the_oracle_reader():
         ref_float, rate = mo.read_wav_pcm16(os.path.join(REF_AUDIO, name + ".wav"))
         assert rate == 44100 and np.array_equal(pcm, z[name])
         assert np.array_equal(mo.pcm16_to_float(pcm), ref_float)
+
+
+def test_parser_never_reads_outside_the_file():
+    """Truncated and bit-flipped files either parse to something that fits inside the bytes given or are rejected."""
+    from hypothesis import given, settings, strategies as st
+    good = [make_wav(np.arange(64, dtype=np.int16)), make_wav(np.arange(120, dtype=np.int16).reshape(40, 3), rate=8000)]
+
+    @settings(max_examples=300, deadline=None)
+    @given(st.integers(0, 1), st.integers(0, 300), st.lists(st.tuples(st.integers(0, 299), st.integers(0, 255)), max_size=6),
+           st.binary(max_size=40))
+    def check(which, cut, flips, tail):
+        b = bytearray(good[which])
+        for pos, val in flips:
+            if pos < len(b):
+                b[pos] = val
+        blob = bytes(b[:max(0, len(b) - cut)]) + tail
+        try:
+            i = mb.wav_info(blob)
+        except mb.MeydaNativeError as e:
+            assert e.status == _capi.MB_ERR_INVALID_ARG
+            return
+        assert i["channels"] >= 1 and i["bitsPerSample"] % 8 == 0 and i["sampleFrames"] >= 0
+        assert 0 <= i["dataOffset"] <= len(blob)
+        assert i["dataOffset"] + i["sampleFrames"] * i["channels"] * (i["bitsPerSample"] // 8) <= len(blob)
+
+    check()
