@@ -112,7 +112,9 @@ struct mb_plan {
     double2 *d_tw_exact = nullptr;
     double *d_mel_w_exact = nullptr;
     MbWarpTables *d_warp_tables = nullptr;
+    MbWarpMfTables *d_warp_mf_tables = nullptr;
     bool has_warp_kernel = false;
+    bool has_mf_kernel = false;
     bool use_cluster = false;
     bool has_big_kernel = false;
     int64_t launches_warp = 0, launches_generic = 0;
@@ -301,6 +303,9 @@ mb_status launch(mb_plan *p, const int64_t *d_off, const int64_t *d_frame_start,
     } else if (p->has_warp_kernel && tuned_ok && out_ok && ((uintptr_t)d_samples % (pcm ? 2 : 4) == 0)) {
         MB_CUDA(mb_launch_warp2048(p->dev, T, d_samples, d_out, p->num_sms, stream));
         p->launches_warp++;
+    } else if (p->has_mf_kernel && tuned_ok && out_ok && ((uintptr_t)d_samples % (pcm ? 2 : 4) == 0)) {
+        MB_CUDA(mb_launch_warpmf(p->dev, T, d_samples, d_out, p->num_sms, stream));
+        p->launches_warp++;
     } else {
         MB_CUDA(mb_launch_generic(p->dev, T, d_samples, d_out, p->num_sms, stream));
         p->launches_generic++;
@@ -351,8 +356,8 @@ void build_warp_tables(MbWarpTables &W, const MbDevPlan &D) {
     // piece ids: a lane's pieces are consecutive, head first (the kernel walks them with one pointer)
     auto head_id = [&](int lane) { return W.lane_slot_base[lane] + lane; };
     auto boundary_id = [&](int s) { return s + below[s] / 32 + 1; };
-    for (int lane = 0; lane < 32; lane++) W.piece_edge[head_id(lane)] = 32 * lane;
-    for (int s = 0; s < W.n_slots; s++) W.piece_edge[boundary_id(s)] = 32 * (below[s] / 32);
+    for (int lane = 0; lane < 32; lane++) W.piece_edge[head_id(lane)] = 32 * lane;  // a piece's first bin
+    for (int s = 0; s < W.n_slots; s++) W.piece_edge[boundary_id(s)] = below[s];
     // pieces of every Bark band [bb[b], bb[b+1]) and mel segment [mel[s], mel[s+1])
     int n_items = 0;
     auto add_segment = [&](int seg, int e0, int e1) {
@@ -368,6 +373,74 @@ void build_warp_tables(MbWarpTables &W, const MbDevPlan &D) {
     for (int s = 0; s <= MB_NUM_MEL_FILTERS; s++) add_segment(MB_NUM_BARK_BANDS + s, D.mel[s], D.mel[s + 1]);
     W.seg_ptr[MB_WARP_SEGMENTS] = n_items;
     if (n_items >= MB_WARP_MAX_ITEMS) W.n_slots = MB_WARP_MAX_SLOTS + 1;
+}
+
+// The same bookkeeping for the multi-frame warp kernel (bufferSize 512 / 1024): the warp's 32 lanes are F frames
+// of A = M / 32 lanes each; a lane's pieces are consecutive (head first), lanes in order, so piece ids run
+// frame-major.  Segments: f * MB_WARP_SEGMENTS + (band b | 24 + mel segment s).
+void build_warp_mf_tables(MbWarpMfTables &W, const MbDevPlan &D) {
+    const int M = D.M, A = M / 32, F = 32 / A;
+    memset(&W, 0, sizeof(W));
+    for (int c = 0; c < 32; c++)
+        for (int b = 0; b < 32; b++) {
+            const double ang = 2 * M_PI * (double)((c % A) * b) / (double)M;
+            W.tw32[c * 32 + b] = make_float2((float)cos(ang), (float)sin(ang));
+        }
+    std::vector<int> edges;
+    for (int i = 0; i <= MB_NUM_BARK_BANDS; i++) edges.push_back(D.bb[i]);
+    for (int i = 0; i < MB_NUM_MEL_FILTERS + 2; i++) edges.push_back(D.mel[i]);
+    std::sort(edges.begin(), edges.end());
+    edges.erase(std::unique(edges.begin(), edges.end()), edges.end());
+    std::vector<int> below;  // boundaries < M (frame-local bins)
+    for (int e : edges)
+        if (e < M) below.push_back(e);
+    const int nb = (int)below.size();
+    W.n_pieces = F * (A + nb);
+    if (W.n_pieces > MB_MF_MAX_PIECES || below.empty() || below[0] != 0) {
+        W.n_pieces = MB_MF_MAX_PIECES + 1;  // signals "does not fit" to the caller
+        return;
+    }
+    // piece ids of one frame: row r's head, then the boundaries inside row r, rows in order
+    std::vector<int> head_id(A), head_end(A), boundary_id(nb);
+    int id = 0;
+    for (int r = 0; r < A; r++) {
+        head_id[r] = id++;
+        head_end[r] = 32 * r + 32;
+        uint32_t m = 0;
+        for (int s = 0; s < nb; s++)
+            if (below[s] >= 32 * r && below[s] < 32 * r + 32) {
+                if (head_end[r] == 32 * r + 32) head_end[r] = below[s];
+                boundary_id[s] = id++;
+                m |= 1u << (below[s] - 32 * r);
+            }
+        for (int f = 0; f < F; f++) W.lane_bmask[f * A + r] = m;
+    }
+    const int per_frame = id;  // == A + nb
+    for (int f = 0; f < F; f++)
+        for (int r = 0; r < A; r++) W.lane_slot_base[f * A + r] = f * per_frame + head_id[r] - (f * A + r);
+    for (int f = 0; f < F; f++) {
+        for (int r = 0; r < A; r++) W.piece_edge[f * per_frame + head_id[r]] = (short)(32 * r);
+        for (int s = 0; s < nb; s++) W.piece_edge[f * per_frame + boundary_id[s]] = (short)below[s];  // a piece's first bin
+    }
+    int n_items = 0;
+    bool overflow = false;
+    auto add_segment = [&](int f, int seg, int e0, int e1) {
+        W.seg_ptr[f * MB_WARP_SEGMENTS + seg] = (short)n_items;
+        auto push = [&](int pid) {
+            if (n_items < MB_MF_MAX_ITEMS) W.seg_items[n_items++] = (unsigned short)(f * per_frame + pid);
+            else overflow = true;
+        };
+        for (int s = 0; s < nb; s++)
+            if (below[s] >= e0 && below[s] < e1) push(boundary_id[s]);
+        for (int r = 0; r < A; r++)
+            if (head_end[r] > 32 * r && 32 * r > e0 && 32 * r < e1) push(head_id[r]);
+    };
+    for (int f = 0; f < F; f++) {
+        for (int b = 0; b < MB_NUM_BARK_BANDS; b++) add_segment(f, b, D.bb[b], D.bb[b + 1]);
+        for (int s = 0; s <= MB_NUM_MEL_FILTERS; s++) add_segment(f, MB_NUM_BARK_BANDS + s, D.mel[s], D.mel[s + 1]);
+    }
+    for (int i = F * MB_WARP_SEGMENTS; i <= MB_MF_MAX_SEGMENTS; i++) W.seg_ptr[i] = (short)n_items;
+    if (overflow) W.n_pieces = MB_MF_MAX_PIECES + 1;
 }
 
 void offset_outputs(mb_outputs &o, const mb_outputs &base, int64_t frame0, int N) {
@@ -570,6 +643,28 @@ mb_status mb_plan_create(mb_plan **plan, int device, int buffer_size, int hop, d
             p->kernel_name = "warp2048";
         }
     }
+    D.warp_mf_tables = nullptr;
+    if ((N == 512 || N == 1024) && !D.exact && !(flags & MB_FLAG_GENERIC_KERNEL)) {
+        MbWarpMfTables *W = new MbWarpMfTables();
+        build_warp_mf_tables(*W, D);
+        const bool fits = W->n_pieces <= MB_MF_MAX_PIECES && (size_t)prop.sharedMemPerBlockOptin >= mb_warpmf_smem_bytes();
+        cudaError_t we = cudaSuccess;
+        if (fits) {
+            we = cudaMalloc((void **)&p->d_warp_mf_tables, sizeof(MbWarpMfTables));
+            if (we == cudaSuccess) we = cudaMemcpy(p->d_warp_mf_tables, W, sizeof(MbWarpMfTables), cudaMemcpyHostToDevice);
+        }
+        delete W;
+        if (we != cudaSuccess) {
+            mb_status st = fail(MB_ERR_CUDA, "warp-kernel table upload failed: %s", cudaGetErrorString(we));
+            mb_plan_destroy(p);
+            return st;
+        }
+        if (fits) {
+            D.warp_mf_tables = p->d_warp_mf_tables;
+            p->has_mf_kernel = true;
+            p->kernel_name = N == 512 ? "warpmf512" : "warpmf1024";
+        }
+    }
     p->bytes_per_frame = 0;
     for (int i = 0; i < kNumFields; i++)
         if (mb_has(feature_mask, kFields[i].feature)) p->bytes_per_frame += 4 * (int64_t)field_elems(kFields[i], N);
@@ -590,6 +685,7 @@ void mb_plan_destroy(mb_plan *p) {
     cudaFree(p->d_tw_exact);
     cudaFree(p->d_mel_w_exact);
     cudaFree(p->d_warp_tables);
+    cudaFree(p->d_warp_mf_tables);
     cudaFree(p->d_tab);
     if (p->h_tab) cudaFreeHost(p->h_tab);
     if (p->tab_event) cudaEventDestroy(p->tab_event);

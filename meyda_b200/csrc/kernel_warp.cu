@@ -515,16 +515,20 @@ mb_warp2048_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
                         const float4 t = *reinterpret_cast<const float4 *>(slot + kAmpStride * lane + 4 * q);
                         ab[4 * q] = t.x; ab[4 * q + 1] = t.y; ab[4 * q + 2] = t.z; ab[4 * q + 3] = t.w;
                     }
-                    // One sequential pass per lane over its 32 bins: running sums of a, p = a^2 and i p (i = the
-                    // bin's position in the lane) since the last boundary, flushed into a piece at every boundary.
+                    // One sequential pass per lane over its 32 bins: running sums of a, p = a^2 and w p (w = bins
+                    // since the piece began) since the last boundary, flushed into a piece at every boundary.
                     // Only additions of non-negative terms: a silent band next to a loud bin keeps its value.
                     // (float32 is enough: at most 32 non-negative terms per piece.)  The lane's pieces have
                     // consecutive ids (head first), and the pass is branch-free: boundaries sit at different
                     // positions in every lane, so a branch per boundary would run the flush ~30 times per warp.
                     // A flush is a predicated store, and the restart is folded into the next accumulation
                     // (r * keep + x with keep 0 or 1; r is finite unless the whole frame is NaN anyway).
-                    float4 *piece = reinterpret_cast<float4 *>(slot + kPieceOff);  // [kPieces]: {sum a, sum p, sum i p, -}
+                    float4 *piece = reinterpret_cast<float4 *>(slot + kPieceOff);  // [kPieces]: {sum a, sum p, sum w p, -}
                     float ra = 0.f, rp = 0.f, rr = 0.f;
+                    // k-weights count from the piece's own first bin: a strong bin that opens a mel segment then
+                    // weighs exactly 0 there (counted from the lane start it left a rounding residue of
+                    // 6e-8 x 17 x its power in a filter that may hold a billion times less)
+                    float wk = -1.f;
                     // Float64 on the otherwise idle DP pipe: sum i^q a over the lane's bins, i = 0..31 (exact
                     // products, compile-time weights).  q = 0 is the lane total the rolloff scan needs (a
                     // discrete output); q = 1..4 become the spectral moments (src/utils.js:1-11) after the
@@ -556,9 +560,10 @@ mb_warp2048_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
                             : "f"(ra), "f"(rp), "f"(rr), "f"(0.f), "r"(bmask), "r"(1u << i)
                             : "memory");
                         const float pf = __fmul_rn(ab[i], ab[i]);
+                        wk = fmaf(wk, keep, keep);  // bins since the piece began: 0 at a boundary, else one more
                         ra = fmaf(ra, keep, ab[i]);
                         rp = fmaf(rp, keep, pf);
-                        rr = fmaf((float)i, pf, rr * keep);
+                        rr = fmaf(wk, pf, rr * keep);
                     }
                     if (want_pieces)
                         asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(paddr), "f"(ra), "f"(rp), "f"(rr), "f"(0.f)
@@ -645,7 +650,7 @@ mb_warp2048_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
                                 const int pc = S.seg_items[it];
                                 const float4 pv = piece[pc];
                                 const float pp = pv.y;
-                                // sum (k - e0) p over the piece (pv.z counts k from the piece's lane start), then its
+                                // sum (k - e0) p over the piece (pv.z counts k from the piece's own first bin, at or after e0: non-negative terms only), then its
                                 // complement (e1 - k) p: both non-negative up to rounding (NaN stays NaN)
                                 float up = fmaf((float)(S.piece_edge[pc] - e0), pp, pv.z) * inv;
                                 up = (up < 0.f) ? 0.f : up;

@@ -25,10 +25,26 @@ struct MbWarpTables {
     uint32_t lane_bmask[32];       // bit i: bin 32*lane + i is a Bark limit or a mel edge
     int lane_slot_base[32];        // number of such boundaries below bin 32*lane
     int lane_seg_start[32];        // largest boundary <= 32*lane
-    int piece_edge[MB_WARP_PIECES];            // the bin a piece's k-weights are measured from (its lane's first bin)
+    int piece_edge[MB_WARP_PIECES];            // the bin a piece's k-weights are measured from (its own first bin)
     int seg_ptr[MB_WARP_SEGMENTS + 1];         // CSR: pieces of band b (0..23) / mel segment s (24 + s)
     unsigned char seg_items[MB_WARP_MAX_ITEMS];
     int n_slots;                   // boundaries below M
+};
+
+// Tables of the multi-frame warp kernel (bufferSize 512 / 1024: F = 2048 / N frames per warp at a time).  Same
+// idea as MbWarpTables with the warp's 1024 bins being F frames back to back: lane L = (frame L / A, row L % A)
+// owns bins [32 (L % A), +32) of its frame; segments are numbered frame-major (f * MB_WARP_SEGMENTS + s).
+#define MB_MF_MAX_PIECES 240
+#define MB_MF_MAX_SEGMENTS (4 * MB_WARP_SEGMENTS)
+#define MB_MF_MAX_ITEMS 640
+struct MbWarpMfTables {
+    float2 tw32[32 * 32];          // [c'][b]: exp(+2 pi i (c' mod A) b / M)
+    uint32_t lane_bmask[32];       // bit i: bin 32 (lane % A) + i of the frame is a Bark limit or a mel edge
+    int lane_slot_base[32];        // boundaries in the lanes below (all frames below included)
+    short piece_edge[MB_MF_MAX_PIECES];  // the frame-local bin a piece's k-weights are measured from
+    short seg_ptr[MB_MF_MAX_SEGMENTS + 1];
+    unsigned short seg_items[MB_MF_MAX_ITEMS];
+    int n_pieces;                  // > MB_MF_MAX_PIECES: does not fit, the plan keeps the generic kernel
 };
 
 // Per-plan constants handed to kernels by value (__grid_constant__).  Tables
@@ -56,6 +72,7 @@ struct MbDevPlan {
     const double *mel_w_exact;  // exact mode: filter f's weights for bins mel[f] .. mel[f+2]-1, (i-lo)/(hi-lo) as doubles
     int mel_w_off[MB_NUM_MEL_FILTERS + 1];  // offsets of each filter's run in mel_w_exact
     const MbWarpTables *warp_tables;  // bufferSize 2048 only, else NULL
+    const MbWarpMfTables *warp_mf_tables;  // bufferSize 512 / 1024 only, else NULL
     int bb[MB_NUM_BARK_BANDS + 1];     // loudness.js:24-45
     int mel[MB_NUM_MEL_FILTERS + 2];   // mfcc.js:31-38
 };

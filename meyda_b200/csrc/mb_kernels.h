@@ -12,6 +12,11 @@ size_t mb_warp2048_smem_bytes();
 cudaError_t mb_launch_warp2048(const MbDevPlan &P, const MbClipTable &T, const float *samples, const mb_outputs &O,
                                int num_sms, cudaStream_t stream);
 
+// Multi-frame warp kernel, bufferSize 512 and 1024 (F = 2048 / N frames per warp at a time), float32 FFT.
+size_t mb_warpmf_smem_bytes();
+cudaError_t mb_launch_warpmf(const MbDevPlan &P, const MbClipTable &T, const float *samples, const mb_outputs &O,
+                             int num_sms, cudaStream_t stream);
+
 // bufferSize 32768, float32 FFT: 16 warps per frame (16 x 1024-point register sub-FFTs + radix-16 combine).
 // Needs 16-byte aligned frames like the warp kernel.
 size_t mb_big32768_smem_bytes();
