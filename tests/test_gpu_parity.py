@@ -382,3 +382,32 @@ def test_ragged_clips_stay_on_the_warp_kernel():
     # and an odd hop
     out, per = run_gpu(clips[1], N, 333)
     verify(out, clips[1], N, 333)
+
+
+@pytest.mark.parametrize("N", [512, 1024])
+def test_multi_frame_warp_kernel_groups(N):
+    """bufferSize 512 / 1024 run 4 / 2 frames per warp at a time: a frame's bits must not depend on its
+    neighbours in the group (partial last groups, groups that straddle clips, frames off the 16-byte grid,
+    one rescaled or NaN frame next to ordinary ones), and the kernel must agree with the oracle."""
+    hop = N // 4
+    lens = [N + hop * 6 + 1, N, N - 1, N + hop, 3 * N + 5, 0, N + 2 * hop + 3]
+    clips = [mo.synth_clip(80 + i, L) for i, L in enumerate(lens)]
+    clips[4] = clips[4].copy()
+    clips[4][N:N + N // 2] *= np.float32(1e-30)   # a stretch the float32 squares would underflow on
+    clips[6] = clips[6].copy()
+    clips[6][N // 2] = np.nan
+    data, off, ln = mb.meyda._normalize_clips(clips)
+    plan = mb.Plan(N, hop, SR)
+    out, per = plan.extract_host(data, off, ln)
+    assert plan.kernel_name == "warpmf%d" % N
+    assert per.tolist() == [mo.num_frames(L, N, hop) for L in lens]
+    # every frame on its own (a launch of one frame = a group of one valid frame) gives the same bits
+    row = 0
+    for c, L in zip(clips, lens):
+        for f in range(mo.num_frames(L, N, hop)):
+            one, _ = plan.extract_host(c[f * hop:f * hop + N].copy(), np.zeros(1, np.int64), np.array([N], np.int64))
+            for k in out:
+                assert np.array_equal(one[k][0], out[k][row], equal_nan=True), (N, k, row)
+            row += 1
+    plan.close()
+    verify(out, [c for c in clips if len(c) >= N], N, hop, max_banded_frac=1.0)
