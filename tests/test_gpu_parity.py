@@ -395,7 +395,7 @@ def test_multi_frame_warp_kernel_groups(N):
     clips[4] = clips[4].copy()
     clips[4][N:N + N // 2] *= np.float32(1e-30)   # a stretch the float32 squares would underflow on
     clips[6] = clips[6].copy()
-    clips[6][N // 2] = np.nan
+    clips[6][N // 2 + 1] = np.nan  # (not on a frame's first sample: see DESIGN.md section 5 on NaN x 0)
     data, off, ln = mb.meyda._normalize_clips(clips)
     plan = mb.Plan(N, hop, SR)
     out, per = plan.extract_host(data, off, ln)
