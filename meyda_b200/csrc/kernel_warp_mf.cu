@@ -141,7 +141,8 @@ __device__ __forceinline__ void fft_frames(float2 (&v)[32], std::integer_sequenc
 
 // kA: rows of 32 bins per frame (bufferSize = 64 kA).  kPcm: 16-bit PCM input converted in the pass-A load
 // (x = s / 32768, exact), as in kernel_warp.cu: bit-identical to the float path on the converted samples.
-template <int kA, bool kPcm>
+// kMask: compile-time feature set (0 = the plan's, at run time), as in kernel_warp.cu.
+template <int kA, bool kPcm, uint32_t kMask>
 __global__ void __launch_bounds__(kThreads, 1)
 mb_warpmf_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ MbClipTable T,
                  const float *__restrict__ samples, const __grid_constant__ mb_outputs O, const int64_t total_chunks) {
@@ -156,7 +157,7 @@ mb_warpmf_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ Mb
     Smem &S = *reinterpret_cast<Smem *>(smem_raw);
     if (smem_u32(smem_raw) & 127u) __trap();
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t mask = P.mask;
+    const uint32_t mask = kMask ? kMask : P.mask;
     const MbWarpMfTables *__restrict__ WT = P.warp_mf_tables;
 
     for (int i = tid; i < kP * kP; i += kThreads) S.tw32[i] = WT->tw32[i];
@@ -727,8 +728,11 @@ cudaError_t mb_launch_warpmf(const MbDevPlan &P, const MbClipTable &T, const flo
                              int num_sms, cudaStream_t stream) {
     const size_t smem = mb_warpmf_smem_bytes();
     const bool pcm = T.pcm_channels > 0;
-    auto kernel = P.N == 1024 ? (pcm ? mb_warpmf_kernel<16, true> : mb_warpmf_kernel<16, false>)
-                              : (pcm ? mb_warpmf_kernel<8, true> : mb_warpmf_kernel<8, false>);
+    const bool full = (P.mask & MB_ALL_FEATURES) == MB_ALL_FEATURES;
+#define MB_PICK(A) (pcm ? (full ? mb_warpmf_kernel<A, true, MB_ALL_FEATURES> : mb_warpmf_kernel<A, true, 0u>) \
+                        : (full ? mb_warpmf_kernel<A, false, MB_ALL_FEATURES> : mb_warpmf_kernel<A, false, 0u>))
+    auto kernel = P.N == 1024 ? MB_PICK(16) : MB_PICK(8);
+#undef MB_PICK
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const int64_t chunks = (T.total_frames + kChunk - 1) / kChunk;
