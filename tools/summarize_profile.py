@@ -7,26 +7,28 @@ out_dir = os.path.join(ROOT, "profiles"); os.makedirs(out_dir, exist_ok=True)
 go = os.path.join(ROOT, "gpurun_out")
 
 # ---- launch list: per-kernel totals and shares
-rows = [r for r in csv.reader(open(os.path.join(go, "launches.csv"))) if r and not r[0].startswith("==")]
-hdr = rows[0]; col = {h: i for i, h in enumerate(hdr)}
-agg = collections.OrderedDict()
-for r in rows[1:]:
-    if len(r) < len(hdr) or r[col["Metric Name"]] != "gpu__time_duration.sum": continue
-    k = r[col["Kernel Name"]]; v = float(r[col["Metric Value"]].replace(",", ""))
-    unit = r[col["Metric Unit"]]
-    v_us = v / 1e3 if unit in ("ns", "nsecond") else (v * 1e3 if unit in ("ms", "msecond") else v)
-    a = agg.setdefault(k, [0, 0.0]); a[0] += 1; a[1] += v_us
-tot = sum(v for _, v in agg.values())
-mine = sum(v for k, (_, v) in agg.items() if "mb_" in k)
-with open(os.path.join(out_dir, f"{tag}_launches_{name}.txt"), "w") as f:
-    f.write("# ncu --metrics gpu__time_duration.sum --clock-control none (cold-cache, serialised: compare SHARES)\n")
-    f.write("# command: python bench.py --clips 600 --steps 1 --warmup 3 --no-e2e --no-cpu-baseline (includes torch's input generation)\n")
-    f.write("%-90s %6s %12s %7s\n" % ("kernel", "count", "total_us", "share"))
-    for k, (n, v) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
-        f.write("%-90s %6d %12.1f %6.2f%%\n" % (k[:90], n, v, 100 * v / tot))
-    f.write("\nmeyda_b200 kernels: %.1f us of %.1f us profiled (%.1f%%); the rest is torch generating the synthetic clips\n" % (mine, tot, 100 * mine / tot))
-    steps = [(k, n, v) for k, (n, v) in agg.items() if "mb_" in k]
-    f.write("share of the feature kernel inside the bench step (only meyda_b200 kernels run in the timed region): %s\n" % ", ".join("%s %.1f%%" % (k.split("(")[0][-40:], 100 * v / mine) for k, n, v in steps))
+if name == "warp2048":  # (the launch list is taken on the headline bench only)
+    rows = [r for r in csv.reader(open(os.path.join(go, "launches.csv"))) if r and not r[0].startswith("==")]
+    hdr = rows[0]; col = {h: i for i, h in enumerate(hdr)}
+    agg = collections.OrderedDict()
+    for r in rows[1:]:
+        if len(r) < len(hdr) or r[col["Metric Name"]] != "gpu__time_duration.sum": continue
+        k = r[col["Kernel Name"]]; v = float(r[col["Metric Value"]].replace(",", ""))
+        unit = r[col["Metric Unit"]]
+        v_us = v / 1e3 if unit in ("ns", "nsecond") else (v * 1e3 if unit in ("ms", "msecond") else v)
+        a = agg.setdefault(k, [0, 0.0]); a[0] += 1; a[1] += v_us
+    tot = sum(v for _, v in agg.values())
+    mine = sum(v for k, (_, v) in agg.items() if "mb_" in k)
+    with open(os.path.join(out_dir, f"{tag}_launches_{name}.txt"), "w") as f:
+        f.write("# ncu --metrics gpu__time_duration.sum --clock-control none (cold-cache, serialised: compare SHARES)\n")
+        f.write("# command: python bench.py --clips 600 --steps 1 --warmup 3 --no-e2e --no-cpu-baseline (includes torch's input generation)\n")
+        f.write("%-90s %6s %12s %7s\n" % ("kernel", "count", "total_us", "share"))
+        for k, (n, v) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+            f.write("%-90s %6d %12.1f %6.2f%%\n" % (k[:90], n, v, 100 * v / tot))
+        f.write("\nmeyda_b200 kernels: %.1f us of %.1f us profiled (%.1f%%); the rest is torch generating the synthetic clips\n" % (mine, tot, 100 * mine / tot))
+        steps = [(k, n, v) for k, (n, v) in agg.items() if "mb_" in k]
+        f.write("share of the feature kernel inside the bench step (only meyda_b200 kernels run in the timed region): %s\n" % ", ".join("%s %.1f%%" % (k.split("(")[0][-40:], 100 * v / mine) for k, n, v in steps))
+
 
 # ---- full capture: headline metrics
 rep = os.path.join(go, f"prof_{name}.ncu-rep")
@@ -51,11 +53,13 @@ with open(os.path.join(out_dir, f"{tag}_ncu_{name}.txt"), "w") as f:
     frames = float(sys.argv[3]) if len(sys.argv) > 3 else None
     if frames:
         dr, dw = float(vals["dram__bytes_read.sum"]), float(vals["dram__bytes_write.sum"])
-        f.write("\nframes in this launch: %d; algorithmic bytes %d x 35,016 = %.3f GB; DRAM traffic %.3f GB (%.3fx)\n" % (
-            frames, frames, frames * 35016 / 1e9, dr + dw, (dr + dw) / (frames * 35016 / 1e9)))
+        bpf = int(sys.argv[4]) if len(sys.argv) > 4 else 35016
+        f.write("\nframes in this launch: %d; algorithmic bytes %d x %d = %.3f GB; DRAM traffic %.3f GB (%.3fx)\n" % (
+            frames, frames, bpf, frames * bpf / 1e9, dr + dw, (dr + dw) / (frames * bpf / 1e9)))
         f.write("warp-instructions per frame: %.0f\n" % (float(vals["smsp__inst_executed.sum"]) / frames))
-        json.dump({"dram_bytes_per_launch": (dr + dw) * 1e9, "frames_per_launch": frames, "kernel": name, "round": tag},
-                  open(os.path.join(out_dir, "traffic.json"), "w"))
+        if name == "warp2048":  # bench.py reads this one for the headline kernel's roofline.traffic
+            json.dump({"dram_bytes_per_launch": (dr + dw) * 1e9, "frames_per_launch": frames, "kernel": name, "round": tag},
+                      open(os.path.join(out_dir, "traffic.json"), "w"))
 # ---- stall / opcode breakdown from the source page
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"], capture_output=True, text=True).stdout
 rows = list(csv.reader(src.splitlines()))
