@@ -1,0 +1,69 @@
+"""Seeded random batches through the tuned kernels: ragged clips, arbitrary hops (aligned or not), frame counts that
+are not multiples of a warp's chunk or group.  Checks that do not need the noise band: frame bookkeeping,
+bit-exact zcr / buffer, spectra and the robust numbers against the oracle, and that a batch equals its clips
+extracted one by one, bit for bit (a frame's bits depend on nothing but its samples)."""
+import numpy as np
+import pytest
+
+import meyda_b200 as mb
+from oracle import c_oracle, meyda_oracle as mo
+from tests import parity
+from tests.test_gpu_parity import SR
+
+pytestmark = pytest.mark.gpu
+
+
+def _cases():
+    rng = np.random.default_rng(20261018)
+    out = []
+    for i in range(36):
+        N = int(rng.choice([512, 1024, 2048]))
+        hop = int(rng.choice([N, N // 2, N // 4, int(rng.integers(1, 2 * N)), 4 * int(rng.integers(1, N // 2))]))
+        lens = [int(rng.integers(0, 6 * N)) for _ in range(int(rng.integers(1, 7)))]
+        out.append(pytest.param(N, hop, lens, i, id="%d-N%d-hop%d-%dclips" % (i, N, hop, len(lens))))
+    return out
+
+
+@pytest.mark.parametrize("N,hop,lens,seed", _cases())
+def test_random_batches(N, hop, lens, seed):
+    clips = [mo.synth_clip(1000 + 17 * seed + j, L) if L else np.zeros(0, np.float32) for j, L in enumerate(lens)]
+    data, off, ln = mb.meyda._normalize_clips(clips)
+    plan = mb.Plan(N, hop, SR)
+    try:
+        out, per = plan.extract_host(data, off, ln)
+        assert plan.kernel_name in ("warp2048", "warpmf512", "warpmf1024")
+        assert per.tolist() == [mo.num_frames(L, N, hop) for L in lens]
+        row = 0
+        for c, L in zip(clips, lens):  # the batch equals its clips one by one
+            nf = mo.num_frames(L, N, hop)
+            if nf == 0:
+                continue
+            one, _ = plan.extract_host(c, np.zeros(1, np.int64), np.array([L], np.int64))
+            for k in out:
+                assert np.array_equal(one[k], out[k][row:row + nf], equal_nan=True), (k, row)
+            row += nf
+    finally:
+        plan.close()
+    kept = [c for c in clips if len(c) >= N]
+    if not kept:
+        assert all(len(v) == 0 for v in out.values())
+        return
+    ref = mo._concat([c_oracle.extract(c, N, hop, SR, "hanning") for c in kept])
+    parity.assert_bits("buffer", out["buffer"], ref["buffer"])
+    assert np.array_equal(out["zcr"].astype(np.int64), ref["zcr"].astype(np.int64))
+    rr, ri = ref["complexSpectrum"]["real"], ref["complexSpectrum"]["imag"]
+    pk = np.sqrt(rr.astype(np.float64) ** 2 + ri.astype(np.float64) ** 2).max(axis=1)
+    parity.assert_spectrum("complexSpectrum.real", out["complex_real"], rr, peak=pk)
+    parity.assert_spectrum("complexSpectrum.imag", out["complex_imag"], ri, peak=pk)
+    parity.assert_spectrum("amplitudeSpectrum", out["amplitude_spectrum"], ref["amplitudeSpectrum"])
+    parity.assert_spectrum("powerSpectrum", out["power_spectrum"], ref["powerSpectrum"])
+    for f, k in (("rms", "rms"), ("energy", "energy"), ("spectral_centroid", "spectralCentroid"),
+                 ("spectral_spread", "spectralSpread"), ("spectral_flatness", "spectralFlatness"),
+                 ("spectral_slope", "spectralSlope"), ("loudness_total", None), ("perceptual_spread", "perceptualSpread"),
+                 ("perceptual_sharpness", "perceptualSharpness")):
+        r = ref["loudness"]["total"] if k is None else ref[k]
+        parity.assert_numbers(f, out[f], r, abs_tol=parity.SLOPE_ABS_TOL if f == "spectral_slope" else None)
+    parity.assert_numbers("mfcc", out["mfcc"], ref["mfcc"])
+    parity.assert_numbers("loudness.specific", out["loudness_specific"], ref["loudness"]["specific"])
+    binhz = SR / (2 * (N // 2 - 1))
+    assert np.array_equal(np.rint(out["spectral_rolloff"] / binhz), np.rint(ref["spectralRolloff"] / binhz))
