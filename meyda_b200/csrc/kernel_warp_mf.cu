@@ -728,11 +728,17 @@ cudaError_t mb_launch_warpmf(const MbDevPlan &P, const MbClipTable &T, const flo
                              int num_sms, cudaStream_t stream) {
     const size_t smem = mb_warpmf_smem_bytes();
     const bool pcm = T.pcm_channels > 0;
-    const bool full = (P.mask & MB_ALL_FEATURES) == MB_ALL_FEATURES;
-#define MB_PICK(A) (pcm ? (full ? mb_warpmf_kernel<A, true, MB_ALL_FEATURES> : mb_warpmf_kernel<A, true, 0u>) \
-                        : (full ? mb_warpmf_kernel<A, false, MB_ALL_FEATURES> : mb_warpmf_kernel<A, false, 0u>))
+    // fixed feature sets: all, and all but the big arrays (the config-3 set of kernel_warp.cu trips a ptxas
+    // register-allocation failure in this kernel -- "register count of 7", the predicate file -- and runs
+    // through the run-time-mask instantiation instead)
+    const uint32_t m = P.mask & MB_ALL_FEATURES;
+    constexpr uint32_t kNoArrays = MB_ALL_FEATURES & ~(MB_FEATURE_BIT(MB_FEAT_BUFFER) | MB_FEATURE_BIT(MB_FEAT_COMPLEX_SPECTRUM) |
+                                                       MB_FEATURE_BIT(MB_FEAT_AMPLITUDE_SPECTRUM) | MB_FEATURE_BIT(MB_FEAT_POWER_SPECTRUM));
+#define MB_PICK2(A, MASK) (pcm ? mb_warpmf_kernel<A, true, MASK> : mb_warpmf_kernel<A, false, MASK>)
+#define MB_PICK(A) (m == MB_ALL_FEATURES ? MB_PICK2(A, MB_ALL_FEATURES) : m == kNoArrays ? MB_PICK2(A, kNoArrays) : MB_PICK2(A, 0u))
     auto kernel = P.N == 1024 ? MB_PICK(16) : MB_PICK(8);
 #undef MB_PICK
+#undef MB_PICK2
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const int64_t chunks = (T.total_frames + kChunk - 1) / kChunk;

@@ -191,6 +191,14 @@ def test_feature_subsets_match_full_run(golden_audio):
         sub, _ = run_gpu(x, 2048, 512, features=feats)
         for k, v in sub.items():
             assert np.array_equal(v, full[k], equal_nan=True), (feats, k)
+    for N in (512, 1024):  # the multi-frame kernel has the same fixed sets
+        full, _ = run_gpu(x, N, N // 2)
+        for feats in (["mfcc", "spectralCentroid", "spectralSpread", "spectralSkewness", "spectralKurtosis"],
+                      [f for f in mb.FEATURES if f not in ("buffer", "complexSpectrum", "amplitudeSpectrum", "powerSpectrum")],
+                      ["mfcc", "zcr"], ["complexSpectrum", "spectralRolloff"]):
+            sub, _ = run_gpu(x, N, N // 2, features=feats)
+            for k, v in sub.items():
+                assert np.array_equal(v, full[k], equal_nan=True), (N, feats, k)
 
 
 def test_device_memory_call_matches_host_call(golden_audio):

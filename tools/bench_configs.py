@@ -13,6 +13,9 @@ dev = torch.device("cuda", 0)
 PER = {"buffer": lambda N: N, "complexSpectrum": lambda N: 2 * N, "amplitudeSpectrum": lambda N: N // 2,
        "powerSpectrum": lambda N: N // 2, "loudness": lambda N: 25, "mfcc": lambda N: 13}
 
+C3 = ["mfcc", "spectralCentroid", "spectralSpread", "spectralSkewness", "spectralKurtosis"]
+C5 = ["amplitudeSpectrum", "spectralRolloff", "spectralFlatness", "spectralSlope"]
+
 def run(name, N, hop, n_clips, clip_len, feats, flags=0, steps=3, pcm16=False):
     g = torch.Generator(device=dev).manual_seed(7)
     x = (torch.rand(n_clips, clip_len, device=dev, generator=g) - 0.5) * 0.5
@@ -45,8 +48,6 @@ def run(name, N, hop, n_clips, clip_len, feats, flags=0, steps=3, pcm16=False):
                       "hbm_frac_of_measured": round(fps * bpf / 1e9 / 6542.7, 4)}), flush=True)
     plan.close(); del x, outs; torch.cuda.empty_cache()
 
-C3 = ["mfcc", "spectralCentroid", "spectralSpread", "spectralSkewness", "spectralKurtosis"]
-C5 = ["amplitudeSpectrum", "spectralRolloff", "spectralFlatness", "spectralSlope"]
 which = sys.argv[1:] or ["c3", "c5", "exact", "sizes", "pcm"]
 if "pcm" in which:
     run("full set, float32 input", 2048, 512, 1500, 441000, mb.FEATURES)
@@ -65,6 +66,10 @@ if "small" in which:  # the reference's own cadence: back-to-back buffers (hop =
         run("full set N=%d hop=N" % N, N, N, 800, 441000, mb.FEATURES)
     run("config-1 features N=512 hop=N", 512, 512, 2000, 441000, ["rms", "energy", "zcr", "amplitudeSpectrum", "spectralCentroid"])
     run("full set exact-FFT N=512 hop=N", 512, 512, 200, 441000, mb.FEATURES, flags=_capi.MB_FLAG_EXACT_FFT)
+    run("config-3 features (mfcc + moments) N=512 hop=N", 512, 512, 3000, 441000, C3)
+    run("config-3 features (mfcc + moments) N=1024 hop=N", 1024, 1024, 3000, 441000, C3)
+    run("full set N=512 hop=N, 3000 clips", 512, 512, 3000, 441000, mb.FEATURES)
+    run("full set N=1024 hop=N, 3000 clips", 1024, 1024, 3000, 441000, mb.FEATURES)
 if "sizes" in which:
     for N in (256, 512, 1024, 4096):
         run("full set N=%d hop=N/4" % N, N, N // 4, 400, 441000, mb.FEATURES)
