@@ -30,8 +30,11 @@
 #include "mb_device.cuh"
 #include "mb_fft.cuh"
 #include "mb_kernels.h"
+#include "mb_warp_common.cuh"
 
 namespace {
+
+using namespace mbwarp;
 
 constexpr int kP = 32;             // points per lane per pass
 constexpr int kM = kP * kP;        // 1024 complex points
@@ -47,7 +50,6 @@ constexpr int kAmpStride = 36;                // floats per lane in the blocked 
 constexpr int kPieceOff = 1152;               // float offset of the piece area (after 32*36 amps)
 constexpr int kPieces = MB_WARP_PIECES;       // 96: 64 boundary pieces + 32 lane heads
 constexpr int kStashRows = 18;                // floats per frame in the scalar stash
-constexpr int kChunk = 32;                    // frames per work unit
 
 static_assert(kPieceOff * 4 + kPieces * 16 <= kSlotFloats * 4, "band pieces must fit the warp slot");
 
@@ -69,76 +71,11 @@ struct Smem {
 static_assert(offsetof(Smem, slot) % 128 == 0 && (kSlotFloats * 4) % 16 == 0, "warp slots must stay 16-byte aligned");
 static_assert(offsetof(Smem, twN) % 8 == 0 && offsetof(Smem, window) % 8 == 0, "float2 tables");
 
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(unsigned long long *bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "MB_WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra MB_DONE_%=;\n\t"
-        "bra MB_WAIT_%=;\n\t"
-        "MB_DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-}
-// TMA bulk copies (1-D): global -> shared with mbarrier completion, shared -> global as a bulk group.
-// L2 policies: a frame's samples are read again by the next three frames (hop 512 of 2048), while the
-// output stream is written once and is 16x larger -- keep the former, let the latter go first.
-__device__ __forceinline__ uint64_t l2_policy_evict_last() {
-    uint64_t p;
-    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
-    return p;
-}
-__device__ __forceinline__ uint64_t l2_policy_evict_first() {
-    uint64_t p;
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
-    return p;
-}
-__device__ __forceinline__ void bulk_load(void *dst_smem, const void *src_gmem, uint32_t bytes, unsigned long long *bar,
-                                          uint64_t policy) {
-    asm volatile(
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
-            smem_u32(dst_smem)),
-        "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
-        : "memory");
-}
-__device__ __forceinline__ void bulk_store(void *dst_gmem, const void *src_smem, uint32_t bytes, uint64_t policy) {
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(dst_gmem),
-                 "r"(smem_u32(src_smem)), "r"(bytes), "l"(policy)
-                 : "memory");
-    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-}
-// streaming store: written once, never read back by this kernel
-__device__ __forceinline__ void st_stream(float *p, float v) { __stcs(p, v); }
-__device__ __forceinline__ void bulk_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void bulk_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-
 // ---- 32-point FFT in registers (mb_fft.cuh): natural order in, X[k] left in v[brev5(k)].
 __device__ __forceinline__ void fft32(float2 (&v)[32]) { mbfft::fft_reg<32>(v); }
 __host__ __device__ constexpr int brev5(int k) { return mbfft::brev<5>(k); }
 
 __device__ __forceinline__ double warp_sum_d(double v) { return mb_warp_sum(v); }
-
-// One MUFU each, <= 1 ulp.  .ftz: the arguments are |Z|^2 and |Z| of a frame whose samples were brought
-// into [2^-40, 2^40] (see kscale), so a subnormal argument is 2^-86 below the frame's scale: flushing it
-// to zero changes nothing that float32 could have resolved.  0 -> 0 / -inf, NaN -> NaN.
-__device__ __forceinline__ float sqrt_approx(float x) {
-    float r;
-    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-    return r;
-}
-__device__ __forceinline__ float log2_approx(float x) {
-    float r;
-    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-    return r;
-}
 
 // Sums four doubles across the warp with 6 shuffle steps instead of 20: the first two steps fold the four
 // values onto lane bits 4 and 3 (a lane keeps one value of a pair and hands over the other), the last three
@@ -152,14 +89,6 @@ __device__ __forceinline__ double warp_sum4_d(double a0, double a1, double a2, d
     c += __shfl_xor_sync(0xffffffffu, c, 2);
     c += __shfl_xor_sync(0xffffffffu, c, 1);
     return c;
-}
-
-__device__ __forceinline__ void stash_put_d(float (*st)[kChunk], int row, int col, double v) {
-    st[row][col] = __int_as_float(__double2hiint(v));
-    st[row + 1][col] = __int_as_float(__double2loint(v));
-}
-__device__ __forceinline__ double stash_get_d(float (*st)[kChunk], int row, int col) {
-    return __hiloint2double(__float_as_int(st[row][col]), __float_as_int(st[row + 1][col]));
 }
 
 // kMask: a compile-time feature set (0 = take the plan's at run time).  With the set known the per-bin feature

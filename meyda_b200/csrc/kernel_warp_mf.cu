@@ -21,8 +21,11 @@
 #include "mb_device.cuh"
 #include "mb_fft.cuh"
 #include "mb_kernels.h"
+#include "mb_warp_common.cuh"
 
 namespace {
+
+using namespace mbwarp;
 
 constexpr int kP = 32;
 constexpr int kPts = kP * kP;  // complex points per warp per group: F frames x M
@@ -34,7 +37,6 @@ constexpr int kAmpStride = 36;
 constexpr int kPieceOff = 1152;
 constexpr int kMaxPieces = MB_MF_MAX_PIECES;  // 240 float4 after the blocked amplitudes
 constexpr int kStashRows = 18;
-constexpr int kChunk = 32;
 static_assert(kPieceOff + 4 * kMaxPieces <= kSlotFloats, "pieces must fit the slot");
 
 struct Smem {
@@ -53,69 +55,7 @@ struct Smem {
 };
 static_assert(offsetof(Smem, slot) % 128 == 0 && (kSlotFloats * 4) % 16 == 0, "warp slots must stay 16-byte aligned");
 
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long *bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "MBF_WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra MBF_DONE_%=;\n\t"
-        "bra MBF_WAIT_%=;\n\t"
-        "MBF_DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-}
-__device__ __forceinline__ uint64_t l2_policy_evict_last() {
-    uint64_t p;
-    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
-    return p;
-}
-__device__ __forceinline__ uint64_t l2_policy_evict_first() {
-    uint64_t p;
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
-    return p;
-}
-__device__ __forceinline__ void bulk_load(void *dst_smem, const void *src_gmem, uint32_t bytes, unsigned long long *bar,
-                                          uint64_t policy) {
-    asm volatile(
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
-            smem_u32(dst_smem)),
-        "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
-        : "memory");
-}
-__device__ __forceinline__ void bulk_store(void *dst_gmem, const void *src_smem, uint32_t bytes, uint64_t policy) {
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(dst_gmem),
-                 "r"(smem_u32(src_smem)), "r"(bytes), "l"(policy)
-                 : "memory");
-    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-}
-__device__ __forceinline__ void st_stream(float *p, float v) { __stcs(p, v); }
-__device__ __forceinline__ void bulk_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void bulk_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ float sqrt_approx(float x) {
-    float r;
-    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-    return r;
-}
-__device__ __forceinline__ float log2_approx(float x) {
-    float r;
-    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-    return r;
-}
 __host__ __device__ constexpr int brev5(int k) { return mbfft::brev<5>(k); }
-__device__ __forceinline__ void stash_put_d(float (*st)[kChunk], int row, int col, double v) {
-    st[row][col] = __int_as_float(__double2hiint(v));
-    st[row + 1][col] = __int_as_float(__double2loint(v));
-}
-__device__ __forceinline__ double stash_get_d(float (*st)[kChunk], int row, int col) {
-    return __hiloint2double(__float_as_int(st[row][col]), __float_as_int(st[row + 1][col]));
-}
 // sums inside aligned groups of G lanes
 template <int G>
 __device__ __forceinline__ double group_sum_d(double v) {
