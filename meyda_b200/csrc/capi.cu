@@ -396,7 +396,8 @@ void build_warp_mf_tables(MbWarpMfTables &W, const MbDevPlan &D) {
         if (e < M) below.push_back(e);
     const int nb = (int)below.size();
     W.n_pieces = F * (A + nb);
-    if (W.n_pieces > MB_MF_MAX_PIECES || below.empty() || below[0] != 0) {
+    const int piece_cap = A == 4 ? MB_MF_MAX_PIECES : 256;  // what the warp's slot holds (12- / 16-byte pieces)
+    if (W.n_pieces > piece_cap || below.empty() || below[0] != 0) {
         W.n_pieces = MB_MF_MAX_PIECES + 1;  // signals "does not fit" to the caller
         return;
     }
@@ -644,7 +645,7 @@ mb_status mb_plan_create(mb_plan **plan, int device, int buffer_size, int hop, d
         }
     }
     D.warp_mf_tables = nullptr;
-    if ((N == 512 || N == 1024) && !D.exact && !(flags & MB_FLAG_GENERIC_KERNEL)) {
+    if ((N == 256 || N == 512 || N == 1024) && !D.exact && !(flags & MB_FLAG_GENERIC_KERNEL)) {
         MbWarpMfTables *W = new MbWarpMfTables();
         build_warp_mf_tables(*W, D);
         const bool fits = W->n_pieces <= MB_MF_MAX_PIECES && (size_t)prop.sharedMemPerBlockOptin >= mb_warpmf_smem_bytes();
@@ -662,7 +663,7 @@ mb_status mb_plan_create(mb_plan **plan, int device, int buffer_size, int hop, d
         if (fits) {
             D.warp_mf_tables = p->d_warp_mf_tables;
             p->has_mf_kernel = true;
-            p->kernel_name = N == 512 ? "warpmf512" : "warpmf1024";
+            p->kernel_name = N == 256 ? "warpmf256" : N == 512 ? "warpmf512" : "warpmf1024";
         }
     }
     p->bytes_per_frame = 0;

@@ -32,12 +32,15 @@ constexpr int kPts = kP * kP;  // complex points per warp per group: F frames x 
 constexpr int kWarps = 16;
 constexpr int kThreads = kWarps * 32;
 constexpr int kRow = kP + 1;
-constexpr int kSlotFloats = 2 * kP * kRow;  // 2112 floats per warp
+constexpr int kSlotFloats = 2176;  // per warp: >= the 32 x 33 float2 transpose, F (M + 8) float2 spectra, amplitudes + pieces
 constexpr int kAmpStride = 36;
 constexpr int kPieceOff = 1152;
-constexpr int kMaxPieces = MB_MF_MAX_PIECES;  // 240 float4 after the blocked amplitudes
+constexpr int kMaxPieces = MB_MF_MAX_PIECES;
 constexpr int kStashRows = 18;
-static_assert(kPieceOff + 4 * kMaxPieces <= kSlotFloats, "pieces must fit the slot");
+// pieces follow the blocked amplitudes: {sum a, sum p, sum w p} as a float4 (one 16-byte store per flush), or packed
+// as three floats at bufferSize 256, where eight frames need 336 of them
+static_assert(kSlotFloats >= 2 * kP * kRow && kPieceOff + 4 * 256 <= kSlotFloats && kPieceOff + 3 * kMaxPieces <= kSlotFloats,
+              "slot layout");
 
 struct Smem {
     float2 tw32[kP * kP];  // [c'][b]: exp(+2 pi i p b / M), p = c' mod A
@@ -90,8 +93,9 @@ mb_warpmf_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ Mb
     constexpr int kM = 32 * kA;        // complex points = amplitude bins per frame
     constexpr int kN = 2 * kM;         // bufferSize
     constexpr int kMs = kM + 8;        // float2 stride between the frames' spectra in the slot
-    constexpr int kABits = kA == 16 ? 4 : 3;
-    static_assert(kA == 16 || kA == 8, "bufferSize 1024 or 512");
+    constexpr int kABits = kA == 16 ? 4 : kA == 8 ? 3 : 2;
+    constexpr int kPf = kA == 4 ? 3 : 4;  // floats per piece
+    static_assert(kA == 16 || kA == 8 || kA == 4, "bufferSize 1024, 512 or 256");
     static_assert(2 * (kF * kMs) <= kSlotFloats, "spectra must fit the slot");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Smem &S = *reinterpret_cast<Smem *>(smem_raw);
@@ -456,14 +460,14 @@ mb_warpmf_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ Mb
                         const float4 t = *reinterpret_cast<const float4 *>(slot + kAmpStride * lane + 4 * q);
                         ab[4 * q] = t.x; ab[4 * q + 1] = t.y; ab[4 * q + 2] = t.z; ab[4 * q + 3] = t.w;
                     }
-                    float4 *piece = reinterpret_cast<float4 *>(slot + kPieceOff);
+                    float *piece = slot + kPieceOff;  // piece id -> piece + kPf * id: {sum a, sum p, sum w p}
                     float ra = 0.f, rp = 0.f, rr = 0.f;
                     // k-weights count from the piece's own first bin: a strong bin that opens a mel segment then
                     // weighs exactly 0 there (counted from the lane start it left a rounding residue of
                     // 6e-8 x 17 x its power in a filter that may hold a billion times less)
                     float wk = -1.f;
                     double ta = 0, t1 = 0, t2 = 0, t3 = 0, t4 = 0;
-                    uint32_t paddr = smem_u32(piece + (slot_base + lane));
+                    uint32_t paddr = smem_u32(piece + kPf * (slot_base + lane));
 #pragma unroll
                     for (int i = 0; i < 32; i++) {
                         if (want_moments || want_rolloff) {
@@ -478,25 +482,46 @@ mb_warpmf_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ Mb
                         }
                         if (!want_pieces) continue;
                         float keep;
-                        asm volatile(
-                            "{\n\t.reg .pred p;\n\t.reg .b32 t;\n\t"
-                            "and.b32 t, %6, %7;\n\t"
-                            "setp.ne.u32 p, t, 0;\n\t"
-                            "@p st.shared.v4.f32 [%1], {%2, %3, %4, %5};\n\t"
-                            "@p add.u32 %1, %1, 16;\n\t"
-                            "selp.f32 %0, 0f00000000, 0f3F800000, p;\n\t}"
-                            : "=f"(keep), "+r"(paddr)
-                            : "f"(ra), "f"(rp), "f"(rr), "f"(0.f), "r"(bmask), "r"(1u << i)
-                            : "memory");
+                        if constexpr (kPf == 4) {
+                            asm volatile(
+                                "{\n\t.reg .pred p;\n\t.reg .b32 t;\n\t"
+                                "and.b32 t, %6, %7;\n\t"
+                                "setp.ne.u32 p, t, 0;\n\t"
+                                "@p st.shared.v4.f32 [%1], {%2, %3, %4, %5};\n\t"
+                                "@p add.u32 %1, %1, 16;\n\t"
+                                "selp.f32 %0, 0f00000000, 0f3F800000, p;\n\t}"
+                                : "=f"(keep), "+r"(paddr)
+                                : "f"(ra), "f"(rp), "f"(rr), "f"(0.f), "r"(bmask), "r"(1u << i)
+                                : "memory");
+                        } else {
+                            asm volatile(
+                                "{\n\t.reg .pred p;\n\t.reg .b32 t;\n\t"
+                                "and.b32 t, %5, %6;\n\t"
+                                "setp.ne.u32 p, t, 0;\n\t"
+                                "@p st.shared.f32 [%1], %2;\n\t"
+                                "@p st.shared.f32 [%1+4], %3;\n\t"
+                                "@p st.shared.f32 [%1+8], %4;\n\t"
+                                "@p add.u32 %1, %1, 12;\n\t"
+                                "selp.f32 %0, 0f00000000, 0f3F800000, p;\n\t}"
+                                : "=f"(keep), "+r"(paddr)
+                                : "f"(ra), "f"(rp), "f"(rr), "r"(bmask), "r"(1u << i)
+                                : "memory");
+                        }
                         const float pf = __fmul_rn(ab[i], ab[i]);
                         wk = fmaf(wk, keep, keep);  // bins since the piece began: 0 at a boundary, else one more
                         ra = fmaf(ra, keep, ab[i]);
                         rp = fmaf(rp, keep, pf);
                         rr = fmaf(wk, pf, rr * keep);
                     }
-                    if (want_pieces)
-                        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(paddr), "f"(ra), "f"(rp), "f"(rr), "f"(0.f)
-                                     : "memory");
+                    if (want_pieces) {
+                        if constexpr (kPf == 4)
+                            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(paddr), "f"(ra), "f"(rp), "f"(rr), "f"(0.f)
+                                         : "memory");
+                        else
+                            asm volatile("st.shared.f32 [%0], %1;\n\tst.shared.f32 [%0+4], %2;\n\tst.shared.f32 [%0+8], %3;" ::"r"(paddr),
+                                         "f"(ra), "f"(rp), "f"(rr)
+                                         : "memory");
+                    }
                     if (want_moments) {
                         const double c = (double)(32 * lp), c2 = c * c;  // bins counted inside the lane's own frame
                         const double s1 = fma(c, ta, t1);
@@ -562,7 +587,7 @@ mb_warpmf_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ Mb
                                 const int f = seg / MB_NUM_BARK_BANDS, bnd = seg % MB_NUM_BARK_BANDS;
                                 const int ts = f * MB_WARP_SEGMENTS + bnd;
                                 float bsum = 0.f;
-                                for (int it = S.seg_ptr[ts]; it < S.seg_ptr[ts + 1]; it++) bsum += piece[S.seg_items[it]].x;
+                                for (int it = S.seg_ptr[ts]; it < S.seg_ptr[ts + 1]; it++) bsum += piece[kPf * S.seg_items[it]];
                                 const float sp = powf(bsum, 0.23f);
                                 sp_s[seg] = sp;
                                 if (mb_has(mask, MB_FEAT_LOUDNESS) && f < nfg) O.loudness_specific[g * MB_NUM_BARK_BANDS + seg] = sp;
@@ -592,9 +617,8 @@ mb_warpmf_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ Mb
                                 float rise = 0.f, fall = 0.f;
                                 for (int it = S.seg_ptr[ts]; it < S.seg_ptr[ts + 1]; it++) {
                                     const int pc = S.seg_items[it];
-                                    const float4 pv = piece[pc];
-                                    const float pp = pv.y;
-                                    float up = fmaf((float)((int)S.piece_edge[pc] - e0), pp, pv.z) * inv;
+                                    const float pp = piece[kPf * pc + 1], pz = piece[kPf * pc + 2];
+                                    float up = fmaf((float)((int)S.piece_edge[pc] - e0), pp, pz) * inv;
                                     up = (up < 0.f) ? 0.f : up;
                                     rise += up;
                                     fall += fmaxf(pp - up, 0.f);
@@ -676,7 +700,8 @@ cudaError_t mb_launch_warpmf(const MbDevPlan &P, const MbClipTable &T, const flo
                                                        MB_FEATURE_BIT(MB_FEAT_AMPLITUDE_SPECTRUM) | MB_FEATURE_BIT(MB_FEAT_POWER_SPECTRUM));
 #define MB_PICK2(A, MASK) (pcm ? mb_warpmf_kernel<A, true, MASK> : mb_warpmf_kernel<A, false, MASK>)
 #define MB_PICK(A) (m == MB_ALL_FEATURES ? MB_PICK2(A, MB_ALL_FEATURES) : m == kNoArrays ? MB_PICK2(A, kNoArrays) : MB_PICK2(A, 0u))
-    auto kernel = P.N == 1024 ? MB_PICK(16) : MB_PICK(8);
+    auto kernel = P.N == 1024 ? MB_PICK(16) : P.N == 512 ? MB_PICK(8)
+                  : (m == MB_ALL_FEATURES ? MB_PICK2(4, MB_ALL_FEATURES) : MB_PICK2(4, 0u));
 #undef MB_PICK
 #undef MB_PICK2
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -31,12 +31,12 @@ struct MbWarpTables {
     int n_slots;                   // boundaries below M
 };
 
-// Tables of the multi-frame warp kernel (bufferSize 512 / 1024: F = 2048 / N frames per warp at a time).  Same
+// Tables of the multi-frame warp kernel (bufferSize 256 / 512 / 1024: F = 2048 / N frames per warp at a time).  Same
 // idea as MbWarpTables with the warp's 1024 bins being F frames back to back: lane L = (frame L / A, row L % A)
 // owns bins [32 (L % A), +32) of its frame; segments are numbered frame-major (f * MB_WARP_SEGMENTS + s).
-#define MB_MF_MAX_PIECES 240
-#define MB_MF_MAX_SEGMENTS (4 * MB_WARP_SEGMENTS)
-#define MB_MF_MAX_ITEMS 640
+#define MB_MF_MAX_PIECES 340  // (256 when a piece is a float4: bufferSize 512 / 1024; three floats at 256)
+#define MB_MF_MAX_SEGMENTS (8 * MB_WARP_SEGMENTS)
+#define MB_MF_MAX_ITEMS 1024
 struct MbWarpMfTables {
     float2 tw32[32 * 32];          // [c'][b]: exp(+2 pi i (c' mod A) b / M)
     uint32_t lane_bmask[32];       // bit i: bin 32 (lane % A) + i of the frame is a Bark limit or a mel edge
@@ -72,7 +72,7 @@ struct MbDevPlan {
     const double *mel_w_exact;  // exact mode: filter f's weights for bins mel[f] .. mel[f+2]-1, (i-lo)/(hi-lo) as doubles
     int mel_w_off[MB_NUM_MEL_FILTERS + 1];  // offsets of each filter's run in mel_w_exact
     const MbWarpTables *warp_tables;  // bufferSize 2048 only, else NULL
-    const MbWarpMfTables *warp_mf_tables;  // bufferSize 512 / 1024 only, else NULL
+    const MbWarpMfTables *warp_mf_tables;  // bufferSize 256 / 512 / 1024 only, else NULL
     int bb[MB_NUM_BARK_BANDS + 1];     // loudness.js:24-45
     int mel[MB_NUM_MEL_FILTERS + 2];   // mfcc.js:31-38
 };

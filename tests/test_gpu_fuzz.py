@@ -17,7 +17,7 @@ def _cases():
     rng = np.random.default_rng(20261018)
     out = []
     for i in range(36):
-        N = int(rng.choice([512, 1024, 2048]))
+        N = int(rng.choice([256, 512, 1024, 2048]))
         hop = int(rng.choice([N, N // 2, N // 4, int(rng.integers(1, 2 * N)), 4 * int(rng.integers(1, N // 2))]))
         lens = [int(rng.integers(0, 6 * N)) for _ in range(int(rng.integers(1, 7)))]
         out.append(pytest.param(N, hop, lens, i, id="%d-N%d-hop%d-%dclips" % (i, N, hop, len(lens))))
@@ -31,7 +31,7 @@ def test_random_batches(N, hop, lens, seed):
     plan = mb.Plan(N, hop, SR)
     try:
         out, per = plan.extract_host(data, off, ln)
-        assert plan.kernel_name in ("warp2048", "warpmf512", "warpmf1024")
+        assert plan.kernel_name in ("warp2048", "warpmf256", "warpmf512", "warpmf1024")
         assert per.tolist() == [mo.num_frames(L, N, hop) for L in lens]
         row = 0
         for c, L in zip(clips, lens):  # the batch equals its clips one by one
@@ -63,7 +63,7 @@ def test_random_batches(N, hop, lens, seed):
                  ("perceptual_sharpness", "perceptualSharpness")):
         r = ref["loudness"]["total"] if k is None else ref[k]
         parity.assert_numbers(f, out[f], r, abs_tol=parity.SLOPE_ABS_TOL if f == "spectral_slope" else None)
-    parity.assert_numbers("mfcc", out["mfcc"], ref["mfcc"])
+    parity.assert_numbers("mfcc", out["mfcc"], ref["mfcc"])  # (+-Infinity at bufferSize 256: positions and signs must match)
     parity.assert_numbers("loudness.specific", out["loudness_specific"], ref["loudness"]["specific"])
     binhz = SR / (2 * (N // 2 - 1))
     assert np.array_equal(np.rint(out["spectral_rolloff"] / binhz), np.rint(ref["spectralRolloff"] / binhz))

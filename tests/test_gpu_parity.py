@@ -191,7 +191,7 @@ def test_feature_subsets_match_full_run(golden_audio):
         sub, _ = run_gpu(x, 2048, 512, features=feats)
         for k, v in sub.items():
             assert np.array_equal(v, full[k], equal_nan=True), (feats, k)
-    for N in (512, 1024):  # the multi-frame kernel has the same fixed sets
+    for N in (256, 512, 1024):  # the multi-frame kernel has fixed sets too
         full, _ = run_gpu(x, N, N // 2)
         for feats in (["mfcc", "spectralCentroid", "spectralSpread", "spectralSkewness", "spectralKurtosis"],
                       [f for f in mb.FEATURES if f not in ("buffer", "complexSpectrum", "amplitudeSpectrum", "powerSpectrum")],
@@ -392,9 +392,9 @@ def test_ragged_clips_stay_on_the_warp_kernel():
     verify(out, clips[1], N, 333)
 
 
-@pytest.mark.parametrize("N", [512, 1024])
+@pytest.mark.parametrize("N", [256, 512, 1024])
 def test_multi_frame_warp_kernel_groups(N):
-    """bufferSize 512 / 1024 run 4 / 2 frames per warp at a time: a frame's bits must not depend on its
+    """bufferSize 256 / 512 / 1024 run 8 / 4 / 2 frames per warp at a time: a frame's bits must not depend on its
     neighbours in the group (partial last groups, groups that straddle clips, frames off the 16-byte grid,
     one rescaled or NaN frame next to ordinary ones), and the kernel must agree with the oracle."""
     hop = N // 4
