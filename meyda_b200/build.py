@@ -38,17 +38,23 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not _stale():
         return LIB
     os.makedirs(LIB_DIR, exist_ok=True)
-    objs = []
-    for src in SOURCES:
+    def compile_one(src):
         obj = os.path.join(LIB_DIR, src.replace(".cu", ".o"))
         cmd = [nvcc()] + [f for f in NVCC_FLAGS if f != "--use_fast_math=false"] + ["-c", os.path.join(CSRC, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
+        with open(os.path.join(LIB_DIR, src.replace(".cu", ".ptxas.txt")), "w") as f:
+            f.write(r.stderr)
+        return src, obj, r
+
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 1)) as pool:  # one nvcc per source file
+        results = list(pool.map(compile_one, SOURCES))
+    objs = []
+    for src, obj, r in results:
         if verbose or r.returncode:
             sys.stderr.write(r.stdout + r.stderr)
         if r.returncode:
             raise RuntimeError("nvcc failed on %s" % src)
-        with open(os.path.join(LIB_DIR, src.replace(".cu", ".ptxas.txt")), "w") as f:
-            f.write(r.stderr)
         objs.append(obj)
     cmd = [nvcc(), "-shared", "-o", LIB] + objs + ["-lcudart_static", "-lpthread", "-ldl", "-lrt"]
     r = subprocess.run(cmd, capture_output=True, text=True)
