@@ -375,7 +375,7 @@ void build_warp_tables(MbWarpTables &W, const MbDevPlan &D) {
     if (n_items >= MB_WARP_MAX_ITEMS) W.n_slots = MB_WARP_MAX_SLOTS + 1;
 }
 
-// The same bookkeeping for the multi-frame warp kernel (bufferSize 512 / 1024): the warp's 32 lanes are F frames
+// The same bookkeeping for the multi-frame warp kernel (bufferSize 256 / 512 / 1024): the warp's 32 lanes are F frames
 // of A = M / 32 lanes each; a lane's pieces are consecutive (head first), lanes in order, so piece ids run
 // frame-major.  Segments: f * MB_WARP_SEGMENTS + (band b | 24 + mel segment s).
 void build_warp_mf_tables(MbWarpMfTables &W, const MbDevPlan &D) {

@@ -1,7 +1,7 @@
-// kernel_warp_mf.cu -- warp kernel for bufferSize 512 and 1024 (the reference's own default sizes), float32 FFT.
+// kernel_warp_mf.cu -- warp kernel for bufferSize 256, 512 and 1024 (the reference's own default sizes), float32 FFT.
 //
 // Same machinery as kernel_warp.cu (bufferSize 2048), with F = 2048 / N frames transformed by a warp at a time:
-// the warp's 1024 complex points are F packed frames of M = N/2 = 32 A points each (A = 16 or 8).
+// the warp's 1024 complex points are F packed frames of M = N/2 = 32 A points each (A = 16, 8 or 4).
 //   pass A  lane b holds z_f[32 a + b], a < A, for every frame f: F register FFTs of A points per lane;
 //   pass B  after a twiddle and a transpose through the warp's slot, lane f A + p holds row p of frame f and
 //           runs ONE 32-point register FFT -> X_f[p + A q], q < 32 (the 2048 kernel's pass 2, unchanged);

@@ -12,7 +12,7 @@ size_t mb_warp2048_smem_bytes();
 cudaError_t mb_launch_warp2048(const MbDevPlan &P, const MbClipTable &T, const float *samples, const mb_outputs &O,
                                int num_sms, cudaStream_t stream);
 
-// Multi-frame warp kernel, bufferSize 512 and 1024 (F = 2048 / N frames per warp at a time), float32 FFT.
+// Multi-frame warp kernel, bufferSize 256, 512 and 1024 (F = 2048 / N frames per warp at a time), float32 FFT.
 size_t mb_warpmf_smem_bytes();
 cudaError_t mb_launch_warpmf(const MbDevPlan &P, const MbClipTable &T, const float *samples, const mb_outputs &O,
                              int num_sms, cudaStream_t stream);
