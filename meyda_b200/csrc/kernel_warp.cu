@@ -552,7 +552,7 @@ mb_warp2048_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
                         if (lane < MB_NUM_BARK_BANDS) {
                             float bsum = 0.f;
                             for (int it = S.seg_ptr[lane]; it < S.seg_ptr[lane + 1]; it++) bsum += piece[S.seg_items[it]].x;
-                            sp = powf(bsum, 0.23f);
+                            sp = pow023_approx(bsum);
                             if (mb_has(mask, MB_FEAT_LOUDNESS)) O.loudness_specific[g * MB_NUM_BARK_BANDS + lane] = sp;
                         }
                         const float total = mb_warp_sum(sp);
@@ -588,7 +588,7 @@ mb_warp2048_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
                             }
                         }
                         const float fall_next = __shfl_down_sync(0xffffffffu, fall, 1);
-                        const float lgE = logf(rise + fall_next);  // lanes >= 26 are not used below
+                        const float lgE = ln_approx(rise + fall_next);  // lanes >= 26 are not used below
                         // 13 x 26 DCT on 26 lanes: lane k + 13 h sums filters 13 h .. 13 h + 12 of coefficient k
                         float acc = 0.f;
                         const int half = lane >= MB_NUM_MFCC ? MB_NUM_MFCC : 0;

@@ -588,7 +588,7 @@ mb_warpmf_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ Mb
                                 const int ts = f * MB_WARP_SEGMENTS + bnd;
                                 float bsum = 0.f;
                                 for (int it = S.seg_ptr[ts]; it < S.seg_ptr[ts + 1]; it++) bsum += piece[kPf * S.seg_items[it]];
-                                const float sp = powf(bsum, 0.23f);
+                                const float sp = pow023_approx(bsum);
                                 sp_s[seg] = sp;
                                 if (mb_has(mask, MB_FEAT_LOUDNESS) && f < nfg) O.loudness_specific[g * MB_NUM_BARK_BANDS + seg] = sp;
                             }
@@ -632,7 +632,7 @@ mb_warpmf_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ Mb
                             const int idx = it0 + lane;
                             if (idx < MB_NUM_MEL_FILTERS * kF) {
                                 const int f = idx / MB_NUM_MEL_FILTERS, m = idx % MB_NUM_MEL_FILTERS;
-                                lge_s[idx] = logf(rise_s[f * (MB_NUM_MEL_FILTERS + 1) + m] + fall_s[f * (MB_NUM_MEL_FILTERS + 1) + m + 1]);
+                                lge_s[idx] = ln_approx(rise_s[f * (MB_NUM_MEL_FILTERS + 1) + m] + fall_s[f * (MB_NUM_MEL_FILTERS + 1) + m + 1]);
                             }
                         }
                         __syncwarp();
