@@ -267,6 +267,12 @@ int64_t mb_stream_frames_after(const mb_stream *stream, int64_t n_new_samples);
 mb_status mb_stream_push(mb_stream *stream, const float *new_samples, int64_t n_new_samples,
                          const mb_outputs *out, int mem_kind, int64_t *frames_done);
 mb_status mb_stream_reset(mb_stream *stream);
+/* The same for 16-bit PCM blocks (what a capture device or a WAV reader hands over): the stream keeps int16 sample
+ * frames (`channels` interleaved) on the device and the kernels convert on load, as mb_extract_pcm16 does.
+ * n_new_sample_frames counts frames of `channels` samples. */
+mb_status mb_stream_create_pcm16(mb_stream **stream, mb_plan *plan, int channels, int channel);
+mb_status mb_stream_push_pcm16(mb_stream *stream, const int16_t *new_sample_frames, int64_t n_new_sample_frames,
+                               const mb_outputs *out, int mem_kind, int64_t *frames_done);
 /* How many pushes were replayed as a CUDA graph so far (MB_MEM_HOST pushes of a repeating shape). */
 int64_t mb_stream_graph_launches(const mb_stream *stream);
 

@@ -29,6 +29,7 @@ EXPORTS = [
     "mb_plan_launch_count", "mb_plan_kernel_name", "mb_host_alloc", "mb_host_free",
     "mb_stream_create", "mb_stream_destroy", "mb_stream_frames_after", "mb_stream_push", "mb_stream_reset",
     "mb_extract_pcm16", "mb_extract_pcm16_async", "mb_wav_parse", "mb_stream_graph_launches", "mb_extract_pcm",
+    "mb_stream_create_pcm16", "mb_stream_push_pcm16",
 ]
 
 # (field name in mb_outputs, feature name, per-frame length as a function of N)
@@ -124,6 +125,8 @@ def lib():
     L.mb_stream_frames_after.argtypes = [vp, C.c_int64]
     L.mb_stream_push.argtypes = [vp, vp, C.c_int64, C.POINTER(Outputs), C.c_int, i64p]
     L.mb_stream_reset.argtypes = [vp]
+    L.mb_stream_create_pcm16.argtypes = [C.POINTER(vp), vp, C.c_int, C.c_int]
+    L.mb_stream_push_pcm16.argtypes = [vp, vp, C.c_int64, C.POINTER(Outputs), C.c_int, i64p]
     L.mb_stream_graph_launches.restype = C.c_int64
     L.mb_stream_graph_launches.argtypes = [vp]
     L.mb_extract_pcm16.argtypes = [vp, vp, C.c_int64, C.c_int, C.c_int, i64p, i64p, C.c_int64, C.POINTER(Outputs),

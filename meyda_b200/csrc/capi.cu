@@ -139,14 +139,17 @@ struct StreamGraph {  // one captured push: same buffer parity, same fill level,
 
 struct mb_stream {
     mb_plan *plan = nullptr;
-    float *d_buf[2] = {nullptr, nullptr};
-    size_t cap = 0;  // floats per buffer
+    char *d_buf[2] = {nullptr, nullptr};
+    size_t cap = 0;  // sample frames per buffer
+    // what a sample frame is: one float32 (4 bytes), or `pcm_channels` interleaved int16 (mb_stream_create_pcm16)
+    int pcm_channels = 0, pcm_channel = 0;
+    size_t frame_bytes = 4;
     int cur = 0;
     int64_t filled = 0;
     int64_t skip = 0;  // samples still to drop before the next frame starts (hop > bufferSize)
     // host-memory pushes: pinned staging both ways, one device arena for all outputs, a private clip table
-    float *h_in = nullptr;
-    size_t h_in_cap = 0;  // floats
+    char *h_in = nullptr;
+    size_t h_in_cap = 0;  // sample frames
     char *d_out = nullptr, *h_out = nullptr;
     size_t out_cap = 0;  // bytes
     int64_t *d_tab = nullptr, *h_tab = nullptr;  // {clip_off = 0, frame_start = 0, nf}
@@ -1083,29 +1086,28 @@ mb_status mb_stream_reset(mb_stream *s) {
     return MB_OK;
 }
 
-mb_status mb_stream_push(mb_stream *s, const float *new_samples, int64_t n_new, const mb_outputs *out, int mem_kind,
-                         int64_t *frames_done) {
-    if (!s) return fail(MB_ERR_INVALID_ARG, "stream is NULL");
+static mb_status stream_push(mb_stream *s, const char *new_samples, int64_t n_new, const mb_outputs *out, int mem_kind,
+                             int64_t *frames_done) {
     if (n_new < 0 || (n_new > 0 && !new_samples)) return fail(MB_ERR_INVALID_ARG, "bad sample block");
+    const size_t fb = s->frame_bytes;
     if (mem_kind != MB_MEM_HOST && mem_kind != MB_MEM_DEVICE) return fail(MB_ERR_INVALID_ARG, "unknown memory kind");
     mb_plan *p = s->plan;
     DeviceGuard guard(p->device);
     if (frames_done) *frames_done = 0;
     {
         const int64_t drop = std::min(s->skip, n_new);
-        new_samples += drop;
+        new_samples += (size_t)drop * fb;
         n_new -= drop;
         s->skip -= drop;
     }
     const int64_t need = s->filled + n_new;
     if ((int64_t)s->cap < need) {
         size_t cap = (size_t)need + (size_t)need / 2 + p->N;
-        float *nb[2] = {nullptr, nullptr};
-        MB_CUDA(cudaMalloc((void **)&nb[0], cap * sizeof(float)));
-        MB_CUDA(cudaMalloc((void **)&nb[1], cap * sizeof(float)));
+        char *nb[2] = {nullptr, nullptr};
+        MB_CUDA(cudaMalloc((void **)&nb[0], cap * fb));
+        MB_CUDA(cudaMalloc((void **)&nb[1], cap * fb));
         if (s->filled)
-            MB_CUDA(cudaMemcpyAsync(nb[0], s->d_buf[s->cur], s->filled * sizeof(float), cudaMemcpyDeviceToDevice,
-                                    p->stream));
+            MB_CUDA(cudaMemcpyAsync(nb[0], s->d_buf[s->cur], s->filled * fb, cudaMemcpyDeviceToDevice, p->stream));
         MB_CUDA(cudaStreamSynchronize(p->stream));
         cudaFree(s->d_buf[0]);
         cudaFree(s->d_buf[1]);
@@ -1115,7 +1117,7 @@ mb_status mb_stream_push(mb_stream *s, const float *new_samples, int64_t n_new, 
         s->cap = cap;
         for (auto &g : s->graphs) g.cur = -1;  // captured pushes point into the old buffers
     }
-    float *buf = s->d_buf[s->cur];
+    char *buf = s->d_buf[s->cur];
     const int64_t filled_before = s->filled;
     const int64_t nf = mb_num_frames(need, p->N, p->hop);
     if (nf > 0) {
@@ -1127,15 +1129,15 @@ mb_status mb_stream_push(mb_stream *s, const float *new_samples, int64_t n_new, 
 
     if (mem_kind == MB_MEM_DEVICE) {
         if (n_new)
-            MB_CUDA(cudaMemcpyAsync(buf + filled_before, new_samples, n_new * sizeof(float), cudaMemcpyDeviceToDevice,
-                                    p->stream));
+            MB_CUDA(cudaMemcpyAsync(buf + filled_before * fb, new_samples, n_new * fb, cudaMemcpyDeviceToDevice, p->stream));
         if (nf > 0) {
             const int64_t off = 0, len = need;
-            mb_status st = mb_extract_async(p, buf, need, &off, &len, 1, out);
+            mb_status st = extract_device(p, reinterpret_cast<const float *>(buf), need, &off, &len, 1, out, s->pcm_channels,
+                                          s->pcm_channel);
             if (st != MB_OK) return st;
             if (rest)
-                MB_CUDA(cudaMemcpyAsync(s->d_buf[s->cur ^ 1], buf + consumed, rest * sizeof(float),
-                                        cudaMemcpyDeviceToDevice, p->stream));
+                MB_CUDA(cudaMemcpyAsync(s->d_buf[s->cur ^ 1], buf + consumed * fb, rest * fb, cudaMemcpyDeviceToDevice,
+                                        p->stream));
         }
         MB_CUDA(cudaStreamSynchronize(p->stream));
     } else {
@@ -1148,7 +1150,7 @@ mb_status mb_stream_push(mb_stream *s, const float *new_samples, int64_t n_new, 
             if (s->h_in) cudaFreeHost(s->h_in);
             s->h_in = nullptr;
             s->h_in_cap = 0;
-            MB_CUDA(cudaMallocHost((void **)&s->h_in, ((size_t)n_new + (size_t)n_new / 2 + 64) * sizeof(float)));
+            MB_CUDA(cudaMallocHost((void **)&s->h_in, ((size_t)n_new + (size_t)n_new / 2 + 64) * fb));
             s->h_in_cap = (size_t)n_new + (size_t)n_new / 2 + 64;
             for (auto &g : s->graphs) g.cur = -1;  // captured pointers are stale
         }
@@ -1175,7 +1177,7 @@ mb_status mb_stream_push(mb_stream *s, const float *new_samples, int64_t n_new, 
             MB_CUDA(cudaMemcpyAsync(s->d_tab, s->h_tab, 3 * sizeof(int64_t), cudaMemcpyHostToDevice, p->stream));
             s->tab_nf = nf;
         }
-        if (n_new) memcpy(s->h_in, new_samples, (size_t)n_new * sizeof(float));
+        if (n_new) memcpy(s->h_in, new_samples, (size_t)n_new * fb);
         mb_outputs d_out;
         memset(&d_out, 0, sizeof(d_out));
         size_t cursor = 0;
@@ -1186,15 +1188,15 @@ mb_status mb_stream_push(mb_stream *s, const float *new_samples, int64_t n_new, 
         }
         auto enqueue = [&]() -> mb_status {
             if (n_new)
-                MB_CUDA(cudaMemcpyAsync(buf + filled_before, s->h_in, n_new * sizeof(float), cudaMemcpyHostToDevice,
-                                        p->stream));
+                MB_CUDA(cudaMemcpyAsync(buf + filled_before * fb, s->h_in, n_new * fb, cudaMemcpyHostToDevice, p->stream));
             if (nf > 0) {
-                mb_status st = launch(p, s->d_tab, s->d_tab + 1, 1, nf, buf, d_out, p->stream, true);
+                mb_status st = launch(p, s->d_tab, s->d_tab + 1, 1, nf, reinterpret_cast<const float *>(buf), d_out, p->stream,
+                                      true, s->pcm_channels, s->pcm_channel);
                 if (st != MB_OK) return st;
                 MB_CUDA(cudaMemcpyAsync(s->h_out, s->d_out, out_bytes, cudaMemcpyDeviceToHost, p->stream));
                 if (rest)
-                    MB_CUDA(cudaMemcpyAsync(s->d_buf[s->cur ^ 1], buf + consumed, rest * sizeof(float),
-                                            cudaMemcpyDeviceToDevice, p->stream));
+                    MB_CUDA(cudaMemcpyAsync(s->d_buf[s->cur ^ 1], buf + consumed * fb, rest * fb, cudaMemcpyDeviceToDevice,
+                                            p->stream));
             }
             return MB_OK;
         };
@@ -1259,6 +1261,31 @@ mb_status mb_stream_push(mb_stream *s, const float *new_samples, int64_t n_new, 
     }
     if (frames_done) *frames_done = nf;
     return MB_OK;
+}
+
+mb_status mb_stream_push(mb_stream *s, const float *new_samples, int64_t n_new, const mb_outputs *out, int mem_kind,
+                         int64_t *frames_done) {
+    if (!s) return fail(MB_ERR_INVALID_ARG, "stream is NULL");
+    if (s->pcm_channels) return fail(MB_ERR_INVALID_ARG, "this stream takes 16-bit PCM (mb_stream_push_pcm16)");
+    return stream_push(s, reinterpret_cast<const char *>(new_samples), n_new, out, mem_kind, frames_done);
+}
+
+mb_status mb_stream_create_pcm16(mb_stream **stream, mb_plan *plan, int channels, int channel) {
+    mb_status st = check_pcm(channels, channel);
+    if (st != MB_OK) return st;
+    st = mb_stream_create(stream, plan);
+    if (st != MB_OK) return st;
+    (*stream)->pcm_channels = channels;
+    (*stream)->pcm_channel = channel;
+    (*stream)->frame_bytes = 2u * (size_t)channels;
+    return MB_OK;
+}
+
+mb_status mb_stream_push_pcm16(mb_stream *s, const int16_t *new_sample_frames, int64_t n_new, const mb_outputs *out,
+                               int mem_kind, int64_t *frames_done) {
+    if (!s) return fail(MB_ERR_INVALID_ARG, "stream is NULL");
+    if (!s->pcm_channels) return fail(MB_ERR_INVALID_ARG, "this stream takes float32 samples (mb_stream_push)");
+    return stream_push(s, reinterpret_cast<const char *>(new_sample_frames), n_new, out, mem_kind, frames_done);
 }
 
 }  // extern "C"

@@ -547,15 +547,24 @@ class Stream:
     """Stateful buffer-by-buffer extractor (mb_stream_*): push samples, get the
     features of every frame they complete."""
 
-    def __init__(self, plan: Plan):
+    def __init__(self, plan: Plan, pcm16_channels: int = 0, channel: int = 0):
+        """pcm16_channels > 0: the stream takes int16 blocks of that many interleaved channels (a capture device's
+        or WAV reader's format) and `channel` of them is analysed; the conversion happens in the kernels."""
         self.plan = plan
         self._L = plan._L
         self._h = C.c_void_p()
-        _capi.check(self._L.mb_stream_create(C.byref(self._h), plan.handle))
+        self.pcm16_channels = int(pcm16_channels)
+        if self.pcm16_channels:
+            _capi.check(self._L.mb_stream_create_pcm16(C.byref(self._h), plan.handle, self.pcm16_channels, channel))
+        else:
+            _capi.check(self._L.mb_stream_create(C.byref(self._h), plan.handle))
 
     def close(self):
         if getattr(self, "_h", None):
-            self._L.mb_stream_destroy(self._h)
+            # the native stream points into its plan: if the plan is already gone (garbage collection order at
+            # interpreter exit, or a plan closed first) there is nothing safe left to release
+            if getattr(self.plan, "_h", None):
+                self._L.mb_stream_destroy(self._h)
             self._h = None
 
     __del__ = close
@@ -577,13 +586,17 @@ class Stream:
         return int(done.value)
 
     def push(self, samples) -> ExtractResult:
-        x = np.ascontiguousarray(samples, dtype=np.float32).reshape(-1)
-        nf = int(self._L.mb_stream_frames_after(self._h, x.size))
+        if self.pcm16_channels:
+            x = np.ascontiguousarray(samples, dtype=np.int16).reshape(-1, self.pcm16_channels)
+            n, fn = x.shape[0], self._L.mb_stream_push_pcm16
+        else:
+            x = np.ascontiguousarray(samples, dtype=np.float32).reshape(-1)
+            n, fn = x.size, self._L.mb_stream_push
+        nf = int(self._L.mb_stream_frames_after(self._h, n))
         out = self.plan.alloc_host_outputs(nf)
         o = Plan.pack_outputs({k: v.ctypes.data for k, v in out.items()})
         done = C.c_int64(0)
-        _capi.check(self._L.mb_stream_push(self._h, x.ctypes.data, x.size, C.byref(o), _capi.MB_MEM_HOST,
-                                           C.byref(done)))
+        _capi.check(fn(self._h, x.ctypes.data, n, C.byref(o), _capi.MB_MEM_HOST, C.byref(done)))
         assert done.value == nf
         return ExtractResult(self.plan.features, out, np.array([nf], np.int64), self.plan.bufferSize)
 

@@ -189,3 +189,27 @@ def test_pcm_errors():
         b = io.BytesIO(); w = wave.open(b, "wb"); w.setnchannels(1); w.setsampwidth(1); w.setframerate(8000)
         w.writeframes(bytes(64)); w.close()
         mb.extract_wav(b.getvalue(), 16, features=["rms"])
+
+
+@pytest.mark.parametrize("N,hop,channels", [(2048, 512, 1), (512, 512, 1), (1024, 300, 2), (256, 64, 1)])
+def test_pcm16_streaming_matches_batch(N, hop, channels):
+    """Buffer-by-buffer pushes of int16 blocks (one per onaudioprocess call): bit-identical to the batch PCM call,
+    which is bit-identical to the float path; repeating push shapes replay as a CUDA graph."""
+    g = golden_pcm()["sound2"][:24000]
+    pcm = np.stack([np.roll(g, 555 * c) for c in range(channels)], axis=1) if channels > 1 else g
+    ch = channels - 1
+    batch, per = run_pcm(pcm, [0], [len(g)], N, hop, channel=ch)
+    plan = mb.Plan(N, hop, SR)
+    st = mb.Stream(plan, pcm16_channels=channels, channel=ch)
+    block = 512
+    got = [st.push(pcm[pos:pos + block]).arrays for pos in range(0, len(g), block)]
+    cat = {k: np.concatenate([x[k] for x in got]) for k in batch}
+    assert len(cat["rms"]) == per[0]
+    assert_same_bits(cat, batch)
+    if block % hop == 0:  # the push shape repeats: captured once, then replayed
+        assert st.graph_launches > 10
+    with pytest.raises(mb.MeydaNativeError):  # a float block on a PCM stream
+        o = plan.alloc_host_outputs(4)
+        st.push_into(np.zeros(64, np.float32), o)
+    st.close()
+    plan.close()
