@@ -14,9 +14,10 @@ pytestmark = pytest.mark.gpu
 
 
 def _cases():
-    rng = np.random.default_rng(20261018)
+    import os
+    rng = np.random.default_rng(int(os.environ.get("MEYDA_FUZZ_SEED", "20261018")))
     out = []
-    for i in range(36):
+    for i in range(int(os.environ.get("MEYDA_FUZZ_CASES", "36"))):  # (a longer soak: MEYDA_FUZZ_CASES=400 MEYDA_FUZZ_SEED=...)
         N = int(rng.choice([256, 512, 1024, 2048]))
         hop = int(rng.choice([N, N // 2, N // 4, int(rng.integers(1, 2 * N)), 4 * int(rng.integers(1, N // 2))]))
         lens = [int(rng.integers(0, 6 * N)) for _ in range(int(rng.integers(1, 7)))]
