@@ -830,6 +830,14 @@ class Interpreter:
                 return JSTypedArray(self, kind, data)
             f = self.native(ctor, kind)
             f.props["prototype"] = self.typed_protos[kind]
+
+            def subarray(this, a):  # a view on the same storage, as in JS (numpy basic slicing)
+                n = len(this.data)
+                lo = int(to_number(a[0])) if a else 0
+                hi = int(to_number(a[1])) if len(a) > 1 and a[1] is not undefined else n
+                lo, hi = (max(n + v, 0) if v < 0 else min(v, n) for v in (lo, hi))
+                return JSTypedArray(self, kind, this.data[lo:max(hi, lo)])
+            self.typed_protos[kind].props["subarray"] = self.native(subarray, "subarray")
             return f
 
         G["Float32Array"] = typed_ctor("Float32Array", np.float32)

@@ -107,3 +107,50 @@ def test_minijs_semantics():
     assert np.isnan(run("return 0/0")) and run("return 1/0") == float("inf") and run("return Math.pow(0, 0.23)") == 0.0
     assert run("var i = 0, s = 0; while (i < 5) { i++; if (i == 2) continue; s += i } return s") == 13.0
     assert run("return (7 % 2 === 1) && (-7 % 2 === -1) && ('a' + 1 === 'a1')")
+
+
+def _node_baseline_core():
+    src = open(os.path.join(ROOT, "baseline", "node", "ref_worker.js"), encoding="utf-8").read()
+    return src.split("// ---- BEGIN ES5 CORE")[1].split("// ---- END ES5 CORE")[0]
+
+
+def test_node_baseline_core_is_plain_es5():
+    """baseline/node/ref_worker.js cannot run here (no Node); its numeric core at least parses as the ES5 subset."""
+    from oracle.minijs import Parser
+    assert len(Parser(_node_baseline_core()).program()[1]) == 3  # makeReferencePath, framesOf, runClips
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/src/extractors"), reason="reference checkout not mounted")
+def test_node_baseline_core_drives_the_reference_sources(js, golden_audio):
+    """The per-frame sequence of the Node baseline, executed under minijs on the reference's own files, returns the
+    golden vectors (so what that script times is the path the oracle restates), and frames clips like the C ABI."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import make_js_golden as gen
+    from oracle.minijs import JSArray, JSObject, JSTypedArray
+    it = gen.build()
+    G = it.global_env.vars
+    it.run_source(_node_baseline_core())
+    env = JSObject(it.object_proto)
+    for k in ["ComplexArray", "extractors"] + gen.METHODS:
+        env.put(k, G[k])
+    G["env"] = env
+    G["audioContext"] = JSObject(it.object_proto)
+    G["audioContext"].put("sampleRate", SR)
+    G["names"] = JSArray(it, ["buffer"] + gen.EXTRACTORS + ["loudness"])
+    ci = 2
+    clip, N, f, window = [str(c).split("/") for c in js["cases"]][ci]
+    N, f = int(N), int(f)
+    G["clip"] = JSTypedArray(it, "Float32Array", np.asarray(golden_audio[clip][:(f + 1) * N], np.float32).copy())
+    it.run_source("var P = makeReferencePath(env, %d, %r, '%s', names); var one = P.frame(clip.subarray(%d, %d));"
+                  % (N, SR, window, f * N, (f + 1) * N))
+    r = {k: gen.to_py(v) for k, v in G["one"].props.items()}  # copied now: the reference returns aliases of reused buffers
+    it.run_source("var rc = runClips(P, [clip.subarray(0, 1024), clip.subarray(0, 700), clip.subarray(0, 100)], %d, 128);" % N)
+    for k in NUMBERS:
+        assert _num(r[k], js["%d/%s" % (ci, k)]), k
+    for k in ("mfcc", "amplitudeSpectrum", "powerSpectrum", "buffer"):
+        assert _bits(r[k], js["%d/%s" % (ci, k)]), k
+    assert _bits(r["complexSpectrum"]["real"], js["%d/complexSpectrum.real" % ci])
+    assert _bits(r["loudness"]["specific"], js["%d/loudness.specific" % ci])
+    want = sum(mo.num_frames(n, N, 128) for n in (1024, 700, 100))
+    assert gen.to_py(G["rc"])["frames"] == want == 11
