@@ -98,6 +98,22 @@ enum {
 #define MB_NUM_MEL_FILTERS 26 /* src/extractors/mfcc.js:15 */
 #define MB_NUM_MFCC 13        /* src/extractors/mfcc.js:71 */
 
+/* The constants above are what the reference hard-codes; a plan may be created with others (mb_plan_create_ex).
+ * NUM_BARK_BANDS is an option of the reference's Loudness constructor (src/extractors/loudness.js:14); the mel
+ * filter count (mfcc.js:15), the coefficient count (mfcc.js:71) and the rolloff fraction (spectralRolloff.js:9)
+ * are local constants there.  A field left 0 takes the reference's value.  Plans with non-reference values run
+ * on the generic kernels (any bufferSize, float32 or exact FFT); output rows then hold num_bark_bands /
+ * num_mfcc floats instead of 24 / 13. */
+#define MB_MAX_BARK_BANDS 64
+#define MB_MAX_MEL_FILTERS 128
+typedef struct mb_params {
+    int32_t num_bark_bands;   /* 1 .. MB_MAX_BARK_BANDS; 0 = 24 */
+    int32_t num_mel_filters;  /* 1 .. MB_MAX_MEL_FILTERS; 0 = 26 */
+    int32_t num_mfcc;         /* 1 .. num_mel_filters; 0 = 13 */
+    int32_t reserved;         /* must be 0 */
+    double rolloff_fraction;  /* in (0, 1]; 0 = 0.99 */
+} mb_params;
+
 /* `windowingFunction`, src/meyda.js:41, docs.md:5-11.  Blackman is the window the reference leaves commented
  * out as unfinished (src/meyda.js:140-156); its stated formula, 0.42 - 0.5 cos(2 pi i/(N-1)) + 0.08 cos(4 pi i/(N-1)). */
 enum { MB_WINDOW_HANNING = 0, MB_WINDOW_HAMMING = 1, MB_WINDOW_BLACKMAN = 2 };
@@ -145,11 +161,11 @@ typedef struct mb_outputs {
     float *spectral_spread;      /* [frames]      spectralSpread.js */
     float *spectral_skewness;    /* [frames]      spectralSkewness.js */
     float *spectral_kurtosis;    /* [frames]      spectralKurtosis.js */
-    float *loudness_specific;    /* [frames][24]  loudness.js -> .specific */
+    float *loudness_specific;    /* [frames][24]  loudness.js -> .specific (24 = the plan's num_bark_bands) */
     float *loudness_total;       /* [frames]                  -> .total */
     float *perceptual_spread;    /* [frames]      perceptualSpread.js */
     float *perceptual_sharpness; /* [frames]      perceptualSharpness.js */
-    float *mfcc;                 /* [frames][13]  mfcc.js */
+    float *mfcc;                 /* [frames][13]  mfcc.js (13 = the plan's num_mfcc) */
 } mb_outputs;
 
 /* Result shapes for a given clip list (what `get([...])` would have produced). */
@@ -161,6 +177,8 @@ typedef struct mb_layout {
     int32_t reserved;
     int64_t output_bytes;     /* sum over requested outputs, all frames */
     int64_t bytes_per_frame;  /* requested output bytes per frame */
+    int32_t num_bark_bands;   /* floats per frame of loudness_specific (24 unless mb_plan_create_ex said otherwise) */
+    int32_t num_mfcc;         /* floats per frame of mfcc (13 ...) */
 } mb_layout;
 
 int mb_version(void);
@@ -174,6 +192,11 @@ int64_t mb_num_frames(int64_t clip_len, int buffer_size, int hop);
 
 mb_status mb_plan_create(mb_plan **plan, int device, int buffer_size, int hop, double sample_rate,
                          int window, uint32_t feature_mask, uint32_t flags);
+/* The same with the parameters the reference keeps as constants; params == NULL is mb_plan_create. */
+mb_status mb_plan_create_ex(mb_plan **plan, int device, int buffer_size, int hop, double sample_rate,
+                            int window, uint32_t feature_mask, uint32_t flags, const mb_params *params);
+/* The parameters a plan runs with (defaults filled in). */
+mb_status mb_plan_get_params(const mb_plan *plan, mb_params *params);
 void mb_plan_destroy(mb_plan *plan);
 
 /* Launch on this CUDA stream (a cudaStream_t) instead of the plan's own;
@@ -181,7 +204,7 @@ void mb_plan_destroy(mb_plan *plan);
 mb_status mb_plan_set_stream(mb_plan *plan, void *cuda_stream);
 
 /* Read back plan tables (host copies) for inspection/tests.  Any pointer may
- * be NULL.  window: N floats; bb_limits: 25 ints; mel_bins: 28 ints. */
+ * be NULL.  window: N floats; bb_limits: num_bark_bands + 1 ints (25); mel_bins: num_mel_filters + 2 ints (28). */
 mb_status mb_plan_tables(const mb_plan *plan, float *window, int32_t *bb_limits, int32_t *mel_bins);
 
 mb_status mb_query_output(const mb_plan *plan, int64_t n_clips, const int64_t *clip_len,

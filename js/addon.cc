@@ -60,17 +60,20 @@ static napi_value CreatePlan(napi_env env, napi_callback_info info) {
     NAPI_OK_OR_THROW(env, napi_get_cb_info(env, info, &argc, argv, NULL, NULL));
     const int32_t n = get_i32(env, argv[0], "bufferSize", 0);
     mb_plan *plan = NULL;
-    mb_status st = mb_plan_create(&plan, get_i32(env, argv[0], "device", 0), n, get_i32(env, argv[0], "hop", n),
-                                  get_f64(env, argv[0], "sampleRate", 44100.0), get_i32(env, argv[0], "window", 0),
-                                  (uint32_t)get_i32(env, argv[0], "featureMask", (int32_t)MB_ALL_FEATURES),
-                                  (uint32_t)get_i32(env, argv[0], "flags", 0));
+    // 0 = the reference's constant (loudness.js:14, mfcc.js:15,71, spectralRolloff.js:9)
+    mb_params prm = {get_i32(env, argv[0], "numBarkBands", 0), get_i32(env, argv[0], "numMelFilters", 0),
+                     get_i32(env, argv[0], "numMfccCoefficients", 0), 0, get_f64(env, argv[0], "rolloffFraction", 0.0)};
+    mb_status st = mb_plan_create_ex(&plan, get_i32(env, argv[0], "device", 0), n, get_i32(env, argv[0], "hop", n),
+                                     get_f64(env, argv[0], "sampleRate", 44100.0), get_i32(env, argv[0], "window", 0),
+                                     (uint32_t)get_i32(env, argv[0], "featureMask", (int32_t)MB_ALL_FEATURES),
+                                     (uint32_t)get_i32(env, argv[0], "flags", 0), &prm);
     if (st != MB_OK) return throw_mb(env, st);
     napi_value ext;
     NAPI_OK_OR_THROW(env, napi_create_external(env, plan, plan_finalize, NULL, &ext));
     return ext;
 }
 
-struct FieldDesc { const char *name; int feature; int kind; size_t offset; };  // kind 0:1 1:N 2:N/2 3:24 4:13
+struct FieldDesc { const char *name; int feature; int kind; size_t offset; };  // kind 0:1 1:N 2:N/2 3:Bark bands (24) 4:mfcc coefficients (13)
 #define F(name, feat, kind) {#name, feat, kind, offsetof(mb_outputs, name)}
 static const FieldDesc kFields[] = {
     F(buffer, MB_FEAT_BUFFER, 1), F(rms, MB_FEAT_RMS, 0), F(energy, MB_FEAT_ENERGY, 0), F(zcr, MB_FEAT_ZCR, 0),
@@ -119,7 +122,7 @@ static napi_value ExtractImpl(napi_env env, napi_callback_info info, bool pcm16)
     for (const FieldDesc &f : kFields) {
         if (!((lay.feature_mask >> f.feature) & 1u)) continue;
         const size_t per = f.kind == 0 ? 1 : f.kind == 1 ? (size_t)lay.buffer_size : f.kind == 2 ? (size_t)lay.spectrum_size
-                                         : f.kind == 3 ? MB_NUM_BARK_BANDS : MB_NUM_MFCC;
+                                         : f.kind == 3 ? (size_t)lay.num_bark_bands : (size_t)lay.num_mfcc;
         const size_t elems = per * (size_t)lay.total_frames;
         napi_value ab, ta;
         void *data = NULL;
@@ -139,6 +142,11 @@ static napi_value ExtractImpl(napi_env env, napi_callback_info info, bool pcm16)
     napi_value frames;
     NAPI_OK_OR_THROW(env, napi_create_int64(env, lay.total_frames, &frames));
     NAPI_OK_OR_THROW(env, napi_set_named_property(env, result, "totalFrames", frames));
+    napi_value nbands, ncoefs;  // row widths of loudness_specific and mfcc
+    NAPI_OK_OR_THROW(env, napi_create_int32(env, lay.num_bark_bands, &nbands));
+    NAPI_OK_OR_THROW(env, napi_set_named_property(env, result, "numBarkBands", nbands));
+    NAPI_OK_OR_THROW(env, napi_create_int32(env, lay.num_mfcc, &ncoefs));
+    NAPI_OK_OR_THROW(env, napi_set_named_property(env, result, "numMfccCoefficients", ncoefs));
     return result;
 }
 

@@ -19,13 +19,13 @@ const featureInfo = {
   perceptualSpread: {type: 'number'}, perceptualSharpness: {type: 'number'}, mfcc: {type: 'array'}
 }
 const FEATURES = Object.keys(featureInfo)
-const FIELD = {  // feature -> [mb_outputs field, per-frame length(N)]
+const FIELD = {  // feature -> [mb_outputs field, per-frame length(N, out)]
   buffer: ['buffer', N => N], rms: ['rms'], energy: ['energy'], zcr: ['zcr'],
   amplitudeSpectrum: ['amplitude_spectrum', N => N / 2], powerSpectrum: ['power_spectrum', N => N / 2],
   spectralCentroid: ['spectral_centroid'], spectralFlatness: ['spectral_flatness'], spectralSlope: ['spectral_slope'],
   spectralRolloff: ['spectral_rolloff'], spectralSpread: ['spectral_spread'], spectralSkewness: ['spectral_skewness'],
   spectralKurtosis: ['spectral_kurtosis'], perceptualSpread: ['perceptual_spread'],
-  perceptualSharpness: ['perceptual_sharpness'], mfcc: ['mfcc', () => 13]
+  perceptualSharpness: ['perceptual_sharpness'], mfcc: ['mfcc', (N, out) => out.numMfccCoefficients || 13]
 }
 
 // src/utils.js:13-19
@@ -51,11 +51,12 @@ function frameValue (out, N, i, feature) {
     return {real: out.complex_real.subarray(i * N, (i + 1) * N), imag: out.complex_imag.subarray(i * N, (i + 1) * N)}
   }
   if (feature === 'loudness') {
-    return {specific: out.loudness_specific.subarray(i * 24, (i + 1) * 24), total: out.loudness_total[i]}
+    const nb = out.numBarkBands || 24
+    return {specific: out.loudness_specific.subarray(i * nb, (i + 1) * nb), total: out.loudness_total[i]}
   }
   const [field, len] = FIELD[feature]
   if (!len) return out[field][i]
-  const n = len(N)
+  const n = len(N, out)
   return out[field].subarray(i * n, (i + 1) * n)
 }
 
@@ -74,7 +75,9 @@ function extract (clips, opts, callback) {
   const featureMask = features.reduce((m, f) => m | (1 << FEATURES.indexOf(f)), 0)
   const plan = native.createPlan({
     bufferSize: N, hop: opts.hop || N, sampleRate: opts.sampleRate || 44100, featureMask,
-    window: {hanning: 0, hamming: 1, blackman: 2}[opts.windowingFunction || 'hanning'] || 0, device: opts.device || 0
+    window: {hanning: 0, hamming: 1, blackman: 2}[opts.windowingFunction || 'hanning'] || 0, device: opts.device || 0,
+    numBarkBands: opts.numBarkBands || 0, numMelFilters: opts.numMelFilters || 0,  // 0: the reference's 24 / 26 / 13 / 0.99
+    numMfccCoefficients: opts.numMfccCoefficients || 0, rolloffFraction: opts.rolloffFraction || 0
   })
   const out = native.extract(plan, samples, offsets, lengths)
   native.destroyPlan(plan)
@@ -113,7 +116,9 @@ function extractWav (files, opts, callback) {
   const featureMask = features.reduce((m, f) => m | (1 << FEATURES.indexOf(f)), 0)
   const plan = native.createPlan({
     bufferSize: N, hop: opts.hop || N, sampleRate: infos[0].sampleRate, featureMask,
-    window: {hanning: 0, hamming: 1, blackman: 2}[opts.windowingFunction || 'hanning'] || 0, device: opts.device || 0
+    window: {hanning: 0, hamming: 1, blackman: 2}[opts.windowingFunction || 'hanning'] || 0, device: opts.device || 0,
+    numBarkBands: opts.numBarkBands || 0, numMelFilters: opts.numMelFilters || 0,  // 0: the reference's 24 / 26 / 13 / 0.99
+    numMfccCoefficients: opts.numMfccCoefficients || 0, rolloffFraction: opts.rolloffFraction || 0
   })
   const out = native.extractPcm16(plan, pcm, ch, opts.channel || 0, offsets, lengths)
   native.destroyPlan(plan)

@@ -29,31 +29,32 @@ EXPORTS = [
     "mb_plan_launch_count", "mb_plan_kernel_name", "mb_host_alloc", "mb_host_free",
     "mb_stream_create", "mb_stream_destroy", "mb_stream_frames_after", "mb_stream_push", "mb_stream_reset",
     "mb_extract_pcm16", "mb_extract_pcm16_async", "mb_wav_parse", "mb_stream_graph_launches", "mb_extract_pcm",
-    "mb_stream_create_pcm16", "mb_stream_push_pcm16",
+    "mb_stream_create_pcm16", "mb_stream_push_pcm16", "mb_plan_create_ex", "mb_plan_get_params",
 ]
 
-# (field name in mb_outputs, feature name, per-frame length as a function of N)
+# (field name in mb_outputs, feature name, per-frame length as a function of N and of the plan's Bark-band and
+#  mfcc-coefficient counts: 24 and 13 unless the plan was created with other parameters)
 OUTPUT_FIELDS = [
-    ("buffer", "buffer", lambda N: N),
-    ("rms", "rms", lambda N: 1),
-    ("energy", "energy", lambda N: 1),
-    ("zcr", "zcr", lambda N: 1),
-    ("complex_real", "complexSpectrum", lambda N: N),
-    ("complex_imag", "complexSpectrum", lambda N: N),
-    ("amplitude_spectrum", "amplitudeSpectrum", lambda N: N // 2),
-    ("power_spectrum", "powerSpectrum", lambda N: N // 2),
-    ("spectral_centroid", "spectralCentroid", lambda N: 1),
-    ("spectral_flatness", "spectralFlatness", lambda N: 1),
-    ("spectral_slope", "spectralSlope", lambda N: 1),
-    ("spectral_rolloff", "spectralRolloff", lambda N: 1),
-    ("spectral_spread", "spectralSpread", lambda N: 1),
-    ("spectral_skewness", "spectralSkewness", lambda N: 1),
-    ("spectral_kurtosis", "spectralKurtosis", lambda N: 1),
-    ("loudness_specific", "loudness", lambda N: 24),
-    ("loudness_total", "loudness", lambda N: 1),
-    ("perceptual_spread", "perceptualSpread", lambda N: 1),
-    ("perceptual_sharpness", "perceptualSharpness", lambda N: 1),
-    ("mfcc", "mfcc", lambda N: 13),
+    ("buffer", "buffer", lambda N, nb=24, nc=13: N),
+    ("rms", "rms", lambda N, nb=24, nc=13: 1),
+    ("energy", "energy", lambda N, nb=24, nc=13: 1),
+    ("zcr", "zcr", lambda N, nb=24, nc=13: 1),
+    ("complex_real", "complexSpectrum", lambda N, nb=24, nc=13: N),
+    ("complex_imag", "complexSpectrum", lambda N, nb=24, nc=13: N),
+    ("amplitude_spectrum", "amplitudeSpectrum", lambda N, nb=24, nc=13: N // 2),
+    ("power_spectrum", "powerSpectrum", lambda N, nb=24, nc=13: N // 2),
+    ("spectral_centroid", "spectralCentroid", lambda N, nb=24, nc=13: 1),
+    ("spectral_flatness", "spectralFlatness", lambda N, nb=24, nc=13: 1),
+    ("spectral_slope", "spectralSlope", lambda N, nb=24, nc=13: 1),
+    ("spectral_rolloff", "spectralRolloff", lambda N, nb=24, nc=13: 1),
+    ("spectral_spread", "spectralSpread", lambda N, nb=24, nc=13: 1),
+    ("spectral_skewness", "spectralSkewness", lambda N, nb=24, nc=13: 1),
+    ("spectral_kurtosis", "spectralKurtosis", lambda N, nb=24, nc=13: 1),
+    ("loudness_specific", "loudness", lambda N, nb=24, nc=13: nb),
+    ("loudness_total", "loudness", lambda N, nb=24, nc=13: 1),
+    ("perceptual_spread", "perceptualSpread", lambda N, nb=24, nc=13: 1),
+    ("perceptual_sharpness", "perceptualSharpness", lambda N, nb=24, nc=13: 1),
+    ("mfcc", "mfcc", lambda N, nb=24, nc=13: nc),
 ]
 
 
@@ -64,7 +65,13 @@ class Outputs(C.Structure):
 class Layout(C.Structure):
     _fields_ = [("total_frames", C.c_int64), ("buffer_size", C.c_int32), ("spectrum_size", C.c_int32),
                 ("feature_mask", C.c_uint32), ("reserved", C.c_int32), ("output_bytes", C.c_int64),
-                ("bytes_per_frame", C.c_int64)]
+                ("bytes_per_frame", C.c_int64), ("num_bark_bands", C.c_int32), ("num_mfcc", C.c_int32)]
+
+
+class Params(C.Structure):
+    """mb_params: what the reference keeps as constants (loudness.js:14, mfcc.js:15,71, spectralRolloff.js:9)."""
+    _fields_ = [("num_bark_bands", C.c_int32), ("num_mel_filters", C.c_int32), ("num_mfcc", C.c_int32),
+                ("reserved", C.c_int32), ("rolloff_fraction", C.c_double)]
 
 
 class WavInfo(C.Structure):
@@ -102,6 +109,9 @@ def lib():
     L.mb_num_frames.argtypes = [C.c_int64, C.c_int, C.c_int]
     L.mb_plan_create.argtypes = [C.POINTER(vp), C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_uint32,
                                  C.c_uint32]
+    L.mb_plan_create_ex.argtypes = [C.POINTER(vp), C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_uint32,
+                                    C.c_uint32, C.POINTER(Params)]
+    L.mb_plan_get_params.argtypes = [vp, C.POINTER(Params)]
     L.mb_plan_destroy.argtypes = [vp]
     L.mb_plan_destroy.restype = None
     L.mb_plan_set_stream.argtypes = [vp, vp]

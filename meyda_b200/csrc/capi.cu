@@ -44,7 +44,7 @@ const char *const kFeatureNames[MB_NUM_FEATURES] = {
 struct OutField {
     size_t offset;  // byte offset of the pointer inside mb_outputs
     int feature;
-    int kind;  // 0: 1, 1: N, 2: N/2, 3: 24, 4: 13
+    int kind;  // 0: 1, 1: N, 2: N/2, 3: the plan's Bark bands (24), 4: its mfcc coefficients (13)
 };
 #define MB_FIELD(name, feat, kind) {offsetof(mb_outputs, name), feat, kind}
 const OutField kFields[] = {
@@ -71,13 +71,13 @@ const OutField kFields[] = {
 };
 constexpr int kNumFields = sizeof(kFields) / sizeof(kFields[0]);
 
-int field_elems(const OutField &f, int N) {
+int field_elems(const OutField &f, const MbDevPlan &D) {
     switch (f.kind) {
         case 0: return 1;
-        case 1: return N;
-        case 2: return N / 2;
-        case 3: return MB_NUM_BARK_BANDS;
-        default: return MB_NUM_MFCC;
+        case 1: return D.N;
+        case 2: return D.N / 2;
+        case 3: return D.nb;
+        default: return D.nc;
     }
 }
 void *&field_ptr(mb_outputs &o, const OutField &f) { return *reinterpret_cast<void **>(reinterpret_cast<char *>(&o) + f.offset); }
@@ -187,7 +187,7 @@ void build_window(std::vector<float> &w, int N, int which) {
     }
 }
 
-void build_bark_limits(int *bb, int N, double sr) {
+void build_bark_limits(int *bb, int N, double sr, int nb) {
     // src/meyda.js:170-182 then src/extractors/loudness.js:24-45
     const int n = N / 2;
     std::vector<float> bark(N);
@@ -196,24 +196,24 @@ void build_bark_limits(int *bb, int N, double sr) {
         bark[i] = (float)(13 * atan((double)hz / 1315.8) + 3.5 * atan(pow((double)hz / 7518, 2)));
     }
     const double last = bark[n - 1];
-    double band_end = last / MB_NUM_BARK_BANDS;
+    double band_end = last / nb;
     int band = 1;
-    for (int i = 0; i <= MB_NUM_BARK_BANDS; i++) bb[i] = 0;
+    for (int i = 0; i <= nb; i++) bb[i] = 0;
     for (int i = 0; i < n; i++) {
         while ((double)bark[i] > band_end) {
-            if (band <= MB_NUM_BARK_BANDS) bb[band] = i;
+            if (band <= nb) bb[band] = i;
             band++;
-            band_end = band * last / MB_NUM_BARK_BANDS;
+            band_end = band * last / nb;
         }
     }
-    bb[MB_NUM_BARK_BANDS] = n - 1;
+    bb[nb] = n - 1;
 }
 
-void build_mel_bins(int *mel, int N, double sr) {
+void build_mel_bins(int *mel, int N, double sr, int nf) {
     // src/extractors/mfcc.js:7-38
     const double lower = 1125 * log(1 + 0.0 / 700), upper = 1125 * log(1 + (sr / 2) / 700);
-    const double step = (upper - lower) / (MB_NUM_MEL_FILTERS + 1);
-    for (int i = 0; i < MB_NUM_MEL_FILTERS + 2; i++) {
+    const double step = (upper - lower) / (nf + 1);
+    for (int i = 0; i < nf + 2; i++) {
         const float m = (float)(i * step);
         const float hz = (float)(700 * (exp((double)m / 1125) - 1));
         int b = (int)floor((N + 1) * (double)hz / sr);
@@ -221,13 +221,13 @@ void build_mel_bins(int *mel, int N, double sr) {
     }
 }
 
-void build_dct(float *dct) {
+void build_dct(float *dct, int nf, int nc) {
     // src/extractors/mfcc.js:67-83
-    const double k = M_PI / MB_NUM_MEL_FILTERS;
-    const double w1 = 1.0 / sqrt((double)MB_NUM_MEL_FILTERS), w2 = sqrt(2.0 / MB_NUM_MEL_FILTERS);
-    for (int i = 0; i < MB_NUM_MFCC; i++)
-        for (int j = 0; j < MB_NUM_MEL_FILTERS; j++)
-            dct[i + j * MB_NUM_MFCC] = (float)((i == 0 ? w1 : w2) * cos(k * (i + 1) * (j + 0.5)));
+    const double k = M_PI / nf;
+    const double w1 = 1.0 / sqrt((double)nf), w2 = sqrt(2.0 / nf);
+    for (int i = 0; i < nc; i++)
+        for (int j = 0; j < nf; j++)
+            dct[i + j * nc] = (float)((i == 0 ? w1 : w2) * cos(k * (i + 1) * (j + 0.5)));
 }
 
 template <typename T>
@@ -447,11 +447,11 @@ void build_warp_mf_tables(MbWarpMfTables &W, const MbDevPlan &D) {
     if (overflow) W.n_pieces = MB_MF_MAX_PIECES + 1;
 }
 
-void offset_outputs(mb_outputs &o, const mb_outputs &base, int64_t frame0, int N) {
+void offset_outputs(mb_outputs &o, const mb_outputs &base, int64_t frame0, const MbDevPlan &D) {
     o = base;
     for (int i = 0; i < kNumFields; i++) {
         void *b = field_ptr(base, kFields[i]);
-        if (b) field_ptr(o, kFields[i]) = (char *)b + (size_t)frame0 * field_elems(kFields[i], N) * 4;
+        if (b) field_ptr(o, kFields[i]) = (char *)b + (size_t)frame0 * field_elems(kFields[i], D) * 4;
     }
 }
 
@@ -491,8 +491,42 @@ int64_t mb_num_frames(int64_t clip_len, int buffer_size, int hop) {
 
 mb_status mb_plan_create(mb_plan **plan, int device, int buffer_size, int hop, double sample_rate, int window,
                          uint32_t feature_mask, uint32_t flags) {
+    return mb_plan_create_ex(plan, device, buffer_size, hop, sample_rate, window, feature_mask, flags, nullptr);
+}
+
+mb_status mb_plan_get_params(const mb_plan *p, mb_params *params) {
+    if (!p || !params) return fail(MB_ERR_INVALID_ARG, "plan or params is NULL");
+    params->num_bark_bands = p->dev.nb;
+    params->num_mel_filters = p->dev.nf;
+    params->num_mfcc = p->dev.nc;
+    params->reserved = 0;
+    params->rolloff_fraction = p->dev.rolloff_frac;
+    return MB_OK;
+}
+
+mb_status mb_plan_create_ex(mb_plan **plan, int device, int buffer_size, int hop, double sample_rate, int window,
+                            uint32_t feature_mask, uint32_t flags, const mb_params *params) {
     if (!plan) return fail(MB_ERR_INVALID_ARG, "plan is NULL");
     *plan = nullptr;
+    // the constants of loudness.js:14, mfcc.js:15,71 and spectralRolloff.js:9 unless the caller says otherwise
+    int nb = MB_NUM_BARK_BANDS, nf = MB_NUM_MEL_FILTERS, nc = MB_NUM_MFCC;
+    double rolloff_frac = 0.99;
+    if (params) {
+        if (params->reserved != 0) return fail(MB_ERR_INVALID_ARG, "mb_params.reserved must be 0");
+        if (params->num_bark_bands) nb = params->num_bark_bands;
+        if (params->num_mel_filters) nf = params->num_mel_filters;
+        if (params->num_mfcc) nc = params->num_mfcc;
+        if (params->rolloff_fraction != 0) rolloff_frac = params->rolloff_fraction;
+        if (nb < 1 || nb > MB_MAX_BARK_BANDS)
+            return fail(MB_ERR_INVALID_ARG, "num_bark_bands %d outside [1, %d]", nb, MB_MAX_BARK_BANDS);
+        if (nf < 1 || nf > MB_MAX_MEL_FILTERS)
+            return fail(MB_ERR_INVALID_ARG, "num_mel_filters %d outside [1, %d]", nf, MB_MAX_MEL_FILTERS);
+        if (nc < 1 || nc > nf) return fail(MB_ERR_INVALID_ARG, "num_mfcc %d outside [1, num_mel_filters = %d]", nc, nf);
+        if (!(rolloff_frac > 0 && rolloff_frac <= 1))
+            return fail(MB_ERR_INVALID_ARG, "rolloff_fraction %g outside (0, 1]", rolloff_frac);
+    }
+    // the tuned warp kernels are built around the reference's constants; anything else runs on the generic family
+    const bool reference_params = nb == MB_NUM_BARK_BANDS && nf == MB_NUM_MEL_FILTERS && nc == MB_NUM_MFCC && rolloff_frac == 0.99;
     if (!is_power_of_two(buffer_size))  // src/meyda.js:20-22
         return fail(MB_ERR_NOT_POWER_OF_TWO, "Buffer size is not a power of two: Meyda will not run.");
     if (buffer_size < MB_MIN_BUFFER_SIZE || buffer_size > MB_MAX_BUFFER_SIZE)
@@ -555,15 +589,21 @@ mb_status mb_plan_create(mb_plan **plan, int device, int buffer_size, int hop, d
         D.slope_pow_freq_sum = pfs;
         D.rolloff_bin_hz = sample_rate / (2 * (M - 1));
         double sc = 0;
-        for (int i = 15; i < MB_NUM_BARK_BANDS; i++) sc += 0.066 * exp(0.171 * (i + 1));
-        D.sharp_const = sc;
+        for (int i = 15; i < nb; i++) sc += 0.066 * exp(0.171 * (i + 1));
+        // perceptualSharpness.js:6-8 reads spec[i + 1] for every i < min(15, length): with 15 bands or fewer the
+        // last read is past the end (undefined) and the reference returns NaN
+        D.sharp_const = nb >= 16 ? sc : nan("");
     }
+    D.nb = nb;
+    D.nf = nf;
+    D.nc = nc;
+    D.rolloff_frac = rolloff_frac;
     build_window(p->h_window, N, window);
-    build_bark_limits(D.bb, N, sample_rate);
-    build_mel_bins(D.mel, N, sample_rate);
-    std::vector<float> dct(MB_NUM_MFCC * MB_NUM_MEL_FILTERS), mel_inv(MB_NUM_MEL_FILTERS + 1);
-    build_dct(dct.data());
-    for (int s = 0; s <= MB_NUM_MEL_FILTERS; s++) {
+    build_bark_limits(D.bb, N, sample_rate, nb);
+    build_mel_bins(D.mel, N, sample_rate, nf);
+    std::vector<float> dct((size_t)nc * nf), mel_inv(nf + 1);
+    build_dct(dct.data(), nf, nc);
+    for (int s = 0; s <= nf; s++) {
         const int w = D.mel[s + 1] - D.mel[s];
         mel_inv[s] = w > 0 ? (float)(1.0 / w) : 0.f;
     }
@@ -588,13 +628,13 @@ mb_status mb_plan_create(mb_plan **plan, int device, int buffer_size, int hop, d
     }
     std::vector<double> mel_w;
     if (flags & MB_FLAG_EXACT_FFT) {  // src/extractors/mfcc.js:45-50, evaluated in doubles as the reference does
-        for (int f = 0; f < MB_NUM_MEL_FILTERS; f++) {
+        for (int f = 0; f < nf; f++) {
             D.mel_w_off[f] = (int)mel_w.size();
             const int e0 = D.mel[f], e1 = D.mel[f + 1], e2 = D.mel[f + 2];
             for (int k = e0; k < e1; k++) mel_w.push_back((double)(k - e0) / (double)(e1 - e0));
             for (int k = e1; k < e2; k++) mel_w.push_back((double)(e2 - k) / (double)(e2 - e1));
         }
-        D.mel_w_off[MB_NUM_MEL_FILTERS] = (int)mel_w.size();
+        D.mel_w_off[nf] = (int)mel_w.size();
     }
     bool ok = upload(&p->d_mel_w_exact, mel_w) == cudaSuccess && upload(&p->d_tw_exact, tw_exact) == cudaSuccess && upload(&p->d_window, p->h_window) == cudaSuccess && upload(&p->d_dct, dct) == cudaSuccess &&
               upload(&p->d_mel_inv, mel_inv) == cudaSuccess && upload(&p->d_twM, twM) == cudaSuccess &&
@@ -621,12 +661,12 @@ mb_status mb_plan_create(mb_plan **plan, int device, int buffer_size, int hop, d
         p->kernel_name = "exact-cluster2";
     }
     D.warp_tables = nullptr;
-    if (N == 32768 && !D.exact && !(flags & MB_FLAG_GENERIC_KERNEL) &&
+    if (N == 32768 && !D.exact && !(flags & MB_FLAG_GENERIC_KERNEL) &&  // (shares the generic epilogue: any parameters)
         (size_t)prop.sharedMemPerBlockOptin >= mb_big32768_smem_bytes() + 2048) {
         p->has_big_kernel = true;
         p->kernel_name = "big32768";
     }
-    if (N == 2048 && !D.exact && !(flags & MB_FLAG_GENERIC_KERNEL)) {
+    if (N == 2048 && !D.exact && !(flags & MB_FLAG_GENERIC_KERNEL) && reference_params) {
         MbWarpTables *W = new MbWarpTables();
         build_warp_tables(*W, D);
         const bool fits = W->n_slots <= MB_WARP_MAX_SLOTS && (size_t)prop.sharedMemPerBlockOptin >= mb_warp2048_smem_bytes();
@@ -648,7 +688,7 @@ mb_status mb_plan_create(mb_plan **plan, int device, int buffer_size, int hop, d
         }
     }
     D.warp_mf_tables = nullptr;
-    if ((N == 256 || N == 512 || N == 1024) && !D.exact && !(flags & MB_FLAG_GENERIC_KERNEL)) {
+    if ((N == 256 || N == 512 || N == 1024) && !D.exact && !(flags & MB_FLAG_GENERIC_KERNEL) && reference_params) {
         MbWarpMfTables *W = new MbWarpMfTables();
         build_warp_mf_tables(*W, D);
         const bool fits = W->n_pieces <= MB_MF_MAX_PIECES && (size_t)prop.sharedMemPerBlockOptin >= mb_warpmf_smem_bytes();
@@ -671,7 +711,7 @@ mb_status mb_plan_create(mb_plan **plan, int device, int buffer_size, int hop, d
     }
     p->bytes_per_frame = 0;
     for (int i = 0; i < kNumFields; i++)
-        if (mb_has(feature_mask, kFields[i].feature)) p->bytes_per_frame += 4 * (int64_t)field_elems(kFields[i], N);
+        if (mb_has(feature_mask, kFields[i].feature)) p->bytes_per_frame += 4 * (int64_t)field_elems(kFields[i], D);
     *plan = p;
     return MB_OK;
 }
@@ -706,8 +746,8 @@ mb_status mb_plan_set_stream(mb_plan *p, void *cuda_stream) {
 mb_status mb_plan_tables(const mb_plan *p, float *window, int32_t *bb_limits, int32_t *mel_bins) {
     if (!p) return fail(MB_ERR_INVALID_ARG, "plan is NULL");
     if (window) memcpy(window, p->h_window.data(), sizeof(float) * p->N);
-    if (bb_limits) memcpy(bb_limits, p->dev.bb, sizeof(p->dev.bb));
-    if (mel_bins) memcpy(mel_bins, p->dev.mel, sizeof(p->dev.mel));
+    if (bb_limits) memcpy(bb_limits, p->dev.bb, sizeof(int) * (p->dev.nb + 1));
+    if (mel_bins) memcpy(mel_bins, p->dev.mel, sizeof(int) * (p->dev.nf + 2));
     return MB_OK;
 }
 
@@ -730,6 +770,8 @@ mb_status mb_query_output(const mb_plan *p, int64_t n_clips, const int64_t *clip
         layout->reserved = 0;
         layout->bytes_per_frame = p->bytes_per_frame;
         layout->output_bytes = p->bytes_per_frame * total;
+        layout->num_bark_bands = p->dev.nb;
+        layout->num_mfcc = p->dev.nc;
     }
     return MB_OK;
 }
@@ -873,14 +915,14 @@ static mb_status extract_host(mb_plan *p, const void *samples, const int64_t *cl
         for (int i = 0; i < kNumFields; i++) {
             if (!mb_has(p->mask, kFields[i].feature)) continue;
             field_ptr(d_out, kFields[i]) = s.d_out + cursor;
-            cursor += (size_t)frames * field_elems(kFields[i], N) * 4;
+            cursor += (size_t)frames * field_elems(kFields[i], p->dev) * 4;
         }
         st = launch(p, s.d_tab, s.d_tab + v.size(), (int64_t)v.size(), frames, s.d_samples, d_out, s.stream,
                     offsets_aligned(s.h_tab, (int64_t)v.size()), pcm_channels, pcm_channel, pcm_format);
         if (st != MB_OK) return st;
         for (int i = 0; i < kNumFields; i++) {
             if (!mb_has(p->mask, kFields[i].feature)) continue;
-            const size_t per = (size_t)field_elems(kFields[i], N) * 4;
+            const size_t per = (size_t)field_elems(kFields[i], p->dev) * 4;
             MB_CUDA(cudaMemcpyAsync((char *)field_ptr(*out, kFields[i]) + (size_t)g_done * per,
                                     field_ptr(d_out, kFields[i]), (size_t)frames * per, cudaMemcpyDeviceToHost,
                                     s.stream));
@@ -993,7 +1035,9 @@ mb_status mb_extract_multi(mb_plan *const *plans, int n_plans, const float *samp
     for (int i = 0; i < n_plans; i++) {
         if (!plans[i]) return fail(MB_ERR_INVALID_ARG, "plan %d is NULL", i);
         if (plans[i]->N != plans[0]->N || plans[i]->hop != plans[0]->hop || plans[i]->mask != plans[0]->mask ||
-            plans[i]->sr != plans[0]->sr || plans[i]->window != plans[0]->window)
+            plans[i]->sr != plans[0]->sr || plans[i]->window != plans[0]->window ||
+            plans[i]->dev.nb != plans[0]->dev.nb || plans[i]->dev.nf != plans[0]->dev.nf ||
+            plans[i]->dev.nc != plans[0]->dev.nc || plans[i]->dev.rolloff_frac != plans[0]->dev.rolloff_frac)
             return fail(MB_ERR_INVALID_ARG, "plan %d was created with different parameters than plan 0", i);
     }
     mb_plan *p0 = plans[0];
@@ -1021,7 +1065,7 @@ mb_status mb_extract_multi(mb_plan *const *plans, int n_plans, const float *samp
             const int64_t c0 = cut[d], c1 = cut[d + 1];
             if (c1 <= c0) return;
             mb_outputs o;
-            offset_outputs(o, *out, prefix[c0], p0->N);
+            offset_outputs(o, *out, prefix[c0], p0->dev);
             status[d] = mb_extract(plans[d], samples, n_samples, clip_offset + c0, clip_len + c0, c1 - c0, &o,
                                    MB_MEM_HOST);
             if (status[d] != MB_OK) msgs[d] = mb_last_error();
@@ -1184,7 +1228,7 @@ static mb_status stream_push(mb_stream *s, const char *new_samples, int64_t n_ne
         for (int i = 0; i < kNumFields; i++) {
             if (!mb_has(p->mask, kFields[i].feature)) continue;
             field_ptr(d_out, kFields[i]) = s->d_out + cursor;
-            cursor += (size_t)nf * field_elems(kFields[i], p->N) * 4;
+            cursor += (size_t)nf * field_elems(kFields[i], p->dev) * 4;
         }
         auto enqueue = [&]() -> mb_status {
             if (n_new)
@@ -1247,7 +1291,7 @@ static mb_status stream_push(mb_stream *s, const char *new_samples, int64_t n_ne
         cursor = 0;
         for (int i = 0; i < kNumFields && nf > 0; i++) {
             if (!mb_has(p->mask, kFields[i].feature)) continue;
-            const size_t bytes = (size_t)nf * field_elems(kFields[i], p->N) * 4;
+            const size_t bytes = (size_t)nf * field_elems(kFields[i], p->dev) * 4;
             memcpy(field_ptr(*out, kFields[i]), s->h_out + cursor, bytes);
             cursor += bytes;
         }

@@ -171,9 +171,9 @@ struct Scratch {
     float red_f[kWarps];
     int red_i[kWarps];
     double scan_d[kWarps];
-    double band_sum[MB_NUM_BARK_BANDS];
-    float specific[MB_NUM_BARK_BANDS];
-    float mel_log[MB_NUM_MEL_FILTERS];
+    double band_sum[MB_MAX_BARK_BANDS];
+    float specific[MB_MAX_BARK_BANDS];
+    float mel_log[MB_MAX_MEL_FILTERS];
 };
 
 template <bool EXACT>
@@ -181,6 +181,7 @@ __device__ __forceinline__ void frame_epilogue(const MbDevPlan &P, const mb_outp
                                                const MomentAcc &acc, const float *amp, Scratch &sc) {
     const int M = P.M;
     const uint32_t mask = P.mask;
+    const int nb = P.nb, nf = P.nf, nc = P.nc;  // 24 / 26 / 13 unless the plan was created with other parameters
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     double *red_d = sc.red_d, *scan_d = sc.scan_d, *band_sum = sc.band_sum;
     int *red_i = sc.red_i;
@@ -216,7 +217,7 @@ __device__ __forceinline__ void frame_epilogue(const MbDevPlan &P, const mb_outp
         const double mine = lane < kWarps ? scan_d[lane] : 0.0;
         const double total = mb_warp_sum(mine);
         double run = mb_warp_sum(lane < warp ? mine : 0.0);  // sum of amp[0 .. k_lo)
-        const double thr = 0.99 * total;
+        const double thr = P.rolloff_frac * total;  // spectralRolloff.js:9 (0.99)
         // bins below this warp's range all count when its first prefix is under the threshold, none of its
         // own count when it is over; only the warp the threshold falls into scans bin by bin
         int cnt = 0;
@@ -243,13 +244,14 @@ __device__ __forceinline__ void frame_epilogue(const MbDevPlan &P, const mb_outp
     // ---- bark band sums (loudness.js:55-63), one warp per band
     if (want_bark) {
         if constexpr (kWarps <= kLaneBandWarps) {  // small CTAs: one lane per band, ascending like sumArray (loudness.js:69-77)
-            if (warp == 0 && lane < MB_NUM_BARK_BANDS) {
-                double s = 0;
-                for (int k = P.bb[lane]; k < P.bb[lane + 1]; k++) s += (double)amp[k];
-                band_sum[lane] = s;
-            }
+            if (warp == 0)
+                for (int b = lane; b < nb; b += 32) {
+                    double s = 0;
+                    for (int k = P.bb[b]; k < P.bb[b + 1]; k++) s += (double)amp[k];
+                    band_sum[b] = s;
+                }
         } else {
-            for (int b = warp; b < MB_NUM_BARK_BANDS; b += kWarps) {
+            for (int b = warp; b < nb; b += kWarps) {
                 double s = 0;
                 for (int k = P.bb[b] + lane; k < P.bb[b + 1]; k += 32) s += (double)amp[k];
                 s = mb_warp_sum(s);
@@ -260,23 +262,24 @@ __device__ __forceinline__ void frame_epilogue(const MbDevPlan &P, const mb_outp
     // ---- mel filterbank energies (mfcc.js:40-65)
     if (mb_has(mask, MB_FEAT_MFCC)) {
         if (EXACT) {  // the reference's order: one float32 running sum per filter
-            if (tid < MB_NUM_MEL_FILTERS) {
-                const int e0 = P.mel[tid], e1 = P.mel[tid + 1], e2 = P.mel[tid + 2];
+            for (int f = tid; f < nf; f += kThreads) {
+                const int e0 = P.mel[f], e1 = P.mel[f + 1], e2 = P.mel[f + 2];
                 // weights (i - lo) / (hi - lo) and (hi - i) / (hi - lo) come from the plan (float64 divisions
                 // done once, mfcc.js:45-50); the float32 running sum keeps the reference's order (mfcc.js:56-62)
-                const double *__restrict__ wgt = P.mel_w_exact + P.mel_w_off[tid] - e0;
+                const double *__restrict__ wgt = P.mel_w_exact + P.mel_w_off[f] - e0;
                 (void)e1;
                 float s = 0.f;
                 for (int k = e0; k < e2 && k < M; k++) {
                     const float a = amp[k];
                     s = (float)__dadd_rn((double)s, __dmul_rn(__ldg(wgt + k), (double)__fmul_rn(a, a)));
                 }
-                mel_log[tid] = (float)log((double)s);
+                mel_log[f] = (float)log((double)s);
             }
         } else if constexpr (kWarps <= kLaneBandWarps) {  // small CTAs: one lane per filter (on the second warp where there is one)
-            if (warp == (kWarps > 1 ? 1 : 0) && lane < MB_NUM_MEL_FILTERS) {
-                const int e0 = P.mel[lane], e1 = P.mel[lane + 1], e2 = min(P.mel[lane + 2], M);
-                const float up = __ldg(P.mel_inv_width + lane), dn = __ldg(P.mel_inv_width + lane + 1);
+            if (warp == (kWarps > 1 ? 1 : 0))
+            for (int f = lane; f < nf; f += 32) {
+                const int e0 = P.mel[f], e1 = P.mel[f + 1], e2 = min(P.mel[f + 2], M);
+                const float up = __ldg(P.mel_inv_width + f), dn = __ldg(P.mel_inv_width + f + 1);
                 float s = 0.f;
                 for (int k = e0; k < e1; k++) {
                     const float a = amp[k];
@@ -286,10 +289,10 @@ __device__ __forceinline__ void frame_epilogue(const MbDevPlan &P, const mb_outp
                     const float a = amp[k];
                     s += (float)(e2 - k) * dn * (a * a);
                 }
-                mel_log[lane] = s;  // (the logarithm is taken below, all filters at once)
+                mel_log[f] = s;  // (the logarithm is taken below, all filters at once)
             }
         } else {  // one warp per filter
-            for (int f = warp; f < MB_NUM_MEL_FILTERS; f += kWarps) {
+            for (int f = warp; f < nf; f += kWarps) {
                 const int e0 = P.mel[f], e1 = P.mel[f + 1], e2 = P.mel[f + 2];
                 const float up = __ldg(P.mel_inv_width + f), dn = __ldg(P.mel_inv_width + f + 1);
                 float s = 0.f;
@@ -309,20 +312,20 @@ __device__ __forceinline__ void frame_epilogue(const MbDevPlan &P, const mb_outp
     block_sync();
     // ln of the 26 filter energies by 26 threads at once (mfcc.js:63), not one filter at a time
     if (!EXACT && mb_has(mask, MB_FEAT_MFCC)) {
-        if (tid < MB_NUM_MEL_FILTERS) mel_log[tid] = (float)log((double)mel_log[tid]);
+        for (int f = tid; f < nf; f += kThreads) mel_log[f] = (float)log((double)mel_log[f]);
         block_sync();
     }
 
     if (want_bark) {
-        if (tid < MB_NUM_BARK_BANDS) {
-            const float sp = (float)pow(band_sum[tid], 0.23);
-            specific[tid] = sp;
-            if (mb_has(mask, MB_FEAT_LOUDNESS)) O.loudness_specific[g * MB_NUM_BARK_BANDS + tid] = sp;
+        for (int b = tid; b < nb; b += kThreads) {
+            const float sp = (float)pow(band_sum[b], 0.23);
+            specific[b] = sp;
+            if (mb_has(mask, MB_FEAT_LOUDNESS)) O.loudness_specific[g * nb + b] = sp;
         }
         block_sync();
         if (tid == 0) {
             double total = 0, mx = 0, sharp = 0;
-            for (int i = 0; i < MB_NUM_BARK_BANDS; i++) {
+            for (int i = 0; i < nb; i++) {
                 const double sp = (double)specific[i];
                 total += sp;
                 if (sp > mx) mx = sp;
@@ -339,13 +342,12 @@ __device__ __forceinline__ void frame_epilogue(const MbDevPlan &P, const mb_outp
         }
     }
     constexpr int kDctThread0 = kThreads > 32 ? 32 : 0;  // (a second warp where there is one)
-    if (mb_has(mask, MB_FEAT_MFCC) && tid >= kDctThread0 && tid < kDctThread0 + MB_NUM_MFCC) {
-        const int c = tid - kDctThread0;
-        double v = 0;
-        for (int f = 0; f < MB_NUM_MEL_FILTERS; f++)
-            v += (double)__ldg(P.dct + c + f * MB_NUM_MFCC) * (double)mel_log[f];
-        O.mfcc[g * MB_NUM_MFCC + c] = (float)(v / (double)MB_NUM_MFCC);
-    }
+    if (mb_has(mask, MB_FEAT_MFCC) && tid >= kDctThread0)
+        for (int c = tid - kDctThread0; c < nc; c += kThreads - kDctThread0) {
+            double v = 0;
+            for (int f = 0; f < nf; f++) v += (double)__ldg(P.dct + c + f * nc) * (double)mel_log[f];
+            O.mfcc[g * nc + c] = (float)(v / (double)nc);
+        }
 }
 
 template <bool EXACT>

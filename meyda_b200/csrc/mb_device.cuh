@@ -65,16 +65,21 @@ struct MbDevPlan {
     const float *window;        // [N] hanning or hamming (src/meyda.js:116-138)
     const float2 *twM;          // [M/2] exp(+2 pi i j / M)
     const float2 *twN;          // [M]   exp(+2 pi i k / N)
-    const float *dct;           // [13*26] idx = i + j*13 (mfcc.js:72-83)
-    const float *mel_inv_width; // [27] 1 / (mel[s+1] - mel[s]) (0 if empty)
+    const float *dct;           // [nc*nf] (13*26) idx = i + j*nc (mfcc.js:72-83)
+    const float *mel_inv_width; // [nf+1] (27) 1 / (mel[s+1] - mel[s]) (0 if empty)
     const double2 *tw_exact;    // [N-1] jsfft recurrence twiddles, stage of width w at [w-1, 2w-1) (exact mode)
     int exact;                  // MB_FLAG_EXACT_FFT
     const double *mel_w_exact;  // exact mode: filter f's weights for bins mel[f] .. mel[f+2]-1, (i-lo)/(hi-lo) as doubles
-    int mel_w_off[MB_NUM_MEL_FILTERS + 1];  // offsets of each filter's run in mel_w_exact
+    int mel_w_off[MB_MAX_MEL_FILTERS + 1];  // offsets of each filter's run in mel_w_exact
     const MbWarpTables *warp_tables;  // bufferSize 2048 only, else NULL
     const MbWarpMfTables *warp_mf_tables;  // bufferSize 256 / 512 / 1024 only, else NULL
-    int bb[MB_NUM_BARK_BANDS + 1];     // loudness.js:24-45
-    int mel[MB_NUM_MEL_FILTERS + 2];   // mfcc.js:31-38
+    int bb[MB_MAX_BARK_BANDS + 1];     // loudness.js:24-45: nb + 1 limits
+    int mel[MB_MAX_MEL_FILTERS + 2];   // mfcc.js:31-38: nf + 2 bins
+    // what the reference keeps as constants (mb_plan_create_ex); the warp kernels only ever see 24 / 26 / 13 / 0.99
+    int nb;               // Bark bands   (loudness.js:14)
+    int nf;               // mel filters  (mfcc.js:15)
+    int nc;               // coefficients (mfcc.js:71)
+    double rolloff_frac;  // spectralRolloff.js:9
 };
 
 // Clip list of one extract call (device arrays).

@@ -102,7 +102,11 @@ class Plan:
 
     def __init__(self, bufferSize: int, hop: int | None = None, sampleRate: float = 44100.0,
                  windowingFunction: str = "hanning", features: Sequence[str] = tuple(FEATURES),
-                 device: int = 0, flags: int = 0):
+                 device: int = 0, flags: int = 0, numBarkBands: int | None = None, numMelFilters: int | None = None,
+                 numMfccCoefficients: int | None = None, rolloffFraction: float | None = None):
+        """numBarkBands is the NUM_BARK_BANDS option of the reference's Loudness constructor
+        (src/extractors/loudness.js:14); numMelFilters, numMfccCoefficients and rolloffFraction replace the local
+        constants 26, 13 (mfcc.js:15,71) and 0.99 (spectralRolloff.js:9).  None keeps the reference's value."""
         if not isPowerOfTwo(bufferSize):
             raise MeydaError("Buffer size is not a power of two: Meyda will not run.")
         if windowingFunction not in _capi.MB_WINDOW:
@@ -116,8 +120,13 @@ class Plan:
         self.mask = feature_mask(self.features)
         self._L = _capi.lib()
         self._h = C.c_void_p()
-        _capi.check(self._L.mb_plan_create(C.byref(self._h), device, self.bufferSize, self.hop, self.sampleRate,
-                                           _capi.MB_WINDOW[windowingFunction], self.mask, flags))
+        prm = _capi.Params(int(numBarkBands or 0), int(numMelFilters or 0), int(numMfccCoefficients or 0), 0,
+                           float(rolloffFraction or 0.0))
+        _capi.check(self._L.mb_plan_create_ex(C.byref(self._h), device, self.bufferSize, self.hop, self.sampleRate,
+                                              _capi.MB_WINDOW[windowingFunction], self.mask, flags, C.byref(prm)))
+        _capi.check(self._L.mb_plan_get_params(self._h, C.byref(prm)))
+        self.numBarkBands, self.numMelFilters = int(prm.num_bark_bands), int(prm.num_mel_filters)
+        self.numMfccCoefficients, self.rolloffFraction = int(prm.num_mfcc), float(prm.rolloff_fraction)
 
     def close(self):
         if getattr(self, "_h", None):
@@ -153,8 +162,8 @@ class Plan:
 
     def tables(self) -> dict:
         win = np.zeros(self.bufferSize, np.float32)
-        bb = np.zeros(25, np.int32)
-        mel = np.zeros(28, np.int32)
+        bb = np.zeros(self.numBarkBands + 1, np.int32)
+        mel = np.zeros(self.numMelFilters + 2, np.int32)
         _capi.check(self._L.mb_plan_tables(self._h, win.ctypes.data, bb.ctypes.data, mel.ctypes.data))
         return {"window": win, "bbLimits": bb, "melBins": mel}
 
@@ -171,8 +180,9 @@ class Plan:
         shapes = {}
         for field, feat, per in OUTPUT_FIELDS:
             if feat in self.features:
-                n = per(self.bufferSize)
-                shapes[field] = ((total_frames,) if n == 1 else (total_frames, n),
+                n = per(self.bufferSize, self.numBarkBands, self.numMfccCoefficients)
+                scalar = n == 1 and field not in ("loudness_specific", "mfcc")
+                shapes[field] = ((total_frames,) if scalar else (total_frames, n),
                                  np.int32 if field == "zcr" else np.float32)
         return shapes
 
@@ -349,8 +359,9 @@ def _split_features(features):
 def extract(clips, bufferSize: int, hop: int | None = None, sampleRate: float = 44100.0,
             windowingFunction: str = "hanning", features=tuple(FEATURES),
             callback: Callable[[dict], None] | None = None, devices: Sequence[int] | None = None,
-            flags: int = 0) -> ExtractResult:
+            flags: int = 0, **params) -> ExtractResult:
     """Batched drop-in for "construct Meyda, feed every buffer, get(features)".
+    **params: numBarkBands / numMelFilters / numMfccCoefficients / rolloffFraction (see Plan).
 
     clips: 1-D array, list of 1-D arrays, 2-D [clips, samples] array, or
     {"data", "offsets", "lengths"}.  If `callback` is given it is invoked once
@@ -361,7 +372,8 @@ def extract(clips, bufferSize: int, hop: int | None = None, sampleRate: float = 
         raise MeydaError("Invalid Feature Format")
     data, offsets, lengths = _normalize_clips(clips)
     devices = [0] if devices is None else list(devices)
-    plans = [Plan(bufferSize, hop, sampleRate, windowingFunction, feats, device=d, flags=flags) for d in devices]
+    plans = [Plan(bufferSize, hop, sampleRate, windowingFunction, feats, device=d, flags=flags, **params)
+             for d in devices]
     try:
         if len(plans) == 1:
             arrays, per = plans[0].extract_host(data, offsets, lengths)

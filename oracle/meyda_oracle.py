@@ -322,7 +322,7 @@ def _maxdict(a: dict, b: dict) -> dict:
 
 
 def extract_frames(frames: np.ndarray, sr: float = 44100.0, window: str = "hanning",
-                   features=None, fft="jsfft") -> dict:
+                   features=None, fft="jsfft", params: dict | None = None) -> dict:
     """All requested features for a [F, N] float32 batch of raw frames.
 
     Number features -> float64[F]; arrays -> float32[F, len];
@@ -332,7 +332,15 @@ def extract_frames(frames: np.ndarray, sr: float = 44100.0, window: str = "hanni
     mathematically exact transform (numpy.fft in float64, same sign and 1/sqrt(N)
     scaling, rounded to float32 once): NOT the reference -- it measures how far the
     reference's own per-stage float32 rounding moves each feature (tests/parity.py).
+
+    params: numBarkBands (the NUM_BARK_BANDS option of loudness.js:14), numMelFilters / numMfccCoefficients
+    (the local constants of mfcc.js:15,71) and rolloffFraction (spectralRolloff.js:9) when not 24 / 26 / 13 / 0.99.
     """
+    params = params or {}
+    nb = int(params.get("numBarkBands") or NUM_BARK_BANDS)
+    nf = int(params.get("numMelFilters") or NUM_MEL_FILTERS)
+    nc = int(params.get("numMfccCoefficients") or NUM_MFCC)
+    rolloff_fraction = float(params.get("rolloffFraction") or 0.99)
     feats = ALL_FEATURES if features is None else ([features] if isinstance(features, str) else list(features))
     frames = np.atleast_2d(np.asarray(frames, dtype=f32))
     F, N = frames.shape
@@ -393,11 +401,11 @@ def extract_frames(frames: np.ndarray, sr: float = 44100.0, window: str = "hanni
             amp_freq_sum = _seqsum(freq * amp64)
             out["spectralSlope"] = (n * amp_freq_sum - freq_sum * amp_sum) / (amp_sum * (pow_freq_sum - freq_sum ** 2))
         if "spectralRolloff" in need:  # spectralRolloff.js:1-16
-            out["spectralRolloff"] = _rolloff(amp64, sr)
+            out["spectralRolloff"] = _rolloff(amp64, sr, rolloff_fraction)
         if need & {"loudness", "perceptualSpread", "perceptualSharpness"}:
-            bb = bark_band_limits(bark_scale(N, sr), n)
-            specific = np.zeros((F, NUM_BARK_BANDS), dtype=f32)
-            for b in range(NUM_BARK_BANDS):  # loudness.js:47-66
+            bb = bark_band_limits(bark_scale(N, sr), n, nb)
+            specific = np.zeros((F, nb), dtype=f32)
+            for b in range(nb):  # loudness.js:47-66
                 specific[:, b] = np.power(_seqsum(amp64[:, bb[b]:bb[b + 1]]), 0.23).astype(f32)
             total = _seqsum(specific)
             if "loudness" in need:
@@ -407,22 +415,22 @@ def extract_frames(frames: np.ndarray, sr: float = 44100.0, window: str = "hanni
                 out["perceptualSpread"] = ((total - mx) / total) ** 2
             if "perceptualSharpness" in need:  # perceptualSharpness.js:1-16
                 acc = np.zeros(F, dtype=f64)
-                for i in range(NUM_BARK_BANDS):
-                    if i < 15:
-                        acc = acc + (i + 1) * specific[:, i + 1].astype(f64)
+                for i in range(nb):
+                    if i < 15:  # spec[i + 1] past the end is `undefined`: NaN (fewer than 16 bands)
+                        acc = acc + (i + 1) * (specific[:, i + 1].astype(f64) if i + 1 < nb else np.nan)
                     else:
                         acc = acc + 0.066 * np.exp(0.171 * (i + 1))
                 out["perceptualSharpness"] = acc * (0.11 / total)
         if "mfcc" in need:
-            out["mfcc"] = _mfcc(power, N, sr)
+            out["mfcc"] = _mfcc(power, N, sr, nf, nc)
     return {k: out[k] for k in feats if k in out}
 
 
-def _rolloff(amp64: np.ndarray, sr: float) -> np.ndarray:
+def _rolloff(amp64: np.ndarray, sr: float, fraction: float = 0.99) -> np.ndarray:
     F, n = amp64.shape
     nyq_bin = sr / (2 * (n - 1))
     ec = _seqsum(amp64)
-    thr = 0.99 * ec
+    thr = fraction * ec
     # ec after subtracting amp[n-1], ..., amp[m] in that order (sequential float64)
     seq = np.cumsum(np.concatenate([ec[:, None], -amp64[:, ::-1]], axis=1), axis=1)  # [F, n+1]
     # seq[:, t] = ec after t subtractions; loop stops at first t with !(seq > thr) or t == n
@@ -431,14 +439,15 @@ def _rolloff(amp64: np.ndarray, sr: float) -> np.ndarray:
     return (n - t).astype(f64) * nyq_bin  # (q + 1) with q = n - 1 - t
 
 
-def _mfcc(power: np.ndarray, N: int, sr: float) -> np.ndarray:
+def _mfcc(power: np.ndarray, N: int, sr: float, num_filters: int = NUM_MEL_FILTERS,
+          num_coeffs: int = NUM_MFCC) -> np.ndarray:
     """src/extractors/mfcc.js:53-93 with the float32 running sum."""
     F, n = power.shape
-    fb = mel_filterbank(N, sr)
+    fb = mel_filterbank(N, sr, num_filters)
     p64 = power.astype(f64)
-    logged = np.zeros((F, NUM_MEL_FILTERS), dtype=f32)
+    logged = np.zeros((F, num_filters), dtype=f32)
     nonfinite = ~np.isfinite(p64).all(axis=1)
-    for i in range(NUM_MEL_FILTERS):
+    for i in range(num_filters):
         acc = np.zeros(F, dtype=f32)
         nz = np.nonzero(fb[i, :n])[0]
         if len(nz):
@@ -446,24 +455,26 @@ def _mfcc(power: np.ndarray, N: int, sr: float) -> np.ndarray:
                 acc = (acc.astype(f64) + fb[i, j] * p64[:, j]).astype(f32)
         acc = np.where(nonfinite, f32(np.nan), acc)  # 0 * inf / NaN anywhere poisons every band
         logged[:, i] = np.log(acc.astype(f64)).astype(f32)
-    dct = dct_matrix()
-    out = np.zeros((F, NUM_MFCC), dtype=f32)
-    for k in range(NUM_MFCC):
+    dct = dct_matrix(num_filters, num_coeffs)
+    out = np.zeros((F, num_coeffs), dtype=f32)
+    for k in range(num_coeffs):
         v = np.zeros(F, dtype=f64)
-        for m in range(NUM_MEL_FILTERS):
-            v = v + f64(dct[k + m * NUM_MFCC]) * logged[:, m].astype(f64)
-        out[:, k] = (v / NUM_MFCC).astype(f32)
+        for m in range(num_filters):
+            v = v + f64(dct[k + m * num_coeffs]) * logged[:, m].astype(f64)
+        out[:, k] = (v / num_coeffs).astype(f32)
     return out
 
 
 def extract(signal: np.ndarray, bufferSize: int, hop: int | None = None, sr: float = 44100.0,
-            window: str = "hanning", features=None, chunk: int = 4096, fft: str = "jsfft") -> dict:
+            window: str = "hanning", features=None, chunk: int = 4096, fft: str = "jsfft",
+            params: dict | None = None) -> dict:
     """Frame a clip ([f*hop, f*hop+N), no padding) and extract, in chunks."""
     hop = bufferSize if hop is None else hop
     frames = frame_signal(signal, bufferSize, hop)
-    parts = [extract_frames(frames[i:i + chunk], sr, window, features, fft) for i in range(0, len(frames), chunk)]
+    parts = [extract_frames(frames[i:i + chunk], sr, window, features, fft, params)
+             for i in range(0, len(frames), chunk)]
     if not parts:
-        parts = [extract_frames(np.zeros((0, bufferSize), dtype=f32), sr, window, features, fft)]
+        parts = [extract_frames(np.zeros((0, bufferSize), dtype=f32), sr, window, features, fft, params)]
     return _concat(parts)
 
 

@@ -946,6 +946,9 @@ class Interpreter:
         module.put("exports", exports)
         self.modules[full] = module
         src = open(full, encoding="utf-8").read()
+        for old, new in getattr(self, "source_edits", {}).get(os.path.basename(full), []):
+            assert src.count(old) == 1, (full, old)  # (a constant of the module replaced for a parameter study)
+            src = src.replace(old, new)
         ast = Parser(src).program()
         env = Env(self.global_env)
         d = os.path.dirname(full)

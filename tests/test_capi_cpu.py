@@ -62,6 +62,14 @@ def test_plan_create_errors_without_device(lib):
     assert lib.mb_plan_create(C.byref(h), 0, 512, 0, 44100.0, 0, 1, 0) == _capi.MB_ERR_INVALID_ARG
     assert lib.mb_plan_create(C.byref(h), 0, 512, 512, 44100.0, 7, 1, 0) == _capi.MB_ERR_INVALID_ARG
     assert lib.mb_plan_create(C.byref(h), 0, 512, 512, 44100.0, 0, 0, 0) == _capi.MB_ERR_INVALID_ARG
+    # mb_plan_create_ex: the parameters are validated before any device is touched
+    bad = [_capi.Params(65, 0, 0, 0, 0.0), _capi.Params(-1, 0, 0, 0, 0.0), _capi.Params(0, 129, 0, 0, 0.0),
+           _capi.Params(0, 20, 21, 0, 0.0), _capi.Params(0, 0, 27, 0, 0.0), _capi.Params(0, 0, 0, 1, 0.0),
+           _capi.Params(0, 0, 0, 0, 1.5), _capi.Params(0, 0, 0, 0, -0.1), _capi.Params(0, 0, 0, 0, float("nan"))]
+    for prm in bad:
+        st = lib.mb_plan_create_ex(C.byref(h), 0, 512, 512, 44100.0, 0, 1, 0, C.byref(prm))
+        assert st == _capi.MB_ERR_INVALID_ARG and not h.value, (prm.num_bark_bands, prm.num_mel_filters, prm.num_mfcc)
+    assert b"rolloff_fraction" in lib.mb_last_error()
     n = C.c_int(-1)
     lib.mb_device_count(C.byref(n))
     if n.value == 0:  # no GPU here: the product path must fail loudly, not fall back
@@ -72,7 +80,8 @@ def test_plan_create_errors_without_device(lib):
 
 def test_struct_layouts_match_header():
     assert C.sizeof(_capi.Outputs) == 20 * C.sizeof(C.c_void_p)
-    assert C.sizeof(_capi.Layout) == 8 + 4 + 4 + 4 + 4 + 8 + 8
+    assert C.sizeof(_capi.Layout) == 8 + 4 + 4 + 4 + 4 + 8 + 8 + 4 + 4
+    assert C.sizeof(_capi.Params) == 4 * 4 + 8 and _capi.Params.rolloff_fraction.offset == 16
     assert [f for f, _, _ in _capi.OUTPUT_FIELDS][:4] == ["buffer", "rms", "energy", "zcr"]
 
 

@@ -419,3 +419,76 @@ def test_multi_frame_warp_kernel_groups(N):
             row += 1
     plan.close()
     verify(out, [c for c in clips if len(c) >= N], N, hop, max_banded_frac=1.0)
+
+
+# ---- the parameters the reference keeps as constants (mb_plan_create_ex)
+PARAM_SETS = [
+    pytest.param(dict(numBarkBands=30, numMelFilters=40, numMfccCoefficients=20, rolloffFraction=0.85), id="30-40-20-0.85"),
+    pytest.param(dict(numBarkBands=12), id="12-bands"),  # perceptualSharpness.js:8 reads past the end: NaN
+    pytest.param(dict(numBarkBands=64, numMelFilters=128, numMfccCoefficients=128, rolloffFraction=1.0), id="maxima"),
+    pytest.param(dict(numBarkBands=1, numMelFilters=1, numMfccCoefficients=1, rolloffFraction=0.5), id="minima"),
+    pytest.param(dict(numMfccCoefficients=5), id="5-coefficients"),
+]
+
+
+@pytest.mark.parametrize("params", PARAM_SETS)
+@pytest.mark.parametrize("flags", FLAG_VARIANTS)
+@pytest.mark.parametrize("N,hop", [(512, 512), (2048, 512), (256, 128), (4096, 4096)])
+def test_plan_parameters(golden_audio, N, hop, flags, params):
+    """Oracle: the numpy restatement with the same parameters, itself pinned to the reference's JavaScript run with
+    them (tests/test_js_pin.py::test_oracle_parameters_reproduce_the_reference_javascript).  sound1 needs no noise band."""
+    x = golden_audio["sound1"][:40 * N if N <= 512 else 70000]
+    data, off, ln = mb.meyda._normalize_clips(x)
+    plan = mb.Plan(N, hop, SR, "hanning", flags=flags, **params)
+    try:
+        assert plan.kernel_name.startswith(("generic", "exact")), plan.kernel_name
+        nb, nc = params.get("numBarkBands", 24), params.get("numMfccCoefficients", 13)
+        assert (plan.numBarkBands, plan.numMfccCoefficients) == (nb, nc)
+        assert plan.rolloffFraction == params.get("rolloffFraction", 0.99)
+        t = plan.tables()
+        assert np.array_equal(t["bbLimits"], mo.bark_band_limits(mo.bark_scale(N, SR), N // 2, nb))
+        assert np.array_equal(t["melBins"], np.minimum(mo.mel_bins(N, SR, plan.numMelFilters), N // 2).astype(np.int32))
+        out, per = plan.extract_host(data, off, ln)
+        _, lay = plan.query(ln)
+        assert (lay.num_bark_bands, lay.num_mfcc) == (nb, nc)
+    finally:
+        plan.close()
+    assert out["loudness_specific"].shape == (per[0], nb) and out["mfcc"].shape == (per[0], nc)
+    ref = mo.extract(x, N, hop, SR, "hanning", params=params)
+    assert ref["mfcc"].shape == out["mfcc"].shape
+    banded = parity.compare_all(out, ref, N, noise_band=None, exact=bool(flags & EXACT))
+    assert not any(banded.values()), banded
+    if nb < 16:
+        assert np.isnan(out["perceptual_sharpness"]).all()
+
+
+def test_default_parameters_keep_the_tuned_kernels():
+    for N, name in [(2048, "warp2048"), (512, "warpmf512")]:
+        plan = mb.Plan(N, N // 4, SR, "hanning", numBarkBands=24, numMelFilters=26, numMfccCoefficients=13, rolloffFraction=0.99)
+        assert plan.kernel_name == name
+        plan.close()
+        plan = mb.Plan(N, N // 4, SR, "hanning", rolloffFraction=0.95)
+        assert plan.kernel_name == "generic"
+        plan.close()
+
+
+def test_streaming_and_sharding_with_parameters(golden_audio):
+    """The packed streaming outputs and the multi-device split use the plan's row widths."""
+    params = dict(numBarkBands=30, numMelFilters=40, numMfccCoefficients=20)
+    x = golden_audio["sound2"][:30000]
+    N, hop = 512, 256
+    plan = mb.Plan(N, hop, SR, "hanning", **params)
+    try:
+        data, off, ln = mb.meyda._normalize_clips(x)
+        batch, _ = plan.extract_host(data, off, ln)
+        st = mb.Stream(plan)
+        parts = [st.push(x[i:i + 1000]).arrays for i in range(0, len(x), 1000)]
+        st.close()
+    finally:
+        plan.close()
+    for k in ("mfcc", "loudness_specific", "spectral_rolloff"):
+        got = np.concatenate([p[k] for p in parts])
+        assert got.shape == batch[k].shape and np.array_equal(got, batch[k], equal_nan=True), k
+    res = mb.extract([x, x[:5000]], N, hop, features=["mfcc", "loudness"], devices=[0, 0], **params)
+    assert np.array_equal(res["mfcc"][:len(batch["mfcc"])], batch["mfcc"], equal_nan=True)
+    assert res["loudness"]["specific"].shape[1] == 30

@@ -154,3 +154,25 @@ def test_node_baseline_core_drives_the_reference_sources(js, golden_audio):
     assert _bits(r["loudness"]["specific"], js["%d/loudness.specific" % ci])
     want = sum(mo.num_frames(n, N, 128) for n in (1024, 700, 100))
     assert gen.to_py(G["rc"])["frames"] == want == 11
+
+
+def test_oracle_parameters_reproduce_the_reference_javascript(golden_audio):
+    """numBarkBands through the reference's own NUM_BARK_BANDS option; filter / coefficient counts and the rolloff
+    fraction through the reference's module text with that one constant replaced (tools/make_js_golden_params.py)."""
+    js = np.load(os.path.join(ROOT, "tests", "golden", "js_reference_params.npz"))
+    cases = [str(c).split("/") for c in js["cases"]]
+    assert len(cases) == 4
+    for ci, (clip, N, f, window, nb, edited) in enumerate(cases):
+        N, f, nb = int(N), int(f), int(nb)
+        params = {"numBarkBands": nb}
+        if int(edited):
+            params.update(numMelFilters=40, numMfccCoefficients=20, rolloffFraction=0.85)
+        r = mo.extract(_signal(golden_audio, clip, N, f), N, N, SR, window, params=params)
+        assert np.array_equal(mo.bark_band_limits(mo.bark_scale(N, SR), N // 2, nb), js["%d/bbLimits" % ci].astype(np.int32))
+        assert r["loudness"]["specific"].shape == (1, nb) and r["mfcc"].shape == (1, 20 if int(edited) else 13)
+        assert _bits(r["loudness"]["specific"][0], js["%d/loudness.specific" % ci]), (ci, "specific")
+        assert _bits(r["mfcc"][0], js["%d/mfcc" % ci]), (ci, "mfcc")
+        for k in ("perceptualSpread", "perceptualSharpness", "spectralRolloff", "spectralCentroid"):
+            assert _num(r[k][0], js["%d/%s" % (ci, k)]), (ci, k, r[k][0], float(js["%d/%s" % (ci, k)]))
+        assert _num(r["loudness"]["total"][0], js["%d/loudness.total" % ci])
+    assert np.isnan(js["1/perceptualSharpness"])  # 12 bands: spec[12] is undefined (perceptualSharpness.js:8)

@@ -44,7 +44,7 @@ var spec = data.FFT();
 m.complexSpectrum = spec;
 m.ampSpectrum = new Float32Array(N / 2);
 computeAmplitude.call(m, spec, m.ampSpectrum, N);
-var loud = extractors.loudness({NUM_BARK_BANDS: 24, barkScale: m.barkScale, normalisedSpectrum: m.ampSpectrum, sampleRate: SR});
+var loud = extractors.loudness({NUM_BARK_BANDS: NBARK, barkScale: m.barkScale, normalisedSpectrum: m.ampSpectrum, sampleRate: SR});
 m.featureExtractors.loudness = function(bufferSize, mm) { return loud.process(); };
 var results = {};
 for (var x = 0; x < names.length; x++) { results[names[x]] = extractors[names[x]](N, m); }
@@ -83,8 +83,11 @@ def to_py(v):
     return v
 
 
-def build():
+def build(source_edits=None):
+    """source_edits: {file name: [(old, new)]} -- used only by the parameter vectors (make_js_golden_params.py),
+    to replace the local constants numFilters / numCoeffs / 0.99 of mfcc.js and spectralRolloff.js."""
     it = Interpreter(REF)
+    it.source_edits = source_edits or {}
     ca = it.require("lib/jsfft/complex_array")
     it.require("lib/jsfft/fft")  # decorates ComplexArray.prototype with FFT
     utils = it.require("src/utils")
@@ -100,11 +103,11 @@ def build():
     return it
 
 
-def run_frame(it, signal, sr, window):
+def run_frame(it, signal, sr, window, num_bark_bands=24):
     G = it.global_env.vars
     N = len(signal)
     G["signal"] = JSTypedArray(it, "Float32Array", np.asarray(signal, dtype=np.float32).copy())
-    G["N"], G["SR"], G["WINDOW"] = float(N), float(sr), window
+    G["N"], G["SR"], G["WINDOW"], G["NBARK"] = float(N), float(sr), window, float(num_bark_bands)
     G["audioContext"] = JSObject(it.object_proto)  # free global in mfcc.js:20,37
     G["audioContext"].put("sampleRate", float(sr))
     G["names"] = JSArray(it, EXTRACTORS)
