@@ -237,7 +237,7 @@ mb_status mb_extract_multi(mb_plan *const *plans, int n_plans, const float *samp
                            const mb_outputs *out);
 
 /*
- * 16-bit PCM input (what the reference's fixtures audio/*.wav hold).  `pcm` is
+ * 16-bit PCM input (what the reference's fixtures audio/sound1-3.wav hold).  `pcm` is
  * n_sample_frames x channels interleaved int16; channel `channel` is used and
  * every sample becomes (float)s / 32768 on load (Web Audio decodeAudioData),
  * so the results equal mb_extract on the converted samples bit for bit while

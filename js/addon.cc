@@ -9,6 +9,8 @@
 //   const plan = native.createPlan({bufferSize, hop, sampleRate, window, featureMask, device, flags})
 //   const out  = native.extract(plan, samples /*Float32Array*/, offsets /*BigInt64Array*/, lengths /*BigInt64Array*/)
 //   const out  = native.extractPcm16(plan, pcm /*Int16Array, interleaved*/, channels, channel, offsets, lengths)
+//   const out  = await native.extractAsync(plan, samples, offsets, lengths)     // napi_async_work on the libuv pool
+//   const out  = await native.extractPcm16Async(plan, pcm, channels, channel, offsets, lengths)
 //   const info = native.wavInfo(fileBytes /*Uint8Array*/)   // {format, channels, sampleRate, bitsPerSample, dataOffset, sampleFrames}
 //   native.destroyPlan(plan)
 //
@@ -86,39 +88,63 @@ static const FieldDesc kFields[] = {
     F(loudness_total, MB_FEAT_LOUDNESS, 0), F(perceptual_spread, MB_FEAT_PERCEPTUAL_SPREAD, 0),
     F(perceptual_sharpness, MB_FEAT_PERCEPTUAL_SHARPNESS, 0), F(mfcc, MB_FEAT_MFCC, 4)};
 
-// extract(plan, Float32Array, offsets, lengths)  /  extractPcm16(plan, Int16Array, channels, channel, offsets, lengths)
-static napi_value ExtractImpl(napi_env env, napi_callback_info info, bool pcm16) {
+// One extract call: arguments parsed and outputs allocated on the JS thread, the blocking C-ABI call either made in
+// place (extract / extractPcm16) or on the libuv pool (extractAsync / extractPcm16Async, SURVEY.md 8b "Threading").
+struct Job {
+    mb_plan *plan = NULL;
+    bool pcm16 = false;
+    void *samples = NULL, *offs = NULL, *lens = NULL;
+    size_t n_samples = 0, n_clips = 0;
+    int32_t channels = 1, channel = 0;
+    mb_outputs out;
+    // async only
+    mb_status status = MB_OK;
+    char error[512];
+    napi_async_work work = NULL;
+    napi_deferred deferred = NULL;
+    napi_ref keep_result = NULL, keep_args = NULL;  // the typed arrays must outlive the pool thread's use of them
+};
+
+static mb_status run_job(Job *j) {
+    if (j->pcm16)  // the WAV data chunk as it is: conversion and channel pick happen on the device
+        return mb_extract_pcm16(j->plan, (const int16_t *)j->samples, (int64_t)(j->n_samples / (j->channels > 0 ? j->channels : 1)),
+                                j->channels, j->channel, (const int64_t *)j->offs, (const int64_t *)j->lens, (int64_t)j->n_clips,
+                                &j->out, MB_MEM_HOST);
+    return mb_extract(j->plan, (const float *)j->samples, (int64_t)j->n_samples, (const int64_t *)j->offs, (const int64_t *)j->lens,
+                      (int64_t)j->n_clips, &j->out, MB_MEM_HOST);
+}
+
+// (plan, Float32Array, offsets, lengths)  /  (plan, Int16Array, channels, channel, offsets, lengths).
+// Returns the result object (typed arrays allocated, not yet filled) or NULL with an exception pending.
+static napi_value prepare_job(napi_env env, napi_callback_info info, bool pcm16, Job *j, napi_value *args_array) {
     size_t argc = 6;
     napi_value argv[6];
     NAPI_OK_OR_THROW(env, napi_get_cb_info(env, info, &argc, argv, NULL, NULL));
-    mb_plan *plan = NULL;
-    NAPI_OK_OR_THROW(env, napi_get_value_external(env, argv[0], (void **)&plan));
+    j->pcm16 = pcm16;
+    memset(&j->out, 0, sizeof(j->out));
+    NAPI_OK_OR_THROW(env, napi_get_value_external(env, argv[0], (void **)&j->plan));
     napi_typedarray_type tt;
-    size_t n_samples = 0, n_clips = 0, n_len = 0;
-    void *samples = NULL, *offs = NULL, *lens = NULL;
-    int32_t channels = 1, channel = 0;
-    NAPI_OK_OR_THROW(env, napi_get_typedarray_info(env, argv[1], &tt, &n_samples, &samples, NULL, NULL));
+    size_t n_len = 0;
+    NAPI_OK_OR_THROW(env, napi_get_typedarray_info(env, argv[1], &tt, &j->n_samples, &j->samples, NULL, NULL));
     if (tt != (pcm16 ? napi_int16_array : napi_float32_array)) {
         napi_throw_type_error(env, NULL, pcm16 ? "pcm must be an Int16Array" : "samples must be a Float32Array");
         return NULL;
     }
     if (pcm16) {
-        NAPI_OK_OR_THROW(env, napi_get_value_int32(env, argv[2], &channels));
-        NAPI_OK_OR_THROW(env, napi_get_value_int32(env, argv[3], &channel));
+        NAPI_OK_OR_THROW(env, napi_get_value_int32(env, argv[2], &j->channels));
+        NAPI_OK_OR_THROW(env, napi_get_value_int32(env, argv[3], &j->channel));
     }
     const int a0 = pcm16 ? 4 : 2;
-    NAPI_OK_OR_THROW(env, napi_get_typedarray_info(env, argv[a0], &tt, &n_clips, &offs, NULL, NULL));
+    NAPI_OK_OR_THROW(env, napi_get_typedarray_info(env, argv[a0], &tt, &j->n_clips, &j->offs, NULL, NULL));
     if (tt != napi_bigint64_array) { napi_throw_type_error(env, NULL, "offsets must be a BigInt64Array"); return NULL; }
-    NAPI_OK_OR_THROW(env, napi_get_typedarray_info(env, argv[a0 + 1], &tt, &n_len, &lens, NULL, NULL));
-    if (tt != napi_bigint64_array || n_len != n_clips) { napi_throw_type_error(env, NULL, "lengths must match offsets"); return NULL; }
+    NAPI_OK_OR_THROW(env, napi_get_typedarray_info(env, argv[a0 + 1], &tt, &n_len, &j->lens, NULL, NULL));
+    if (tt != napi_bigint64_array || n_len != j->n_clips) { napi_throw_type_error(env, NULL, "lengths must match offsets"); return NULL; }
 
     mb_layout lay;
-    mb_status st = mb_query_output(plan, (int64_t)n_clips, (const int64_t *)lens, NULL, &lay);
+    mb_status st = mb_query_output(j->plan, (int64_t)j->n_clips, (const int64_t *)j->lens, NULL, &lay);
     if (st != MB_OK) return throw_mb(env, st);
     napi_value result;
     NAPI_OK_OR_THROW(env, napi_create_object(env, &result));
-    mb_outputs out;
-    memset(&out, 0, sizeof(out));
     for (const FieldDesc &f : kFields) {
         if (!((lay.feature_mask >> f.feature) & 1u)) continue;
         const size_t per = f.kind == 0 ? 1 : f.kind == 1 ? (size_t)lay.buffer_size : f.kind == 2 ? (size_t)lay.spectrum_size
@@ -129,29 +155,89 @@ static napi_value ExtractImpl(napi_env env, napi_callback_info info, bool pcm16)
         NAPI_OK_OR_THROW(env, napi_create_arraybuffer(env, elems * 4, &data, &ab));
         NAPI_OK_OR_THROW(env, napi_create_typedarray(env, strcmp(f.name, "zcr") == 0 ? napi_int32_array : napi_float32_array,
                                                      elems, ab, 0, &ta));
-        *(void **)((char *)&out + f.offset) = data;
+        *(void **)((char *)&j->out + f.offset) = data;
         NAPI_OK_OR_THROW(env, napi_set_named_property(env, result, f.name, ta));
     }
-    if (pcm16)  // the WAV data chunk as it is: conversion and channel pick happen on the device
-        st = mb_extract_pcm16(plan, (const int16_t *)samples, (int64_t)(n_samples / (channels > 0 ? channels : 1)), channels,
-                              channel, (const int64_t *)offs, (const int64_t *)lens, (int64_t)n_clips, &out, MB_MEM_HOST);
-    else
-        st = mb_extract(plan, (const float *)samples, (int64_t)n_samples, (const int64_t *)offs, (const int64_t *)lens,
-                        (int64_t)n_clips, &out, MB_MEM_HOST);
-    if (st != MB_OK) return throw_mb(env, st);
-    napi_value frames;
+    napi_value frames, nbands, ncoefs;
     NAPI_OK_OR_THROW(env, napi_create_int64(env, lay.total_frames, &frames));
     NAPI_OK_OR_THROW(env, napi_set_named_property(env, result, "totalFrames", frames));
-    napi_value nbands, ncoefs;  // row widths of loudness_specific and mfcc
-    NAPI_OK_OR_THROW(env, napi_create_int32(env, lay.num_bark_bands, &nbands));
+    NAPI_OK_OR_THROW(env, napi_create_int32(env, lay.num_bark_bands, &nbands));  // row widths of loudness_specific and mfcc
     NAPI_OK_OR_THROW(env, napi_set_named_property(env, result, "numBarkBands", nbands));
     NAPI_OK_OR_THROW(env, napi_create_int32(env, lay.num_mfcc, &ncoefs));
     NAPI_OK_OR_THROW(env, napi_set_named_property(env, result, "numMfccCoefficients", ncoefs));
+    if (args_array) {  // plan + every input array, kept alive while the pool thread reads them
+        NAPI_OK_OR_THROW(env, napi_create_array_with_length(env, argc, args_array));
+        for (size_t i = 0; i < argc; i++) NAPI_OK_OR_THROW(env, napi_set_element(env, *args_array, (uint32_t)i, argv[i]));
+    }
+    return result;
+}
+
+static napi_value ExtractImpl(napi_env env, napi_callback_info info, bool pcm16) {
+    Job j;
+    napi_value result = prepare_job(env, info, pcm16, &j, NULL);
+    if (!result) return NULL;
+    const mb_status st = run_job(&j);
+    if (st != MB_OK) return throw_mb(env, st);
     return result;
 }
 
 static napi_value Extract(napi_env env, napi_callback_info info) { return ExtractImpl(env, info, false); }
 static napi_value ExtractPcm16(napi_env env, napi_callback_info info) { return ExtractImpl(env, info, true); }
+
+// ---- the same calls as Promises: mb_extract* block, so they run on the libuv pool (one plan must not be used by two
+// jobs at once: the C ABI is thread-compatible, not thread-safe).  No N-API call is made off the JS thread.
+static void job_execute(napi_env, void *data) {
+    Job *j = (Job *)data;
+    j->status = run_job(j);
+    if (j->status != MB_OK) {  // mb_last_error() is thread-local: take it on this thread
+        strncpy(j->error, mb_last_error(), sizeof(j->error) - 1);
+        j->error[sizeof(j->error) - 1] = 0;
+    }
+}
+
+static void job_complete(napi_env env, napi_status status, void *data) {
+    Job *j = (Job *)data;
+    napi_value result = NULL;
+    if (status == napi_ok && j->status == MB_OK && napi_get_reference_value(env, j->keep_result, &result) == napi_ok) {
+        napi_resolve_deferred(env, j->deferred, result);
+    } else {
+        napi_value code, msg, err;
+        const char *text = status != napi_ok ? "extract was cancelled" : j->error;
+        napi_create_string_utf8(env, j->status == MB_ERR_NOT_POWER_OF_TWO ? "ERR_MEYDA_BUFFER_SIZE" : "ERR_MEYDA_NATIVE",
+                                NAPI_AUTO_LENGTH, &code);
+        napi_create_string_utf8(env, text, NAPI_AUTO_LENGTH, &msg);
+        napi_create_error(env, code, msg, &err);
+        napi_reject_deferred(env, j->deferred, err);
+    }
+    napi_delete_reference(env, j->keep_result);
+    napi_delete_reference(env, j->keep_args);
+    napi_delete_async_work(env, j->work);
+    delete j;
+}
+
+static napi_value ExtractAsyncImpl(napi_env env, napi_callback_info info, bool pcm16) {
+    Job *j = new Job();
+    napi_value args, promise, name;
+    napi_value result = prepare_job(env, info, pcm16, j, &args);
+    if (!result) { delete j; return NULL; }
+    if (napi_create_reference(env, result, 1, &j->keep_result) != napi_ok ||
+        napi_create_reference(env, args, 1, &j->keep_args) != napi_ok ||
+        napi_create_promise(env, &j->deferred, &promise) != napi_ok ||
+        napi_create_string_utf8(env, "meyda_b200.extract", NAPI_AUTO_LENGTH, &name) != napi_ok ||
+        napi_create_async_work(env, NULL, name, job_execute, job_complete, j, &j->work) != napi_ok ||
+        napi_queue_async_work(env, j->work) != napi_ok) {
+        if (j->keep_result) napi_delete_reference(env, j->keep_result);
+        if (j->keep_args) napi_delete_reference(env, j->keep_args);
+        if (j->work) napi_delete_async_work(env, j->work);
+        delete j;
+        napi_throw_error(env, NULL, "could not queue the extract job");
+        return NULL;
+    }
+    return promise;
+}
+
+static napi_value ExtractAsync(napi_env env, napi_callback_info info) { return ExtractAsyncImpl(env, info, false); }
+static napi_value ExtractPcm16Async(napi_env env, napi_callback_info info) { return ExtractAsyncImpl(env, info, true); }
 
 // wavInfo(Uint8Array) -> the fields of mb_wav_info (replaces the header half of decodeAudioData, lib/bufferLoader.js:28-38)
 static napi_value WavInfo(napi_env env, napi_callback_info info) {
@@ -192,6 +278,8 @@ static napi_value Init(napi_env env, napi_value exports) {
         {"createPlan", NULL, CreatePlan, NULL, NULL, NULL, napi_default, NULL},
         {"extract", NULL, Extract, NULL, NULL, NULL, napi_default, NULL},
         {"extractPcm16", NULL, ExtractPcm16, NULL, NULL, NULL, napi_default, NULL},
+        {"extractAsync", NULL, ExtractAsync, NULL, NULL, NULL, napi_default, NULL},
+        {"extractPcm16Async", NULL, ExtractPcm16Async, NULL, NULL, NULL, napi_default, NULL},
         {"wavInfo", NULL, WavInfo, NULL, NULL, NULL, napi_default, NULL},
         {"destroyPlan", NULL, DestroyPlan, NULL, NULL, NULL, napi_default, NULL},
     };

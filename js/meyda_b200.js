@@ -79,18 +79,25 @@ function extract (clips, opts, callback) {
     numBarkBands: opts.numBarkBands || 0, numMelFilters: opts.numMelFilters || 0,  // 0: the reference's 24 / 26 / 13 / 0.99
     numMfccCoefficients: opts.numMfccCoefficients || 0, rolloffFraction: opts.rolloffFraction || 0
   })
-  const out = native.extract(plan, samples, offsets, lengths)
-  native.destroyPlan(plan)
-  const result = {
-    features, arrays: out, totalFrames: Number(out.totalFrames),
-    value: (i, f) => frameValue(out, N, i, f),
-    frame: i => Object.fromEntries(features.map(f => [f, frameValue(out, N, i, f)]))
+  const finish = out => {
+    native.destroyPlan(plan)
+    const result = {
+      features, arrays: out, totalFrames: Number(out.totalFrames),
+      value: (i, f) => frameValue(out, N, i, f),
+      frame: i => Object.fromEntries(features.map(f => [f, frameValue(out, N, i, f)]))
+    }
+    if (typeof callback === 'function') {  // the buffer-by-buffer contract, src/meyda.js:87-89 (on the JS thread)
+      for (let i = 0; i < result.totalFrames; i++) callback(result.frame(i))
+    }
+    return result
   }
-  if (typeof callback === 'function') {  // the buffer-by-buffer contract, src/meyda.js:87-89
-    for (let i = 0; i < result.totalFrames; i++) callback(result.frame(i))
-  }
-  return result
+  // opts.async: the blocking C-ABI call runs on the libuv pool (napi_async_work) and a Promise is returned
+  if (opts.async) return native.extractAsync(plan, samples, offsets, lengths).then(finish, e => { native.destroyPlan(plan); throw e })
+  return finish(native.extract(plan, samples, offsets, lengths))
 }
+
+// extractAsync(clips, opts, callback?) -> Promise of the same result; the event loop stays free while the GPU works
+function extractAsync (clips, opts, callback) { return extract(clips, Object.assign({}, opts, {async: true}), callback) }
 
 // extractWav(files /* Uint8Array | Uint8Array[] of 16-bit PCM WAV files */, {bufferSize, hop, windowingFunction,
 // features, channel, device}, callback?): BufferLoader + decodeAudioData + getChannelData(channel)
@@ -131,4 +138,4 @@ function extractWav (files, opts, callback) {
   return result
 }
 
-module.exports = {extract, extractWav, featureInfo, isPowerOfTwo, FEATURES}
+module.exports = {extract, extractAsync, extractWav, featureInfo, isPowerOfTwo, FEATURES}

@@ -93,3 +93,19 @@ def test_product_package_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in txt.replace("oracle/ (or", ""), os.path.join(dirpath, f)
+
+
+def test_napi_addon_source_type_checks_against_the_c_abi():
+    """Node and its headers are absent here, so js/addon.cc cannot be built; it is at least type-checked against
+    include/meyda_b200.h and a declaration-only stand-in for node_api.h (tools/napi_stub, documented signatures)."""
+    import shutil
+    import subprocess
+    gxx = shutil.which("g++")
+    if not gxx:
+        pytest.skip("no g++")
+    r = subprocess.run([gxx, "-std=c++17", "-Wall", "-Werror", "-fsyntax-only", "-I", os.path.join(ROOT, "tools", "napi_stub"),
+                        os.path.join(ROOT, "js", "addon.cc")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    src = open(os.path.join(ROOT, "js", "addon.cc")).read()
+    for name in ("mb_plan_create_ex", "mb_extract", "mb_extract_pcm16", "mb_query_output", "mb_wav_parse", "napi_queue_async_work"):
+        assert name in src
