@@ -492,3 +492,76 @@ def test_streaming_and_sharding_with_parameters(golden_audio):
     res = mb.extract([x, x[:5000]], N, hop, features=["mfcc", "loudness"], devices=[0, 0], **params)
     assert np.array_equal(res["mfcc"][:len(batch["mfcc"])], batch["mfcc"], equal_nan=True)
     assert res["loudness"]["specific"].shape[1] == 30
+
+
+# ---- the CUDA path against the reference's own JavaScript outputs (no oracle in between)
+def _js_case_ref(js, ci):
+    """One case of tests/golden/js_reference_vectors.npz (what the unmodified .js files returned under minijs,
+    tools/make_js_golden.py) in the oracle's result layout."""
+    g = lambda k: np.asarray(js["%d/%s" % (ci, k)])  # noqa: E731
+    ref = {k: g(k).reshape(1).astype(np.float64) for k in parity.NUMBER_FIELDS.values() if "%d/%s" % (ci, k) in js}
+    ref["spectralRolloff"] = g("spectralRolloff").reshape(1).astype(np.float64)
+    ref["zcr"] = g("zcr").reshape(1)
+    for k in ("buffer", "amplitudeSpectrum", "powerSpectrum", "mfcc"):
+        ref[k] = g(k)[None].astype(np.float32)
+    ref["complexSpectrum"] = {"real": g("complexSpectrum.real")[None].astype(np.float32),
+                              "imag": g("complexSpectrum.imag")[None].astype(np.float32)}
+    ref["loudness"] = {"specific": g("loudness.specific")[None].astype(np.float32),
+                       "total": g("loudness.total").reshape(1).astype(np.float64)}
+    return ref
+
+
+@pytest.mark.parametrize("flags", FLAG_VARIANTS)
+def test_cuda_against_the_reference_javascript_vectors(golden_audio, flags):
+    js = np.load(os.path.join(os.path.dirname(__file__), "golden", "js_reference_vectors.npz"))
+    cases = [str(c).split("/") for c in js["cases"]]
+    exact = bool(flags & EXACT)
+    checked = 0
+    for ci, (clip, N, f, window) in enumerate(cases):
+        N, f = int(N), int(f)
+        if clip == "nan" and not exact:
+            continue  # (DESIGN.md section 5: a NaN on a window zero; only the exact mode keeps the reference's finite imag plane)
+        sig = golden_audio[clip][f * N:(f + 1) * N] if clip in golden_audio else mo.degenerate_frame(clip, N)
+        out, per = run_gpu(sig, N, window=window, flags=flags)
+        assert per.tolist() == [1]
+        noise = None if exact else mo.noise_band(sig, N, N, SR, window)
+        if clip == "square" and not exact:
+            # DESIGN.md section 5, second corner: the DC bin of this frame cancels to an exact 0 in the reference's
+            # arithmetic, so TWO mel filters are empty there (ln 0 = -Infinity twice, opposite DCT signs: NaN in
+            # coefficients 8..12); a float32 FFT leaves ~1e-9 of rounding noise in that bin and gets -+Infinity
+            m = out.pop("mfcc")[0]
+            assert np.all(m[:8] == -np.inf) and not np.isfinite(m[8:]).any()
+        try:
+            parity.compare_all(out, _js_case_ref(js, ci), N, noise_band=noise, exact=exact)
+        except AssertionError as e:
+            raise AssertionError("case %d %s N=%d frame %d %s: %s" % (ci, clip, N, f, window, e)) from None
+        checked += 1
+    assert checked == (17 if exact else 16)
+
+
+@pytest.mark.parametrize("flags", [pytest.param(_capi.MB_FLAG_GENERIC_KERNEL, id="generic"), pytest.param(EXACT, id="exact")])
+def test_cuda_parameters_against_the_reference_javascript_vectors(golden_audio, flags):
+    """tests/golden/js_reference_params.npz: NUM_BARK_BANDS 30 / 12 / 40, 40 filters, 20 coefficients, fraction 0.85."""
+    js = np.load(os.path.join(os.path.dirname(__file__), "golden", "js_reference_params.npz"))
+    for ci, (clip, N, f, window, nb, edited) in enumerate(str(c).split("/") for c in js["cases"]):
+        N, f, nb = int(N), int(f), int(nb)
+        if clip == "sound3" and not flags & EXACT:
+            continue  # a near-pure tone: bands that hold only FFT rounding noise need the noise band (see verify())
+        params = dict(numBarkBands=nb)
+        if int(edited):
+            params.update(numMelFilters=40, numMfccCoefficients=20, rolloffFraction=0.85)
+        sig = golden_audio[clip][f * N:(f + 1) * N]
+        data, off, ln = mb.meyda._normalize_clips(sig)
+        feats = ["loudness", "perceptualSpread", "perceptualSharpness", "mfcc", "spectralRolloff", "spectralCentroid"]
+        plan = mb.Plan(N, N, SR, window, feats, flags=flags, **params)
+        try:
+            out, _ = plan.extract_host(data, off, ln)
+        finally:
+            plan.close()
+        tol = 5e-6 if flags & EXACT else 1e-3
+        for field, key in (("loudness_total", "loudness.total"), ("perceptual_spread", "perceptualSpread"),
+                           ("perceptual_sharpness", "perceptualSharpness"), ("spectral_centroid", "spectralCentroid"),
+                           ("spectral_rolloff", "spectralRolloff")):
+            parity.assert_numbers(key, out[field], np.asarray(js["%d/%s" % (ci, key)]).reshape(1), tol=tol)
+        parity.assert_numbers("loudness.specific", out["loudness_specific"], js["%d/loudness.specific" % ci][None], tol=tol)
+        parity.assert_numbers("mfcc", out["mfcc"], js["%d/mfcc" % ci][None], tol=tol)
