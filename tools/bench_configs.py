@@ -70,6 +70,9 @@ if "small" in which:  # the reference's own cadence: back-to-back buffers (hop =
     run("config-3 features (mfcc + moments) N=1024 hop=N", 1024, 1024, 3000, 441000, C3)
     run("full set N=512 hop=N, 3000 clips", 512, 512, 3000, 441000, mb.FEATURES)
     run("full set N=1024 hop=N, 3000 clips", 1024, 1024, 3000, 441000, mb.FEATURES)
+if "c1" in which:  # BASELINE config 1's feature list at the reference's default bufferSize
+    run("config-1 features N=512 hop=N, 3000 clips", 512, 512, 3000, 441000, ["rms", "energy", "zcr", "amplitudeSpectrum", "spectralCentroid"])
+    run("config-1 features N=512 hop=N/4", 512, 128, 800, 441000, ["rms", "energy", "zcr", "amplitudeSpectrum", "spectralCentroid"])
 if "sizes" in which:
     for N in (256, 512, 1024, 4096):
         run("full set N=%d hop=N/4" % N, N, N // 4, 400, 441000, mb.FEATURES)
