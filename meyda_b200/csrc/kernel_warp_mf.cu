@@ -133,6 +133,10 @@ mb_warpmf_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ Mb
         (mask & (MB_FEATURE_BIT(MB_FEAT_SPECTRAL_CENTROID) | MB_FEATURE_BIT(MB_FEAT_SPECTRAL_SPREAD) |
                  MB_FEATURE_BIT(MB_FEAT_SPECTRAL_SKEWNESS) | MB_FEATURE_BIT(MB_FEAT_SPECTRAL_KURTOSIS) |
                  MB_FEATURE_BIT(MB_FEAT_SPECTRAL_FLATNESS) | MB_FEATURE_BIT(MB_FEAT_SPECTRAL_SLOPE)));
+    // sum k^2 a .. sum k^4 a are only needed by spread / skewness / kurtosis (centroid, flatness and slope stop at k a)
+    // (decided at compile time only: the run-time-mask instantiation keeps all five sums, a branch there cost 3 %)
+    constexpr bool want_high = kMask == 0 || (kMask & (MB_FEATURE_BIT(MB_FEAT_SPECTRAL_SPREAD) | MB_FEATURE_BIT(MB_FEAT_SPECTRAL_SKEWNESS) |
+                                                       MB_FEATURE_BIT(MB_FEAT_SPECTRAL_KURTOSIS))) != 0;
     const bool want_log = mb_has(mask, MB_FEAT_SPECTRAL_FLATNESS);
     const bool want_rolloff = mb_has(mask, MB_FEAT_SPECTRAL_ROLLOFF);
     const bool want_bark = (mask & (MB_FEATURE_BIT(MB_FEAT_LOUDNESS) | MB_FEATURE_BIT(MB_FEAT_PERCEPTUAL_SPREAD) |
@@ -475,9 +479,11 @@ mb_warpmf_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ Mb
                             ta += ad;
                             if (want_moments) {
                                 t1 = fma(ad, (double)i, t1);
-                                t2 = fma(ad, (double)(i * i), t2);
-                                t3 = fma(ad, (double)(i * i * i), t3);
-                                t4 = fma(ad, (double)(i * i * i * i), t4);
+                                if (want_high) {
+                                    t2 = fma(ad, (double)(i * i), t2);
+                                    t3 = fma(ad, (double)(i * i * i), t3);
+                                    t4 = fma(ad, (double)(i * i * i * i), t4);
+                                }
                             }
                         }
                         if (!want_pieces) continue;
@@ -525,17 +531,21 @@ mb_warpmf_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ Mb
                     if (want_moments) {
                         const double c = (double)(32 * lp), c2 = c * c;  // bins counted inside the lane's own frame
                         const double s1 = fma(c, ta, t1);
-                        const double s2 = fma(c2, ta, fma(2.0 * c, t1, t2));
-                        const double s3 = fma(c2 * c, ta, fma(3.0 * c2, t1, fma(3.0 * c, t2, t3)));
-                        const double s4 = fma(c2 * c2, ta, fma(4.0 * c2 * c, t1, fma(6.0 * c2, t2, fma(4.0 * c, t3, t4))));
-                        const double r0 = group_sum_d<kA>(ta), r1 = group_sum_d<kA>(s1), r2 = group_sum_d<kA>(s2),
-                                     r3 = group_sum_d<kA>(s3), r4 = group_sum_d<kA>(s4);
+                        const double r0 = group_sum_d<kA>(ta), r1 = group_sum_d<kA>(s1);
                         if (lp == 0 && lf < nfg) {
                             if (!want_rolloff) stash_put_d(stash, 2, j + lf, r0);
                             stash_put_d(stash, 4, j + lf, r1);
-                            stash_put_d(stash, 6, j + lf, r2);
-                            stash_put_d(stash, 8, j + lf, r3);
-                            stash_put_d(stash, 10, j + lf, r4);
+                        }
+                        if (want_high) {
+                            const double s2 = fma(c2, ta, fma(2.0 * c, t1, t2));
+                            const double s3 = fma(c2 * c, ta, fma(3.0 * c2, t1, fma(3.0 * c, t2, t3)));
+                            const double s4 = fma(c2 * c2, ta, fma(4.0 * c2 * c, t1, fma(6.0 * c2, t2, fma(4.0 * c, t3, t4))));
+                            const double r2 = group_sum_d<kA>(s2), r3 = group_sum_d<kA>(s3), r4 = group_sum_d<kA>(s4);
+                            if (lp == 0 && lf < nfg) {
+                                stash_put_d(stash, 6, j + lf, r2);
+                                stash_put_d(stash, 8, j + lf, r3);
+                                stash_put_d(stash, 10, j + lf, r4);
+                            }
                         }
                     }
                     if (want_rolloff) {
@@ -700,7 +710,10 @@ cudaError_t mb_launch_warpmf(const MbDevPlan &P, const MbClipTable &T, const flo
                                                        MB_FEATURE_BIT(MB_FEAT_AMPLITUDE_SPECTRUM) | MB_FEATURE_BIT(MB_FEAT_POWER_SPECTRUM));
 #define MB_PICK2(A, MASK) (pcm ? mb_warpmf_kernel<A, true, MASK> : mb_warpmf_kernel<A, false, MASK>)
 #define MB_PICK(A) (m == MB_ALL_FEATURES ? MB_PICK2(A, MB_ALL_FEATURES) : m == kNoArrays ? MB_PICK2(A, kNoArrays) : MB_PICK2(A, 0u))
-    auto kernel = P.N == 1024 ? MB_PICK(16) : P.N == 512 ? MB_PICK(8)
+    // BASELINE config 1 (the feature list of the reference's own demo run) at the reference's default bufferSize
+    constexpr uint32_t kConfig1 = MB_FEATURE_BIT(MB_FEAT_RMS) | MB_FEATURE_BIT(MB_FEAT_ENERGY) | MB_FEATURE_BIT(MB_FEAT_ZCR) |
+                                  MB_FEATURE_BIT(MB_FEAT_AMPLITUDE_SPECTRUM) | MB_FEATURE_BIT(MB_FEAT_SPECTRAL_CENTROID);
+    auto kernel = P.N == 1024 ? MB_PICK(16) : P.N == 512 ? (m == kConfig1 ? MB_PICK2(8, kConfig1) : MB_PICK(8))
                   : (m == MB_ALL_FEATURES ? MB_PICK2(4, MB_ALL_FEATURES) : MB_PICK2(4, 0u));
 #undef MB_PICK
 #undef MB_PICK2
