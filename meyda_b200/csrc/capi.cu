@@ -662,7 +662,7 @@ mb_status mb_plan_create_ex(mb_plan **plan, int device, int buffer_size, int hop
     }
     D.warp_tables = nullptr;
     if (N == 32768 && !D.exact && !(flags & MB_FLAG_GENERIC_KERNEL) &&  // (shares the generic epilogue: any parameters)
-        (size_t)prop.sharedMemPerBlockOptin >= mb_big32768_smem_bytes() + 2048) {
+        (size_t)prop.sharedMemPerBlockOptin >= mb_big32768_smem_bytes() + 4096) {  // (+ the kernel's static scratch)
         p->has_big_kernel = true;
         p->kernel_name = "big32768";
     }

@@ -171,6 +171,7 @@ struct Scratch {
     float red_f[kWarps];
     int red_i[kWarps];
     double scan_d[kWarps];
+    double red6[6][kWarps];
     double band_sum[MB_MAX_BARK_BANDS];
     float specific[MB_MAX_BARK_BANDS];
     float mel_log[MB_MAX_MEL_FILTERS];
@@ -183,7 +184,7 @@ __device__ __forceinline__ void frame_epilogue(const MbDevPlan &P, const mb_outp
     const uint32_t mask = P.mask;
     const int nb = P.nb, nf = P.nf, nc = P.nc;  // 24 / 26 / 13 unless the plan was created with other parameters
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    double *red_d = sc.red_d, *scan_d = sc.scan_d, *band_sum = sc.band_sum;
+    double *scan_d = sc.scan_d, *band_sum = sc.band_sum;
     int *red_i = sc.red_i;
     float *specific = sc.specific, *mel_log = sc.mel_log;
     const bool want_moments =
@@ -194,12 +195,22 @@ __device__ __forceinline__ void frame_epilogue(const MbDevPlan &P, const mb_outp
     const bool want_bark = mask & (MB_FEATURE_BIT(MB_FEAT_LOUDNESS) | MB_FEATURE_BIT(MB_FEAT_PERCEPTUAL_SPREAD) |
                                    MB_FEATURE_BIT(MB_FEAT_PERCEPTUAL_SHARPNESS));
     if (want_moments) {
-        S.s0 = block_sum(acc.s0, red_d);
-        S.s1 = block_sum(acc.s1, red_d);
-        S.s2 = block_sum(acc.s2, red_d);
-        S.s3 = block_sum(acc.s3, red_d);
-        S.s4 = block_sum(acc.s4, red_d);
-        if (want_log) S.log2sum = block_sum(acc.lg, red_d);
+        // the six sums through ONE pair of barriers (each is reduced exactly as block_sum would: same bits)
+        double v[6] = {acc.s0, acc.s1, acc.s2, acc.s3, acc.s4, acc.lg};
+#pragma unroll
+        for (int q = 0; q < 6; q++) v[q] = mb_warp_sum(v[q]);
+        if constexpr (kWarps > 1) {
+            block_sync();
+            if (lane == 0) {
+#pragma unroll
+                for (int q = 0; q < 6; q++) sc.red6[q][warp] = v[q];
+            }
+            block_sync();
+#pragma unroll
+            for (int q = 0; q < 6; q++) v[q] = mb_warp_sum(lane < kWarps ? sc.red6[q][lane] : 0.0);
+        }
+        S.s0 = v[0]; S.s1 = v[1]; S.s2 = v[2]; S.s3 = v[3]; S.s4 = v[4];
+        if (want_log) S.log2sum = v[5];
     }
     block_sync();
 
