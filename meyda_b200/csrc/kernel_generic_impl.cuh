@@ -394,7 +394,7 @@ mb_generic_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ M
     const bool want_spectrum = (mask & ~time_only) != 0;
 
     for (int64_t g = blockIdx.x; g < T.total_frames; g += gridDim.x) {
-        const int64_t clip = mb_find_clip(T, g);
+        const int64_t clip = mb_find_clip_warp(T, g);
         const MbFrameSrc src = mb_frame_src(T, samples, T.clip_off[clip] + (g - T.frame_start[clip]) * (int64_t)P.hop);
 
         MbFrameSums S;
@@ -573,7 +573,7 @@ mb_exact_cluster_kernel(const __grid_constant__ MbDevPlan P, const __grid_consta
     const int64_t n_clusters = gridDim.x / 2, cid = blockIdx.x / 2;
 
     for (int64_t g = cid; g < T.total_frames; g += n_clusters) {
-        const int64_t clip = mb_find_clip(T, g);
+        const int64_t clip = mb_find_clip_warp(T, g);
         const MbFrameSrc src = mb_frame_src(T, samples, T.clip_off[clip] + (g - T.frame_start[clip]) * (int64_t)P.hop);
         MbFrameSums S;
         S.s0 = S.s1 = S.s2 = S.s3 = S.s4 = S.log2sum = S.energy = 0;
@@ -699,8 +699,9 @@ mb_big32768_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
     block_sync();
     float2 *slot = B.area + warp * kBigSlot;  // this warp's transpose slot / sub-spectrum row
 
+    int64_t clip_next = -1;  // the clip of this CTA's next frame, found while its samples are prefetched
     for (int64_t g = blockIdx.x; g < T.total_frames; g += gridDim.x) {
-        const int64_t clip = mb_find_clip(T, g);
+        const int64_t clip = clip_next >= 0 ? clip_next : mb_find_clip_warp(T, g);
         const float *__restrict__ src = samples + T.clip_off[clip] + (g - T.frame_start[clip]) * (int64_t)P.hop;
         MbFrameSums S;
         S.s0 = S.s1 = S.s2 = S.s3 = S.s4 = S.log2sum = S.energy = 0;
@@ -758,6 +759,17 @@ mb_big32768_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
             }
         }
         const float unscale = ldexpf(1.f, -kscale);
+        {   // this CTA's next frame on its way into L2 while the current one is transformed (its 128 KB were
+            // otherwise fetched with four exposed round trips at the top of the next iteration)
+            const int64_t gn = g + gridDim.x;
+            clip_next = -1;
+            if (gn < T.total_frames) {
+                clip_next = mb_find_clip_warp(T, gn);
+                const float *nsrc = samples + T.clip_off[clip_next] + (gn - T.frame_start[clip_next]) * (int64_t)P.hop;
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(nsrc + 32 * tid));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(nsrc + 32 * (tid + kThreads)));
+            }
+        }
         block_sync();
 
         if (want_spectrum) {
