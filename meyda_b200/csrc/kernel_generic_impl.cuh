@@ -716,7 +716,7 @@ mb_big32768_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
             float mxabs = 0.f;
             const float4 *__restrict__ src4 = reinterpret_cast<const float4 *>(src);
             const float4 *__restrict__ win4 = reinterpret_cast<const float4 *>(P.window);
-#pragma unroll 4
+#pragma unroll 8
             for (int i = tid; i < N / 4; i += kThreads) {
                 const float4 x = __ldg(src4 + i), w = __ldg(win4 + i);
                 mxabs = fmaxf(mxabs, fmaxf(fmaxf(fabsf(x.x), fabsf(x.y)), fmaxf(fabsf(x.z), fabsf(x.w))));
@@ -823,7 +823,7 @@ mb_big32768_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
             // ---- 6. real-FFT split, spectra out, amplitude into smem, moment partials
             MomentAcc acc;
             const float sc_n = P.inv_sqrt_N;
-#pragma unroll 4
+#pragma unroll 8
             for (int k = tid; k < M; k += kThreads) {
                 const float2 w = __ldg(&P.twN[k]);  // 128 KB table, L2-resident: issued first, four in flight
                 const float2 a = B.area[k];
