@@ -661,10 +661,10 @@ mb_status mb_plan_create_ex(mb_plan **plan, int device, int buffer_size, int hop
         p->kernel_name = "exact-cluster2";
     }
     D.warp_tables = nullptr;
-    if (N == 32768 && !D.exact && !(flags & MB_FLAG_GENERIC_KERNEL) &&  // (shares the generic epilogue: any parameters)
-        (size_t)prop.sharedMemPerBlockOptin >= mb_big32768_smem_bytes() + 4096) {  // (+ the kernel's static scratch)
-        p->has_big_kernel = true;
-        p->kernel_name = "big32768";
+    if (N >= 4096 && !D.exact && !(flags & MB_FLAG_GENERIC_KERNEL) &&  // (shares the generic epilogue: any parameters)
+        (size_t)prop.sharedMemPerBlockOptin >= mb_big_smem_bytes(N) + 4096) {  // (+ the kernel's static scratch)
+        p->has_big_kernel = true;  // bufferSize / 2048 warps per frame
+        p->kernel_name = N == 32768 ? "big32768" : N == 16384 ? "big16384" : N == 8192 ? "big8192" : "big4096";
     }
     if (N == 2048 && !D.exact && !(flags & MB_FLAG_GENERIC_KERNEL) && reference_params) {
         MbWarpTables *W = new MbWarpTables();

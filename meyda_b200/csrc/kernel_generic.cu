@@ -91,19 +91,36 @@ MB_DEFINE_LAUNCH_GENERIC(g128, 128)
 MB_DEFINE_LAUNCH_GENERIC(g256, 256)
 MB_DEFINE_LAUNCH_GENERIC(g1024, 1024)
 
-size_t mb_big32768_smem_bytes() { return sizeof(g512::BigSmem); }
+// bufferSize 4096 / 8192 / 16384 / 32768: R = bufferSize / 2048 warps per frame, 16 / R persistent CTAs per SM
+size_t mb_big_smem_bytes(int N) {
+    return N == 32768 ? sizeof(g512::BigSmem) : N == 16384 ? sizeof(g256::BigSmem) : N == 8192 ? sizeof(g128::BigSmem)
+                                                                                               : sizeof(g64::BigSmem);
+}
+size_t mb_big32768_smem_bytes() { return mb_big_smem_bytes(32768); }
 
-cudaError_t mb_launch_big32768(const MbDevPlan &P, const MbClipTable &T, const float *samples, const mb_outputs &O,
-                               int num_sms, cudaStream_t stream) {
-    const size_t smem = mb_big32768_smem_bytes();
-    cudaError_t e = cudaFuncSetAttribute(g512::mb_big32768_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+template <typename K>
+static cudaError_t launch_big(K kernel, int threads, const MbDevPlan &P, const MbClipTable &T, const float *samples,
+                              const mb_outputs &O, int num_sms, cudaStream_t stream) {
+    const size_t smem = mb_big_smem_bytes(P.N);
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    int64_t grid = num_sms;
+    int per_sm = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem);
+    if (per_sm < 1) per_sm = 1;
+    int64_t grid = (int64_t)num_sms * per_sm;
     if (grid > T.total_frames) grid = T.total_frames;
     if (grid < 1) return cudaSuccess;
     (void)cudaGetLastError();
-    g512::mb_big32768_kernel<<<(unsigned)grid, 512, smem, stream>>>(P, T, samples, O);
+    kernel<<<(unsigned)grid, threads, smem, stream>>>(P, T, samples, O);
     return cudaGetLastError();
+}
+
+cudaError_t mb_launch_big32768(const MbDevPlan &P, const MbClipTable &T, const float *samples, const mb_outputs &O,
+                               int num_sms, cudaStream_t stream) {
+    if (P.N == 32768) return launch_big(g512::mb_big32768_kernel, 512, P, T, samples, O, num_sms, stream);
+    if (P.N == 16384) return launch_big(g256::mb_big32768_kernel, 256, P, T, samples, O, num_sms, stream);
+    if (P.N == 8192) return launch_big(g128::mb_big32768_kernel, 128, P, T, samples, O, num_sms, stream);
+    return launch_big(g64::mb_big32768_kernel, 64, P, T, samples, O, num_sms, stream);
 }
 
 size_t mb_exact_cluster_smem_bytes(int N) {

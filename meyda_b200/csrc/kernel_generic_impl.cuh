@@ -644,8 +644,10 @@ mb_exact_cluster_kernel(const __grid_constant__ MbDevPlan P, const __grid_consta
 
 #endif
 
-#if MB_GENERIC_THREADS == 512
-// ---- bufferSize 32768, float32 FFT: one CTA (16 warps) per frame ---------------------------------
+#if MB_GENERIC_THREADS == 64 || MB_GENERIC_THREADS == 128 || MB_GENERIC_THREADS == 256 || MB_GENERIC_THREADS == 512
+// ---- bufferSize 4096 / 8192 / 16384 / 32768, float32 FFT: one CTA of R = 2 / 4 / 8 / 16 warps per frame ----------
+// (written for R = 16, bufferSize 32768 = BASELINE config 5, and described for it; the same code compiled in the
+// 64- / 128- / 256-thread instantiations of this header serves the three sizes below it with 8 / 4 / 2 CTAs per SM)
 // The packed frame is M = 16384 complex points = 16 x 1024.  Decimation in time by 16: warp r
 // transforms z_r[m] = z[16 m + r] with the same 32 x 32 register FFT as the bufferSize-2048 kernel
 // (two register FFTs and one transpose through the warp's slot), multiplies X_r[k] by
@@ -653,15 +655,16 @@ mb_exact_cluster_kernel(const __grid_constant__ MbDevPlan P, const __grid_consta
 // C[k + 1024 q].  Shared memory (213 KB): one 136 KB area that is in turn the padded windowed frame,
 // the sixteen transpose slots, the twiddled sub-spectra and the natural-order spectrum; 64 KB of
 // amplitudes for the band features; 12 KB of twiddle tables.
-constexpr int kBigN = 32768, kBigM = 16384, kBigRow = 33, kBigSlot = 32 * kBigRow;  // slot: 1056 float2
+constexpr int kBigR = kWarps, kBigLogR = kBigR == 16 ? 4 : kBigR == 8 ? 3 : kBigR == 4 ? 2 : 1, kBigK = 32 / kBigR;
+constexpr int kBigN = 2048 * kBigR, kBigM = 1024 * kBigR, kBigRow = 33, kBigSlot = 32 * kBigRow;  // slot: 1056 float2
 struct BigSmem {
     float2 area[kBigM + kBigM / 16];  // 17408 float2: z padded one per 16; >= 16 slots of 1056; >= C[16384]
     float amp[kBigM];
     float2 tw32[32 * 32];             // exp(+2 pi i b c / 1024) at [c*32 + b]
-    float2 tw16[16 * 32];             // exp(+2 pi i r d / 512) at [r*32 + d]
+    float2 tw16[kBigR * 32];          // exp(+2 pi i r d / (32 R)) at [r*32 + d]  (R = 16: / 512)
 };
 
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads, 512 / kThreads)
 mb_big32768_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ MbClipTable T,
                    const float *__restrict__ samples, const __grid_constant__ mb_outputs O) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -687,8 +690,8 @@ mb_big32768_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
         const double ang = 2.0 * 3.14159265358979323846 * (double)((i >> 5) * (i & 31)) / 1024.0;
         B.tw32[i] = make_float2((float)cos(ang), (float)sin(ang));
     }
-    for (int i = tid; i < 16 * 32; i += kThreads) {
-        const double ang = 2.0 * 3.14159265358979323846 * (double)((i >> 5) * (i & 31)) / 512.0;
+    for (int i = tid; i < kBigR * 32; i += kThreads) {
+        const double ang = 2.0 * 3.14159265358979323846 * (double)((i >> 5) * (i & 31)) / (32.0 * kBigR);
         B.tw16[i] = make_float2((float)cos(ang), (float)sin(ang));
     }
     float2 tw_own;
@@ -776,7 +779,10 @@ mb_big32768_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
             // ---- 2. warp r takes z[16 m + r], m = 32 a + lane
             float2 v[32];
 #pragma unroll
-            for (int a = 0; a < 32; a++) v[a] = B.area[544 * a + 17 * lane + warp];  // (512a+16b+r) + its padding (32a+b)
+            for (int a = 0; a < 32; a++) {  // z[R m + r], m = 32 a + lane, behind its padding (R = 16: 544 a + 17 lane + r)
+                const int zi = 32 * kBigR * a + kBigR * lane + warp;
+                v[a] = B.area[zi + (zi >> 4)];
+            }
             block_sync();  // everybody has its samples: the area becomes the sixteen warp slots
             // ---- 3. the 1024-point sub-FFT of this warp: 32 x 32 in registers, one transpose through the slot
 #pragma unroll 1
@@ -804,20 +810,20 @@ mb_big32768_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
                 slot[lane + 32 * d] = y;
             }
             block_sync();
-            // ---- 5. radix-16 across the warps' rows: C[k + 1024 q] for k = tid, tid + 512
-            float2 u0[16], u1[16];
+            // ---- 5. radix-R across the warps' rows: C[k + 1024 q] for k = tid + kThreads kk (R = 16: k = tid, tid + 512)
+            float2 u[kBigK][kBigR];
 #pragma unroll
-            for (int r = 0; r < 16; r++) {
-                u0[r] = B.area[r * kBigSlot + tid];
-                u1[r] = B.area[r * kBigSlot + tid + 512];
+            for (int kk = 0; kk < kBigK; kk++) {
+#pragma unroll
+                for (int r = 0; r < kBigR; r++) u[kk][r] = B.area[r * kBigSlot + tid + kThreads * kk];
             }
-            mbfft::fft_reg<16>(u0);
-            mbfft::fft_reg<16>(u1);
+#pragma unroll
+            for (int kk = 0; kk < kBigK; kk++) mbfft::fft_reg<kBigR>(u[kk]);
             block_sync();  // all rows consumed: the area becomes the natural-order spectrum C[0 .. M)
 #pragma unroll
-            for (int q = 0; q < 16; q++) {
-                B.area[tid + 1024 * q] = u0[mbfft::brev<4>(q)];
-                B.area[tid + 512 + 1024 * q] = u1[mbfft::brev<4>(q)];
+            for (int kk = 0; kk < kBigK; kk++) {
+#pragma unroll
+                for (int q = 0; q < kBigR; q++) B.area[tid + kThreads * kk + 1024 * q] = u[kk][mbfft::brev<kBigLogR>(q)];
             }
             block_sync();
             // ---- 6. real-FFT split, spectra out, amplitude into smem, moment partials
@@ -857,4 +863,4 @@ mb_big32768_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
         block_sync();  // smem reused by the next frame
     }
 }
-#endif  // MB_GENERIC_THREADS == 512
+#endif  // MB_GENERIC_THREADS == 64 .. 512

@@ -20,6 +20,7 @@ cudaError_t mb_launch_warpmf(const MbDevPlan &P, const MbClipTable &T, const flo
 // bufferSize 32768, float32 FFT: 16 warps per frame (16 x 1024-point register sub-FFTs + radix-16 combine).
 // Needs 16-byte aligned frames like the warp kernel.
 size_t mb_big32768_smem_bytes();
+size_t mb_big_smem_bytes(int N);  // bufferSize 4096 / 8192 / 16384 / 32768
 cudaError_t mb_launch_big32768(const MbDevPlan &P, const MbClipTable &T, const float *samples, const mb_outputs &O,
                                int num_sms, cudaStream_t stream);
 

@@ -135,16 +135,48 @@ def test_ragged_and_empty_clips(flags):
 
 
 @pytest.mark.parametrize("flags", FLAG_VARIANTS)
-@pytest.mark.parametrize("N", [16, 64, 128, 4096, 8192, 32768])
+@pytest.mark.parametrize("N", [16, 64, 128, 4096, 8192, 16384, 32768])
 def test_other_buffer_sizes(N, flags):
     if (flags & EXACT) and N > 16384:  # does not fit one CTA: the 2-CTA cluster kernel takes over
         plan = mb.Plan(N, N, SR, flags=flags)
         assert plan.kernel_name == "exact-cluster2"
         plan.close()
+    if flags == 0:  # bufferSize / 2048 warps per frame from 4096 up
+        plan = mb.Plan(N, N // 4, SR)
+        assert plan.kernel_name == ("big%d" % N if N >= 4096 else "generic")
+        plan.close()
     x = mo.synth_clip(N, N * 3 + 5)
     hop = N // 4
     out, per = run_gpu(x, N, hop, flags=flags)
     verify(out, x, N, hop, flags=flags)
+
+
+@pytest.mark.parametrize("N", [4096, 8192, 16384])
+def test_multi_warp_frame_kernels(N):
+    """The bufferSize-32768 kernel compiled for 2 / 4 / 8 warps per frame: many frames (several CTAs per SM, the
+    grid-stride loop, the prefetch of the next frame), ragged clips, feature subsets, and a misaligned clip that
+    must fall back to the generic kernel with results inside the same tolerances."""
+    lens = [N * 6 + 4 * 37, N - 4, N, 0, N * 9, N * 2 + 8]
+    clips = [mo.synth_clip(700 + i, L) for i, L in enumerate(lens)]
+    hop = N // 4
+    out, per = run_gpu(clips, N, hop)
+    assert per.tolist() == [mo.num_frames(L, N, hop) for L in lens]
+    verify(out, clips, N, hop)
+    sub, _ = run_gpu(clips, N, hop, features=["amplitudeSpectrum", "spectralRolloff", "spectralFlatness", "spectralSlope"])
+    for k in sub:
+        assert np.array_equal(sub[k], out[k], equal_nan=True), k
+    # many frames through few CTAs: every frame equals its single-clip run bit for bit
+    x = mo.synth_clip(901, N + hop * 700)
+    big, per = run_gpu(x, N, hop, features=["rms", "spectralCentroid", "mfcc", "loudness"])
+    assert per[0] == 701
+    pick = [0, 1, 147, 148, 295, 296, 592, 699, 700]
+    for f in pick:
+        one, _ = run_gpu(x[f * hop:f * hop + N], N, hop, features=["rms", "spectralCentroid", "mfcc", "loudness"])
+        for k in one:
+            assert np.array_equal(one[k][0], big[k][f], equal_nan=True), (k, f)
+    odd = [np.concatenate([np.zeros(1, np.float32), clips[0]])[1:], clips[4]]  # same samples, fresh arrays
+    out2, _ = run_gpu(odd, N, hop + 2)  # hop not a multiple of 4: the generic kernel
+    verify(out2, odd, N, hop + 2)
 
 
 @pytest.mark.parametrize("flags", FLAG_VARIANTS)

@@ -73,6 +73,10 @@ if "small" in which:  # the reference's own cadence: back-to-back buffers (hop =
 if "c1" in which:  # BASELINE config 1's feature list at the reference's default bufferSize
     run("config-1 features N=512 hop=N, 3000 clips", 512, 512, 3000, 441000, ["rms", "energy", "zcr", "amplitudeSpectrum", "spectralCentroid"])
     run("config-1 features N=512 hop=N/4", 512, 128, 800, 441000, ["rms", "energy", "zcr", "amplitudeSpectrum", "spectralCentroid"])
+if "large" in which:
+    for N in (4096, 8192, 16384, 32768):
+        run("full set N=%d hop=N/4" % N, N, N // 4, 64, 2646000, mb.FEATURES)
+        run("config-5 features N=%d hop=N/4" % N, N, N // 4, 256, 2646000, C5)
 if "sizes" in which:
     for N in (256, 512, 1024, 4096):
         run("full set N=%d hop=N/4" % N, N, N // 4, 400, 441000, mb.FEATURES)
