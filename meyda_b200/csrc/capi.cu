@@ -293,14 +293,14 @@ mb_status launch(mb_plan *p, const int64_t *d_off, const int64_t *d_frame_start,
     const bool pcm = pcm_channels > 0;
     // the tuned kernels take float32 mono or 16-bit PCM; other payloads go through the generic kernel's loader
     const bool tuned_ok = !pcm || pcm_format == MB_SAMPLE_S16;
-    // 16-byte aligned frames: required by the bufferSize-32768 kernel's float4 loads; the warp kernel takes
-    // any float-aligned frame (misaligned ones bypass TMA inside the kernel) but bulk-stores `buffer` rows
+    // the tuned kernels take any float-aligned frame (misaligned ones bypass TMA / the float4 loads inside the
+    // kernel, same bits) but store `buffer` rows 16 bytes at a time
     const bool out_ok = (uintptr_t)d_out.buffer % 16 == 0;
-    const bool tma_ok = aligned && ((uintptr_t)d_samples % 16 == 0) && out_ok && (p->hop % 4 == 0);
+    (void)aligned;
     if (p->use_cluster) {
         MB_CUDA(mb_launch_exact_cluster(p->dev, T, d_samples, d_out, p->num_sms, stream));
         p->launches_generic++;
-    } else if (p->has_big_kernel && tma_ok && !pcm) {
+    } else if (p->has_big_kernel && out_ok && !pcm && ((uintptr_t)d_samples % 4 == 0)) {  // (misaligned frames: read by the lanes)
         MB_CUDA(mb_launch_big32768(p->dev, T, d_samples, d_out, p->num_sms, stream));
         p->launches_warp++;
     } else if (p->has_warp_kernel && tuned_ok && out_ok && ((uintptr_t)d_samples % (pcm ? 2 : 4) == 0)) {

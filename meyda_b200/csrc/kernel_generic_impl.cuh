@@ -719,9 +719,11 @@ mb_big32768_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
             float mxabs = 0.f;
             const float4 *__restrict__ src4 = reinterpret_cast<const float4 *>(src);
             const float4 *__restrict__ win4 = reinterpret_cast<const float4 *>(P.window);
-#pragma unroll 8
-            for (int i = tid; i < N / 4; i += kThreads) {
-                const float4 x = __ldg(src4 + i), w = __ldg(win4 + i);
+            // a frame off the 16-byte grid (odd clip offsets, hop not a multiple of 4) is read sample by sample:
+            // same values, same arithmetic, so a frame's bits do not depend on where it lies
+            const bool src_aligned = (reinterpret_cast<uintptr_t>(src) & 15) == 0;
+            auto take = [&](const int i, const float4 x) {
+                const float4 w = __ldg(win4 + i);
                 mxabs = fmaxf(mxabs, fmaxf(fmaxf(fabsf(x.x), fabsf(x.y)), fmaxf(fabsf(x.z), fabsf(x.w))));
                 if (want_time) {
                     e += (double)(x.x * x.x + x.y * x.y) + (double)(x.z * x.z + x.w * x.w);
@@ -735,6 +737,14 @@ mb_big32768_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
                 const int m0 = 2 * i, m1 = 2 * i + 1;
                 B.area[m0 + (m0 >> 4)] = make_float2(__fmul_rn(x.x, w.x), __fmul_rn(x.y, w.y));
                 B.area[m1 + (m1 >> 4)] = make_float2(__fmul_rn(x.z, w.z), __fmul_rn(x.w, w.w));
+            };
+            if (src_aligned) {
+#pragma unroll 8
+                for (int i = tid; i < N / 4; i += kThreads) take(i, __ldg(src4 + i));
+            } else {
+#pragma unroll 2
+                for (int i = tid; i < N / 4; i += kThreads)
+                    take(i, make_float4(__ldg(src + 4 * i), __ldg(src + 4 * i + 1), __ldg(src + 4 * i + 2), __ldg(src + 4 * i + 3)));
             }
             if (want_time) {
                 S.energy = block_sum(e, sc.red_d);
@@ -778,11 +788,10 @@ mb_big32768_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
         if (want_spectrum) {
             // ---- 2. warp r takes z[16 m + r], m = 32 a + lane
             float2 v[32];
+            // z[R m + r], m = 32 a + lane, behind its padding of one per 16: (32 R a + R lane + r) >> 4 = 2 R a + const
+            const int z0 = kBigR * lane + warp, zb = z0 + (z0 >> 4);  // (R = 16: 544 a + 17 lane + r)
 #pragma unroll
-            for (int a = 0; a < 32; a++) {  // z[R m + r], m = 32 a + lane, behind its padding (R = 16: 544 a + 17 lane + r)
-                const int zi = 32 * kBigR * a + kBigR * lane + warp;
-                v[a] = B.area[zi + (zi >> 4)];
-            }
+            for (int a = 0; a < 32; a++) v[a] = B.area[34 * kBigR * a + zb];
             block_sync();  // everybody has its samples: the area becomes the sixteen warp slots
             // ---- 3. the 1024-point sub-FFT of this warp: 32 x 32 in registers, one transpose through the slot
 #pragma unroll 1
@@ -813,17 +822,17 @@ mb_big32768_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
             // ---- 5. radix-R across the warps' rows: C[k + 1024 q] for k = tid + kThreads kk (R = 16: k = tid, tid + 512)
             float2 u[kBigK][kBigR];
 #pragma unroll
-            for (int kk = 0; kk < kBigK; kk++) {
+            for (int r = 0; r < kBigR; r++) {
 #pragma unroll
-                for (int r = 0; r < kBigR; r++) u[kk][r] = B.area[r * kBigSlot + tid + kThreads * kk];
+                for (int kk = 0; kk < kBigK; kk++) u[kk][r] = B.area[r * kBigSlot + tid + kThreads * kk];
             }
 #pragma unroll
             for (int kk = 0; kk < kBigK; kk++) mbfft::fft_reg<kBigR>(u[kk]);
             block_sync();  // all rows consumed: the area becomes the natural-order spectrum C[0 .. M)
 #pragma unroll
-            for (int kk = 0; kk < kBigK; kk++) {
+            for (int q = 0; q < kBigR; q++) {
 #pragma unroll
-                for (int q = 0; q < kBigR; q++) B.area[tid + kThreads * kk + 1024 * q] = u[kk][mbfft::brev<kBigLogR>(q)];
+                for (int kk = 0; kk < kBigK; kk++) B.area[tid + kThreads * kk + 1024 * q] = u[kk][mbfft::brev<kBigLogR>(q)];
             }
             block_sync();
             // ---- 6. real-FFT split, spectra out, amplitude into smem, moment partials

@@ -174,9 +174,32 @@ def test_multi_warp_frame_kernels(N):
         one, _ = run_gpu(x[f * hop:f * hop + N], N, hop, features=["rms", "spectralCentroid", "mfcc", "loudness"])
         for k in one:
             assert np.array_equal(one[k][0], big[k][f], equal_nan=True), (k, f)
-    odd = [np.concatenate([np.zeros(1, np.float32), clips[0]])[1:], clips[4]]  # same samples, fresh arrays
-    out2, _ = run_gpu(odd, N, hop + 2)  # hop not a multiple of 4: the generic kernel
-    verify(out2, odd, N, hop + 2)
+    # frames off the 16-byte grid (odd clip lengths in front, hop not a multiple of 4) are read by the lanes inside
+    # the same kernel: same bits as the aligned single-frame run; and streaming in odd blocks == the batch call
+    odd = [mo.synth_clip(77, 3), mo.synth_clip(78, N * 2 + 13), x[:N + 5 * (hop + 2)]]
+    feats = ["rms", "zcr", "spectralCentroid", "spectralKurtosis", "mfcc", "loudness", "amplitudeSpectrum"]
+    out2, per2 = run_gpu(odd, N, hop + 2, features=feats)
+    assert per2.tolist() == [0, mo.num_frames(N * 2 + 13, N, hop + 2), 6]
+    f0 = int(per2[1])
+    for f in range(6):
+        a = f * (hop + 2)
+        one, _ = run_gpu(x[a:a + N].copy(), N, hop + 2, features=feats)
+        for k in one:
+            assert np.array_equal(one[k][0], out2[k][f0 + f], equal_nan=True), (k, f)
+    plan = mb.Plan(N, hop + 2, SR, "hanning", feats)
+    assert plan.kernel_name == "big%d" % N
+    st = mb.Stream(plan)
+    got, pos, rng = [], 0, np.random.default_rng(N)
+    sig = odd[2]
+    while pos < len(sig):
+        step = int(rng.integers(1, 3 * N))
+        got.append(st.push(sig[pos:pos + step]).arrays)
+        pos += step
+    st.close()
+    plan.close()
+    for k in got[0]:
+        cat = np.concatenate([g[k] for g in got])
+        assert np.array_equal(cat, out2[k][f0:], equal_nan=True), k
 
 
 @pytest.mark.parametrize("flags", FLAG_VARIANTS)
