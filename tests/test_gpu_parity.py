@@ -496,7 +496,8 @@ def test_plan_parameters(golden_audio, N, hop, flags, params):
     data, off, ln = mb.meyda._normalize_clips(x)
     plan = mb.Plan(N, hop, SR, "hanning", flags=flags, **params)
     try:
-        assert plan.kernel_name.startswith(("generic", "exact")), plan.kernel_name
+        # never a warp kernel (built around 24 / 26 / 13 / 0.99); the multi-warp-per-frame kernels share the generic epilogue
+        assert plan.kernel_name.startswith(("generic", "exact", "big")), plan.kernel_name
         nb, nc = params.get("numBarkBands", 24), params.get("numMfccCoefficients", 13)
         assert (plan.numBarkBands, plan.numMfccCoefficients) == (nb, nc)
         assert plan.rolloffFraction == params.get("rolloffFraction", 0.99)
