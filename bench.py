@@ -232,6 +232,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--generic", action="store_true", help="force the generic kernel")
+    ap.add_argument("--no-refine", action="store_true", help="float32 FFT only: no adaptive exact second pass (A/B)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
@@ -260,7 +261,7 @@ def main():
     my_clips = c1 - c0
     fpc = frames_per_clip()
     plan = mb.Plan(N, HOP, SR, "hanning", feats, device=local_rank,
-                   flags=_capi.MB_FLAG_GENERIC_KERNEL if args.generic else 0)
+                   flags=(_capi.MB_FLAG_GENERIC_KERNEL if args.generic else 0) | (_capi.MB_FLAG_NO_REFINE if args.no_refine else 0))
     _, lay = plan.query(np.array([CLIP_LEN], np.int64))
     out_bpf = int(lay.bytes_per_frame)
 
@@ -321,6 +322,9 @@ def main():
     barrier()
     ms = e0.elapsed_time(e1)
     launches = plan.launch_count - launches0
+    refined_last_wave = plan.refined_frames  # frames of the last wave redone with the exact FFT (adaptive plans)
+    # the dominant kernel runs once per wave; an adaptive plan adds one (normally empty) exact-FFT launch per wave
+    main_launches = len(wave_tabs) * args.steps
     clocks = sampler.stop() if rank == 0 else None
     if world > 1:
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
@@ -338,8 +342,8 @@ def main():
     # ---- roofline of the dominant (only) kernel on this rank
     peak, peak_src = measured_peaks()
     alg_bpf = algorithmic_bytes_per_frame(feats)
-    avg_launch_s = (ms * 1e-3) / max(1, launches)
-    frames_per_launch = frames_rank * args.steps / max(1, launches)
+    avg_launch_s = (ms * 1e-3) / max(1, main_launches)
+    frames_per_launch = frames_rank * args.steps / max(1, main_launches)
     achieved = alg_bpf * frames_per_launch / avg_launch_s / 1e9
     traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
@@ -426,7 +430,7 @@ def main():
             "config": workload_config(my_clips * world, world, wave_clips),
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": launches_all,
             "clocks": clocks, "parity": parity_note, "kernel": plan.kernel_name,
-            "frames_per_step": frames_all,
+            "frames_per_step": frames_all, "refined_frames_last_wave": refined_last_wave,
         }
         if reduced:
             line["config"]["note"] = "clip count reduced from %d to fit GPU memory" % args.clips

@@ -136,7 +136,14 @@ enum {
     MB_FLAG_EXACT_FFT = 1u << 1,
     /* With MB_FLAG_EXACT_FFT: use the 2-CTA cluster kernel at every bufferSize >= 64
      * (it is automatic above 16384). */
-    MB_FLAG_CLUSTER_FFT = 1u << 2
+    MB_FLAG_CLUSTER_FFT = 1u << 2,
+    /* Float32 FFT only.  By default a float32-FFT plan is ADAPTIVE: the kernels bound, per frame, how far each
+     * requested feature can move under FFT rounding noise, and the frames whose values the reference's own
+     * per-stage float32 rounding decides (near-pure tones, silent bands: x^0.23, ln x and k^3 / k^4 weights
+     * amplify the noise floor without bound) are redone with the MB_FLAG_EXACT_FFT arithmetic, so that every
+     * feature lands within 1e-3 of the reference.  Ordinary (noisy) audio flags nothing.  This flag turns the
+     * second pass off (A/B measurements). */
+    MB_FLAG_NO_REFINE = 1u << 3
 };
 #define MB_MAX_EXACT_BUFFER_SIZE 32768
 
@@ -271,6 +278,9 @@ mb_status mb_wav_parse(const void *file_bytes, int64_t n_bytes, mb_wav_info *inf
 
 /* Number of kernel launches issued by this plan so far (bench evidence). */
 int64_t mb_plan_launch_count(const mb_plan *plan);
+/* How many frames of the plan's last extract call (or stream push) were redone with the exact-FFT arithmetic
+ * (adaptive plans; 0 otherwise).  Synchronizes the plan's stream after a device-memory call. */
+mb_status mb_plan_refined_frames(mb_plan *plan, int64_t *frames);
 /* Name of the kernel variant the plan dispatches to ("generic", "warp2048", ...). */
 const char *mb_plan_kernel_name(const mb_plan *plan);
 

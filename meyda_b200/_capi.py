@@ -18,6 +18,7 @@ MB_WINDOW = {"hanning": 0, "hamming": 1, "blackman": 2}
 MB_FLAG_GENERIC_KERNEL = 1
 MB_FLAG_EXACT_FFT = 2
 MB_FLAG_CLUSTER_FFT = 4
+MB_FLAG_NO_REFINE = 8
 MB_NUM_FEATURES = 18
 MB_SAMPLE_S16, MB_SAMPLE_S24, MB_SAMPLE_F32 = 1, 2, 3
 
@@ -30,6 +31,7 @@ EXPORTS = [
     "mb_stream_create", "mb_stream_destroy", "mb_stream_frames_after", "mb_stream_push", "mb_stream_reset",
     "mb_extract_pcm16", "mb_extract_pcm16_async", "mb_wav_parse", "mb_stream_graph_launches", "mb_extract_pcm",
     "mb_stream_create_pcm16", "mb_stream_push_pcm16", "mb_plan_create_ex", "mb_plan_get_params",
+    "mb_plan_refined_frames",
 ]
 
 # (field name in mb_outputs, feature name, per-frame length as a function of N and of the plan's Bark-band and
@@ -123,6 +125,7 @@ def lib():
     L.mb_extract_multi.argtypes = [C.POINTER(vp), C.c_int, vp, C.c_int64, i64p, i64p, C.c_int64, C.POINTER(Outputs)]
     L.mb_plan_launch_count.restype = C.c_int64
     L.mb_plan_launch_count.argtypes = [vp]
+    L.mb_plan_refined_frames.argtypes = [vp, i64p]
     L.mb_plan_kernel_name.restype = C.c_char_p
     L.mb_plan_kernel_name.argtypes = [vp]
     L.mb_host_alloc.argtypes = [C.POINTER(vp), C.c_size_t]

@@ -13,6 +13,7 @@
 #include <thread>
 #include <vector>
 
+#include "mb_adaptive.cuh"
 #include "mb_kernels.h"
 
 namespace {
@@ -96,6 +97,10 @@ struct Slot {  // one pipeline stage of a host-memory extract
     int64_t *d_tab = nullptr;
     int64_t *h_tab = nullptr;  // pinned
     size_t tab_cap = 0;        // int64 entries
+    int *d_fix = nullptr;      // [0]: how many frames the float32 kernel flagged, [1 ..]: which (mb_adaptive.cuh)
+    size_t fix_cap = 0;        // ints
+    int *h_fix = nullptr;      // pinned: the counts of this slot's chunks, one after the other
+    size_t h_fix_cap = 0, h_fix_used = 0;
 };
 
 }  // namespace
@@ -125,6 +130,14 @@ struct mb_plan {
     cudaEvent_t tab_event = nullptr;
     bool tab_event_pending = false;
     Slot slots[2];
+    // adaptive exactness (mb_adaptive.cuh): frames the float32 kernels flag are redone by the exact-FFT kernel
+    bool adaptive = false;
+    MbDevPlan dev_fix{};       // the plan as the exact kernel sees it: spectral features only
+    MbNoiseTables *d_noise = nullptr;
+    int *d_fix = nullptr;      // device-memory calls and streams (one stream at a time)
+    size_t fix_cap = 0;
+    int64_t refined_frames = 0;  // host-memory calls: frames redone in the last call
+    bool refined_on_device = false;  // the last call was a device-memory one: its count still lies in d_fix[0]
     int64_t launches = 0;
     int64_t bytes_per_frame = 0;
     const char *kernel_name = "generic";
@@ -239,6 +252,8 @@ cudaError_t upload(T **dst, const std::vector<T> &src) {
 
 void free_slot(Slot &s) {
     if (s.stream) cudaStreamDestroy(s.stream);
+    cudaFree(s.d_fix);
+    if (s.h_fix) cudaFreeHost(s.h_fix);
     cudaFree(s.d_samples);
     cudaFree(s.d_out);
     cudaFree(s.d_tab);
@@ -285,18 +300,33 @@ mb_status check_clips(const mb_plan *p, int64_t n_samples, const int64_t *off, c
 // already in device memory.
 // `aligned`: every frame of this call starts on a 16-byte boundary (TMA bulk copies).
 // `pcm_channels` > 0: d_samples is interleaved PCM of `pcm_format` (see MbClipTable).
+// `fix`/`fix_cap`: where the float32 kernels list the frames to be redone exactly (grown here; NULL: plan not adaptive).
 mb_status launch(mb_plan *p, const int64_t *d_off, const int64_t *d_frame_start, int64_t n, int64_t total_frames,
-                 const float *d_samples, const mb_outputs &d_out, cudaStream_t stream, bool aligned,
+                 const float *d_samples, const mb_outputs &d_out, cudaStream_t stream, int **fix, size_t *fix_cap,
                  int pcm_channels = 0, int pcm_channel = 0, int pcm_format = MB_SAMPLE_S16) {
     if (total_frames == 0) return MB_OK;
-    MbClipTable T{d_off, d_frame_start, n, total_frames, pcm_channels, pcm_channel, pcm_format};
+    if (total_frames > 0x7fffffff) return fail(MB_ERR_UNSUPPORTED, "more than 2^31 - 1 frames in one launch");
+    MbClipTable T{d_off, d_frame_start, n, total_frames, pcm_channels, pcm_channel, pcm_format, nullptr, nullptr, nullptr, nullptr};
+    const bool adaptive = p->adaptive && fix != nullptr;
+    if (adaptive) {
+        if (*fix_cap < (size_t)total_frames + 1) {
+            cudaFree(*fix);  // (synchronises with whatever still uses the old list)
+            *fix = nullptr;
+            *fix_cap = 0;
+            const size_t want = (size_t)total_frames + (size_t)total_frames / 2 + 64;
+            MB_CUDA(cudaMalloc((void **)fix, want * sizeof(int)));
+            *fix_cap = want;
+        }
+        MB_CUDA(cudaMemsetAsync(*fix, 0, sizeof(int), stream));
+        T.fix_count = *fix;
+        T.fix_list = *fix + 1;
+    }
     const bool pcm = pcm_channels > 0;
     // the tuned kernels take float32 mono or 16-bit PCM; other payloads go through the generic kernel's loader
     const bool tuned_ok = !pcm || pcm_format == MB_SAMPLE_S16;
     // the tuned kernels take any float-aligned frame (misaligned ones bypass TMA / the float4 loads inside the
     // kernel, same bits) but store `buffer` rows 16 bytes at a time
     const bool out_ok = (uintptr_t)d_out.buffer % 16 == 0;
-    (void)aligned;
     if (p->use_cluster) {
         MB_CUDA(mb_launch_exact_cluster(p->dev, T, d_samples, d_out, p->num_sms, stream));
         p->launches_generic++;
@@ -314,13 +344,20 @@ mb_status launch(mb_plan *p, const int64_t *d_off, const int64_t *d_frame_start,
         p->launches_generic++;
     }
     p->launches++;
+    if (adaptive) {
+        // the flagged frames again, with the reference's own FFT arithmetic (the kernel reads the count on the device:
+        // nothing to do is one empty launch)
+        MbClipTable Tx = T;
+        Tx.fix_count = nullptr;
+        Tx.fix_list = nullptr;
+        Tx.sel_count = *fix;
+        Tx.sel_list = *fix + 1;
+        if (p->N > 16384) MB_CUDA(mb_launch_exact_cluster(p->dev_fix, Tx, d_samples, d_out, p->num_sms, stream));
+        else MB_CUDA(mb_launch_generic(p->dev_fix, Tx, d_samples, d_out, p->num_sms, stream));
+        p->launches++;
+        p->launches_generic++;
+    }
     return MB_OK;
-}
-
-bool offsets_aligned(const int64_t *off, int64_t n) {
-    for (int64_t c = 0; c < n; c++)
-        if (off[c] & 3) return false;
-    return true;
 }
 
 // Boundary bookkeeping of the warp kernel: the union of Bark limits and mel edges below M, in order.
@@ -535,7 +572,7 @@ mb_status mb_plan_create_ex(mb_plan **plan, int device, int buffer_size, int hop
     if ((flags & MB_FLAG_EXACT_FFT) && buffer_size > MB_MAX_EXACT_BUFFER_SIZE)
         return fail(MB_ERR_UNSUPPORTED, "exact-FFT mode supports bufferSize <= %d (got %d)", MB_MAX_EXACT_BUFFER_SIZE,
                     buffer_size);
-    if (flags & ~(uint32_t)(MB_FLAG_GENERIC_KERNEL | MB_FLAG_EXACT_FFT | MB_FLAG_CLUSTER_FFT))
+    if (flags & ~(uint32_t)(MB_FLAG_GENERIC_KERNEL | MB_FLAG_EXACT_FFT | MB_FLAG_CLUSTER_FFT | MB_FLAG_NO_REFINE))
         return fail(MB_ERR_INVALID_ARG, "unknown plan flags 0x%x", flags);
     if (hop <= 0) return fail(MB_ERR_INVALID_ARG, "hop must be positive (got %d)", hop);
     if (!(sample_rate > 0)) return fail(MB_ERR_INVALID_ARG, "sampleRate must be positive");
@@ -611,8 +648,13 @@ mb_status mb_plan_create_ex(mb_plan **plan, int device, int buffer_size, int hop
     for (int j = 0; j < M / 2; j++) twM[j] = make_float2((float)cos(2 * M_PI * j / M), (float)sin(2 * M_PI * j / M));
     for (int k = 0; k < M; k++) twN[k] = make_float2((float)cos(2 * M_PI * k / N), (float)sin(2 * M_PI * k / N));
 
+    // the exact-FFT tables also serve the adaptive path of the float32 kernels (mb_adaptive.cuh)
+    const uint32_t time_only_mask = MB_FEATURE_BIT(MB_FEAT_RMS) | MB_FEATURE_BIT(MB_FEAT_ENERGY) |
+                                    MB_FEATURE_BIT(MB_FEAT_ZCR) | MB_FEATURE_BIT(MB_FEAT_BUFFER);
+    const bool may_refine = !(flags & (MB_FLAG_EXACT_FFT | MB_FLAG_NO_REFINE)) && (feature_mask & ~time_only_mask) != 0;
+    const bool want_exact_tables = (flags & MB_FLAG_EXACT_FFT) || may_refine;
     std::vector<double2> tw_exact;
-    if (flags & MB_FLAG_EXACT_FFT) {
+    if (want_exact_tables) {
         // lib/jsfft/fft.js:143-164: per stage del = (cos, sin)(PI / width); f <- f * del, in doubles
         tw_exact.resize(N - 1);
         for (int width = 1; width < N; width <<= 1) {
@@ -627,7 +669,7 @@ mb_status mb_plan_create_ex(mb_plan **plan, int device, int buffer_size, int hop
         }
     }
     std::vector<double> mel_w;
-    if (flags & MB_FLAG_EXACT_FFT) {  // src/extractors/mfcc.js:45-50, evaluated in doubles as the reference does
+    if (want_exact_tables) {  // src/extractors/mfcc.js:45-50, evaluated in doubles as the reference does
         for (int f = 0; f < nf; f++) {
             D.mel_w_off[f] = (int)mel_w.size();
             const int e0 = D.mel[f], e1 = D.mel[f + 1], e2 = D.mel[f + 2];
@@ -709,6 +751,42 @@ mb_status mb_plan_create_ex(mb_plan **plan, int device, int buffer_size, int hop
             p->kernel_name = N == 256 ? "warpmf256" : N == 512 ? "warpmf512" : "warpmf1024";
         }
     }
+    {   // constants of the noise bounds (mb_adaptive.cuh)
+        MbNoiseTables *NT = new MbNoiseTables();
+        memset(NT, 0, sizeof(*NT));
+        for (int b = 0; b < nb; b++) {
+            const double n_b = (double)std::max(0, D.bb[b + 1] - D.bb[b]);
+            NT->band_c[b] = (float)(n_b > 0 ? 2.0 * n_b + (double)kMbNoiseK * sqrt(n_b) : 0.0);
+        }
+        for (int f = 0; f < nf; f++) {  // total weight of filter f over the bins below N/2 (mfcc.js:40-51)
+            const int e0 = D.mel[f], e1 = D.mel[f + 1], e2 = std::min(D.mel[f + 2], M);
+            double W = 0;
+            for (int k = e0; k < e1 && k < M; k++) W += (double)(k - e0) / (double)(e1 - e0);
+            for (int k = e1; k < e2; k++) W += (double)(D.mel[f + 2] - k) / (double)(D.mel[f + 2] - e1);
+            NT->mel_c1[f] = (float)(W > 0 ? 2.0 * (double)kMbNoiseK * sqrt(W / std::max(W, 1.0)) : 0.0);
+            NT->mel_c2[f] = (float)(4.0 * W);
+        }
+        for (int q = 0; q < 5; q++) {
+            double t = 0;
+            for (int k = 0; k < M; k++) t += pow((double)k, 2.0 * q);
+            D.noise_sqrtT[q] = kMbNoiseKap * sqrt(t);
+        }
+        cudaError_t ne = cudaMalloc((void **)&p->d_noise, sizeof(MbNoiseTables));
+        if (ne == cudaSuccess) ne = cudaMemcpy(p->d_noise, NT, sizeof(MbNoiseTables), cudaMemcpyHostToDevice);
+        delete NT;
+        if (ne != cudaSuccess) {
+            mb_status st = fail(MB_ERR_CUDA, "noise-bound table upload failed: %s", cudaGetErrorString(ne));
+            mb_plan_destroy(p);
+            return st;
+        }
+        D.noise = p->d_noise;
+    }
+    // Adaptive exactness: the warp kernels flag the frames whose features sit in the reference's own rounding noise
+    // and the exact-FFT kernel redoes exactly those (time-domain features never need it).
+    p->adaptive = may_refine && (p->has_warp_kernel || p->has_mf_kernel);
+    p->dev_fix = D;
+    p->dev_fix.mask = feature_mask & ~time_only_mask;
+    p->dev_fix.exact = 1;
     p->bytes_per_frame = 0;
     for (int i = 0; i < kNumFields; i++)
         if (mb_has(feature_mask, kFields[i].feature)) p->bytes_per_frame += 4 * (int64_t)field_elems(kFields[i], D);
@@ -730,6 +808,8 @@ void mb_plan_destroy(mb_plan *p) {
     cudaFree(p->d_mel_w_exact);
     cudaFree(p->d_warp_tables);
     cudaFree(p->d_warp_mf_tables);
+    cudaFree(p->d_noise);
+    cudaFree(p->d_fix);
     cudaFree(p->d_tab);
     if (p->h_tab) cudaFreeHost(p->h_tab);
     if (p->tab_event) cudaEventDestroy(p->tab_event);
@@ -739,7 +819,14 @@ void mb_plan_destroy(mb_plan *p) {
 
 mb_status mb_plan_set_stream(mb_plan *p, void *cuda_stream) {
     if (!p) return fail(MB_ERR_INVALID_ARG, "plan is NULL");
-    p->stream = cuda_stream ? (cudaStream_t)cuda_stream : p->own_stream;
+    cudaStream_t next = cuda_stream ? (cudaStream_t)cuda_stream : p->own_stream;
+    if (next != p->stream) {
+        // the plan's clip table and flagged-frame list are ordered by the stream alone: work still in flight on
+        // the old stream must not meet the next call's uploads on the new one
+        DeviceGuard guard(p->device);
+        MB_CUDA(cudaStreamSynchronize(p->stream));
+        p->stream = next;
+    }
     return MB_OK;
 }
 
@@ -805,8 +892,10 @@ static mb_status extract_device(mb_plan *p, const float *samples, int64_t n_samp
     MB_CUDA(cudaMemcpyAsync(p->d_tab, p->h_tab, entries * sizeof(int64_t), cudaMemcpyHostToDevice, p->stream));
     MB_CUDA(cudaEventRecord(p->tab_event, p->stream));
     p->tab_event_pending = true;
-    return launch(p, p->d_tab, p->d_tab + n_clips, n_clips, total, samples, *out, p->stream,
-                  offsets_aligned(clip_offset, n_clips), pcm_channels, pcm_channel, pcm_format);
+    p->refined_on_device = p->adaptive && total > 0;
+    p->refined_frames = 0;
+    return launch(p, p->d_tab, p->d_tab + n_clips, n_clips, total, samples, *out, p->stream, &p->d_fix, &p->fix_cap,
+                  pcm_channels, pcm_channel, pcm_format);
 }
 
 mb_status mb_extract_async(mb_plan *p, const float *samples, int64_t n_samples, const int64_t *clip_offset,
@@ -855,6 +944,9 @@ static mb_status extract_host(mb_plan *p, const void *samples, const int64_t *cl
 
     struct VClip { int64_t off, frames; };
     std::vector<VClip> v;
+    p->refined_frames = 0;
+    p->refined_on_device = false;
+    for (auto &s : p->slots) s.h_fix_used = 0;
     int64_t c = 0, f_in_clip = 0, g_done = 0;
     int chunk_idx = 0;
     mb_status st = MB_OK;
@@ -917,9 +1009,21 @@ static mb_status extract_host(mb_plan *p, const void *samples, const int64_t *cl
             field_ptr(d_out, kFields[i]) = s.d_out + cursor;
             cursor += (size_t)frames * field_elems(kFields[i], p->dev) * 4;
         }
-        st = launch(p, s.d_tab, s.d_tab + v.size(), (int64_t)v.size(), frames, s.d_samples, d_out, s.stream,
-                    offsets_aligned(s.h_tab, (int64_t)v.size()), pcm_channels, pcm_channel, pcm_format);
+        st = launch(p, s.d_tab, s.d_tab + v.size(), (int64_t)v.size(), frames, s.d_samples, d_out, s.stream, &s.d_fix,
+                    &s.fix_cap, pcm_channels, pcm_channel, pcm_format);
         if (st != MB_OK) return st;
+        if (p->adaptive) {  // how many frames were redone: read back with the outputs, summed after the last chunk
+            if (s.h_fix_used == s.h_fix_cap) {
+                MB_CUDA(cudaStreamSynchronize(s.stream));
+                for (size_t i = 0; i < s.h_fix_used; i++) p->refined_frames += s.h_fix[i];
+                s.h_fix_used = 0;
+                if (!s.h_fix) {
+                    MB_CUDA(cudaMallocHost((void **)&s.h_fix, 256 * sizeof(int)));
+                    s.h_fix_cap = 256;
+                }
+            }
+            MB_CUDA(cudaMemcpyAsync(s.h_fix + s.h_fix_used++, s.d_fix, sizeof(int), cudaMemcpyDeviceToHost, s.stream));
+        }
         for (int i = 0; i < kNumFields; i++) {
             if (!mb_has(p->mask, kFields[i].feature)) continue;
             const size_t per = (size_t)field_elems(kFields[i], p->dev) * 4;
@@ -930,8 +1034,11 @@ static mb_status extract_host(mb_plan *p, const void *samples, const int64_t *cl
         g_done += frames;
         chunk_idx++;
     }
-    for (auto &s : p->slots)
+    for (auto &s : p->slots) {
         if (s.stream) MB_CUDA(cudaStreamSynchronize(s.stream));
+        for (size_t i = 0; i < s.h_fix_used; i++) p->refined_frames += s.h_fix[i];
+        s.h_fix_used = 0;
+    }
     return MB_OK;
 }
 
@@ -1078,6 +1185,22 @@ mb_status mb_extract_multi(mb_plan *const *plans, int n_plans, const float *samp
 }
 
 int64_t mb_plan_launch_count(const mb_plan *p) { return p ? p->launches : 0; }
+
+mb_status mb_plan_refined_frames(mb_plan *p, int64_t *frames) {
+    if (!p || !frames) return fail(MB_ERR_INVALID_ARG, "plan/frames is NULL");
+    *frames = 0;
+    if (!p->adaptive) return MB_OK;
+    if (p->refined_on_device && p->d_fix) {  // device-memory call (or stream push): the count lies next to the list
+        DeviceGuard guard(p->device);
+        int n = 0;
+        MB_CUDA(cudaStreamSynchronize(p->stream));
+        MB_CUDA(cudaMemcpy(&n, p->d_fix, sizeof(int), cudaMemcpyDeviceToHost));
+        *frames = n;
+    } else {
+        *frames = p->refined_frames;
+    }
+    return MB_OK;
+}
 const char *mb_plan_kernel_name(const mb_plan *p) { return p ? p->kernel_name : ""; }
 
 mb_status mb_host_alloc(void **ptr, size_t bytes) {
@@ -1168,6 +1291,10 @@ static mb_status stream_push(mb_stream *s, const char *new_samples, int64_t n_ne
         mb_status st = check_outputs(p, out);
         if (st != MB_OK) return st;
     }
+    if (nf > 0) {
+        p->refined_on_device = p->adaptive;
+        p->refined_frames = 0;
+    }
     const int64_t consumed = nf * p->hop;  // the hop-overlap tail [consumed, need) stays for the next push
     const int64_t rest = std::max<int64_t>(0, need - consumed);
 
@@ -1209,6 +1336,16 @@ static mb_status stream_push(mb_stream *s, const char *new_samples, int64_t n_ne
             s->out_cap = out_bytes + out_bytes / 2;
             for (auto &g : s->graphs) g.cur = -1;
         }
+        if (p->adaptive && p->fix_cap < (size_t)nf + 1) {  // (never inside a capture: the graphs hold this pointer)
+            MB_CUDA(cudaStreamSynchronize(p->stream));
+            cudaFree(p->d_fix);
+            p->d_fix = nullptr;
+            p->fix_cap = 0;
+            const size_t want = std::max<size_t>(4096, 2 * (size_t)nf + 64);
+            MB_CUDA(cudaMalloc((void **)&p->d_fix, want * sizeof(int)));
+            p->fix_cap = want;
+            for (auto &g : s->graphs) g.cur = -1;
+        }
         if (!s->d_tab) {
             MB_CUDA(cudaMalloc((void **)&s->d_tab, 3 * sizeof(int64_t)));
             MB_CUDA(cudaMallocHost((void **)&s->h_tab, 3 * sizeof(int64_t)));
@@ -1235,7 +1372,7 @@ static mb_status stream_push(mb_stream *s, const char *new_samples, int64_t n_ne
                 MB_CUDA(cudaMemcpyAsync(buf + filled_before * fb, s->h_in, n_new * fb, cudaMemcpyHostToDevice, p->stream));
             if (nf > 0) {
                 mb_status st = launch(p, s->d_tab, s->d_tab + 1, 1, nf, reinterpret_cast<const float *>(buf), d_out, p->stream,
-                                      true, s->pcm_channels, s->pcm_channel);
+                                      &p->d_fix, &p->fix_cap, s->pcm_channels, s->pcm_channel);
                 if (st != MB_OK) return st;
                 MB_CUDA(cudaMemcpyAsync(s->h_out, s->d_out, out_bytes, cudaMemcpyDeviceToHost, p->stream));
                 if (rest)

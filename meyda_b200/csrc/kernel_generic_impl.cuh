@@ -427,7 +427,10 @@ mb_generic_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ M
                                MB_FEATURE_BIT(MB_FEAT_ZCR) | MB_FEATURE_BIT(MB_FEAT_BUFFER);
     const bool want_spectrum = (mask & ~time_only) != 0;
 
-    for (int64_t g = blockIdx.x; g < T.total_frames; g += gridDim.x) {
+    // (sel_list: only the frames a float32-FFT kernel flagged, mb_adaptive.cuh)
+    const int64_t n_work = T.sel_list ? (int64_t)*T.sel_count : T.total_frames;
+    for (int64_t it = blockIdx.x; it < n_work; it += gridDim.x) {
+        const int64_t g = T.sel_list ? (int64_t)T.sel_list[it] : it;
         const int64_t clip = mb_find_clip_warp(T, g);
         const MbFrameSrc src = mb_frame_src(T, samples, T.clip_off[clip] + (g - T.frame_start[clip]) * (int64_t)P.hop);
 
@@ -606,7 +609,9 @@ mb_exact_cluster_kernel(const __grid_constant__ MbDevPlan P, const __grid_consta
     const double SQRT1_2 = 0.70710678118654752440;
     const int64_t n_clusters = gridDim.x / 2, cid = blockIdx.x / 2;
 
-    for (int64_t g = cid; g < T.total_frames; g += n_clusters) {
+    const int64_t n_work = T.sel_list ? (int64_t)*T.sel_count : T.total_frames;
+    for (int64_t it = cid; it < n_work; it += n_clusters) {
+        const int64_t g = T.sel_list ? (int64_t)T.sel_list[it] : it;
         const int64_t clip = mb_find_clip_warp(T, g);
         const MbFrameSrc src = mb_frame_src(T, samples, T.clip_off[clip] + (g - T.frame_start[clip]) * (int64_t)P.hop);
         MbFrameSums S;

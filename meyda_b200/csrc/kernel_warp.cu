@@ -27,6 +27,7 @@
 #include <cstddef>
 #include <utility>
 
+#include "mb_adaptive.cuh"
 #include "mb_device.cuh"
 #include "mb_fft.cuh"
 #include "mb_kernels.h"
@@ -35,6 +36,12 @@
 namespace {
 
 using namespace mbwarp;
+
+#ifdef MB_NO_NOISE_STATS  // A/B builds only (tools/build_variants.sh): the kernels without the mb_adaptive.cuh statistics
+constexpr bool kNoise = false;
+#else
+constexpr bool kNoise = true;
+#endif
 
 constexpr int kP = 32;             // points per lane per pass
 constexpr int kM = kP * kP;        // 1024 complex points
@@ -49,7 +56,7 @@ constexpr int kSlotFloats = 2 * kP * kRow;    // 2112 floats = 8448 B per warp
 constexpr int kAmpStride = 36;                // floats per lane in the blocked amplitude layout
 constexpr int kPieceOff = 1152;               // float offset of the piece area (after 32*36 amps)
 constexpr int kPieces = MB_WARP_PIECES;       // 96: 64 boundary pieces + 32 lane heads
-constexpr int kStashRows = 18;                // floats per frame in the scalar stash
+constexpr int kStashRows = 22;                // floats per frame in the scalar stash (18 .. 21: mb_adaptive.cuh statistics)
 
 static_assert(kPieceOff * 4 + kPieces * 16 <= kSlotFloats * 4, "band pieces must fit the warp slot");
 
@@ -62,6 +69,7 @@ struct Smem {
     float mel_inv[MB_NUM_MEL_FILTERS + 2];
     int mel_edge[MB_NUM_MEL_FILTERS + 2];
     int piece_edge[kPieces];
+    float noise_c[3][32];        // mb_adaptive.cuh: band_c[lane], mel_c1[lane], mel_c2[lane]
     int seg_ptr[MB_WARP_SEGMENTS + 1];
     unsigned char seg_items[MB_WARP_MAX_ITEMS];
     unsigned long long bar[kWarps];
@@ -126,6 +134,11 @@ mb_warp2048_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
         S.mel_inv[tid] = tid < MB_NUM_MEL_FILTERS + 1 ? P.mel_inv_width[tid] : 0.f;
     }
     if (tid < kPieces) S.piece_edge[tid] = WT->piece_edge[tid];
+    if (tid < 32) {
+        S.noise_c[0][tid] = tid < MB_NUM_BARK_BANDS ? P.noise->band_c[tid] : 0.f;
+        S.noise_c[1][tid] = tid < MB_NUM_MEL_FILTERS ? P.noise->mel_c1[tid] : 0.f;
+        S.noise_c[2][tid] = tid < MB_NUM_MEL_FILTERS ? P.noise->mel_c2[tid] : 0.f;
+    }
     if (tid <= MB_WARP_SEGMENTS) S.seg_ptr[tid] = WT->seg_ptr[tid];
     if (tid < MB_WARP_MAX_ITEMS) S.seg_items[tid] = WT->seg_items[tid];
     if (lane == 0) mbar_init(&S.bar[warp], 1);
@@ -293,6 +306,10 @@ mb_warp2048_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
                 }
             }
             const float unscale = ldexpf(1.f, -kscale);
+            // mb_adaptive.cuh: the rms rounding error of one spectrum bin, in the units of the amplitudes used below
+            const float sigma = mb_noise_sigma(energy, 1.0f / (float)kN) * unscale;
+            // as_float(cf - as_int(a)) ~ theta sigma / a (valid while theta sigma < 1: rescaled frames are flagged outright)
+            const int cf = 0x7EF311C7 + __float_as_int(kMbNoiseTheta * sigma) - 0x3F800000;
             int zcr = 0;
             if (want_time) {
                 // crossings inside a pair (2m, 2m+1), and between 2m+1 and 2m+2 (= lane+1, or lane 0 of the next row)
@@ -463,6 +480,7 @@ mb_warp2048_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
                     // discrete output); q = 1..4 become the spectral moments (src/utils.js:1-11) after the
                     // shift to k = 32 lane + i below.
                     double ta = 0, t1 = 0, t2 = 0, t3 = 0, t4 = 0;
+                    float qn = 0.f;  // sum min(1 / a, 1 / (theta sigma))^2 over the lane's bins (mb_adaptive.cuh: q(a) / (theta sigma)^2)
                     uint32_t paddr = smem_u32(piece + (slot_base + lane));
 #pragma unroll
                     for (int i = 0; i < 32; i++) {
@@ -470,6 +488,14 @@ mb_warp2048_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
                             const double ad = (double)ab[i];
                             ta += ad;
                             if (want_moments) {
+                                if (kNoise) {
+                                    // theta sigma / a from the exponent trick (ONE integer subtraction, within ~20 %: this feeds a
+                                    // bound, and MUFU.RCP with its range fix-up would cost six more instructions per bin), squared
+                                    // and clipped to 1 by the multiplier's .sat; 0 and denormals come out huge: a floor bin counts 1
+                                    float u_;
+                                    asm("mul.sat.f32 %0, %1, %1;" : "=f"(u_) : "f"(__int_as_float(cf - __float_as_int(ab[i]))));
+                                    qn += u_;
+                                }
                                 t1 = fma(ad, (double)i, t1);
                                 t2 = fma(ad, (double)(i * i), t2);
                                 t3 = fma(ad, (double)(i * i * i), t3);
@@ -511,6 +537,15 @@ mb_warp2048_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
                             const double r0 = warp_sum_d(ta);
                             if (lane == j) stash_put_d(stash, 2, j, r0);
                         }
+                        // Q_0 and Q_4 of mb_adaptive.cuh (k := the last bin of the lane's block)
+                        const float ql = 1.6f * qn,  /* (1.6: the exponent trick's worst case, squared) */ k4 = (float)(32 * lane + 31) * (float)(32 * lane + 31);
+                        if (kNoise) {
+                            const float q0 = mb_warp_sum(ql), q4 = mb_warp_sum(ql * (k4 * k4));
+                            if (lane == j) {
+                                stash[18][j] = q0;
+                                stash[19][j] = q4;
+                            }
+                        }
                     }
                     if (want_rolloff) {
                         // spectralRolloff.js: the largest m with sum_{k<m} a[k] <= 0.99 sum a.  Lane totals are
@@ -548,14 +583,16 @@ mb_warp2048_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
                     __syncwarp();
                     // ---- lanes finish the bands: loudness.js:55-63, perceptual*.js
                     if (want_bark) {
-                        float sp = 0.f;
+                        float sp = 0.f, nu = 0.f;
                         if (lane < MB_NUM_BARK_BANDS) {
                             float bsum = 0.f;
                             for (int it = S.seg_ptr[lane]; it < S.seg_ptr[lane + 1]; it++) bsum += piece[S.seg_items[it]].x;
                             sp = pow023_approx(bsum);
                             if (mb_has(mask, MB_FEAT_LOUDNESS)) O.loudness_specific[g * MB_NUM_BARK_BANDS + lane] = sp;
+                            if (kNoise) nu = mb_noise_band(bsum, sp, S.noise_c[0][lane], sigma);
                         }
                         const float total = mb_warp_sum(sp);
+                        if (kNoise) nu = mb_warp_sum(nu);
                         float mx = (sp > 0.f) ? sp : 0.f;  // NaN never compares greater (perceptualSpread.js:6)
 #pragma unroll
                         for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
@@ -565,6 +602,7 @@ mb_warp2048_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
                             stash[14][j] = total;
                             stash[15][j] = mx;
                             stash[16][j] = sharp;
+                            stash[20][j] = nu;
                         }
                     }
                     // ---- mel energies from the pieces, log, DCT (mfcc.js:40-93).  Lane s owns mel segment
@@ -588,7 +626,12 @@ mb_warp2048_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
                             }
                         }
                         const float fall_next = __shfl_down_sync(0xffffffffu, fall, 1);
-                        const float lgE = ln_approx(rise + fall_next);  // lanes >= 26 are not used below
+                        const float melE = rise + fall_next;
+                        const float lgE = ln_approx(melE);  // lanes >= 26 are not used below
+                        if (kNoise) {
+                            const float ndl = mb_warp_sum(lane < MB_NUM_MEL_FILTERS ? mb_noise_mel(melE, S.noise_c[1][lane], S.noise_c[2][lane], sigma) : 0.f);
+                            if (lane == j) stash[21][j] = ndl;
+                        }
                         // 13 x 26 DCT on 26 lanes: lane k + 13 h sums filters 13 h .. 13 h + 12 of coefficient k
                         float acc = 0.f;
                         const int half = lane >= MB_NUM_MFCC ? MB_NUM_MFCC : 0;
@@ -606,6 +649,7 @@ mb_warp2048_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
 
         // ---- 5. one frame per lane: the "number" features of the chunk, coalesced
         __syncwarp();
+        bool need_exact = false;
         if (lane < nfc) {
             MbFrameSums F;
             F.energy = ldexp((double)stash[0][lane], -2 * __float_as_int(stash[17][lane]));
@@ -630,7 +674,19 @@ mb_warp2048_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
                 }
                 if (mb_has(mask, MB_FEAT_PERCEPTUAL_SHARPNESS)) O.perceptual_sharpness[g] = (float)(sharp * (0.11 / total));
             }
+            if (kNoise && want_spectrum && T.fix_count != nullptr) {
+                MbNoiseFrame NF;
+                NF.sigma = (float)((double)kMbNoiseRel * sqrt(F.energy * (1.0 / kN)));
+                NF.q0 = stash[18][lane];
+                NF.q4 = stash[19][lane];
+                NF.sum_u = stash[20][lane];
+                NF.sum_dl = stash[21][lane];
+                NF.total = stash[14][lane];
+                NF.sharp = stash[16][lane] + (float)P.sharp_const;
+                need_exact = __float_as_int(stash[17][lane]) != 0 || mb_noise_needs_exact(P, mask, F, NF);
+            }
         }
+        mb_noise_append(T, need_exact, g0 + lane);  // frames of this chunk that the exact-FFT kernel redoes
     }
     if (lane == 0) bulk_store_wait_all();  // outstanding `buffer` stores complete before the CTA retires
 }

@@ -18,6 +18,7 @@
 #include <cstddef>
 #include <utility>
 
+#include "mb_adaptive.cuh"
 #include "mb_device.cuh"
 #include "mb_fft.cuh"
 #include "mb_kernels.h"
@@ -26,6 +27,12 @@
 namespace {
 
 using namespace mbwarp;
+
+#ifdef MB_NO_NOISE_STATS  // A/B builds only (tools/build_variants.sh): the kernels without the mb_adaptive.cuh statistics
+constexpr bool kNoise = false;
+#else
+constexpr bool kNoise = true;
+#endif
 
 constexpr int kP = 32;
 constexpr int kPts = kP * kP;  // complex points per warp per group: F frames x M
@@ -36,7 +43,7 @@ constexpr int kSlotFloats = 2176;  // per warp: >= the 32 x 33 float2 transpose,
 constexpr int kAmpStride = 36;
 constexpr int kPieceOff = 1152;
 constexpr int kMaxPieces = MB_MF_MAX_PIECES;
-constexpr int kStashRows = 18;
+constexpr int kStashRows = 22;  // (18 .. 21: mb_adaptive.cuh statistics)
 // pieces follow the blocked amplitudes: {sum a, sum p, sum w p} as a float4 (one 16-byte store per flush), or packed
 // as three floats at bufferSize 256, where eight frames need 336 of them
 static_assert(kSlotFloats >= 2 * kP * kRow && kPieceOff + 4 * 256 <= kSlotFloats && kPieceOff + 3 * kMaxPieces <= kSlotFloats,
@@ -50,6 +57,7 @@ struct Smem {
     float mel_inv[MB_NUM_MEL_FILTERS + 2];
     int mel_edge[MB_NUM_MEL_FILTERS + 2];
     short piece_edge[kMaxPieces];
+    float noise_c[3][32];  // mb_adaptive.cuh: band_c[b], mel_c1[f], mel_c2[f]
     short seg_ptr[MB_MF_MAX_SEGMENTS + 1];
     unsigned short seg_items[MB_MF_MAX_ITEMS];
     unsigned long long bar[kWarps];
@@ -62,6 +70,12 @@ __host__ __device__ constexpr int brev5(int k) { return mbfft::brev<5>(k); }
 // sums inside aligned groups of G lanes
 template <int G>
 __device__ __forceinline__ double group_sum_d(double v) {
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+template <int G>
+__device__ __forceinline__ float group_sum_f(float v) {
 #pragma unroll
     for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
@@ -116,6 +130,11 @@ mb_warpmf_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ Mb
         S.mel_inv[tid] = tid < MB_NUM_MEL_FILTERS + 1 ? P.mel_inv_width[tid] : 0.f;
     }
     for (int i = tid; i < kMaxPieces; i += kThreads) S.piece_edge[i] = WT->piece_edge[i];
+    if (tid < 32) {
+        S.noise_c[0][tid] = tid < MB_NUM_BARK_BANDS ? P.noise->band_c[tid] : 0.f;
+        S.noise_c[1][tid] = tid < MB_NUM_MEL_FILTERS ? P.noise->mel_c1[tid] : 0.f;
+        S.noise_c[2][tid] = tid < MB_NUM_MEL_FILTERS ? P.noise->mel_c2[tid] : 0.f;
+    }
     for (int i = tid; i <= MB_MF_MAX_SEGMENTS; i += kThreads) S.seg_ptr[i] = WT->seg_ptr[i];
     for (int i = tid; i < MB_MF_MAX_ITEMS; i += kThreads) S.seg_items[i] = WT->seg_items[i];
     if (lane == 0) mbar_init(&S.bar[warp], 1);
@@ -333,6 +352,13 @@ mb_warpmf_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ Mb
             for (int f = 0; f < kF; f++)
                 if (lane == 0 && f < nfg) stash[0][j + f] = energy[f];  // (of the rescaled samples where a frame was rescaled)
 
+            __syncwarp();
+            // mb_adaptive.cuh: rms rounding error of one spectrum bin of frame f of the group, in the frame's own units
+            auto sigma_of = [&](int f) {
+                const int col = min(j + f, kChunk - 1);
+                return mb_noise_sigma(stash[0][min(j + min(f, nfg - 1), kChunk - 1)], 1.0f / (float)kN) *
+                       ldexpf(1.f, -__float_as_int(stash[17][col]));
+            };
             if (want_spectrum) {
                 // ---- 3. pass A: F FFTs of A points per lane; twiddle; transpose
                 fft_frames<kA>(v, std::make_integer_sequence<int, kF>{});
@@ -471,6 +497,10 @@ mb_warpmf_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ Mb
                     // 6e-8 x 17 x its power in a filter that may hold a billion times less)
                     float wk = -1.f;
                     double ta = 0, t1 = 0, t2 = 0, t3 = 0, t4 = 0;
+                    const float sigma_l = sigma_of(lf);  // this lane's frame
+                    // as_float(cf - as_int(a)) ~ theta sigma / a (valid while theta sigma < 1: rescaled frames are flagged outright)
+                    const int cf = 0x7EF311C7 + __float_as_int(kMbNoiseTheta * sigma_l) - 0x3F800000;
+                    float qn = 0.f;  // sum min(1 / a, 1 / (theta sigma))^2 over the lane's bins (mb_adaptive.cuh)
                     uint32_t paddr = smem_u32(piece + kPf * (slot_base + lane));
 #pragma unroll
                     for (int i = 0; i < 32; i++) {
@@ -478,6 +508,14 @@ mb_warpmf_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ Mb
                             const double ad = (double)ab[i];
                             ta += ad;
                             if (want_moments) {
+                                if (kNoise) {
+                                    // theta sigma / a from the exponent trick (ONE integer subtraction, within ~20 %: this feeds a
+                                    // bound, and MUFU.RCP with its range fix-up would cost six more instructions per bin), squared
+                                    // and clipped to 1 by the multiplier's .sat; 0 and denormals come out huge: a floor bin counts 1
+                                    float u_;
+                                    asm("mul.sat.f32 %0, %1, %1;" : "=f"(u_) : "f"(__int_as_float(cf - __float_as_int(ab[i]))));
+                                    qn += u_;
+                                }
                                 t1 = fma(ad, (double)i, t1);
                                 if (want_high) {
                                     t2 = fma(ad, (double)(i * i), t2);
@@ -532,9 +570,14 @@ mb_warpmf_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ Mb
                         const double c = (double)(32 * lp), c2 = c * c;  // bins counted inside the lane's own frame
                         const double s1 = fma(c, ta, t1);
                         const double r0 = group_sum_d<kA>(ta), r1 = group_sum_d<kA>(s1);
+                        // Q_0 and Q_4 of mb_adaptive.cuh (k := the last bin of the lane's block)
+                        const float ql = 1.6f * qn,  /* (1.6: the exponent trick's worst case, squared) */ k4 = (float)(32 * lp + 31) * (float)(32 * lp + 31);
+                        const float q0 = kNoise ? group_sum_f<kA>(ql) : 0.f, q4 = kNoise ? group_sum_f<kA>(ql * (k4 * k4)) : 0.f;
                         if (lp == 0 && lf < nfg) {
                             if (!want_rolloff) stash_put_d(stash, 2, j + lf, r0);
                             stash_put_d(stash, 4, j + lf, r1);
+                            stash[18][j + lf] = q0;
+                            stash[19][j + lf] = q4;
                         }
                         if (want_high) {
                             const double s2 = fma(c2, ta, fma(2.0 * c, t1, t2));
@@ -586,8 +629,9 @@ mb_warpmf_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ Mb
                         }
                     }
                     __syncwarp();  // pieces visible; the blocked amplitudes are spent and become scratch
-                    float *sp_s = slot;                                  // [24 F] specific loudness
-                    float *rise_s = slot + 24 * kF;                      // [27 F]
+                    float *sp_s = slot;                                  // [24 F] specific loudness (later [26 F]: noise bounds of the mel filters)
+                    float *rise_s = slot + 26 * kF;                      // [27 F] (before that [24 F]: noise bounds of the Bark bands)
+                    float *nu_s = rise_s, *ndl_s = sp_s;
                     float *fall_s = rise_s + 27 * kF;                    // [27 F]
                     float *lge_s = fall_s + 27 * kF;                     // [26 F]
                     if (want_bark) {
@@ -600,14 +644,16 @@ mb_warpmf_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ Mb
                                 for (int it = S.seg_ptr[ts]; it < S.seg_ptr[ts + 1]; it++) bsum += piece[kPf * S.seg_items[it]];
                                 const float sp = pow023_approx(bsum);
                                 sp_s[seg] = sp;
+                                if (kNoise) nu_s[seg] = mb_noise_band(bsum, sp, S.noise_c[0][bnd], sigma_of(f));
                                 if (mb_has(mask, MB_FEAT_LOUDNESS) && f < nfg) O.loudness_specific[g * MB_NUM_BARK_BANDS + seg] = sp;
                             }
                         }
                         __syncwarp();
                         if (lane < nfg) {
-                            float total = 0.f, mx = 0.f, sharp = 0.f;
+                            float total = 0.f, mx = 0.f, sharp = 0.f, nu = 0.f;
                             for (int i = 0; i < MB_NUM_BARK_BANDS; i++) {
                                 const float sp = sp_s[lane * MB_NUM_BARK_BANDS + i];
+                                if (kNoise) nu += nu_s[lane * MB_NUM_BARK_BANDS + i];
                                 total += sp;
                                 mx = (sp > mx) ? sp : mx;  // NaN never compares greater (perceptualSpread.js:6)
                                 if (i >= 1 && i <= 15) sharp = fmaf((float)i, sp, sharp);
@@ -615,7 +661,9 @@ mb_warpmf_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ Mb
                             stash[14][j + lane] = total;
                             stash[15][j + lane] = mx;
                             stash[16][j + lane] = sharp;
+                            stash[20][j + lane] = nu;
                         }
+                        __syncwarp();  // (nu_s shares its floats with rise_s)
                     }
                     if (want_mfcc) {
                         for (int it0 = 0; it0 < (MB_NUM_MEL_FILTERS + 1) * kF; it0 += 32) {
@@ -642,10 +690,17 @@ mb_warpmf_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ Mb
                             const int idx = it0 + lane;
                             if (idx < MB_NUM_MEL_FILTERS * kF) {
                                 const int f = idx / MB_NUM_MEL_FILTERS, m = idx % MB_NUM_MEL_FILTERS;
-                                lge_s[idx] = ln_approx(rise_s[f * (MB_NUM_MEL_FILTERS + 1) + m] + fall_s[f * (MB_NUM_MEL_FILTERS + 1) + m + 1]);
+                                const float melE = rise_s[f * (MB_NUM_MEL_FILTERS + 1) + m] + fall_s[f * (MB_NUM_MEL_FILTERS + 1) + m + 1];
+                                lge_s[idx] = ln_approx(melE);
+                                if (kNoise) ndl_s[idx] = mb_noise_mel(melE, S.noise_c[1][m], S.noise_c[2][m], sigma_of(f));
                             }
                         }
                         __syncwarp();
+                        if (kNoise && lane < nfg) {
+                            float ndl = 0.f;
+                            for (int m = 0; m < MB_NUM_MEL_FILTERS; m++) ndl += ndl_s[lane * MB_NUM_MEL_FILTERS + m];
+                            stash[21][j + lane] = ndl;
+                        }
                         for (int it0 = 0; it0 < MB_NUM_MFCC * kF; it0 += 32) {
                             const int idx = it0 + lane;
                             if (idx < MB_NUM_MFCC * kF) {
@@ -664,6 +719,7 @@ mb_warpmf_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ Mb
 
         // ---- 6. one frame per lane: the "number" features of the chunk, coalesced
         __syncwarp();
+        bool need_exact = false;
         if (lane < nfc) {
             MbFrameSums F;
             const int ks = want_spectrum ? __float_as_int(stash[17][lane]) : 0;
@@ -688,7 +744,19 @@ mb_warpmf_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ Mb
                 }
                 if (mb_has(mask, MB_FEAT_PERCEPTUAL_SHARPNESS)) O.perceptual_sharpness[gg] = (float)(sharp * (0.11 / total));
             }
+            if (kNoise && want_spectrum && T.fix_count != nullptr) {
+                MbNoiseFrame NF;
+                NF.sigma = (float)((double)kMbNoiseRel * sqrt(F.energy * (1.0 / kN)));
+                NF.q0 = stash[18][lane];
+                NF.q4 = stash[19][lane];
+                NF.sum_u = stash[20][lane];
+                NF.sum_dl = stash[21][lane];
+                NF.total = stash[14][lane];
+                NF.sharp = stash[16][lane] + (float)P.sharp_const;
+                need_exact = ks != 0 || mb_noise_needs_exact(P, mask, F, NF);
+            }
         }
+        mb_noise_append(T, need_exact, g0 + lane);  // frames of this chunk that the exact-FFT kernel redoes
         __syncwarp();
     }
     if (lane == 0) bulk_store_wait_all();

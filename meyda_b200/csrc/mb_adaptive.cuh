@@ -1,0 +1,139 @@
+// mb_adaptive.cuh -- which frames of a float32-FFT kernel must be redone with the reference's own FFT arithmetic.
+//
+// Why: x^0.23 (loudness.js:60), ln x (mfcc.js:63) and the k^3 / k^4 weighted sums of src/utils.js:1-11 amplify the
+// spectrum's rounding-noise floor without bound.  Where a Bark band, a mel filter or the upper bins of a tonal frame
+// hold nothing but FFT rounding noise, the REFERENCE's value is set by its own float32 per-stage rounding
+// (lib/jsfft/fft.js:158-161) and only a bit-identical FFT lands within 1e-3 of it.  The float32 kernels therefore
+// bound, per frame, how far each requested feature can move under spectral noise of the size that separates a float32
+// FFT from the reference's (measured: rms |Z_fast - Z_ref| = 1.5e-7 sqrt(E_windowed / N), both noises together), and
+// frames whose bound exceeds half the parity tolerance (1e-3 relative or absolute, BASELINE.json) are appended to a
+// list that the exact-FFT kernel then works through, overwriting those frames' spectral outputs.
+//
+// The noise model (tools/flag_calibrate.py checks it against the reference arithmetic on tonal, noisy, low-passed and
+// quantised signals: no violating frame is missed, ordinary audio is not flagged):
+//   sigma   = 1e-7 sqrt(E_raw / N)                      rms error of one spectrum bin (E_raw >= E_windowed)
+//   a bin   moves by ~sigma where a <~ sigma (its value IS the noise) and by sigma^2 / a above: bias ~ sigma q(a),
+//           q(a) = min(1, (32 sigma / a)^2);  Q_p = sum_k q(a_k) k^p (accumulated per 32-bin block, k := block end)
+//   a sum   of n bins moves by K sigma sqrt(n) (random signs, K = 16 covers the spikes a tone leaves at its
+//           radix-2 aliases k0 + N / 2^s) plus the bias of its floor bins
+// Everything here is plan-time constants and a few dozen instructions per frame; the per-bin part is three
+// instructions in the kernels' blocked loop (MUFU.RCP, FMNMX, FFMA).
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "mb_device.cuh"
+
+constexpr float kMbNoiseRel = 1e-7f;    // sigma / sqrt(E_raw / N)
+constexpr float kMbNoiseTheta = 32.f;   // q(a) = min(1, (theta sigma / a)^2)
+constexpr float kMbNoiseK = 16.f;       // random-sum safety factor (band / filter sums)
+constexpr double kMbNoiseKap = 8.0;     // random-sum safety factor (moment sums over all n bins)
+constexpr float kMbNoiseHalfTol = 5e-4f;  // half of the 1e-3 parity tolerance
+
+// sigma of a frame from its raw energy (the caller passes the energy in the units its amplitudes are in)
+__device__ __forceinline__ float mb_noise_sigma(float energy, float inv_N) { return kMbNoiseRel * sqrtf(energy * inv_N); }
+
+// One Bark band (loudness.js:55-63): how far specific[b] = (sum a)^0.23 can move.  cB = 2 n_b + K sqrt(n_b) (plan
+// constant, 0 for an empty band).  Returns the bound u; +inf when it alone breaks the tolerance (or is NaN).
+__device__ __forceinline__ float mb_noise_band(float bsum, float sp, float cB, float sigma) {
+    const float eB = cB * sigma;
+    float lu, ll, up, lo;
+    asm("lg2.approx.f32 %0, %1;" : "=f"(lu) : "f"(bsum + eB));
+    asm("ex2.approx.f32 %0, %1;" : "=f"(up) : "f"(0.23f * lu));
+    asm("lg2.approx.f32 %0, %1;" : "=f"(ll) : "f"(fmaxf(bsum - eB, 0.f)));
+    asm("ex2.approx.f32 %0, %1;" : "=f"(lo) : "f"(0.23f * ll));
+    const float u = up - lo;
+    return (u <= kMbNoiseHalfTol * fmaxf(1.f, sp)) ? u : INFINITY;  // (NaN: out)
+}
+
+// One mel filter (mfcc.js:53-65): how far ln E_f can move.  c1 = 2 K sqrt(W_f / max(W_f, 1)), c2 = 4 W_f with
+// W_f the filter's total weight (0: the filter is empty, -inf in the reference too).
+__device__ __forceinline__ float mb_noise_mel(float E, float c1, float c2, float sigma) {
+    if (c2 == 0.f || sigma == 0.f) return 0.f;
+    const float r2 = sigma * (sigma / E);  // (E == 0: inf)
+    const float d = fmaf(c1, sqrtf(r2), c2 * r2);
+    return (d < 0.5f) ? 2.f * d : INFINITY;
+}
+
+struct MbNoiseFrame {
+    float sigma;    // mb_noise_sigma of the frame (its own units)
+    float q0, q4;   // sum q(a_k), sum q(a_k) k_blockend^4
+    float sum_u;    // sum of mb_noise_band over the bands (inf: one band alone is out)
+    float sum_dl;   // sum of mb_noise_mel over the filters
+    float total, sharp;  // loudness.total and the weighted sum of perceptualSharpness.js:6-8 + its constant
+};
+
+// The frame-level decision, one frame per thread.  `mask`: requested features; P.noise_sqrtT[p] = kap sqrt(sum_k k^(2p)).
+static __device__ __noinline__ bool mb_noise_needs_exact(const MbDevPlan &P, uint32_t mask, const MbFrameSums &S, const MbNoiseFrame &F) {
+    if (!(S.energy > 0.0)) return S.energy != 0.0;  // silence: nothing to amplify; NaN: the exact path owns the special values
+    const float tol = kMbNoiseHalfTol;
+    bool bad = false;
+    const uint32_t bark = MB_FEATURE_BIT(MB_FEAT_LOUDNESS) | MB_FEATURE_BIT(MB_FEAT_PERCEPTUAL_SPREAD) | MB_FEATURE_BIT(MB_FEAT_PERCEPTUAL_SHARPNESS);
+    if (mask & bark) {
+        const float su = F.sum_u, tot = F.total;
+        bad |= !(su <= tol * fmaxf(1.f, tot));                              // loudness.total (and every specific[b], see mb_noise_band)
+        bad |= !(4.f * su <= tol * tot);                                    // perceptualSpread: d(r^2) <= 2 r (max u + sum u) / total
+        const float sh = 0.11f * F.sharp / tot;
+        bad |= !((1.65f + sh) * su <= tol * fmaxf(1.f, sh) * tot);          // perceptualSharpness: weights <= 15 x 0.11
+    }
+    if (mb_has(mask, MB_FEAT_MFCC)) bad |= !(0.02134f * F.sum_dl <= tol);   // max |dct| / 13 = sqrt(2/26) / 13
+    const uint32_t mom = MB_FEATURE_BIT(MB_FEAT_SPECTRAL_CENTROID) | MB_FEATURE_BIT(MB_FEAT_SPECTRAL_SPREAD) |
+                         MB_FEATURE_BIT(MB_FEAT_SPECTRAL_SKEWNESS) | MB_FEATURE_BIT(MB_FEAT_SPECTRAL_KURTOSIS) |
+                         MB_FEATURE_BIT(MB_FEAT_SPECTRAL_FLATNESS) | MB_FEATURE_BIT(MB_FEAT_SPECTRAL_SLOPE);
+    if ((mask & mom) && !bad) {
+        const double sg = (double)F.sigma, n = (double)P.M;
+        const double q0 = (double)F.q0, q4 = (double)F.q4;
+        // Q_p <= Q_0^(1 - p/4) Q_4^(p/4) (moments are log-convex in p)
+        const double g = (q0 > 0.0 && q4 > 0.0) ? sqrt(sqrt(q4 / q0)) : 0.0;
+        double dS[5], qp = q0;
+#pragma unroll
+        for (int p = 0; p < 5; p++) {
+            dS[p] = sg * (P.noise_sqrtT[p] + qp);
+            qp *= g;
+        }
+        const double s[5] = {S.s0, S.s1, S.s2, S.s3, S.s4};
+        // spectralCentroid.js .. spectralKurtosis.js at the sums as they are and with one sum moved at a time
+        double f0[4], dd[4] = {0, 0, 0, 0};
+#pragma unroll 1
+        for (int p = -1; p < 5; p++) {
+            double t[5];
+#pragma unroll
+            for (int i = 0; i < 5; i++) t[i] = s[i] + (i == p ? dS[i] : 0.0);
+            const double m1 = t[1] / t[0], m2 = t[2] / t[0], m3 = t[3] / t[0], m4 = t[4] / t[0];
+            const double sd = sqrt(m2 - m1 * m1);
+            const double f[4] = {m1, sd, (2 * m1 * m1 * m1 - 3 * m1 * m2 + m3) / (sd * sd * sd),
+                                 (-3 * m1 * m1 * m1 * m1 + 6 * m1 * m2 - 4 * m1 * m3 + m4) / (sd * sd * sd * sd)};
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                if (p < 0) f0[i] = f[i];
+                else dd[i] += fabs(f[i] - f0[i]);
+            }
+        }
+        const int feat[4] = {MB_FEAT_SPECTRAL_CENTROID, MB_FEAT_SPECTRAL_SPREAD, MB_FEAT_SPECTRAL_SKEWNESS, MB_FEAT_SPECTRAL_KURTOSIS};
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+            if (mb_has(mask, feat[i])) bad |= !(dd[i] <= (double)tol * fmax(1.0, fabs(f0[i])));
+        // spectralSlope.js:17 is linear in the centroid, alpha (c - (n-1)/2), and compared relatively
+        if (mb_has(mask, MB_FEAT_SPECTRAL_SLOPE)) bad |= !(dd[0] <= (double)tol * fabs(f0[0] - 0.5 * (n - 1.0)));
+        if (mb_has(mask, MB_FEAT_SPECTRAL_FLATNESS)) {
+            // flatness = exp(mean ln a) n / S0: mean ln a moves by (Q0 + 4 sqrt(Q0) / theta) / n, S0 by dS0
+            const double flat = exp(S.log2sum * 0.6931471805599453 / n) * n / S.s0;
+            const double dml = (q0 + 4.0 * sqrt(q0) / (double)kMbNoiseTheta) / n + dS[0] / S.s0;
+            bad |= !(flat * expm1(dml) <= (double)tol);
+            bad |= (S.log2sum < -1e30) && (S.s0 > 0.0);  // a bin that is exactly 0 here need not be in the reference
+        }
+    }
+    return bad;
+}
+
+// A warp appends its flagged frames (need: one frame per lane) to the plan's list.
+__device__ __forceinline__ void mb_noise_append(const MbClipTable &T, bool need, int64_t g) {
+    const unsigned m = __ballot_sync(0xffffffffu, need);
+    if (m == 0u || T.fix_count == nullptr) return;
+    const int lane = threadIdx.x & 31;
+    int base = 0;
+    if (lane == 0) base = atomicAdd(T.fix_count, __popc(m));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (need) T.fix_list[base + __popc(m & ((1u << lane) - 1u))] = (int)g;
+}

@@ -47,6 +47,13 @@ struct MbWarpMfTables {
     int n_pieces;                  // > MB_MF_MAX_PIECES: does not fit, the plan keeps the generic kernel
 };
 
+// Plan constants of the noise bounds (mb_adaptive.cuh), one device copy per plan.
+struct MbNoiseTables {
+    float band_c[MB_MAX_BARK_BANDS];    // 2 n_b + K sqrt(n_b), n_b = bins of Bark band b (0: empty band)
+    float mel_c1[MB_MAX_MEL_FILTERS];   // 2 K sqrt(W_f / max(W_f, 1)), W_f = total weight of mel filter f
+    float mel_c2[MB_MAX_MEL_FILTERS];   // 4 W_f (0: empty filter)
+};
+
 // Per-plan constants handed to kernels by value (__grid_constant__).  Tables
 // are what `new Meyda(...)` precomputes (src/meyda.js:44-48) plus the ones
 // mfcc.js rebuilds per call (src/extractors/mfcc.js:15-83).
@@ -76,6 +83,9 @@ struct MbDevPlan {
     int bb[MB_MAX_BARK_BANDS + 1];     // loudness.js:24-45: nb + 1 limits
     int mel[MB_MAX_MEL_FILTERS + 2];   // mfcc.js:31-38: nf + 2 bins
     // what the reference keeps as constants (mb_plan_create_ex); the warp kernels only ever see 24 / 26 / 13 / 0.99
+    // mb_adaptive.cuh: kap sqrt(sum_k k^(2p)), p = 0..4, and the per-band / per-filter constants of the noise bounds
+    double noise_sqrtT[5];
+    const struct MbNoiseTables *noise;
     int nb;               // Bark bands   (loudness.js:14)
     int nf;               // mel filters  (mfcc.js:15)
     int nc;               // coefficients (mfcc.js:71)
@@ -95,6 +105,13 @@ struct MbClipTable {
     int pcm_channels;
     int pcm_channel;
     int pcm_format;  // MB_SAMPLE_S16 / MB_SAMPLE_S24 / MB_SAMPLE_F32 (meaningful when pcm_channels > 0)
+    // Adaptive exactness (mb_adaptive.cuh).  A float32-FFT kernel appends the frames whose features sit in the
+    // reference's own rounding noise to fix_list (fix_count: how many; NULL: do not).  An exact-FFT kernel given
+    // sel_list works through frames sel_list[0 .. *sel_count) instead of [0, total_frames).
+    int *fix_count;
+    int *fix_list;
+    const int *sel_count;
+    const int *sel_list;
 };
 
 // One frame's samples, whatever the storage.

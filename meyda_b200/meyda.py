@@ -147,6 +147,14 @@ class Plan:
     def launch_count(self) -> int:
         return int(self._L.mb_plan_launch_count(self._h))
 
+    @property
+    def refined_frames(self) -> int:
+        """Frames of the last extract call (or stream push) that were redone with the reference's own FFT
+        arithmetic because their features sit in its rounding noise (adaptive float32 plans; else 0)."""
+        n = C.c_int64(0)
+        _capi.check(self._L.mb_plan_refined_frames(self._h, C.byref(n)))
+        return int(n.value)
+
     def set_stream(self, cuda_stream: int | None):
         """Launch on this cudaStream_t handle; None restores the plan's own stream.  Handle 0 (the legacy
         default stream, e.g. torch's default `current_stream().cuda_stream`) is passed as cudaStreamLegacy,
@@ -196,11 +204,23 @@ class Plan:
             setattr(o, k, v)
         return o
 
+    def _check_out(self, out: dict, total_frames: int):
+        """Caller-supplied output arrays must be what the C ABI will write: shape, dtype, C-contiguous."""
+        for k, (shape, dtype) in self.output_shapes(total_frames).items():
+            a = out.get(k)
+            if not isinstance(a, np.ndarray) or a.shape != shape or a.dtype != dtype or not a.flags["C_CONTIGUOUS"]:
+                raise TypeError("output %r must be a C-contiguous %s array of shape %s" % (k, np.dtype(dtype).name, shape))
+
     def extract_host(self, data: np.ndarray, offsets: np.ndarray, lengths: np.ndarray, out: dict | None = None):
         """MB_MEM_HOST call: numpy in, numpy out (dict field -> array)."""
+        data = np.ascontiguousarray(data, dtype=np.float32)
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        lengths = np.ascontiguousarray(lengths, dtype=np.int64)
         per, lay = self.query(lengths)
         if out is None:
             out = self.alloc_host_outputs(int(lay.total_frames))
+        else:
+            self._check_out(out, int(lay.total_frames))
         o = self.pack_outputs({k: v.ctypes.data for k, v in out.items()})
         i64p = C.POINTER(C.c_int64)
         _capi.check(self._L.mb_extract(self._h, data.ctypes.data, data.size, offsets.ctypes.data_as(i64p),
@@ -279,9 +299,14 @@ def extract_multi(plans: Sequence[Plan], data: np.ndarray, offsets: np.ndarray, 
                   out: dict | None = None):
     """Clip-sharded MB_MEM_HOST extraction over several devices (no collectives)."""
     p0 = plans[0]
+    data = np.ascontiguousarray(data, dtype=np.float32)
+    offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+    lengths = np.ascontiguousarray(lengths, dtype=np.int64)
     per, lay = p0.query(lengths)
     if out is None:
         out = p0.alloc_host_outputs(int(lay.total_frames))
+    else:
+        p0._check_out(out, int(lay.total_frames))
     o = Plan.pack_outputs({k: v.ctypes.data for k, v in out.items()})
     handles = (C.c_void_p * len(plans))(*[p.handle for p in plans])
     i64p = C.POINTER(C.c_int64)
