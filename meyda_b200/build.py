@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "_lib")
 LIB = os.path.join(LIB_DIR, "libmeyda_b200.so")
-SOURCES = ["capi.cu", "kernel_generic.cu", "kernel_warp.cu", "kernel_warp_mf.cu"]
+SOURCES = ["capi.cu", "kernel_generic.cu", "kernel_warp.cu", "kernel_warp_mf.cu", "kernel_exact_warp.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "--use_fast_math=false", "-Xcompiler", "-fPIC,-O2,-Wall", "-Xptxas", "-v",

@@ -122,6 +122,8 @@ struct mb_plan {
     bool has_mf_kernel = false;
     bool use_cluster = false;
     bool has_big_kernel = false;
+    bool has_exact_warp = false;  // exact-FFT arithmetic on the warp-per-frame kernel (kernel_exact_warp.cu)
+    double tw_small[30] = {0};    // the recurrence twiddles of widths 1, 2, 4, 8 (its first register pass)
     int64_t launches_warp = 0, launches_generic = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr;
     // device-memory calls: clip tables staged through pinned memory
@@ -330,6 +332,9 @@ mb_status launch(mb_plan *p, const int64_t *d_off, const int64_t *d_frame_start,
     if (p->use_cluster) {
         MB_CUDA(mb_launch_exact_cluster(p->dev, T, d_samples, d_out, p->num_sms, stream));
         p->launches_generic++;
+    } else if (p->dev.exact && p->has_exact_warp) {
+        MB_CUDA(mb_launch_exact_warp(p->dev, T, d_samples, d_out, p->num_sms, stream, p->tw_small));
+        p->launches_warp++;
     } else if (p->has_big_kernel && out_ok && !pcm && ((uintptr_t)d_samples % 4 == 0)) {  // (misaligned frames: read by the lanes)
         MB_CUDA(mb_launch_big32768(p->dev, T, d_samples, d_out, p->num_sms, stream));
         p->launches_warp++;
@@ -353,6 +358,7 @@ mb_status launch(mb_plan *p, const int64_t *d_off, const int64_t *d_frame_start,
         Tx.sel_count = *fix;
         Tx.sel_list = *fix + 1;
         if (p->N > 16384) MB_CUDA(mb_launch_exact_cluster(p->dev_fix, Tx, d_samples, d_out, p->num_sms, stream));
+        else if (p->has_exact_warp) MB_CUDA(mb_launch_exact_warp(p->dev_fix, Tx, d_samples, d_out, p->num_sms, stream, p->tw_small));
         else MB_CUDA(mb_launch_generic(p->dev_fix, Tx, d_samples, d_out, p->num_sms, stream));
         p->launches++;
         p->launches_generic++;
@@ -662,6 +668,10 @@ mb_status mb_plan_create_ex(mb_plan **plan, int device, int buffer_size, int hop
             double f_r = 1, f_i = 0;
             for (int j = 0; j < width; j++) {
                 tw_exact[width - 1 + j] = make_double2(f_r, f_i);
+                if (width <= 8) {
+                    p->tw_small[2 * (width - 1 + j)] = f_r;
+                    p->tw_small[2 * (width - 1 + j) + 1] = f_i;
+                }
                 const double temp = f_r * del_r - f_i * del_i;
                 f_i = f_r * del_i + f_i * del_r;
                 f_r = temp;
@@ -698,6 +708,10 @@ mb_status mb_plan_create_ex(mb_plan **plan, int device, int buffer_size, int hop
     D.mel_w_exact = p->d_mel_w_exact;
     D.exact = (flags & MB_FLAG_EXACT_FFT) ? 1 : 0;
     if (D.exact) p->kernel_name = "generic-exact";
+    // the warp-per-frame exact kernel: MB_FLAG_EXACT_FFT plans of its sizes, and the second pass of the adaptive plans
+    p->has_exact_warp = want_exact_tables && mb_exact_warp_supports(N) && !(flags & MB_FLAG_GENERIC_KERNEL) &&
+                        (size_t)prop.sharedMemPerBlockOptin >= mb_exact_warp_smem_bytes(N) + 16384;  // (+ its static scratch)
+    if (D.exact && p->has_exact_warp) p->kernel_name = N == 2048 ? "exactw2048" : N == 1024 ? "exactw1024" : "exactw512";
     if (D.exact && (N > 16384 || ((flags & MB_FLAG_CLUSTER_FFT) && N >= 64))) {
         p->use_cluster = true;
         p->kernel_name = "exact-cluster2";

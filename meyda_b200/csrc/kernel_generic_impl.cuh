@@ -3,6 +3,13 @@
 
 constexpr int kThreads = MB_GENERIC_THREADS;
 constexpr int kWarps = kThreads / 32;
+// MB_GENERIC_WARP_LOCAL (kernel_exact_warp.cu, with MB_GENERIC_THREADS 32): the warps of a CTA work on frames of their
+// own, so "the thread's index in its frame's team" is its lane and the epilogue's team is one warp.
+#ifdef MB_GENERIC_WARP_LOCAL
+#define MB_TID ((int)(threadIdx.x & 31))
+#else
+#define MB_TID ((int)threadIdx.x)
+#endif
 // One-warp CTAs (bufferSize <= 512) need no block barrier: warp-level ordering is enough.
 __device__ __forceinline__ void block_sync() {
     if constexpr (kWarps == 1) __syncwarp();
@@ -43,7 +50,7 @@ __device__ __forceinline__ void exact_pass(float *xre, float *xim, const double2
                                            int log2w) {
     constexpr int R = 1 << Q;
     const int w = 1 << log2w;
-    for (int idx = threadIdx.x; idx < (n >> Q); idx += kThreads) {
+    for (int idx = MB_TID; idx < (n >> Q); idx += kThreads) {
         const int j = idx & (w - 1);
         const int base = ((idx >> log2w) << (log2w + Q)) + j;
         float re[R], im[R];
@@ -91,7 +98,7 @@ __device__ __forceinline__ void fft_pass(float2 *work, const float2 *__restrict_
     const int items = M >> Q;
     const int log2sub = log2s - Q;
     const int sub = 1 << log2sub;
-    for (int idx = threadIdx.x; idx < items; idx += kThreads) {
+    for (int idx = MB_TID; idx < items; idx += kThreads) {
         const int j = idx & (sub - 1);
         const int b = (idx >> log2sub) << log2s;
         float2 v[R];
@@ -121,9 +128,9 @@ __device__ __forceinline__ double block_sum(double v, double *scratch /*[kWarps]
     v = mb_warp_sum(v);
     if constexpr (kWarps == 1) return v;
     block_sync();
-    if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
+    if ((MB_TID & 31) == 0) scratch[MB_TID >> 5] = v;
     block_sync();
-    const int lane = threadIdx.x & 31;
+    const int lane = MB_TID & 31;
     return mb_warp_sum(lane < kWarps ? scratch[lane] : 0.0);
 }
 
@@ -131,9 +138,9 @@ __device__ __forceinline__ int block_sum_int(int v, int *scratch /*[kWarps]*/) {
     v = mb_warp_sum(v);
     if constexpr (kWarps == 1) return v;
     block_sync();
-    if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
+    if ((MB_TID & 31) == 0) scratch[MB_TID >> 5] = v;
     block_sync();
-    const int lane = threadIdx.x & 31;
+    const int lane = MB_TID & 31;
     return mb_warp_sum(lane < kWarps ? scratch[lane] : 0);
 }
 
@@ -183,7 +190,7 @@ __device__ __forceinline__ void frame_epilogue(const MbDevPlan &P, const mb_outp
     const int M = P.M;
     const uint32_t mask = P.mask;
     const int nb = P.nb, nf = P.nf, nc = P.nc;  // 24 / 26 / 13 unless the plan was created with other parameters
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = MB_TID, lane = tid & 31, warp = tid >> 5;
     double *scan_d = sc.scan_d, *band_sum = sc.band_sum;
     int *red_i = sc.red_i;
     float *specific = sc.specific, *mel_log = sc.mel_log;
@@ -413,7 +420,7 @@ mb_generic_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ M
     int *red_i = sc.red_i;
 
     const uint32_t mask = P.mask;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = MB_TID, lane = tid & 31, warp = tid >> 5;
     const bool want_moments =
         mask & (MB_FEATURE_BIT(MB_FEAT_SPECTRAL_CENTROID) | MB_FEATURE_BIT(MB_FEAT_SPECTRAL_SPREAD) |
                 MB_FEATURE_BIT(MB_FEAT_SPECTRAL_SKEWNESS) | MB_FEATURE_BIT(MB_FEAT_SPECTRAL_KURTOSIS) |
@@ -595,7 +602,7 @@ mb_exact_cluster_kernel(const __grid_constant__ MbDevPlan P, const __grid_consta
     float *amp0 = cluster.map_shared_rank(amp, 0);
 
     const uint32_t mask = P.mask;
-    const int tid = threadIdx.x;
+    const int tid = MB_TID;
     const bool want_moments =
         mask & (MB_FEATURE_BIT(MB_FEAT_SPECTRAL_CENTROID) | MB_FEATURE_BIT(MB_FEAT_SPECTRAL_SPREAD) |
                 MB_FEATURE_BIT(MB_FEAT_SPECTRAL_SKEWNESS) | MB_FEATURE_BIT(MB_FEAT_SPECTRAL_KURTOSIS) |
@@ -711,7 +718,7 @@ mb_big32768_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
     __shared__ Scratch sc;
     const int N = kBigN, M = kBigM;
     const uint32_t mask = P.mask;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = MB_TID, lane = tid & 31, warp = tid >> 5;
     const bool want_moments =
         mask & (MB_FEATURE_BIT(MB_FEAT_SPECTRAL_CENTROID) | MB_FEATURE_BIT(MB_FEAT_SPECTRAL_SPREAD) |
                 MB_FEATURE_BIT(MB_FEAT_SPECTRAL_SKEWNESS) | MB_FEATURE_BIT(MB_FEAT_SPECTRAL_KURTOSIS) |

@@ -488,7 +488,7 @@ mb_warp2048_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
                             const double ad = (double)ab[i];
                             ta += ad;
                             if (want_moments) {
-                                if (kNoise) {
+                                if (kNoise && ((i + (i >> 2)) & 3) == 0) {  // bins 0, 7, 10, 13, 16, 23, 26, 29 of the block: a quarter, off every comb
                                     // theta sigma / a from the exponent trick (ONE integer subtraction, within ~20 %: this feeds a
                                     // bound, and MUFU.RCP with its range fix-up would cost six more instructions per bin), squared
                                     // and clipped to 1 by the multiplier's .sat; 0 and denormals come out huge: a floor bin counts 1
@@ -538,13 +538,10 @@ mb_warp2048_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
                             if (lane == j) stash_put_d(stash, 2, j, r0);
                         }
                         // Q_0 and Q_4 of mb_adaptive.cuh (k := the last bin of the lane's block)
-                        const float ql = 1.6f * qn,  /* (1.6: the exponent trick's worst case, squared) */ k4 = (float)(32 * lane + 31) * (float)(32 * lane + 31);
+                        const float ql = 6.4f * qn,  /* (4: every fourth bin was looked at; 1.6: the exponent trick's worst case, squared) */ k4 = (float)(32 * lane + 31) * (float)(32 * lane + 31);
                         if (kNoise) {
-                            const float q0 = mb_warp_sum(ql), q4 = mb_warp_sum(ql * (k4 * k4));
-                            if (lane == j) {
-                                stash[18][j] = q0;
-                                stash[19][j] = q4;
-                            }
+                            const float q04 = mb_warp_sum2(ql, ql * (k4 * k4), lane);  // lanes < 16: Q_0, the others: Q_4
+                            if ((lane & 15) == 0) stash[18 + (lane >> 4)][j] = q04;
                         }
                     }
                     if (want_rolloff) {
@@ -581,6 +578,7 @@ mb_warp2048_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
                         }
                     }
                     __syncwarp();
+                    float nu_lane = 0.f, ndl_lane = 0.f;  // this lane's share of the noise bounds (mb_adaptive.cuh)
                     // ---- lanes finish the bands: loudness.js:55-63, perceptual*.js
                     if (want_bark) {
                         float sp = 0.f, nu = 0.f;
@@ -592,7 +590,7 @@ mb_warp2048_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
                             if (kNoise) nu = mb_noise_band(bsum, sp, S.noise_c[0][lane], sigma);
                         }
                         const float total = mb_warp_sum(sp);
-                        if (kNoise) nu = mb_warp_sum(nu);
+                        nu_lane = nu;
                         float mx = (sp > 0.f) ? sp : 0.f;  // NaN never compares greater (perceptualSpread.js:6)
 #pragma unroll
                         for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
@@ -602,7 +600,6 @@ mb_warp2048_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
                             stash[14][j] = total;
                             stash[15][j] = mx;
                             stash[16][j] = sharp;
-                            stash[20][j] = nu;
                         }
                     }
                     // ---- mel energies from the pieces, log, DCT (mfcc.js:40-93).  Lane s owns mel segment
@@ -628,10 +625,7 @@ mb_warp2048_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
                         const float fall_next = __shfl_down_sync(0xffffffffu, fall, 1);
                         const float melE = rise + fall_next;
                         const float lgE = ln_approx(melE);  // lanes >= 26 are not used below
-                        if (kNoise) {
-                            const float ndl = mb_warp_sum(lane < MB_NUM_MEL_FILTERS ? mb_noise_mel(melE, S.noise_c[1][lane], S.noise_c[2][lane], sigma) : 0.f);
-                            if (lane == j) stash[21][j] = ndl;
-                        }
+                        if (kNoise && lane < MB_NUM_MEL_FILTERS) ndl_lane = mb_noise_mel(melE, S.noise_c[1][lane], S.noise_c[2][lane], sigma);
                         // 13 x 26 DCT on 26 lanes: lane k + 13 h sums filters 13 h .. 13 h + 12 of coefficient k
                         float acc = 0.f;
                         const int half = lane >= MB_NUM_MFCC ? MB_NUM_MFCC : 0;
@@ -642,6 +636,10 @@ mb_warp2048_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
                         }
                         acc += __shfl_down_sync(0xffffffffu, acc, MB_NUM_MFCC);
                         if (lane < MB_NUM_MFCC) O.mfcc[g * MB_NUM_MFCC + lane] = acc * (1.0f / (float)MB_NUM_MFCC);
+                    }
+                    if (kNoise && want_pieces) {
+                        const float nb2 = mb_warp_sum2(nu_lane, ndl_lane, lane);  // lanes < 16: the bands' bound, the others: the filters'
+                        if ((lane & 15) == 0) stash[20 + (lane >> 4)][j] = nb2;
                     }
                 }
             }
@@ -663,7 +661,8 @@ mb_warp2048_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
             F.log2sum = (double)stash[12][lane] - (double)(kM * __float_as_int(stash[17][lane]));
             F.rolloff_bin = __float_as_int(stash[13][lane]);
             const int64_t g = g0 + lane;
-            mb_store_scalars(P, O, g, F);
+            MbMoments MO;
+            mb_store_scalars(P, O, g, F, &MO);
             if (want_bark) {
                 const double total = (double)stash[14][lane], mx = (double)stash[15][lane];
                 const double sharp = (double)stash[16][lane] + P.sharp_const;
@@ -676,14 +675,14 @@ mb_warp2048_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
             }
             if (kNoise && want_spectrum && T.fix_count != nullptr) {
                 MbNoiseFrame NF;
-                NF.sigma = (float)((double)kMbNoiseRel * sqrt(F.energy * (1.0 / kN)));
+                NF.sigma = mb_noise_sigma((float)F.energy, 1.0f / (float)kN);  // (frames too small for this float were rescaled: flagged below)
                 NF.q0 = stash[18][lane];
                 NF.q4 = stash[19][lane];
                 NF.sum_u = stash[20][lane];
                 NF.sum_dl = stash[21][lane];
                 NF.total = stash[14][lane];
                 NF.sharp = stash[16][lane] + (float)P.sharp_const;
-                need_exact = __float_as_int(stash[17][lane]) != 0 || mb_noise_needs_exact(P, mask, F, NF);
+                need_exact = __float_as_int(stash[17][lane]) != 0 || mb_noise_needs_exact(P, mask, F, MO, NF);
             }
         }
         mb_noise_append(T, need_exact, g0 + lane);  // frames of this chunk that the exact-FFT kernel redoes

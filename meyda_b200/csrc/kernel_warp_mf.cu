@@ -508,7 +508,7 @@ mb_warpmf_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ Mb
                             const double ad = (double)ab[i];
                             ta += ad;
                             if (want_moments) {
-                                if (kNoise) {
+                                if (kNoise && ((i + (i >> 2)) & 3) == 0) {  // bins 0, 7, 10, 13, 16, 23, 26, 29 of the block: a quarter, off every comb
                                     // theta sigma / a from the exponent trick (ONE integer subtraction, within ~20 %: this feeds a
                                     // bound, and MUFU.RCP with its range fix-up would cost six more instructions per bin), squared
                                     // and clipped to 1 by the multiplier's .sat; 0 and denormals come out huge: a floor bin counts 1
@@ -571,7 +571,7 @@ mb_warpmf_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ Mb
                         const double s1 = fma(c, ta, t1);
                         const double r0 = group_sum_d<kA>(ta), r1 = group_sum_d<kA>(s1);
                         // Q_0 and Q_4 of mb_adaptive.cuh (k := the last bin of the lane's block)
-                        const float ql = 1.6f * qn,  /* (1.6: the exponent trick's worst case, squared) */ k4 = (float)(32 * lp + 31) * (float)(32 * lp + 31);
+                        const float ql = 6.4f * qn,  /* (4: every fourth bin was looked at; 1.6: the exponent trick's worst case, squared) */ k4 = (float)(32 * lp + 31) * (float)(32 * lp + 31);
                         const float q0 = kNoise ? group_sum_f<kA>(ql) : 0.f, q4 = kNoise ? group_sum_f<kA>(ql * (k4 * k4)) : 0.f;
                         if (lp == 0 && lf < nfg) {
                             if (!want_rolloff) stash_put_d(stash, 2, j + lf, r0);
@@ -733,7 +733,8 @@ mb_warpmf_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ Mb
             F.log2sum = (double)stash[12][lane] - (double)(kM * ks);
             F.rolloff_bin = __float_as_int(stash[13][lane]);
             const int64_t gg = g0 + lane;
-            mb_store_scalars(P, O, gg, F);
+            MbMoments MO;
+            mb_store_scalars(P, O, gg, F, &MO);
             if (want_bark) {
                 const double total = (double)stash[14][lane], mx = (double)stash[15][lane];
                 const double sharp = (double)stash[16][lane] + P.sharp_const;
@@ -746,14 +747,14 @@ mb_warpmf_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ Mb
             }
             if (kNoise && want_spectrum && T.fix_count != nullptr) {
                 MbNoiseFrame NF;
-                NF.sigma = (float)((double)kMbNoiseRel * sqrt(F.energy * (1.0 / kN)));
+                NF.sigma = mb_noise_sigma((float)F.energy, 1.0f / (float)kN);  // (frames too small for this float were rescaled: flagged below)
                 NF.q0 = stash[18][lane];
                 NF.q4 = stash[19][lane];
                 NF.sum_u = stash[20][lane];
                 NF.sum_dl = stash[21][lane];
                 NF.total = stash[14][lane];
                 NF.sharp = stash[16][lane] + (float)P.sharp_const;
-                need_exact = ks != 0 || mb_noise_needs_exact(P, mask, F, NF);
+                need_exact = ks != 0 || mb_noise_needs_exact(P, mask, F, MO, NF);
             }
         }
         mb_noise_append(T, need_exact, g0 + lane);  // frames of this chunk that the exact-FFT kernel redoes

@@ -64,8 +64,11 @@ struct MbNoiseFrame {
     float total, sharp;  // loudness.total and the weighted sum of perceptualSharpness.js:6-8 + its constant
 };
 
-// The frame-level decision, one frame per thread.  `mask`: requested features; P.noise_sqrtT[p] = kap sqrt(sum_k k^(2p)).
-static __device__ __noinline__ bool mb_noise_needs_exact(const MbDevPlan &P, uint32_t mask, const MbFrameSums &S, const MbNoiseFrame &F) {
+// The frame-level decision, one frame per thread.  `mask`: requested features; M: what mb_store_scalars derived from
+// the sums; P.noise_sqrtT[p] = kap sqrt(sum_k k^(2p)).  First-order error propagation with the exact partial
+// derivatives of spectralSkewness.js / spectralKurtosis.js (a handful of multiplications and three divisions).
+__device__ __forceinline__ bool mb_noise_needs_exact(const MbDevPlan &P, uint32_t mask, const MbFrameSums &S, const MbMoments &M,
+                                                     const MbNoiseFrame &F) {
     if (!(S.energy > 0.0)) return S.energy != 0.0;  // silence: nothing to amplify; NaN: the exact path owns the special values
     const float tol = kMbNoiseHalfTol;
     bool bad = false;
@@ -81,50 +84,58 @@ static __device__ __noinline__ bool mb_noise_needs_exact(const MbDevPlan &P, uin
     const uint32_t mom = MB_FEATURE_BIT(MB_FEAT_SPECTRAL_CENTROID) | MB_FEATURE_BIT(MB_FEAT_SPECTRAL_SPREAD) |
                          MB_FEATURE_BIT(MB_FEAT_SPECTRAL_SKEWNESS) | MB_FEATURE_BIT(MB_FEAT_SPECTRAL_KURTOSIS) |
                          MB_FEATURE_BIT(MB_FEAT_SPECTRAL_FLATNESS) | MB_FEATURE_BIT(MB_FEAT_SPECTRAL_SLOPE);
-    if ((mask & mom) && !bad) {
-        const double sg = (double)F.sigma, n = (double)P.M;
+    if (mask & mom) {
+        const double sg = (double)F.sigma, n = (double)P.M, dtol = (double)tol;
         const double q0 = (double)F.q0, q4 = (double)F.q4;
-        // Q_p <= Q_0^(1 - p/4) Q_4^(p/4) (moments are log-convex in p)
+        // Q_p <= Q_0^(1 - p/4) Q_4^(p/4) (moments are log-convex in p); sums move by sigma (kap sqrt(T_2p) + Q_p)
         const double g = (q0 > 0.0 && q4 > 0.0) ? sqrt(sqrt(q4 / q0)) : 0.0;
-        double dS[5], qp = q0;
-#pragma unroll
-        for (int p = 0; p < 5; p++) {
-            dS[p] = sg * (P.noise_sqrtT[p] + qp);
-            qp *= g;
-        }
-        const double s[5] = {S.s0, S.s1, S.s2, S.s3, S.s4};
-        // spectralCentroid.js .. spectralKurtosis.js at the sums as they are and with one sum moved at a time
-        double f0[4], dd[4] = {0, 0, 0, 0};
-#pragma unroll 1
-        for (int p = -1; p < 5; p++) {
-            double t[5];
-#pragma unroll
-            for (int i = 0; i < 5; i++) t[i] = s[i] + (i == p ? dS[i] : 0.0);
-            const double m1 = t[1] / t[0], m2 = t[2] / t[0], m3 = t[3] / t[0], m4 = t[4] / t[0];
-            const double sd = sqrt(m2 - m1 * m1);
-            const double f[4] = {m1, sd, (2 * m1 * m1 * m1 - 3 * m1 * m2 + m3) / (sd * sd * sd),
-                                 (-3 * m1 * m1 * m1 * m1 + 6 * m1 * m2 - 4 * m1 * m3 + m4) / (sd * sd * sd * sd)};
-#pragma unroll
-            for (int i = 0; i < 4; i++) {
-                if (p < 0) f0[i] = f[i];
-                else dd[i] += fabs(f[i] - f0[i]);
+        const double inv0 = 1.0 / S.s0;
+        const double r0 = sg * (P.noise_sqrtT[0] + q0) * inv0;  // relative motion of S_0
+        const double q1 = q0 * g, q2 = q1 * g, q3 = q2 * g;
+        // absolute motion of m_i = S_i / S_0: (dS_i + m_i dS_0) / S_0
+        const double d1 = sg * (P.noise_sqrtT[1] + q1) * inv0 + M.m1 * r0;
+        const double d2 = sg * (P.noise_sqrtT[2] + q2) * inv0 + M.m2 * r0;
+        const double d3 = sg * (P.noise_sqrtT[3] + q3) * inv0 + M.m3 * r0;
+        const double d4 = sg * (P.noise_sqrtT[4] + q4) * inv0 + M.m4 * r0;
+        const double m1 = M.m1, m2 = M.m2, m3 = M.m3, var = M.var, sd = M.sd;
+        if (mb_has(mask, MB_FEAT_SPECTRAL_CENTROID)) bad |= !(d1 <= dtol * fmax(1.0, m1));
+        // spectralSlope.js:17 is linear in the centroid, alpha (c - (n-1)/2), and compared relatively
+        if (mb_has(mask, MB_FEAT_SPECTRAL_SLOPE)) bad |= !(d1 <= dtol * fabs(m1 - 0.5 * (n - 1.0)));
+        const uint32_t high = MB_FEATURE_BIT(MB_FEAT_SPECTRAL_SPREAD) | MB_FEATURE_BIT(MB_FEAT_SPECTRAL_SKEWNESS) | MB_FEATURE_BIT(MB_FEAT_SPECTRAL_KURTOSIS);
+        if (mask & high) {
+            const double dv = d2 + 2.0 * m1 * d1;  // motion of var = m2 - m1^2
+            bad |= !(dv <= 0.25 * var);            // (first order only holds while the variance keeps its size)
+            const double iv = 1.0 / var, isd = 1.0 / sd;
+            if (mb_has(mask, MB_FEAT_SPECTRAL_SPREAD)) bad |= !(0.5 * dv * isd <= dtol * fmax(1.0, sd));
+            if (mb_has(mask, MB_FEAT_SPECTRAL_SKEWNESS)) {  // A / var^1.5, A = 2 m1^3 - 3 m1 m2 + m3
+                const double A = 2.0 * m1 * m1 * m1 - 3.0 * m1 * m2 + m3, c = 1.5 * A * iv;
+                const double e = (fabs(6.0 * m1 * m1 - 3.0 * m2 + c * 2.0 * m1) * d1 + fabs(-3.0 * m1 - c) * d2 + d3) * iv * isd;
+                bad |= !(e <= dtol * fmax(1.0, fabs(A * iv * isd)));
+            }
+            if (mb_has(mask, MB_FEAT_SPECTRAL_KURTOSIS)) {  // B / var^2, B = -3 m1^4 + 6 m1 m2 - 4 m1 m3 + m4
+                const double B = -3.0 * m1 * m1 * m1 * m1 + 6.0 * m1 * m2 - 4.0 * m1 * m3 + M.m4, c = 2.0 * B * iv;
+                const double e = (fabs(-12.0 * m1 * m1 * m1 + 6.0 * m2 - 4.0 * m3 + c * 2.0 * m1) * d1 + fabs(6.0 * m1 - c) * d2 +
+                                  4.0 * m1 * d3 + d4) * iv * iv;
+                bad |= !(e <= dtol * fmax(1.0, fabs(B * iv * iv)));
             }
         }
-        const int feat[4] = {MB_FEAT_SPECTRAL_CENTROID, MB_FEAT_SPECTRAL_SPREAD, MB_FEAT_SPECTRAL_SKEWNESS, MB_FEAT_SPECTRAL_KURTOSIS};
-#pragma unroll
-        for (int i = 0; i < 4; i++)
-            if (mb_has(mask, feat[i])) bad |= !(dd[i] <= (double)tol * fmax(1.0, fabs(f0[i])));
-        // spectralSlope.js:17 is linear in the centroid, alpha (c - (n-1)/2), and compared relatively
-        if (mb_has(mask, MB_FEAT_SPECTRAL_SLOPE)) bad |= !(dd[0] <= (double)tol * fabs(f0[0] - 0.5 * (n - 1.0)));
         if (mb_has(mask, MB_FEAT_SPECTRAL_FLATNESS)) {
-            // flatness = exp(mean ln a) n / S0: mean ln a moves by (Q0 + 4 sqrt(Q0) / theta) / n, S0 by dS0
-            const double flat = exp(S.log2sum * 0.6931471805599453 / n) * n / S.s0;
-            const double dml = (q0 + 4.0 * sqrt(q0) / (double)kMbNoiseTheta) / n + dS[0] / S.s0;
-            bad |= !(flat * expm1(dml) <= (double)tol);
+            // flatness = exp(mean ln a) n / S0: mean ln a moves by (Q0 + 4 sqrt(Q0) / theta) / n, S0 by r0
+            const double dml = (q0 + 4.0 * sqrt(q0) / (double)kMbNoiseTheta) / n + r0;
+            bad |= !(dml <= 1.0) || !(M.flatness * (dml + dml * dml) <= dtol);  // e^x - 1 <= x + x^2 on [0, 1]
             bad |= (S.log2sum < -1e30) && (S.s0 > 0.0);  // a bin that is exactly 0 here need not be in the reference
         }
     }
     return bad;
+}
+
+// Sums two floats over the warp with five shuffle steps: lanes < 16 return the total of a, the others that of b.
+__device__ __forceinline__ float mb_warp_sum2(float a, float b, int lane) {
+    const bool h = lane & 16;
+    float c = (h ? b : a) + __shfl_xor_sync(0xffffffffu, h ? a : b, 16);
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    return c;
 }
 
 // A warp appends its flagged frames (need: one frame per lane) to the plan's list.

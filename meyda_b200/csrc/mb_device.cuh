@@ -204,8 +204,15 @@ struct MbFrameSums {
     int rolloff_bin;            // (n + 1) of spectralRolloff.js:15
 };
 
+// What mb_store_scalars derived on the way (mb_adaptive.cuh bounds its error terms from these).
+struct MbMoments {
+    double m1, m2, m3, m4;  // S_i / S_0
+    double var, sd;         // m2 - m1^2 and its root
+    double flatness;
+};
+
 __device__ __forceinline__ void mb_store_scalars(const MbDevPlan &P, const mb_outputs &O, int64_t g,
-                                                 const MbFrameSums &S) {
+                                                 const MbFrameSums &S, MbMoments *mo = nullptr) {
     const uint32_t mask = P.mask;
     const double n = (double)P.M;
     if (mb_has(mask, MB_FEAT_RMS)) O.rms[g] = (float)sqrt(S.energy / (double)P.N);
@@ -221,8 +228,16 @@ __device__ __forceinline__ void mb_store_scalars(const MbDevPlan &P, const mb_ou
     if (mb_has(mask, MB_FEAT_SPECTRAL_KURTOSIS))  // spectralKurtosis.js:7-9: 6*m1*m2, not 6*m1^2*m2
         O.spectral_kurtosis[g] =
             (float)((-3 * m1 * m1 * m1 * m1 + 6 * m1 * m2 - 4 * m1 * m3 + m4) / (sd * sd * sd * sd));
-    if (mb_has(mask, MB_FEAT_SPECTRAL_FLATNESS))  // (exp(mean ln a) * n) / sum a
-        O.spectral_flatness[g] = (float)(exp(S.log2sum * 0.6931471805599453 / n) * n / S.s0);
+    double flat = 0.0;
+    if (mb_has(mask, MB_FEAT_SPECTRAL_FLATNESS)) {  // (exp(mean ln a) * n) / sum a
+        flat = exp(S.log2sum * 0.6931471805599453 / n) * n / S.s0;
+        O.spectral_flatness[g] = (float)flat;
+    }
+    if (mo) {
+        mo->m1 = m1; mo->m2 = m2; mo->m3 = m3; mo->m4 = m4;
+        mo->var = var; mo->sd = sd;
+        mo->flatness = flat;
+    }
     if (mb_has(mask, MB_FEAT_SPECTRAL_SLOPE)) {   // spectralSlope.js:17; sum f a = (sr/N) s1
         const double amp_freq_sum = S.s1 * (P.sr / (double)P.N);
         O.spectral_slope[g] = (float)((n * amp_freq_sum - P.slope_freq_sum * S.s0) /

@@ -29,5 +29,12 @@ size_t mb_exact_cluster_smem_bytes(int N);
 cudaError_t mb_launch_exact_cluster(const MbDevPlan &P, const MbClipTable &T, const float *samples, const mb_outputs &O,
                                     int num_sms, cudaStream_t stream);
 
+// Exact-FFT mode, one warp per frame (bufferSize 512 / 1024 / 2048): float64 register passes with the float32 stage
+// stores emulated in registers.  tw_small: the 15 recurrence twiddles of widths 1, 2, 4, 8 as (re, im) pairs.
+size_t mb_exact_warp_smem_bytes(int N);
+bool mb_exact_warp_supports(int N);
+cudaError_t mb_launch_exact_warp(const MbDevPlan &P, const MbClipTable &T, const float *samples, const mb_outputs &O,
+                                 int num_sms, cudaStream_t stream, const double *tw_small);
+
 cudaError_t mb_launch_generic(const MbDevPlan &P, const MbClipTable &T, const float *samples, const mb_outputs &O,
                               int num_sms, cudaStream_t stream);

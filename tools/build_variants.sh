@@ -7,7 +7,7 @@ FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompil
 build() { # name, extra flags
   name=$1; shift
   objs=""
-  for f in capi kernel_generic kernel_warp kernel_warp_mf; do nvcc $FLAGS "$@" -c meyda_b200/csrc/$f.cu -o $OUT/${name}_$f.o -Xptxas -v 2> $OUT/${name}_$f.ptxas.txt; objs="$objs $OUT/${name}_$f.o"; done
+  for f in capi kernel_generic kernel_warp kernel_warp_mf kernel_exact_warp; do nvcc $FLAGS "$@" -c meyda_b200/csrc/$f.cu -o $OUT/${name}_$f.o -Xptxas -v 2> $OUT/${name}_$f.ptxas.txt; objs="$objs $OUT/${name}_$f.o"; done
   nvcc -shared -o $OUT/lib_$name.so $objs -lcudart_static -lpthread -ldl -lrt
   grep -A2 "warp2048_kernelILj262143ELb0" $OUT/${name}_kernel_warp.ptxas.txt | grep -E "registers|spill" | tr '\n' ' '; echo " <- $name"
 }
