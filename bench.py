@@ -111,17 +111,17 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def gen_clips(torch, n_clips: int, seed: int, device):
+def gen_clips(torch, n_clips: int, seed: int, device, clip_len: int = CLIP_LEN):
     """Deterministic synthetic audio on the device: white noise (amp 0.25) + three
     sines (amp 0.2) at log-uniform 55..15000 Hz per clip; |x| < 0.85."""
     g = torch.Generator(device=device).manual_seed(seed)
-    x = torch.empty(n_clips, CLIP_LEN, dtype=torch.float32, device=device)
-    t = torch.arange(CLIP_LEN, dtype=torch.float32, device=device) / SR
-    chunk = 64
+    x = torch.empty(n_clips, clip_len, dtype=torch.float32, device=device)
+    t = torch.arange(clip_len, dtype=torch.float32, device=device) / SR
+    chunk = max(1, min(64, (64 * 1323000) // clip_len))
     for c0 in range(0, n_clips, chunk):
         c1 = min(n_clips, c0 + chunk)
         m = c1 - c0
-        blk = (torch.rand(m, CLIP_LEN, device=device, generator=g) - 0.5) * 0.5
+        blk = (torch.rand(m, clip_len, device=device, generator=g) - 0.5) * 0.5
         f = torch.exp(torch.rand(m, 3, device=device, generator=g) * (np.log(15000.0) - np.log(55.0)) + np.log(55.0))
         ph = torch.rand(m, 3, device=device, generator=g) * (2 * np.pi)
         for p in range(3):
@@ -221,6 +221,157 @@ def bind_near_gpu(index: int):
     return "unbound"
 
 
+def alloc_outputs(torch, plan, nf, dev, pin=False):
+    return {k: torch.empty((nf,) + tuple(s[1:]), dtype=torch.int32 if d == np.int32 else torch.float32,
+                           **({"pin_memory": True} if pin else {"device": dev}))
+            for k, (s, d) in plan.output_shapes(nf).items()}
+
+
+def flops_per_frame(n, feats):
+    """real FFT 2.5 N log2 N + window N + magnitude 3 N/2 + ~2 flop per bin and running sum of the
+    requested epilogues (+ the 13 x 26 DCT)."""
+    m = n // 2
+    f = 2.5 * n * np.log2(n) + n + 3 * m
+    sums = 0
+    if set(feats) & {"spectralCentroid", "spectralSpread", "spectralSkewness", "spectralKurtosis"}:
+        sums += 4
+    if "spectralFlatness" in feats:
+        sums += 1
+    if "spectralSlope" in feats:
+        sums += 2
+    if "spectralRolloff" in feats:
+        sums += 1
+    if set(feats) & {"loudness", "perceptualSpread", "perceptualSharpness"}:
+        sums += 1
+    if "mfcc" in feats:
+        sums += 2
+    f += 2 * m * sums
+    if set(feats) & {"powerSpectrum", "mfcc"}:
+        f += m
+    if "mfcc" in feats:
+        f += 2 * 13 * 26
+    return float(f)
+
+
+def run_resident(torch, dist, mb, dev, world, n, hop, feats, clips_rank, clip_len, seed, steps, warmup, flags=0,
+                 ring_bytes_max=24 << 30, sampler=None):
+    """Device-resident throughput of one configuration on this rank: `clips_rank` synthetic clips of `clip_len`
+    samples stay in HBM, a step is one pass over them in waves through a reused output ring; CUDA events on the
+    launching stream.  Returns a dict (this rank's numbers; the caller reduces over ranks)."""
+    plan = mb.Plan(n, hop, SR, "hanning", feats, device=dev.index, flags=flags)
+    fpc = (clip_len - n) // hop + 1
+    _, lay = plan.query(np.array([clip_len], np.int64))
+    out_bpf = max(4, int(lay.bytes_per_frame))
+    free_b, _ = torch.cuda.mem_get_info(dev)
+    budget = int(free_b * 0.92)
+    ring_budget = min(ring_bytes_max, budget // 5)
+    wave = max(1, min(clips_rank, ring_budget // (fpc * out_bpf)))
+    max_clips = (budget - wave * fpc * out_bpf) // (clip_len * 4)
+    reduced = clips_rank > max_clips
+    clips_rank = int(min(clips_rank, max_clips))
+    if world > 1:  # every rank processes the same number of clips
+        t = torch.tensor([clips_rank], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        reduced = reduced or int(t.item()) < clips_rank
+        clips_rank = int(t.item())
+    wave = min(wave, clips_rank)
+    x = gen_clips(torch, clips_rank, seed=seed, device=dev, clip_len=clip_len)
+    outs = alloc_outputs(torch, plan, wave * fpc, dev)
+    ptrs = {k: v.data_ptr() for k, v in outs.items()}
+    stream = torch.cuda.current_stream(dev)
+    assert stream.cuda_stream != 0
+    plan.set_stream(stream.cuda_stream)
+    tabs = [(np.arange(w0, min(clips_rank, w0 + wave), dtype=np.int64) * clip_len,
+             np.full(min(clips_rank, w0 + wave) - w0, clip_len, np.int64)) for w0 in range(0, clips_rank, wave)]
+
+    def step():
+        for off, ln in tabs:
+            plan.extract_device(x.data_ptr(), x.numel(), off, ln, ptrs, sync=False)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    if sampler:  # (started ahead of the warm-up: nvidia-smi needs a moment, and the short configurations last under a second)
+        sampler.start()
+    for _ in range(warmup):
+        step()
+    barrier()
+    l0 = plan.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for _ in range(steps):
+        step()
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if sampler else None
+    res = {"plan": plan, "x": x, "ms": ms, "launches": plan.launch_count - l0, "main_launches": len(tabs) * steps,
+           "frames_rank": clips_rank * fpc, "clips_rank": clips_rank, "wave": wave, "fpc": fpc, "reduced": reduced,
+           "refined_last_wave": plan.refined_frames, "clocks": clocks, "kernel": plan.kernel_name}
+    del outs
+    return res
+
+
+def reduce_max(torch, dist, dev, world, v):
+    if world == 1:
+        return v
+    t = torch.tensor([v], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def reduce_sum(torch, dist, dev, world, v):
+    if world == 1:
+        return v
+    t = torch.tensor([v], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return float(t.item())
+
+
+def parity_spot_check(torch, plan, x, clip_len, n, hop, dev, nfc=40):
+    """This rank's first clips and its LAST clip (SURVEY.md 8d generator rule) against the oracle, flat tolerances,
+    no noise band: returns (note, banded count)."""
+    from oracle import c_oracle
+    from tests import parity
+    L = n + hop * (nfc - 1)
+    picks = sorted(set([0, 1, 2, 3, x.shape[0] - 1]) & set(range(x.shape[0])))
+    small = alloc_outputs(torch, plan, nfc, dev)
+    banded = 0
+    for c in picks:
+        plan.extract_device(x.data_ptr(), x.numel(), np.array([c * clip_len], np.int64), np.array([L], np.int64),
+                            {k: v.data_ptr() for k, v in small.items()})
+        ref = c_oracle.extract(x[c, :L].cpu().numpy(), n, hop, SR)
+        b = parity.compare_all({k: v.cpu().numpy() for k, v in small.items()}, ref, n, noise_band=None)
+        banded += sum(b.values())
+    return "ok (%d frames of clips %s vs the oracle, flat tolerances, no noise band)" % (nfc, picks), banded
+
+
+def pcie_ceiling(torch, dev, h2d_bytes, d2h_bytes, reps=3):
+    """Raw pinned-memory copies of the same byte counts, both directions at once on two streams: what the host link
+    gives this rank while every other rank does the same (the caller puts a barrier in front)."""
+    hin = torch.empty(max(1, h2d_bytes), dtype=torch.uint8, pin_memory=True)
+    hout = torch.empty(max(1, d2h_bytes), dtype=torch.uint8, pin_memory=True)
+    din = torch.empty(max(1, h2d_bytes), dtype=torch.uint8, device=dev)
+    dout = torch.empty(max(1, d2h_bytes), dtype=torch.uint8, device=dev)
+    s1, s2 = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+    best = None
+    for r in range(reps + 1):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        with torch.cuda.stream(s1):
+            din.copy_(hin, non_blocking=True)
+        with torch.cuda.stream(s2):
+            hout.copy_(dout, non_blocking=True)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if r > 0:
+            best = dt if best is None else min(best, dt)
+    return best
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -231,6 +382,7 @@ def main():
     ap.add_argument("--features", default="all")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip BASELINE configs[2] and [4]")
     ap.add_argument("--generic", action="store_true", help="force the generic kernel")
     ap.add_argument("--no-refine", action="store_true", help="float32 FFT only: no adaptive exact second pass (A/B)")
     args = ap.parse_args()
@@ -254,103 +406,39 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
+    # A real (non-default) stream: the legacy default stream's handle is 0, which mb_plan_set_stream
+    # reads as "use the plan's own stream" -- the events must sit on the launching stream.
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
 
     feats = mb.FEATURES if args.features == "all" else args.features.split(",")
     from meyda_b200.sharding import shard_range
     c0, c1 = shard_range(args.clips, world, rank)
-    my_clips = c1 - c0
-    fpc = frames_per_clip()
-    plan = mb.Plan(N, HOP, SR, "hanning", feats, device=local_rank,
-                   flags=(_capi.MB_FLAG_GENERIC_KERNEL if args.generic else 0) | (_capi.MB_FLAG_NO_REFINE if args.no_refine else 0))
-    _, lay = plan.query(np.array([CLIP_LEN], np.int64))
-    out_bpf = int(lay.bytes_per_frame)
+    flags = (_capi.MB_FLAG_GENERIC_KERNEL if args.generic else 0) | (_capi.MB_FLAG_NO_REFINE if args.no_refine else 0)
 
-    # ---- memory plan: resident clips + output ring for one wave
-    free_b, _total_b = torch.cuda.mem_get_info(dev)
-    budget = int(free_b * 0.92)
-    ring_budget = min(24 << 30, budget // 5)
-    wave_clips = max(1, min(my_clips, ring_budget // (fpc * out_bpf)))
-    ring_bytes = wave_clips * fpc * out_bpf
-    max_clips = (budget - ring_bytes) // (CLIP_LEN * 4)
-    reduced = False
-    if my_clips > max_clips:
-        my_clips = int(max_clips)
-        reduced = True
-    if world > 1:  # every rank processes the same number of clips
-        t = torch.tensor([my_clips], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MIN)
-        if int(t.item()) < my_clips:
-            my_clips, reduced = int(t.item()), True
-    wave_clips = min(wave_clips, my_clips)
-    x = gen_clips(torch, my_clips, seed=0x4D455944 + rank, device=dev)
-    shapes = plan.output_shapes(wave_clips * fpc)
-    outs = {k: torch.empty(s, dtype=torch.int32 if d == np.int32 else torch.float32, device=dev)
-            for k, (s, d) in shapes.items()}
-    out_ptrs = {k: v.data_ptr() for k, v in outs.items()}
-    # A real (non-default) stream: the legacy default stream's handle is 0, which mb_plan_set_stream
-    # reads as "use the plan's own stream" -- the events below must sit on the launching stream.
-    stream = torch.cuda.Stream(device=dev)
-    torch.cuda.set_stream(stream)
-    assert stream.cuda_stream != 0
-    plan.set_stream(stream.cuda_stream)
-    waves = [(w0, min(my_clips, w0 + wave_clips)) for w0 in range(0, my_clips, wave_clips)]
-    wave_tabs = [(np.arange(w0, w1, dtype=np.int64) * CLIP_LEN, np.full(w1 - w0, CLIP_LEN, np.int64))
-                 for w0, w1 in waves]
-
-    def step():
-        for off, ln in wave_tabs:
-            plan.extract_device(x.data_ptr(), x.numel(), off, ln, out_ptrs, sync=False)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for _ in range(args.warmup):
-        step()
-    barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    launches0 = plan.launch_count
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record(stream)
-    for _ in range(args.steps):
-        step()
-    e1.record(stream)
-    barrier()
-    ms = e0.elapsed_time(e1)
-    launches = plan.launch_count - launches0
-    refined_last_wave = plan.refined_frames  # frames of the last wave redone with the exact FFT (adaptive plans)
-    # the dominant kernel runs once per wave; an adaptive plan adds one (normally empty) exact-FFT launch per wave
-    main_launches = len(wave_tabs) * args.steps
-    clocks = sampler.stop() if rank == 0 else None
-    if world > 1:
-        t = torch.tensor([ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_max = float(t.item())
-        lt = torch.tensor([launches], device=dev, dtype=torch.int64)
-        dist.all_reduce(lt, op=dist.ReduceOp.SUM)
-        launches_all = int(lt.item())
-    else:
-        ms_max, launches_all = ms, launches
-    frames_rank = my_clips * fpc
-    frames_all = frames_rank * world
+    # ---- headline: BASELINE configs[3]
+    r = run_resident(torch, dist, mb, dev, world, N, HOP, feats, c1 - c0, CLIP_LEN, 0x4D455944 + rank, args.steps,
+                     args.warmup, flags=flags, sampler=ClockSampler(local_rank) if rank == 0 else None)
+    plan, x, fpc = r["plan"], r["x"], r["fpc"]
+    ms_max = reduce_max(torch, dist, dev, world, r["ms"])
+    launches_all = int(reduce_sum(torch, dist, dev, world, r["launches"]))
+    frames_all = r["frames_rank"] * world
     value = frames_all * args.steps / (ms_max * 1e-3)
+    clocks = r["clocks"]
 
-    # ---- roofline of the dominant (only) kernel on this rank
+    # ---- roofline of the dominant kernel on this rank (one launch per wave; an adaptive plan adds one, normally
+    # empty, exact-FFT launch per wave, which is inside the same timed region)
     peak, peak_src = measured_peaks()
     alg_bpf = algorithmic_bytes_per_frame(feats)
-    avg_launch_s = (ms * 1e-3) / max(1, main_launches)
-    frames_per_launch = frames_rank * args.steps / max(1, main_launches)
+    avg_launch_s = (r["ms"] * 1e-3) / max(1, r["main_launches"])
+    frames_per_launch = r["frames_rank"] * args.steps / max(1, r["main_launches"])
     achieved = alg_bpf * frames_per_launch / avg_launch_s / 1e9
     traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
         try:
             tj = json.load(open(tp))
-            # measured by ncu on a full 302-clip launch of this kernel with the full feature set; DRAM traffic is
+            # measured by ncu on a full launch of this kernel with the full feature set; DRAM traffic is
             # proportional to the frames of a launch, so it is restated for this run's (average) launch size
             if tj.get("kernel") == plan.kernel_name and feats == mb.FEATURES:
                 traffic = tj["dram_bytes_per_launch"] * frames_per_launch / tj["frames_per_launch"]
@@ -362,56 +450,78 @@ def main():
                 "algorithmic_bytes_per_frame": alg_bpf, "frames_per_launch": frames_per_launch,
                 "avg_launch_ms": avg_launch_s * 1e3}
 
-    # ---- parity spot check against the oracle on this rank's first clip (outside the timed region)
-    parity_note = None
+    # ---- parity spot check against the oracle (outside the timed region)
+    parity_note, parity_banded = None, None
     if rank == 0:
         try:
-            from oracle import c_oracle
-            from tests import parity
-            nfc = 40
-            L = N + HOP * (nfc - 1)
-            small = {k: torch.empty((nfc,) + tuple(s[1:]), dtype=torch.int32 if d == np.int32 else torch.float32,
-                                    device=dev) for k, (s, d) in plan.output_shapes(nfc).items()}
-            plan.extract_device(x.data_ptr(), x.numel(), np.array([0], np.int64), np.array([L], np.int64),
-                                {k: v.data_ptr() for k, v in small.items()})
-            ref = c_oracle.extract(x[0, :L].cpu().numpy(), N, HOP, SR)
-            parity.compare_all({k: v.cpu().numpy() for k, v in small.items()}, ref, N)
-            parity_note = "ok (%d frames vs oracle)" % nfc
+            parity_note, parity_banded = parity_spot_check(torch, plan, x, CLIP_LEN, N, HOP, dev)
         except AssertionError as e:  # report, never hide
             parity_note = "FAILED: %s" % (str(e)[:200],)
 
-    # ---- e2e: public host-memory API, pinned buffers, H2D + kernel + D2H timed
+    # ---- e2e: public host-memory API, H2D + kernel + D2H timed; pinned (the facade's default) and pageable buffers
     e2e = None
     if not args.no_e2e:
         e2e_clips = 12
         host_x = torch.empty(e2e_clips, CLIP_LEN, dtype=torch.float32, pin_memory=True)
         host_x.copy_(x[:e2e_clips])
         nf = e2e_clips * fpc
-        host_out = {k: torch.empty((nf,) + tuple(s[1:]), dtype=torch.int32 if d == np.int32 else torch.float32,
-                                   pin_memory=True) for k, (s, d) in plan.output_shapes(nf).items()}
         hx = host_x.numpy().reshape(-1)
-        ho = {k: v.numpy() for k, v in host_out.items()}
+        ho = plan.alloc_host_outputs(nf, pinned=True)  # mb_host_alloc, what Plan.extract_host and js/addon.cc hand out
         off = np.arange(e2e_clips, dtype=np.int64) * CLIP_LEN
         ln = np.full(e2e_clips, CLIP_LEN, np.int64)
         plan.set_stream(None)
-        for _ in range(2):
-            plan.extract_host(hx, off, ln, out=ho)
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            plan.extract_host(hx, off, ln, out=ho)
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
+
+        def timed(fn, reps):
+            for _ in range(2):
+                fn()
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                fn()
+            torch.cuda.synchronize()
+            return reduce_max(torch, dist, dev, world, (time.perf_counter() - t0) / reps)
+
+        dt = timed(lambda: plan.extract_host(hx, off, ln, out=ho), args.steps)
+        d2h = int(sum(v.nbytes for k, v in ho.items() if k != "buffer"))  # `buffer` rows are filled on the host
+        e2e = {"value": nf * world / dt, "unit": UNIT, "h2d_bytes_per_step": int(hx.nbytes), "d2h_bytes_per_step": d2h,
+               "batch": "%d clips x 30 s per rank per step, mb_extract(MB_MEM_HOST) into mb_host_alloc (pinned) arrays; the "
+                        "`buffer` rows are the caller's own samples and are filled on the host, not copied back" % e2e_clips}
+        # the host link's own ceiling for these byte counts, every rank at once
         if world > 1:
-            t = torch.tensor([dt], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
-        e2e = {"value": nf * world * args.steps / dt, "unit": UNIT, "h2d_bytes_per_step": int(hx.nbytes),
-               "d2h_bytes_per_step": int(sum(v.nbytes for v in ho.values())),
-               "batch": "%d clips x 30 s per rank per step, pinned host memory, mb_extract(MB_MEM_HOST)" % e2e_clips}
+            dist.barrier()
+        ceil_dt = reduce_max(torch, dist, dev, world, pcie_ceiling(torch, dev, int(hx.nbytes), d2h))
+        e2e["pcie_ceiling"] = {"value": nf * world / ceil_dt, "unit": UNIT,
+                               "h2d_GBps_per_rank": hx.nbytes / ceil_dt / 1e9, "d2h_GBps_per_rank": d2h / ceil_dt / 1e9,
+                               "how": "raw pinned cudaMemcpyAsync of the same H2D and D2H byte counts on two streams, all ranks at once"}
+        e2e["frac_of_pcie_ceiling"] = e2e["value"] / e2e["pcie_ceiling"]["value"]
+        ho_page = plan.alloc_host_outputs(nf, pinned=False)
+        hx_page = np.array(hx)
+        dtp = timed(lambda: plan.extract_host(hx_page, off, ln, out=ho_page), max(1, min(args.steps, 3)))
+        e2e["pageable"] = {"value": nf * world / dtp, "unit": UNIT, "note": "the same call with pageable numpy arrays on both sides"}
         if numa_note:
             e2e["host_binding"] = numa_note
-        del host_x, host_out
+        # one process driving every visible GPU through mb_extract_multi (what the N-API caller does)
+        if world == 1 and torch.cuda.device_count() > 1:
+            ndev = torch.cuda.device_count()
+            plans = [plan] + [mb.Plan(N, HOP, SR, "hanning", feats, device=d, flags=flags) for d in range(1, ndev)]
+            mc = e2e_clips * ndev
+            mx = torch.empty(mc, CLIP_LEN, dtype=torch.float32, pin_memory=True)
+            for i in range(ndev):
+                mx[i * e2e_clips:(i + 1) * e2e_clips].copy_(x[:e2e_clips])
+            mo_ = plan.alloc_host_outputs(mc * fpc, pinned=True)
+            moff = np.arange(mc, dtype=np.int64) * CLIP_LEN
+            mln = np.full(mc, CLIP_LEN, np.int64)
+            mxn = mx.numpy().reshape(-1)
+            dtm = timed(lambda: mb.meyda.extract_multi(plans, mxn, moff, mln, out=mo_), max(1, min(args.steps, 3)))
+            e2e["multi_device_one_process"] = {"value": mc * fpc / dtm, "unit": UNIT, "devices": ndev,
+                                               "call": "mb_extract_multi, %d clips per device per step" % e2e_clips}
+            for p_ in plans[1:]:
+                p_.close()
+            del mx, mo_
+        del host_x, ho, ho_page
+        plan.set_stream(stream.cuda_stream)
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -421,21 +531,70 @@ def main():
         cpu_baseline = {"value": f / dt, "unit": UNIT, "cores": threads, "kind": "port",
                         "sample": "%d clips x %d frames, all 18 features, oracle C restatement on %d pthreads (%.1f s)"
                                   % (clips.shape[0], cfpc, threads, dt)}
+    kernel_name, wave_clips, reduced, clips_used = plan.kernel_name, r["wave"], r["reduced"], r["clips_rank"] * world
+    refined_last = r["refined_last_wave"]
+    plan.close()
+    del x, r, plan
+    torch.cuda.empty_cache()
+
+    # ---- BASELINE configs[2] and [4] (compute-bound: reported against the FP32 FFMA peak measured in this process)
+    secondary = []
+    if not args.no_secondary:
+        import ctypes
+        f32 = ctypes.c_double(0)
+        _capi.check(_capi.lib().mb_measure_peaks(local_rank, ctypes.byref(f32), None))
+        ffma = float(f32.value)
+        C3 = ["mfcc", "spectralCentroid", "spectralSpread", "spectralSkewness", "spectralKurtosis"]
+        C5 = ["amplitudeSpectrum", "spectralRolloff", "spectralFlatness", "spectralSlope"]
+        for name, n2, hop2, feats2, total, clen in (
+                ("BASELINE configs[2]: synthetic 10,000 clips x 10 s @44.1 kHz mono f32, bufferSize=2048 hop=512, mfcc + spectral moments",
+                 2048, 512, C3, max(world, 10000 * args.clips // CLIPS_TOTAL), 441000),
+                ("BASELINE configs[4]: bufferSize=32768 hop=8192, amplitudeSpectrum + rolloff/flatness/slope over a 1,024-channel x 60 s synthetic array",
+                 32768, 8192, C5, max(world, 1024 * args.clips // CLIPS_TOTAL), 2646000)):
+            a0, a1 = shard_range(total, world, rank)
+            smp = ClockSampler(local_rank) if rank == 0 else None
+            r2 = run_resident(torch, dist, mb, dev, world, n2, hop2, feats2, a1 - a0, clen, 0x4D455944 + 1000 + rank,
+                              args.steps, args.warmup, flags=flags, sampler=smp)
+            ms2 = reduce_max(torch, dist, dev, world, r2["ms"])
+            fps = r2["frames_rank"] * world * args.steps / (ms2 * 1e-3)
+            fl = flops_per_frame(n2, feats2)
+            bpf2 = 4 * hop2 + 4 * sum({"amplitudeSpectrum": n2 // 2, "mfcc": 13}.get(f_, 1) for f_ in feats2)
+            note2 = None
+            if rank == 0:
+                try:
+                    note2, _ = parity_spot_check(torch, r2["plan"], r2["x"], clen, n2, hop2, dev, nfc=6 if n2 > 4096 else 40)
+                except AssertionError as e:
+                    note2 = "FAILED: %s" % (str(e)[:200],)
+            per_gpu = fps / world
+            secondary.append({
+                "config": {"workload": name, "clips_total": r2["clips_rank"] * world, "bufferSize": n2, "hop": hop2,
+                           "features": feats2, "frames_per_clip": r2["fpc"], "wave_clips": r2["wave"],
+                           "parallelism": "clip-shard x%d, no collective" % world},
+                "metric": "feature frames/sec", "value": fps, "unit": UNIT, "ms_per_step": ms2 / args.steps,
+                "kernel": r2["kernel"], "gpu_launches": int(reduce_sum(torch, dist, dev, world, r2["launches"])),
+                "roofline": {"bound": "fp32", "achieved": per_gpu * fl / 1e12, "peak": ffma, "unit": "TFLOP/s",
+                             "frac": per_gpu * fl / 1e12 / ffma, "flops_per_frame": fl,
+                             "peak_source": "FFMA micro-kernel run in this process (mb_measure_peaks)",
+                             "hbm_frac": per_gpu * bpf2 / 1e9 / peak, "algorithmic_bytes_per_frame": bpf2},
+                "clocks": r2["clocks"], "parity": note2})
+            r2["plan"].close()
+            del r2
+            torch.cuda.empty_cache()
 
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(my_clips * world, world, wave_clips),
+            "config": workload_config(clips_used, world, wave_clips),
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": launches_all,
-            "clocks": clocks, "parity": parity_note, "kernel": plan.kernel_name,
-            "frames_per_step": frames_all, "refined_frames_last_wave": refined_last_wave,
+            "clocks": clocks, "parity": parity_note, "parity_banded": parity_banded, "kernel": kernel_name,
+            "frames_per_step": frames_all, "refined_frames_last_wave": refined_last,
+            "secondary": secondary,
         }
         if reduced:
             line["config"]["note"] = "clip count reduced from %d to fit GPU memory" % args.clips
         print(json.dumps(line), flush=True)
-    plan.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

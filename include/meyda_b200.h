@@ -223,6 +223,9 @@ mb_status mb_query_output(const mb_plan *plan, int64_t n_clips, const int64_t *c
  * both memory kinds.  Blocking: returns after the results are in `out`.
  *   MB_MEM_HOST:   samples/out are host pointers (pinned memory from
  *                  mb_host_alloc makes the copies asynchronous and overlapped).
+ *                  The rows of `buffer` (the caller's own samples, framed) are
+ *                  filled on the host while the device works; they never
+ *                  cross PCIe.
  *   MB_MEM_DEVICE: samples/out are device pointers on the plan's device.
  * n_samples is the length of `samples` in floats (bounds check).
  */
@@ -275,6 +278,11 @@ typedef struct mb_wav_info {
     int64_t n_sample_frames; /* per channel */
 } mb_wav_info;
 mb_status mb_wav_parse(const void *file_bytes, int64_t n_bytes, mb_wav_info *info);
+
+/* Measured non-tensor arithmetic peaks of a device, TFLOP/s (an FFMA / DFMA micro-kernel, a few milliseconds): the
+ * denominators of the FP32 / FP64 rooflines bench.py reports for the compute-bound configurations.  Either pointer
+ * may be NULL. */
+mb_status mb_measure_peaks(int device, double *fp32_ffma_tflops, double *fp64_dfma_tflops);
 
 /* Number of kernel launches issued by this plan so far (bench evidence). */
 int64_t mb_plan_launch_count(const mb_plan *plan);

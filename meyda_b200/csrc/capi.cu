@@ -305,11 +305,15 @@ mb_status check_clips(const mb_plan *p, int64_t n_samples, const int64_t *off, c
 // `fix`/`fix_cap`: where the float32 kernels list the frames to be redone exactly (grown here; NULL: plan not adaptive).
 mb_status launch(mb_plan *p, const int64_t *d_off, const int64_t *d_frame_start, int64_t n, int64_t total_frames,
                  const float *d_samples, const mb_outputs &d_out, cudaStream_t stream, int **fix, size_t *fix_cap,
-                 int pcm_channels = 0, int pcm_channel = 0, int pcm_format = MB_SAMPLE_S16) {
+                 int pcm_channels = 0, int pcm_channel = 0, int pcm_format = MB_SAMPLE_S16, uint32_t drop_mask = 0) {
     if (total_frames == 0) return MB_OK;
+    MbDevPlan dev_main = p->dev;
+    dev_main.mask &= ~drop_mask;
     if (total_frames > 0x7fffffff) return fail(MB_ERR_UNSUPPORTED, "more than 2^31 - 1 frames in one launch");
     MbClipTable T{d_off, d_frame_start, n, total_frames, pcm_channels, pcm_channel, pcm_format, nullptr, nullptr, nullptr, nullptr};
-    const bool adaptive = p->adaptive && fix != nullptr;
+    const uint32_t time_only = MB_FEATURE_BIT(MB_FEAT_RMS) | MB_FEATURE_BIT(MB_FEAT_ENERGY) | MB_FEATURE_BIT(MB_FEAT_ZCR) | MB_FEATURE_BIT(MB_FEAT_BUFFER);
+    if ((dev_main.mask & MB_ALL_FEATURES) == 0) return MB_OK;  // (nothing left for the device to produce)
+    const bool adaptive = p->adaptive && fix != nullptr && (dev_main.mask & ~time_only) != 0;
     if (adaptive) {
         if (*fix_cap < (size_t)total_frames + 1) {
             cudaFree(*fix);  // (synchronises with whatever still uses the old list)
@@ -330,22 +334,22 @@ mb_status launch(mb_plan *p, const int64_t *d_off, const int64_t *d_frame_start,
     // kernel, same bits) but store `buffer` rows 16 bytes at a time
     const bool out_ok = (uintptr_t)d_out.buffer % 16 == 0;
     if (p->use_cluster) {
-        MB_CUDA(mb_launch_exact_cluster(p->dev, T, d_samples, d_out, p->num_sms, stream));
+        MB_CUDA(mb_launch_exact_cluster(dev_main, T, d_samples, d_out, p->num_sms, stream));
         p->launches_generic++;
     } else if (p->dev.exact && p->has_exact_warp) {
-        MB_CUDA(mb_launch_exact_warp(p->dev, T, d_samples, d_out, p->num_sms, stream, p->tw_small));
+        MB_CUDA(mb_launch_exact_warp(dev_main, T, d_samples, d_out, p->num_sms, stream, p->tw_small));
         p->launches_warp++;
     } else if (p->has_big_kernel && out_ok && !pcm && ((uintptr_t)d_samples % 4 == 0)) {  // (misaligned frames: read by the lanes)
-        MB_CUDA(mb_launch_big32768(p->dev, T, d_samples, d_out, p->num_sms, stream));
+        MB_CUDA(mb_launch_big32768(dev_main, T, d_samples, d_out, p->num_sms, stream));
         p->launches_warp++;
     } else if (p->has_warp_kernel && tuned_ok && out_ok && ((uintptr_t)d_samples % (pcm ? 2 : 4) == 0)) {
-        MB_CUDA(mb_launch_warp2048(p->dev, T, d_samples, d_out, p->num_sms, stream));
+        MB_CUDA(mb_launch_warp2048(dev_main, T, d_samples, d_out, p->num_sms, stream));
         p->launches_warp++;
     } else if (p->has_mf_kernel && tuned_ok && out_ok && ((uintptr_t)d_samples % (pcm ? 2 : 4) == 0)) {
-        MB_CUDA(mb_launch_warpmf(p->dev, T, d_samples, d_out, p->num_sms, stream));
+        MB_CUDA(mb_launch_warpmf(dev_main, T, d_samples, d_out, p->num_sms, stream));
         p->launches_warp++;
     } else {
-        MB_CUDA(mb_launch_generic(p->dev, T, d_samples, d_out, p->num_sms, stream));
+        MB_CUDA(mb_launch_generic(dev_main, T, d_samples, d_out, p->num_sms, stream));
         p->launches_generic++;
     }
     p->launches++;
@@ -357,9 +361,11 @@ mb_status launch(mb_plan *p, const int64_t *d_off, const int64_t *d_frame_start,
         Tx.fix_list = nullptr;
         Tx.sel_count = *fix;
         Tx.sel_list = *fix + 1;
-        if (p->N > 16384) MB_CUDA(mb_launch_exact_cluster(p->dev_fix, Tx, d_samples, d_out, p->num_sms, stream));
-        else if (p->has_exact_warp) MB_CUDA(mb_launch_exact_warp(p->dev_fix, Tx, d_samples, d_out, p->num_sms, stream, p->tw_small));
-        else MB_CUDA(mb_launch_generic(p->dev_fix, Tx, d_samples, d_out, p->num_sms, stream));
+        MbDevPlan dev_fix = p->dev_fix;
+        dev_fix.mask &= ~drop_mask;
+        if (p->N > 16384) MB_CUDA(mb_launch_exact_cluster(dev_fix, Tx, d_samples, d_out, p->num_sms, stream));
+        else if (p->has_exact_warp) MB_CUDA(mb_launch_exact_warp(dev_fix, Tx, d_samples, d_out, p->num_sms, stream, p->tw_small));
+        else MB_CUDA(mb_launch_generic(dev_fix, Tx, d_samples, d_out, p->num_sms, stream));
         p->launches++;
         p->launches_generic++;
     }
@@ -496,6 +502,17 @@ void offset_outputs(mb_outputs &o, const mb_outputs &base, int64_t frame0, const
         void *b = field_ptr(base, kFields[i]);
         if (b) field_ptr(o, kFields[i]) = (char *)b + (size_t)frame0 * field_elems(kFields[i], D) * 4;
     }
+}
+
+template <typename T>
+__global__ void mb_fma_peak_kernel(T *out, int iters) {
+    T a0 = threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const T b = (T)1.000001, c = (T)0.5;
+    for (int i = 0; i < iters; i++) {
+        a0 = a0 * b + c; a1 = a1 * b + c; a2 = a2 * b + c; a3 = a3 * b + c;
+        a4 = a4 * b + c; a5 = a5 * b + c; a6 = a6 * b + c; a7 = a7 * b + c;
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
 }
 
 }  // namespace
@@ -943,19 +960,67 @@ mb_status mb_plan_synchronize(mb_plan *p) {
 // each chunk is copied in, processed and copied out on one of two streams so
 // that PCIe traffic in both directions overlaps the kernels.
 // `samples` is float32 (pcm_channels == 0) or interleaved int16 PCM; offsets count sample frames either way.
+static mb_status extract_host_impl(mb_plan *p, const void *samples, const int64_t *clip_offset, const int64_t *clip_len,
+                                   int64_t n_clips, const mb_outputs *out, int pcm_channels, int pcm_channel, int pcm_format);
+
 static mb_status extract_host(mb_plan *p, const void *samples, const int64_t *clip_offset, const int64_t *clip_len,
                               int64_t n_clips, const mb_outputs *out, int pcm_channels = 0, int pcm_channel = 0,
                               int pcm_format = MB_SAMPLE_S16) {
     DeviceGuard guard(p->device);
+    const mb_status st = extract_host_impl(p, samples, clip_offset, clip_len, n_clips, out, pcm_channels, pcm_channel, pcm_format);
+    if (st != MB_OK) {
+        // copies of earlier chunks may still be writing into the caller's arrays: drain before reporting the failure
+        const std::string msg = g_last_error;
+        for (auto &s : p->slots)
+            if (s.stream) cudaStreamSynchronize(s.stream);
+        (void)cudaGetLastError();
+        g_last_error = msg;
+    }
+    return st;
+}
+
+static mb_status extract_host_impl(mb_plan *p, const void *samples, const int64_t *clip_offset, const int64_t *clip_len,
+                                   int64_t n_clips, const mb_outputs *out, int pcm_channels, int pcm_channel, int pcm_format) {
     const int N = p->N, hop = p->hop;
     const size_t frame_bytes =
         pcm_channels > 0 ? (size_t)mb_sample_bytes(pcm_format) * (size_t)pcm_channels : 4u;  // bytes per sample frame
     const int64_t bpf = std::max<int64_t>(p->bytes_per_frame, 4);
+    (void)bpf;
     // chunk budget: ~192 MiB of output or ~64 MiB of fresh input, whichever is hit first
-    const int64_t max_frames_out = std::max<int64_t>(1, (192ll << 20) / bpf);
+    const int64_t max_frames_out = std::max<int64_t>(1, (192ll << 20) / std::max<int64_t>(p->bytes_per_frame, 4));
     const int64_t max_frames_in = std::max<int64_t>(1, (64ll << 20) / (4ll * hop));
     const int64_t chunk_frames = std::min(max_frames_out, max_frames_in);
 
+    // `buffer` is the caller's own samples cut into frames (docs.md:19-21): for float32 input the host fills those rows
+    // itself, on a few threads, while the device works -- bit-identical by construction, and a quarter of the full
+    // set's output bytes (8 KB of 33 KB per frame at bufferSize 2048) never crosses PCIe.
+    const bool host_buffer = pcm_channels == 0 && mb_has(p->mask, MB_FEAT_BUFFER);
+    const uint32_t drop_mask = host_buffer ? MB_FEATURE_BIT(MB_FEAT_BUFFER) : 0u;
+    std::vector<std::thread> fillers;
+    if (host_buffer) {
+        std::vector<int64_t> fstart(n_clips + 1, 0);
+        for (int64_t i = 0; i < n_clips; i++) fstart[i + 1] = fstart[i] + mb_num_frames(clip_len[i], N, hop);
+        const int64_t total = fstart[n_clips];
+        const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+        const int nt = (int)std::min<int64_t>(std::max<int64_t>(1, total / 4096), std::min(4u, std::max(1u, hw / 2)));
+        const float *src = (const float *)samples;
+        float *dst = out->buffer;
+        for (int t = 0; t < nt; t++) {
+            const int64_t g0 = total * t / nt, g1 = total * (t + 1) / nt;
+            fillers.emplace_back([=, fs = fstart]() {
+                int64_t c = std::upper_bound(fs.begin(), fs.end(), g0) - fs.begin() - 1;
+                for (int64_t g = g0; g < g1; g++) {
+                    while (g >= fs[c + 1]) c++;
+                    memcpy(dst + g * N, src + clip_offset[c] + (g - fs[c]) * hop, sizeof(float) * (size_t)N);
+                }
+            });
+        }
+    }
+    struct FillJoin {  // (every return path waits for the fillers: they write into the caller's array)
+        std::vector<std::thread> &t;
+        ~FillJoin() { for (auto &x : t) if (x.joinable()) x.join(); }
+    } fill_join{fillers};
+    const int64_t dev_bpf = p->bytes_per_frame - (host_buffer ? 4 * (int64_t)N : 0);  // bytes per frame the device produces
     struct VClip { int64_t off, frames; };
     std::vector<VClip> v;
     p->refined_frames = 0;
@@ -993,7 +1058,7 @@ static mb_status extract_host(mb_plan *p, const void *samples, const int64_t *cl
             MB_CUDA(cudaMalloc((void **)&s.d_samples, span * frame_bytes));
             s.samples_cap = span * frame_bytes;
         }
-        const size_t out_bytes = (size_t)frames * (size_t)p->bytes_per_frame;
+        const size_t out_bytes = std::max<size_t>(16, (size_t)frames * (size_t)dev_bpf);
         if (s.out_cap < out_bytes) {
             cudaFree(s.d_out);
             s.d_out = nullptr;
@@ -1019,12 +1084,12 @@ static mb_status extract_host(mb_plan *p, const void *samples, const int64_t *cl
         memset(&d_out, 0, sizeof(d_out));
         size_t cursor = 0;
         for (int i = 0; i < kNumFields; i++) {
-            if (!mb_has(p->mask, kFields[i].feature)) continue;
+            if (!mb_has(p->mask & ~drop_mask, kFields[i].feature)) continue;
             field_ptr(d_out, kFields[i]) = s.d_out + cursor;
             cursor += (size_t)frames * field_elems(kFields[i], p->dev) * 4;
         }
         st = launch(p, s.d_tab, s.d_tab + v.size(), (int64_t)v.size(), frames, s.d_samples, d_out, s.stream, &s.d_fix,
-                    &s.fix_cap, pcm_channels, pcm_channel, pcm_format);
+                    &s.fix_cap, pcm_channels, pcm_channel, pcm_format, drop_mask);
         if (st != MB_OK) return st;
         if (p->adaptive) {  // how many frames were redone: read back with the outputs, summed after the last chunk
             if (s.h_fix_used == s.h_fix_cap) {
@@ -1039,7 +1104,7 @@ static mb_status extract_host(mb_plan *p, const void *samples, const int64_t *cl
             MB_CUDA(cudaMemcpyAsync(s.h_fix + s.h_fix_used++, s.d_fix, sizeof(int), cudaMemcpyDeviceToHost, s.stream));
         }
         for (int i = 0; i < kNumFields; i++) {
-            if (!mb_has(p->mask, kFields[i].feature)) continue;
+            if (!mb_has(p->mask & ~drop_mask, kFields[i].feature)) continue;
             const size_t per = (size_t)field_elems(kFields[i], p->dev) * 4;
             MB_CUDA(cudaMemcpyAsync((char *)field_ptr(*out, kFields[i]) + (size_t)g_done * per,
                                     field_ptr(d_out, kFields[i]), (size_t)frames * per, cudaMemcpyDeviceToHost,
@@ -1195,6 +1260,43 @@ mb_status mb_extract_multi(mb_plan *const *plans, int n_plans, const float *samp
     for (auto &t : th) t.join();
     for (int d = 0; d < n_plans; d++)
         if (status[d] != MB_OK) return fail(status[d], "device shard %d: %s", d, msgs[d].c_str());
+    return MB_OK;
+}
+
+// ---- measured non-tensor arithmetic peaks of a device (the FP32 / FP64 roofline denominators bench.py reports against)
+mb_status mb_measure_peaks(int device, double *fp32_ffma_tflops, double *fp64_dfma_tflops) {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev)
+        return fail(MB_ERR_NO_DEVICE, "device %d out of range", device);
+    DeviceGuard guard(device);
+    cudaDeviceProp prop;
+    MB_CUDA(cudaGetDeviceProperties(&prop, device));
+    const int blocks = prop.multiProcessorCount * 8, threads = 256;
+    void *buf = nullptr;
+    MB_CUDA(cudaMalloc(&buf, (size_t)blocks * threads * sizeof(double)));
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    auto best_of = [&](bool dbl, int iters) {
+        float best = 1e30f;
+        for (int r = 0; r < 6; r++) {  // (the first run warms up)
+            cudaEventRecord(e0);
+            if (dbl) mb_fma_peak_kernel<double><<<blocks, threads>>>((double *)buf, iters);
+            else mb_fma_peak_kernel<float><<<blocks, threads>>>((float *)buf, iters);
+            cudaEventRecord(e1);
+            cudaEventSynchronize(e1);
+            float ms = 0;
+            cudaEventElapsedTime(&ms, e0, e1);
+            if (r > 0 && ms < best) best = ms;
+        }
+        return 2.0 * 8 * iters * (double)blocks * threads / (best * 1e-3) / 1e12;
+    };
+    if (fp32_ffma_tflops) *fp32_ffma_tflops = best_of(false, 1 << 15);
+    if (fp64_dfma_tflops) *fp64_dfma_tflops = best_of(true, 1 << 13);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(buf);
+    MB_CUDA(cudaGetLastError());
     return MB_OK;
 }
 

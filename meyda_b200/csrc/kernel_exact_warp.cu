@@ -58,6 +58,10 @@ __device__ __forceinline__ double round_f32(double x) {
     return __hiloint2double(__double2hiint(y) | (hi & (int)0x80000000), __double2loint(y));
 }
 
+// The same store as a conversion pair (two instructions on the quarter-rate XU pipe instead of seven on the FP64 and
+// integer pipes): used for half of the values so that all three pipes carry the roundings.
+__device__ __forceinline__ double round_f32_cvt(double x) { return (double)__double2float_rn(x); }
+
 // fft.js:151-161 on float64 registers holding float32 values; results NOT yet rounded.
 __device__ __forceinline__ void bfly(double &lr, double &li, double &xr, double &xi, const double fr, const double fi) {
     const double SQRT1_2 = 0.70710678118654752440;
@@ -101,8 +105,8 @@ __device__ __forceinline__ void pass_smem(float2 *X, const double2 *tw, int lane
                 const double2 f = tw[(h << LOG2W) - 16 + ((t & (h - 1)) << LOG2W) + j];  // entry (hW - 1) + index, table starts at 15
                 bfly(vr[t], vi[t], vr[t + h], vi[t + h], f.x, f.y);
                 if (q + 1 < Q) {
-                    vr[t] = round_f32(vr[t]); vi[t] = round_f32(vi[t]);
-                    vr[t + h] = round_f32(vr[t + h]); vi[t + h] = round_f32(vi[t + h]);
+                    vr[t] = round_f32(vr[t]); vi[t] = round_f32_cvt(vi[t]);
+                    vr[t + h] = round_f32_cvt(vr[t + h]); vi[t + h] = round_f32(vi[t + h]);
                 }
             }
         }
@@ -146,9 +150,15 @@ mb_exact_warp_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant_
 
     // (sel_list: only the frames a float32-FFT kernel flagged, mb_adaptive.cuh)
     const int64_t n_work = T.sel_list ? (int64_t)*T.sel_count : T.total_frames;
-    const int64_t w0 = (int64_t)blockIdx.x * kWarpsPerCta + warp, wstride = (int64_t)gridDim.x * kWarpsPerCta;
-    for (int64_t it = w0; it < n_work; it += wstride) {
-        const int64_t g = T.sel_list ? (int64_t)T.sel_list[it] : it;
+    // The warps of a CTA take one frame each per round and move through the phases of a round TOGETHER (a block
+    // barrier between phases, nothing shared but the instruction stream): a phase's unrolled register code is
+    // 10-25 KB, and with every warp in a phase of its own the SM's instruction cache thrashed (54 % of the stall
+    // samples were instruction fetches, issue slots 19 % busy).
+    const int64_t r0 = (int64_t)blockIdx.x * kWarpsPerCta, rstride = (int64_t)gridDim.x * kWarpsPerCta;
+    for (int64_t round = r0; round < n_work; round += rstride) {
+        const int64_t it = round + warp;
+        const bool active = it < n_work;
+        const int64_t g = !active ? 0 : T.sel_list ? (int64_t)T.sel_list[it] : it;
         const int64_t clip = mb_find_clip_warp(T, g);
         const MbFrameSrc src = mb_frame_src(T, samples, T.clip_off[clip] + (g - T.frame_start[clip]) * (int64_t)P.hop);
         MbFrameSums S;
@@ -156,24 +166,47 @@ mb_exact_warp_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant_
         S.zcr = 0;
         S.rolloff_bin = M;
 
-        if (want_time) {  // energy.js, zcr.js, buffer over the raw frame
+        if (want_time && active) {  // energy.js, zcr.js, buffer over the raw frame
             double e = 0;
             int z = 0;
+            const bool vec = src.format < 0 && ((reinterpret_cast<uintptr_t>(src.base) | reinterpret_cast<uintptr_t>(O.buffer)) & 15) == 0;
+            if (vec) {  // float32 frames on the 16-byte grid: four samples per lane and load
+                const float4 *s4 = reinterpret_cast<const float4 *>(src.base);
 #pragma unroll 4
-            for (int i = lane; i < N; i += 32) {
-                const float x0 = src[i];
-                e += (double)x0 * (double)x0;
-                if (i + 1 < N) {
-                    const float x1 = src[i + 1];
-                    z += ((x0 >= 0.f) != (x1 >= 0.f)) && (x0 == x0) && (x1 == x1);
+                for (int i = lane; i < N / 4; i += 32) {
+                    const float4 x = __ldg(s4 + i);
+                    float nx = __shfl_down_sync(0xffffffffu, x.x, 1);  // the sample after this lane's four
+                    if (lane == 31) nx = (i + 1 < N / 4) ? __ldg(reinterpret_cast<const float *>(src.base) + 4 * i + 4) : x.w;
+                    e += ((double)x.x * (double)x.x + (double)x.y * (double)x.y) + ((double)x.z * (double)x.z + (double)x.w * (double)x.w);
+                    const bool p0 = x.x >= 0.f, p1 = x.y >= 0.f, p2 = x.z >= 0.f, p3 = x.w >= 0.f, p4 = nx >= 0.f;
+                    const bool n0 = x.x == x.x, n1 = x.y == x.y, n2 = x.z == x.z, n3 = x.w == x.w, n4 = nx == nx;
+                    z += ((p0 != p1) && n0 && n1) + ((p1 != p2) && n1 && n2) + ((p2 != p3) && n2 && n3) +
+                         ((p3 != p4) && n3 && n4 && (4 * i + 4 < N));  // (the frame's last sample has no successor)
+                    if (mb_has(mask, MB_FEAT_BUFFER)) __stcs(reinterpret_cast<float4 *>(O.buffer + g * N) + i, x);
                 }
-                if (mb_has(mask, MB_FEAT_BUFFER)) O.buffer[g * N + i] = x0;
+            } else {
+#pragma unroll 4
+                for (int i = lane; i < N; i += 32) {
+                    const float x0 = src[i];
+                    e += (double)x0 * (double)x0;
+                    if (i + 1 < N) {
+                        const float x1 = src[i + 1];
+                        z += ((x0 >= 0.f) != (x1 >= 0.f)) && (x0 == x0) && (x1 == x1);
+                    }
+                    if (mb_has(mask, MB_FEAT_BUFFER)) O.buffer[g * N + i] = x0;
+                }
             }
             S.energy = mb_warp_sum(e);
             S.zcr = mb_warp_sum(z);
         }
         if (want_spectrum) {
-            __syncwarp();  // the previous frame's epilogue is done with the buffer
+            // (the next group's samples are fetched while this one is transformed: with the warps of the CTA in step, a
+            // load every lane waits for is a stall of the whole SM)
+            float xin[16];
+#pragma unroll
+            for (int j = 0; j < 16; j++) xin[j] = active ? src[lane + (N / 16) * rev_bits(j, 4)] : 0.f;  // (in flight across the barrier)
+            __syncthreads();  // (also: the previous round's epilogue is done with the buffer)
+            if (active) {
             // ---- pass 1: widths 1, 2, 4, 8 on BitReverseComplexArray(windowed frame): group g16 holds positions
             // 16 g16 + j = samples rev(g16) + (N/16) rev4(j); this lane takes r = rev(g16) = lane + 32 i
 #pragma unroll 1
@@ -182,8 +215,12 @@ mb_exact_warp_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant_
 #pragma unroll
                 for (int j = 0; j < 16; j++) {
                     const int idx = r + (N / 16) * rev_bits(j, 4);
-                    vr[j] = (double)__fmul_rn(src[idx], __ldg(P.window + idx));  // computeWindow src/meyda.js:158-168
+                    vr[j] = (double)__fmul_rn(xin[j], __ldg(P.window + idx));  // computeWindow src/meyda.js:158-168
                     vi[j] = 0.0;
+                }
+                if (r + 32 < N / 16) {
+#pragma unroll
+                    for (int j = 0; j < 16; j++) xin[j] = src[r + 32 + (N / 16) * rev_bits(j, 4)];
                 }
 #pragma unroll
                 for (int q = 0; q < 4; q++) {
@@ -194,8 +231,8 @@ mb_exact_warp_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant_
                         const double2 f = TW.f[(h - 1) + (t & (h - 1))];
                         bfly(vr[t], vi[t], vr[t + h], vi[t + h], f.x, f.y);
                         if (q < 3) {
-                            vr[t] = round_f32(vr[t]); vi[t] = round_f32(vi[t]);
-                            vr[t + h] = round_f32(vr[t + h]); vi[t + h] = round_f32(vi[t + h]);
+                            vr[t] = round_f32(vr[t]); vi[t] = round_f32_cvt(vi[t]);
+                            vr[t + h] = round_f32_cvt(vr[t + h]); vi[t + h] = round_f32(vi[t + h]);
                         }
                     }
                 }
@@ -204,37 +241,47 @@ mb_exact_warp_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant_
                 for (int j = 0; j < 16; j++)
                     X[swz<LOG2N>(16 * g16 + j)] = make_float2(__double2float_rn(vr[j]), __double2float_rn(vi[j]));
             }
-            __syncwarp();
+            }
+            __syncthreads();
             // ---- pass 2: widths 16 .. 16 * 2^(Q1 - 1)
-            pass_smem<LOG2N, 4, Q1>(X, tw, lane);
-            __syncwarp();
+            if (active) pass_smem<LOG2N, 4, Q1>(X, tw, lane);
+            __syncthreads();
             // ---- pass 3: the last Q2 stages
-            pass_smem<LOG2N, LOG2N - Q2, Q2>(X, tw, lane);
-            __syncwarp();
+            if (active) pass_smem<LOG2N, LOG2N - Q2, Q2>(X, tw, lane);
+            __syncthreads();
+            gw::MomentAcc acc;
+            if (active) {
             // ---- spectra out; amplitudes (computeAmplitude src/meyda.js:104-114: bins below N/2) into the upper half of
             // the buffer (the bins above N/2 are only ever needed for complexSpectrum, stored right here)
-            gw::MomentAcc acc;
-#pragma unroll 2
-            for (int k = lane; k < N; k += 32) {
+            if (want_cs) {
+#pragma unroll 4
+                for (int k = M + lane; k < N; k += 32) {
+                    const float2 z = X[swz<LOG2N>(k)];
+                    __stcs(O.complex_real + g * N + k, z.x);
+                    __stcs(O.complex_imag + g * N + k, z.y);
+                }
+            }
+            __syncwarp();  // the upper half is out: its floats become the amplitude array
+#pragma unroll 4
+            for (int k = lane; k < M; k += 32) {
                 const float2 z = X[swz<LOG2N>(k)];
                 if (want_cs) {
                     __stcs(O.complex_real + g * N + k, z.x);
                     __stcs(O.complex_imag + g * N + k, z.y);
                 }
-                if (k < M) {
-                    const double re = (double)z.x, im = (double)z.y;
-                    const float a = (float)sqrt(__dadd_rn(__dmul_rn(re, re), __dmul_rn(im, im)));
-                    amp[k] = a;
-                    if (mb_has(mask, MB_FEAT_AMPLITUDE_SPECTRUM)) __stcs(O.amplitude_spectrum + g * M + k, a);
-                    if (mb_has(mask, MB_FEAT_POWER_SPECTRUM)) __stcs(O.power_spectrum + g * M + k, __fmul_rn(a, a));
-                    if (want_moments) acc.add(a, k, want_log);
-                }
+                const double re = (double)z.x, im = (double)z.y;
+                const float a = (float)sqrt(__dadd_rn(__dmul_rn(re, re), __dmul_rn(im, im)));
+                amp[k] = a;
+                if (mb_has(mask, MB_FEAT_AMPLITUDE_SPECTRUM)) __stcs(O.amplitude_spectrum + g * M + k, a);
+                if (mb_has(mask, MB_FEAT_POWER_SPECTRUM)) __stcs(O.power_spectrum + g * M + k, __fmul_rn(a, a));
+                if (want_moments) acc.add(a, k, want_log);
             }
             __syncwarp();
-            gw::frame_epilogue<true>(P, O, g, S, acc, amp, sc);
+            }
+            __syncthreads();
+            if (active) gw::frame_epilogue<true>(P, O, g, S, acc, amp, sc);
         }
-        if (lane == 0) mb_store_scalars(P, O, g, S);
-        __syncwarp();
+        if (active && lane == 0) mb_store_scalars(P, O, g, S);
     }
 }
 

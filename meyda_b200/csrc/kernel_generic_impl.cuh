@@ -167,7 +167,11 @@ struct MomentAcc {
         t *= kd; s2 += t;
         t *= kd; s3 += t;
         t *= kd; s4 += t;
+#ifdef MB_GENERIC_WARP_LOCAL
+        if (want_log) lg += (double)log2_fast(av);  // (2^-22 per term, random: 1e-9 of the sum; flatness is compared at 5e-6)
+#else
         if (want_log) lg += (double)(FAST ? log2_fast(av) : log2f(av));
+#endif
     }
 };
 
@@ -320,12 +324,27 @@ __device__ __forceinline__ void frame_epilogue(const MbDevPlan &P, const mb_outp
                 // done once, mfcc.js:45-50); the float32 running sum keeps the reference's order (mfcc.js:56-62)
                 const double *__restrict__ wgt = P.mel_w_exact + P.mel_w_off[f] - e0;
                 (void)e1;
-                float s = 0.f;
-                for (int k = e0; k < e2 && k < M; k++) {
+                // s <- float32(s + w p), kept as a float64 that sits on the float32 grid.  The running sum never
+                // shrinks, so it stays in the binade of the previous step or moves up: (u + M) - M with the previous
+                // step's M = 1.5 * 2^(e + 29) is the float32 rounding of u unless u left that binade (then, or for a
+                // NaN, the general sequence below picks the new one).  The loop-carried chain is three DADDs instead
+                // of an add and two conversions on the quarter-rate pipe.
+                double s = 0.0, Mv = 0.0;
+                int eb = -1;  // exponent field M was made for (-1: none yet)
+                const int kend = min(e2, M);
+                for (int k = e0; k < kend; k++) {
                     const float a = amp[k];
-                    s = (float)__dadd_rn((double)s, __dmul_rn(__ldg(wgt + k), (double)__fmul_rn(a, a)));
+                    const double u = __dadd_rn(s, __dmul_rn(__ldg(wgt + k), (double)__fmul_rn(a, a)));
+                    double y = __dsub_rn(__dadd_rn(u, Mv), Mv);  // speculative: issued before the binade check resolves
+                    const int eu = max(__double2hiint(u) & 0x7FF00000, 0x38100000);
+                    if (eu != eb) {  // rare: at most once per binade the sum climbs through
+                        eb = eu;
+                        Mv = __hiloint2double(eu + 0x01D80000, 0);
+                        y = __dsub_rn(__dadd_rn(u, Mv), Mv);
+                    }
+                    s = y;  // (u >= +0 or NaN: no zero sign to restore)
                 }
-                mel_log[f] = (float)log((double)s);
+                mel_log[f] = (float)log((double)(float)s);
             }
         } else if constexpr (kWarps <= kLaneBandWarps) {  // small CTAs: one lane per filter (on the second warp where there is one)
             if (warp == (kWarps > 1 ? 1 : 0))

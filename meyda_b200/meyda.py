@@ -96,6 +96,19 @@ def _normalize_clips(clips):
     return data, offsets, lengths
 
 
+def pinned_empty(shape, dtype) -> np.ndarray:
+    """A numpy array over page-locked host memory (mb_host_alloc); freed with mb_host_free when collected."""
+    import weakref
+    L = _capi.lib()
+    nbytes = max(1, int(np.prod(shape)) * np.dtype(dtype).itemsize)
+    ptr = C.c_void_p()
+    _capi.check(L.mb_host_alloc(C.byref(ptr), nbytes))
+    buf = (C.c_char * nbytes).from_address(ptr.value)
+    arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+    weakref.finalize(buf, L.mb_host_free, C.c_void_p(ptr.value))  # (arr keeps buf alive through its base chain)
+    return arr
+
+
 class Plan:
     """One (device, bufferSize, hop, sampleRate, window, feature set): the
     tables `new Meyda(...)` precomputes, resident on the GPU."""
@@ -194,8 +207,16 @@ class Plan:
                                  np.int32 if field == "zcr" else np.float32)
         return shapes
 
-    def alloc_host_outputs(self, total_frames: int) -> dict:
-        return {k: np.zeros(s, dtype=d) for k, (s, d) in self.output_shapes(total_frames).items()}
+    def alloc_host_outputs(self, total_frames: int, pinned: bool | None = None) -> dict:
+        """Output arrays for `total_frames` frames.  pinned (the default for results of a megabyte and more): page-locked
+        memory from mb_host_alloc, which lets the device copy straight into them asynchronously (pageable arrays make
+        every copy a staged, synchronous one); the memory is returned by mb_host_free when the array is collected."""
+        shapes = self.output_shapes(total_frames)
+        if pinned is None:
+            pinned = sum(int(np.prod(s)) * 4 for s, _ in shapes.values()) >= (1 << 20)
+        if not pinned:
+            return {k: np.zeros(s, dtype=d) for k, (s, d) in shapes.items()}
+        return {k: pinned_empty(s, d) for k, (s, d) in shapes.items()}
 
     @staticmethod
     def pack_outputs(ptrs: dict) -> Outputs:

@@ -14,7 +14,8 @@ pytestmark = pytest.mark.gpu
 SR = 44100.0
 EXACT = _capi.MB_FLAG_EXACT_FFT
 FLAG_VARIANTS = [pytest.param(0, id="fast"), pytest.param(_capi.MB_FLAG_GENERIC_KERNEL, id="generic"),
-                 pytest.param(EXACT, id="exact"),
+                 pytest.param(EXACT, id="exact"),  # (the warp-per-frame exact kernel at 512 / 1024 / 2048)
+                 pytest.param(EXACT | _capi.MB_FLAG_GENERIC_KERNEL, id="exact-generic"),  # (block per frame)
                  pytest.param(EXACT | _capi.MB_FLAG_CLUSTER_FFT, id="exact-cluster")]
 
 

@@ -61,6 +61,15 @@ if "c5" in which:
 if "exact" in which:
     run("full set exact-FFT", 2048, 512, 200, 441000, mb.FEATURES, flags=_capi.MB_FLAG_EXACT_FFT)
     run("config3 exact-FFT", 2048, 512, 200, 441000, C3, flags=_capi.MB_FLAG_EXACT_FFT)
+if "exactone" in which:  # (profiling target)
+    run("full set exact-FFT (warp per frame) N=2048", 2048, 512, 400, 441000, mb.FEATURES, flags=_capi.MB_FLAG_EXACT_FFT, steps=1)
+if "exactcmp" in which:  # the warp-per-frame exact kernel against the block-per-frame one
+    EX, GEN = _capi.MB_FLAG_EXACT_FFT, _capi.MB_FLAG_GENERIC_KERNEL
+    for N, hop in ((2048, 512), (1024, 1024), (512, 512)):
+        run("full set exact-FFT (warp per frame) N=%d" % N, N, hop, 400, 441000, mb.FEATURES, flags=EX)
+        run("full set exact-FFT (block per frame) N=%d" % N, N, hop, 200, 441000, mb.FEATURES, flags=EX | GEN)
+    run("config3 exact-FFT (warp per frame)", 2048, 512, 400, 441000, C3, flags=EX)
+    run("config3 exact-FFT (block per frame)", 2048, 512, 200, 441000, C3, flags=EX | GEN)
 if "small" in which:  # the reference's own cadence: back-to-back buffers (hop = bufferSize)
     for N in (256, 512, 1024):
         run("full set N=%d hop=N" % N, N, N, 800, 441000, mb.FEATURES)

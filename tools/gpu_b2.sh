@@ -1,0 +1,11 @@
+#!/bin/bash
+cd "$GRAFT_REPO_ROOT" 2>/dev/null || true
+mkdir -p gpurun_out
+python -m pytest tests -m gpu -q -x -k "exact" > gpurun_out/pytest_exact.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_exact.log
+tail -5 gpurun_out/pytest_exact.log
+python tools/diag_adaptive.py > gpurun_out/diag_adaptive.log 2>&1; grep -c OK gpurun_out/diag_adaptive.log
+python tools/bench_configs.py exactcmp > gpurun_out/bench_exactcmp.json 2>&1
+cut -c1-200 gpurun_out/bench_exactcmp.json
+python tools/bench_configs.py exactone > gpurun_out/plain.log 2>&1 && \
+ncu --set full --clock-control none --import-source on -k regex:mb_exact_warp -s 2 -c 1 -f -o gpurun_out/prof_exactw python tools/bench_configs.py exactone > gpurun_out/ncu_full.log 2>&1
+echo "ncu exit $?"; tail -2 gpurun_out/ncu_full.log
