@@ -147,6 +147,9 @@ enum {
 };
 #define MB_MAX_EXACT_BUFFER_SIZE 32768
 
+/* A plan is NOT thread-safe and runs on ONE stream at a time: its clip table, flagged-frame list and staging
+ * buffers are ordered by that stream alone.  Use one plan per thread; mb_plan_set_stream synchronizes the stream it
+ * leaves before switching.  (mb_extract_multi drives one plan per device from its own threads.) */
 typedef struct mb_plan mb_plan;     /* opaque: tables, stream, scratch of one (device, bufferSize, hop, ...) */
 typedef struct mb_stream mb_stream; /* opaque: stateful buffer-by-buffer extractor */
 

@@ -12,7 +12,16 @@
 //   const out  = await native.extractAsync(plan, samples, offsets, lengths)     // napi_async_work on the libuv pool
 //   const out  = await native.extractPcm16Async(plan, pcm, channels, channel, offsets, lengths)
 //   const info = native.wavInfo(fileBytes /*Uint8Array*/)   // {format, channels, sampleRate, bitsPerSample, dataOffset, sampleFrames}
+//   const out  = native.extractMulti([plan0, plan1, ...], samples, offsets, lengths)   // one plan per device, clip-sharded
+//   const prm  = native.getParams(plan)            // {numBarkBands, numMelFilters, numMfccCoefficients, rolloffFraction}
+//   const n    = native.refinedFrames(plan)        // frames of the last call redone with the exact FFT (adaptive plans)
+//   const st   = native.createStream(plan)         // the onaudioprocess cadence (src/meyda.js:69-91)
+//   const out  = native.streamPush(st, block /*Float32Array*/)   // features of the frames this block completes
+//   native.streamReset(st); native.destroyStream(st)
 //   native.destroyPlan(plan)
+//
+// Output arrays live in page-locked memory (mb_host_alloc, wrapped as external ArrayBuffers and released by
+// mb_host_free when collected), so the device copies straight into them, asynchronously.
 //
 // `out` maps mb_outputs field names to typed arrays laid out exactly as the C
 // ABI documents (frame-major SoA); js/meyda_b200.js turns them into the
@@ -88,6 +97,29 @@ static const FieldDesc kFields[] = {
     F(loudness_total, MB_FEAT_LOUDNESS, 0), F(perceptual_spread, MB_FEAT_PERCEPTUAL_SPREAD, 0),
     F(perceptual_sharpness, MB_FEAT_PERCEPTUAL_SHARPNESS, 0), F(mfcc, MB_FEAT_MFCC, 4)};
 
+static void host_finalize(napi_env, void *data, void *) { mb_host_free(data); }
+
+// A typed array over page-locked memory; plain (pageable) ArrayBuffer if the allocation fails.
+static napi_status make_output_array(napi_env env, bool is_int, size_t elems, void **data, napi_value *ta) {
+    napi_value ab;
+    void *pinned = NULL;
+    napi_status ns = napi_generic_failure;
+    if (elems > 0 && mb_host_alloc(&pinned, elems * 4) == MB_OK) {
+        ns = napi_create_external_arraybuffer(env, pinned, elems * 4, host_finalize, NULL, &ab);
+        if (ns != napi_ok) mb_host_free(pinned);  // (engines that forbid external buffers: fall back below)
+        else *data = pinned;
+    }
+    if (ns != napi_ok) {
+        ns = napi_create_arraybuffer(env, elems * 4, data, &ab);
+        if (ns != napi_ok) return ns;
+    }
+    return napi_create_typedarray(env, is_int ? napi_int32_array : napi_float32_array, elems, ab, 0, ta);
+}
+
+// The result object for `lay`: one typed array per requested field (pointers also written into *out) plus
+// totalFrames / numBarkBands / numMfccCoefficients.
+static napi_value make_result(napi_env env, const mb_layout &lay, int64_t frames, mb_outputs *out);
+
 // One extract call: arguments parsed and outputs allocated on the JS thread, the blocking C-ABI call either made in
 // place (extract / extractPcm16) or on the libuv pool (extractAsync / extractPcm16Async, SURVEY.md 8b "Threading").
 struct Job {
@@ -143,32 +175,36 @@ static napi_value prepare_job(napi_env env, napi_callback_info info, bool pcm16,
     mb_layout lay;
     mb_status st = mb_query_output(j->plan, (int64_t)j->n_clips, (const int64_t *)j->lens, NULL, &lay);
     if (st != MB_OK) return throw_mb(env, st);
+    napi_value result = make_result(env, lay, lay.total_frames, &j->out);
+    if (!result) return NULL;
+    if (args_array) {  // plan + every input array, kept alive while the pool thread reads them
+        NAPI_OK_OR_THROW(env, napi_create_array_with_length(env, argc, args_array));
+        for (size_t i = 0; i < argc; i++) NAPI_OK_OR_THROW(env, napi_set_element(env, *args_array, (uint32_t)i, argv[i]));
+    }
+    return result;
+}
+
+static napi_value make_result(napi_env env, const mb_layout &lay, int64_t frames_n, mb_outputs *out) {
     napi_value result;
     NAPI_OK_OR_THROW(env, napi_create_object(env, &result));
+    memset(out, 0, sizeof(*out));
     for (const FieldDesc &f : kFields) {
         if (!((lay.feature_mask >> f.feature) & 1u)) continue;
         const size_t per = f.kind == 0 ? 1 : f.kind == 1 ? (size_t)lay.buffer_size : f.kind == 2 ? (size_t)lay.spectrum_size
                                          : f.kind == 3 ? (size_t)lay.num_bark_bands : (size_t)lay.num_mfcc;
-        const size_t elems = per * (size_t)lay.total_frames;
-        napi_value ab, ta;
+        napi_value ta;
         void *data = NULL;
-        NAPI_OK_OR_THROW(env, napi_create_arraybuffer(env, elems * 4, &data, &ab));
-        NAPI_OK_OR_THROW(env, napi_create_typedarray(env, strcmp(f.name, "zcr") == 0 ? napi_int32_array : napi_float32_array,
-                                                     elems, ab, 0, &ta));
-        *(void **)((char *)&j->out + f.offset) = data;
+        NAPI_OK_OR_THROW(env, make_output_array(env, strcmp(f.name, "zcr") == 0, per * (size_t)frames_n, &data, &ta));
+        *(void **)((char *)out + f.offset) = data;
         NAPI_OK_OR_THROW(env, napi_set_named_property(env, result, f.name, ta));
     }
     napi_value frames, nbands, ncoefs;
-    NAPI_OK_OR_THROW(env, napi_create_int64(env, lay.total_frames, &frames));
+    NAPI_OK_OR_THROW(env, napi_create_int64(env, frames_n, &frames));
     NAPI_OK_OR_THROW(env, napi_set_named_property(env, result, "totalFrames", frames));
     NAPI_OK_OR_THROW(env, napi_create_int32(env, lay.num_bark_bands, &nbands));  // row widths of loudness_specific and mfcc
     NAPI_OK_OR_THROW(env, napi_set_named_property(env, result, "numBarkBands", nbands));
     NAPI_OK_OR_THROW(env, napi_create_int32(env, lay.num_mfcc, &ncoefs));
     NAPI_OK_OR_THROW(env, napi_set_named_property(env, result, "numMfccCoefficients", ncoefs));
-    if (args_array) {  // plan + every input array, kept alive while the pool thread reads them
-        NAPI_OK_OR_THROW(env, napi_create_array_with_length(env, argc, args_array));
-        for (size_t i = 0; i < argc; i++) NAPI_OK_OR_THROW(env, napi_set_element(env, *args_array, (uint32_t)i, argv[i]));
-    }
     return result;
 }
 
@@ -264,6 +300,139 @@ static napi_value WavInfo(napi_env env, napi_callback_info info) {
     return result;
 }
 
+// extractMulti([plan, ...], Float32Array, offsets, lengths): mb_extract_multi -- contiguous clip ranges balanced on frame
+// count, one plan per device, results exactly where a single-device call would put them.
+static napi_value ExtractMulti(napi_env env, napi_callback_info info) {
+    size_t argc = 4;
+    napi_value argv[4];
+    NAPI_OK_OR_THROW(env, napi_get_cb_info(env, info, &argc, argv, NULL, NULL));
+    uint32_t n_plans = 0;
+    NAPI_OK_OR_THROW(env, napi_get_array_length(env, argv[0], &n_plans));
+    if (n_plans == 0 || n_plans > 64) { napi_throw_type_error(env, NULL, "plans must be an array of 1..64 plans"); return NULL; }
+    mb_plan *plans[64];
+    for (uint32_t i = 0; i < n_plans; i++) {
+        napi_value e;
+        NAPI_OK_OR_THROW(env, napi_get_element(env, argv[0], i, &e));
+        NAPI_OK_OR_THROW(env, napi_get_value_external(env, e, (void **)&plans[i]));
+    }
+    napi_typedarray_type tt;
+    size_t n_samples = 0, n_clips = 0, n_len = 0;
+    void *samples = NULL, *offs = NULL, *lens = NULL;
+    NAPI_OK_OR_THROW(env, napi_get_typedarray_info(env, argv[1], &tt, &n_samples, &samples, NULL, NULL));
+    if (tt != napi_float32_array) { napi_throw_type_error(env, NULL, "samples must be a Float32Array"); return NULL; }
+    NAPI_OK_OR_THROW(env, napi_get_typedarray_info(env, argv[2], &tt, &n_clips, &offs, NULL, NULL));
+    if (tt != napi_bigint64_array) { napi_throw_type_error(env, NULL, "offsets must be a BigInt64Array"); return NULL; }
+    NAPI_OK_OR_THROW(env, napi_get_typedarray_info(env, argv[3], &tt, &n_len, &lens, NULL, NULL));
+    if (tt != napi_bigint64_array || n_len != n_clips) { napi_throw_type_error(env, NULL, "lengths must match offsets"); return NULL; }
+    mb_layout lay;
+    mb_status st = mb_query_output(plans[0], (int64_t)n_clips, (const int64_t *)lens, NULL, &lay);
+    if (st != MB_OK) return throw_mb(env, st);
+    mb_outputs out;
+    napi_value result = make_result(env, lay, lay.total_frames, &out);
+    if (!result) return NULL;
+    st = mb_extract_multi(plans, (int)n_plans, (const float *)samples, (int64_t)n_samples, (const int64_t *)offs,
+                          (const int64_t *)lens, (int64_t)n_clips, &out);
+    if (st != MB_OK) return throw_mb(env, st);
+    return result;
+}
+
+// getParams(plan): the constants the plan runs with (mb_plan_get_params)
+static napi_value GetParams(napi_env env, napi_callback_info info) {
+    size_t argc = 1;
+    napi_value argv[1], result, v;
+    NAPI_OK_OR_THROW(env, napi_get_cb_info(env, info, &argc, argv, NULL, NULL));
+    mb_plan *plan = NULL;
+    NAPI_OK_OR_THROW(env, napi_get_value_external(env, argv[0], (void **)&plan));
+    mb_params prm;
+    const mb_status st = mb_plan_get_params(plan, &prm);
+    if (st != MB_OK) return throw_mb(env, st);
+    NAPI_OK_OR_THROW(env, napi_create_object(env, &result));
+    const struct { const char *name; int32_t value; } ints[] = {
+        {"numBarkBands", prm.num_bark_bands}, {"numMelFilters", prm.num_mel_filters}, {"numMfccCoefficients", prm.num_mfcc}};
+    for (const auto &f : ints) {
+        NAPI_OK_OR_THROW(env, napi_create_int32(env, f.value, &v));
+        NAPI_OK_OR_THROW(env, napi_set_named_property(env, result, f.name, v));
+    }
+    NAPI_OK_OR_THROW(env, napi_create_double(env, prm.rolloff_fraction, &v));
+    NAPI_OK_OR_THROW(env, napi_set_named_property(env, result, "rolloffFraction", v));
+    return result;
+}
+
+// refinedFrames(plan): how many frames of the last call the adaptive plan redid with the reference's own FFT arithmetic
+static napi_value RefinedFrames(napi_env env, napi_callback_info info) {
+    size_t argc = 1;
+    napi_value argv[1], v;
+    NAPI_OK_OR_THROW(env, napi_get_cb_info(env, info, &argc, argv, NULL, NULL));
+    mb_plan *plan = NULL;
+    NAPI_OK_OR_THROW(env, napi_get_value_external(env, argv[0], (void **)&plan));
+    int64_t n = 0;
+    const mb_status st = mb_plan_refined_frames(plan, &n);
+    if (st != MB_OK) return throw_mb(env, st);
+    NAPI_OK_OR_THROW(env, napi_create_int64(env, n, &v));
+    return v;
+}
+
+// ---- streaming, the reference's actual usage model: one buffer per onaudioprocess event (src/meyda.js:69-91)
+static void stream_finalize(napi_env, void *data, void *) { mb_stream_destroy((mb_stream *)data); }
+
+// createStream(plan) -> stream.  The plan must outlive the stream (the facade keeps both).
+static napi_value CreateStream(napi_env env, napi_callback_info info) {
+    size_t argc = 1;
+    napi_value argv[1], ext;
+    NAPI_OK_OR_THROW(env, napi_get_cb_info(env, info, &argc, argv, NULL, NULL));
+    mb_plan *plan = NULL;
+    NAPI_OK_OR_THROW(env, napi_get_value_external(env, argv[0], (void **)&plan));
+    mb_stream *st = NULL;
+    const mb_status s = mb_stream_create(&st, plan);
+    if (s != MB_OK) return throw_mb(env, s);
+    NAPI_OK_OR_THROW(env, napi_create_external(env, st, stream_finalize, NULL, &ext));
+    return ext;
+}
+
+// streamPush(stream, plan, Float32Array block) -> the result object for the frames this block completes (0 or more)
+static napi_value StreamPush(napi_env env, napi_callback_info info) {
+    size_t argc = 3;
+    napi_value argv[3];
+    NAPI_OK_OR_THROW(env, napi_get_cb_info(env, info, &argc, argv, NULL, NULL));
+    mb_stream *st = NULL;
+    mb_plan *plan = NULL;
+    NAPI_OK_OR_THROW(env, napi_get_value_external(env, argv[0], (void **)&st));
+    NAPI_OK_OR_THROW(env, napi_get_value_external(env, argv[1], (void **)&plan));
+    napi_typedarray_type tt;
+    size_t n_new = 0;
+    void *block = NULL;
+    NAPI_OK_OR_THROW(env, napi_get_typedarray_info(env, argv[2], &tt, &n_new, &block, NULL, NULL));
+    if (tt != napi_float32_array) { napi_throw_type_error(env, NULL, "block must be a Float32Array"); return NULL; }
+    const int64_t nf = mb_stream_frames_after(st, (int64_t)n_new);
+    mb_layout lay;
+    const int64_t one = 0;
+    mb_status s = mb_query_output(plan, 0, &one, NULL, &lay);  // (shapes only: feature mask, row widths)
+    if (s != MB_OK) return throw_mb(env, s);
+    mb_outputs out;
+    napi_value result = make_result(env, lay, nf, &out);
+    if (!result) return NULL;
+    int64_t done = 0;
+    s = mb_stream_push(st, (const float *)block, (int64_t)n_new, &out, MB_MEM_HOST, &done);
+    if (s != MB_OK) return throw_mb(env, s);
+    return result;
+}
+
+static napi_value StreamReset(napi_env env, napi_callback_info info) {
+    size_t argc = 1;
+    napi_value argv[1];
+    NAPI_OK_OR_THROW(env, napi_get_cb_info(env, info, &argc, argv, NULL, NULL));
+    mb_stream *st = NULL;
+    NAPI_OK_OR_THROW(env, napi_get_value_external(env, argv[0], (void **)&st));
+    const mb_status s = mb_stream_reset(st);
+    if (s != MB_OK) return throw_mb(env, s);
+    return NULL;
+}
+
+static napi_value DestroyStream(napi_env env, napi_callback_info info) {
+    (void)env; (void)info;  // externals are released by their finalizers (stream_finalize)
+    return NULL;
+}
+
 static napi_value DestroyPlan(napi_env env, napi_callback_info info) {
     size_t argc = 1;
     napi_value argv[1];
@@ -282,6 +451,13 @@ static napi_value Init(napi_env env, napi_value exports) {
         {"extractPcm16Async", NULL, ExtractPcm16Async, NULL, NULL, NULL, napi_default, NULL},
         {"wavInfo", NULL, WavInfo, NULL, NULL, NULL, napi_default, NULL},
         {"destroyPlan", NULL, DestroyPlan, NULL, NULL, NULL, napi_default, NULL},
+        {"extractMulti", NULL, ExtractMulti, NULL, NULL, NULL, napi_default, NULL},
+        {"getParams", NULL, GetParams, NULL, NULL, NULL, napi_default, NULL},
+        {"refinedFrames", NULL, RefinedFrames, NULL, NULL, NULL, napi_default, NULL},
+        {"createStream", NULL, CreateStream, NULL, NULL, NULL, napi_default, NULL},
+        {"streamPush", NULL, StreamPush, NULL, NULL, NULL, napi_default, NULL},
+        {"streamReset", NULL, StreamReset, NULL, NULL, NULL, napi_default, NULL},
+        {"destroyStream", NULL, DestroyStream, NULL, NULL, NULL, napi_default, NULL},
     };
     napi_define_properties(env, exports, sizeof(props) / sizeof(props[0]), props);
     return exports;

@@ -1038,9 +1038,14 @@ static mb_status extract_host_impl(mb_plan *p, const void *samples, const int64_
             if (f_in_clip >= nf) { c++; f_in_clip = 0; continue; }
             const int64_t take = std::min(nf - f_in_clip, chunk_frames - frames);
             const int64_t off = clip_offset[c] + f_in_clip * hop;
+            // The chunk's samples are staged as ONE contiguous span of the host array.  Clips that lie far apart
+            // (a shuffled or repeated clip list, many short clips with hop << bufferSize) would stretch that span
+            // towards the whole array: close the chunk instead when the span outgrows twice the input budget.
+            const int64_t nlo = std::min(lo, off), nhi = std::max(hi, off + (take - 1) * hop + N);
+            if (!v.empty() && (nhi - nlo) > 2 * (chunk_frames * (int64_t)hop + N)) break;
             v.push_back({off, take});
-            lo = std::min(lo, off);
-            hi = std::max(hi, off + (take - 1) * hop + N);
+            lo = nlo;
+            hi = nhi;
             frames += take;
             f_in_clip += take;
         }

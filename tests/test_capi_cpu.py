@@ -107,5 +107,17 @@ def test_napi_addon_source_type_checks_against_the_c_abi():
                         os.path.join(ROOT, "js", "addon.cc")], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     src = open(os.path.join(ROOT, "js", "addon.cc")).read()
-    for name in ("mb_plan_create_ex", "mb_extract", "mb_extract_pcm16", "mb_query_output", "mb_wav_parse", "napi_queue_async_work"):
+    for name in ("mb_plan_create_ex", "mb_extract", "mb_extract_pcm16", "mb_query_output", "mb_wav_parse", "napi_queue_async_work",
+                 "mb_stream_create", "mb_stream_push", "mb_stream_reset", "mb_stream_frames_after", "mb_stream_destroy",
+                 "mb_extract_multi", "mb_plan_get_params", "mb_plan_refined_frames", "mb_host_alloc", "mb_host_free",
+                 "napi_create_external_arraybuffer"):
         assert name in src
+    # every native entry the JavaScript facade calls is one the addon registers
+    import re
+    facade = open(os.path.join(ROOT, "js", "meyda_b200.js")).read()
+    used = set(re.findall(r"native\.(\w+)", facade))
+    registered = set(re.findall(r'\{"(\w+)", NULL, \w+, NULL, NULL, NULL, napi_default, NULL\}', src))
+    assert used and used <= registered, used - registered
+    # and the facade carries the reference's class surface (src/meyda.js:229-261)
+    for name in ("class Meyda", "setSource (", "start (", "stop (", "get (", "windowingFunction", "featureInfo"):
+        assert name in facade, name

@@ -55,6 +55,11 @@ napi_status napi_get_typedarray_info(napi_env env, napi_value typedarray, napi_t
                                      napi_value *arraybuffer, size_t *byte_offset);
 napi_status napi_create_object(napi_env env, napi_value *result);
 napi_status napi_create_arraybuffer(napi_env env, size_t byte_length, void **data, napi_value *result);
+napi_status napi_create_external_arraybuffer(napi_env env, void *external_data, size_t byte_length, napi_finalize finalize_cb,
+                                             void *finalize_hint, napi_value *result);
+napi_status napi_get_array_length(napi_env env, napi_value value, uint32_t *result);
+napi_status napi_get_element(napi_env env, napi_value object, uint32_t index, napi_value *result);
+napi_status napi_create_double(napi_env env, double value, napi_value *result);
 napi_status napi_create_typedarray(napi_env env, napi_typedarray_type type, size_t length, napi_value arraybuffer, size_t byte_offset,
                                    napi_value *result);
 napi_status napi_create_int32(napi_env env, int32_t value, napi_value *result);
