@@ -64,17 +64,16 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region."""
+    """nvidia-smi clocks / throttle reasons, sampled for the whole run (one nvidia-smi process: it needs a moment to
+    start, and the short configurations last under a second); window(t0, t1) summarises the samples of one region."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index: int):
         self.gpu = gpu_index
-        self.rows = []
+        self.rows = []  # (arrival time, fields)
         self.proc = None
-
-    def start(self):
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
@@ -86,19 +85,24 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
-    def stop(self):
+    def close(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+
+    def window(self, t0: float, t1: float):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        self.thread.join(timeout=2)
+        time.sleep(0.25)  # (let the samples of the region's tail arrive)
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        for t, r in list(self.rows):
+            if t < t0 or t > t1 + 0.15:
+                continue
             try:
                 sm.append(float(r[1]))
                 mx.append(float(r[2]))
@@ -293,8 +297,7 @@ def run_resident(torch, dist, mb, dev, world, n, hop, feats, clips_rank, clip_le
             dist.barrier()
         torch.cuda.synchronize()
 
-    if sampler:  # (started ahead of the warm-up: nvidia-smi needs a moment, and the short configurations last under a second)
-        sampler.start()
+    t_load0 = time.time()  # (the clocks window covers warm-up and timed steps: both run the same kernel under load)
     for _ in range(warmup):
         step()
     barrier()
@@ -307,7 +310,7 @@ def run_resident(torch, dist, mb, dev, world, n, hop, feats, clips_rank, clip_le
     e1.record(stream)
     barrier()
     ms = e0.elapsed_time(e1)
-    clocks = sampler.stop() if sampler else None
+    clocks = sampler.window(t_load0, time.time()) if sampler else None
     res = {"plan": plan, "x": x, "ms": ms, "launches": plan.launch_count - l0, "main_launches": len(tabs) * steps,
            "frames_rank": clips_rank * fpc, "clips_rank": clips_rank, "wave": wave, "fpc": fpc, "reduced": reduced,
            "refined_last_wave": plan.refined_frames, "clocks": clocks, "kernel": plan.kernel_name}
@@ -417,8 +420,9 @@ def main():
     flags = (_capi.MB_FLAG_GENERIC_KERNEL if args.generic else 0) | (_capi.MB_FLAG_NO_REFINE if args.no_refine else 0)
 
     # ---- headline: BASELINE configs[3]
+    sampler = ClockSampler(local_rank) if rank == 0 else None
     r = run_resident(torch, dist, mb, dev, world, N, HOP, feats, c1 - c0, CLIP_LEN, 0x4D455944 + rank, args.steps,
-                     args.warmup, flags=flags, sampler=ClockSampler(local_rank) if rank == 0 else None)
+                     args.warmup, flags=flags, sampler=sampler)
     plan, x, fpc = r["plan"], r["x"], r["fpc"]
     ms_max = reduce_max(torch, dist, dev, world, r["ms"])
     launches_all = int(reduce_sum(torch, dist, dev, world, r["launches"]))
@@ -484,10 +488,12 @@ def main():
             return reduce_max(torch, dist, dev, world, (time.perf_counter() - t0) / reps)
 
         dt = timed(lambda: plan.extract_host(hx, off, ln, out=ho), args.steps)
-        d2h = int(sum(v.nbytes for k, v in ho.items() if k != "buffer"))  # `buffer` rows are filled on the host
+        host_made = {"buffer"} | ({"power_spectrum"} if "amplitude_spectrum" in ho else set())  # rows the host fills itself
+        d2h = int(sum(v.nbytes for k, v in ho.items() if k not in host_made))
         e2e = {"value": nf * world / dt, "unit": UNIT, "h2d_bytes_per_step": int(hx.nbytes), "d2h_bytes_per_step": d2h,
-               "batch": "%d clips x 30 s per rank per step, mb_extract(MB_MEM_HOST) into mb_host_alloc (pinned) arrays; the "
-                        "`buffer` rows are the caller's own samples and are filled on the host, not copied back" % e2e_clips}
+               "batch": "%d clips x 30 s per rank per step, mb_extract(MB_MEM_HOST) into mb_host_alloc (pinned) arrays; the `buffer` "
+                        "rows (the caller's own samples) and the powerSpectrum rows (amplitude squared) are produced on the host "
+                        "while the device works and are not copied back" % e2e_clips}
         # the host link's own ceiling for these byte counts, every rank at once
         if world > 1:
             dist.barrier()
@@ -552,9 +558,8 @@ def main():
                 ("BASELINE configs[4]: bufferSize=32768 hop=8192, amplitudeSpectrum + rolloff/flatness/slope over a 1,024-channel x 60 s synthetic array",
                  32768, 8192, C5, max(world, 1024 * args.clips // CLIPS_TOTAL), 2646000)):
             a0, a1 = shard_range(total, world, rank)
-            smp = ClockSampler(local_rank) if rank == 0 else None
             r2 = run_resident(torch, dist, mb, dev, world, n2, hop2, feats2, a1 - a0, clen, 0x4D455944 + 1000 + rank,
-                              args.steps, args.warmup, flags=flags, sampler=smp)
+                              args.steps, args.warmup, flags=flags, sampler=sampler)
             ms2 = reduce_max(torch, dist, dev, world, r2["ms"])
             fps = r2["frames_rank"] * world * args.steps / (ms2 * 1e-3)
             fl = flops_per_frame(n2, feats2)
@@ -581,6 +586,8 @@ def main():
             del r2
             torch.cuda.empty_cache()
 
+    if sampler:
+        sampler.close()
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,

@@ -9,6 +9,11 @@
 #include <string.h>
 
 #include <algorithm>
+#include <condition_variable>
+#include <deque>
+#include <functional>
+#include <mutex>
+#include <memory>
 #include <string>
 #include <thread>
 #include <vector>
@@ -174,6 +179,87 @@ struct mb_stream {
 };
 
 namespace {
+
+// Row producers of the host threads: streaming (non-temporal) stores, so that rows nobody reads again soon neither
+// cost a read-for-ownership nor push the caller's data out of the caches.
+#if defined(__SSE2__) || defined(__x86_64__)
+#include <emmintrin.h>
+inline void copy_row_stream(float *dst, const float *src, int64_t n) {
+    if (((uintptr_t)dst & 15) == 0 && (n & 3) == 0) {
+        for (int64_t i = 0; i < n; i += 4) _mm_stream_ps(dst + i, _mm_loadu_ps(src + i));
+    } else {
+        memcpy(dst, src, sizeof(float) * (size_t)n);
+    }
+}
+inline void square_rows_stream(float *dst, const float *src, int64_t n) {
+    int64_t i = 0;
+    if ((((uintptr_t)dst | (uintptr_t)src) & 15) == 0) {
+        for (; i + 4 <= n; i += 4) {
+            const __m128 a = _mm_load_ps(src + i);
+            _mm_stream_ps(dst + i, _mm_mul_ps(a, a));  // (one IEEE float32 multiply per element: what __fmul_rn does)
+        }
+    }
+    for (; i < n; i++) dst[i] = src[i] * src[i];
+}
+inline void stream_fence() { _mm_sfence(); }
+#else
+inline void copy_row_stream(float *dst, const float *src, int64_t n) { memcpy(dst, src, sizeof(float) * (size_t)n); }
+inline void square_rows_stream(float *dst, const float *src, int64_t n) {
+    for (int64_t i = 0; i < n; i++) dst[i] = src[i] * src[i];
+}
+inline void stream_fence() {}
+#endif
+
+// A few host threads that finish what needs no device: the `buffer` rows (the caller's own samples, framed) and the
+// powerSpectrum rows (amplitude squared, float32: the same single rounding the kernels apply) of a host-memory call.
+class HostWorkers {
+public:
+    explicit HostWorkers(int n) {
+        for (int i = 0; i < n; i++) threads_.emplace_back([this]() { run(); });
+    }
+    ~HostWorkers() {
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            done_ = true;
+        }
+        cv_.notify_all();
+        for (auto &t : threads_) t.join();  // (drains the queue first)
+    }
+    void post(std::function<void()> f) {
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            q_.push_back(std::move(f));
+        }
+        cv_.notify_one();
+    }
+    // Cut [g0, g1) into pieces and post f(piece begin, piece end) for each.
+    void post_range(int64_t g0, int64_t g1, int64_t grain, std::function<void(int64_t, int64_t)> f) {
+        for (int64_t a = g0; a < g1; a += grain) {
+            const int64_t b = std::min(g1, a + grain);
+            post([f, a, b]() { f(a, b); });
+        }
+    }
+
+private:
+    void run() {
+        for (;;) {
+            std::function<void()> f;
+            {
+                std::unique_lock<std::mutex> lk(m_);
+                cv_.wait(lk, [this]() { return done_ || !q_.empty(); });
+                if (q_.empty()) return;
+                f = std::move(q_.front());
+                q_.pop_front();
+            }
+            f();
+        }
+    }
+    std::vector<std::thread> threads_;
+    std::deque<std::function<void()>> q_;
+    std::mutex m_;
+    std::condition_variable cv_;
+    bool done_ = false;
+};
 
 struct DeviceGuard {
     int prev = -1;
@@ -995,32 +1081,43 @@ static mb_status extract_host_impl(mb_plan *p, const void *samples, const int64_
     // itself, on a few threads, while the device works -- bit-identical by construction, and a quarter of the full
     // set's output bytes (8 KB of 33 KB per frame at bufferSize 2048) never crosses PCIe.
     const bool host_buffer = pcm_channels == 0 && mb_has(p->mask, MB_FEAT_BUFFER);
-    const uint32_t drop_mask = host_buffer ? MB_FEATURE_BIT(MB_FEAT_BUFFER) : 0u;
-    std::vector<std::thread> fillers;
+    // powerSpectrum[k] = float32(amplitudeSpectrum[k]^2) (powerSpectrum.js:1-7; one float32 multiply in every kernel):
+    // where both are asked for, the host squares the amplitude rows as they land and the power rows stay off PCIe too.
+    const bool host_power = mb_has(p->mask, MB_FEAT_POWER_SPECTRUM) && mb_has(p->mask, MB_FEAT_AMPLITUDE_SPECTRUM);
+    const uint32_t drop_mask = (host_buffer ? MB_FEATURE_BIT(MB_FEAT_BUFFER) : 0u) | (host_power ? MB_FEATURE_BIT(MB_FEAT_POWER_SPECTRUM) : 0u);
+    int64_t total_frames_call = 0;
+    for (int64_t i = 0; i < n_clips; i++) total_frames_call += mb_num_frames(clip_len[i], N, hop);
+    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    const int n_workers = (host_buffer || host_power) ? (int)std::min<int64_t>(std::max<int64_t>(1, total_frames_call / 2048), std::min(8u, std::max(1u, hw / 2))) : 0;
+    HostWorkers workers(n_workers);  // (its destructor, on every return path, waits for the posted work: it writes into the caller's arrays)
     if (host_buffer) {
-        std::vector<int64_t> fstart(n_clips + 1, 0);
-        for (int64_t i = 0; i < n_clips; i++) fstart[i + 1] = fstart[i] + mb_num_frames(clip_len[i], N, hop);
-        const int64_t total = fstart[n_clips];
-        const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
-        const int nt = (int)std::min<int64_t>(std::max<int64_t>(1, total / 4096), std::min(4u, std::max(1u, hw / 2)));
+        auto fstart = std::make_shared<std::vector<int64_t>>(n_clips + 1, 0);
+        for (int64_t i = 0; i < n_clips; i++) (*fstart)[i + 1] = (*fstart)[i] + mb_num_frames(clip_len[i], N, hop);
         const float *src = (const float *)samples;
         float *dst = out->buffer;
-        for (int t = 0; t < nt; t++) {
-            const int64_t g0 = total * t / nt, g1 = total * (t + 1) / nt;
-            fillers.emplace_back([=, fs = fstart]() {
-                int64_t c = std::upper_bound(fs.begin(), fs.end(), g0) - fs.begin() - 1;
-                for (int64_t g = g0; g < g1; g++) {
-                    while (g >= fs[c + 1]) c++;
-                    memcpy(dst + g * N, src + clip_offset[c] + (g - fs[c]) * hop, sizeof(float) * (size_t)N);
-                }
-            });
-        }
+        workers.post_range(0, total_frames_call, 2048, [=](int64_t g0, int64_t g1) {
+            const std::vector<int64_t> &fs = *fstart;
+            int64_t c = std::upper_bound(fs.begin(), fs.end(), g0) - fs.begin() - 1;
+            for (int64_t g = g0; g < g1; g++) {
+                while (g >= fs[c + 1]) c++;
+                copy_row_stream(dst + g * N, src + clip_offset[c] + (g - fs[c]) * hop, N);
+            }
+            stream_fence();
+        });
     }
-    struct FillJoin {  // (every return path waits for the fillers: they write into the caller's array)
-        std::vector<std::thread> &t;
-        ~FillJoin() { for (auto &x : t) if (x.joinable()) x.join(); }
-    } fill_join{fillers};
-    const int64_t dev_bpf = p->bytes_per_frame - (host_buffer ? 4 * (int64_t)N : 0);  // bytes per frame the device produces
+    // frames [g0, g1) of the amplitude rows have landed: square them into the power rows
+    auto post_power = [&](int64_t g0, int64_t g1) {
+        if (!host_power || g1 <= g0) return;
+        const float *amp = out->amplitude_spectrum;
+        float *pw = out->power_spectrum;
+        const int64_t M = N / 2;
+        workers.post_range(g0, g1, 1024, [=](int64_t a, int64_t b) {
+            square_rows_stream(pw + a * M, amp + a * M, (b - a) * M);
+            stream_fence();
+        });
+    };
+    int64_t slot_g0[2] = {0, 0}, slot_g1[2] = {0, 0};  // the frame range each slot's copies in flight will deliver
+    const int64_t dev_bpf = p->bytes_per_frame - (host_buffer ? 4 * (int64_t)N : 0) - (host_power ? 2 * (int64_t)N : 0);  // bytes per frame the device produces
     struct VClip { int64_t off, frames; };
     std::vector<VClip> v;
     p->refined_frames = 0;
@@ -1055,6 +1152,9 @@ static mb_status extract_host_impl(mb_plan *p, const void *samples, const int64_
         if (!s.stream) MB_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
         // the slot's previous chunk (two chunks ago) must have drained before its buffers are reused
         MB_CUDA(cudaStreamSynchronize(s.stream));
+        post_power(slot_g0[chunk_idx & 1], slot_g1[chunk_idx & 1]);
+        slot_g0[chunk_idx & 1] = g_done;
+        slot_g1[chunk_idx & 1] = g_done + frames;
         const size_t span = (size_t)(hi - lo);
         if (s.samples_cap < span * frame_bytes) {
             cudaFree(s.d_samples);
@@ -1118,12 +1218,15 @@ static mb_status extract_host_impl(mb_plan *p, const void *samples, const int64_
         g_done += frames;
         chunk_idx++;
     }
-    for (auto &s : p->slots) {
+    for (int k = 0; k < 2; k++) {
+        Slot &s = p->slots[k];
         if (s.stream) MB_CUDA(cudaStreamSynchronize(s.stream));
+        post_power(slot_g0[k], slot_g1[k]);
+        slot_g0[k] = slot_g1[k] = 0;
         for (size_t i = 0; i < s.h_fix_used; i++) p->refined_frames += s.h_fix[i];
         s.h_fix_used = 0;
     }
-    return MB_OK;
+    return MB_OK;  // (`workers` joins here: every posted row is written before the call returns)
 }
 
 mb_status mb_extract(mb_plan *p, const float *samples, int64_t n_samples, const int64_t *clip_offset,

@@ -134,6 +134,14 @@ mb_exact_warp_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant_
     gw::Scratch &sc = sc_all[warp];
     for (int i = threadIdx.x; i < N - 16; i += kWarpsPerCta * 32) tw[i] = P.tw_exact[15 + i];
     __syncthreads();
+    // Two groups of warps, each in step with itself only (named barriers 1 and 2): while one group sits in a
+    // latency-bound phase (the sequential mel sums, the frame loads) the other is in a register pass, and the SM's
+    // instruction cache still only has to hold two phases.  The second group starts half a round late.
+    constexpr int kGroupA = (kWarpsPerCta + 1) / 2;
+    const int grp = warp < kGroupA ? 0 : 1;
+    const int grp_threads = 32 * (grp == 0 ? kGroupA : kWarpsPerCta - kGroupA);
+    auto group_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "r"(grp_threads) : "memory"); };
+    if (grp == 1) __nanosleep(30000);
 
     const uint32_t mask = P.mask;
     const bool want_moments =
@@ -205,7 +213,7 @@ mb_exact_warp_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant_
             float xin[16];
 #pragma unroll
             for (int j = 0; j < 16; j++) xin[j] = active ? src[lane + (N / 16) * rev_bits(j, 4)] : 0.f;  // (in flight across the barrier)
-            __syncthreads();  // (also: the previous round's epilogue is done with the buffer)
+            group_sync();  // (also: the previous round's epilogue is done with the buffer)
             if (active) {
             // ---- pass 1: widths 1, 2, 4, 8 on BitReverseComplexArray(windowed frame): group g16 holds positions
             // 16 g16 + j = samples rev(g16) + (N/16) rev4(j); this lane takes r = rev(g16) = lane + 32 i
@@ -242,13 +250,13 @@ mb_exact_warp_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant_
                     X[swz<LOG2N>(16 * g16 + j)] = make_float2(__double2float_rn(vr[j]), __double2float_rn(vi[j]));
             }
             }
-            __syncthreads();
+            group_sync();
             // ---- pass 2: widths 16 .. 16 * 2^(Q1 - 1)
             if (active) pass_smem<LOG2N, 4, Q1>(X, tw, lane);
-            __syncthreads();
+            group_sync();
             // ---- pass 3: the last Q2 stages
             if (active) pass_smem<LOG2N, LOG2N - Q2, Q2>(X, tw, lane);
-            __syncthreads();
+            group_sync();
             gw::MomentAcc acc;
             if (active) {
             // ---- spectra out; amplitudes (computeAmplitude src/meyda.js:104-114: bins below N/2) into the upper half of
@@ -278,7 +286,7 @@ mb_exact_warp_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant_
             }
             __syncwarp();
             }
-            __syncthreads();
+            group_sync();
             if (active) gw::frame_epilogue<true>(P, O, g, S, acc, amp, sc);
         }
         if (active && lane == 0) mb_store_scalars(P, O, g, S);
