@@ -898,9 +898,9 @@ mb_status mb_plan_create_ex(mb_plan **plan, int device, int buffer_size, int hop
         }
         D.noise = p->d_noise;
     }
-    // Adaptive exactness: the warp kernels flag the frames whose features sit in the reference's own rounding noise
+    // Adaptive exactness: the float32 kernels flag the frames whose features sit in the reference's own rounding noise
     // and the exact-FFT kernel redoes exactly those (time-domain features never need it).
-    p->adaptive = may_refine && (p->has_warp_kernel || p->has_mf_kernel);
+    p->adaptive = may_refine;  // every float32 kernel family flags (warp, multi-frame warp, generic, multi-warp-per-frame)
     p->dev_fix = D;
     p->dev_fix.mask = feature_mask & ~time_only_mask;
     p->dev_fix.exact = 1;

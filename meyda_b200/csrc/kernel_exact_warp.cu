@@ -27,6 +27,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "mb_adaptive.cuh"
 #include "mb_device.cuh"
 #include "mb_kernels.h"
 

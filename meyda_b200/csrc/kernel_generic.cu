@@ -18,8 +18,8 @@
 // lib/jsfft/fft.js:123-208, the extractor files under src/extractors/ (see
 // mb_device.cuh for the per-formula citations).
 #include <cooperative_groups.h>
-#include <stdlib.h>
 
+#include "mb_adaptive.cuh"
 #include "mb_device.cuh"
 #include "mb_fft.cuh"
 #include "mb_kernels.h"
@@ -146,15 +146,6 @@ cudaError_t mb_launch_exact_cluster(const MbDevPlan &P, const MbClipTable &T, co
 
 cudaError_t mb_launch_generic(const MbDevPlan &P, const MbClipTable &T, const float *samples, const mb_outputs &O,
                               int num_sms, cudaStream_t stream) {
-    if (const char *env = getenv("MB_GENERIC_CTA")) {  // tuning experiments only: force a CTA size
-        const int t = atoi(env);
-#define MB_FORCE(NS, T_)                                                                        \
-    if (t == T_)                                                                                \
-        return P.exact ? launch_generic_##NS<true>(P, T, samples, O, num_sms, stream)           \
-                       : launch_generic_##NS<false>(P, T, samples, O, num_sms, stream);
-        MB_FORCE(g32, 32) MB_FORCE(g64, 64) MB_FORCE(g128, 128) MB_FORCE(g256, 256) MB_FORCE(g512, 512) MB_FORCE(g1024, 1024)
-#undef MB_FORCE
-    }
     // CTA size by bufferSize, from a sweep on the B200 (tools/sweep_generic_cta.py): one warp per frame up to 512
     // (no block-wide barriers left, every reduction is a shuffle), then just enough threads to keep the N/2
     // complex points busy; large frames are shared-memory bound and want few, big CTAs.

@@ -158,39 +158,57 @@ __device__ __forceinline__ float log2_fast(float x) {
 
 struct MomentAcc {
     double s0 = 0, s1 = 0, s2 = 0, s3 = 0, s4 = 0, lg = 0;
+    // mb_adaptive.cuh (float32 kernels of an adaptive plan): q0 = sum q(a_k), q4 = sum q(a_k) k^4 with
+    // q(a) = min(1, (theta sigma / a)^2) from the exponent trick; cf = 0: off
+    float q0 = 0.f, q4 = 0.f;
+    int cf = 0;
     template <bool FAST = false>
     __device__ __forceinline__ void add(float av, int k, bool want_log) {
         const double ad = (double)av, kd = (double)k;
+        if (FAST && cf != 0) {
+            float u;
+            asm("mul.sat.f32 %0, %1, %1;" : "=f"(u) : "f"(__int_as_float(cf - __float_as_int(av))));
+            const float k2 = (float)k * (float)k;
+            q0 += u;
+            q4 = fmaf(u, k2 * k2, q4);
+        }
         double t = ad * kd;
         s0 += ad;
         s1 += t;
         t *= kd; s2 += t;
         t *= kd; s3 += t;
         t *= kd; s4 += t;
-#ifdef MB_GENERIC_WARP_LOCAL
-        if (want_log) lg += (double)log2_fast(av);  // (2^-22 per term, random: 1e-9 of the sum; flatness is compared at 5e-6)
-#else
-        if (want_log) lg += (double)(FAST ? log2_fast(av) : log2f(av));
-#endif
+        // (one MUFU in every kernel family, exact mode included, so that a frame's flatness does not depend on which
+        // kernel served it: 2^-22 per term, 2e-7 of the mean at worst; flatness is compared at 5e-6 in exact mode)
+        if (want_log) lg += (double)log2_fast(av);
     }
 };
 
 // Everything after the amplitude spectrum: block reductions of the moment partials, rolloff, Bark bands,
 // mel/log/DCT and the per-band outputs.  `amp` holds the N/2 amplitudes of the frame in shared memory.
+#ifdef MB_GENERIC_WARP_LOCAL  // (exact arithmetic only: the float32 kernels' noise bounds are never written there)
+constexpr int kNoiseBands = 1, kNoiseFilters = 1;
+#else
+constexpr int kNoiseBands = MB_MAX_BARK_BANDS, kNoiseFilters = MB_MAX_MEL_FILTERS;
+#endif
 struct Scratch {
+    float noise_u[kNoiseBands];   // mb_adaptive.cuh: per-band / per-filter bounds and what the decision needs
+    float noise_dl[kNoiseFilters];
+    float noise_q[2], noise_total, noise_sharp;
     double red_d[kWarps];
     float red_f[kWarps];
     int red_i[kWarps];
     double scan_d[kWarps];
-    double red6[6][kWarps];
+    double red6[8][kWarps];
     double band_sum[MB_MAX_BARK_BANDS];
     float specific[MB_MAX_BARK_BANDS];
     float mel_log[MB_MAX_MEL_FILTERS];
 };
 
+// noise_sigma > 0: the float32 kernel of an adaptive plan also leaves the mb_adaptive.cuh bounds in `sc`.
 template <bool EXACT>
 __device__ __forceinline__ void frame_epilogue(const MbDevPlan &P, const mb_outputs &O, int64_t g, MbFrameSums &S,
-                                               const MomentAcc &acc, const float *amp, Scratch &sc) {
+                                               const MomentAcc &acc, const float *amp, Scratch &sc, float noise_sigma = 0.f) {
     const int M = P.M;
     const uint32_t mask = P.mask;
     const int nb = P.nb, nf = P.nf, nc = P.nc;  // 24 / 26 / 13 unless the plan was created with other parameters
@@ -206,22 +224,27 @@ __device__ __forceinline__ void frame_epilogue(const MbDevPlan &P, const mb_outp
     const bool want_bark = mask & (MB_FEATURE_BIT(MB_FEAT_LOUDNESS) | MB_FEATURE_BIT(MB_FEAT_PERCEPTUAL_SPREAD) |
                                    MB_FEATURE_BIT(MB_FEAT_PERCEPTUAL_SHARPNESS));
     if (want_moments) {
-        // the six sums through ONE pair of barriers (each is reduced exactly as block_sum would: same bits)
-        double v[6] = {acc.s0, acc.s1, acc.s2, acc.s3, acc.s4, acc.lg};
+        // the six sums (and the two floor measures of mb_adaptive.cuh) through ONE pair of barriers (each is reduced
+        // exactly as block_sum would: same bits)
+        double v[8] = {acc.s0, acc.s1, acc.s2, acc.s3, acc.s4, acc.lg, (double)acc.q0, (double)acc.q4};
 #pragma unroll
-        for (int q = 0; q < 6; q++) v[q] = mb_warp_sum(v[q]);
+        for (int q = 0; q < 8; q++) v[q] = mb_warp_sum(v[q]);
         if constexpr (kWarps > 1) {
             block_sync();
             if (lane == 0) {
 #pragma unroll
-                for (int q = 0; q < 6; q++) sc.red6[q][warp] = v[q];
+                for (int q = 0; q < 8; q++) sc.red6[q][warp] = v[q];
             }
             block_sync();
 #pragma unroll
-            for (int q = 0; q < 6; q++) v[q] = mb_warp_sum(lane < kWarps ? sc.red6[q][lane] : 0.0);
+            for (int q = 0; q < 8; q++) v[q] = mb_warp_sum(lane < kWarps ? sc.red6[q][lane] : 0.0);
         }
         S.s0 = v[0]; S.s1 = v[1]; S.s2 = v[2]; S.s3 = v[3]; S.s4 = v[4];
         if (want_log) S.log2sum = v[5];
+        if (!EXACT && tid == 0) {  // (1.6: the exponent trick's worst case, squared; every bin was looked at)
+            sc.noise_q[0] = 1.6f * (float)v[6];
+            sc.noise_q[1] = 1.6f * (float)v[7];
+        }
     }
     block_sync();
 
@@ -383,7 +406,10 @@ __device__ __forceinline__ void frame_epilogue(const MbDevPlan &P, const mb_outp
     block_sync();
     // ln of the 26 filter energies by 26 threads at once (mfcc.js:63), not one filter at a time
     if (!EXACT && mb_has(mask, MB_FEAT_MFCC)) {
-        for (int f = tid; f < nf; f += kThreads) mel_log[f] = (float)log((double)mel_log[f]);
+        for (int f = tid; f < nf; f += kThreads) {
+            if (noise_sigma > 0.f) sc.noise_dl[f] = mb_noise_mel(mel_log[f], __ldg(&P.noise->mel_c1[f]), __ldg(&P.noise->mel_c2[f]), noise_sigma);
+            mel_log[f] = (float)log((double)mel_log[f]);
+        }
         block_sync();
     }
 
@@ -391,6 +417,7 @@ __device__ __forceinline__ void frame_epilogue(const MbDevPlan &P, const mb_outp
         for (int b = tid; b < nb; b += kThreads) {
             const float sp = (float)pow(band_sum[b], 0.23);
             specific[b] = sp;
+            if (!EXACT && noise_sigma > 0.f) sc.noise_u[b] = mb_noise_band((float)band_sum[b], sp, __ldg(&P.noise->band_c[b]), noise_sigma);
             if (mb_has(mask, MB_FEAT_LOUDNESS)) O.loudness_specific[g * nb + b] = sp;
         }
         block_sync();
@@ -403,6 +430,8 @@ __device__ __forceinline__ void frame_epilogue(const MbDevPlan &P, const mb_outp
                 if (i >= 1 && i <= 15) sharp += (double)i * sp;  // (i+1) * spec[i+1], i < 15
             }
             sharp += P.sharp_const;
+            sc.noise_total = (float)total;
+            sc.noise_sharp = (float)sharp;
             if (mb_has(mask, MB_FEAT_LOUDNESS)) O.loudness_total[g] = (float)total;
             if (mb_has(mask, MB_FEAT_PERCEPTUAL_SPREAD)) {
                 const double r = (total - mx) / total;
@@ -419,6 +448,32 @@ __device__ __forceinline__ void frame_epilogue(const MbDevPlan &P, const mb_outp
             for (int f = 0; f < nf; f++) v += (double)__ldg(P.dct + c + f * nc) * (double)mel_log[f];
             O.mfcc[g * nc + c] = (float)(v / (double)nc);
         }
+}
+
+// The exponent trick behind MomentAcc::cf needs theta sigma < 1; a frame beyond that (samples above ~2^18, or a NaN)
+// is simply redone: reported to frame_finish as if it had been rescaled.
+__device__ __forceinline__ bool acc_cf_missing(float noise_sigma) { return !(noise_sigma < 1.f / kMbNoiseTheta); }
+
+// The frame's number features and, in the float32 kernel of an adaptive plan, the decision whether the exact-FFT
+// kernel has to redo it (mb_adaptive.cuh); one thread, after the epilogue's scratch is visible.
+__device__ __forceinline__ void frame_finish(const MbDevPlan &P, const MbClipTable &T, const mb_outputs &O, int64_t g,
+                                             const MbFrameSums &S, const Scratch &sc, float noise_sigma, int kscale) {
+    MbMoments MO;
+    mb_store_scalars(P, O, g, S, &MO);
+    if (noise_sigma >= 0.f && T.fix_count != nullptr) {
+        MbNoiseFrame NF;
+        NF.sigma = noise_sigma;
+        NF.q0 = sc.noise_q[0];
+        NF.q4 = sc.noise_q[1];
+        NF.sum_u = 0.f;
+        for (int b = 0; b < P.nb; b++) NF.sum_u += sc.noise_u[b];
+        NF.sum_dl = 0.f;
+        for (int f = 0; f < P.nf; f++) NF.sum_dl += sc.noise_dl[f];
+        NF.total = sc.noise_total;
+        NF.sharp = sc.noise_sharp;
+        // (a frame rescaled by 2^kscale lies outside the range the bounds were made for: redo it)
+        if (kscale != 0 || mb_noise_needs_exact(P, P.mask, S, MO, NF)) T.fix_list[atomicAdd(T.fix_count, 1)] = (int)g;
+    }
 }
 
 template <bool EXACT>
@@ -452,6 +507,7 @@ mb_generic_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ M
     const uint32_t time_only = MB_FEATURE_BIT(MB_FEAT_RMS) | MB_FEATURE_BIT(MB_FEAT_ENERGY) |
                                MB_FEATURE_BIT(MB_FEAT_ZCR) | MB_FEATURE_BIT(MB_FEAT_BUFFER);
     const bool want_spectrum = (mask & ~time_only) != 0;
+    const bool adapt = !EXACT && want_spectrum && T.fix_count != nullptr;  // this launch lists the frames to be redone exactly
 
     // (sel_list: only the frames a float32-FFT kernel flagged, mb_adaptive.cuh)
     const int64_t n_work = T.sel_list ? (int64_t)*T.sel_count : T.total_frames;
@@ -474,6 +530,7 @@ mb_generic_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ M
             for (int i = tid; i < M; i += kThreads) {
                 const float x0 = src[2 * i], x1 = src[2 * i + 1];
                 mxabs = fmaxf(mxabs, fmaxf(fabsf(x0), fabsf(x1)));
+                if (adapt && !want_time) e += (double)x0 * (double)x0 + (double)x1 * (double)x1;
                 if (want_time) {
                     e += (double)x0 * (double)x0 + (double)x1 * (double)x1;
                     z += ((x0 >= 0.f) != (x1 >= 0.f)) && (x0 == x0) && (x1 == x1);
@@ -502,6 +559,8 @@ mb_generic_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ M
             if (want_time) {
                 S.energy = block_sum(e, red_d);
                 S.zcr = block_sum_int(z, red_i);
+            } else if (adapt) {
+                S.energy = block_sum(e, red_d);
             }
             if (!EXACT && want_spectrum) {
                 // the reference squares |Z| in float64; a frame far outside the float32 comfort zone is
@@ -529,8 +588,12 @@ mb_generic_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ M
         const float unscale = ldexpf(1.f, -kscale);
         block_sync();
 
+        // mb_adaptive.cuh: rms rounding error of one spectrum bin (the frame's own units); < 0: not an adaptive launch
+        const float noise_sigma = adapt ? mb_noise_sigma((float)S.energy, 1.0f / (float)N) : -1.f;
         if (want_spectrum) {
             MomentAcc acc;
+            if (adapt && noise_sigma > 0.f && noise_sigma < 1.f / kMbNoiseTheta)
+                acc.cf = 0x7EF311C7 + __float_as_int(kMbNoiseTheta * noise_sigma) - 0x3F800000;
             if (EXACT) {
                 // ---- FFT_2_Iterative lib/jsfft/fft.js:139-168: doubles, no FMA, f32 stage stores
                 exact_stages(xre, xim, P.tw_exact, N, 0, log2M + 1);
@@ -591,9 +654,10 @@ mb_generic_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ M
                     if (want_moments) acc.add<true>(av, k, want_log);
                 }
             }
-            frame_epilogue<EXACT>(P, O, g, S, acc, amp, sc);
+            frame_epilogue<EXACT>(P, O, g, S, acc, amp, sc, adapt ? noise_sigma : 0.f);
         }
-        if (tid == kScalarThread) mb_store_scalars(P, O, g, S);
+        if (adapt) block_sync();  // (the epilogue's bounds are read by the one thread below)
+        if (tid == kScalarThread) frame_finish(P, T, O, g, S, sc, adapt ? noise_sigma : -1.f, (adapt && acc_cf_missing(noise_sigma)) ? 1 : kscale);
         block_sync();  // smem reused by the next frame
     }
 }
@@ -749,6 +813,7 @@ mb_big32768_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
                                MB_FEATURE_BIT(MB_FEAT_ZCR) | MB_FEATURE_BIT(MB_FEAT_BUFFER);
     const bool want_spectrum = (mask & ~time_only) != 0;
     const bool want_cs = mb_has(mask, MB_FEAT_COMPLEX_SPECTRUM);
+    const bool adapt = want_spectrum && T.fix_count != nullptr;  // this launch lists the frames to be redone exactly
 
     // tables (once per persistent CTA) and this thread's own twiddle exp(+2 pi i warp lane / M)
     for (int i = tid; i < 32 * 32; i += kThreads) {
@@ -790,6 +855,7 @@ mb_big32768_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
             auto take = [&](const int i, const float4 x) {
                 const float4 w = __ldg(win4 + i);
                 mxabs = fmaxf(mxabs, fmaxf(fmaxf(fabsf(x.x), fabsf(x.y)), fmaxf(fabsf(x.z), fabsf(x.w))));
+                if (adapt && !want_time) e += (double)(x.x * x.x + x.y * x.y) + (double)(x.z * x.z + x.w * x.w);
                 if (want_time) {
                     e += (double)(x.x * x.x + x.y * x.y) + (double)(x.z * x.z + x.w * x.w);
                     const float nx = (4 * i + 4 < N) ? __ldg(src + 4 * i + 4) : x.w;  // last sample has no successor
@@ -814,6 +880,8 @@ mb_big32768_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
             if (want_time) {
                 S.energy = block_sum(e, sc.red_d);
                 S.zcr = block_sum_int(z, sc.red_i);
+            } else if (adapt) {
+                S.energy = block_sum(e, sc.red_d);
             }
             if (want_spectrum) {  // frames outside the float32 comfort zone: exact power-of-two rescale (see generic kernel)
 #pragma unroll
@@ -837,6 +905,7 @@ mb_big32768_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
             }
         }
         const float unscale = ldexpf(1.f, -kscale);
+        const float noise_sigma = adapt ? mb_noise_sigma((float)S.energy, 1.0f / (float)N) : -1.f;  // mb_adaptive.cuh
         {   // this CTA's next frame on its way into L2 while the current one is transformed (its 128 KB were
             // otherwise fetched with four exposed round trips at the top of the next iteration)
             const int64_t gn = g + gridDim.x;
@@ -902,6 +971,8 @@ mb_big32768_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
             block_sync();
             // ---- 6. real-FFT split, spectra out, amplitude into smem, moment partials
             MomentAcc acc;
+            if (adapt && noise_sigma > 0.f && noise_sigma < 1.f / kMbNoiseTheta)
+                acc.cf = 0x7EF311C7 + __float_as_int(kMbNoiseTheta * noise_sigma) - 0x3F800000;
             const float sc_n = P.inv_sqrt_N;
 #pragma unroll 8
             for (int k = tid; k < M; k += kThreads) {
@@ -931,9 +1002,10 @@ mb_big32768_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
                 if (mb_has(mask, MB_FEAT_POWER_SPECTRUM)) __stcs(O.power_spectrum + g * M + k, __fmul_rn(av, av));
                 if (want_moments) acc.add<true>(av, k, want_log);
             }
-            frame_epilogue<false>(P, O, g, S, acc, B.amp, sc);
+            frame_epilogue<false>(P, O, g, S, acc, B.amp, sc, adapt ? noise_sigma : 0.f);
         }
-        if (tid == kScalarThread) mb_store_scalars(P, O, g, S);
+        if (adapt) block_sync();
+        if (tid == kScalarThread) frame_finish(P, T, O, g, S, sc, adapt ? noise_sigma : -1.f, (adapt && acc_cf_missing(noise_sigma)) ? 1 : kscale);
         block_sync();  // smem reused by the next frame
     }
 }

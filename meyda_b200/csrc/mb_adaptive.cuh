@@ -122,7 +122,7 @@ __device__ __forceinline__ bool mb_noise_needs_exact(const MbDevPlan &P, uint32_
         if (mb_has(mask, MB_FEAT_SPECTRAL_FLATNESS)) {
             // flatness = exp(mean ln a) n / S0: mean ln a moves by (Q0 + 4 sqrt(Q0) / theta) / n, S0 by r0
             const double dml = (q0 + 4.0 * sqrt(q0) / (double)kMbNoiseTheta) / n + r0;
-            bad |= !(dml <= 1.0) || !(M.flatness * (dml + dml * dml) <= dtol);  // e^x - 1 <= x + x^2 on [0, 1]
+            bad |= !(dml + dml * dml <= dtol);  // RELATIVE motion of the flatness (its magnitude runs from 1e-5 on tones to 1); e^x - 1 <= x + x^2
             bad |= (S.log2sum < -1e30) && (S.s0 > 0.0);  // a bin that is exactly 0 here need not be in the reference
         }
     }

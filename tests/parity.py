@@ -9,7 +9,9 @@ oracle.meyda_oracle.extract returns).  Tolerances are BASELINE.json's:
                          ~1e-8 * peak per bin: SURVEY.md section 7)
   numbers, loudness, mfcc   1e-3 relative OR absolute (slope: relative, or 1e-13
                          absolute -- its magnitude is ~1e-7, an absolute 1e-3 would
-                         be vacuous, and on a flat spectrum it is pure cancellation)
+                         be vacuous, and on a flat spectrum it is pure cancellation;
+                         rms / energy: relative only; flatness: the absolute floor is
+                         1e-3 x the batch's median flatness)
   NaN / +-Inf            same positions and signs
 
 Noise band (float32-FFT kernels only).  Some features amplify the spectrum's
@@ -143,8 +145,19 @@ def compare_all(gpu: dict, ref: dict, N: int, sr: float = 44100.0, noise_band: d
         assert_numbers("spectralRolloff", gpu["spectral_rolloff"], ref["spectralRolloff"], tol=1e-6, abs_tol=0.0)
     for field, feat in NUMBER_FIELDS.items():
         if field in gpu:
-            out[feat] = assert_numbers(feat, gpu[field], ref[feat], tol=tol,
-                                       abs_tol=SLOPE_ABS_TOL if feat == "spectralSlope" else None, band=nb(feat))
+            # The flat "1e-3 relative OR absolute" rule is vacuous where a feature's magnitude is far below 1e-3
+            # (a wrong formula would pass): rms and energy are plain sums and are held to the relative bound alone,
+            # slope (~1e-7) to 1e-13, flatness (1e-5 .. 1 on tonal .. noisy frames) to a floor scaled to the batch.
+            abs_tol = None
+            if feat == "spectralSlope":
+                abs_tol = SLOPE_ABS_TOL
+            elif feat in ("rms", "energy"):
+                abs_tol = 1.2e-38  # (outputs are float32: a reference value below its normal range cannot be held)
+            elif feat == "spectralFlatness":
+                fin = np.isfinite(np.asarray(ref[feat], dtype=np.float64))
+                med = float(np.median(np.abs(np.asarray(ref[feat], dtype=np.float64)[fin]))) if fin.any() else 0.0
+                abs_tol = min(tol, max(1e-7, tol * med))
+            out[feat] = assert_numbers(feat, gpu[field], ref[feat], tol=tol, abs_tol=abs_tol, band=nb(feat))
     if "loudness_specific" in gpu:
         nl = nb("loudness")
         out["loudness.specific"] = assert_numbers("loudness.specific", gpu["loudness_specific"],

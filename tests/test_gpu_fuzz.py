@@ -1,7 +1,7 @@
 """Seeded random batches through the tuned kernels: ragged clips, arbitrary hops (aligned or not), frame counts that
-are not multiples of a warp's chunk or group.  Checks that do not need the noise band: frame bookkeeping,
-bit-exact zcr / buffer, spectra and the robust numbers against the oracle, and that a batch equals its clips
-extracted one by one, bit for bit (a frame's bits depend on nothing but its samples)."""
+are not multiples of a warp's chunk or group.  Frame bookkeeping, every feature against the oracle at the flat
+tolerances (no noise band), and a batch equals its clips extracted one by one, bit for bit (a frame's bits depend on
+nothing but its samples and the feature list)."""
 import numpy as np
 import pytest
 
@@ -50,21 +50,6 @@ def test_random_batches(N, hop, lens, seed):
         assert all(len(v) == 0 for v in out.values())
         return
     ref = mo._concat([c_oracle.extract(c, N, hop, SR, "hanning") for c in kept])
-    parity.assert_bits("buffer", out["buffer"], ref["buffer"])
-    assert np.array_equal(out["zcr"].astype(np.int64), ref["zcr"].astype(np.int64))
-    rr, ri = ref["complexSpectrum"]["real"], ref["complexSpectrum"]["imag"]
-    pk = np.sqrt(rr.astype(np.float64) ** 2 + ri.astype(np.float64) ** 2).max(axis=1)
-    parity.assert_spectrum("complexSpectrum.real", out["complex_real"], rr, peak=pk)
-    parity.assert_spectrum("complexSpectrum.imag", out["complex_imag"], ri, peak=pk)
-    parity.assert_spectrum("amplitudeSpectrum", out["amplitude_spectrum"], ref["amplitudeSpectrum"])
-    parity.assert_spectrum("powerSpectrum", out["power_spectrum"], ref["powerSpectrum"])
-    for f, k in (("rms", "rms"), ("energy", "energy"), ("spectral_centroid", "spectralCentroid"),
-                 ("spectral_spread", "spectralSpread"), ("spectral_flatness", "spectralFlatness"),
-                 ("spectral_slope", "spectralSlope"), ("loudness_total", None), ("perceptual_spread", "perceptualSpread"),
-                 ("perceptual_sharpness", "perceptualSharpness")):
-        r = ref["loudness"]["total"] if k is None else ref[k]
-        parity.assert_numbers(f, out[f], r, abs_tol=parity.SLOPE_ABS_TOL if f == "spectral_slope" else None)
-    parity.assert_numbers("mfcc", out["mfcc"], ref["mfcc"])  # (+-Infinity at bufferSize 256: positions and signs must match)
-    parity.assert_numbers("loudness.specific", out["loudness_specific"], ref["loudness"]["specific"])
-    binhz = SR / (2 * (N // 2 - 1))
-    assert np.array_equal(np.rint(out["spectral_rolloff"] / binhz), np.rint(ref["spectralRolloff"] / binhz))
+    # every feature, spectralSkewness / spectralKurtosis included, at BASELINE.json's flat tolerances and with NO noise
+    # band: the plans are adaptive (frames whose values the reference's own rounding decides are redone exactly)
+    assert parity.compare_all(out, ref, N, noise_band=None) == {}

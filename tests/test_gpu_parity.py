@@ -14,6 +14,7 @@ pytestmark = pytest.mark.gpu
 SR = 44100.0
 EXACT = _capi.MB_FLAG_EXACT_FFT
 FLAG_VARIANTS = [pytest.param(0, id="fast"), pytest.param(_capi.MB_FLAG_GENERIC_KERNEL, id="generic"),
+                 pytest.param(_capi.MB_FLAG_NO_REFINE, id="fast-norefine"),  # (float32 FFT alone: may use the noise band)
                  pytest.param(EXACT, id="exact"),  # (the warp-per-frame exact kernel at 512 / 1024 / 2048)
                  pytest.param(EXACT | _capi.MB_FLAG_GENERIC_KERNEL, id="exact-generic"),  # (block per frame)
                  pytest.param(EXACT | _capi.MB_FLAG_CLUSTER_FFT, id="exact-cluster")]
@@ -34,13 +35,14 @@ def oracle_concat(clips, N, hop, window="hanning", impl=c_oracle, **kw):
     return mo._concat(parts)
 
 
-ADAPTIVE_SIZES = (256, 512, 1024, 2048)  # the warp kernels: adaptive exactness (mb_adaptive.cuh)
+NO_REFINE = _capi.MB_FLAG_NO_REFINE
 
 
-def is_adaptive(flags, N):
-    """The default float32 plan at the warp kernels' sizes flags the frames whose features sit in the reference's own
-    rounding noise and redoes them with the exact FFT: it must meet the flat 1e-3 tolerance with NO noise band."""
-    return flags == 0 and N in ADAPTIVE_SIZES
+def is_adaptive(flags, N=None):
+    """Every float32 plan (warp, multi-frame warp, generic and multi-warp-per-frame kernels alike) flags the frames
+    whose features sit in the reference's own rounding noise and redoes them with the exact FFT (mb_adaptive.cuh):
+    it must meet the flat 1e-3 tolerance with NO noise band.  Only MB_FLAG_NO_REFINE plans may use the band."""
+    return not (flags & (EXACT | NO_REFINE))
 
 
 def verify(out, clips, N, hop, window="hanning", flags=0, max_banded_frac=0.10, adaptive=None):
@@ -64,6 +66,34 @@ def verify(out, clips, N, hop, window="hanning", flags=0, max_banded_frac=0.10, 
         per_frame = {"mfcc": 13, "loudness.specific": 24}.get(k, 1)
         assert v <= max_banded_frac * frames * per_frame, (k, v, frames)
     return banded
+
+
+# ---- BASELINE config 5's shape: bufferSize 32768, hop 8192, amplitudeSpectrum + rolloff / flatness / slope over several
+# channels of 319 frames, in the default (adaptive multi-warp-per-frame kernel) and the exact-cluster mode
+@pytest.mark.parametrize("flags", [pytest.param(0, id="fast"), pytest.param(EXACT, id="exact-cluster")])
+def test_config5_shape(flags):
+    N, hop, frames = 32768, 8192, 319
+    L = N + hop * (frames - 1)  # 2,637,824 samples: 60 s at 44.1 kHz holds 319 frames
+    feats = ["amplitudeSpectrum", "spectralRolloff", "spectralFlatness", "spectralSlope"]
+    clips = [mo.synth_clip(70 + c, L) for c in range(4)]
+    t = np.arange(L) / SR
+    clips[3] = (0.4 * np.sin(2 * np.pi * 997.0 * t)).astype(np.float32)  # one tonal channel: its frames are redone exactly
+    data, off, ln = mb.meyda._normalize_clips(clips)
+    plan = mb.Plan(N, hop, SR, "hanning", feats, flags=flags)
+    try:
+        out, per = plan.extract_host(data, off, ln)
+        name, refined = plan.kernel_name, plan.refined_frames
+    finally:
+        plan.close()
+    assert per.tolist() == [frames] * 4 and name == ("exact-cluster2" if flags else "big32768")
+    if not flags:
+        assert frames <= refined < 2 * frames, refined  # the tonal channel, and hardly anything of the noisy ones
+    pick = np.r_[0:3, frames - 2:frames + 2, 2 * frames - 1, 3 * frames:3 * frames + 3, 4 * frames - 1]  # a few frames of every channel
+    for g in pick:
+        c, f = divmod(int(g), frames)
+        ref = c_oracle.extract(clips[c][f * hop:f * hop + N], N, N, SR)
+        one = {k: v[g:g + 1] for k, v in out.items()}
+        assert parity.compare_all(one, ref, N, exact=bool(flags & EXACT)) == {}, (c, f)
 
 
 # ---- BASELINE config 1: sound1.wav, N=512, five features
@@ -618,7 +648,7 @@ def test_cuda_against_the_reference_javascript_vectors(golden_audio, flags):
         except AssertionError as e:
             raise AssertionError("case %d %s N=%d frame %d %s: %s" % (ci, clip, N, f, window, e)) from None
         checked += 1
-    assert checked == (17 if (exact or flags == 0) else 16)
+    assert checked == (17 if (exact or is_adaptive(flags)) else 16)
 
 
 @pytest.mark.parametrize("flags", [pytest.param(_capi.MB_FLAG_GENERIC_KERNEL, id="generic"), pytest.param(EXACT, id="exact")])

@@ -112,7 +112,7 @@ def flags(amp, Eraw, N, K=16.0, theta=32.0, kap=8.0, m=0.5, t=1e-3, kb=2.0, k2=4
         L = np.log(amp).sum(1)
         flat = np.exp(L/n)*n/S[0]
         dml = (q0 + 4*np.sqrt(q0)/theta)/n + r0
-        out['spectralFlatness'] = (~(dml <= 1.0) | ~(flat*(dml+dml*dml) <= tl) | (np.isneginf(L))) & ok0
+        out['spectralFlatness'] = (~(dml <= 1.0) | ~((dml+dml*dml) <= tl) | (np.isneginf(L))) & ok0
     if detail: out['_dd'] = dd
     return out
 
