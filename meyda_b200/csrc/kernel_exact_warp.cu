@@ -133,6 +133,8 @@ mb_exact_warp_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant_
     float2 *X = Xall + warp * N;
     float *amp = reinterpret_cast<float *>(X) + N;  // N/2 floats over the upper half of the buffer (bins >= N/2), once those are stored
     gw::Scratch &sc = sc_all[warp];
+    // (the second pass of an adaptive plan usually finds nothing to do: leave before the 32 KB table is fetched)
+    if ((T.sel_list ? (int64_t)*T.sel_count : T.total_frames) <= (int64_t)blockIdx.x * kWarpsPerCta) return;
     for (int i = threadIdx.x; i < N - 16; i += kWarpsPerCta * 32) tw[i] = P.tw_exact[15 + i];
     __syncthreads();
     // Two groups of warps, each in step with itself only (named barriers 1 and 2): while one group sits in a

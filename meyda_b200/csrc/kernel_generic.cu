@@ -146,7 +146,7 @@ cudaError_t mb_launch_exact_cluster(const MbDevPlan &P, const MbClipTable &T, co
 
 cudaError_t mb_launch_generic(const MbDevPlan &P, const MbClipTable &T, const float *samples, const mb_outputs &O,
                               int num_sms, cudaStream_t stream) {
-    // CTA size by bufferSize, from a sweep on the B200 (tools/sweep_generic_cta.py): one warp per frame up to 512
+    // CTA size by bufferSize, from a sweep on the B200 (round 1, profiles/README.md): one warp per frame up to 512
     // (no block-wide barriers left, every reduction is a shuffle), then just enough threads to keep the N/2
     // complex points busy; large frames are shared-memory bound and want few, big CTAs.
 #define MB_GO(NS)                                                                           \

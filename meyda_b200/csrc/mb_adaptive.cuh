@@ -85,44 +85,46 @@ __device__ __forceinline__ bool mb_noise_needs_exact(const MbDevPlan &P, uint32_
                          MB_FEATURE_BIT(MB_FEAT_SPECTRAL_SKEWNESS) | MB_FEATURE_BIT(MB_FEAT_SPECTRAL_KURTOSIS) |
                          MB_FEATURE_BIT(MB_FEAT_SPECTRAL_FLATNESS) | MB_FEATURE_BIT(MB_FEAT_SPECTRAL_SLOPE);
     if (mask & mom) {
-        const double sg = (double)F.sigma, n = (double)P.M, dtol = (double)tol;
-        const double q0 = (double)F.q0, q4 = (double)F.q4;
+        // float32 throughout (MUFU reciprocals and roots): these are bounds with safety factors of 2 .. 16 behind them,
+        // and in the block-per-frame kernels ONE thread evaluates them while the CTA waits.  Where float32 runs out
+        // (var cancelling below 1e-7 m1^2) the comparisons fail on a NaN or a negative and the frame is redone.
+        const float sg = F.sigma, n = (float)P.M, q0 = F.q0, q4 = F.q4;
         // Q_p <= Q_0^(1 - p/4) Q_4^(p/4) (moments are log-convex in p); sums move by sigma (kap sqrt(T_2p) + Q_p)
-        const double g = (q0 > 0.0 && q4 > 0.0) ? sqrt(sqrt(q4 / q0)) : 0.0;
-        const double inv0 = 1.0 / S.s0;
-        const double r0 = sg * (P.noise_sqrtT[0] + q0) * inv0;  // relative motion of S_0
-        const double q1 = q0 * g, q2 = q1 * g, q3 = q2 * g;
+        const float g = (q0 > 0.f && q4 > 0.f) ? sqrtf(sqrtf(__fdividef(q4, q0))) : 0.f;
+        const float inv0 = sg * __fdividef(1.f, (float)S.s0);  // sigma / S_0
+        const float r0 = ((float)P.noise_sqrtT[0] + q0) * inv0;  // relative motion of S_0
+        const float q1 = q0 * g, q2 = q1 * g, q3 = q2 * g;
+        const float m1 = (float)M.m1, m2 = (float)M.m2, m3 = (float)M.m3, m4 = (float)M.m4, var = (float)M.var, sd = (float)M.sd;
         // absolute motion of m_i = S_i / S_0: (dS_i + m_i dS_0) / S_0
-        const double d1 = sg * (P.noise_sqrtT[1] + q1) * inv0 + M.m1 * r0;
-        const double d2 = sg * (P.noise_sqrtT[2] + q2) * inv0 + M.m2 * r0;
-        const double d3 = sg * (P.noise_sqrtT[3] + q3) * inv0 + M.m3 * r0;
-        const double d4 = sg * (P.noise_sqrtT[4] + q4) * inv0 + M.m4 * r0;
-        const double m1 = M.m1, m2 = M.m2, m3 = M.m3, var = M.var, sd = M.sd;
-        if (mb_has(mask, MB_FEAT_SPECTRAL_CENTROID)) bad |= !(d1 <= dtol * fmax(1.0, m1));
+        const float d1 = ((float)P.noise_sqrtT[1] + q1) * inv0 + m1 * r0;
+        const float d2 = ((float)P.noise_sqrtT[2] + q2) * inv0 + m2 * r0;
+        const float d3 = ((float)P.noise_sqrtT[3] + q3) * inv0 + m3 * r0;
+        const float d4 = ((float)P.noise_sqrtT[4] + q4) * inv0 + m4 * r0;
+        if (mb_has(mask, MB_FEAT_SPECTRAL_CENTROID)) bad |= !(d1 <= tol * fmaxf(1.f, m1));
         // spectralSlope.js:17 is linear in the centroid, alpha (c - (n-1)/2), and compared relatively
-        if (mb_has(mask, MB_FEAT_SPECTRAL_SLOPE)) bad |= !(d1 <= dtol * fabs(m1 - 0.5 * (n - 1.0)));
+        if (mb_has(mask, MB_FEAT_SPECTRAL_SLOPE)) bad |= !(d1 <= tol * fabsf(m1 - 0.5f * (n - 1.f)));
         const uint32_t high = MB_FEATURE_BIT(MB_FEAT_SPECTRAL_SPREAD) | MB_FEATURE_BIT(MB_FEAT_SPECTRAL_SKEWNESS) | MB_FEATURE_BIT(MB_FEAT_SPECTRAL_KURTOSIS);
         if (mask & high) {
-            const double dv = d2 + 2.0 * m1 * d1;  // motion of var = m2 - m1^2
-            bad |= !(dv <= 0.25 * var);            // (first order only holds while the variance keeps its size)
-            const double iv = 1.0 / var, isd = 1.0 / sd;
-            if (mb_has(mask, MB_FEAT_SPECTRAL_SPREAD)) bad |= !(0.5 * dv * isd <= dtol * fmax(1.0, sd));
+            const float dv = d2 + 2.f * m1 * d1;  // motion of var = m2 - m1^2
+            bad |= !(dv <= 0.25f * var);          // (first order only holds while the variance keeps its size)
+            const float iv = __fdividef(1.f, var), isd = __fdividef(1.f, sd);
+            if (mb_has(mask, MB_FEAT_SPECTRAL_SPREAD)) bad |= !(0.5f * dv * isd <= tol * fmaxf(1.f, sd));
             if (mb_has(mask, MB_FEAT_SPECTRAL_SKEWNESS)) {  // A / var^1.5, A = 2 m1^3 - 3 m1 m2 + m3
-                const double A = 2.0 * m1 * m1 * m1 - 3.0 * m1 * m2 + m3, c = 1.5 * A * iv;
-                const double e = (fabs(6.0 * m1 * m1 - 3.0 * m2 + c * 2.0 * m1) * d1 + fabs(-3.0 * m1 - c) * d2 + d3) * iv * isd;
-                bad |= !(e <= dtol * fmax(1.0, fabs(A * iv * isd)));
+                const float A = (float)(2.0 * M.m1 * M.m1 * M.m1 - 3.0 * M.m1 * M.m2 + M.m3), c = 1.5f * A * iv;
+                const float e = (fabsf(6.f * m1 * m1 - 3.f * m2 + c * 2.f * m1) * d1 + fabsf(-3.f * m1 - c) * d2 + d3) * iv * isd;
+                bad |= !(e <= tol * fmaxf(1.f, fabsf(A * iv * isd)));
             }
             if (mb_has(mask, MB_FEAT_SPECTRAL_KURTOSIS)) {  // B / var^2, B = -3 m1^4 + 6 m1 m2 - 4 m1 m3 + m4
-                const double B = -3.0 * m1 * m1 * m1 * m1 + 6.0 * m1 * m2 - 4.0 * m1 * m3 + M.m4, c = 2.0 * B * iv;
-                const double e = (fabs(-12.0 * m1 * m1 * m1 + 6.0 * m2 - 4.0 * m3 + c * 2.0 * m1) * d1 + fabs(6.0 * m1 - c) * d2 +
-                                  4.0 * m1 * d3 + d4) * iv * iv;
-                bad |= !(e <= dtol * fmax(1.0, fabs(B * iv * iv)));
+                const float B = (float)(-3.0 * M.m1 * M.m1 * M.m1 * M.m1 + 6.0 * M.m1 * M.m2 - 4.0 * M.m1 * M.m3 + M.m4), c = 2.f * B * iv;
+                const float e = (fabsf(-12.f * m1 * m1 * m1 + 6.f * m2 - 4.f * m3 + c * 2.f * m1) * d1 + fabsf(6.f * m1 - c) * d2 +
+                                 4.f * m1 * d3 + d4) * iv * iv;
+                bad |= !(e <= tol * fmaxf(1.f, fabsf(B * iv * iv)));
             }
         }
         if (mb_has(mask, MB_FEAT_SPECTRAL_FLATNESS)) {
             // flatness = exp(mean ln a) n / S0: mean ln a moves by (Q0 + 4 sqrt(Q0) / theta) / n, S0 by r0
-            const double dml = (q0 + 4.0 * sqrt(q0) / (double)kMbNoiseTheta) / n + r0;
-            bad |= !(dml + dml * dml <= dtol);  // RELATIVE motion of the flatness (its magnitude runs from 1e-5 on tones to 1); e^x - 1 <= x + x^2
+            const float dml = __fdividef(q0 + 4.f * sqrtf(q0) * (1.f / kMbNoiseTheta), n) + r0;
+            bad |= !(dml + dml * dml <= tol);  // RELATIVE motion of the flatness (its magnitude runs from 1e-5 on tones to 1); e^x - 1 <= x + x^2
             bad |= (S.log2sum < -1e30) && (S.s0 > 0.0);  // a bin that is exactly 0 here need not be in the reference
         }
     }

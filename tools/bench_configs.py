@@ -58,6 +58,11 @@ if "c3" in which:
     run("config3 generic", 2048, 512, 1000, 441000, C3, flags=_capi.MB_FLAG_GENERIC_KERNEL)
 if "c5" in which:
     run("config5 N=32768 hop=8192", 32768, 8192, 256, 2646000, C5)
+if "c5ab" in which:  # the adaptive statistics' cost in the multi-warp-per-frame kernel
+    run("config5 N=32768 hop=8192", 32768, 8192, 256, 2646000, C5)
+    run("config5 N=32768 hop=8192, MB_FLAG_NO_REFINE", 32768, 8192, 256, 2646000, C5, flags=_capi.MB_FLAG_NO_REFINE)
+    run("config5 features N=8192, adaptive", 8192, 2048, 256, 2646000, C5)
+    run("config5 features N=8192, MB_FLAG_NO_REFINE", 8192, 2048, 256, 2646000, C5, flags=_capi.MB_FLAG_NO_REFINE)
 if "exact" in which:
     run("full set exact-FFT", 2048, 512, 200, 441000, mb.FEATURES, flags=_capi.MB_FLAG_EXACT_FFT)
     run("config3 exact-FFT", 2048, 512, 200, 441000, C3, flags=_capi.MB_FLAG_EXACT_FFT)

@@ -21,7 +21,7 @@ if name == "warp2048":  # (the launch list is taken on the headline bench only)
     mine = sum(v for k, (_, v) in agg.items() if "mb_" in k)
     with open(os.path.join(out_dir, f"{tag}_launches_{name}.txt"), "w") as f:
         f.write("# ncu --metrics gpu__time_duration.sum --clock-control none (cold-cache, serialised: compare SHARES)\n")
-        f.write("# command: python bench.py --clips 600 --steps 1 --warmup 3 --no-e2e --no-cpu-baseline (includes torch's input generation)\n")
+        f.write("# command: python bench.py --clips 600 --steps 1 --warmup 3 --no-e2e --no-cpu-baseline --no-secondary (includes torch's input generation)\n")
         f.write("%-90s %6s %12s %7s\n" % ("kernel", "count", "total_us", "share"))
         for k, (n, v) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
             f.write("%-90s %6d %12.1f %6.2f%%\n" % (k[:90], n, v, 100 * v / tot))
@@ -45,14 +45,16 @@ want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "sm__cycles_elapsed.avg"]
 vals = {}
 with open(os.path.join(out_dir, f"{tag}_ncu_{name}.txt"), "w") as f:
-    f.write("# ncu --set full --clock-control none --import-source on -k regex:mb_%s -s 3 -c 1 (one launch, ~40 replays)\n" % name)
+    f.write("# ncu --set full --clock-control none --import-source on -k regex:... -c 1 (one launch, ~40 replays; tools/gpu.sh profile %s)\n" % name)
     f.write("# kernel: %s\n" % r[2][h.index("Kernel Name")])
     for i, m in enumerate(h):
         if m in want:
             f.write("%-70s %-14s %s\n" % (m, r[1][i], r[2][i])); vals[m] = r[2][i]
     frames = float(sys.argv[3]) if len(sys.argv) > 3 else None
     if frames:
-        dr, dw = float(vals["dram__bytes_read.sum"]), float(vals["dram__bytes_write.sum"])
+        unit = {m: r[1][i] for i, m in enumerate(h)}
+        gb = lambda m: float(vals[m]) * {"Gbyte": 1.0, "Mbyte": 1e-3, "Kbyte": 1e-6, "byte": 1e-9, "Tbyte": 1e3}.get(unit[m], 1.0)
+        dr, dw = gb("dram__bytes_read.sum"), gb("dram__bytes_write.sum")
         bpf = int(sys.argv[4]) if len(sys.argv) > 4 else 35016
         f.write("\nframes in this launch: %d; algorithmic bytes %d x %d = %.3f GB; DRAM traffic %.3f GB (%.3fx)\n" % (
             frames, frames, bpf, frames * bpf / 1e9, dr + dw, (dr + dw) / (frames * bpf / 1e9)))
@@ -76,7 +78,7 @@ for x in rows[hi + 1:]:
 with open(os.path.join(out_dir, f"{tag}_ncu_{name}.txt"), "a") as f:
     S = sum(st.values()); T = sum(ops.values())
     f.write("\nwarp stall samples: " + ", ".join("%s %.1f%%" % (k.replace("stall_", ""), 100 * v / S) for k, v in st.most_common(10)) + "\n")
-    f.write("executed SASS by opcode (per frame): " + ", ".join("%s %.0f" % (k, v / (frames or 1)) for k, v in ops.most_common(24)) + "\n")
+    f.write("executed SASS by opcode (warp-instructions per frame): " + ", ".join("%s %.0f" % (k, v / (frames or 1)) for k, v in ops.most_common(24)) + "\n")
     sass = subprocess.run("cuobjdump -sass %s | grep -cE 'UBLKCP'" % os.path.join(ROOT, "meyda_b200/_lib/libmeyda_b200.so"), shell=True, capture_output=True, text=True).stdout.strip()
     f.write("TMA evidence: %s UBLKCP (cp.async.bulk) instructions in the library's SASS\n" % sass)
 print(open(os.path.join(out_dir, f"{tag}_ncu_{name}.txt")).read())
