@@ -1072,8 +1072,10 @@ static mb_status extract_host_impl(mb_plan *p, const void *samples, const int64_
         pcm_channels > 0 ? (size_t)mb_sample_bytes(pcm_format) * (size_t)pcm_channels : 4u;  // bytes per sample frame
     const int64_t bpf = std::max<int64_t>(p->bytes_per_frame, 4);
     (void)bpf;
-    // chunk budget: ~192 MiB of output or ~64 MiB of fresh input, whichever is hit first
-    const int64_t max_frames_out = std::max<int64_t>(1, (192ll << 20) / std::max<int64_t>(p->bytes_per_frame, 4));
+    // chunk budget: ~64 MiB of output or ~64 MiB of fresh input, whichever is hit first
+    // (64 MiB of output per chunk: ~1 ms of PCIe each, so that the pipeline's fill and the host threads' tail stay short
+    // against a moderate batch; the per-chunk overhead is ~20 asynchronous copies)
+    const int64_t max_frames_out = std::max<int64_t>(1, (64ll << 20) / std::max<int64_t>(p->bytes_per_frame, 4));
     const int64_t max_frames_in = std::max<int64_t>(1, (64ll << 20) / (4ll * hop));
     const int64_t chunk_frames = std::min(max_frames_out, max_frames_in);
 

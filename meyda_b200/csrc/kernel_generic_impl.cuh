@@ -457,25 +457,31 @@ __device__ __forceinline__ void frame_epilogue(const MbDevPlan &P, const mb_outp
 __device__ __forceinline__ bool acc_cf_missing(float noise_sigma) { return !(noise_sigma < 1.f / kMbNoiseTheta); }
 
 // The frame's number features and, in the float32 kernel of an adaptive plan, the decision whether the exact-FFT
-// kernel has to redo it (mb_adaptive.cuh); one thread, after the epilogue's scratch is visible.
-__device__ __forceinline__ void frame_finish(const MbDevPlan &P, const MbClipTable &T, const mb_outputs &O, int64_t g,
-                                             const MbFrameSums &S, const Scratch &sc, float noise_sigma, int kscale) {
-    MbMoments MO;
-    mb_store_scalars(P, O, g, S, &MO);
-    if (noise_sigma >= 0.f && T.fix_count != nullptr) {
-        MbNoiseFrame NF;
-        NF.sigma = noise_sigma;
+// kernel has to redo it (mb_adaptive.cuh): ONE thread's work, ~10 float64 divisions and roots.  It is split so that the
+// CTA does not wait for it: frame_gather copies what the epilogue left in shared memory into the thread's registers in
+// front of the frame's last barrier, frame_finish does the arithmetic and the stores behind it, while the other warps
+// are already loading the next frame (the thread's own warp joins them a little later, well before the load's barrier).
+__device__ __forceinline__ MbNoiseFrame frame_gather(const MbDevPlan &P, const Scratch &sc, float noise_sigma) {
+    MbNoiseFrame NF;
+    NF.sigma = noise_sigma;
+    NF.q0 = NF.q4 = NF.sum_u = NF.sum_dl = NF.total = NF.sharp = 0.f;
+    if (noise_sigma >= 0.f) {
         NF.q0 = sc.noise_q[0];
         NF.q4 = sc.noise_q[1];
-        NF.sum_u = 0.f;
         for (int b = 0; b < P.nb; b++) NF.sum_u += sc.noise_u[b];
-        NF.sum_dl = 0.f;
         for (int f = 0; f < P.nf; f++) NF.sum_dl += sc.noise_dl[f];
         NF.total = sc.noise_total;
         NF.sharp = sc.noise_sharp;
-        // (a frame rescaled by 2^kscale lies outside the range the bounds were made for: redo it)
-        if (kscale != 0 || mb_noise_needs_exact(P, P.mask, S, MO, NF)) T.fix_list[atomicAdd(T.fix_count, 1)] = (int)g;
     }
+    return NF;
+}
+__device__ __forceinline__ void frame_finish(const MbDevPlan &P, const MbClipTable &T, const mb_outputs &O, int64_t g,
+                                             const MbFrameSums &S, const MbNoiseFrame &NF, int kscale) {
+    MbMoments MO;
+    mb_store_scalars(P, O, g, S, &MO);
+    // (a frame rescaled by 2^kscale lies outside the range the bounds were made for: redo it)
+    if (NF.sigma >= 0.f && T.fix_count != nullptr && (kscale != 0 || mb_noise_needs_exact(P, P.mask, S, MO, NF)))
+        T.fix_list[atomicAdd(T.fix_count, 1)] = (int)g;
 }
 
 template <bool EXACT>
@@ -659,8 +665,10 @@ mb_generic_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ M
             frame_epilogue<EXACT>(P, O, g, S, acc, amp, sc, adapt ? noise_sigma : 0.f);
         }
         if (adapt) block_sync();  // (the epilogue's bounds are read by the one thread below)
-        if (tid == kScalarThread) frame_finish(P, T, O, g, S, sc, adapt ? noise_sigma : -1.f, (adapt && acc_cf_missing(noise_sigma)) ? 1 : kscale);
+        MbNoiseFrame NF;
+        if (tid == kScalarThread) NF = frame_gather(P, sc, adapt ? noise_sigma : -1.f);
         block_sync();  // smem reused by the next frame
+        if (tid == kScalarThread) frame_finish(P, T, O, g, S, NF, (adapt && acc_cf_missing(noise_sigma)) ? 1 : kscale);
     }
 }
 
@@ -1012,8 +1020,10 @@ mb_big32768_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
             frame_epilogue<false>(P, O, g, S, acc, B.amp, sc, adapt ? noise_sigma : 0.f);
         }
         if (adapt) block_sync();
-        if (tid == kScalarThread) frame_finish(P, T, O, g, S, sc, adapt ? noise_sigma : -1.f, (adapt && acc_cf_missing(noise_sigma)) ? 1 : kscale);
+        MbNoiseFrame NF;
+        if (tid == kScalarThread) NF = frame_gather(P, sc, adapt ? noise_sigma : -1.f);
         block_sync();  // smem reused by the next frame
+        if (tid == kScalarThread) frame_finish(P, T, O, g, S, NF, (adapt && acc_cf_missing(noise_sigma)) ? 1 : kscale);
     }
 }
 #endif  // MB_GENERIC_THREADS == 64 .. 512

@@ -480,7 +480,7 @@ mb_warp2048_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
                     // discrete output); q = 1..4 become the spectral moments (src/utils.js:1-11) after the
                     // shift to k = 32 lane + i below.
                     double ta = 0, t1 = 0, t2 = 0, t3 = 0, t4 = 0;
-                    float qn = 0.f;  // sum min(1 / a, 1 / (theta sigma))^2 over the lane's bins (mb_adaptive.cuh: q(a) / (theta sigma)^2)
+                    float qn = 0.f, q_lane = 0.f, q4_lane = 0.f;  // sum of q(a) over the lane's looked-at bins (mb_adaptive.cuh)
                     uint32_t paddr = smem_u32(piece + (slot_base + lane));
 #pragma unroll
                     for (int i = 0; i < 32; i++) {
@@ -539,10 +539,8 @@ mb_warp2048_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
                         }
                         // Q_0 and Q_4 of mb_adaptive.cuh (k := the last bin of the lane's block)
                         const float ql = 6.4f * qn,  /* (4: every fourth bin was looked at; 1.6: the exponent trick's worst case, squared) */ k4 = (float)(32 * lane + 31) * (float)(32 * lane + 31);
-                        if (kNoise) {
-                            const float q04 = mb_warp_sum2(ql, ql * (k4 * k4), lane);  // lanes < 16: Q_0, the others: Q_4
-                            if ((lane & 15) == 0) stash[18 + (lane >> 4)][j] = q04;
-                        }
+                        q_lane = ql;
+                        q4_lane = ql * (k4 * k4);
                     }
                     if (want_rolloff) {
                         // spectralRolloff.js: the largest m with sum_{k<m} a[k] <= 0.99 sum a.  Lane totals are
@@ -637,9 +635,9 @@ mb_warp2048_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
                         acc += __shfl_down_sync(0xffffffffu, acc, MB_NUM_MFCC);
                         if (lane < MB_NUM_MFCC) O.mfcc[g * MB_NUM_MFCC + lane] = acc * (1.0f / (float)MB_NUM_MFCC);
                     }
-                    if (kNoise && want_pieces) {
-                        const float nb2 = mb_warp_sum2(nu_lane, ndl_lane, lane);  // lanes < 16: the bands' bound, the others: the filters'
-                        if ((lane & 15) == 0) stash[20 + (lane >> 4)][j] = nb2;
+                    if (kNoise) {  // Q_0, Q_4, the bands' bound, the filters' bound: one reduction, lanes 0 / 8 / 16 / 24 hold them
+                        const float t4 = mb_warp_sum4(q_lane, q4_lane, nu_lane, ndl_lane, lane);
+                        if ((lane & 7) == 0) stash[18 + (lane >> 3)][j] = t4;
                     }
                 }
             }

@@ -38,6 +38,10 @@ constexpr int kP = 32;
 constexpr int kPts = kP * kP;  // complex points per warp per group: F frames x M
 constexpr int kWarps = 16;
 constexpr int kThreads = kWarps * 32;
+#ifndef MB_MF_LOCK_WARPS
+#define MB_MF_LOCK_WARPS 4
+#endif
+constexpr int kLockWarps = MB_MF_LOCK_WARPS;  // warps that step through a group's phases together (see the kernel)
 constexpr int kRow = kP + 1;
 constexpr int kSlotFloats = 2176;  // per warp: >= the 32 x 33 float2 transpose, F (M + 8) float2 spectra, amplitudes + pieces
 constexpr int kAmpStride = 36;
@@ -58,6 +62,7 @@ struct Smem {
     int mel_edge[MB_NUM_MEL_FILTERS + 2];
     short piece_edge[kMaxPieces];
     float noise_c[3][32];  // mb_adaptive.cuh: band_c[b], mel_c1[f], mel_c2[f]
+    float sig[kWarps][8];  // rms rounding error of one spectrum bin, per frame of the warp's current group
     short seg_ptr[MB_MF_MAX_SEGMENTS + 1];
     unsigned short seg_items[MB_MF_MAX_ITEMS];
     unsigned long long bar[kWarps];
@@ -181,11 +186,30 @@ mb_warpmf_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ Mb
     const int64_t warp_global = (int64_t)blockIdx.x * kWarps + warp;
     const int64_t warp_stride = (int64_t)gridDim.x * kWarps;
 
-    for (int64_t ch = warp_global; ch < total_chunks; ch += warp_stride) {
+    // Lock-step phases.  A group's code is ~8000 straight-line instructions (~125 KB): sixteen warps each somewhere
+    // else in it cycle through more than the SM's instruction cache holds, and the kernel then starves on instruction
+    // fetch (ncu: 28 % of the stall samples "no instruction" once the adaptive statistics had added 6 % of code;
+    // profiles/README.md, round 2).  Warps therefore march in groups of kLockWarps -- one warp per scheduler -- that
+    // meet at a named barrier after every phase (load + time domain, pass A, pass B, split, blocked sums; the band
+    // loops share the next group's first phase), so that at most 16 / kLockWarps phases are resident at a time.  The
+    // groups drift against each other as before and keep hiding each other's memory and barrier waits.  Trip counts
+    // are uniform per CTA; a warp without work just keeps the barrier count.
+    const int n_phase_bars = 1 + (want_spectrum ? 3 + (want_blocked ? 1 : 0) : 0);
+    auto phase_sync = [&]() {
+        __syncwarp();
+        asm volatile("bar.sync %0, %1;" ::"r"(1 + warp / kLockWarps), "n"(32 * kLockWarps) : "memory");
+    };
+    (void)warp_global;
+    for (int64_t base = (int64_t)blockIdx.x * kWarps; base < total_chunks; base += warp_stride) {
+        const int64_t ch = base + warp;
         const int64_t g0 = ch * kChunk;
-        const int nfc = (int)min((int64_t)kChunk, T.total_frames - g0);
+        const int nfc = ch < total_chunks ? (int)min((int64_t)kChunk, T.total_frames - g0) : 0;
 
-        for (int j = 0; j < nfc; j += kF) {
+        for (int j = 0; j < kChunk; j += kF) {
+            if (j >= nfc) {
+                for (int b = 0; b < n_phase_bars; b++) phase_sync();
+                continue;
+            }
             const int64_t g = g0 + j;             // first frame of the group
             const int nfg = min(kF, nfc - j);     // valid frames in it
             // ---- where the frames start (a short group repeats its last frame)
@@ -354,11 +378,13 @@ mb_warpmf_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ Mb
 
             __syncwarp();
             // mb_adaptive.cuh: rms rounding error of one spectrum bin of frame f of the group, in the frame's own units
-            auto sigma_of = [&](int f) {
-                const int col = min(j + f, kChunk - 1);
-                return mb_noise_sigma(stash[0][min(j + min(f, nfg - 1), kChunk - 1)], 1.0f / (float)kN) *
-                       ldexpf(1.f, -__float_as_int(stash[17][col]));
-            };
+            if (kNoise && lane < kF) {
+                const int col = min(j + min(lane, nfg - 1), kChunk - 1);
+                S.sig[warp][lane] = mb_noise_sigma(stash[0][col], 1.0f / (float)kN) * ldexpf(1.f, -__float_as_int(stash[17][min(j + lane, kChunk - 1)]));
+            }
+            __syncwarp();
+            auto sigma_of = [&](int f) { return S.sig[warp][f]; };
+            phase_sync();
             if (want_spectrum) {
                 // ---- 3. pass A: F FFTs of A points per lane; twiddle; transpose
                 fft_frames<kA>(v, std::make_integer_sequence<int, kF>{});
@@ -375,7 +401,7 @@ mb_warpmf_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ Mb
                     }
                     slot2[c * kRow + lane] = y;
                 }
-                __syncwarp();
+                phase_sync();
                 // ---- pass B: one 32-point FFT per lane (row lp of frame lf) -> X[lp + A q] in v[brev5(q)]
 #pragma unroll
                 for (int b = 0; b < 32; b++) v[b] = slot2[lane * kRow + b];
@@ -387,7 +413,7 @@ mb_warpmf_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ Mb
                     for (int q = 0; q < 32; q++) xf[kA * q] = v[brev5(q)];
                     if (lp == 0) slot2[lf * kMs + kM] = v[0];  // X[M] := X[0]
                 }
-                __syncwarp();
+                phase_sync();
 
                 // ---- 4. real-FFT split over 32 rows of 32 bins (A rows per frame); spectra out
                 float av[32];
@@ -478,6 +504,7 @@ mb_warpmf_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ Mb
                     }
                 }
 
+                phase_sync();
                 if (want_blocked) {
                     // ---- 5. blocked layout: lane L = (frame lf, row lp) owns bins [32 lp, 32 lp + 32) of its frame
                     __syncwarp();
@@ -628,79 +655,75 @@ mb_warpmf_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ Mb
                             }
                         }
                     }
-                    __syncwarp();  // pieces visible; the blocked amplitudes are spent and become scratch
-                    float *sp_s = slot;                                  // [24 F] specific loudness (later [26 F]: noise bounds of the mel filters)
-                    float *rise_s = slot + 26 * kF;                      // [27 F] (before that [24 F]: noise bounds of the Bark bands)
-                    float *nu_s = rise_s, *ndl_s = sp_s;
+                    phase_sync();  // pieces visible; the blocked amplitudes are spent and become scratch
+                    float *sp_s = slot;                                  // [24 F] specific loudness
+                    float *rise_s = slot + 24 * kF;                      // [27 F]
                     float *fall_s = rise_s + 27 * kF;                    // [27 F]
                     float *lge_s = fall_s + 27 * kF;                     // [26 F]
+                    // Lane (lf, lp) works on its own frame, as in the blocked layout: bands / segments lp, lp + A, ... .
+                    // The per-frame sums (loudness total, its maximum, the sharpness sum, the noise bounds of
+                    // mb_adaptive.cuh) then stay in registers and close with log2(A) shuffles inside the frame's lanes.
                     if (want_bark) {
-                        for (int it0 = 0; it0 < MB_NUM_BARK_BANDS * kF; it0 += 32) {
-                            const int seg = it0 + lane;
-                            if (seg < MB_NUM_BARK_BANDS * kF) {
-                                const int f = seg / MB_NUM_BARK_BANDS, bnd = seg % MB_NUM_BARK_BANDS;
-                                const int ts = f * MB_WARP_SEGMENTS + bnd;
-                                float bsum = 0.f;
-                                for (int it = S.seg_ptr[ts]; it < S.seg_ptr[ts + 1]; it++) bsum += piece[kPf * S.seg_items[it]];
-                                const float sp = pow023_approx(bsum);
-                                sp_s[seg] = sp;
-                                if (kNoise) nu_s[seg] = mb_noise_band(bsum, sp, S.noise_c[0][bnd], sigma_of(f));
-                                if (mb_has(mask, MB_FEAT_LOUDNESS) && f < nfg) O.loudness_specific[g * MB_NUM_BARK_BANDS + seg] = sp;
-                            }
+                        float total = 0.f, mx = 0.f, sharp = 0.f, nu = 0.f;
+                        for (int bnd = lp; bnd < MB_NUM_BARK_BANDS; bnd += kA) {
+                            const int ts = lf * MB_WARP_SEGMENTS + bnd;
+                            float bsum = 0.f;
+                            for (int it = S.seg_ptr[ts]; it < S.seg_ptr[ts + 1]; it++) bsum += piece[kPf * S.seg_items[it]];
+                            const float sp = pow023_approx(bsum);
+                            sp_s[lf * MB_NUM_BARK_BANDS + bnd] = sp;
+                            total += sp;
+                            mx = (sp > mx) ? sp : mx;  // NaN never compares greater (perceptualSpread.js:6)
+                            if (bnd >= 1 && bnd <= 15) sharp = fmaf((float)bnd, sp, sharp);
+                            if (kNoise) nu += mb_noise_band(bsum, sp, S.noise_c[0][bnd], sigma_l);
                         }
-                        __syncwarp();
-                        if (lane < nfg) {
-                            float total = 0.f, mx = 0.f, sharp = 0.f, nu = 0.f;
-                            for (int i = 0; i < MB_NUM_BARK_BANDS; i++) {
-                                const float sp = sp_s[lane * MB_NUM_BARK_BANDS + i];
-                                if (kNoise) nu += nu_s[lane * MB_NUM_BARK_BANDS + i];
-                                total += sp;
-                                mx = (sp > mx) ? sp : mx;  // NaN never compares greater (perceptualSpread.js:6)
-                                if (i >= 1 && i <= 15) sharp = fmaf((float)i, sp, sharp);
-                            }
-                            stash[14][j + lane] = total;
-                            stash[15][j + lane] = mx;
-                            stash[16][j + lane] = sharp;
-                            stash[20][j + lane] = nu;
+#pragma unroll
+                        for (int o = kA / 2; o > 0; o >>= 1) {
+                            total += __shfl_xor_sync(0xffffffffu, total, o);
+                            sharp += __shfl_xor_sync(0xffffffffu, sharp, o);
+                            nu += __shfl_xor_sync(0xffffffffu, nu, o);
+                            const float other = __shfl_xor_sync(0xffffffffu, mx, o);
+                            mx = (other > mx) ? other : mx;
                         }
-                        __syncwarp();  // (nu_s shares its floats with rise_s)
+                        if (lp == 0 && lf < nfg) {
+                            stash[14][j + lf] = total;
+                            stash[15][j + lf] = mx;
+                            stash[16][j + lf] = sharp;
+                            if (kNoise) stash[20][j + lf] = nu;
+                        }
+                        if (mb_has(mask, MB_FEAT_LOUDNESS)) {
+                            __syncwarp();
+                            for (int idx = lane; idx < MB_NUM_BARK_BANDS * nfg; idx += 32) O.loudness_specific[g * MB_NUM_BARK_BANDS + idx] = sp_s[idx];
+                        }
                     }
                     if (want_mfcc) {
-                        for (int it0 = 0; it0 < (MB_NUM_MEL_FILTERS + 1) * kF; it0 += 32) {
-                            const int seg = it0 + lane;
-                            if (seg < (MB_NUM_MEL_FILTERS + 1) * kF) {
-                                const int f = seg / (MB_NUM_MEL_FILTERS + 1), s = seg % (MB_NUM_MEL_FILTERS + 1);
-                                const int ts = f * MB_WARP_SEGMENTS + MB_NUM_BARK_BANDS + s, e0 = S.mel_edge[s];
-                                const float inv = S.mel_inv[s];
-                                float rise = 0.f, fall = 0.f;
-                                for (int it = S.seg_ptr[ts]; it < S.seg_ptr[ts + 1]; it++) {
-                                    const int pc = S.seg_items[it];
-                                    const float pp = piece[kPf * pc + 1], pz = piece[kPf * pc + 2];
-                                    float up = fmaf((float)((int)S.piece_edge[pc] - e0), pp, pz) * inv;
-                                    up = (up < 0.f) ? 0.f : up;
-                                    rise += up;
-                                    fall += fmaxf(pp - up, 0.f);
-                                }
-                                rise_s[seg] = rise;
-                                fall_s[seg] = fall;
+                        for (int sg = lp; sg < MB_NUM_MEL_FILTERS + 1; sg += kA) {
+                            const int ts = lf * MB_WARP_SEGMENTS + MB_NUM_BARK_BANDS + sg, e0 = S.mel_edge[sg];
+                            const float inv = S.mel_inv[sg];
+                            float rise = 0.f, fall = 0.f;
+                            for (int it = S.seg_ptr[ts]; it < S.seg_ptr[ts + 1]; it++) {
+                                const int pc = S.seg_items[it];
+                                const float pp = piece[kPf * pc + 1], pz = piece[kPf * pc + 2];
+                                float up = fmaf((float)((int)S.piece_edge[pc] - e0), pp, pz) * inv;
+                                up = (up < 0.f) ? 0.f : up;
+                                rise += up;
+                                fall += fmaxf(pp - up, 0.f);
                             }
+                            rise_s[lf * (MB_NUM_MEL_FILTERS + 1) + sg] = rise;
+                            fall_s[lf * (MB_NUM_MEL_FILTERS + 1) + sg] = fall;
                         }
                         __syncwarp();
-                        for (int it0 = 0; it0 < MB_NUM_MEL_FILTERS * kF; it0 += 32) {
-                            const int idx = it0 + lane;
-                            if (idx < MB_NUM_MEL_FILTERS * kF) {
-                                const int f = idx / MB_NUM_MEL_FILTERS, m = idx % MB_NUM_MEL_FILTERS;
-                                const float melE = rise_s[f * (MB_NUM_MEL_FILTERS + 1) + m] + fall_s[f * (MB_NUM_MEL_FILTERS + 1) + m + 1];
-                                lge_s[idx] = ln_approx(melE);
-                                if (kNoise) ndl_s[idx] = mb_noise_mel(melE, S.noise_c[1][m], S.noise_c[2][m], sigma_of(f));
-                            }
+                        float ndl = 0.f;
+                        for (int m = lp; m < MB_NUM_MEL_FILTERS; m += kA) {
+                            const float melE = rise_s[lf * (MB_NUM_MEL_FILTERS + 1) + m] + fall_s[lf * (MB_NUM_MEL_FILTERS + 1) + m + 1];
+                            lge_s[lf * MB_NUM_MEL_FILTERS + m] = ln_approx(melE);
+                            if (kNoise) ndl += mb_noise_mel(melE, S.noise_c[1][m], S.noise_c[2][m], sigma_l);
+                        }
+                        if (kNoise) {
+#pragma unroll
+                            for (int o = kA / 2; o > 0; o >>= 1) ndl += __shfl_xor_sync(0xffffffffu, ndl, o);
+                            if (lp == 0 && lf < nfg) stash[21][j + lf] = ndl;
                         }
                         __syncwarp();
-                        if (kNoise && lane < nfg) {
-                            float ndl = 0.f;
-                            for (int m = 0; m < MB_NUM_MEL_FILTERS; m++) ndl += ndl_s[lane * MB_NUM_MEL_FILTERS + m];
-                            stash[21][j + lane] = ndl;
-                        }
                         for (int it0 = 0; it0 < MB_NUM_MFCC * kF; it0 += 32) {
                             const int idx = it0 + lane;
                             if (idx < MB_NUM_MFCC * kF) {

@@ -34,26 +34,25 @@ constexpr float kMbNoiseHalfTol = 5e-4f;  // half of the 1e-3 parity tolerance
 // sigma of a frame from its raw energy (the caller passes the energy in the units its amplitudes are in)
 __device__ __forceinline__ float mb_noise_sigma(float energy, float inv_N) { return kMbNoiseRel * sqrtf(energy * inv_N); }
 
-// One Bark band (loudness.js:55-63): how far specific[b] = (sum a)^0.23 can move.  cB = 2 n_b + K sqrt(n_b) (plan
-// constant, 0 for an empty band).  Returns the bound u; +inf when it alone breaks the tolerance (or is NaN).
+// One Bark band (loudness.js:55-63): how far specific[b] = (sum a)^0.23 can move when the sum moves by e = cB sigma,
+// cB = 2 n_b + K sqrt(n_b) (plan constant, 0 for an empty band): 0.23 sp (e / sum)(1 + e / sum) x 2 while e < sum / 2
+// (the x^0.23 curve's own bound there is 0.23 (e/sum) / (1 - e/sum)^0.77 <= 0.39 (e/sum)), "out" (+inf) beyond, or when it
+// alone breaks the tolerance, or on a NaN.  Branch-free: one reciprocal, a handful of multiplies and selects.
 __device__ __forceinline__ float mb_noise_band(float bsum, float sp, float cB, float sigma) {
-    const float eB = cB * sigma;
-    float lu, ll, up, lo;
-    asm("lg2.approx.f32 %0, %1;" : "=f"(lu) : "f"(bsum + eB));
-    asm("ex2.approx.f32 %0, %1;" : "=f"(up) : "f"(0.23f * lu));
-    asm("lg2.approx.f32 %0, %1;" : "=f"(ll) : "f"(fmaxf(bsum - eB, 0.f)));
-    asm("ex2.approx.f32 %0, %1;" : "=f"(lo) : "f"(0.23f * ll));
-    const float u = up - lo;
-    return (u <= kMbNoiseHalfTol * fmaxf(1.f, sp)) ? u : INFINITY;  // (NaN: out)
+    const float r = __fdividef(cB * sigma, bsum);             // (0 / 0 = NaN for an empty or silent band: nothing to move)
+    const float u = 0.46f * sp * r * (1.f + r);
+    const bool none = !(cB * sigma > 0.f);
+    const bool ok = (r < 0.5f) && (u <= kMbNoiseHalfTol * fmaxf(1.f, sp));
+    return none ? 0.f : (ok ? u : INFINITY);
 }
 
 // One mel filter (mfcc.js:53-65): how far ln E_f can move.  c1 = 2 K sqrt(W_f / max(W_f, 1)), c2 = 4 W_f with
-// W_f the filter's total weight (0: the filter is empty, -inf in the reference too).
+// W_f the filter's total weight (0: the filter is empty, -inf in the reference too).  Branch-free.
 __device__ __forceinline__ float mb_noise_mel(float E, float c1, float c2, float sigma) {
-    if (c2 == 0.f || sigma == 0.f) return 0.f;
-    const float r2 = sigma * (sigma / E);  // (E == 0: inf)
+    const float r2 = sigma * __fdividef(sigma, E);  // (E == 0: inf)
     const float d = fmaf(c1, sqrtf(r2), c2 * r2);
-    return (d < 0.5f) ? 2.f * d : INFINITY;
+    const bool none = !(c2 * sigma > 0.f);
+    return none ? 0.f : ((d < 0.5f) ? 2.f * d : INFINITY);
 }
 
 struct MbNoiseFrame {
@@ -129,6 +128,19 @@ __device__ __forceinline__ bool mb_noise_needs_exact(const MbDevPlan &P, uint32_
         }
     }
     return bad;
+}
+
+// Sums four floats over the warp with five shuffle steps (the first two fold the four values onto lane bits 4 and 3):
+// lane l returns the total of value (l >> 3) & 3.
+__device__ __forceinline__ float mb_warp_sum4(float a0, float a1, float a2, float a3, int lane) {
+    const bool h16 = lane & 16, h8 = lane & 8;
+    const float b0 = (h16 ? a2 : a0) + __shfl_xor_sync(0xffffffffu, h16 ? a0 : a2, 16);  // a0 | a2
+    const float b1 = (h16 ? a3 : a1) + __shfl_xor_sync(0xffffffffu, h16 ? a1 : a3, 16);  // a1 | a3
+    float c = (h8 ? b1 : b0) + __shfl_xor_sync(0xffffffffu, h8 ? b0 : b1, 8);             // a0, a1 | a2, a3
+    c += __shfl_xor_sync(0xffffffffu, c, 4);
+    c += __shfl_xor_sync(0xffffffffu, c, 2);
+    c += __shfl_xor_sync(0xffffffffu, c, 1);
+    return c;
 }
 
 // Sums two floats over the warp with five shuffle steps: lanes < 16 return the total of a, the others that of b.

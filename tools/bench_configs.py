@@ -43,7 +43,7 @@ def run(name, N, hop, n_clips, clip_len, feats, flags=0, steps=3, pcm16=False):
     ms = e0.elapsed_time(e1) / steps
     bpf = (2 if pcm16 else 4) * hop + 4 * sum(PER.get(f, lambda N: 1)(N) for f in feats)
     fps = nf / (ms * 1e-3)
-    print(json.dumps({"config": name, "kernel": plan.kernel_name, "N": N, "hop": hop, "frames": nf, "ms": round(ms, 3),
+    print(json.dumps({"config": name, "kernel": plan.kernel_name, "N": N, "hop": hop, "frames": nf, "refined": plan.refined_frames, "ms": round(ms, 3),
                       "frames_per_s": round(fps), "alg_bytes_per_frame": bpf, "alg_GBps": round(fps * bpf / 1e9, 1),
                       "hbm_frac_of_measured": round(fps * bpf / 1e9 / 6542.7, 4)}), flush=True)
     plan.close(); del x, outs; torch.cuda.empty_cache()
@@ -84,6 +84,10 @@ if "small" in which:  # the reference's own cadence: back-to-back buffers (hop =
     run("config-3 features (mfcc + moments) N=1024 hop=N", 1024, 1024, 3000, 441000, C3)
     run("full set N=512 hop=N, 3000 clips", 512, 512, 3000, 441000, mb.FEATURES)
     run("full set N=1024 hop=N, 3000 clips", 1024, 1024, 3000, 441000, mb.FEATURES)
+if "smallab" in which:  # what the adaptive second pass costs at the reference's own sizes
+    for N in (256, 512, 1024):
+        run("full set N=%d hop=N, adaptive" % N, N, N, 800, 441000, mb.FEATURES)
+        run("full set N=%d hop=N, MB_FLAG_NO_REFINE" % N, N, N, 800, 441000, mb.FEATURES, flags=_capi.MB_FLAG_NO_REFINE)
 if "c1" in which:  # BASELINE config 1's feature list at the reference's default bufferSize
     run("config-1 features N=512 hop=N, 3000 clips", 512, 512, 3000, 441000, ["rms", "energy", "zcr", "amplitudeSpectrum", "spectralCentroid"])
     run("config-1 features N=512 hop=N/4", 512, 128, 800, 441000, ["rms", "energy", "zcr", "amplitudeSpectrum", "spectralCentroid"])
