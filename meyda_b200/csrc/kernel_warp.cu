@@ -51,6 +51,10 @@ constexpr int kN = 2 * kM;         // bufferSize 2048
 #endif
 constexpr int kWarps = MB_WARPS;  // warps per persistent CTA: 128 registers each at 16
 constexpr int kThreads = kWarps * 32;
+#ifndef MB_LOCK_WARPS
+#define MB_LOCK_WARPS 2
+#endif
+constexpr int kLockWarps = MB_LOCK_WARPS;  // warps that step through a frame's phases together (0: free-running); see the kernel
 constexpr int kRow = kP + 1;                  // float2 stride of a transpose row
 constexpr int kSlotFloats = 2 * kP * kRow;    // 2112 floats = 8448 B per warp
 constexpr int kAmpStride = 36;                // floats per lane in the blocked amplitude layout
@@ -179,11 +183,29 @@ mb_warp2048_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
     const int64_t warp_global = (int64_t)blockIdx.x * kWarps + warp;
     const int64_t warp_stride = (int64_t)gridDim.x * kWarps;
 
-    for (int64_t ch = warp_global; ch < total_chunks; ch += warp_stride) {
+    // Lock-step phases (as in kernel_warp_mf.cu): warps march in groups of kLockWarps that meet at a named barrier
+    // after every phase (load + pass 1, the two FFT passes, the split, the blocked sums), so that fewer distinct
+    // stretches of the ~70 KB of straight-line code compete for the instruction cache.  PAIRS here: this kernel waits
+    // on HBM as well, and warps that wait for their frames together lose what the shared instruction stream gains --
+    // one box, round 2: free-running 129.3 M frames/s (full set) / 238.5 M (mfcc + moments), pairs 129.6 / 243.5,
+    // groups of four 125.6, groups of eight 119 / 213.  0 = free-running.
+    const int n_phase_bars = 1 + (want_spectrum ? 2 + (want_blocked ? 2 : 0) : 0);
+    auto phase_sync = [&]() {
+        __syncwarp();
+        if constexpr (kLockWarps > 0)
+            asm volatile("bar.sync %0, %1;" ::"r"(1 + warp / (kLockWarps > 0 ? kLockWarps : 1)), "n"(32 * (kLockWarps > 0 ? kLockWarps : 1)) : "memory");
+    };
+    (void)warp_global;
+    for (int64_t base = (int64_t)blockIdx.x * kWarps; base < total_chunks; base += warp_stride) {
+        const int64_t ch = base + warp;
         const int64_t g0 = ch * kChunk;
-        const int nfc = (int)min((int64_t)kChunk, T.total_frames - g0);
+        const int nfc = ch < total_chunks ? (int)min((int64_t)kChunk, T.total_frames - g0) : 0;
 
-        for (int j = 0; j < nfc; j++) {
+        for (int j = 0; j < (kLockWarps > 0 ? kChunk : nfc); j++) {
+            if (j >= nfc) {
+                for (int b = 0; b < n_phase_bars; b++) phase_sync();
+                continue;
+            }
             const int64_t g = g0 + j;
             // ---- which clip (frames ascend, so mostly the cached one or its successor)
             if (g >= clip_f1 || g < clip_f0) {
@@ -338,6 +360,7 @@ mb_warp2048_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
                 stash[1][j] = __int_as_float(zcr);
                 stash[17][j] = __int_as_float(kscale);
             }
+            phase_sync();
 
             if (want_spectrum) {
                 // Both FFT passes run through ONE copy of the 32-point register FFT (a two-trip loop, not
@@ -371,7 +394,7 @@ mb_warp2048_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
                         for (int d = 0; d < 32; d++) slot2[lane + 32 * d] = v[brev5(d)];
                         if (lane == 0) slot2[kM] = v[0];  // X[M] := X[0], so that X[M-k] is slot2[kM - k] for every k
                     }
-                    __syncwarp();
+                    phase_sync();
                 }
 
                 float av[32];
@@ -451,7 +474,7 @@ mb_warp2048_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
 
                 if (want_blocked) {
                     // ---- 4. amplitudes into the blocked layout: lane L gets bins [32 L, 32 L + 32)
-                    __syncwarp();  // every lane has fetched its X[M-k]
+                    phase_sync();  // every lane has fetched its X[M-k]
 #pragma unroll
                     for (int d = 0; d < 32; d++) slot[lane + kAmpStride * d] = av[d];
                     __syncwarp();
@@ -575,7 +598,7 @@ mb_warp2048_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
                             if (want_moments) stash_put_d(stash, 2, j, total_a);
                         }
                     }
-                    __syncwarp();
+                    phase_sync();
                     float nu_lane = 0.f, ndl_lane = 0.f;  // this lane's share of the noise bounds (mb_adaptive.cuh)
                     // ---- lanes finish the bands: loudness.js:55-63, perceptual*.js
                     if (want_bark) {

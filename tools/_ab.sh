@@ -1,3 +1,4 @@
-python -m pytest tests -m gpu -q -x -p no:cacheprovider 2>&1 | tail -3
-echo "== main (lock 4)"; python tools/bench_configs.py smallab c3 c1 2>&1 | python tools/_fmt.py
-for v in MB_NO_NOISE_STATS; do echo "== $v"; MEYDA_B200_LIB=$PWD/meyda_b200/_lib/variants/lib_$v.so python tools/bench_configs.py smallab c3 c1 2>&1 | python tools/_fmt.py; done
+for r in 1 2; do
+echo "== main (lock 0)"; python tools/bench_configs.py c3 pcm 2>&1 | python tools/_fmt.py
+for v in MB_LOCK_WARPS=2 MB_LOCK_WARPS=4 MB_LOCK_WARPS=8; do echo "== $v"; MEYDA_B200_LIB=$PWD/meyda_b200/_lib/variants/lib_$v.so python tools/bench_configs.py c3 pcm 2>&1 | python tools/_fmt.py; done
+done
