@@ -389,6 +389,9 @@ def main():
     ap.add_argument("--generic", action="store_true", help="force the generic kernel")
     ap.add_argument("--no-refine", action="store_true", help="float32 FFT only: no adaptive exact second pass (A/B)")
     args = ap.parse_args()
+    if os.environ.get("MEYDA_B200_HOST_THREADS"):  # (tuning runs: tools/gpu.sh; the default is the library's own choice)
+        import meyda_b200 as _mb
+        _mb.set_host_threads(int(os.environ["MEYDA_B200_HOST_THREADS"]))
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
         return reference_arm(args)

@@ -287,6 +287,11 @@ mb_status mb_wav_parse(const void *file_bytes, int64_t n_bytes, mb_wav_info *inf
  * may be NULL. */
 mb_status mb_measure_peaks(int device, double *fp32_ffma_tflops, double *fp64_dfma_tflops);
 
+/* Host threads that a host-memory call (MB_MEM_HOST) uses to write the rows the device does not produce: `buffer`
+ * (the caller's own samples, framed) and powerSpectrum (amplitudeSpectrum squared).  Process-wide; 0 (the default)
+ * picks min(8, cores / 2).  Calls already running keep their count. */
+mb_status mb_set_host_threads(int n);
+
 /* Number of kernel launches issued by this plan so far (bench evidence). */
 int64_t mb_plan_launch_count(const mb_plan *plan);
 /* How many frames of the plan's last extract call (or stream push) were redone with the exact-FFT arithmetic

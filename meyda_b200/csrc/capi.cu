@@ -9,6 +9,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
 #include <condition_variable>
 #include <deque>
 #include <functional>
@@ -137,6 +138,7 @@ struct mb_plan {
     cudaEvent_t tab_event = nullptr;
     bool tab_event_pending = false;
     Slot slots[2];
+    std::vector<cudaEvent_t> landed;  // host-memory calls: chunk i's amplitude rows have arrived (kept across calls)
     // adaptive exactness (mb_adaptive.cuh): frames the float32 kernels flag are redone by the exact-FFT kernel
     bool adaptive = false;
     MbDevPlan dev_fix{};       // the plan as the exact kernel sees it: spectral features only
@@ -212,6 +214,12 @@ inline void stream_fence() {}
 
 // A few host threads that finish what needs no device: the `buffer` rows (the caller's own samples, framed) and the
 // powerSpectrum rows (amplitude squared, float32: the same single rounding the kernels apply) of a host-memory call.
+// Work may be gated on a CUDA event (rows that a device-to-host copy is still delivering): a worker takes a gated piece
+// as soon as its event has completed, fills the wait with ungated pieces, and only blocks on an event when nothing
+// else is left.
+constexpr unsigned kDefaultHostThreads = 8;
+std::atomic<int> g_host_threads{0};  // mb_set_host_threads (0: min(kDefaultHostThreads, cores / 2))
+
 class HostWorkers {
 public:
     explicit HostWorkers(int n) {
@@ -225,37 +233,52 @@ public:
         cv_.notify_all();
         for (auto &t : threads_) t.join();  // (drains the queue first)
     }
-    void post(std::function<void()> f) {
+    // Cut [g0, g1) into pieces and post f(piece begin, piece end) for each; `after` (optional): the event the pieces
+    // wait for.  Gated pieces are posted in the order their events complete (one stream after the other, chunk by chunk).
+    void post_range(int64_t g0, int64_t g1, int64_t grain, std::function<void(int64_t, int64_t)> f, cudaEvent_t after = nullptr) {
         {
             std::lock_guard<std::mutex> lk(m_);
-            q_.push_back(std::move(f));
+            for (int64_t a = g0; a < g1; a += grain) {
+                const int64_t b = std::min(g1, a + grain);
+                if (after) gated_.push_back({after, [f, a, b]() { f(a, b); }});
+                else q_.push_back([f, a, b]() { f(a, b); });
+            }
         }
-        cv_.notify_one();
-    }
-    // Cut [g0, g1) into pieces and post f(piece begin, piece end) for each.
-    void post_range(int64_t g0, int64_t g1, int64_t grain, std::function<void(int64_t, int64_t)> f) {
-        for (int64_t a = g0; a < g1; a += grain) {
-            const int64_t b = std::min(g1, a + grain);
-            post([f, a, b]() { f(a, b); });
-        }
+        cv_.notify_all();
     }
 
 private:
+    struct Gated {
+        cudaEvent_t after;
+        std::function<void()> f;
+    };
     void run() {
         for (;;) {
             std::function<void()> f;
+            cudaEvent_t wait_for = nullptr;
             {
                 std::unique_lock<std::mutex> lk(m_);
-                cv_.wait(lk, [this]() { return done_ || !q_.empty(); });
-                if (q_.empty()) return;
-                f = std::move(q_.front());
-                q_.pop_front();
+                cv_.wait(lk, [this]() { return done_ || !q_.empty() || !gated_.empty(); });
+                if (!gated_.empty() && (q_.empty() || cudaEventQuery(gated_.front().after) != cudaErrorNotReady)) {
+                    // (ready, or nothing else to do: then block on it below, outside the lock; an error is left to the
+                    // stream synchronize of the calling thread to report)
+                    if (q_.empty()) wait_for = gated_.front().after;
+                    f = std::move(gated_.front().f);
+                    gated_.pop_front();
+                } else if (!q_.empty()) {
+                    f = std::move(q_.front());
+                    q_.pop_front();
+                } else {
+                    return;  // done_, both queues drained
+                }
             }
+            if (wait_for) (void)cudaEventSynchronize(wait_for);
             f();
         }
     }
     std::vector<std::thread> threads_;
     std::deque<std::function<void()>> q_;
+    std::deque<Gated> gated_;
     std::mutex m_;
     std::condition_variable cv_;
     bool done_ = false;
@@ -916,6 +939,7 @@ void mb_plan_destroy(mb_plan *p) {
     DeviceGuard guard(p->device);
     if (p->own_stream) cudaStreamSynchronize(p->own_stream);
     for (auto &s : p->slots) free_slot(s);
+    for (cudaEvent_t ev : p->landed) cudaEventDestroy(ev);
     cudaFree(p->d_window);
     cudaFree(p->d_dct);
     cudaFree(p->d_mel_inv);
@@ -1090,7 +1114,8 @@ static mb_status extract_host_impl(mb_plan *p, const void *samples, const int64_
     int64_t total_frames_call = 0;
     for (int64_t i = 0; i < n_clips; i++) total_frames_call += mb_num_frames(clip_len[i], N, hop);
     const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
-    const int n_workers = (host_buffer || host_power) ? (int)std::min<int64_t>(std::max<int64_t>(1, total_frames_call / 2048), std::min(8u, std::max(1u, hw / 2))) : 0;
+    const int want_workers = g_host_threads.load() > 0 ? g_host_threads.load() : (int)std::min(kDefaultHostThreads, std::max(1u, hw / 2));
+    const int n_workers = (host_buffer || host_power) ? (int)std::min<int64_t>(std::max<int64_t>(1, total_frames_call / 2048), want_workers) : 0;
     HostWorkers workers(n_workers);  // (its destructor, on every return path, waits for the posted work: it writes into the caller's arrays)
     if (host_buffer) {
         auto fstart = std::make_shared<std::vector<int64_t>>(n_clips + 1, 0);
@@ -1107,8 +1132,8 @@ static mb_status extract_host_impl(mb_plan *p, const void *samples, const int64_
             stream_fence();
         });
     }
-    // frames [g0, g1) of the amplitude rows have landed: square them into the power rows
-    auto post_power = [&](int64_t g0, int64_t g1) {
+    // frames [g0, g1) of the amplitude rows land when `landed` completes: square them into the power rows then
+    auto post_power = [&](int64_t g0, int64_t g1, cudaEvent_t landed) {
         if (!host_power || g1 <= g0) return;
         const float *amp = out->amplitude_spectrum;
         float *pw = out->power_spectrum;
@@ -1116,9 +1141,8 @@ static mb_status extract_host_impl(mb_plan *p, const void *samples, const int64_
         workers.post_range(g0, g1, 1024, [=](int64_t a, int64_t b) {
             square_rows_stream(pw + a * M, amp + a * M, (b - a) * M);
             stream_fence();
-        });
+        }, landed);
     };
-    int64_t slot_g0[2] = {0, 0}, slot_g1[2] = {0, 0};  // the frame range each slot's copies in flight will deliver
     const int64_t dev_bpf = p->bytes_per_frame - (host_buffer ? 4 * (int64_t)N : 0) - (host_power ? 2 * (int64_t)N : 0);  // bytes per frame the device produces
     struct VClip { int64_t off, frames; };
     std::vector<VClip> v;
@@ -1154,9 +1178,6 @@ static mb_status extract_host_impl(mb_plan *p, const void *samples, const int64_
         if (!s.stream) MB_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
         // the slot's previous chunk (two chunks ago) must have drained before its buffers are reused
         MB_CUDA(cudaStreamSynchronize(s.stream));
-        post_power(slot_g0[chunk_idx & 1], slot_g1[chunk_idx & 1]);
-        slot_g0[chunk_idx & 1] = g_done;
-        slot_g1[chunk_idx & 1] = g_done + frames;
         const size_t span = (size_t)(hi - lo);
         if (s.samples_cap < span * frame_bytes) {
             cudaFree(s.d_samples);
@@ -1210,12 +1231,26 @@ static mb_status extract_host_impl(mb_plan *p, const void *samples, const int64_
             }
             MB_CUDA(cudaMemcpyAsync(s.h_fix + s.h_fix_used++, s.d_fix, sizeof(int), cudaMemcpyDeviceToHost, s.stream));
         }
-        for (int i = 0; i < kNumFields; i++) {
-            if (!mb_has(p->mask & ~drop_mask, kFields[i].feature)) continue;
-            const size_t per = (size_t)field_elems(kFields[i], p->dev) * 4;
-            MB_CUDA(cudaMemcpyAsync((char *)field_ptr(*out, kFields[i]) + (size_t)g_done * per,
-                                    field_ptr(d_out, kFields[i]), (size_t)frames * per, cudaMemcpyDeviceToHost,
-                                    s.stream));
+        // the amplitude rows first when the host squares them: that work then overlaps the rest of the chunk's copies
+        for (int pass = host_power ? 0 : 1; pass < 2; pass++) {
+            for (int i = 0; i < kNumFields; i++) {
+                if (!mb_has(p->mask & ~drop_mask, kFields[i].feature)) continue;
+                const bool is_amp = kFields[i].feature == MB_FEAT_AMPLITUDE_SPECTRUM;
+                if (host_power && is_amp != (pass == 0)) continue;
+                const size_t per = (size_t)field_elems(kFields[i], p->dev) * 4;
+                MB_CUDA(cudaMemcpyAsync((char *)field_ptr(*out, kFields[i]) + (size_t)g_done * per,
+                                        field_ptr(d_out, kFields[i]), (size_t)frames * per, cudaMemcpyDeviceToHost,
+                                        s.stream));
+            }
+            if (pass == 0) {  // (one event per chunk of the call: a worker may still be waiting on an earlier one)
+                if ((size_t)chunk_idx >= p->landed.size()) {
+                    cudaEvent_t ev = nullptr;
+                    MB_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+                    p->landed.push_back(ev);
+                }
+                MB_CUDA(cudaEventRecord(p->landed[chunk_idx], s.stream));
+                post_power(g_done, g_done + frames, p->landed[chunk_idx]);
+            }
         }
         g_done += frames;
         chunk_idx++;
@@ -1223,8 +1258,6 @@ static mb_status extract_host_impl(mb_plan *p, const void *samples, const int64_
     for (int k = 0; k < 2; k++) {
         Slot &s = p->slots[k];
         if (s.stream) MB_CUDA(cudaStreamSynchronize(s.stream));
-        post_power(slot_g0[k], slot_g1[k]);
-        slot_g0[k] = slot_g1[k] = 0;
         for (size_t i = 0; i < s.h_fix_used; i++) p->refined_frames += s.h_fix[i];
         s.h_fix_used = 0;
     }
@@ -1374,6 +1407,12 @@ mb_status mb_extract_multi(mb_plan *const *plans, int n_plans, const float *samp
 }
 
 // ---- measured non-tensor arithmetic peaks of a device (the FP32 / FP64 roofline denominators bench.py reports against)
+mb_status mb_set_host_threads(int n) {
+    if (n < 0 || n > 256) return fail(MB_ERR_INVALID_ARG, "host thread count %d out of range [0, 256]", n);
+    g_host_threads.store(n);
+    return MB_OK;
+}
+
 mb_status mb_measure_peaks(int device, double *fp32_ffma_tflops, double *fp64_dfma_tflops) {
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev)

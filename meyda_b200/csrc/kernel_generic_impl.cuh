@@ -510,8 +510,6 @@ mb_generic_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ M
     const bool want_log = mb_has(mask, MB_FEAT_SPECTRAL_FLATNESS);
     const bool want_time = mask & (MB_FEATURE_BIT(MB_FEAT_RMS) | MB_FEATURE_BIT(MB_FEAT_ENERGY) |
                                    MB_FEATURE_BIT(MB_FEAT_ZCR) | MB_FEATURE_BIT(MB_FEAT_BUFFER));
-    const bool want_bark = mask & (MB_FEATURE_BIT(MB_FEAT_LOUDNESS) | MB_FEATURE_BIT(MB_FEAT_PERCEPTUAL_SPREAD) |
-                                   MB_FEATURE_BIT(MB_FEAT_PERCEPTUAL_SHARPNESS));
     const uint32_t time_only = MB_FEATURE_BIT(MB_FEAT_RMS) | MB_FEATURE_BIT(MB_FEAT_ENERGY) |
                                MB_FEATURE_BIT(MB_FEAT_ZCR) | MB_FEATURE_BIT(MB_FEAT_BUFFER);
     const bool want_spectrum = (mask & ~time_only) != 0;

@@ -96,6 +96,12 @@ def _normalize_clips(clips):
     return data, offsets, lengths
 
 
+def set_host_threads(n: int) -> None:
+    """Host threads a host-memory extract uses for the rows the device does not produce (`buffer`, powerSpectrum);
+    0 = automatic (mb_set_host_threads, include/meyda_b200.h)."""
+    _capi.check(_capi.lib().mb_set_host_threads(int(n)))
+
+
 def pinned_empty(shape, dtype) -> np.ndarray:
     """A numpy array over page-locked host memory (mb_host_alloc); freed with mb_host_free when collected."""
     import weakref
