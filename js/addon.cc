@@ -15,6 +15,7 @@
 //   const out  = native.extractMulti([plan0, plan1, ...], samples, offsets, lengths)   // one plan per device, clip-sharded
 //   const prm  = native.getParams(plan)            // {numBarkBands, numMelFilters, numMfccCoefficients, rolloffFraction}
 //   const n    = native.refinedFrames(plan)        // frames of the last call redone with the exact FFT (adaptive plans)
+//   native.setHostThreads(n)                        // host threads for the rows the device does not produce (0: automatic)
 //   const st   = native.createStream(plan)         // the onaudioprocess cadence (src/meyda.js:69-91)
 //   const out  = native.streamPush(st, block /*Float32Array*/)   // features of the frames this block completes
 //   native.streamReset(st); native.destroyStream(st)
@@ -372,6 +373,18 @@ static napi_value RefinedFrames(napi_env env, napi_callback_info info) {
     return v;
 }
 
+// setHostThreads(n): host threads a host-memory call uses for the `buffer` and powerSpectrum rows (mb_set_host_threads)
+static napi_value SetHostThreads(napi_env env, napi_callback_info info) {
+    size_t argc = 1;
+    napi_value argv[1];
+    NAPI_OK_OR_THROW(env, napi_get_cb_info(env, info, &argc, argv, NULL, NULL));
+    int32_t n = 0;
+    NAPI_OK_OR_THROW(env, napi_get_value_int32(env, argv[0], &n));
+    const mb_status st = mb_set_host_threads(n);
+    if (st != MB_OK) return throw_mb(env, st);
+    return NULL;
+}
+
 // ---- streaming, the reference's actual usage model: one buffer per onaudioprocess event (src/meyda.js:69-91)
 static void stream_finalize(napi_env, void *data, void *) { mb_stream_destroy((mb_stream *)data); }
 
@@ -454,6 +467,7 @@ static napi_value Init(napi_env env, napi_value exports) {
         {"extractMulti", NULL, ExtractMulti, NULL, NULL, NULL, napi_default, NULL},
         {"getParams", NULL, GetParams, NULL, NULL, NULL, napi_default, NULL},
         {"refinedFrames", NULL, RefinedFrames, NULL, NULL, NULL, napi_default, NULL},
+        {"setHostThreads", NULL, SetHostThreads, NULL, NULL, NULL, napi_default, NULL},
         {"createStream", NULL, CreateStream, NULL, NULL, NULL, napi_default, NULL},
         {"streamPush", NULL, StreamPush, NULL, NULL, NULL, napi_default, NULL},
         {"streamReset", NULL, StreamReset, NULL, NULL, NULL, napi_default, NULL},

@@ -232,4 +232,7 @@ class Meyda {
   }
 }
 
-module.exports = {Meyda, extract, extractAsync, extractWav, clearPlans, featureInfo, isPowerOfTwo, FEATURES}
+// Host threads a host-memory extract uses for the rows the device does not produce (`buffer`, powerSpectrum); 0 = automatic.
+function setHostThreads(n) { native.setHostThreads(n | 0) }
+
+module.exports = {Meyda, extract, extractAsync, extractWav, clearPlans, setHostThreads, featureInfo, isPowerOfTwo, FEATURES}

@@ -799,6 +799,7 @@ struct BigSmem {
     float amp[kBigM];
     float2 tw32[32 * 32];             // exp(+2 pi i b c / 1024) at [c*32 + b]
     float2 tw16[kBigR * 32];          // exp(+2 pi i r d / (32 R)) at [r*32 + d]  (R = 16: / 512)
+    float2 tw_step[32];               // exp(+2 pi i j / 64): the split twiddle of bin tid + kThreads j over that of bin tid
 };
 
 __global__ void __launch_bounds__(kThreads, 512 / kThreads)
@@ -832,10 +833,16 @@ mb_big32768_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
         const double ang = 2.0 * 3.14159265358979323846 * (double)((i >> 5) * (i & 31)) / (32.0 * kBigR);
         B.tw16[i] = make_float2((float)cos(ang), (float)sin(ang));
     }
-    float2 tw_own;
+    if (tid < 32) {
+        const double ang = 2.0 * 3.14159265358979323846 * (double)tid / 64.0;
+        B.tw_step[tid] = make_float2((float)cos(ang), (float)sin(ang));
+    }
+    float2 tw_own, tw_split;  // tw_split: exp(+2 pi i tid / N), the real-FFT split twiddle of this thread's first bin
     {
         const double ang = 2.0 * 3.14159265358979323846 * (double)(warp * lane) / (double)M;
         tw_own = make_float2((float)cos(ang), (float)sin(ang));
+        const double ang2 = 2.0 * 3.14159265358979323846 * (double)tid / (double)N;
+        tw_split = make_float2((float)cos(ang2), (float)sin(ang2));
     }
     block_sync();
     float2 *slot = B.area + warp * kBigSlot;  // this warp's transpose slot / sub-spectrum row
@@ -879,7 +886,11 @@ mb_big32768_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
                 B.area[m1 + (m1 >> 4)] = make_float2(__fmul_rn(x.z, w.z), __fmul_rn(x.w, w.w));
             };
             if (src_aligned) {
-#pragma unroll 8
+#ifndef MB_BIG_LOAD_UNROLL
+#define MB_BIG_LOAD_UNROLL 8
+#endif
+                constexpr int kLoadUnroll = MB_BIG_LOAD_UNROLL;
+#pragma unroll kLoadUnroll
                 for (int i = tid; i < N / 4; i += kThreads) take(i, __ldg(src4 + i));
             } else {
 #pragma unroll 2
@@ -987,9 +998,14 @@ mb_big32768_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
             if (adapt && noise_sigma > 0.f && noise_sigma < 1.f / kMbNoiseTheta)
                 acc.cf = 0x7EF311C7 + __float_as_int(kMbNoiseTheta * noise_sigma) - 0x3F800000;
             const float sc_n = P.inv_sqrt_N;
+            // (the split twiddle exp(+2 pi i k / N) of bin k = tid + kThreads j is this thread's own one times a
+            // broadcast table entry, exp(+2 pi i j / 64): the 128 KB global table cost an exposed L2 round trip per
+            // four bins here -- 11 % of the kernel's stall samples, profiles/r02_ncu_big32768_source.txt)
+            static_assert(kBigM / kThreads == 32, "32 bins per thread");
 #pragma unroll 8
-            for (int k = tid; k < M; k += kThreads) {
-                const float2 w = __ldg(&P.twN[k]);  // 128 KB table, L2-resident: issued first, four in flight
+            for (int jj = 0; jj < 32; jj++) {
+                const int k = tid + kThreads * jj;
+                const float2 w = cmul(tw_split, B.tw_step[jj]);
                 const float2 a = B.area[k];
                 const float2 b = B.area[(M - k) & (M - 1)];
                 const float er = 0.5f * (a.x + b.x), ei = 0.5f * (a.y - b.y);

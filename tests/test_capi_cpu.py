@@ -121,3 +121,13 @@ def test_napi_addon_source_type_checks_against_the_c_abi():
     # and the facade carries the reference's class surface (src/meyda.js:229-261)
     for name in ("class Meyda", "setSource (", "start (", "stop (", "get (", "windowingFunction", "featureInfo"):
         assert name in facade, name
+
+
+def test_set_host_threads_validates_its_argument():
+    """mb_set_host_threads touches no device: range-checked, 0 restores the automatic choice."""
+    from meyda_b200 import _capi
+    L = _capi.lib()
+    assert L.mb_set_host_threads(4) == 0
+    assert L.mb_set_host_threads(0) == 0
+    assert L.mb_set_host_threads(-1) != 0
+    assert b"host thread count" in L.mb_last_error()
