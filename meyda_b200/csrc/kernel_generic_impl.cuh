@@ -134,6 +134,29 @@ __device__ __forceinline__ double block_sum(double v, double *scratch /*[kWarps]
     return mb_warp_sum(lane < kWarps ? scratch[lane] : 0.0);
 }
 
+// Eight warp sums at once.  Step o = 16 / 8 / 4 halves the number of values a lane still carries (the lane keeps the
+// ones its bit of o selects and hands the others to its partner), o = 2, 1 are plain butterflies: lane L ends with the
+// total of v[(L >> 2) & 7], added in the same order as mb_warp_sum adds it.
+__device__ __forceinline__ double mb_warp_sum8(const double (&v)[8]) {
+    const int lane = MB_TID & 31;
+    double w[4], x[2];
+    const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const double keep = b4 ? v[i + 4] : v[i], send = b4 ? v[i] : v[i + 4];
+        w[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+        const double keep = b3 ? w[i + 2] : w[i], send = b3 ? w[i] : w[i + 2];
+        x[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+    double y = (b2 ? x[1] : x[0]) + __shfl_xor_sync(0xffffffffu, b2 ? x[0] : x[1], 4);
+    y += __shfl_xor_sync(0xffffffffu, y, 2);
+    y += __shfl_xor_sync(0xffffffffu, y, 1);
+    return y;
+}
+
 __device__ __forceinline__ int block_sum_int(int v, int *scratch /*[kWarps]*/) {
     v = mb_warp_sum(v);
     if constexpr (kWarps == 1) return v;
@@ -188,14 +211,12 @@ struct MomentAcc {
 
 // Everything after the amplitude spectrum: block reductions of the moment partials, rolloff, Bark bands,
 // mel/log/DCT and the per-band outputs.  `amp` holds the N/2 amplitudes of the frame in shared memory.
-#ifdef MB_GENERIC_WARP_LOCAL  // (exact arithmetic only: the float32 kernels' noise bounds are never written there)
-constexpr int kNoiseBands = 1, kNoiseFilters = 1;
-#else
-constexpr int kNoiseBands = MB_MAX_BARK_BANDS, kNoiseFilters = MB_MAX_MEL_FILTERS;
-#endif
 struct Scratch {
-    float noise_u[kNoiseBands];   // mb_adaptive.cuh: per-band / per-filter bounds and what the decision needs
-    float noise_dl[kNoiseFilters];
+    // mb_adaptive.cuh: what the decision needs.  The bands' / filters' bounds are summed as they are made, through
+    // integer atomics in 2^-20 fixed point (order-independent, so the decision is reproducible; each term rounded up
+    // and clipped to 14: "out" stays out) -- two words instead of two arrays: at bufferSize 4096 the arrays' 768 bytes
+    // cost the sixth CTA per SM (21.8 -> 27 M frames/s)
+    int noise_fx[2];
     float noise_q[2], noise_total, noise_sharp;
     double red_d[kWarps];
     float red_f[kWarps];
@@ -206,6 +227,10 @@ struct Scratch {
     float specific[MB_MAX_BARK_BANDS];
     float mel_log[MB_MAX_MEL_FILTERS];
 };
+
+__device__ __forceinline__ void noise_fx_add(int *acc, float u) {  // (a NaN or +inf clips to 14 as well)
+    atomicAdd(acc, (int)fminf(u * 1048576.f, 1.5e7f) + 1);
+}
 
 // noise_sigma > 0: the float32 kernel of an adaptive plan also leaves the mb_adaptive.cuh bounds in `sc`.
 template <bool EXACT>
@@ -225,22 +250,25 @@ __device__ __forceinline__ void frame_epilogue(const MbDevPlan &P, const mb_outp
     const bool want_log = mb_has(mask, MB_FEAT_SPECTRAL_FLATNESS);
     const bool want_bark = mask & (MB_FEATURE_BIT(MB_FEAT_LOUDNESS) | MB_FEATURE_BIT(MB_FEAT_PERCEPTUAL_SPREAD) |
                                    MB_FEATURE_BIT(MB_FEAT_PERCEPTUAL_SHARPNESS));
+    if (tid == 0) sc.noise_fx[0] = sc.noise_fx[1] = 0;  // (read last by frame_gather, in front of the previous frame's final barrier)
     if (want_moments) {
         // the six sums (and the two floor measures of mb_adaptive.cuh) through ONE pair of barriers (each is reduced
         // exactly as block_sum would: same bits)
+        // (mb_warp_sum8: the eight butterflies folded into one -- 9 exchanges instead of 40, same pairings and so the
+        // same bits; the straight-line code of these kernels sits at the edge of the instruction cache, every
+        // hundred instructions count: profiles/README.md, round 2)
         double v[8] = {acc.s0, acc.s1, acc.s2, acc.s3, acc.s4, acc.lg, (double)acc.q0, (double)acc.q4};
-#pragma unroll
-        for (int q = 0; q < 8; q++) v[q] = mb_warp_sum(v[q]);
+        double r = mb_warp_sum8(v);  // lane L: the warp's total of quantity (L >> 2) & 7
         if constexpr (kWarps > 1) {
             block_sync();
-            if (lane == 0) {
-#pragma unroll
-                for (int q = 0; q < 8; q++) sc.red6[q][warp] = v[q];
-            }
+            if ((lane & 3) == 0) sc.red6[lane >> 2][warp] = r;
             block_sync();
 #pragma unroll
-            for (int q = 0; q < 8; q++) v[q] = mb_warp_sum(lane < kWarps ? sc.red6[q][lane] : 0.0);
+            for (int q = 0; q < 8; q++) v[q] = lane < kWarps ? sc.red6[q][lane] : 0.0;
+            r = mb_warp_sum8(v);
         }
+#pragma unroll
+        for (int q = 0; q < 8; q++) v[q] = __shfl_sync(0xffffffffu, r, 4 * q);
         S.s0 = v[0]; S.s1 = v[1]; S.s2 = v[2]; S.s3 = v[3]; S.s4 = v[4];
         if (want_log) S.log2sum = v[5];
         if (!EXACT && tid == 0) {  // (4: every fourth bin was looked at; 1.6: the exponent trick's worst case, squared)
@@ -409,7 +437,7 @@ __device__ __forceinline__ void frame_epilogue(const MbDevPlan &P, const mb_outp
     // ln of the 26 filter energies by 26 threads at once (mfcc.js:63), not one filter at a time
     if (!EXACT && mb_has(mask, MB_FEAT_MFCC)) {
         for (int f = tid; f < nf; f += kThreads) {
-            if (noise_sigma > 0.f) sc.noise_dl[f] = mb_noise_mel(mel_log[f], __ldg(&P.noise->mel_c1[f]), __ldg(&P.noise->mel_c2[f]), noise_sigma);
+            if (noise_sigma > 0.f) noise_fx_add(&sc.noise_fx[1], mb_noise_mel(mel_log[f], __ldg(&P.noise->mel_c1[f]), __ldg(&P.noise->mel_c2[f]), noise_sigma));
             mel_log[f] = (float)log((double)mel_log[f]);
         }
         block_sync();
@@ -419,7 +447,7 @@ __device__ __forceinline__ void frame_epilogue(const MbDevPlan &P, const mb_outp
         for (int b = tid; b < nb; b += kThreads) {
             const float sp = (float)pow(band_sum[b], 0.23);
             specific[b] = sp;
-            if (!EXACT && noise_sigma > 0.f) sc.noise_u[b] = mb_noise_band((float)band_sum[b], sp, __ldg(&P.noise->band_c[b]), noise_sigma);
+            if (!EXACT && noise_sigma > 0.f) noise_fx_add(&sc.noise_fx[0], mb_noise_band((float)band_sum[b], sp, __ldg(&P.noise->band_c[b]), noise_sigma));
             if (mb_has(mask, MB_FEAT_LOUDNESS)) O.loudness_specific[g * nb + b] = sp;
         }
         block_sync();
@@ -468,8 +496,8 @@ __device__ __forceinline__ MbNoiseFrame frame_gather(const MbDevPlan &P, const S
     if (noise_sigma >= 0.f) {
         NF.q0 = sc.noise_q[0];
         NF.q4 = sc.noise_q[1];
-        for (int b = 0; b < P.nb; b++) NF.sum_u += sc.noise_u[b];
-        for (int f = 0; f < P.nf; f++) NF.sum_dl += sc.noise_dl[f];
+        NF.sum_u = (float)sc.noise_fx[0] * (1.0f / 1048576.f);
+        NF.sum_dl = (float)sc.noise_fx[1] * (1.0f / 1048576.f);
         NF.total = sc.noise_total;
         NF.sharp = sc.noise_sharp;
     }
@@ -886,11 +914,7 @@ mb_big32768_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
                 B.area[m1 + (m1 >> 4)] = make_float2(__fmul_rn(x.z, w.z), __fmul_rn(x.w, w.w));
             };
             if (src_aligned) {
-#ifndef MB_BIG_LOAD_UNROLL
-#define MB_BIG_LOAD_UNROLL 8
-#endif
-                constexpr int kLoadUnroll = MB_BIG_LOAD_UNROLL;
-#pragma unroll kLoadUnroll
+#pragma unroll 4
                 for (int i = tid; i < N / 4; i += kThreads) take(i, __ldg(src4 + i));
             } else {
 #pragma unroll 2
@@ -1002,7 +1026,7 @@ mb_big32768_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
             // broadcast table entry, exp(+2 pi i j / 64): the 128 KB global table cost an exposed L2 round trip per
             // four bins here -- 11 % of the kernel's stall samples, profiles/r02_ncu_big32768_source.txt)
             static_assert(kBigM / kThreads == 32, "32 bins per thread");
-#pragma unroll 8
+#pragma unroll 4
             for (int jj = 0; jj < 32; jj++) {
                 const int k = tid + kThreads * jj;
                 const float2 w = cmul(tw_split, B.tw_step[jj]);

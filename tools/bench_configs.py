@@ -63,6 +63,15 @@ if "c5ab" in which:  # the adaptive statistics' cost in the multi-warp-per-frame
     run("config5 N=32768 hop=8192, MB_FLAG_NO_REFINE", 32768, 8192, 256, 2646000, C5, flags=_capi.MB_FLAG_NO_REFINE)
     run("config5 features N=8192, adaptive", 8192, 2048, 256, 2646000, C5)
     run("config5 features N=8192, MB_FLAG_NO_REFINE", 8192, 2048, 256, 2646000, C5, flags=_capi.MB_FLAG_NO_REFINE)
+if "largeab" in which:  # the same, full set, at every large size
+    for N in (4096, 8192, 16384, 32768):
+        run("full set N=%d hop=N/4, adaptive" % N, N, N // 4, 64, 2646000, mb.FEATURES)
+        run("full set N=%d hop=N/4, MB_FLAG_NO_REFINE" % N, N, N // 4, 64, 2646000, mb.FEATURES, flags=_capi.MB_FLAG_NO_REFINE)
+if "bigab" in which:  # (short form of largeab + c5ab for variant runs)
+    for fl, nm in ((0, "adaptive"), (_capi.MB_FLAG_NO_REFINE, "MB_FLAG_NO_REFINE")):
+        run("full set N=4096 hop=N/4, " + nm, 4096, 1024, 64, 2646000, mb.FEATURES, flags=fl)
+        run("full set N=8192 hop=N/4, " + nm, 8192, 2048, 64, 2646000, mb.FEATURES, flags=fl)
+        run("config5 N=32768 hop=8192, " + nm, 32768, 8192, 256, 2646000, C5, flags=fl)
 if "exact" in which:
     run("full set exact-FFT", 2048, 512, 200, 441000, mb.FEATURES, flags=_capi.MB_FLAG_EXACT_FFT)
     run("config3 exact-FFT", 2048, 512, 200, 441000, C3, flags=_capi.MB_FLAG_EXACT_FFT)

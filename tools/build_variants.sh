@@ -11,4 +11,4 @@ build() { # name, extra flags
   nvcc -shared -o $OUT/lib_$name.so $objs -lcudart_static -lpthread -ldl -lrt
   grep -A2 "warp2048_kernelILj262143ELb0" $OUT/${name}_kernel_warp.ptxas.txt | grep -E "registers|spill" | tr '\n' ' '; echo " <- $name"
 }
-for v in "$@"; do case $v in [0-9]*) build w$v -DMB_WARPS=$v;; *) build $v -D$v;; esac; done
+for v in "$@"; do case $v in [0-9]*) build w$v -DMB_WARPS=$v;; *+*) build $v $(echo "-D$v" | sed "s/+/ -D/g");; *) build $v -D$v;; esac; done
