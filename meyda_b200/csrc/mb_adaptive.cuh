@@ -32,7 +32,14 @@ constexpr double kMbNoiseKap = 8.0;     // random-sum safety factor (moment sums
 constexpr float kMbNoiseHalfTol = 5e-4f;  // half of the 1e-3 parity tolerance
 
 // sigma of a frame from its raw energy (the caller passes the energy in the units its amplitudes are in)
-__device__ __forceinline__ float mb_noise_sigma(float energy, float inv_N) { return kMbNoiseRel * sqrtf(energy * inv_N); }
+// (these are bounds with safety factors of 2 .. 32 behind them: one MUFU root, 2^-22 relative, subnormals flushed,
+// instead of the ten-instruction IEEE sequence with its slow path)
+__device__ __forceinline__ float mb_noise_sqrt(float x) {
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float mb_noise_sigma(float energy, float inv_N) { return kMbNoiseRel * mb_noise_sqrt(energy * inv_N); }
 
 // One Bark band (loudness.js:55-63): how far specific[b] = (sum a)^0.23 can move when the sum moves by e = cB sigma,
 // cB = 2 n_b + K sqrt(n_b) (plan constant, 0 for an empty band): 0.23 sp (e / sum)(1 + e / sum) x 2 while e < sum / 2
@@ -50,7 +57,7 @@ __device__ __forceinline__ float mb_noise_band(float bsum, float sp, float cB, f
 // W_f the filter's total weight (0: the filter is empty, -inf in the reference too).  Branch-free.
 __device__ __forceinline__ float mb_noise_mel(float E, float c1, float c2, float sigma) {
     const float r2 = sigma * __fdividef(sigma, E);  // (E == 0: inf)
-    const float d = fmaf(c1, sqrtf(r2), c2 * r2);
+    const float d = fmaf(c1, mb_noise_sqrt(r2), c2 * r2);
     const bool none = !(c2 * sigma > 0.f);
     return none ? 0.f : ((d < 0.5f) ? 2.f * d : INFINITY);
 }
@@ -76,7 +83,7 @@ __device__ __forceinline__ bool mb_noise_needs_exact(const MbDevPlan &P, uint32_
         const float su = F.sum_u, tot = F.total;
         bad |= !(su <= tol * fmaxf(1.f, tot));                              // loudness.total (and every specific[b], see mb_noise_band)
         bad |= !(4.f * su <= tol * tot);                                    // perceptualSpread: d(r^2) <= 2 r (max u + sum u) / total
-        const float sh = 0.11f * F.sharp / tot;
+        const float sh = __fdividef(0.11f * F.sharp, tot);
         bad |= !((1.65f + sh) * su <= tol * fmaxf(1.f, sh) * tot);          // perceptualSharpness: weights <= 15 x 0.11
     }
     if (mb_has(mask, MB_FEAT_MFCC)) bad |= !(0.02134f * F.sum_dl <= tol);   // max |dct| / 13 = sqrt(2/26) / 13
@@ -89,7 +96,7 @@ __device__ __forceinline__ bool mb_noise_needs_exact(const MbDevPlan &P, uint32_
         // (var cancelling below 1e-7 m1^2) the comparisons fail on a NaN or a negative and the frame is redone.
         const float sg = F.sigma, n = (float)P.M, q0 = F.q0, q4 = F.q4;
         // Q_p <= Q_0^(1 - p/4) Q_4^(p/4) (moments are log-convex in p); sums move by sigma (kap sqrt(T_2p) + Q_p)
-        const float g = (q0 > 0.f && q4 > 0.f) ? sqrtf(sqrtf(__fdividef(q4, q0))) : 0.f;
+        const float g = (q0 > 0.f && q4 > 0.f) ? mb_noise_sqrt(mb_noise_sqrt(__fdividef(q4, q0))) : 0.f;
         const float inv0 = sg * __fdividef(1.f, (float)S.s0);  // sigma / S_0
         const float r0 = ((float)P.noise_sqrtT[0] + q0) * inv0;  // relative motion of S_0
         const float q1 = q0 * g, q2 = q1 * g, q3 = q2 * g;
@@ -122,7 +129,7 @@ __device__ __forceinline__ bool mb_noise_needs_exact(const MbDevPlan &P, uint32_
         }
         if (mb_has(mask, MB_FEAT_SPECTRAL_FLATNESS)) {
             // flatness = exp(mean ln a) n / S0: mean ln a moves by (Q0 + 4 sqrt(Q0) / theta) / n, S0 by r0
-            const float dml = __fdividef(q0 + 4.f * sqrtf(q0) * (1.f / kMbNoiseTheta), n) + r0;
+            const float dml = __fdividef(q0 + 4.f * mb_noise_sqrt(q0) * (1.f / kMbNoiseTheta), n) + r0;
             bad |= !(dml + dml * dml <= tol);  // RELATIVE motion of the flatness (its magnitude runs from 1e-5 on tones to 1); e^x - 1 <= x + x^2
             bad |= (S.log2sum < -1e30) && (S.s0 > 0.0);  // a bin that is exactly 0 here need not be in the reference
         }
