@@ -392,6 +392,9 @@ def main():
     if os.environ.get("MEYDA_B200_HOST_THREADS"):  # (tuning runs: tools/gpu.sh; the default is the library's own choice)
         import meyda_b200 as _mb
         _mb.set_host_threads(int(os.environ["MEYDA_B200_HOST_THREADS"]))
+    if os.environ.get("MEYDA_B200_HOST_ROWS"):
+        import meyda_b200 as _mb
+        _mb.set_host_rows(int(os.environ["MEYDA_B200_HOST_ROWS"]))
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
         return reference_arm(args)

@@ -292,6 +292,12 @@ mb_status mb_measure_peaks(int device, double *fp32_ffma_tflops, double *fp64_df
  * picks min(8, cores / 2).  Calls already running keep their count. */
 mb_status mb_set_host_threads(int n);
 
+/* Whether a host-memory call produces the `buffer` and powerSpectrum rows on the host (1, the default; -1 restores
+ * it) or leaves them to the device and copies them back like every other output (0).  On the host they save 12 KB of
+ * 33 KB per frame of PCIe traffic at bufferSize 2048: 2.02 vs 1.49 M frames/s end to end with one device per host,
+ * 3.33 vs 2.82 M with eight (profiles/README.md).  0 is for hosts short of cores.  Process-wide. */
+mb_status mb_set_host_rows(int mode);
+
 /* Number of kernel launches issued by this plan so far (bench evidence). */
 int64_t mb_plan_launch_count(const mb_plan *plan);
 /* How many frames of the plan's last extract call (or stream push) were redone with the exact-FFT arithmetic

@@ -385,6 +385,18 @@ static napi_value SetHostThreads(napi_env env, napi_callback_info info) {
     return NULL;
 }
 
+// setHostRows(mode): 1 (default) / 0 -- the `buffer` and powerSpectrum rows of a host-memory call on the host, or on the device
+static napi_value SetHostRows(napi_env env, napi_callback_info info) {
+    size_t argc = 1;
+    napi_value argv[1];
+    NAPI_OK_OR_THROW(env, napi_get_cb_info(env, info, &argc, argv, NULL, NULL));
+    int32_t mode = -1;
+    NAPI_OK_OR_THROW(env, napi_get_value_int32(env, argv[0], &mode));
+    const mb_status st = mb_set_host_rows(mode);
+    if (st != MB_OK) return throw_mb(env, st);
+    return NULL;
+}
+
 // ---- streaming, the reference's actual usage model: one buffer per onaudioprocess event (src/meyda.js:69-91)
 static void stream_finalize(napi_env, void *data, void *) { mb_stream_destroy((mb_stream *)data); }
 
@@ -468,6 +480,7 @@ static napi_value Init(napi_env env, napi_value exports) {
         {"getParams", NULL, GetParams, NULL, NULL, NULL, napi_default, NULL},
         {"refinedFrames", NULL, RefinedFrames, NULL, NULL, NULL, napi_default, NULL},
         {"setHostThreads", NULL, SetHostThreads, NULL, NULL, NULL, napi_default, NULL},
+        {"setHostRows", NULL, SetHostRows, NULL, NULL, NULL, napi_default, NULL},
         {"createStream", NULL, CreateStream, NULL, NULL, NULL, napi_default, NULL},
         {"streamPush", NULL, StreamPush, NULL, NULL, NULL, napi_default, NULL},
         {"streamReset", NULL, StreamReset, NULL, NULL, NULL, napi_default, NULL},

@@ -234,5 +234,7 @@ class Meyda {
 
 // Host threads a host-memory extract uses for the rows the device does not produce (`buffer`, powerSpectrum); 0 = automatic.
 function setHostThreads(n) { native.setHostThreads(n | 0) }
+// 1 (default) / 0: those rows on the host, or on the device and copied back.
+function setHostRows(mode) { native.setHostRows(mode | 0) }
 
-module.exports = {Meyda, extract, extractAsync, extractWav, clearPlans, setHostThreads, featureInfo, isPowerOfTwo, FEATURES}
+module.exports = {Meyda, extract, extractAsync, extractWav, clearPlans, setHostThreads, setHostRows, featureInfo, isPowerOfTwo, FEATURES}

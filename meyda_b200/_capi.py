@@ -31,7 +31,7 @@ EXPORTS = [
     "mb_stream_create", "mb_stream_destroy", "mb_stream_frames_after", "mb_stream_push", "mb_stream_reset",
     "mb_extract_pcm16", "mb_extract_pcm16_async", "mb_wav_parse", "mb_stream_graph_launches", "mb_extract_pcm",
     "mb_stream_create_pcm16", "mb_stream_push_pcm16", "mb_plan_create_ex", "mb_plan_get_params",
-    "mb_plan_refined_frames", "mb_measure_peaks", "mb_set_host_threads",
+    "mb_plan_refined_frames", "mb_measure_peaks", "mb_set_host_threads", "mb_set_host_rows",
 ]
 
 # (field name in mb_outputs, feature name, per-frame length as a function of N and of the plan's Bark-band and
@@ -128,6 +128,7 @@ def lib():
     L.mb_plan_refined_frames.argtypes = [vp, i64p]
     L.mb_measure_peaks.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.mb_set_host_threads.argtypes = [C.c_int]
+    L.mb_set_host_rows.argtypes = [C.c_int]
     L.mb_plan_kernel_name.restype = C.c_char_p
     L.mb_plan_kernel_name.argtypes = [vp]
     L.mb_host_alloc.argtypes = [C.POINTER(vp), C.c_size_t]

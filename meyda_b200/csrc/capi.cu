@@ -219,6 +219,7 @@ inline void stream_fence() {}
 // else is left.
 constexpr unsigned kDefaultHostThreads = 8;
 std::atomic<int> g_host_threads{0};  // mb_set_host_threads (0: min(kDefaultHostThreads, cores / 2))
+std::atomic<int> g_host_rows{1};     // mb_set_host_rows: 1 on (default), 0 off
 
 class HostWorkers {
 public:
@@ -1106,10 +1107,13 @@ static mb_status extract_host_impl(mb_plan *p, const void *samples, const int64_
     // `buffer` is the caller's own samples cut into frames (docs.md:19-21): for float32 input the host fills those rows
     // itself, on a few threads, while the device works -- bit-identical by construction, and a quarter of the full
     // set's output bytes (8 KB of 33 KB per frame at bufferSize 2048) never crosses PCIe.
-    const bool host_buffer = pcm_channels == 0 && mb_has(p->mask, MB_FEAT_BUFFER);
+    // (measured with one and with eight devices per host, ranks or one process: on the host wins both times,
+    // 2.02 vs 1.49 M and 3.33 vs 2.82 M frames/s; mb_set_host_rows(0) is for hosts short of cores)
+    const bool host_rows = g_host_rows.load() != 0;
+    const bool host_buffer = host_rows && pcm_channels == 0 && mb_has(p->mask, MB_FEAT_BUFFER);
     // powerSpectrum[k] = float32(amplitudeSpectrum[k]^2) (powerSpectrum.js:1-7; one float32 multiply in every kernel):
     // where both are asked for, the host squares the amplitude rows as they land and the power rows stay off PCIe too.
-    const bool host_power = mb_has(p->mask, MB_FEAT_POWER_SPECTRUM) && mb_has(p->mask, MB_FEAT_AMPLITUDE_SPECTRUM);
+    const bool host_power = host_rows && mb_has(p->mask, MB_FEAT_POWER_SPECTRUM) && mb_has(p->mask, MB_FEAT_AMPLITUDE_SPECTRUM);
     const uint32_t drop_mask = (host_buffer ? MB_FEATURE_BIT(MB_FEAT_BUFFER) : 0u) | (host_power ? MB_FEATURE_BIT(MB_FEAT_POWER_SPECTRUM) : 0u);
     int64_t total_frames_call = 0;
     for (int64_t i = 0; i < n_clips; i++) total_frames_call += mb_num_frames(clip_len[i], N, hop);
@@ -1407,6 +1411,12 @@ mb_status mb_extract_multi(mb_plan *const *plans, int n_plans, const float *samp
 }
 
 // ---- measured non-tensor arithmetic peaks of a device (the FP32 / FP64 roofline denominators bench.py reports against)
+mb_status mb_set_host_rows(int mode) {
+    if (mode < -1 || mode > 1) return fail(MB_ERR_INVALID_ARG, "host rows mode %d (1 on, 0 off, -1 default)", mode);
+    g_host_rows.store(mode < 0 ? 1 : mode);
+    return MB_OK;
+}
+
 mb_status mb_set_host_threads(int n) {
     if (n < 0 || n > 256) return fail(MB_ERR_INVALID_ARG, "host thread count %d out of range [0, 256]", n);
     g_host_threads.store(n);

@@ -102,6 +102,12 @@ def set_host_threads(n: int) -> None:
     _capi.check(_capi.lib().mb_set_host_threads(int(n)))
 
 
+def set_host_rows(mode: int) -> None:
+    """1 (default; -1 restores it): host-memory extracts produce the `buffer` / powerSpectrum rows on the host while the
+    device works; 0: the device does and they are copied back (mb_set_host_rows, include/meyda_b200.h)."""
+    _capi.check(_capi.lib().mb_set_host_rows(int(mode)))
+
+
 def pinned_empty(shape, dtype) -> np.ndarray:
     """A numpy array over page-locked host memory (mb_host_alloc); freed with mb_host_free when collected."""
     import weakref

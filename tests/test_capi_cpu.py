@@ -131,3 +131,12 @@ def test_set_host_threads_validates_its_argument():
     assert L.mb_set_host_threads(0) == 0
     assert L.mb_set_host_threads(-1) != 0
     assert b"host thread count" in L.mb_last_error()
+
+
+def test_set_host_rows_validates_its_argument():
+    from meyda_b200 import _capi
+    L = _capi.lib()
+    for mode in (1, 0, -1):
+        assert L.mb_set_host_rows(mode) == 0
+    assert L.mb_set_host_rows(2) != 0
+    assert b"host rows mode" in L.mb_last_error()

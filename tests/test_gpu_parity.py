@@ -331,6 +331,23 @@ def test_device_memory_call_matches_host_call(golden_audio):
     plan.close()
 
 
+def test_host_produced_rows_equal_device_produced_rows(golden_audio):
+    """`buffer` and powerSpectrum written by the host threads of a host-memory call (the default for up to two devices
+    per host) are bit for bit what the device writes (mb_set_host_rows 0)."""
+    x = golden_audio["sound1"][:120000]
+    try:
+        for N, hop in ((2048, 512), (512, 512)):
+            mb.set_host_rows(1)
+            on, _ = run_gpu(x, N, hop)
+            mb.set_host_rows(0)
+            off, _ = run_gpu(x, N, hop)
+            assert set(on) == set(off)
+            for k in on:
+                assert np.array_equal(on[k], off[k], equal_nan=True), (N, k)
+    finally:
+        mb.set_host_rows(-1)
+
+
 def test_clip_sharding_is_bit_identical():
     """mb_extract_multi over two plans on the same device == single call."""
     clips = [mo.synth_clip(40 + i, 3000 + 977 * i) for i in range(9)]
