@@ -195,9 +195,16 @@ mb_warpmf_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ Mb
     // groups drift against each other as before and keep hiding each other's memory and barrier waits.  Trip counts
     // are uniform per CTA; a warp without work just keeps the barrier count.
     const int n_phase_bars = 1 + (want_spectrum ? 3 + (want_blocked ? 1 : 0) : 0);
+    // (a feature set without band features -- no pieces, no Bark / mel loops: the config-1 instantiation -- is a third of
+    // the code and fits as it is: there the barriers only cost)
+    constexpr bool kLock = kMask == 0 || (kMask & (MB_FEATURE_BIT(MB_FEAT_LOUDNESS) | MB_FEATURE_BIT(MB_FEAT_PERCEPTUAL_SPREAD) |
+                                                   MB_FEATURE_BIT(MB_FEAT_PERCEPTUAL_SHARPNESS) | MB_FEATURE_BIT(MB_FEAT_MFCC))) != 0;
     auto phase_sync = [&]() {
         __syncwarp();
-        asm volatile("bar.sync %0, %1;" ::"r"(1 + warp / kLockWarps), "n"(32 * kLockWarps) : "memory");
+        if constexpr (kLock) {
+            if (kMask != 0 || want_pieces)  // (run-time mask: the same rule, decided per launch)
+                asm volatile("bar.sync %0, %1;" ::"r"(1 + warp / kLockWarps), "n"(32 * kLockWarps) : "memory");
+        }
     };
     (void)warp_global;
     for (int64_t base = (int64_t)blockIdx.x * kWarps; base < total_chunks; base += warp_stride) {
