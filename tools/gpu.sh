@@ -46,7 +46,17 @@ tests)
 bench)
   python bench.py "$@" > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench exit $?"; tail -3 gpurun_out/bench.err; digest gpurun_out/bench.json ;;
 configs)
-  python tools/bench_configs.py "$@" > gpurun_out/bench_configs.json 2>&1; cut -c1-230 gpurun_out/bench_configs.json ;;
+  python tools/bench_configs.py "$@" > gpurun_out/bench_configs.json 2>&1
+  python - <<'PY'
+import json
+for l in open("gpurun_out/bench_configs.json"):
+    if l.startswith("{"):
+        d = json.loads(l)
+        print("%-58s %-12s %9.2f M frames/s  refined %s" % (d["config"][:58], d["kernel"], d["frames_per_s"] / 1e6, d.get("refined")))
+    else:
+        print(l.rstrip()[:200])
+PY
+  ;;
 adaptive)
   python tools/diag_adaptive.py > gpurun_out/diag_adaptive.log 2>&1; grep -v Warning gpurun_out/diag_adaptive.log | grep -v "err = " ;;
 variants)
