@@ -828,6 +828,11 @@ struct BigSmem {
     float2 tw32[32 * 32];             // exp(+2 pi i b c / 1024) at [c*32 + b]
     float2 tw16[kBigR * 32];          // exp(+2 pi i r d / (32 R)) at [r*32 + d]  (R = 16: / 512)
     float2 tw_step[32];               // exp(+2 pi i j / 64): the split twiddle of bin tid + kThreads j over that of bin tid
+    // a frame whose number features and refine decision are still to be made (see "deferred finish" in the kernel)
+    MbFrameSums fin_S;
+    MbNoiseFrame fin_NF;
+    int64_t fin_g;
+    int fin_kscale;
 };
 
 __global__ void __launch_bounds__(kThreads, 512 / kThreads)
@@ -875,6 +880,17 @@ mb_big32768_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
     block_sync();
     float2 *slot = B.area + warp * kBigSlot;  // this warp's transpose slot / sub-spectrum row
 
+    // Deferred finish.  Turning a frame's sums into its number features and deciding whether the exact kernel must
+    // redo it is ~2,000 clocks of ONE thread (float64 roots, powers and divisions); at the end of the frame the other
+    // warps wait for it at the next barrier.  With 8 or 16 warps per frame the thread's warp instead does it while
+    // the OTHER warps load the next frame -- a phase bound by two L2 round trips, not by issue slots, so that the
+    // loaders take over its share for free.  Only when no time-domain output is asked for: those sums (energy, zcr)
+    // are per-thread partials whose order -- and so whose last bit -- would otherwise depend on whether a frame is a
+    // CTA's first.  (BASELINE config 5: 5.8 -> 6.1 M frames/s.)
+    constexpr int kFinWarp = kScalarThread >> 5;
+    const bool defer = kBigR >= 8 && !want_time;
+    bool pending = false;
+
     int64_t clip_next = -1;  // the clip of this CTA's next frame, found while its samples are prefetched
     for (int64_t g = blockIdx.x; g < T.total_frames; g += gridDim.x) {
         const int64_t clip = clip_next >= 0 ? clip_next : mb_find_clip_warp(T, g);
@@ -913,14 +929,18 @@ mb_big32768_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
                 B.area[m0 + (m0 >> 4)] = make_float2(__fmul_rn(x.x, w.x), __fmul_rn(x.y, w.y));
                 B.area[m1 + (m1 >> 4)] = make_float2(__fmul_rn(x.z, w.z), __fmul_rn(x.w, w.w));
             };
-            if (src_aligned) {
+            const int i0 = pending ? tid - (warp > kFinWarp ? 32 : 0) : tid, di = pending ? kThreads - 32 : kThreads;
+            if (pending && warp == kFinWarp) {  // (deferred finish of the previous frame: this warp loads nothing)
+                if (lane == 0) frame_finish(P, T, O, B.fin_g, B.fin_S, B.fin_NF, B.fin_kscale);
+            } else if (src_aligned) {
 #pragma unroll 4
-                for (int i = tid; i < N / 4; i += kThreads) take(i, __ldg(src4 + i));
+                for (int i = i0; i < N / 4; i += di) take(i, __ldg(src4 + i));
             } else {
 #pragma unroll 2
-                for (int i = tid; i < N / 4; i += kThreads)
+                for (int i = i0; i < N / 4; i += di)
                     take(i, make_float4(__ldg(src + 4 * i), __ldg(src + 4 * i + 1), __ldg(src + 4 * i + 2), __ldg(src + 4 * i + 3)));
             }
+            pending = false;
             if (want_time) {
                 S.energy = block_sum(e, sc.red_d);
                 S.zcr = block_sum_int(z, sc.red_i);
@@ -1060,8 +1080,19 @@ mb_big32768_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
         if (adapt) block_sync();
         MbNoiseFrame NF;
         if (tid == kScalarThread) NF = frame_gather(P, sc, adapt ? noise_sigma : -1.f);
+        const int fin_k = (adapt && acc_cf_missing(noise_sigma)) ? 1 : kscale;
+        if (defer) {  // parked; made by this thread's warp while the others load the next frame
+            if (tid == kScalarThread) {
+                B.fin_S = S;
+                B.fin_NF = NF;
+                B.fin_g = g;
+                B.fin_kscale = fin_k;
+            }
+            pending = true;
+        }
         block_sync();  // smem reused by the next frame
-        if (tid == kScalarThread) frame_finish(P, T, O, g, S, NF, (adapt && acc_cf_missing(noise_sigma)) ? 1 : kscale);
+        if (!defer && tid == kScalarThread) frame_finish(P, T, O, g, S, NF, fin_k);
     }
+    if (pending && tid == kScalarThread) frame_finish(P, T, O, B.fin_g, B.fin_S, B.fin_NF, B.fin_kscale);
 }
 #endif  // MB_GENERIC_THREADS == 64 .. 512
