@@ -30,6 +30,7 @@
 #include "mb_adaptive.cuh"
 #include "mb_device.cuh"
 #include "mb_kernels.h"
+#include "mb_fft.cuh"
 
 namespace gw {  // the generic epilogue for a team of one warp
 #define MB_GENERIC_THREADS 32

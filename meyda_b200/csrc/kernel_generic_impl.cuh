@@ -23,8 +23,14 @@ constexpr int kScalarThread = kThreads > 64 ? 64 : 0;  // the lane that turns th
 // single shared-memory bank.
 __device__ __forceinline__ int pidx(int i) { return i + (i >> 5) + (i >> 10); }
 
-__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
-    return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) { return mbx2::cmul(a, b); }  // FMUL2 + FFMA2 (mb_fft.cuh)
+// real-FFT split of one bin: a = X[k], b = X[M-k], w = exp(+2 pi i k / N) -> Z[k] = ((a + conj b) / 2 + w O) sc with
+// O = (a - conj b) / (2 i); seven packed instructions
+__device__ __forceinline__ float2 split_bin(float2 a, float2 b, float2 w, float sc) {
+    const float2 cb = make_float2(b.x, -b.y);
+    const float2 E = mbx2::add(a, cb), F = mbx2::sub(a, cb);                           // (2 er, 2 ei), (-2 oi, 2 orr)
+    const float2 Oo = mbx2::mul(mbx2::swap(F), make_float2(0.5f, -0.5f));              // (orr, oi)
+    return mbx2::mul(mbx2::fma(E, mbx2::bc(0.5f), mbx2::cmul(Oo, w)), mbx2::bc(sc));
 }
 
 // ---- exact mode: the reference's butterfly (lib/jsfft/fft.js:151-161) on float32-stored values, in
@@ -113,8 +119,8 @@ __device__ __forceinline__ void fft_pass(float2 *work, const float2 *__restrict_
                 if (t & h) continue;
                 const int e = (j + (t & (h - 1)) * sub) << tw_shift;
                 const float2 u = v[t], w = v[t + h];
-                v[t] = make_float2(u.x + w.x, u.y + w.y);
-                v[t + h] = cmul(make_float2(u.x - w.x, u.y - w.y), __ldg(&twM[e]));
+                v[t] = mbx2::add(u, w);
+                v[t + h] = cmul(mbx2::sub(u, w), __ldg(&twM[e]));
             }
         }
 #pragma unroll
@@ -663,11 +669,8 @@ mb_generic_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ M
                     const int kk = (M - k) & (M - 1);
                     const float2 a = work[pidx((int)(__brev((unsigned)k) >> rshift))];
                     const float2 b = work[pidx((int)(__brev((unsigned)kk) >> rshift))];
-                    const float er = 0.5f * (a.x + b.x), ei = 0.5f * (a.y - b.y);
-                    const float orr = 0.5f * (a.y + b.y), oi = -0.5f * (a.x - b.x);
-                    const float2 w = __ldg(&P.twN[k]);
-                    float zr = (er + (w.x * orr - w.y * oi)) * sc;
-                    float zi = (ei + (w.x * oi + w.y * orr)) * sc;
+                    const float2 Z = split_bin(a, b, __ldg(&P.twN[k]), sc);
+                    float zr = Z.x, zi = Z.y;
                     if (mb_has(mask, MB_FEAT_COMPLEX_SPECTRUM)) {
                         float *re = O.complex_real + g * N, *im = O.complex_imag + g * N;
                         const float zro = zr * unscale, zio = zi * unscale;
@@ -926,8 +929,8 @@ mb_big32768_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
                     if (mb_has(mask, MB_FEAT_BUFFER)) __stcs(reinterpret_cast<float4 *>(O.buffer + g * N) + i, x);
                 }
                 const int m0 = 2 * i, m1 = 2 * i + 1;
-                B.area[m0 + (m0 >> 4)] = make_float2(__fmul_rn(x.x, w.x), __fmul_rn(x.y, w.y));
-                B.area[m1 + (m1 >> 4)] = make_float2(__fmul_rn(x.z, w.z), __fmul_rn(x.w, w.w));
+                B.area[m0 + (m0 >> 4)] = mbx2::mul(make_float2(x.x, x.y), make_float2(w.x, w.y));
+                B.area[m1 + (m1 >> 4)] = mbx2::mul(make_float2(x.z, x.w), make_float2(w.z, w.w));
             };
             const int i0 = pending ? tid - (warp > kFinWarp ? 32 : 0) : tid, di = pending ? kThreads - 32 : kThreads;
             if (pending && warp == kFinWarp) {  // (deferred finish of the previous frame: this warp loads nothing)
@@ -1052,10 +1055,8 @@ mb_big32768_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
                 const float2 w = cmul(tw_split, B.tw_step[jj]);
                 const float2 a = B.area[k];
                 const float2 b = B.area[(M - k) & (M - 1)];
-                const float er = 0.5f * (a.x + b.x), ei = 0.5f * (a.y - b.y);
-                const float orr = 0.5f * (a.y + b.y), oi = -0.5f * (a.x - b.x);
-                const float zr = (er + (w.x * orr - w.y * oi)) * sc_n;
-                const float zi = (ei + (w.x * oi + w.y * orr)) * sc_n;
+                const float2 Z = split_bin(a, b, w, sc_n);
+                const float zr = Z.x, zi = Z.y;
                 if (want_cs) {
                     float *re = O.complex_real + g * N, *im = O.complex_imag + g * N;
                     const float zro = zr * unscale, zio = zi * unscale;

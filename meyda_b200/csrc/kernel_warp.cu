@@ -271,9 +271,10 @@ mb_warp2048_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
             // ---- 2. pass 1: window, time-domain sums, FFT32 over a for b = lane
             float2 v[32];
             float esum;
+            float2 esum2;  // (even samples, odd samples): one packed FFMA2 per sample pair
             uint32_t sgn_e, sgn_o;  // bit a: sample 2(32a+lane) (+1) is >= 0
             auto pass1 = [&]() {
-                esum = 0.f;
+                esum2 = make_float2(0.f, 0.f);
                 sgn_e = sgn_o = 0;
 #pragma unroll
                 for (int a = 0; a < 32; a++) {
@@ -288,16 +289,16 @@ mb_warp2048_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
                         x = slot2[32 * a + lane];
                     }
                     const float2 w = reinterpret_cast<const float2 *>(S.window)[32 * a + lane];
-                    esum = fmaf(x.x, x.x, esum);
-                    esum = fmaf(x.y, x.y, esum);
+                    esum2 = mbx2::fma(x, x, esum2);
                     if (want_time) {  // (compare + predicated OR: two instructions per sample)
                         asm("{\n\t.reg .pred p;\n\tsetp.ge.f32 p, %1, 0f00000000;\n\t@p or.b32 %0, %0, %2;\n\t}"
                             : "+r"(sgn_e) : "f"(x.x), "r"(1u << a));
                         asm("{\n\t.reg .pred p;\n\tsetp.ge.f32 p, %1, 0f00000000;\n\t@p or.b32 %0, %0, %2;\n\t}"
                             : "+r"(sgn_o) : "f"(x.y), "r"(1u << a));
                     }
-                    v[a] = make_float2(__fmul_rn(x.x, w.x), __fmul_rn(x.y, w.y));
+                    v[a] = mbx2::mul(x, w);
                 }
+                esum = esum2.x + esum2.y;
             };
             pass1();
             float energy = mb_warp_sum(esum);
@@ -384,7 +385,7 @@ mb_warp2048_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
                             if (c > 0) {
                                 const float2 t = t_nx;
                                 if (c + 1 < 32) t_nx = S.tw32[(c + 1) * 32 + lane];
-                                y = make_float2(y.x * t.x - y.y * t.y, y.x * t.y + y.y * t.x);
+                                y = mbx2::cmul(y, t);
                             }
                             slot2[c * kRow + lane] = y;
                         }
@@ -421,9 +422,12 @@ mb_warp2048_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ 
                         b_nx = xm[-32 * (d + 1)];
                         w_nx = twp[32 * (d + 1)];
                     }
-                    const float sx = a.x + b.x, dx = a.x - b.x, sy = a.y + b.y, dy = a.y - b.y;
-                    const float zr = fmaf(hsc, sx, fmaf(w.x, sy, w.y * dx));
-                    const float zi = fmaf(hsc, dy, fmaf(w.y, sy, -(w.x * dx)));
+                    // E = a + conj(b) = (sx, dy), F = a - conj(b) = (dx, sy); Z = hsc E + sy w + dx (w.y, -w.x): five packed
+                    // instructions, each half rounded as in zr = fma(hsc, sx, fma(w.x, sy, w.y dx)), zi = fma(hsc, dy, fma(w.y, sy, -(w.x dx)))
+                    const float2 cb = make_float2(b.x, -b.y);
+                    const float2 E = mbx2::add(a, cb), F = mbx2::sub(a, cb);
+                    const float2 Z = mbx2::fma(E, mbx2::bc(hsc), mbx2::fma(w, mbx2::bc(F.y), mbx2::mul(make_float2(w.y, -w.x), mbx2::bc(F.x))));
+                    const float zr = Z.x, zi = Z.y;
                     if (want_cs && exp_store) {
                         // (a rescaled frame, kscale != 0, is brought back to its own units by the fix-up below)
                         st_stream(out_re + 32 * d, zr);

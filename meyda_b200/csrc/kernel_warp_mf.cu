@@ -282,10 +282,11 @@ mb_warpmf_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ Mb
             // ---- 2. pass A load: window, time-domain sums (per frame)
             float2 v[32];
             float esum[kF];
+            float2 esum2[kF];  // (even samples, odd samples): one packed FFMA2 per sample pair
             uint32_t sgn_e, sgn_o;  // bit a': sample 2(32 a' + lane) (+1) of the warp is >= 0
             auto pass1 = [&]() {
 #pragma unroll
-                for (int f = 0; f < kF; f++) esum[f] = 0.f;
+                for (int f = 0; f < kF; f++) esum2[f] = make_float2(0.f, 0.f);
                 sgn_e = sgn_o = 0;
 #pragma unroll
                 for (int a = 0; a < 32; a++) {
@@ -300,16 +301,17 @@ mb_warpmf_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ Mb
                         x = slot2[32 * a + lane];
                     }
                     const float2 w = reinterpret_cast<const float2 *>(S.window)[32 * a + lane];
-                    esum[a / kA] = fmaf(x.x, x.x, esum[a / kA]);
-                    esum[a / kA] = fmaf(x.y, x.y, esum[a / kA]);
+                    esum2[a / kA] = mbx2::fma(x, x, esum2[a / kA]);
                     if (want_time) {
                         asm("{\n\t.reg .pred p;\n\tsetp.ge.f32 p, %1, 0f00000000;\n\t@p or.b32 %0, %0, %2;\n\t}"
                             : "+r"(sgn_e) : "f"(x.x), "r"(1u << a));
                         asm("{\n\t.reg .pred p;\n\tsetp.ge.f32 p, %1, 0f00000000;\n\t@p or.b32 %0, %0, %2;\n\t}"
                             : "+r"(sgn_o) : "f"(x.y), "r"(1u << a));
                     }
-                    v[a] = make_float2(__fmul_rn(x.x, w.x), __fmul_rn(x.y, w.y));
+                    v[a] = mbx2::mul(x, w);
                 }
+#pragma unroll
+                for (int f = 0; f < kF; f++) esum[f] = esum2[f].x + esum2[f].y;
             };
             pass1();
             float energy[kF];
@@ -404,7 +406,7 @@ mb_warpmf_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ Mb
                     float2 y = v[f * kA + mbfft::brev<kABits>(p)];
                     if (p > 0) {
                         const float2 t = S.tw32[c * 32 + lane];
-                        y = make_float2(y.x * t.x - y.y * t.y, y.x * t.y + y.y * t.x);
+                        y = mbx2::cmul(y, t);
                     }
                     slot2[c * kRow + lane] = y;
                 }
@@ -443,9 +445,11 @@ mb_warpmf_kernel(const __grid_constant__ MbDevPlan P, const __grid_constant__ Mb
                     const float2 a = xa[f * kMs + 32 * r];   // X_f[k], k = 32 r + lane
                     const float2 b = xb[f * kMs - 32 * r];   // X_f[M - k]
                     const float2 w = twp[32 * d];
-                    const float sx = a.x + b.x, dx = a.x - b.x, sy = a.y + b.y, dy = a.y - b.y;
-                    const float zr = fmaf(hsc, sx, fmaf(w.x, sy, w.y * dx));
-                    const float zi = fmaf(hsc, dy, fmaf(w.y, sy, -(w.x * dx)));
+                    // E = a + conj(b) = (sx, dy), F = a - conj(b) = (dx, sy); Z = hsc E + sy w + dx (w.y, -w.x), packed (kernel_warp.cu)
+                    const float2 cb = make_float2(b.x, -b.y);
+                    const float2 E = mbx2::add(a, cb), F = mbx2::sub(a, cb);
+                    const float2 Z = mbx2::fma(E, mbx2::bc(hsc), mbx2::fma(w, mbx2::bc(F.y), mbx2::mul(make_float2(w.y, -w.x), mbx2::bc(F.x))));
+                    const float zr = Z.x, zi = Z.y;
                     if (want_cs && fv) {
                         st_stream(up_re + f * kN + 32 * r, zr);
                         st_stream(up_im + f * kN + 32 * r, zi);
