@@ -107,6 +107,14 @@ struct Slot {  // one pipeline stage of a host-memory extract
     size_t fix_cap = 0;        // ints
     int *h_fix = nullptr;      // pinned: the counts of this slot's chunks, one after the other
     size_t h_fix_cap = 0, h_fix_used = 0;
+    // The per-frame numbers and the short arrays (loudness.specific, mfcc) of a chunk leave the device as ONE copy into
+    // this pinned staging area and are handed out to the caller's arrays once the slot's stream has drained: fifteen
+    // copies of 12 .. 300 KB per chunk cost more in launch gaps than in bytes.
+    char *h_small = nullptr;
+    size_t small_cap = 0;
+    struct SmallPart { int field; size_t off; };  // off: byte offset inside the staged region
+    std::vector<SmallPart> small_parts;           // the pending chunk's small fields (empty: nothing pending)
+    int64_t small_g0 = 0, small_frames = 0;
 };
 
 }  // namespace
@@ -366,6 +374,7 @@ void free_slot(Slot &s) {
     if (s.stream) cudaStreamDestroy(s.stream);
     cudaFree(s.d_fix);
     if (s.h_fix) cudaFreeHost(s.h_fix);
+    if (s.h_small) cudaFreeHost(s.h_small);
     cudaFree(s.d_samples);
     cudaFree(s.d_out);
     cudaFree(s.d_tab);
@@ -1073,6 +1082,15 @@ mb_status mb_plan_synchronize(mb_plan *p) {
 // `samples` is float32 (pcm_channels == 0) or interleaved int16 PCM; offsets count sample frames either way.
 static mb_status extract_host_impl(mb_plan *p, const void *samples, const int64_t *clip_offset, const int64_t *clip_len,
                                    int64_t n_clips, const mb_outputs *out, int pcm_channels, int pcm_channel, int pcm_format);
+// the staged small fields of the slot's last chunk into the caller's arrays (the slot's stream has been synchronized)
+static void scatter_small(mb_plan *p, Slot &s, const mb_outputs *out) {
+    for (const Slot::SmallPart &sp : s.small_parts) {
+        const OutField &f = kFields[sp.field];
+        const size_t per = (size_t)field_elems(f, p->dev) * 4;
+        memcpy((char *)field_ptr(*out, f) + (size_t)s.small_g0 * per, s.h_small + sp.off, (size_t)s.small_frames * per);
+    }
+    s.small_parts.clear();
+}
 
 static mb_status extract_host(mb_plan *p, const void *samples, const int64_t *clip_offset, const int64_t *clip_len,
                               int64_t n_clips, const mb_outputs *out, int pcm_channels = 0, int pcm_channel = 0,
@@ -1082,8 +1100,10 @@ static mb_status extract_host(mb_plan *p, const void *samples, const int64_t *cl
     if (st != MB_OK) {
         // copies of earlier chunks may still be writing into the caller's arrays: drain before reporting the failure
         const std::string msg = g_last_error;
-        for (auto &s : p->slots)
+        for (auto &s : p->slots) {
             if (s.stream) cudaStreamSynchronize(s.stream);
+            s.small_parts.clear();  // (a failed call's staged rows are not handed out)
+        }
         (void)cudaGetLastError();
         g_last_error = msg;
     }
@@ -1182,6 +1202,7 @@ static mb_status extract_host_impl(mb_plan *p, const void *samples, const int64_
         if (!s.stream) MB_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
         // the slot's previous chunk (two chunks ago) must have drained before its buffers are reused
         MB_CUDA(cudaStreamSynchronize(s.stream));
+        scatter_small(p, s, out);  // (the other slot's copies are in flight meanwhile)
         const size_t span = (size_t)(hi - lo);
         if (s.samples_cap < span * frame_bytes) {
             cudaFree(s.d_samples);
@@ -1211,15 +1232,31 @@ static mb_status extract_host_impl(mb_plan *p, const void *samples, const int64_
         MB_CUDA(cudaMemcpyAsync(s.d_tab, s.h_tab, entries * sizeof(int64_t), cudaMemcpyHostToDevice, s.stream));
         MB_CUDA(cudaMemcpyAsync(s.d_samples, (const char *)samples + (size_t)lo * frame_bytes, span * frame_bytes,
                                 cudaMemcpyHostToDevice, s.stream));
-        // carve the slot's output arena
+        // carve the slot's output arena: the big arrays first, then the per-frame numbers and short arrays back to back
+        // (they leave as one copy)
         mb_outputs d_out;
         memset(&d_out, 0, sizeof(d_out));
-        size_t cursor = 0;
-        for (int i = 0; i < kNumFields; i++) {
-            if (!mb_has(p->mask & ~drop_mask, kFields[i].feature)) continue;
-            field_ptr(d_out, kFields[i]) = s.d_out + cursor;
-            cursor += (size_t)frames * field_elems(kFields[i], p->dev) * 4;
+        size_t cursor = 0, small_begin = 0;
+        for (int small = 0; small < 2; small++) {
+            if (small) small_begin = cursor;
+            for (int i = 0; i < kNumFields; i++) {
+                if (!mb_has(p->mask & ~drop_mask, kFields[i].feature)) continue;
+                if ((kFields[i].kind == 1 || kFields[i].kind == 2) == (small == 1)) continue;
+                field_ptr(d_out, kFields[i]) = s.d_out + cursor;
+                if (small) s.small_parts.push_back({i, cursor - small_begin});
+                cursor += (size_t)frames * field_elems(kFields[i], p->dev) * 4;
+            }
         }
+        const size_t small_bytes = cursor - small_begin;
+        if (s.small_cap < small_bytes) {
+            if (s.h_small) cudaFreeHost(s.h_small);
+            s.h_small = nullptr;
+            s.small_cap = 0;
+            MB_CUDA(cudaMallocHost((void **)&s.h_small, small_bytes));
+            s.small_cap = small_bytes;
+        }
+        s.small_g0 = g_done;
+        s.small_frames = frames;
         st = launch(p, s.d_tab, s.d_tab + v.size(), (int64_t)v.size(), frames, s.d_samples, d_out, s.stream, &s.d_fix,
                     &s.fix_cap, pcm_channels, pcm_channel, pcm_format, drop_mask);
         if (st != MB_OK) return st;
@@ -1239,6 +1276,7 @@ static mb_status extract_host_impl(mb_plan *p, const void *samples, const int64_
         for (int pass = host_power ? 0 : 1; pass < 2; pass++) {
             for (int i = 0; i < kNumFields; i++) {
                 if (!mb_has(p->mask & ~drop_mask, kFields[i].feature)) continue;
+                if (kFields[i].kind != 1 && kFields[i].kind != 2) continue;  // (staged: below)
                 const bool is_amp = kFields[i].feature == MB_FEAT_AMPLITUDE_SPECTRUM;
                 if (host_power && is_amp != (pass == 0)) continue;
                 const size_t per = (size_t)field_elems(kFields[i], p->dev) * 4;
@@ -1256,12 +1294,14 @@ static mb_status extract_host_impl(mb_plan *p, const void *samples, const int64_
                 post_power(g_done, g_done + frames, p->landed[chunk_idx]);
             }
         }
+        if (small_bytes) MB_CUDA(cudaMemcpyAsync(s.h_small, s.d_out + small_begin, small_bytes, cudaMemcpyDeviceToHost, s.stream));
         g_done += frames;
         chunk_idx++;
     }
     for (int k = 0; k < 2; k++) {
         Slot &s = p->slots[k];
         if (s.stream) MB_CUDA(cudaStreamSynchronize(s.stream));
+        scatter_small(p, s, out);
         for (size_t i = 0; i < s.h_fix_used; i++) p->refined_frames += s.h_fix[i];
         s.h_fix_used = 0;
     }
