@@ -494,12 +494,16 @@ def main():
             return reduce_max(torch, dist, dev, world, (time.perf_counter() - t0) / reps)
 
         dt = timed(lambda: plan.extract_host(hx, off, ln, out=ho), args.steps)
-        host_made = {"buffer"} | ({"power_spectrum"} if "amplitude_spectrum" in ho else set())  # rows the host fills itself
-        d2h = int(sum(v.nbytes for k, v in ho.items() if k not in host_made))
+        rows_mode = mb.get_host_rows()  # 0 / 1 / 2 (mb_set_host_rows; the default picks by cores per visible device)
+        host_made = ({"buffer"} | ({"power_spectrum"} if "amplitude_spectrum" in ho else set())) if rows_mode >= 1 else set()  # rows the host fills itself
+        half = {"complex_real", "complex_imag"} if rows_mode >= 2 else set()  # bins 0 .. N/2 copied, the mirrored half made on the host
+        d2h = int(sum((v.nbytes // N * (N // 2 + 1) if k in half else v.nbytes) for k, v in ho.items() if k not in host_made))
         e2e = {"value": nf * world / dt, "unit": UNIT, "h2d_bytes_per_step": int(hx.nbytes), "d2h_bytes_per_step": d2h,
-               "batch": "%d clips x 30 s per rank per step, mb_extract(MB_MEM_HOST) into mb_host_alloc (pinned) arrays; the `buffer` "
-                        "rows (the caller's own samples) and the powerSpectrum rows (amplitude squared) are produced on the host "
-                        "while the device works and are not copied back" % e2e_clips}
+               "host_rows_mode": rows_mode,
+               "batch": "%d clips x 30 s per rank per step, mb_extract(MB_MEM_HOST) into mb_host_alloc (pinned) arrays; host-rows mode %d: "
+                        "%s produced on the host while the device works and not copied back" % (
+                            e2e_clips, rows_mode, {0: "nothing is", 1: "the `buffer` rows (the caller's own samples) and the powerSpectrum rows "
+                            "(amplitude squared) are", 2: "the `buffer` rows, the powerSpectrum rows and the mirrored half of complexSpectrum are"}[rows_mode])}
         # the host link's own ceiling for these byte counts, every rank at once
         if world > 1:
             dist.barrier()

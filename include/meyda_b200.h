@@ -292,11 +292,19 @@ mb_status mb_measure_peaks(int device, double *fp32_ffma_tflops, double *fp64_df
  * picks min(8, cores / 2).  Calls already running keep their count. */
 mb_status mb_set_host_threads(int n);
 
-/* Whether a host-memory call produces the `buffer` and powerSpectrum rows on the host (1, the default; -1 restores
- * it) or leaves them to the device and copies them back like every other output (0).  On the host they save 12 KB of
- * 33 KB per frame of PCIe traffic at bufferSize 2048: 2.02 vs 1.49 M frames/s end to end with one device per host,
- * 3.33 vs 2.82 M with eight (profiles/README.md).  0 is for hosts short of cores.  Process-wide. */
+/* Which rows a host-memory call produces on the host while the device works, instead of copying them back:
+ *   1  `buffer` (the caller's own samples, framed) and powerSpectrum (amplitudeSpectrum squared): 12 KB of 33 KB per
+ *      frame of PCIe traffic at bufferSize 2048 -- 2.02 vs 1.49 M frames/s end to end with one device per host,
+ *      3.33 vs 2.82 M with eight (profiles/README.md);
+ *   2  also the upper half of complexSpectrum, Z[N-k] = conj(Z[k]) (8 KB more per frame; 2.55 vs 2.12 M frames/s with
+ *      one device on a 16-core host): the rows of frames that the exact-FFT kernel redid (whose upper half is computed,
+ *      as the reference's is) still come from the device, exact-FFT plans and pageable output arrays copy everything;
+ *   0  nothing: the device produces every row and all are copied back (hosts short of cores);
+ *  -1  (the default) 2 where the host has twelve or more cores per visible device, else 1.
+ * The results are bit-identical in every mode.  Process-wide. */
 mb_status mb_set_host_rows(int mode);
+/* The mode in force: 0, 1 or 2 (the automatic choice resolved). */
+int mb_get_host_rows(void);
 
 /* Number of kernel launches issued by this plan so far (bench evidence). */
 int64_t mb_plan_launch_count(const mb_plan *plan);

@@ -7,10 +7,10 @@ feature-extraction hot path behind the reference's extractor API.
   build.py   nvcc build of _lib/libmeyda_b200.so
 """
 from .meyda import (AudioContext, ExtractResult, FEATURES, Meyda, MeydaError, MeydaNativeError, Plan, Stream,
-                    extract, extract_multi, extract_wav, feature_mask, featureInfo, isPowerOfTwo, set_host_rows,
+                    extract, extract_multi, extract_wav, feature_mask, featureInfo, isPowerOfTwo, set_host_rows, get_host_rows,
                     set_host_threads, wav_info)
 
 __all__ = ["AudioContext", "ExtractResult", "FEATURES", "Meyda", "MeydaError", "MeydaNativeError", "Plan", "Stream",
-           "extract", "extract_multi", "extract_wav", "feature_mask", "featureInfo", "isPowerOfTwo", "set_host_rows",
+           "extract", "extract_multi", "extract_wav", "feature_mask", "featureInfo", "isPowerOfTwo", "set_host_rows", "get_host_rows",
            "set_host_threads", "wav_info"]
 __version__ = "0.1.0"

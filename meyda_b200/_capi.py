@@ -32,6 +32,7 @@ EXPORTS = [
     "mb_extract_pcm16", "mb_extract_pcm16_async", "mb_wav_parse", "mb_stream_graph_launches", "mb_extract_pcm",
     "mb_stream_create_pcm16", "mb_stream_push_pcm16", "mb_plan_create_ex", "mb_plan_get_params",
     "mb_plan_refined_frames", "mb_measure_peaks", "mb_set_host_threads", "mb_set_host_rows",
+    "mb_get_host_rows",
 ]
 
 # (field name in mb_outputs, feature name, per-frame length as a function of N and of the plan's Bark-band and
@@ -129,6 +130,8 @@ def lib():
     L.mb_measure_peaks.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.mb_set_host_threads.argtypes = [C.c_int]
     L.mb_set_host_rows.argtypes = [C.c_int]
+    L.mb_get_host_rows.restype = C.c_int
+    L.mb_get_host_rows.argtypes = []
     L.mb_plan_kernel_name.restype = C.c_char_p
     L.mb_plan_kernel_name.argtypes = [vp]
     L.mb_host_alloc.argtypes = [C.POINTER(vp), C.c_size_t]

@@ -115,6 +115,11 @@ struct Slot {  // one pipeline stage of a host-memory extract
     struct SmallPart { int field; size_t off; };  // off: byte offset inside the staged region
     std::vector<SmallPart> small_parts;           // the pending chunk's small fields (empty: nothing pending)
     int64_t small_g0 = 0, small_frames = 0;
+    // mb_set_host_rows(2): the pending chunk whose complexSpectrum upper halves the host threads mirror; the frames the
+    // exact kernel redid (not conjugate-symmetric to the last bit, like the reference's) get theirs from the device
+    int64_t mir_frames = 0;
+    size_t mir_fix_idx = 0;                       // this chunk's entry of h_fix
+    const float *mir_d_re = nullptr, *mir_d_im = nullptr;
 };
 
 }  // namespace
@@ -147,6 +152,7 @@ struct mb_plan {
     bool tab_event_pending = false;
     Slot slots[2];
     std::vector<cudaEvent_t> landed;  // host-memory calls: chunk i's amplitude rows have arrived (kept across calls)
+    std::vector<cudaEvent_t> landed_c;  // ... chunk i's complexSpectrum lower halves have arrived (mb_set_host_rows(2))
     // adaptive exactness (mb_adaptive.cuh): frames the float32 kernels flag are redone by the exact-FFT kernel
     bool adaptive = false;
     MbDevPlan dev_fix{};       // the plan as the exact kernel sees it: spectral features only
@@ -211,11 +217,46 @@ inline void square_rows_stream(float *dst, const float *src, int64_t n) {
     }
     for (; i < n; i++) dst[i] = src[i] * src[i];
 }
+// The upper half of a complexSpectrum row from its lower half: Z[N-k] = conj(Z[k]), k = 1 .. N/2-1, as every float32
+// kernel stores it: the real part copied, the imaginary part negated BY AN ARITHMETIC INSTRUCTION -- so a NaN comes
+// out as the canonical 0x7fffffff there, whatever its sign was (the kernels' own bits in every host-rows mode).
+inline float mirror_neg(float x) {
+    uint32_t u;
+    memcpy(&u, &x, 4);
+    u = (u & 0x7fffffffu) > 0x7f800000u ? 0x7fffffffu : (u ^ 0x80000000u);
+    memcpy(&x, &u, 4);
+    return x;
+}
+inline void mirror_row_stream(float *row, int N, bool negate) {
+    const int M = N / 2;
+    int j = M + 1;
+    if (((uintptr_t)row & 15) == 0 && M >= 8) {
+        const __m128 sg = _mm_castsi128_ps(_mm_set1_epi32(negate ? (int)0x80000000u : 0));
+        const __m128 qnan = _mm_castsi128_ps(_mm_set1_epi32(0x7fffffff));
+        for (; j < M + 4; j++) row[j] = negate ? mirror_neg(row[N - j]) : row[N - j];
+        for (; j + 4 <= N; j += 4) {  // dst[j .. j+3] = src[N-j], src[N-j-1], src[N-j-2], src[N-j-3]
+            const __m128 a = _mm_loadu_ps(row + (N - j - 3));
+            __m128 r = _mm_xor_ps(_mm_shuffle_ps(a, a, _MM_SHUFFLE(0, 1, 2, 3)), sg);
+            if (negate) {
+                const __m128 un = _mm_cmpunord_ps(r, r);
+                r = _mm_or_ps(_mm_andnot_ps(un, r), _mm_and_ps(un, qnan));
+            }
+            _mm_stream_ps(row + j, r);
+        }
+    }
+    for (; j < N; j++) row[j] = negate ? mirror_neg(row[N - j]) : row[N - j];
+}
 inline void stream_fence() { _mm_sfence(); }
 #else
-inline void copy_row_stream(float *dst, const float *src, int64_t n) { memcpy(dst, src, sizeof(float) * (size_t)n); }
-inline void square_rows_stream(float *dst, const float *src, int64_t n) {
-    for (int64_t i = 0; i < n; i++) dst[i] = src[i] * src[i];
+inline float mirror_neg(float x) {
+    uint32_t u;
+    memcpy(&u, &x, 4);
+    u = (u & 0x7fffffffu) > 0x7f800000u ? 0x7fffffffu : (u ^ 0x80000000u);
+    memcpy(&x, &u, 4);
+    return x;
+}
+inline void mirror_row_stream(float *row, int N, bool negate) {
+    for (int j = N / 2 + 1; j < N; j++) row[j] = negate ? mirror_neg(row[N - j]) : row[N - j];
 }
 inline void stream_fence() {}
 #endif
@@ -227,7 +268,20 @@ inline void stream_fence() {}
 // else is left.
 constexpr unsigned kDefaultHostThreads = 8;
 std::atomic<int> g_host_threads{0};  // mb_set_host_threads (0: min(kDefaultHostThreads, cores / 2))
-std::atomic<int> g_host_rows{1};     // mb_set_host_rows: 1 on (default), 0 off
+std::atomic<int> g_host_rows{-1};    // mb_set_host_rows: 1 buffer + powerSpectrum rows, 2 also the mirrored half of complexSpectrum, 0 off, -1 automatic (default)
+// Automatic: the mirrored half as well where the host has cores to spare for it -- twelve or more per visible device
+// (one B200 on a 16-core host: 2.55 vs 2.12 M frames/s end to end with the full set at bufferSize 2048; eight ranks on
+// the same host have two cores each and stay with mode 1, whose rows already load them).
+int auto_host_rows() {
+    static const int mode = []() {
+        int ndev = 0;
+        if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) ndev = 1;
+        (void)cudaGetLastError();
+        const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+        return hw / (unsigned)ndev >= 12u ? 2 : 1;
+    }();
+    return mode;
+}
 
 class HostWorkers {
 public:
@@ -251,9 +305,16 @@ public:
                 const int64_t b = std::min(g1, a + grain);
                 if (after) gated_.push_back({after, [f, a, b]() { f(a, b); }});
                 else q_.push_back([f, a, b]() { f(a, b); });
+                open_++;
             }
         }
         cv_.notify_all();
+    }
+    // Returns when every piece posted so far has run (the events they wait for must have been recorded).
+    void drain() {
+        if (threads_.empty()) return;
+        std::unique_lock<std::mutex> lk(m_);
+        idle_.wait(lk, [this]() { return open_ == 0; });
     }
 
 private:
@@ -283,13 +344,18 @@ private:
             }
             if (wait_for) (void)cudaEventSynchronize(wait_for);
             f();
+            {
+                std::lock_guard<std::mutex> lk(m_);
+                if (--open_ == 0) idle_.notify_all();
+            }
         }
     }
     std::vector<std::thread> threads_;
     std::deque<std::function<void()>> q_;
     std::deque<Gated> gated_;
     std::mutex m_;
-    std::condition_variable cv_;
+    std::condition_variable cv_, idle_;
+    int64_t open_ = 0;  // pieces posted and not yet finished
     bool done_ = false;
 };
 
@@ -950,6 +1016,7 @@ void mb_plan_destroy(mb_plan *p) {
     if (p->own_stream) cudaStreamSynchronize(p->own_stream);
     for (auto &s : p->slots) free_slot(s);
     for (cudaEvent_t ev : p->landed) cudaEventDestroy(ev);
+    for (cudaEvent_t ev : p->landed_c) cudaEventDestroy(ev);
     cudaFree(p->d_window);
     cudaFree(p->d_dct);
     cudaFree(p->d_mel_inv);
@@ -1103,6 +1170,7 @@ static mb_status extract_host(mb_plan *p, const void *samples, const int64_t *cl
         for (auto &s : p->slots) {
             if (s.stream) cudaStreamSynchronize(s.stream);
             s.small_parts.clear();  // (a failed call's staged rows are not handed out)
+            s.mir_frames = 0;
         }
         (void)cudaGetLastError();
         g_last_error = msg;
@@ -1129,7 +1197,16 @@ static mb_status extract_host_impl(mb_plan *p, const void *samples, const int64_
     // set's output bytes (8 KB of 33 KB per frame at bufferSize 2048) never crosses PCIe.
     // (measured with one and with eight devices per host, ranks or one process: on the host wins both times,
     // 2.02 vs 1.49 M and 3.33 vs 2.82 M frames/s; mb_set_host_rows(0) is for hosts short of cores)
-    const bool host_rows = g_host_rows.load() != 0;
+    const int host_rows_mode = g_host_rows.load() < 0 ? auto_host_rows() : g_host_rows.load();
+    const bool host_rows = host_rows_mode != 0;
+    // mode 2: Z[N-k] = conj(Z[k]) is mirrored by the host threads too (8 KB of the remaining 20.7 KB per frame at
+    // bufferSize 2048 stay off PCIe); not for exact-FFT plans, whose upper half is computed like the reference's
+    bool host_mirror = host_rows_mode >= 2 && mb_has(p->mask, MB_FEAT_COMPLEX_SPECTRUM) && !p->dev.exact && N >= 16;
+    if (host_mirror) {  // (the half rows leave as 2-D copies: into pageable arrays those crawl, 0.49 vs 0.57 M frames/s)
+        cudaPointerAttributes at{};
+        if (cudaPointerGetAttributes(&at, out->complex_real) != cudaSuccess || at.type != cudaMemoryTypeHost) host_mirror = false;
+        (void)cudaGetLastError();
+    }
     const bool host_buffer = host_rows && pcm_channels == 0 && mb_has(p->mask, MB_FEAT_BUFFER);
     // powerSpectrum[k] = float32(amplitudeSpectrum[k]^2) (powerSpectrum.js:1-7; one float32 multiply in every kernel):
     // where both are asked for, the host squares the amplitude rows as they land and the power rows stay off PCIe too.
@@ -1138,8 +1215,12 @@ static mb_status extract_host_impl(mb_plan *p, const void *samples, const int64_
     int64_t total_frames_call = 0;
     for (int64_t i = 0; i < n_clips; i++) total_frames_call += mb_num_frames(clip_len[i], N, hop);
     const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
-    const int want_workers = g_host_threads.load() > 0 ? g_host_threads.load() : (int)std::min(kDefaultHostThreads, std::max(1u, hw / 2));
-    const int n_workers = (host_buffer || host_power) ? (int)std::min<int64_t>(std::max<int64_t>(1, total_frames_call / 2048), want_workers) : 0;
+    // (with the mirrored rows the host threads move 20 KB per frame instead of 12: 8 / 12 / 16 threads on a 16-core host
+    // gave 2.38 / 2.56 / 2.55 M frames/s)
+    const int want_workers = g_host_threads.load() > 0 ? g_host_threads.load()
+                             : host_mirror           ? (int)std::min(12u, std::max(1u, hw * 3 / 4))
+                                                     : (int)std::min(kDefaultHostThreads, std::max(1u, hw / 2));
+    const int n_workers = (host_buffer || host_power || host_mirror) ? (int)std::min<int64_t>(std::max<int64_t>(1, total_frames_call / 2048), want_workers) : 0;
     HostWorkers workers(n_workers);  // (its destructor, on every return path, waits for the posted work: it writes into the caller's arrays)
     if (host_buffer) {
         auto fstart = std::make_shared<std::vector<int64_t>>(n_clips + 1, 0);
@@ -1166,6 +1247,44 @@ static mb_status extract_host_impl(mb_plan *p, const void *samples, const int64_
             square_rows_stream(pw + a * M, amp + a * M, (b - a) * M);
             stream_fence();
         }, landed);
+    };
+    auto post_mirror = [&](int64_t g0, int64_t g1, cudaEvent_t landed) {
+        float *re = out->complex_real, *im = out->complex_imag;
+        workers.post_range(g0, g1, 512, [=](int64_t a, int64_t b) {
+            for (int64_t g = a; g < b; g++) {
+                mirror_row_stream(re + g * N, N, false);
+                mirror_row_stream(im + g * N, N, true);
+            }
+            stream_fence();
+        }, landed);
+    };
+    // a drained slot: its staged small fields handed out; the upper halves of the frames the exact kernel redid
+    auto settle = [&](Slot &s) -> mb_status {
+        scatter_small(p, s, out);
+        if (s.mir_frames > 0 && p->adaptive) {
+            const int cnt = s.h_fix[s.mir_fix_idx];
+            if (cnt > 0) {
+                workers.drain();  // the chunk's mirrored rows are written: what follows overwrites some of them
+                const size_t up = (size_t)(N / 2 - 1) * 4, off = (size_t)(N / 2 + 1);
+                float *hre = out->complex_real + s.small_g0 * N + off, *him = out->complex_imag + s.small_g0 * N + off;
+                if ((int64_t)cnt * 8 > s.mir_frames) {
+                    MB_CUDA(cudaMemcpy2DAsync(hre, (size_t)N * 4, s.mir_d_re + off, (size_t)N * 4, up, (size_t)s.mir_frames, cudaMemcpyDeviceToHost, s.stream));
+                    MB_CUDA(cudaMemcpy2DAsync(him, (size_t)N * 4, s.mir_d_im + off, (size_t)N * 4, up, (size_t)s.mir_frames, cudaMemcpyDeviceToHost, s.stream));
+                } else {
+                    std::vector<int> list((size_t)cnt);
+                    MB_CUDA(cudaMemcpyAsync(list.data(), s.d_fix + 1, (size_t)cnt * sizeof(int), cudaMemcpyDeviceToHost, s.stream));
+                    MB_CUDA(cudaStreamSynchronize(s.stream));
+                    for (int f : list) {
+                        if (f < 0 || f >= s.mir_frames) continue;
+                        MB_CUDA(cudaMemcpyAsync(hre + (size_t)f * N, s.mir_d_re + (size_t)f * N + off, up, cudaMemcpyDeviceToHost, s.stream));
+                        MB_CUDA(cudaMemcpyAsync(him + (size_t)f * N, s.mir_d_im + (size_t)f * N + off, up, cudaMemcpyDeviceToHost, s.stream));
+                    }
+                }
+                MB_CUDA(cudaStreamSynchronize(s.stream));
+            }
+        }
+        s.mir_frames = 0;
+        return MB_OK;
     };
     const int64_t dev_bpf = p->bytes_per_frame - (host_buffer ? 4 * (int64_t)N : 0) - (host_power ? 2 * (int64_t)N : 0);  // bytes per frame the device produces
     struct VClip { int64_t off, frames; };
@@ -1202,7 +1321,8 @@ static mb_status extract_host_impl(mb_plan *p, const void *samples, const int64_
         if (!s.stream) MB_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
         // the slot's previous chunk (two chunks ago) must have drained before its buffers are reused
         MB_CUDA(cudaStreamSynchronize(s.stream));
-        scatter_small(p, s, out);  // (the other slot's copies are in flight meanwhile)
+        st = settle(s);  // (the other slot's copies are in flight meanwhile)
+        if (st != MB_OK) return st;
         const size_t span = (size_t)(hi - lo);
         if (s.samples_cap < span * frame_bytes) {
             cudaFree(s.d_samples);
@@ -1270,27 +1390,48 @@ static mb_status extract_host_impl(mb_plan *p, const void *samples, const int64_
                     s.h_fix_cap = 256;
                 }
             }
+            s.mir_fix_idx = s.h_fix_used;
             MB_CUDA(cudaMemcpyAsync(s.h_fix + s.h_fix_used++, s.d_fix, sizeof(int), cudaMemcpyDeviceToHost, s.stream));
         }
         // the amplitude rows first when the host squares them: that work then overlaps the rest of the chunk's copies
-        for (int pass = host_power ? 0 : 1; pass < 2; pass++) {
+        // (with the mirrored rows on the host too, complexSpectrum goes first -- twice the host work hangs on it -- and
+        // the amplitude rows last)
+        auto record = [&](std::vector<cudaEvent_t> &evs) -> mb_status {
+            if ((size_t)chunk_idx >= evs.size()) {  // (one event per chunk of the call: a worker may still be waiting on an earlier one)
+                cudaEvent_t ev = nullptr;
+                MB_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+                evs.push_back(ev);
+            }
+            MB_CUDA(cudaEventRecord(evs[chunk_idx], s.stream));
+            return MB_OK;
+        };
+        for (int pass = (host_power || host_mirror) ? 0 : 1; pass < 2; pass++) {
             for (int i = 0; i < kNumFields; i++) {
                 if (!mb_has(p->mask & ~drop_mask, kFields[i].feature)) continue;
                 if (kFields[i].kind != 1 && kFields[i].kind != 2) continue;  // (staged: below)
                 const bool is_amp = kFields[i].feature == MB_FEAT_AMPLITUDE_SPECTRUM;
-                if (host_power && is_amp != (pass == 0)) continue;
+                const bool first = host_mirror ? kFields[i].feature == MB_FEAT_COMPLEX_SPECTRUM : is_amp;
+                if ((host_power || host_mirror) && first != (pass == 0)) continue;
                 const size_t per = (size_t)field_elems(kFields[i], p->dev) * 4;
-                MB_CUDA(cudaMemcpyAsync((char *)field_ptr(*out, kFields[i]) + (size_t)g_done * per,
-                                        field_ptr(d_out, kFields[i]), (size_t)frames * per, cudaMemcpyDeviceToHost,
-                                        s.stream));
+                if (host_mirror && kFields[i].feature == MB_FEAT_COMPLEX_SPECTRUM)  // bins 0 .. N/2 of every row
+                    MB_CUDA(cudaMemcpy2DAsync((char *)field_ptr(*out, kFields[i]) + (size_t)g_done * per, per, field_ptr(d_out, kFields[i]),
+                                              per, (size_t)(N / 2 + 1) * 4, (size_t)frames, cudaMemcpyDeviceToHost, s.stream));
+                else
+                    MB_CUDA(cudaMemcpyAsync((char *)field_ptr(*out, kFields[i]) + (size_t)g_done * per,
+                                            field_ptr(d_out, kFields[i]), (size_t)frames * per, cudaMemcpyDeviceToHost,
+                                            s.stream));
             }
-            if (pass == 0) {  // (one event per chunk of the call: a worker may still be waiting on an earlier one)
-                if ((size_t)chunk_idx >= p->landed.size()) {
-                    cudaEvent_t ev = nullptr;
-                    MB_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-                    p->landed.push_back(ev);
-                }
-                MB_CUDA(cudaEventRecord(p->landed[chunk_idx], s.stream));
+            if (pass == 0 && host_mirror) {
+                st = record(p->landed_c);
+                if (st != MB_OK) return st;
+                post_mirror(g_done, g_done + frames, p->landed_c[chunk_idx]);
+                s.mir_frames = frames;
+                s.mir_d_re = d_out.complex_real;
+                s.mir_d_im = d_out.complex_imag;
+            }
+            if (host_power && pass == (host_mirror ? 1 : 0)) {  // (mode 2: the amplitude rows are the last big copy of the chunk)
+                st = record(p->landed);
+                if (st != MB_OK) return st;
                 post_power(g_done, g_done + frames, p->landed[chunk_idx]);
             }
         }
@@ -1301,7 +1442,8 @@ static mb_status extract_host_impl(mb_plan *p, const void *samples, const int64_
     for (int k = 0; k < 2; k++) {
         Slot &s = p->slots[k];
         if (s.stream) MB_CUDA(cudaStreamSynchronize(s.stream));
-        scatter_small(p, s, out);
+        st = settle(s);
+        if (st != MB_OK) return st;
         for (size_t i = 0; i < s.h_fix_used; i++) p->refined_frames += s.h_fix[i];
         s.h_fix_used = 0;
     }
@@ -1452,10 +1594,12 @@ mb_status mb_extract_multi(mb_plan *const *plans, int n_plans, const float *samp
 
 // ---- measured non-tensor arithmetic peaks of a device (the FP32 / FP64 roofline denominators bench.py reports against)
 mb_status mb_set_host_rows(int mode) {
-    if (mode < -1 || mode > 1) return fail(MB_ERR_INVALID_ARG, "host rows mode %d (1 on, 0 off, -1 default)", mode);
-    g_host_rows.store(mode < 0 ? 1 : mode);
+    if (mode < -1 || mode > 2) return fail(MB_ERR_INVALID_ARG, "host rows mode %d (2 all, 1 buffer + powerSpectrum, 0 off, -1 default)", mode);
+    g_host_rows.store(mode);
     return MB_OK;
 }
+
+int mb_get_host_rows(void) { return g_host_rows.load() < 0 ? auto_host_rows() : g_host_rows.load(); }
 
 mb_status mb_set_host_threads(int n) {
     if (n < 0 || n > 256) return fail(MB_ERR_INVALID_ARG, "host thread count %d out of range [0, 256]", n);

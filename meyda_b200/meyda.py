@@ -103,9 +103,16 @@ def set_host_threads(n: int) -> None:
 
 
 def set_host_rows(mode: int) -> None:
-    """1 (default; -1 restores it): host-memory extracts produce the `buffer` / powerSpectrum rows on the host while the
-    device works; 0: the device does and they are copied back (mb_set_host_rows, include/meyda_b200.h)."""
+    """1: host-memory extracts produce the `buffer` / powerSpectrum rows on the host while the device works; 2: the
+    mirrored half of complexSpectrum as well; 0: the device produces every row and all are copied back; -1 (default):
+    2 on hosts with twelve or more cores per visible device, else 1 (mb_set_host_rows, include/meyda_b200.h).  Same bits
+    in every mode."""
     _capi.check(_capi.lib().mb_set_host_rows(int(mode)))
+
+
+def get_host_rows() -> int:
+    """The host-rows mode in force (0, 1 or 2: the automatic choice resolved; mb_get_host_rows)."""
+    return int(_capi.lib().mb_get_host_rows())
 
 
 def pinned_empty(shape, dtype) -> np.ndarray:

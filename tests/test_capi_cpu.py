@@ -136,7 +136,7 @@ def test_set_host_threads_validates_its_argument():
 def test_set_host_rows_validates_its_argument():
     from meyda_b200 import _capi
     L = _capi.lib()
-    for mode in (1, 0, -1):
+    for mode in (2, 1, 0, -1):
         assert L.mb_set_host_rows(mode) == 0
-    assert L.mb_set_host_rows(2) != 0
+    assert L.mb_set_host_rows(3) != 0
     assert b"host rows mode" in L.mb_last_error()

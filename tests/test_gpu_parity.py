@@ -332,18 +332,50 @@ def test_device_memory_call_matches_host_call(golden_audio):
 
 
 def test_host_produced_rows_equal_device_produced_rows(golden_audio):
-    """`buffer` and powerSpectrum written by the host threads of a host-memory call (the default for up to two devices
-    per host) are bit for bit what the device writes (mb_set_host_rows 0)."""
-    x = golden_audio["sound1"][:120000]
+    """`buffer` and powerSpectrum written by the host threads of a host-memory call (mb_set_host_rows 1, the default),
+    and the mirrored half of complexSpectrum as well (mode 2), are bit for bit what the device writes (mode 0).  sound3
+    is tonal: many of its frames are redone by the exact kernel, whose upper half is NOT the mirror image of its lower
+    half to the last bit -- those rows must come from the device in every mode."""
     try:
-        for N, hop in ((2048, 512), (512, 512)):
-            mb.set_host_rows(1)
-            on, _ = run_gpu(x, N, hop)
-            mb.set_host_rows(0)
-            off, _ = run_gpu(x, N, hop)
-            assert set(on) == set(off)
-            for k in on:
-                assert np.array_equal(on[k], off[k], equal_nan=True), (N, k)
+        for name, N, hop in (("sound1", 2048, 512), ("sound1", 512, 512), ("sound3", 1024, 256), ("sound3", 256, 256),
+                             ("sound1", 4096, 1024)):
+            x = golden_audio[name][:120000]
+            res = {}
+            for mode in (0, 1, 2):
+                mb.set_host_rows(mode)
+                res[mode], _ = run_gpu(x, N, hop)
+            for mode in (1, 2):
+                assert set(res[mode]) == set(res[0])
+                for k in res[0]:
+                    assert np.array_equal(res[mode][k], res[0][k], equal_nan=True), (name, N, mode, k)
+    finally:
+        mb.set_host_rows(-1)
+
+
+def test_host_mirrored_rows_with_special_frames():
+    """mode 2 on frames with NaN, -0 and silence (the sign of a mirrored zero and the bits of a mirrored NaN must be the
+    device's), on plans that never refine (MB_FLAG_NO_REFINE: every row is mirrored by the host) and in every float32
+    kernel family."""
+    rng = np.random.default_rng(5)
+    GEN = _capi.MB_FLAG_GENERIC_KERNEL
+    try:
+        for N, flags in ((2048, 0), (2048, NO_REFINE), (512, NO_REFINE), (256, NO_REFINE), (2048, NO_REFINE | GEN), (4096, NO_REFINE),
+                         (32768, NO_REFINE)):
+            x = (0.3 * rng.standard_normal(N * 24)).astype(np.float32)
+            x[N * 3: N * 4] = 0.0
+            x[N * 5: N * 6] = -0.0
+            x[N * 7 + 11] = np.nan
+            x[N * 9 + 5] = -np.nan
+            res = {}
+            for mode in (0, 2):
+                mb.set_host_rows(mode)
+                plan = mb.Plan(N, N, 44100.0, "hanning", ["complexSpectrum", "amplitudeSpectrum", "rms"], device=0, flags=flags)
+                out, _ = plan.extract_host(x, np.array([0], np.int64), np.array([len(x)], np.int64))
+                plan.close()
+                res[mode] = out
+            for k in res[0]:
+                a, b = np.asarray(res[0][k]), np.asarray(res[2][k])
+                assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), (N, flags, k, np.argwhere(a.view(np.uint32) != b.view(np.uint32))[:4])
     finally:
         mb.set_host_rows(-1)
 
