@@ -590,7 +590,11 @@ def main():
                 "roofline": {"bound": "fp32", "achieved": per_gpu * fl / 1e12, "peak": ffma, "unit": "TFLOP/s",
                              "frac": per_gpu * fl / 1e12 / ffma, "flops_per_frame": fl,
                              "peak_source": "FFMA micro-kernel run in this process (mb_measure_peaks)",
-                             "hbm_frac": per_gpu * bpf2 / 1e9 / peak, "algorithmic_bytes_per_frame": bpf2},
+                             "hbm_frac": per_gpu * bpf2 / 1e9 / peak, "algorithmic_bytes_per_frame": bpf2,
+                             # what the committed ncu capture of this kernel shows to be busiest (not measured in this run)
+                             "limiter_ncu": ("L1 / shared-memory data pipe 78 % busy (810 wavefronts per frame), issue slots 58 %: profiles/r02_ncu_c3.txt"
+                                             if n2 == 2048 else
+                                             "one CTA of 16 warps per SM, ~14 block barriers per frame; issue slots 43 %, no pipe above 45 %: profiles/r02_ncu_big32768.txt")},
                 "clocks": r2["clocks"], "parity": note2})
             r2["plan"].close()
             del r2
