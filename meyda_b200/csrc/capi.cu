@@ -118,7 +118,19 @@ struct Slot {  // one pipeline stage of a host-memory extract
     // mb_set_host_rows(2): the pending chunk whose complexSpectrum upper halves the host threads mirror; the frames the
     // exact kernel redid (not conjugate-symmetric to the last bit, like the reference's) get theirs from the device
     int64_t mir_frames = 0;
-    size_t mir_fix_idx = 0;                       // this chunk's entry of h_fix
+    const int *mir_list = nullptr;                // this chunk's copy of d_fix: [0] how many frames were redone, [1 ..] which
+    // the redone frames' upper halves, gathered on the device ([i][re | im][N/2 - 1], in list order), copied as one
+    // piece when the slot drains and handed out at its next drain
+    // (two areas, used in turn: the copy of one chunk's rows runs on the plan's auxiliary stream -- on the slot's own
+    // stream it would hold the next chunk's kernels back behind the other slot's copies -- while the next chunk's
+    // rows are gathered into the other)
+    float *d_gather[2] = {nullptr, nullptr}, *h_gather[2] = {nullptr, nullptr};
+    size_t gather_cap = 0;                        // frames
+    int gat_t = 0;                                // the area the slot's current chunk gathers into
+    cudaEvent_t gat_ev = nullptr;                 // the pending copy has arrived
+    const int *gat_list = nullptr;                // pending hand-out: list, how many, first frame of the chunk, area
+    int gat_cnt = 0, gat_from = 0;
+    int64_t gat_g0 = 0;
     const float *mir_d_re = nullptr, *mir_d_im = nullptr;
 };
 
@@ -153,6 +165,9 @@ struct mb_plan {
     Slot slots[2];
     std::vector<cudaEvent_t> landed;  // host-memory calls: chunk i's amplitude rows have arrived (kept across calls)
     std::vector<cudaEvent_t> landed_c;  // ... chunk i's complexSpectrum lower halves have arrived (mb_set_host_rows(2))
+    cudaStream_t aux_stream = nullptr;  // host-memory calls: the redone frames' gathered upper halves travel on it
+    int *h_fixlist = nullptr;           // pinned: every chunk's list of redone frames, one region per chunk of the call
+    size_t fixlist_cap = 0;             // ints
     // adaptive exactness (mb_adaptive.cuh): frames the float32 kernels flag are redone by the exact-FFT kernel
     bool adaptive = false;
     MbDevPlan dev_fix{};       // the plan as the exact kernel sees it: spectral features only
@@ -305,16 +320,9 @@ public:
                 const int64_t b = std::min(g1, a + grain);
                 if (after) gated_.push_back({after, [f, a, b]() { f(a, b); }});
                 else q_.push_back([f, a, b]() { f(a, b); });
-                open_++;
             }
         }
         cv_.notify_all();
-    }
-    // Returns when every piece posted so far has run (the events they wait for must have been recorded).
-    void drain() {
-        if (threads_.empty()) return;
-        std::unique_lock<std::mutex> lk(m_);
-        idle_.wait(lk, [this]() { return open_ == 0; });
     }
 
 private:
@@ -344,18 +352,13 @@ private:
             }
             if (wait_for) (void)cudaEventSynchronize(wait_for);
             f();
-            {
-                std::lock_guard<std::mutex> lk(m_);
-                if (--open_ == 0) idle_.notify_all();
-            }
         }
     }
     std::vector<std::thread> threads_;
     std::deque<std::function<void()>> q_;
     std::deque<Gated> gated_;
     std::mutex m_;
-    std::condition_variable cv_, idle_;
-    int64_t open_ = 0;  // pieces posted and not yet finished
+    std::condition_variable cv_;
     bool done_ = false;
 };
 
@@ -441,6 +444,11 @@ void free_slot(Slot &s) {
     cudaFree(s.d_fix);
     if (s.h_fix) cudaFreeHost(s.h_fix);
     if (s.h_small) cudaFreeHost(s.h_small);
+    for (int t = 0; t < 2; t++) {
+        if (s.h_gather[t]) cudaFreeHost(s.h_gather[t]);
+        cudaFree(s.d_gather[t]);
+    }
+    if (s.gat_ev) cudaEventDestroy(s.gat_ev);
     cudaFree(s.d_samples);
     cudaFree(s.d_out);
     cudaFree(s.d_tab);
@@ -1017,6 +1025,8 @@ void mb_plan_destroy(mb_plan *p) {
     for (auto &s : p->slots) free_slot(s);
     for (cudaEvent_t ev : p->landed) cudaEventDestroy(ev);
     for (cudaEvent_t ev : p->landed_c) cudaEventDestroy(ev);
+    if (p->h_fixlist) cudaFreeHost(p->h_fixlist);
+    if (p->aux_stream) cudaStreamDestroy(p->aux_stream);
     cudaFree(p->d_window);
     cudaFree(p->d_dct);
     cudaFree(p->d_mel_inv);
@@ -1149,6 +1159,20 @@ mb_status mb_plan_synchronize(mb_plan *p) {
 // `samples` is float32 (pcm_channels == 0) or interleaved int16 PCM; offsets count sample frames either way.
 static mb_status extract_host_impl(mb_plan *p, const void *samples, const int64_t *clip_offset, const int64_t *clip_len,
                                    int64_t n_clips, const mb_outputs *out, int pcm_channels, int pcm_channel, int pcm_format);
+// Block b < fix[0] (and < cap) packs bins N/2+1 .. N-1 of both complexSpectrum rows of frame fix[1 + b] into dst[b].
+__global__ void mb_gather_upper_kernel(const int *__restrict__ fix, int cap, const float *__restrict__ re,
+                                       const float *__restrict__ im, int N, float *__restrict__ dst) {
+    const int b = blockIdx.x, cnt = min(fix[0], cap);
+    if (b >= cnt) return;
+    const int up = N / 2 - 1;
+    const size_t row = (size_t)fix[1 + b] * N + N / 2 + 1;
+    float *d = dst + (size_t)b * 2 * up;
+    for (int i = threadIdx.x; i < up; i += blockDim.x) {
+        d[i] = re[row + i];
+        d[up + i] = im[row + i];
+    }
+}
+
 // the staged small fields of the slot's last chunk into the caller's arrays (the slot's stream has been synchronized)
 static void scatter_small(mb_plan *p, Slot &s, const mb_outputs *out) {
     for (const Slot::SmallPart &sp : s.small_parts) {
@@ -1167,10 +1191,13 @@ static mb_status extract_host(mb_plan *p, const void *samples, const int64_t *cl
     if (st != MB_OK) {
         // copies of earlier chunks may still be writing into the caller's arrays: drain before reporting the failure
         const std::string msg = g_last_error;
+        if (p->aux_stream) cudaStreamSynchronize(p->aux_stream);
         for (auto &s : p->slots) {
             if (s.stream) cudaStreamSynchronize(s.stream);
             s.small_parts.clear();  // (a failed call's staged rows are not handed out)
             s.mir_frames = 0;
+            s.mir_list = nullptr;
+            s.gat_cnt = 0;
         }
         (void)cudaGetLastError();
         g_last_error = msg;
@@ -1248,44 +1275,83 @@ static mb_status extract_host_impl(mb_plan *p, const void *samples, const int64_
             stream_fence();
         }, landed);
     };
-    auto post_mirror = [&](int64_t g0, int64_t g1, cudaEvent_t landed) {
+    // `list` (the chunk's copy of d_fix, landed before `landed`): the frames the exact kernel redid are left alone --
+    // their upper halves come from the device (settle)
+    auto post_mirror = [&](int64_t g0, int64_t g1, cudaEvent_t landed, const int *list) {
         float *re = out->complex_real, *im = out->complex_imag;
         workers.post_range(g0, g1, 512, [=](int64_t a, int64_t b) {
+            std::vector<char> skip;
+            if (list && list[0] > 0) {
+                skip.assign((size_t)(b - a), 0);
+                const int cnt = (int)std::min<int64_t>(list[0], g1 - g0);
+                for (int i = 1; i <= cnt; i++) {
+                    const int64_t g = g0 + list[i];
+                    if (g >= a && g < b) skip[(size_t)(g - a)] = 1;
+                }
+            }
             for (int64_t g = a; g < b; g++) {
+                if (!skip.empty() && skip[(size_t)(g - a)]) continue;
                 mirror_row_stream(re + g * N, N, false);
                 mirror_row_stream(im + g * N, N, true);
             }
             stream_fence();
         }, landed);
     };
-    // a drained slot: its staged small fields handed out; the upper halves of the frames the exact kernel redid
+    // a drained slot: its staged small fields handed out; the upper halves of the frames the exact kernel redid --
+    // gathered on the device behind the kernels -- are copied as one piece, queued on the slot's stream (asynchronous:
+    // the slot's next kernels follow in stream order), and handed out at the slot's next drain
+    auto hand_out = [&](Slot &s) {
+        if (s.gat_cnt == 0) return;
+        (void)cudaEventSynchronize(s.gat_ev);
+        const size_t up = (size_t)(N / 2 - 1), off = (size_t)(N / 2 + 1);
+        const float *src = s.h_gather[s.gat_from];
+        for (int i = 0; i < s.gat_cnt; i++) {
+            const int f = s.gat_list[1 + i];
+            if (f < 0) continue;
+            memcpy(out->complex_real + (s.gat_g0 + f) * N + off, src + (size_t)i * 2 * up, up * 4);
+            memcpy(out->complex_imag + (s.gat_g0 + f) * N + off, src + (size_t)i * 2 * up + up, up * 4);
+        }
+        s.gat_cnt = 0;
+    };
     auto settle = [&](Slot &s) -> mb_status {
         scatter_small(p, s, out);
-        if (s.mir_frames > 0 && p->adaptive) {
-            const int cnt = s.h_fix[s.mir_fix_idx];
+        hand_out(s);
+        if (s.mir_frames > 0 && s.mir_list) {
+            const int cnt = (int)std::min<int64_t>(s.mir_list[0], s.mir_frames);
             if (cnt > 0) {
-                workers.drain();  // the chunk's mirrored rows are written: what follows overwrites some of them
                 const size_t up = (size_t)(N / 2 - 1) * 4, off = (size_t)(N / 2 + 1);
-                float *hre = out->complex_real + s.small_g0 * N + off, *him = out->complex_imag + s.small_g0 * N + off;
-                if ((int64_t)cnt * 8 > s.mir_frames) {
+                if ((size_t)cnt > s.gather_cap) {
+                    // tonal material, redone almost entirely: every upper half of the chunk from the device (the rows the
+                    // host threads mirrored meanwhile hold the same bits), and the chunks that follow copy whole rows
+                    host_mirror = false;
+                    float *hre = out->complex_real + s.small_g0 * N + off, *him = out->complex_imag + s.small_g0 * N + off;
                     MB_CUDA(cudaMemcpy2DAsync(hre, (size_t)N * 4, s.mir_d_re + off, (size_t)N * 4, up, (size_t)s.mir_frames, cudaMemcpyDeviceToHost, s.stream));
                     MB_CUDA(cudaMemcpy2DAsync(him, (size_t)N * 4, s.mir_d_im + off, (size_t)N * 4, up, (size_t)s.mir_frames, cudaMemcpyDeviceToHost, s.stream));
                 } else {
-                    std::vector<int> list((size_t)cnt);
-                    MB_CUDA(cudaMemcpyAsync(list.data(), s.d_fix + 1, (size_t)cnt * sizeof(int), cudaMemcpyDeviceToHost, s.stream));
-                    MB_CUDA(cudaStreamSynchronize(s.stream));
-                    for (int f : list) {
-                        if (f < 0 || f >= s.mir_frames) continue;
-                        MB_CUDA(cudaMemcpyAsync(hre + (size_t)f * N, s.mir_d_re + (size_t)f * N + off, up, cudaMemcpyDeviceToHost, s.stream));
-                        MB_CUDA(cudaMemcpyAsync(him + (size_t)f * N, s.mir_d_im + (size_t)f * N + off, up, cudaMemcpyDeviceToHost, s.stream));
-                    }
+                    // (the gather kernel has finished: the slot's stream was synchronized before this call)
+                    MB_CUDA(cudaMemcpyAsync(s.h_gather[s.gat_t], s.d_gather[s.gat_t], (size_t)cnt * 2 * up, cudaMemcpyDeviceToHost, p->aux_stream));
+                    MB_CUDA(cudaEventRecord(s.gat_ev, p->aux_stream));
+                    s.gat_list = s.mir_list;
+                    s.gat_cnt = cnt;
+                    s.gat_from = s.gat_t;
+                    s.gat_g0 = s.small_g0;
                 }
-                MB_CUDA(cudaStreamSynchronize(s.stream));
             }
         }
         s.mir_frames = 0;
+        s.mir_list = nullptr;
         return MB_OK;
     };
+    if (host_mirror && p->adaptive) {
+        const size_t need = 2 * (size_t)total_frames_call + 16;  // every chunk: its frames + 1
+        if (p->fixlist_cap < need) {
+            if (p->h_fixlist) cudaFreeHost(p->h_fixlist);
+            p->h_fixlist = nullptr;
+            p->fixlist_cap = 0;
+            MB_CUDA(cudaMallocHost((void **)&p->h_fixlist, need * sizeof(int)));
+            p->fixlist_cap = need;
+        }
+    }
     const int64_t dev_bpf = p->bytes_per_frame - (host_buffer ? 4 * (int64_t)N : 0) - (host_power ? 2 * (int64_t)N : 0);  // bytes per frame the device produces
     struct VClip { int64_t off, frames; };
     std::vector<VClip> v;
@@ -1390,8 +1456,35 @@ static mb_status extract_host_impl(mb_plan *p, const void *samples, const int64_
                     s.h_fix_cap = 256;
                 }
             }
-            s.mir_fix_idx = s.h_fix_used;
             MB_CUDA(cudaMemcpyAsync(s.h_fix + s.h_fix_used++, s.d_fix, sizeof(int), cudaMemcpyDeviceToHost, s.stream));
+        }
+        // which frames the exact kernel redid, ahead of the rows (mode 2: the host threads leave those frames alone)
+        const int *chunk_list = nullptr;
+        if (host_mirror && p->adaptive && s.d_fix) {
+            int *dst = p->h_fixlist + g_done + chunk_idx;  // (regions of frames + 1 ints, one after the other)
+            MB_CUDA(cudaMemcpyAsync(dst, s.d_fix, (size_t)(frames + 1) * sizeof(int), cudaMemcpyDeviceToHost, s.stream));
+            chunk_list = dst;
+            // the redone frames' upper halves, packed (up to an eighth of the chunk: beyond that whole rows are copied)
+            const size_t gcap = (size_t)std::max<int64_t>(8, frames / 8), gbytes = gcap * 2 * (size_t)(N / 2 - 1) * 4;
+            if (!p->aux_stream) MB_CUDA(cudaStreamCreateWithFlags(&p->aux_stream, cudaStreamNonBlocking));
+            if (!s.gat_ev) MB_CUDA(cudaEventCreateWithFlags(&s.gat_ev, cudaEventDisableTiming));
+            if (s.gather_cap < gcap) {
+                hand_out(s);  // (a copy into the old area may still be pending: finish and hand it out first)
+                for (int t = 0; t < 2; t++) {
+                    cudaFree(s.d_gather[t]);
+                    if (s.h_gather[t]) cudaFreeHost(s.h_gather[t]);
+                    s.d_gather[t] = s.h_gather[t] = nullptr;
+                }
+                s.gather_cap = 0;
+                for (int t = 0; t < 2; t++) {
+                    MB_CUDA(cudaMalloc((void **)&s.d_gather[t], gbytes));
+                    MB_CUDA(cudaMallocHost((void **)&s.h_gather[t], gbytes));
+                }
+                s.gather_cap = gcap;
+            }
+            s.gat_t ^= 1;
+            mb_gather_upper_kernel<<<(unsigned)s.gather_cap, 128, 0, s.stream>>>(s.d_fix, (int)s.gather_cap, d_out.complex_real, d_out.complex_imag, N, s.d_gather[s.gat_t]);
+            MB_CUDA(cudaGetLastError());
         }
         // the amplitude rows first when the host squares them: that work then overlaps the rest of the chunk's copies
         // (with the mirrored rows on the host too, complexSpectrum goes first -- twice the host work hangs on it -- and
@@ -1424,7 +1517,8 @@ static mb_status extract_host_impl(mb_plan *p, const void *samples, const int64_
             if (pass == 0 && host_mirror) {
                 st = record(p->landed_c);
                 if (st != MB_OK) return st;
-                post_mirror(g_done, g_done + frames, p->landed_c[chunk_idx]);
+                post_mirror(g_done, g_done + frames, p->landed_c[chunk_idx], chunk_list);
+                s.mir_list = chunk_list;
                 s.mir_frames = frames;
                 s.mir_d_re = d_out.complex_real;
                 s.mir_d_im = d_out.complex_imag;
@@ -1442,8 +1536,13 @@ static mb_status extract_host_impl(mb_plan *p, const void *samples, const int64_
     for (int k = 0; k < 2; k++) {
         Slot &s = p->slots[k];
         if (s.stream) MB_CUDA(cudaStreamSynchronize(s.stream));
+        const bool more = s.mir_frames > 0 && s.mir_list && s.mir_list[0] > 0;
         st = settle(s);
         if (st != MB_OK) return st;
+        if (more) {  // (the redone frames' upper halves, queued by settle)
+            MB_CUDA(cudaStreamSynchronize(s.stream));
+            hand_out(s);
+        }
         for (size_t i = 0; i < s.h_fix_used; i++) p->refined_frames += s.h_fix[i];
         s.h_fix_used = 0;
     }

@@ -380,6 +380,30 @@ def test_host_mirrored_rows_with_special_frames():
         mb.set_host_rows(-1)
 
 
+def test_host_mirrored_rows_over_several_chunks():
+    """mode 2 on a call of several pipeline chunks whose frames are partly redone by the exact kernel (white noise: a few
+    per cent): every chunk's redone rows come from the device, the others from the host threads -- same bits as mode 0."""
+    rng = np.random.default_rng(11)
+    clips = [(0.3 * rng.standard_normal(441000)).astype(np.float32) for _ in range(6)]
+    data, off, ln = mb.meyda._normalize_clips(clips)
+    feats = mb.FEATURES
+    res, refined = {}, {}
+    try:
+        for mode in (0, 2):
+            mb.set_host_rows(mode)
+            plan = mb.Plan(2048, 512, SR, "hanning", feats, device=0)
+            res[mode], _ = plan.extract_host(data, off, ln)
+            refined[mode] = plan.refined_frames
+            plan.close()
+    finally:
+        mb.set_host_rows(-1)
+    assert refined[0] == refined[2] and refined[0] > 0
+    assert len(res[0]["complex_real"]) * (33 << 10) > (128 << 20)  # more than two 64 MiB chunks
+    for k in res[0]:
+        a, b = np.asarray(res[0][k]), np.asarray(res[2][k])
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), (k, np.argwhere(a.view(np.uint32) != b.view(np.uint32))[:4])
+
+
 def test_clip_sharding_is_bit_identical():
     """mb_extract_multi over two plans on the same device == single call."""
     clips = [mo.synth_clip(40 + i, 3000 + 977 * i) for i in range(9)]
