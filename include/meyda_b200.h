@@ -300,7 +300,9 @@ mb_status mb_set_host_threads(int n);
  *      one device on a 16-core host): the rows of frames that the exact-FFT kernel redid (whose upper half is computed,
  *      as the reference's is) still come from the device, exact-FFT plans and pageable output arrays copy everything;
  *   0  nothing: the device produces every row and all are copied back (hosts short of cores);
- *  -1  (the default) 2 where the host has twelve or more cores per visible device, else 1.
+ *  -1  (the default) 2 where one device is visible and the host has twelve or more cores, else 1: mode 2 loads the
+ *      host's memory system, which several devices on one host already saturate in mode 1 (two B200s: 3.84 M frames/s
+ *      in mode 1, 2.80 M in mode 2).
  * The results are bit-identical in every mode.  Process-wide. */
 mb_status mb_set_host_rows(int mode);
 /* The mode in force: 0, 1 or 2 (the automatic choice resolved). */

@@ -235,7 +235,7 @@ class Meyda {
 // Host threads a host-memory extract uses for the rows the device does not produce (`buffer`, powerSpectrum); 0 = automatic.
 function setHostThreads(n) { native.setHostThreads(n | 0) }
 // 2 / 1 / 0: those rows and the mirrored half of complexSpectrum, those rows only, or nothing on the host (the device
-// produces the rest and it is copied back); -1 (default): 2 with twelve or more cores per visible device, else 1.
+// produces the rest and it is copied back); -1 (default): 2 with one visible device and twelve or more cores, else 1.
 function setHostRows(mode) { native.setHostRows(mode | 0) }
 
 module.exports = {Meyda, extract, extractAsync, extractWav, clearPlans, setHostThreads, setHostRows, featureInfo, isPowerOfTwo, FEATURES}

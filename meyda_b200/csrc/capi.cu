@@ -284,16 +284,18 @@ inline void stream_fence() {}
 constexpr unsigned kDefaultHostThreads = 8;
 std::atomic<int> g_host_threads{0};  // mb_set_host_threads (0: min(kDefaultHostThreads, cores / 2))
 std::atomic<int> g_host_rows{-1};    // mb_set_host_rows: 1 buffer + powerSpectrum rows, 2 also the mirrored half of complexSpectrum, 0 off, -1 automatic (default)
-// Automatic: the mirrored half as well where the host has cores to spare for it -- twelve or more per visible device
-// (one B200 on a 16-core host: 2.55 vs 2.12 M frames/s end to end with the full set at bufferSize 2048; eight ranks on
-// the same host have two cores each and stay with mode 1, whose rows already load them).
+// Automatic: the mirrored half as well where ONE device is visible and the host has twelve or more cores (one B200 on a
+// 16-core host: 2.55 vs 2.12 M frames/s end to end with the full set at bufferSize 2048).  Mode 2 trades PCIe bytes for
+// host memory traffic (54.7 against 46.7 KB per frame) and runs into the host's memory system at ~2.6 M frames/s however
+// many devices share it: two B200s on one host reach 3.84 M in mode 1 and 2.80 M in mode 2, so hosts with several
+// devices stay with mode 1.
 int auto_host_rows() {
     static const int mode = []() {
         int ndev = 0;
         if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) ndev = 1;
         (void)cudaGetLastError();
         const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
-        return hw / (unsigned)ndev >= 12u ? 2 : 1;
+        return (ndev == 1 && hw >= 12u) ? 2 : 1;
     }();
     return mode;
 }

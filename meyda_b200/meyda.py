@@ -105,8 +105,8 @@ def set_host_threads(n: int) -> None:
 def set_host_rows(mode: int) -> None:
     """1: host-memory extracts produce the `buffer` / powerSpectrum rows on the host while the device works; 2: the
     mirrored half of complexSpectrum as well; 0: the device produces every row and all are copied back; -1 (default):
-    2 on hosts with twelve or more cores per visible device, else 1 (mb_set_host_rows, include/meyda_b200.h).  Same bits
-    in every mode."""
+    2 where one device is visible and the host has twelve or more cores, else 1 (mb_set_host_rows,
+    include/meyda_b200.h).  Same bits in every mode."""
     _capi.check(_capi.lib().mb_set_host_rows(int(mode)))
 
 
