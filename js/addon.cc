@@ -385,7 +385,7 @@ static napi_value SetHostThreads(napi_env env, napi_callback_info info) {
     return NULL;
 }
 
-// setHostRows(mode): 1 (default) / 0 -- the `buffer` and powerSpectrum rows of a host-memory call on the host, or on the device
+// setHostRows(mode): which rows of a host-memory call the host threads produce (2 / 1 / 0, -1: automatic; mb_set_host_rows)
 static napi_value SetHostRows(napi_env env, napi_callback_info info) {
     size_t argc = 1;
     napi_value argv[1];
@@ -395,6 +395,13 @@ static napi_value SetHostRows(napi_env env, napi_callback_info info) {
     const mb_status st = mb_set_host_rows(mode);
     if (st != MB_OK) return throw_mb(env, st);
     return NULL;
+}
+
+// getHostRows() -> 0 | 1 | 2: the mode in force (the automatic choice resolved)
+static napi_value GetHostRows(napi_env env, napi_callback_info) {
+    napi_value v;
+    NAPI_OK_OR_THROW(env, napi_create_int32(env, mb_get_host_rows(), &v));
+    return v;
 }
 
 // ---- streaming, the reference's actual usage model: one buffer per onaudioprocess event (src/meyda.js:69-91)
@@ -481,6 +488,7 @@ static napi_value Init(napi_env env, napi_value exports) {
         {"refinedFrames", NULL, RefinedFrames, NULL, NULL, NULL, napi_default, NULL},
         {"setHostThreads", NULL, SetHostThreads, NULL, NULL, NULL, napi_default, NULL},
         {"setHostRows", NULL, SetHostRows, NULL, NULL, NULL, napi_default, NULL},
+        {"getHostRows", NULL, GetHostRows, NULL, NULL, NULL, napi_default, NULL},
         {"createStream", NULL, CreateStream, NULL, NULL, NULL, napi_default, NULL},
         {"streamPush", NULL, StreamPush, NULL, NULL, NULL, napi_default, NULL},
         {"streamReset", NULL, StreamReset, NULL, NULL, NULL, napi_default, NULL},

@@ -237,5 +237,6 @@ function setHostThreads(n) { native.setHostThreads(n | 0) }
 // 2 / 1 / 0: those rows and the mirrored half of complexSpectrum, those rows only, or nothing on the host (the device
 // produces the rest and it is copied back); -1 (default): 2 with one visible device and twelve or more cores, else 1.
 function setHostRows(mode) { native.setHostRows(mode | 0) }
+function getHostRows() { return native.getHostRows() }
 
-module.exports = {Meyda, extract, extractAsync, extractWav, clearPlans, setHostThreads, setHostRows, featureInfo, isPowerOfTwo, FEATURES}
+module.exports = {Meyda, extract, extractAsync, extractWav, clearPlans, setHostThreads, setHostRows, getHostRows, featureInfo, isPowerOfTwo, FEATURES}
