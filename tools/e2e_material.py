@@ -10,7 +10,8 @@ noise = (0.3 * rng.standard_normal(n)).astype(np.float32)
 for name, sig in (("tone", tone), ("noise", noise)):
     x = torch.empty(clips, n, dtype=torch.float32, pin_memory=True); x.copy_(torch.from_numpy(np.tile(sig, (clips, 1))))
     hx = x.numpy().reshape(-1); off = np.arange(clips, dtype=np.int64) * n; ln = np.full(clips, n, np.int64)
-    for mode in (1, 2, 1, 2):
+    import os
+    for mode in [int(m) for m in os.environ.get("MODES", "1,2,1,2").split(",")]:
         mb.set_host_rows(mode)
         plan = mb.Plan(2048, 512, 44100.0, "hanning", mb.FEATURES, device=0)
         nf = clips * ((n - 2048) // 512 + 1)
